@@ -1,0 +1,112 @@
+/*
+ * opd_b200.h — C ABI of libopd_b200.so, the B200 (sm_100a) implementation of the
+ * Phase 2 -> 3 hot path of Kizuna42/office-person-detection-vit.
+ *
+ * The reference is 100 % Python and has no FFI of its own; these
+ * entry points are what a ctypes binding inside the reference's three engine
+ * classes would call.  Each declaration cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative opd_status on error;
+ *     opd_last_error() returns a thread-local, human readable message;
+ *   - no C++ exception crosses the ABI, no torch type appears in a signature;
+ *   - all pointers named *_dev are device pointers owned by the caller, all
+ *     other pointers are host pointers that are only read during the call;
+ *   - work is enqueued on the caller's stream (`stream` is a cudaStream_t passed
+ *     as void*); no hidden synchronisation except where stated;
+ *   - handles are bound to one device, are not thread-safe, and own only their
+ *     own packed tables / weights.
+ */
+#ifndef OPD_B200_H
+#define OPD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPD_ABI_VERSION 1
+
+typedef enum opd_status {
+  OPD_OK = 0,
+  OPD_ERR_INVALID = -1,     /* bad argument (shape, NULL, range) */
+  OPD_ERR_CUDA = -2,        /* CUDA runtime / driver error, see opd_last_error() */
+  OPD_ERR_UNSUPPORTED = -3, /* valid request outside the implemented envelope */
+  OPD_ERR_NOMEM = -4
+} opd_status;
+
+int opd_version(void);
+const char* opd_last_error(void);
+/* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
+int64_t opd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Floor projection + zone classification + counting  (K9 + K10 + K11)
+ * replaces: src/transform/homography.py:150-197 (transform_batch), :105-133 (transform_pixel)
+ *           src/zone/zone_classifier.py:114-149 (classify), :162-197 (_point_in_polygon)
+ *           src/aggregation/aggregator.py:52-75 (get_zone_counts)
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct opd_zone_table opd_zone_table;
+
+#define OPD_MAX_ZONES 64
+
+/* Build the device-side zone table (polygons + uniform-grid accelerator).
+ *   verts_xy      [poly_offsets[Z], 2] f64 polygon vertices, zones in declaration order
+ *   poly_offsets  [Z+1] first vertex of every polygon (each polygon >= 3 vertices)
+ *   priority      [Z] f64, +inf encodes the reference's `priority is None`
+ *                 (zone_classifier.py:139-145: key = (priority or +inf, declaration order))
+ *   allow_overlap 0: single label = argmin (priority, order); 1: all containing zones
+ * Z may be 0 (every point is unclassified).  Z <= OPD_MAX_ZONES.  Synchronous. */
+int opd_zone_table_create(const double* verts_xy, const int32_t* poly_offsets, const double* priority,
+                          int32_t Z, int32_t allow_overlap, int32_t device, opd_zone_table** out);
+void opd_zone_table_destroy(opd_zone_table* zt);
+/* Introspection for tests / DESIGN.md: grid size and how many cells need the exact test. */
+int opd_zone_table_info(const opd_zone_table* zt, int32_t* grid_w, int32_t* grid_h, int32_t* n_boundary_cells,
+                        int32_t* n_classes);
+
+typedef struct opd_floor_params {
+  double H[9];          /* row-major 3x3 homography, camera px -> floormap px (homography.py:47-91) */
+  double scale_x_mm;    /* FloorMapConfig.scale_x_mm_per_px (floormap_config.py:13-31) */
+  double scale_y_mm;
+  double map_w_px;      /* FloorMapConfig.width_px / height_px — only for the in-bounds flag */
+  double map_h_px;
+  int32_t input_is_bbox;/* 0: input rows are points (x, y); 1: rows are boxes (x, y, w, h) and the
+                           foot point (x + w/2, y + h) is projected (homography.py:166-169) */
+  int32_t skip_projection; /* 1: input rows already are floor px (ZoneClassifier.classify on its own) */
+} opd_floor_params;
+
+/* Fused projection + classification + histogram over N rows.  Any output pointer may be NULL.
+ *   in_dev        [N,2] or [N,4], f32 (…_f32) or f64 (…_f64)
+ *   slot_dev      [N] int32 histogram row (timestamp slot) of each point, or NULL = row 0
+ *   floor_px_dev  [N,2], floor_mm_dev [N,2]   same dtype as the input
+ *   in_bounds_dev [N] u8   0 <= px < map_w && 0 <= py < map_h (homography.py:181)
+ *   zone_idx_dev  [N] int32 zone index in declaration order, -1 = no zone (allow_overlap = 0 tables;
+ *                 with allow_overlap = 1 it receives the highest-priority containing zone)
+ *   zone_mask_dev [N] u64  bit z set <=> point inside zone z (declaration order)
+ *   hist_dev      [T, Z+1] int32, ACCUMULATED (caller zeroes); column Z = "unclassified"
+ *                 (aggregator.py:64-75: one count per containing zone, or one "unclassified")
+ * The f64 entry follows the reference's float64 arithmetic operation by operation; the f32 entry reads
+ * and writes float32 but still projects and classifies in float64, so zone results are identical. */
+int opd_floor_project_classify_count_f32(const opd_floor_params* p, const opd_zone_table* zt,
+                                         const float* in_dev, const int32_t* slot_dev, int64_t N, int32_t T,
+                                         float* floor_px_dev, float* floor_mm_dev, uint8_t* in_bounds_dev,
+                                         int32_t* zone_idx_dev, uint64_t* zone_mask_dev, int32_t* hist_dev,
+                                         void* stream);
+int opd_floor_project_classify_count_f64(const opd_floor_params* p, const opd_zone_table* zt,
+                                         const double* in_dev, const int32_t* slot_dev, int64_t N, int32_t T,
+                                         double* floor_px_dev, double* floor_mm_dev, uint8_t* in_bounds_dev,
+                                         int32_t* zone_idx_dev, uint64_t* zone_mask_dev, int32_t* hist_dev,
+                                         void* stream);
+
+/* Histogram only: Aggregator.get_zone_counts on already classified points (aggregator.py:52-75).
+ * Exactly one of zone_idx_dev / zone_mask_dev is non-NULL. */
+int opd_zone_histogram(const int32_t* zone_idx_dev, const uint64_t* zone_mask_dev, const int32_t* slot_dev,
+                       int64_t N, int32_t Z, int32_t T, int32_t* hist_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPD_B200_H */

@@ -1,0 +1,847 @@
+// K9 + K10 + K11: foot-point homography, polygon zone classification and per-timestamp zone counting,
+// fused into one pass over the points.
+//
+// Replaces (reference, pure Python / NumPy float64):
+//   src/transform/homography.py:150-197   transform_batch  (foot point, H·p, perspective divide, mm, bounds)
+//   src/zone/zone_classifier.py:114-197   classify + _point_in_polygon (ray casting, priority pick)
+//   src/aggregation/aggregator.py:52-75   get_zone_counts  (histogram with an "unclassified" bin)
+//
+// Design: the polygons are rasterised ON THE HOST, in float64, into a uniform grid of
+// one byte per cell.  A cell whose Δ-dilated box is crossed by no polygon edge has a single answer for every
+// point in it ("uniform" cell: the byte is the class id); the other cells are "boundary" cells (byte 255) and
+// carry the list of polygons that must be tested exactly.  The exact test is the reference's ray casting,
+// operation by operation, in float64.  Two kernels use the table:
+//   floor_exact_kernel  — float64 arithmetic throughout, every output, any histogram shape;
+//   floor_fast_kernel   — the HBM-roofline path: float32 projection with a rigorous per-point error bound
+//                         as a *filter*; a point is answered from the grid only when bound <= Δ/2 and its
+//                         cell is uniform, otherwise its index goes to a shared-memory queue that the CTA
+//                         drains densely through the float64 exact path.  Counting uses warp ballots
+//                         (no per-point atomics).  Results are identical to floor_exact_kernel.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "opd_common.h"
+
+namespace {
+
+constexpr int kBoundary = 255;          // grid byte of a boundary cell
+constexpr int kMaxClasses = 255;        // class ids 0..254
+constexpr int kGridCellBudget = 160 * 1024;
+constexpr int kMaxSmemVerts = 1024;     // polygons vertices staged in shared memory (16 KB)
+constexpr int kQueueCap = 8192;         // slow-path queue entries of the fast kernel
+constexpr int kFastThreads = 1024;
+constexpr int kFastPointsPerThread = 4;
+constexpr int kFastChunk = kFastThreads * kFastPointsPerThread;
+
+// ---------------------------------------------------------------------------------------------------------
+// The reference's ray casting (zone_classifier.py:162-197), float64, same operations in the same order.
+// Rounding of every operation is explicit (__d*_rn on the device) so no FMA contraction can change it.
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ inline bool point_in_polygon_ref(double x, double y, const double2* v, int n) {
+  bool inside = false;
+  double p1x = v[0].x, p1y = v[0].y;
+  for (int i = 1; i <= n; ++i) {
+    const double2 q = v[i == n ? 0 : i];
+    const double p2x = q.x, p2y = q.y;
+    const double ymin = p1y < p2y ? p1y : p2y;   // Python min(p1y, p2y) on finite floats
+    const double ymax = p1y < p2y ? p2y : p1y;
+    const double xmax = p1x < p2x ? p2x : p1x;
+    if (y > ymin && y <= ymax && x <= xmax) {
+      // here p1y != p2y (ymin < ymax), so the reference always (re)computes xinters (:187-189)
+#ifdef __CUDA_ARCH__
+      const double xinters =
+          __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(y, p1y), __dsub_rn(p2x, p1x)), __dsub_rn(p2y, p1y)), p1x);
+#else
+      volatile double t0 = y - p1y, t1 = p2x - p1x;
+      volatile double t2 = t0 * t1;
+      volatile double t3 = p2y - p1y;
+      volatile double t4 = t2 / t3;
+      const double xinters = t4 + p1x;
+#endif
+      if (p1x == p2x || x <= xinters) inside = !inside;
+    }
+    p1x = p2x;
+    p1y = p2y;
+  }
+  return inside;
+}
+
+struct FloorK {
+  // projection
+  double H[9];
+  double sx, sy, mw, mh;
+  float Hf[9];        // float32 copy of H for the filter path
+  float Sxy[3];       // max(|H0j|, |H1j|) — magnitude bound of the X and Y rows
+  float Sw[3];        // |H2j|
+  float err_max;      // Δ/2
+  // grid
+  double gx0, gy0, inv_cw, inv_ch;
+  float gx0_f, gy0_f, inv_cw_f, inv_ch_f;
+  int gw, gh;
+  int Z, allow_overlap, input_is_bbox, skip_projection;
+  int n_verts, stage_grid, stage_verts;
+  const uint8_t* grid;
+  const uint64_t* class_mask;    // [256]
+  const int32_t* class_winner;   // [256]
+  const int32_t* cell_entry;     // [gw*gh]
+  const uint64_t* entry_inside;  // [n_boundary]
+  const uint64_t* entry_cand;    // [n_boundary]
+  const double2* verts;          // [n_verts]
+  const int32_t* poly_off;       // [Z+1]
+  const int32_t* zone_rank;      // [64]
+  // io
+  const void* in;
+  const int32_t* slot;
+  long long N;
+  int T;
+  void* floor_px;
+  void* floor_mm;
+  uint8_t* in_bounds;
+  int32_t* zone_idx;
+  uint64_t* zone_mask;
+  int32_t* hist;
+};
+
+struct SmemTables {
+  const uint8_t* grid;
+  const uint64_t* class_mask;
+  const int32_t* class_winner;
+  const double2* verts;
+  const int32_t* poly_off;
+  const int32_t* zone_rank;
+};
+
+__device__ __forceinline__ int winner_of(uint64_t m, const int32_t* zone_rank) {
+  int best = -1, best_rank = 0x7fffffff;
+  while (m) {
+    const int z = __ffsll((long long)m) - 1;
+    m &= m - 1;
+    const int r = zone_rank[z];
+    if (r < best_rank) {
+      best_rank = r;
+      best = z;
+    }
+  }
+  return best;
+}
+
+// float64 classification of one floor point through the grid (+ exact ray casting in boundary cells).
+// Returns the containing-zones mask (declaration-order bits); *win = selected zone or -1.
+__device__ __forceinline__ uint64_t classify_exact(const FloorK& p, const SmemTables& t, double px, double py,
+                                                   int* win) {
+  uint64_t mask = 0;
+  int w = -1;
+  const double fx = (px - p.gx0) * p.inv_cw;
+  const double fy = (py - p.gy0) * p.inv_ch;
+  if (fx >= 0.0 && fx < (double)p.gw && fy >= 0.0 && fy < (double)p.gh) {  // NaN -> outside, like the reference
+    const int cell = (int)fy * p.gw + (int)fx;
+    const int code = t.grid[cell];
+    if (code != kBoundary) {
+      mask = t.class_mask[code];
+      w = t.class_winner[code];
+    } else {
+      const int e = p.cell_entry[cell];
+      mask = p.entry_inside[e];
+      uint64_t cand = p.entry_cand[e];
+      while (cand) {
+        const int z = __ffsll((long long)cand) - 1;
+        cand &= cand - 1;
+        const int o = t.poly_off[z];
+        if (point_in_polygon_ref(px, py, t.verts + o, t.poly_off[z + 1] - o)) mask |= 1ull << z;
+      }
+      w = winner_of(mask, t.zone_rank);
+      if (!p.allow_overlap) mask = w >= 0 ? 1ull << w : 0ull;
+    }
+  }
+  *win = w;
+  return mask;
+}
+
+// H·[x, y, 1] then perspective divide, float64 (homography.py:172-175).
+__device__ __forceinline__ void project_exact(const FloorK& p, double x, double y, double* px, double* py) {
+  const double X = fma(p.H[2], 1.0, fma(p.H[1], y, p.H[0] * x));
+  const double Y = fma(p.H[5], 1.0, fma(p.H[4], y, p.H[3] * x));
+  const double W = fma(p.H[8], 1.0, fma(p.H[7], y, p.H[6] * x));
+  *px = __ddiv_rn(X, W);
+  *py = __ddiv_rn(Y, W);
+}
+
+__device__ __forceinline__ SmemTables stage_tables(const FloorK& p, unsigned char* smem, int cells_rounded) {
+  // layout: [grid bytes][class_mask 256*8][class_winner 256*4][zone_rank 64*4][poly_off 68*4][verts]
+  SmemTables t;
+  unsigned char* cur = smem;
+  uint8_t* s_grid = cur;
+  cur += p.stage_grid ? cells_rounded : 0;
+  uint64_t* s_cm = reinterpret_cast<uint64_t*>(cur);
+  cur += 256 * 8;
+  int32_t* s_cw = reinterpret_cast<int32_t*>(cur);
+  cur += 256 * 4;
+  int32_t* s_rank = reinterpret_cast<int32_t*>(cur);
+  cur += 64 * 4;
+  int32_t* s_off = reinterpret_cast<int32_t*>(cur);
+  cur += 68 * 4;
+  double2* s_verts = reinterpret_cast<double2*>(cur);
+
+  if (p.stage_grid) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.grid);
+    uint4* dst = reinterpret_cast<uint4*>(s_grid);
+    for (int i = threadIdx.x; i < cells_rounded / 16; i += blockDim.x) dst[i] = src[i];
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_cm[i] = p.class_mask[i];
+    s_cw[i] = p.class_winner[i];
+  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_rank[i] = p.zone_rank[i];
+  for (int i = threadIdx.x; i <= p.Z; i += blockDim.x) s_off[i] = p.poly_off[i];
+  if (p.stage_verts)
+    for (int i = threadIdx.x; i < p.n_verts; i += blockDim.x) s_verts[i] = p.verts[i];
+  t.grid = p.stage_grid ? s_grid : p.grid;
+  t.class_mask = s_cm;
+  t.class_winner = s_cw;
+  t.zone_rank = s_rank;
+  t.poly_off = s_off;
+  t.verts = p.stage_verts ? s_verts : p.verts;
+  return t;
+}
+
+__host__ __device__ inline size_t tables_smem_bytes(int stage_grid, int cells_rounded, int stage_verts, int n_verts) {
+  return (size_t)(stage_grid ? cells_rounded : 0) + 256 * 8 + 256 * 4 + 64 * 4 + 68 * 4 +
+         (stage_verts ? (size_t)n_verts * 16 : 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// floor_exact_kernel: one point per thread and iteration, float64 arithmetic, every output optional.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) floor_exact_kernel(const FloorK p, int cells_rounded) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemTables t = stage_tables(p, smem, cells_rounded);
+  __syncthreads();
+
+  const T* in = static_cast<const T*>(p.in);
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_rounded = (p.N + 31) / 32 * 32;  // keep warps converged for match_any
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rounded; i += stride) {
+    const bool live = i < p.N;
+    int key = -1;
+    if (live) {
+      double x, y;
+      if (p.input_is_bbox) {
+        const double bx = (double)in[4 * i + 0], by = (double)in[4 * i + 1];
+        const double bw = (double)in[4 * i + 2], bh = (double)in[4 * i + 3];
+        x = __dadd_rn(bx, __ddiv_rn(bw, 2.0));  // homography.py:167  [x + w / 2, y + h]
+        y = __dadd_rn(by, bh);
+      } else {
+        x = (double)in[2 * i + 0];
+        y = (double)in[2 * i + 1];
+      }
+      double px = x, py = y;
+      if (!p.skip_projection) project_exact(p, x, y, &px, &py);
+      if (p.floor_px) {
+        static_cast<T*>(p.floor_px)[2 * i + 0] = (T)px;
+        static_cast<T*>(p.floor_px)[2 * i + 1] = (T)py;
+      }
+      if (p.floor_mm) {
+        static_cast<T*>(p.floor_mm)[2 * i + 0] = (T)__dmul_rn(px, p.sx);  // homography.py:183-186
+        static_cast<T*>(p.floor_mm)[2 * i + 1] = (T)__dmul_rn(py, p.sy);
+      }
+      if (p.in_bounds) p.in_bounds[i] = (0.0 <= px && px < p.mw && 0.0 <= py && py < p.mh) ? 1 : 0;
+      if (p.zone_idx || p.zone_mask || p.hist) {
+        int win;
+        const uint64_t mask = classify_exact(p, t, px, py, &win);
+        if (p.zone_idx) p.zone_idx[i] = win;
+        if (p.zone_mask) p.zone_mask[i] = mask;
+        if (p.hist) {
+          const int s = p.slot ? p.slot[i] : 0;
+          if ((unsigned)s < (unsigned)p.T) {
+            const int row = s * (p.Z + 1);
+            if (mask == 0) {
+              key = row + p.Z;  // aggregator.py:71-73 "unclassified"
+            } else if ((mask & (mask - 1)) == 0) {
+              key = row + (__ffsll((long long)mask) - 1);
+            } else {  // several zones: one count each (aggregator.py:66-69); rare, plain atomics
+              uint64_t m = mask;
+              while (m) {
+                atomicAdd(p.hist + row + (__ffsll((long long)m) - 1), 1);
+                m &= m - 1;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (p.hist) {  // warp-aggregated atomics: one per distinct (slot, bin) in the warp
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(p.hist + key, __popc(peers));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// floor_fast_kernel: float32 points in, int32 zone index and/or row-0 histogram out.
+// ---------------------------------------------------------------------------------------------------------
+struct WarpCounter {
+  unsigned m[5];   // m[k] = lane bit k set ? 0 : ~0  (XOR mask so that (ballot ^ m) selects "bit k equals mine")
+  unsigned c0, c1; // counts of zones `lane` and `lane + 32`
+  __device__ __forceinline__ void init(int lane) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) m[k] = ((lane >> k) & 1) ? 0u : 0xffffffffu;
+    c0 = c1 = 0;
+  }
+  // zi < 0: not counted here.  All 32 lanes must call.
+  __device__ __forceinline__ void add(int zi) {
+    const unsigned valid = __ballot_sync(0xffffffffu, zi >= 0);
+    if (valid == 0) return;
+    unsigned common = valid;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) common &= __ballot_sync(0xffffffffu, (zi >> k) & 1) ^ m[k];
+    const unsigned hi = __ballot_sync(0xffffffffu, (zi >> 5) & 1);
+    c0 += __popc(common & ~hi);
+    c1 += __popc(common & hi);
+  }
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float4* ptr) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(ptr));
+  return r;
+}
+
+// float32 filter: returns the class code of the point's cell (0..254), or -1 when the point must take the
+// float64 path (error bound too large, non-finite, or boundary cell), or -2 when it is certainly outside the grid.
+__device__ __forceinline__ int filter_point(const FloorK& p, const uint8_t* s_grid, float x, float y) {
+  const float X = fmaf(p.Hf[0], x, fmaf(p.Hf[1], y, p.Hf[2]));
+  const float Y = fmaf(p.Hf[3], x, fmaf(p.Hf[4], y, p.Hf[5]));
+  const float W = fmaf(p.Hf[6], x, fmaf(p.Hf[7], y, p.Hf[8]));
+  const float r = __frcp_rn(W);
+  const float px = X * r, py = Y * r;
+  // |X̂ - X| <= 8u·Sxy, |Ŵ - W| <= 8u·Sw (3 roundings + float32 rounding of H, u = 2^-24), so
+  // |p̂ - p| <= 16u·|r|·(Sxy + max|p̂|·Sw) + 16u·max|p̂|   (constant doubled for the reciprocal / product roundings)
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float sxy = fmaf(p.Sxy[0], ax, fmaf(p.Sxy[1], ay, p.Sxy[2]));
+  const float sw = fmaf(p.Sw[0], ax, fmaf(p.Sw[1], ay, p.Sw[2]));
+  const float pm = fmaxf(fabsf(px), fabsf(py));
+  const float c = 16.0f * 5.9604645e-8f;
+  const float err = c * fmaf(fabsf(r), fmaf(pm, sw, sxy), pm);
+  if (!(err <= p.err_max)) return -1;  // also catches NaN / inf
+  const float fx = (px - p.gx0_f) * p.inv_cw_f;
+  const float fy = (py - p.gy0_f) * p.inv_ch_f;
+  if (!(fx >= 0.0f && fx < (float)p.gw && fy >= 0.0f && fy < (float)p.gh)) return -2;
+  const int code = s_grid[(int)fy * p.gw + (int)fx];
+  return code == kBoundary ? -1 : code;
+}
+
+__global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const FloorK p, int cells_rounded) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemTables t = stage_tables(p, smem, cells_rounded);
+  unsigned char* cur = smem + (tables_smem_bytes(1, cells_rounded, p.stage_verts, p.n_verts) + 15) / 16 * 16;
+  unsigned* s_queue = reinterpret_cast<unsigned*>(cur);
+  cur += kQueueCap * 4;
+  unsigned* s_hist = reinterpret_cast<unsigned*>(cur);  // [64]
+  unsigned* s_qcount = s_hist + 64;
+  if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) *s_qcount = 0;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const bool do_hist = p.hist != nullptr;
+  WarpCounter wc;
+  wc.init(lane);
+
+  const float* in = static_cast<const float*>(p.in);
+  const long long n_chunks = (p.N + kFastChunk - 1) / kFastChunk;
+
+  auto drain = [&]() {
+    // dense float64 pass over the queued points
+    const unsigned n = *s_qcount;
+    for (unsigned k0 = 0; k0 < n; k0 += kFastThreads) {
+      const unsigned k = k0 + threadIdx.x;
+      int win = -1;
+      bool live = k < n;
+      if (live) {
+        const unsigned i = s_queue[k];
+        const float2 xy = reinterpret_cast<const float2*>(in)[i];
+        double px, py;
+        project_exact(p, (double)xy.x, (double)xy.y, &px, &py);
+        classify_exact(p, t, px, py, &win);
+        if (p.zone_idx) p.zone_idx[i] = win;
+      }
+      if (do_hist) wc.add(live ? win : -1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *s_qcount = 0;
+    __syncthreads();
+  };
+
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const long long base = chunk * kFastChunk + (long long)threadIdx.x * kFastPointsPerThread;
+    float xs[4], ys[4];
+    int n_live;
+    if (base + 4 <= p.N) {
+      const float4 a = ldg_stream(reinterpret_cast<const float4*>(in + 2 * base));
+      const float4 b = ldg_stream(reinterpret_cast<const float4*>(in + 2 * base) + 1);
+      xs[0] = a.x; ys[0] = a.y; xs[1] = a.z; ys[1] = a.w;
+      xs[2] = b.x; ys[2] = b.y; xs[3] = b.z; ys[3] = b.w;
+      n_live = 4;
+    } else {
+      n_live = base < p.N ? (int)(p.N - base) : 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xs[j] = j < n_live ? in[2 * (base + j) + 0] : 0.f;
+        ys[j] = j < n_live ? in[2 * (base + j) + 1] : 0.f;
+      }
+    }
+    int zi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int code = j < n_live ? filter_point(p, t.grid, xs[j], ys[j]) : -2;
+      const bool slow = code == -1;
+      // queue push, one shared-memory atomic per warp
+      const unsigned sb = __ballot_sync(0xffffffffu, slow);
+      if (sb) {
+        unsigned pos = 0;
+        if (lane == 0) pos = atomicAdd(s_qcount, __popc(sb));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (slow) s_queue[pos + __popc(sb & ((1u << lane) - 1))] = (unsigned)(base + j);
+      }
+      zi[j] = code >= 0 ? t.class_winner[code] : -1;
+      if (do_hist) wc.add(zi[j]);
+    }
+    if (p.zone_idx) {
+      if (n_live == 4) {
+        *reinterpret_cast<int4*>(p.zone_idx + base) = make_int4(zi[0], zi[1], zi[2], zi[3]);
+      } else {
+        for (int j = 0; j < n_live; ++j) p.zone_idx[base + j] = zi[j];
+      }
+    }
+    __syncthreads();  // queue count visible; also orders the placeholder stores before the drain's stores
+    const unsigned queued = *s_qcount;
+    __syncthreads();  // everyone has read the count before the next iteration's pushes can change it
+    if (queued > kQueueCap - kFastChunk) drain();
+  }
+  __syncthreads();
+  drain();
+
+  if (do_hist) {
+    atomicAdd(&s_hist[lane], wc.c0);
+    atomicAdd(&s_hist[lane + 32], wc.c1);
+    __syncthreads();
+    // classified counts go to their bins; bin Z receives (points handled) - (classified), summed over CTAs
+    if (threadIdx.x < 64 && threadIdx.x < p.Z && s_hist[threadIdx.x]) {
+      atomicAdd(p.hist + threadIdx.x, (int)s_hist[threadIdx.x]);
+      atomicSub(p.hist + p.Z, (int)s_hist[threadIdx.x]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.hist + p.Z, (int)p.N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Histogram-only kernel (Aggregator.get_zone_counts on classified points).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void zone_histogram_kernel(const int32_t* zone_idx, const uint64_t* zone_mask, const int32_t* slot,
+                                      long long N, int Z, int T, int32_t* hist) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const int s = slot ? slot[i] : 0;
+    if ((unsigned)s >= (unsigned)T) continue;
+    int32_t* row = hist + (long long)s * (Z + 1);
+    if (zone_idx) {
+      const int z = zone_idx[i];
+      atomicAdd(row + ((unsigned)z < (unsigned)Z ? z : Z), 1);
+    } else {
+      uint64_t m = zone_mask[i];
+      if (Z < 64) m &= (1ull << Z) - 1;
+      if (m == 0) atomicAdd(row + Z, 1);
+      while (m) {
+        atomicAdd(row + (__ffsll((long long)m) - 1), 1);
+        m &= m - 1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host: zone table construction (float64).
+// ---------------------------------------------------------------------------------------------------------
+bool segment_hits_box(double ax, double ay, double bx, double by, double x0, double y0, double x1, double y1) {
+  // Liang–Barsky clip of segment a->b against [x0,x1]x[y0,y1]; callers pass an already dilated box.
+  double t0 = 0.0, t1 = 1.0;
+  const double dx = bx - ax, dy = by - ay;
+  const double pq[4][2] = {{-dx, ax - x0}, {dx, x1 - ax}, {-dy, ay - y0}, {dy, y1 - ay}};
+  for (int k = 0; k < 4; ++k) {
+    const double pp = pq[k][0], qq = pq[k][1];
+    if (pp == 0.0) {
+      if (qq < 0.0) return false;
+    } else {
+      const double r = qq / pp;
+      if (pp < 0.0) {
+        if (r > t1) return false;
+        if (r > t0) t0 = r;
+      } else {
+        if (r < t0) return false;
+        if (r < t1) t1 = r;
+      }
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+struct opd_zone_table {
+  int device = 0, Z = 0, allow_overlap = 0;
+  int gw = 1, gh = 1, cells_rounded = 16;
+  double gx0 = 0, gy0 = 0, inv_cw = 1, inv_ch = 1, delta = 0.125;
+  int n_classes = 1, n_boundary = 0, n_verts = 0;
+  bool fast_ok = false;
+  unsigned char* d_blob = nullptr;  // one allocation, carved below
+  uint8_t* d_grid = nullptr;
+  uint64_t* d_class_mask = nullptr;
+  int32_t* d_class_winner = nullptr;
+  int32_t* d_cell_entry = nullptr;
+  uint64_t* d_entry_inside = nullptr;
+  uint64_t* d_entry_cand = nullptr;
+  double2* d_verts = nullptr;
+  int32_t* d_poly_off = nullptr;
+  int32_t* d_zone_rank = nullptr;
+};
+
+extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly_offsets, const double* priority,
+                                     int32_t Z, int32_t allow_overlap, int32_t device, opd_zone_table** out) {
+  OPD_REQUIRE(out != nullptr, "opd_zone_table_create: out is NULL");
+  OPD_REQUIRE(Z >= 0 && Z <= OPD_MAX_ZONES, "opd_zone_table_create: Z=%d outside [0,%d]", Z, OPD_MAX_ZONES);
+  OPD_REQUIRE(Z == 0 || (verts_xy && poly_offsets && priority), "opd_zone_table_create: NULL table input");
+  const int n_verts = Z ? poly_offsets[Z] : 0;
+  for (int z = 0; z < Z; ++z)
+    OPD_REQUIRE(poly_offsets[z + 1] - poly_offsets[z] >= 3, "opd_zone_table_create: polygon %d has < 3 vertices", z);
+  for (int i = 0; i < 2 * n_verts; ++i)
+    OPD_REQUIRE(std::isfinite(verts_xy[i]), "opd_zone_table_create: non-finite vertex coordinate");
+
+  auto* zt = new opd_zone_table();
+  zt->device = device;
+  zt->Z = Z;
+  zt->allow_overlap = allow_overlap ? 1 : 0;
+  zt->n_verts = n_verts;
+
+  // rank = position in the order sorted by (priority or +inf, declaration order)  (zone_classifier.py:138-146)
+  std::vector<int32_t> rank(64, 0x7fffffff);
+  {
+    std::vector<int> order(Z);
+    for (int z = 0; z < Z; ++z) order[z] = z;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      const double pa = std::isnan(priority[a]) ? INFINITY : priority[a];
+      const double pb = std::isnan(priority[b]) ? INFINITY : priority[b];
+      return pa < pb;
+    });
+    for (int r = 0; r < Z; ++r) rank[order[r]] = r;
+  }
+  auto winner = [&](uint64_t m) {
+    int best = -1, br = 0x7fffffff;
+    for (int z = 0; z < Z; ++z)
+      if ((m >> z) & 1ull)
+        if (rank[z] < br) {
+          br = rank[z];
+          best = z;
+        }
+    return best;
+  };
+
+  const double2* V = reinterpret_cast<const double2*>(verts_xy);
+  std::vector<uint8_t> grid;
+  std::vector<uint64_t> class_mask(256, 0);
+  std::vector<int32_t> class_winner(256, -1);
+  std::vector<int32_t> cell_entry;
+  std::vector<uint64_t> entry_inside, entry_cand;
+
+  if (Z == 0) {
+    zt->gw = zt->gh = 1;
+    grid.assign(16, 0);
+    cell_entry.assign(1, -1);
+    zt->n_classes = 1;  // class 0 = no zone
+    zt->gx0 = zt->gy0 = 0.0;
+    zt->inv_cw = zt->inv_ch = 1.0;
+    zt->fast_ok = true;
+  } else {
+    double minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY;
+    for (int i = 0; i < n_verts; ++i) {
+      minx = std::min(minx, V[i].x); maxx = std::max(maxx, V[i].x);
+      miny = std::min(miny, V[i].y); maxy = std::max(maxy, V[i].y);
+    }
+    const double mx = std::max(1.0, 0.01 * (maxx - minx)), my = std::max(1.0, 0.01 * (maxy - miny));
+    minx -= mx; maxx += mx; miny -= my; maxy += my;
+    const double ex = maxx - minx, ey = maxy - miny;
+    int gw = (int)std::floor(std::sqrt((double)kGridCellBudget * ex / ey));
+    gw = std::max(1, std::min(gw, kGridCellBudget));
+    int gh = std::max(1, kGridCellBudget / gw);
+    const double cw = ex / gw, ch = ey / gh;
+    zt->gw = gw; zt->gh = gh;
+    zt->gx0 = minx; zt->gy0 = miny;
+    zt->inv_cw = 1.0 / cw; zt->inv_ch = 1.0 / ch;
+    zt->delta = std::min(0.125, 0.125 * std::min(cw, ch));
+    // float32 cell-index slop must stay far below delta for the filter path to be sound
+    const double maxabs = std::max(std::max(std::fabs(minx), std::fabs(maxx)), std::max(std::fabs(miny), std::fabs(maxy)));
+    zt->fast_ok = (8.0 * 5.97e-8 * maxabs) < zt->delta * 0.25 && zt->delta * 0.5 < std::min(mx, my);
+
+    const size_t cells = (size_t)gw * gh;
+    std::vector<uint64_t> cand(cells, 0), inside(cells, 0);
+    const double dil = zt->delta * (1.0 + 1e-9) + 1e-9 * (1.0 + maxabs);
+    for (int z = 0; z < Z; ++z) {
+      const int o = poly_offsets[z], n = poly_offsets[z + 1] - o;
+      double bx0 = INFINITY, by0 = INFINITY, bx1 = -INFINITY, by1 = -INFINITY;
+      for (int i = 0; i < n; ++i) {
+        const double2 a = V[o + i], b = V[o + (i + 1) % n];
+        bx0 = std::min(bx0, a.x); bx1 = std::max(bx1, a.x);
+        by0 = std::min(by0, a.y); by1 = std::max(by1, a.y);
+        // cells whose dilated box the edge crosses
+        const double ex0 = std::min(a.x, b.x) - dil, ex1 = std::max(a.x, b.x) + dil;
+        const double ey0 = std::min(a.y, b.y) - dil, ey1 = std::max(a.y, b.y) + dil;
+        const int cx0 = std::max(0, (int)std::floor((ex0 - minx) / cw) - 1), cx1 = std::min(gw - 1, (int)std::floor((ex1 - minx) / cw) + 1);
+        const int cy0 = std::max(0, (int)std::floor((ey0 - miny) / ch) - 1), cy1 = std::min(gh - 1, (int)std::floor((ey1 - miny) / ch) + 1);
+        for (int cy = cy0; cy <= cy1; ++cy)
+          for (int cx = cx0; cx <= cx1; ++cx) {
+            const double x0 = minx + cx * cw - dil, x1 = minx + (cx + 1) * cw + dil;
+            const double y0 = miny + cy * ch - dil, y1 = miny + (cy + 1) * ch + dil;
+            if (segment_hits_box(a.x, a.y, b.x, b.y, x0, y0, x1, y1)) cand[(size_t)cy * gw + cx] |= 1ull << z;
+          }
+      }
+      // uniform status of the remaining cells inside the polygon's bounding box: test the cell centre
+      const int cx0 = std::max(0, (int)std::floor((bx0 - minx) / cw) - 1), cx1 = std::min(gw - 1, (int)std::floor((bx1 - minx) / cw) + 1);
+      const int cy0 = std::max(0, (int)std::floor((by0 - miny) / ch) - 1), cy1 = std::min(gh - 1, (int)std::floor((by1 - miny) / ch) + 1);
+      for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) {
+          const size_t c = (size_t)cy * gw + cx;
+          if ((cand[c] >> z) & 1ull) continue;
+          if (point_in_polygon_ref(minx + (cx + 0.5) * cw, miny + (cy + 0.5) * ch, V + o, n)) inside[c] |= 1ull << z;
+        }
+    }
+    // classes
+    zt->cells_rounded = (int)((cells + 15) / 16 * 16);
+    grid.assign(zt->cells_rounded, 0);
+    cell_entry.assign(cells, -1);
+    std::map<uint64_t, int> class_of;
+    int n_classes = 0;
+    auto get_class = [&](uint64_t m) -> int {
+      const int w = winner(m);
+      const uint64_t key = zt->allow_overlap ? m : (w >= 0 ? 1ull << w : 0ull);
+      auto it = class_of.find(key);
+      if (it != class_of.end()) return it->second;
+      if (n_classes >= kMaxClasses) return -1;
+      class_mask[n_classes] = key;
+      class_winner[n_classes] = w;
+      class_of[key] = n_classes;
+      return n_classes++;
+    };
+    get_class(0);  // class 0 = no zone
+    for (size_t c = 0; c < cells; ++c) {
+      int code = cand[c] ? -1 : get_class(inside[c]);
+      if (code < 0) {
+        cell_entry[c] = (int32_t)entry_inside.size();
+        entry_inside.push_back(inside[c]);
+        entry_cand.push_back(cand[c]);
+        code = kBoundary;
+      }
+      grid[c] = (uint8_t)code;
+    }
+    zt->n_classes = n_classes;
+    zt->n_boundary = (int)entry_inside.size();
+  }
+  if (entry_inside.empty()) {
+    entry_inside.push_back(0);
+    entry_cand.push_back(0);
+  }
+  std::vector<int32_t> poly_off(68, 0);
+  for (int z = 0; z <= Z && Z > 0; ++z) poly_off[z] = poly_offsets[z];
+
+  // one device blob
+  auto up16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  const size_t o_grid = 0;
+  const size_t o_cm = o_grid + up16(grid.size());
+  const size_t o_cw = o_cm + 256 * 8;
+  const size_t o_ce = o_cw + 256 * 4;
+  const size_t o_ei = up16(o_ce + cell_entry.size() * 4);
+  const size_t o_ec = o_ei + up16(entry_inside.size() * 8);
+  const size_t o_v = o_ec + up16(entry_cand.size() * 8);
+  const size_t o_po = o_v + up16((size_t)std::max(1, n_verts) * 16);
+  const size_t o_rk = o_po + up16(68 * 4);
+  const size_t total = o_rk + 64 * 4;
+  std::vector<unsigned char> blob(total, 0);
+  memcpy(&blob[o_grid], grid.data(), grid.size());
+  memcpy(&blob[o_cm], class_mask.data(), 256 * 8);
+  memcpy(&blob[o_cw], class_winner.data(), 256 * 4);
+  memcpy(&blob[o_ce], cell_entry.data(), cell_entry.size() * 4);
+  memcpy(&blob[o_ei], entry_inside.data(), entry_inside.size() * 8);
+  memcpy(&blob[o_ec], entry_cand.data(), entry_cand.size() * 8);
+  if (n_verts) memcpy(&blob[o_v], verts_xy, (size_t)n_verts * 16);
+  memcpy(&blob[o_po], poly_off.data(), 68 * 4);
+  memcpy(&blob[o_rk], rank.data(), 64 * 4);
+
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&zt->d_blob, total);
+  if (e == cudaSuccess) e = cudaMemcpy(zt->d_blob, blob.data(), total, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (zt->d_blob) cudaFree(zt->d_blob);
+    delete zt;
+    return opd::fail(OPD_ERR_CUDA, "opd_zone_table_create: %s", cudaGetErrorString(e));
+  }
+  zt->d_grid = zt->d_blob + o_grid;
+  zt->d_class_mask = reinterpret_cast<uint64_t*>(zt->d_blob + o_cm);
+  zt->d_class_winner = reinterpret_cast<int32_t*>(zt->d_blob + o_cw);
+  zt->d_cell_entry = reinterpret_cast<int32_t*>(zt->d_blob + o_ce);
+  zt->d_entry_inside = reinterpret_cast<uint64_t*>(zt->d_blob + o_ei);
+  zt->d_entry_cand = reinterpret_cast<uint64_t*>(zt->d_blob + o_ec);
+  zt->d_verts = reinterpret_cast<double2*>(zt->d_blob + o_v);
+  zt->d_poly_off = reinterpret_cast<int32_t*>(zt->d_blob + o_po);
+  zt->d_zone_rank = reinterpret_cast<int32_t*>(zt->d_blob + o_rk);
+  *out = zt;
+  return OPD_OK;
+}
+
+extern "C" void opd_zone_table_destroy(opd_zone_table* zt) {
+  if (!zt) return;
+  if (zt->d_blob) cudaFree(zt->d_blob);
+  delete zt;
+}
+
+extern "C" int opd_zone_table_info(const opd_zone_table* zt, int32_t* grid_w, int32_t* grid_h,
+                                   int32_t* n_boundary_cells, int32_t* n_classes) {
+  OPD_REQUIRE(zt != nullptr, "opd_zone_table_info: NULL table");
+  if (grid_w) *grid_w = zt->gw;
+  if (grid_h) *grid_h = zt->gh;
+  if (n_boundary_cells) *n_boundary_cells = zt->n_boundary;
+  if (n_classes) *n_classes = zt->n_classes;
+  return OPD_OK;
+}
+
+namespace {
+
+int fill_params(FloorK& k, const opd_floor_params* p, const opd_zone_table* zt, const void* in, const int32_t* slot,
+                int64_t N, int32_t T, void* floor_px, void* floor_mm, uint8_t* in_bounds, int32_t* zone_idx,
+                uint64_t* zone_mask, int32_t* hist) {
+  OPD_REQUIRE(p && zt, "floor: NULL params / zone table");
+  OPD_REQUIRE(N >= 0, "floor: N=%lld < 0", (long long)N);
+  OPD_REQUIRE(N == 0 || in != nullptr, "floor: NULL input");
+  OPD_REQUIRE(hist == nullptr || T >= 1, "floor: T=%d must be >= 1 when a histogram is requested", T);
+  memset(&k, 0, sizeof(k));
+  for (int i = 0; i < 9; ++i) {
+    k.H[i] = p->H[i];
+    k.Hf[i] = (float)p->H[i];
+  }
+  for (int j = 0; j < 3; ++j) {
+    // magnitudes rounded up so the float32 bound stays an upper bound
+    k.Sxy[j] = nextafterf((float)std::max(std::fabs(p->H[j]), std::fabs(p->H[3 + j])), INFINITY);
+    k.Sw[j] = nextafterf((float)std::fabs(p->H[6 + j]), INFINITY);
+  }
+  k.sx = p->scale_x_mm; k.sy = p->scale_y_mm; k.mw = p->map_w_px; k.mh = p->map_h_px;
+  k.err_max = (float)(zt->delta * 0.5);
+  k.gx0 = zt->gx0; k.gy0 = zt->gy0; k.inv_cw = zt->inv_cw; k.inv_ch = zt->inv_ch;
+  k.gx0_f = (float)zt->gx0; k.gy0_f = (float)zt->gy0; k.inv_cw_f = (float)zt->inv_cw; k.inv_ch_f = (float)zt->inv_ch;
+  k.gw = zt->gw; k.gh = zt->gh;
+  k.Z = zt->Z; k.allow_overlap = zt->allow_overlap;
+  k.input_is_bbox = p->input_is_bbox; k.skip_projection = p->skip_projection;
+  k.n_verts = zt->n_verts;
+  k.grid = zt->d_grid; k.class_mask = zt->d_class_mask; k.class_winner = zt->d_class_winner;
+  k.cell_entry = zt->d_cell_entry; k.entry_inside = zt->d_entry_inside; k.entry_cand = zt->d_entry_cand;
+  k.verts = zt->d_verts; k.poly_off = zt->d_poly_off; k.zone_rank = zt->d_zone_rank;
+  k.in = in; k.slot = slot; k.N = N; k.T = T;
+  k.floor_px = floor_px; k.floor_mm = floor_mm; k.in_bounds = in_bounds;
+  k.zone_idx = zone_idx; k.zone_mask = zone_mask; k.hist = hist;
+  k.stage_verts = zt->n_verts <= kMaxSmemVerts;
+  return OPD_OK;
+}
+
+int device_sm_count(int device, int* sms) {
+  static int cached_dev = -1, cached = 0;
+  if (cached_dev != device) {
+    OPD_CUDA_OK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, device));
+    cached_dev = device;
+  }
+  *sms = cached;
+  return OPD_OK;
+}
+
+template <typename T>
+int launch_exact(FloorK& k, const opd_zone_table* zt, cudaStream_t s) {
+  if (k.N == 0) return OPD_OK;
+  int sms = 148;
+  if (int rc = device_sm_count(zt->device, &sms)) return rc;
+  // small inputs read the grid from L2; large ones stage it in shared memory once per CTA
+  k.stage_grid = k.N >= (1 << 18);
+  const size_t smem = tables_smem_bytes(k.stage_grid, zt->cells_rounded, k.stage_verts, k.n_verts);
+  auto kern = floor_exact_kernel<T>;
+  OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = 256;
+  long long blocks = (k.N + threads - 1) / threads;
+  const long long cap = k.stage_grid ? sms : (long long)sms * 8;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, threads, smem, s>>>(k, zt->cells_rounded);
+  opd::count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+}  // namespace
+
+extern "C" int opd_floor_project_classify_count_f64(const opd_floor_params* p, const opd_zone_table* zt,
+                                                    const double* in_dev, const int32_t* slot_dev, int64_t N,
+                                                    int32_t T, double* floor_px_dev, double* floor_mm_dev,
+                                                    uint8_t* in_bounds_dev, int32_t* zone_idx_dev,
+                                                    uint64_t* zone_mask_dev, int32_t* hist_dev, void* stream) {
+  FloorK k;
+  if (int rc = fill_params(k, p, zt, in_dev, slot_dev, N, T, floor_px_dev, floor_mm_dev, in_bounds_dev, zone_idx_dev,
+                           zone_mask_dev, hist_dev))
+    return rc;
+  return launch_exact<double>(k, zt, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int opd_floor_project_classify_count_f32(const opd_floor_params* p, const opd_zone_table* zt,
+                                                    const float* in_dev, const int32_t* slot_dev, int64_t N,
+                                                    int32_t T, float* floor_px_dev, float* floor_mm_dev,
+                                                    uint8_t* in_bounds_dev, int32_t* zone_idx_dev,
+                                                    uint64_t* zone_mask_dev, int32_t* hist_dev, void* stream) {
+  FloorK k;
+  if (int rc = fill_params(k, p, zt, in_dev, slot_dev, N, T, floor_px_dev, floor_mm_dev, in_bounds_dev, zone_idx_dev,
+                           zone_mask_dev, hist_dev))
+    return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // The filtered kernel covers the bandwidth-critical shape: many points, zone index and/or a single
+  // histogram row.  Everything else (coordinates out, masks, per-timestamp slots, boxes) takes the exact kernel.
+  const bool fast = zt->fast_ok && N >= (1 << 16) && N < (1ll << 32) && !p->input_is_bbox && !p->skip_projection &&
+                    !floor_px_dev && !floor_mm_dev && !in_bounds_dev && !zone_mask_dev && !slot_dev &&
+                    (zone_idx_dev || hist_dev) && (reinterpret_cast<uintptr_t>(in_dev) % 16 == 0) &&
+                    (zone_idx_dev == nullptr || reinterpret_cast<uintptr_t>(zone_idx_dev) % 16 == 0);
+  if (!fast) return launch_exact<float>(k, zt, s);
+  int sms = 148;
+  if (int rc = device_sm_count(zt->device, &sms)) return rc;
+  k.stage_grid = 1;
+  const size_t smem = (tables_smem_bytes(1, zt->cells_rounded, k.stage_verts, k.n_verts) + 15) / 16 * 16 +
+                      kQueueCap * 4 + 64 * 4 + 16;
+  OPD_CUDA_OK(cudaFuncSetAttribute(floor_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long chunks = (N + kFastChunk - 1) / kFastChunk;
+  const unsigned blocks = (unsigned)std::min<long long>(chunks, sms);
+  floor_fast_kernel<<<blocks, kFastThreads, smem, s>>>(k, zt->cells_rounded);
+  opd::count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+extern "C" int opd_zone_histogram(const int32_t* zone_idx_dev, const uint64_t* zone_mask_dev, const int32_t* slot_dev,
+                                  int64_t N, int32_t Z, int32_t T, int32_t* hist_dev, void* stream) {
+  OPD_REQUIRE((zone_idx_dev != nullptr) != (zone_mask_dev != nullptr), "opd_zone_histogram: pass exactly one of zone_idx / zone_mask");
+  OPD_REQUIRE(hist_dev && Z >= 0 && T >= 1 && N >= 0, "opd_zone_histogram: bad argument");
+  OPD_REQUIRE(zone_idx_dev || Z <= OPD_MAX_ZONES, "opd_zone_histogram: a mask covers at most %d zones", OPD_MAX_ZONES);
+  if (N == 0) return OPD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)std::min<long long>((N + threads - 1) / threads, 148 * 8);
+  zone_histogram_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(zone_idx_dev, zone_mask_dev, slot_dev,
+                                                                                  N, Z, T, hist_dev);
+  opd::count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}

@@ -1,0 +1,45 @@
+// Shared host-side helpers of libopd_b200.so: thread-local error string, CUDA error mapping,
+// kernel-launch counter.  Nothing here is part of the C ABI (see include/opd_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "opd_b200.h"
+
+namespace opd {
+
+std::string& last_error_ref();
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace opd
+
+#define OPD_CUDA_OK(expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return opd::fail(OPD_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,                  \
+                       cudaGetErrorString(_e));                                                    \
+  } while (0)
+
+#define OPD_REQUIRE(cond, ...)                                                                     \
+  do {                                                                                             \
+    if (!(cond)) return opd::fail(OPD_ERR_INVALID, __VA_ARGS__);                                   \
+  } while (0)
