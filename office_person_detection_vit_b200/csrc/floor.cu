@@ -32,7 +32,6 @@ constexpr int kBoundary = 255;          // grid byte of a boundary cell
 constexpr int kMaxClasses = 255;        // class ids 0..254
 constexpr int kGridCellBudget = 160 * 1024;
 constexpr int kMaxSmemVerts = 1024;     // polygons vertices staged in shared memory (16 KB)
-constexpr int kQueueCap = 8192;         // slow-path queue entries of the fast kernel
 constexpr int kFastThreads = 1024;
 constexpr int kFastPointsPerThread = 4;
 constexpr int kFastChunk = kFastThreads * kFastPointsPerThread;
@@ -284,6 +283,10 @@ __global__ void __launch_bounds__(256) floor_exact_kernel(const FloorK p, int ce
 
 // ---------------------------------------------------------------------------------------------------------
 // floor_fast_kernel: float32 points in, int32 zone index and/or row-0 histogram out.
+//
+// Work unit = 128 consecutive points per warp and iteration (lane l owns points 4l..4l+3: two 16-byte loads,
+// one 16-byte store).  Warps never synchronise with each other inside the loop: every warp owns a private
+// slow-path queue in shared memory and drains it, 32 points at a time, through the float64 exact path.
 // ---------------------------------------------------------------------------------------------------------
 struct WarpCounter {
   unsigned m[5];   // m[k] = lane bit k set ? 0 : ~0  (XOR mask so that (ballot ^ m) selects "bit k equals mine")
@@ -294,15 +297,20 @@ struct WarpCounter {
     c0 = c1 = 0;
   }
   // zi < 0: not counted here.  All 32 lanes must call.
+  template <bool kWide>
   __device__ __forceinline__ void add(int zi) {
     const unsigned valid = __ballot_sync(0xffffffffu, zi >= 0);
     if (valid == 0) return;
     unsigned common = valid;
 #pragma unroll
     for (int k = 0; k < 5; ++k) common &= __ballot_sync(0xffffffffu, (zi >> k) & 1) ^ m[k];
-    const unsigned hi = __ballot_sync(0xffffffffu, (zi >> 5) & 1);
-    c0 += __popc(common & ~hi);
-    c1 += __popc(common & hi);
+    if (kWide) {
+      const unsigned hi = __ballot_sync(0xffffffffu, (zi >> 5) & 1);
+      c0 += __popc(common & ~hi);
+      c1 += __popc(common & hi);
+    } else {
+      c0 += __popc(common);
+    }
   }
 };
 
@@ -314,81 +322,106 @@ __device__ __forceinline__ float4 ldg_stream(const float4* ptr) {
   return r;
 }
 
-// float32 filter: returns the class code of the point's cell (0..254), or -1 when the point must take the
-// float64 path (error bound too large, non-finite, or boundary cell), or -2 when it is certainly outside the grid.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// float32 filter.  Returns the class code of the point's cell (0..254), -1 when the point must take the float64
+// path, -2 when it is certainly in no zone (outside the grid by more than its error bound).
+//
+// Error bound (u = 2^-24): X̂, Ŷ, Ŵ carry <= 4u·S (two fma roundings + the float32 rounding of H), the
+// approximate reciprocal 2u and the products u, hence
+//   |p̂ - p| <= 16u·(|r̂|·(Sxy + max|p̂|·Sw) + max|p̂|)        (constants rounded up generously)
+// with Sxy >= |H0·|(|x|,|y|,1), |H1·|(...), Sw = |H2·|(|x|,|y|,1).
 __device__ __forceinline__ int filter_point(const FloorK& p, const uint8_t* s_grid, float x, float y) {
   const float X = fmaf(p.Hf[0], x, fmaf(p.Hf[1], y, p.Hf[2]));
   const float Y = fmaf(p.Hf[3], x, fmaf(p.Hf[4], y, p.Hf[5]));
   const float W = fmaf(p.Hf[6], x, fmaf(p.Hf[7], y, p.Hf[8]));
-  const float r = __frcp_rn(W);
+  const float r = rcp_approx(W);
   const float px = X * r, py = Y * r;
-  // |X̂ - X| <= 8u·Sxy, |Ŵ - W| <= 8u·Sw (3 roundings + float32 rounding of H, u = 2^-24), so
-  // |p̂ - p| <= 16u·|r|·(Sxy + max|p̂|·Sw) + 16u·max|p̂|   (constant doubled for the reciprocal / product roundings)
   const float ax = fabsf(x), ay = fabsf(y);
   const float sxy = fmaf(p.Sxy[0], ax, fmaf(p.Sxy[1], ay, p.Sxy[2]));
   const float sw = fmaf(p.Sw[0], ax, fmaf(p.Sw[1], ay, p.Sw[2]));
   const float pm = fmaxf(fabsf(px), fabsf(py));
-  const float c = 16.0f * 5.9604645e-8f;
-  const float err = c * fmaf(fabsf(r), fmaf(pm, sw, sxy), pm);
-  if (!(err <= p.err_max)) return -1;  // also catches NaN / inf
+  const float err = (16.0f * 5.9604645e-8f) * fmaf(fabsf(r), fmaf(pm, sw, sxy), pm);
+  // grid coordinates of p̂ and of its error box (cells)
   const float fx = (px - p.gx0_f) * p.inv_cw_f;
   const float fy = (py - p.gy0_f) * p.inv_ch_f;
-  if (!(fx >= 0.0f && fx < (float)p.gw && fy >= 0.0f && fy < (float)p.gh)) return -2;
+  const float ex = err * p.inv_cw_f, ey = err * p.inv_ch_f;
+  if (fx + ex < -1.0f || fx - ex > (float)(p.gw + 1) || fy + ey < -1.0f || fy - ey > (float)(p.gh + 1))
+    return -2;                        // the whole error box misses the (margin-padded) grid: no zone
+  if (!(err <= p.err_max)) return -1; // bound too loose (near the horizon), NaN or inf: exact path decides
+  if (!(fx >= 0.0f && fx < (float)p.gw && fy >= 0.0f && fy < (float)p.gh))
+    return -2;                        // within err_max of the grid border, which lies >= 1 px outside every polygon
   const int code = s_grid[(int)fy * p.gw + (int)fx];
   return code == kBoundary ? -1 : code;
 }
 
+constexpr int kWarpQueue = 256;  // entries per warp (a unit adds at most 128)
+
+template <bool kWide>
 __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const FloorK p, int cells_rounded) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemTables t = stage_tables(p, smem, cells_rounded);
   unsigned char* cur = smem + (tables_smem_bytes(1, cells_rounded, p.stage_verts, p.n_verts) + 15) / 16 * 16;
-  unsigned* s_queue = reinterpret_cast<unsigned*>(cur);
-  cur += kQueueCap * 4;
-  unsigned* s_hist = reinterpret_cast<unsigned*>(cur);  // [64]
-  unsigned* s_qcount = s_hist + 64;
+  unsigned* s_queue = reinterpret_cast<unsigned*>(cur);  // [32 warps][kWarpQueue]
+  cur += (kFastThreads / 32) * kWarpQueue * 4;
+  unsigned* s_hist = reinterpret_cast<unsigned*>(cur);   // [64]
   if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
-  if (threadIdx.x == 0) *s_qcount = 0;
   __syncthreads();
 
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1;
+  unsigned* q = s_queue + warp * kWarpQueue;
+  unsigned qn = 0;  // warp-uniform
   const bool do_hist = p.hist != nullptr;
   WarpCounter wc;
   wc.init(lane);
 
   const float* in = static_cast<const float*>(p.in);
-  const long long n_chunks = (p.N + kFastChunk - 1) / kFastChunk;
+  const float2* in2 = reinterpret_cast<const float2*>(in);
 
-  auto drain = [&]() {
-    // dense float64 pass over the queued points
-    const unsigned n = *s_qcount;
-    for (unsigned k0 = 0; k0 < n; k0 += kFastThreads) {
-      const unsigned k = k0 + threadIdx.x;
+  auto drain = [&](unsigned keep) {
+    // float64 pass over this warp's queued points, 32 at a time, until at most `keep` remain
+    while (qn > keep) {
+      const unsigned take = qn < 32u ? qn : 32u;
+      qn -= take;
       int win = -1;
-      bool live = k < n;
-      if (live) {
-        const unsigned i = s_queue[k];
-        const float2 xy = reinterpret_cast<const float2*>(in)[i];
+      if ((unsigned)lane < take) {
+        const unsigned i = q[qn + lane];
+        const float2 xy = in2[i];
         double px, py;
         project_exact(p, (double)xy.x, (double)xy.y, &px, &py);
         classify_exact(p, t, px, py, &win);
         if (p.zone_idx) p.zone_idx[i] = win;
       }
-      if (do_hist) wc.add(live ? win : -1);
+      __syncwarp();
+      if (do_hist) wc.add<kWide>(win);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) *s_qcount = 0;
-    __syncthreads();
   };
 
-  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const long long base = chunk * kFastChunk + (long long)threadIdx.x * kFastPointsPerThread;
+  const long long n_units = (p.N + 127) / 128;
+  const long long w_stride = (long long)gridDim.x * (kFastThreads / 32);
+  long long unit = (long long)blockIdx.x * (kFastThreads / 32) + warp;
+  // software prefetch: the next unit's two 16-byte loads are in flight while this unit is processed
+  float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+  auto prefetch = [&](long long u) {
+    const long long base = u * 128 + lane * 4;
+    if (u < n_units && base + 4 <= p.N) {
+      na = ldg_stream(reinterpret_cast<const float4*>(in + 2 * base));
+      nb = ldg_stream(reinterpret_cast<const float4*>(in + 2 * base) + 1);
+    }
+  };
+  prefetch(unit);
+  for (; unit < n_units; unit += w_stride) {
+    const long long base = unit * 128 + lane * 4;
     float xs[4], ys[4];
     int n_live;
     if (base + 4 <= p.N) {
-      const float4 a = ldg_stream(reinterpret_cast<const float4*>(in + 2 * base));
-      const float4 b = ldg_stream(reinterpret_cast<const float4*>(in + 2 * base) + 1);
-      xs[0] = a.x; ys[0] = a.y; xs[1] = a.z; ys[1] = a.w;
-      xs[2] = b.x; ys[2] = b.y; xs[3] = b.z; ys[3] = b.w;
+      xs[0] = na.x; ys[0] = na.y; xs[1] = na.z; ys[1] = na.w;
+      xs[2] = nb.x; ys[2] = nb.y; xs[3] = nb.z; ys[3] = nb.w;
       n_live = 4;
     } else {
       n_live = base < p.N ? (int)(p.N - base) : 0;
@@ -398,21 +431,19 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
         ys[j] = j < n_live ? in[2 * (base + j) + 1] : 0.f;
       }
     }
+    prefetch(unit + w_stride);
     int zi[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int code = j < n_live ? filter_point(p, t.grid, xs[j], ys[j]) : -2;
+      const int code = j < n_live ? filter_point(p, t.grid, xs[j], ys[j]) : -2;
       const bool slow = code == -1;
-      // queue push, one shared-memory atomic per warp
       const unsigned sb = __ballot_sync(0xffffffffu, slow);
       if (sb) {
-        unsigned pos = 0;
-        if (lane == 0) pos = atomicAdd(s_qcount, __popc(sb));
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (slow) s_queue[pos + __popc(sb & ((1u << lane) - 1))] = (unsigned)(base + j);
+        if (slow) q[qn + __popc(sb & lt_mask)] = (unsigned)(base + j);
+        qn += __popc(sb);
       }
       zi[j] = code >= 0 ? t.class_winner[code] : -1;
-      if (do_hist) wc.add(zi[j]);
+      if (do_hist) wc.add<kWide>(zi[j]);
     }
     if (p.zone_idx) {
       if (n_live == 4) {
@@ -421,17 +452,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
         for (int j = 0; j < n_live; ++j) p.zone_idx[base + j] = zi[j];
       }
     }
-    __syncthreads();  // queue count visible; also orders the placeholder stores before the drain's stores
-    const unsigned queued = *s_qcount;
-    __syncthreads();  // everyone has read the count before the next iteration's pushes can change it
-    if (queued > kQueueCap - kFastChunk) drain();
+    __syncwarp();  // queue entries and placeholder stores are ordered before the drain's loads / stores
+    if (qn > kWarpQueue - 128) drain(kWarpQueue - 128 - 32);
   }
-  __syncthreads();
-  drain();
+  __syncwarp();
+  drain(0);
 
   if (do_hist) {
     atomicAdd(&s_hist[lane], wc.c0);
-    atomicAdd(&s_hist[lane + 32], wc.c1);
+    if (kWide) atomicAdd(&s_hist[lane + 32], wc.c1);
     __syncthreads();
     // classified counts go to their bins; bin Z receives (points handled) - (classified), summed over CTAs
     if (threadIdx.x < 64 && threadIdx.x < p.Z && s_hist[threadIdx.x]) {
@@ -821,11 +850,12 @@ extern "C" int opd_floor_project_classify_count_f32(const opd_floor_params* p, c
   if (int rc = device_sm_count(zt->device, &sms)) return rc;
   k.stage_grid = 1;
   const size_t smem = (tables_smem_bytes(1, zt->cells_rounded, k.stage_verts, k.n_verts) + 15) / 16 * 16 +
-                      kQueueCap * 4 + 64 * 4 + 16;
-  OPD_CUDA_OK(cudaFuncSetAttribute(floor_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                      (kFastThreads / 32) * kWarpQueue * 4 + 64 * 4 + 16;
+  auto kern = zt->Z > 32 ? floor_fast_kernel<true> : floor_fast_kernel<false>;
+  OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long chunks = (N + kFastChunk - 1) / kFastChunk;
   const unsigned blocks = (unsigned)std::min<long long>(chunks, sms);
-  floor_fast_kernel<<<blocks, kFastThreads, smem, s>>>(k, zt->cells_rounded);
+  kern<<<blocks, kFastThreads, smem, s>>>(k, zt->cells_rounded);
   opd::count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

@@ -119,10 +119,12 @@ def test_fast_kernel_matches_oracle(Z, kind, torch_cuda, built_lib):
     hist2 = zc.count(d_pts, transformer=tr)
     assert torch.equal(hist, hist2)
     # exact kernel (forced by asking for masks) agrees with the fast kernel
-    idx_exact = zc.classify_masks(d_pts, transformer=tr)
-    win = torch.where(idx_exact == 0, torch.full_like(idx_exact, -1),
-                      (idx_exact & -idx_exact).double().log2().round().long())
-    assert (win.cpu().numpy() == idx).all()
+    masks = zc.classify_masks(d_pts, transformer=tr).cpu().numpy().astype(np.uint64)
+    win = np.full(n, -1, dtype=np.int32)
+    for z in range(Z):
+        win[masks == np.uint64(1 << z)] = z
+    assert ((masks & (masks - np.uint64(1))) == 0).all()   # single-label table: at most one bit
+    assert (win == idx).all()
 
 
 def test_fast_kernel_ragged_tail_and_idempotence(torch_cuda, built_lib):
