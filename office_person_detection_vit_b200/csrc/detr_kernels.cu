@@ -1,0 +1,597 @@
+// The non-GEMM kernels of the DETR-ResNet-50 detector: preprocessing (K1), uint8 resize, max pooling (K3), sine
+// positional embedding (K7), multi-head attention (K6), prediction heads and post-processing (K8).
+// Reference arithmetic: third-party `transformers` (file:line map in oracle/detr_oracle.py) and the reference's
+// src/detection/yolov8_detector.py:210-225, 229-241 (xyxy -> xywh, foot point).
+#include "detr_kernels.h"
+
+#include <cmath>
+
+#include "opd_common.h"
+
+namespace opd {
+
+namespace {
+
+constexpr int kD = 256;        // d_model
+constexpr int kHeadDim = 32;
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float lo_f(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float hi_f(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// ------------------------------------------------------------------------------------------------------------
+// K1 preprocess.  One thread per (b, y, x, kw): 12 normalised values + 4 zeros = 32 bytes, fully coalesced.
+// normalise: (u8 - 255*mean) / (255*std) in fp32 (image_processing_backends.py:308-331), then bf16.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void preprocess_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, int bgr,
+                                  __nv_bfloat16* __restrict__ x2, int H2, int W2) {
+  const float mean[3] = {0.485f * 255.0f, 0.456f * 255.0f, 0.406f * 255.0f};
+  const float stdv[3] = {0.229f * 255.0f, 0.224f * 255.0f, 0.225f * 255.0f};
+  const long long total = (long long)B * H2 * W2 * 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kw = (int)(i & 3);
+    long long r = i >> 2;
+    const int x = (int)(r % W2);
+    r /= W2;
+    const int y = (int)(r % H2);
+    const int b = (int)(r / H2);
+    const int sx = x + kw - 2;   // space-to-depth column this lane group holds
+    float v[12];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = 2 * y + dy, ix = 2 * sx + dx;
+        const bool ok = sx >= 0 && iy < Hs && ix < Ws && ix >= 0;
+        const uint8_t* px = src + (((long long)b * Hs + (ok ? iy : 0)) * Ws + (ok ? ix : 0)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float u = (float)px[bgr ? 2 - c : c];
+          v[(dy * 2 + dx) * 3 + c] = ok ? (u - mean[c]) / stdv[c] : 0.f;
+        }
+      }
+    uint4 o0, o1;
+    o0.x = pack2(v[0], v[1]); o0.y = pack2(v[2], v[3]); o0.z = pack2(v[4], v[5]); o0.w = pack2(v[6], v[7]);
+    o1.x = pack2(v[8], v[9]); o1.y = pack2(v[10], v[11]); o1.z = 0u; o1.w = 0u;
+    uint4* dst = reinterpret_cast<uint4*>(x2 + i * 16);
+    dst[0] = o0;
+    dst[1] = o1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// uint8 antialias bilinear resize (separable, fixed point), ATen UpSampleKernel.cpp restated:
+//   out = clamp((2^(p-1) + sum_j src[x0 + j] * w[j]) >> p, 0, 255), horizontal pass first, then vertical.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void resize_h_kernel(const uint8_t* __restrict__ src, int B, int H0, int W0, int bgr,
+                                uint8_t* __restrict__ tmp, int W1, const int16_t* __restrict__ wx,
+                                const int32_t* __restrict__ x0, int kx, int px) {
+  const long long total = (long long)B * H0 * W1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % W1);
+    const long long row = i / W1;   // b * H0 + y
+    const uint8_t* s = src + (row * W0 + x0[ox]) * 3;
+    int acc[3] = {1 << (px - 1), 1 << (px - 1), 1 << (px - 1)};
+    for (int j = 0; j < kx; ++j) {
+      const int w = wx[ox * kx + j];
+      if (w == 0) continue;       // padding taps may point past the row end
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += (int)s[j * 3 + c] * w;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int v = min(max(acc[bgr ? 2 - c : c] >> px, 0), 255);
+      tmp[i * 3 + c] = (uint8_t)v;   // RGB from here on
+    }
+  }
+}
+
+__global__ void resize_v_kernel(const uint8_t* __restrict__ tmp, int B, int H0, int W1, uint8_t* __restrict__ dst,
+                                int H1, const int16_t* __restrict__ wy, const int32_t* __restrict__ y0, int ky, int py) {
+  const long long total = (long long)B * H1 * W1 * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int xc = (int)(i % (W1 * 3));
+    long long r = i / (W1 * 3);
+    const int oy = (int)(r % H1);
+    const int b = (int)(r / H1);
+    const uint8_t* s = tmp + ((long long)b * H0 + y0[oy]) * W1 * 3 + xc;
+    int acc = 1 << (py - 1);
+    for (int j = 0; j < ky; ++j) {
+      const int w = wy[oy * ky + j];
+      if (w != 0) acc += (int)s[(long long)j * W1 * 3] * w;
+    }
+    dst[i] = (uint8_t)min(max(acc >> py, 0), 255);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3 max pooling 3x3 / s2 / p1 on NHWC bf16; one thread per (pixel, 8 channels)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C,
+                               __nv_bfloat16* __restrict__ y, int P, int Q) {
+  const int c8 = C / 8;
+  const long long total = (long long)B * P * Q * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8);
+    long long r = i / c8;
+    const int q = (int)(r % Q);
+    r /= Q;
+    const int p = (int)(r % P);
+    const int b = (int)(r / P);
+    __nv_bfloat162 m[4];
+    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = ninf;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = 2 * p - 1 + dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = 2 * q - 1 + dx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + iy) * W + ix) * C) + cg);
+        const __nv_bfloat162* vv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], vv[k]);
+      }
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&m[0]);
+    o.y = *reinterpret_cast<uint32_t*>(&m[1]);
+    o.z = *reinterpret_cast<uint32_t*>(&m[2]);
+    o.w = *reinterpret_cast<uint32_t*>(&m[3]);
+    reinterpret_cast<uint4*>(y + (((long long)b * P + p) * Q + q) * C)[cg] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K7 sine positional embedding (modeling_detr.py:322-349, all-ones mask): pos[y*w + x, 0:128] from y, [128:256] from x
+// ------------------------------------------------------------------------------------------------------------
+__global__ void pos_embed_kernel(float* __restrict__ pos, int h, int w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w * kD) return;
+  const int c = i % kD, t = i / kD;
+  const int x = t % w, y = t / w;
+  const bool from_y = c < 128;
+  const int k = from_y ? c : c - 128;
+  const float scale = 6.283185307179586f;   // 2*pi rounded to float32, like torch's python-float * tensor
+  const float embed = from_y ? ((float)(y + 1) / ((float)h + 1e-6f)) * scale : ((float)(x + 1) / ((float)w + 1e-6f)) * scale;
+  // dim_t = 10000 ** (2 * (k // 2) / 128)   (float32 pow of a float32 exponent)
+  const float dim_t = powf(10000.0f, (float)(2 * (k / 2)) / 128.0f);
+  const float v = embed / dim_t;
+  pos[i] = (k & 1) ? cosf(v) : sinf(v);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6 attention.  CTA = 4 warps x 16 query rows; keys/values stream through shared memory in tiles of 64 via
+// cp.async double buffering; S = Q K^T and O += P V on mma.sync m16n8k16 (bf16 in, fp32 accumulate); online
+// softmax in fp32 with exp2.  (A tcgen05 version is the next step for this kernel; see DESIGN.md.)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kKvTile = 64;
+constexpr int kKvPitch = 40;   // bf16 elements per smem row (80 B): conflict-free fragment loads
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, bool valid) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;   // src-size 0 -> 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(s));
+}
+
+__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
+                                                        const __nv_bfloat16* __restrict__ k, long long ldk,
+                                                        const __nv_bfloat16* __restrict__ v, long long ldv,
+                                                        __nv_bfloat16* __restrict__ o, long long ldo, int Lq, int Lk) {
+  __shared__ __align__(16) __nv_bfloat16 s_k[2][kKvTile][kKvPitch];
+  __shared__ __align__(16) __nv_bfloat16 s_v[2][kKvTile][kKvPitch];
+
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * 64 + warp * 16;
+
+  const __nv_bfloat16* qb = q + (long long)b * Lq * ldq + head * kHeadDim;
+  const __nv_bfloat16* kb = k + (long long)b * Lk * ldk + head * kHeadDim;
+  const __nv_bfloat16* vb = v + (long long)b * Lk * ldv + head * kHeadDim;
+
+  // Q fragments: rows q0+g and q0+g+8 (clamped), two k-steps of 16 dims
+  uint32_t qa[2][4];
+  {
+    const int r0 = min(q0 + g, Lq - 1), r1 = min(q0 + g + 8, Lq - 1);
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      qa[kk][0] = *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * ldq + kk * 16 + 2 * t);
+      qa[kk][1] = *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ldq + kk * 16 + 2 * t);
+      qa[kk][2] = *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * ldq + kk * 16 + 8 + 2 * t);
+      qa[kk][3] = *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ldq + kk * 16 + 8 + 2 * t);
+    }
+  }
+
+  auto load_tile = [&](int buf, int key0) {
+    // 64 rows x 4 chunks of 16 B for K and for V: 512 chunks, 4 per thread
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int c = threadIdx.x + it * 128;
+      const int row = c >> 2, ch = c & 3;
+      const bool ok = key0 + row < Lk;
+      const long long kr = ok ? key0 + row : 0;
+      cp_async_16(&s_k[buf][row][ch * 8], kb + kr * ldk + ch * 8, ok);
+      cp_async_16(&s_v[buf][row][ch * 8], vb + kr * ldv + ch * 8, ok);
+    }
+    cp_async_commit();
+  };
+
+  float oacc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
+
+  const int n_tiles = (Lk + kKvTile - 1) / kKvTile;
+  load_tile(0, 0);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < n_tiles) {
+      load_tile(buf ^ 1, (tile + 1) * kKvTile);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    // S = Q K^T : 8 key tiles of 8
+    float sacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&s_k[buf][8 * j + g][kk * 16 + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&s_k[buf][8 * j + g][kk * 16 + 8 + 2 * t]);
+        mma_bf16_16816(sacc[j], qa[kk], b0, b1);
+      }
+    }
+    // mask keys past Lk (only the last tile)
+    const int key0 = tile * kKvTile;
+    if (key0 + kKvTile > Lk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kc = key0 + 8 * j + 2 * t;
+        if (kc >= Lk) sacc[j][0] = sacc[j][2] = -INFINITY;
+        if (kc + 1 >= Lk) sacc[j][1] = sacc[j][3] = -INFINITY;
+      }
+    }
+    // online softmax (rows g and g+8)
+    float mx[2] = {mrow[0], mrow[1]};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mx[0] = fmaxf(mx[0], fmaxf(sacc[j][0], sacc[j][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(sacc[j][2], sacc[j][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float alpha[2], psum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      alpha[r] = exp2f((mrow[r] - mx[r]) * sl2);   // first tile: exp2(-inf) = 0
+      mrow[r] = mx[r];
+    }
+    uint32_t pa[4][4];   // P as A fragments: k-step ks covers keys 16ks..16ks+15
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f((sacc[j][0] - mx[0]) * sl2), p1 = exp2f((sacc[j][1] - mx[0]) * sl2);
+      const float p2 = exp2f((sacc[j][2] - mx[1]) * sl2), p3 = exp2f((sacc[j][3] - mx[1]) * sl2);
+      psum[0] += p0 + p1;
+      psum[1] += p2 + p3;
+      pa[j >> 1][(j & 1) * 2 + 0] = pack2(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack2(p2, p3);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) lrow[r] = lrow[r] * alpha[r] + psum[r];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      oacc[n][0] *= alpha[0];
+      oacc[n][1] *= alpha[0];
+      oacc[n][2] *= alpha[1];
+      oacc[n][3] *= alpha[1];
+    }
+    // O += P V : 4 k-steps (16 keys) x 4 dim tiles (8); V fragments by ldmatrix.trans, two dim tiles at a time
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t vb4[4];
+        const int mat = lane >> 3, rin = lane & 7;
+        ldmatrix_x4_trans(vb4, &s_v[buf][16 * ks + (mat & 1) * 8 + rin][8 * (2 * np + (mat >> 1))]);
+        mma_bf16_16816(oacc[2 * np], pa[ks], vb4[0], vb4[1]);
+        mma_bf16_16816(oacc[2 * np + 1], pa[ks], vb4[2], vb4[3]);
+      }
+    }
+    __syncthreads();   // everyone is done with `buf` before the next iteration's prefetch overwrites it
+  }
+
+  // finalise: row sums across the 4 lanes of a row, normalise, store
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+  const float inv0 = 1.f / lrow[0], inv1 = 1.f / lrow[1];
+  __nv_bfloat16* ob = o + (long long)b * Lq * ldo + head * kHeadDim;
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    if (q0 + g < Lq)
+      *reinterpret_cast<uint32_t*>(ob + (long long)(q0 + g) * ldo + 8 * n + 2 * t) =
+          pack2(oacc[n][0] * inv0, oacc[n][1] * inv0);
+    if (q0 + g + 8 < Lq)
+      *reinterpret_cast<uint32_t*>(ob + (long long)(q0 + g + 8) * ldo + 8 * n + 2 * t) =
+          pack2(oacc[n][2] * inv1, oacc[n][3] * inv1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// decoder helpers
+// ------------------------------------------------------------------------------------------------------------
+__global__ void decoder_init_kernel(__nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ yp,
+                                    const float* __restrict__ qpos, int B, int Q) {
+  const long long total = (long long)B * Q * kD;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    y[i] = __float2bfloat16(0.f);
+    yp[i] = __float2bfloat16(qpos[i % ((long long)Q * kD)]);
+  }
+}
+
+// one warp per row of 256: fp32 statistics (two-pass in registers)
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4 raw = *reinterpret_cast<const uint4*>(x + (long long)row * kD + lane * 8);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = lo_f(w[j]);
+    v[2 * j + 1] = hi_f(w[j]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += v[j];
+#pragma unroll
+  for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  const float mean = s * (1.f / kD);
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sq += (v[j] - mean) * (v[j] - mean);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+  const float rstd = rsqrtf(sq * (1.f / kD) + 1e-5f);
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane * 8 + 2 * j;
+    o[j] = pack2((v[2 * j] - mean) * rstd * gamma[c] + beta[c], (v[2 * j + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1]);
+  }
+  *reinterpret_cast<uint4*>(y + (long long)row * kD + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K8a heads: one CTA (256 threads) per decoder row; fp32 weights, fp32 math
+//   logits = y Wc^T + bc ; boxes = sigmoid(W2 relu(W1 relu(W0 y + b0) + b1) + b2)   (modeling_detr.py:1275-1297, 1401-1402)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ y, HeadWeights w,
+                                                    float* __restrict__ logits, float* __restrict__ boxes, int n_cls) {
+  __shared__ float s_y[kD], s_h0[kD], s_h1[kD];
+  const int row = blockIdx.x, j = threadIdx.x;
+  s_y[j] = __bfloat162float(y[(long long)row * kD + j]);
+  __syncthreads();
+  if (j < n_cls) {
+    float acc = 0.f;
+    for (int k = 0; k < kD; ++k) acc = fmaf(s_y[k], w.wc_t[k * n_cls + j], acc);
+    logits[(long long)row * n_cls + j] = acc + w.bc[j];
+  }
+  {
+    float acc = 0.f;
+    for (int k = 0; k < kD; ++k) acc = fmaf(s_y[k], w.w0_t[k * kD + j], acc);
+    s_h0[j] = fmaxf(acc + w.b0[j], 0.f);
+  }
+  __syncthreads();
+  {
+    float acc = 0.f;
+    for (int k = 0; k < kD; ++k) acc = fmaf(s_h0[k], w.w1_t[k * kD + j], acc);
+    s_h1[j] = fmaxf(acc + w.b1[j], 0.f);
+  }
+  __syncthreads();
+  const int warp = j >> 5, lane = j & 31;
+  if (warp < 4) {
+    float acc = 0.f;
+    for (int k = lane; k < kD; k += 32) acc = fmaf(s_h1[k], w.w2[warp * kD + k], acc);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) boxes[(long long)row * 4 + warp] = 1.f / (1.f + expf(-(acc + w.b2[warp])));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K8b post-processing: one CTA of 128 threads per frame, thread = query
+//   image_processing_detr.py:826-843 (softmax, best of the first C-1 classes, cxcywh -> xyxy, scale to pixels, threshold)
+//   + person filter, xyxy -> xywh and foot point (x + w/2, y + h) as in yolov8_detector.py:210-225, 229-241
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) postprocess_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
+                                                          int Q, int C, int H0, int W0, float threshold, int person_label,
+                                                          float* __restrict__ scores, int32_t* __restrict__ labels,
+                                                          float* __restrict__ xyxy, float* __restrict__ det_xywh,
+                                                          float* __restrict__ det_score, double* __restrict__ det_foot,
+                                                          int32_t* __restrict__ det_query, int32_t* __restrict__ n_keep) {
+  __shared__ int s_warp_count[4];
+  const int b = blockIdx.x, qi = threadIdx.x;
+  const int lane = qi & 31, warp = qi >> 5;
+  bool keep = false;
+  float sc = 0.f, x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+  if (qi < Q) {
+    const float* lg = logits + ((long long)b * Q + qi) * C;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, lg[c]);
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(lg[c] - mx);
+    int best = 0;
+    float bestv = -INFINITY;
+    for (int c = 0; c < C - 1; ++c)
+      if (lg[c] > bestv) {   // first maximum, like torch.max
+        bestv = lg[c];
+        best = c;
+      }
+    sc = expf(bestv - mx) / sum;
+    const float* bx = boxes + ((long long)b * Q + qi) * 4;
+    const float cx = bx[0], cy = bx[1], bw = bx[2], bh = bx[3];
+    x1 = (cx - 0.5f * bw) * (float)W0;
+    y1 = (cy - 0.5f * bh) * (float)H0;
+    x2 = (cx + 0.5f * bw) * (float)W0;
+    y2 = (cy + 0.5f * bh) * (float)H0;
+    const long long r = (long long)b * Q + qi;
+    scores[r] = sc;
+    labels[r] = best;
+    xyxy[r * 4 + 0] = x1; xyxy[r * 4 + 1] = y1; xyxy[r * 4 + 2] = x2; xyxy[r * 4 + 3] = y2;
+    keep = sc > threshold && best == person_label;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) s_warp_count[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0;
+  for (int wq = 0; wq < warp; ++wq) base += s_warp_count[wq];
+  if (keep) {
+    const int slot = base + __popc(bal & ((1u << lane) - 1));
+    const long long r = (long long)b * Q + slot;
+    const double dx1 = x1, dy1 = y1, dw = (double)x2 - (double)x1, dh = (double)y2 - (double)y1;
+    det_xywh[r * 4 + 0] = x1;
+    det_xywh[r * 4 + 1] = y1;
+    det_xywh[r * 4 + 2] = (float)dw;
+    det_xywh[r * 4 + 3] = (float)dh;
+    det_score[r] = sc;
+    det_foot[r * 2 + 0] = dx1 + dw / 2.0;   // python floats in the reference: float64
+    det_foot[r * 2 + 1] = dy1 + dh;
+    det_query[r] = qi;
+  }
+  if (qi == 0) n_keep[b] = s_warp_count[0] + s_warp_count[1] + s_warp_count[2] + s_warp_count[3];
+}
+
+int grid_for(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+int launch_preprocess(const uint8_t* src, int B, int Hs, int Ws, int src_is_bgr, __nv_bfloat16* x2, cudaStream_t s) {
+  const int H2 = (Hs + 1) / 2, W2 = (Ws + 1) / 2;
+  const long long total = (long long)B * H2 * W2 * 4;
+  preprocess_kernel<<<grid_for(total, 256), 256, 0, s>>>(src, B, Hs, Ws, src_is_bgr, x2, H2, W2);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_resize_u8(const uint8_t* src, int B, int H0, int W0, int src_is_bgr, uint8_t* tmp, uint8_t* dst, int H1,
+                     int W1, const int16_t* wx, const int32_t* x0, int kx, int px, const int16_t* wy, const int32_t* y0,
+                     int ky, int py, cudaStream_t s) {
+  resize_h_kernel<<<grid_for((long long)B * H0 * W1, 256), 256, 0, s>>>(src, B, H0, W0, src_is_bgr, tmp, W1, wx, x0, kx, px);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  resize_v_kernel<<<grid_for((long long)B * H1 * W1 * 3, 256), 256, 0, s>>>(tmp, B, H0, W1, dst, H1, wy, y0, ky, py);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_maxpool(const __nv_bfloat16* x, int B, int H, int W, int C, __nv_bfloat16* y, int P, int Q, cudaStream_t s) {
+  OPD_REQUIRE(C % 8 == 0, "maxpool: C=%d must be a multiple of 8", C);
+  const long long total = (long long)B * P * Q * (C / 8);
+  maxpool_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, B, H, W, C, y, P, Q);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_pos_embed(float* pos, int h, int w, cudaStream_t s) {
+  const int total = h * w * kD;
+  pos_embed_kernel<<<(total + 255) / 256, 256, 0, s>>>(pos, h, w);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_attention(const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v,
+                     int64_t ldv, __nv_bfloat16* o, int64_t ldo, int B, int heads, int Lq, int Lk, cudaStream_t s) {
+  OPD_REQUIRE(Lq > 0 && Lk > 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldq % 2 == 0 && ldo % 2 == 0, "attention: bad strides");
+  dim3 grid((Lq + 63) / 64, heads, B);
+  attention_kernel<<<grid, 128, 0, s>>>(q, ldq, k, ldk, v, ldv, o, ldo, Lq, Lk);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_decoder_init(__nv_bfloat16* y, __nv_bfloat16* yp, const float* qpos, int B, int Q, cudaStream_t s) {
+  decoder_init_kernel<<<grid_for((long long)B * Q * kD, 256), 256, 0, s>>>(y, yp, qpos, B, Q);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_layernorm(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, int rows,
+                     cudaStream_t s) {
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, rows);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_heads(const __nv_bfloat16* y, const HeadWeights& w, float* logits, float* boxes, int rows, cudaStream_t s) {
+  heads_kernel<<<rows, 256, 0, s>>>(y, w, logits, boxes, 92);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_postprocess(const float* logits, const float* boxes, int B, int Q, int C, int H0, int W0, float threshold,
+                       int person_label, float* scores, int32_t* labels, float* xyxy, float* det_xywh, float* det_score,
+                       double* det_foot, int32_t* det_query, int32_t* n_keep, cudaStream_t s) {
+  OPD_REQUIRE(Q <= 128, "postprocess: at most 128 queries per frame (got %d)", Q);
+  postprocess_kernel<<<B, 128, 0, s>>>(logits, boxes, Q, C, H0, W0, threshold, person_label, scores, labels, xyxy,
+                                       det_xywh, det_score, det_foot, det_query, n_keep);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+}  // namespace opd

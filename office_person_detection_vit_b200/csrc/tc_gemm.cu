@@ -1,0 +1,539 @@
+// K4 / K5: bf16 GEMM and implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators
+// in TMEM), operands staged in shared memory by TMA (tiled mode for matrices, im2col mode for NHWC activations),
+// fused epilogues (bias, ReLU, residual add, LayerNorm, positional add) and TMA stores.
+//
+// Arithmetic this replaces (third-party `transformers`, see oracle/detr_oracle.py for the file:line map):
+//   ResNet-50 bottleneck convolutions + frozen BN (+ReLU, +residual), input_projection, every Linear of the
+//   encoder / decoder layers, the post-attention and post-FFN residual + LayerNorm.
+//
+// Kernel shape: persistent, one CTA per SM, 6 warps:
+//   warp 0   TMA producer (one lane)         global -> smem ring (kStages x [A 128x64 | B BLOCK_Nx64], 128B swizzle)
+//   warp 1   MMA issuer (one lane) + TMEM owner   4 x tcgen05.mma (128 x BLOCK_N x 16) per ring slot
+//   warps 2-5 epilogue: tcgen05.ld -> fp32 math -> bf16 -> swizzled smem staging -> TMA store (64-column boxes)
+// TMEM holds two accumulator stages (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "tc_gemm.h"
+
+#include <algorithm>
+#include <mutex>
+
+#include "opd_common.h"
+#include "sm100_ptx.cuh"
+
+namespace opd {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                   // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int STAGING_BYTES = BLOCK_M * 64 * 2;   // one 64-column output box
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 232448;           // 227 KB
+
+__host__ __device__ constexpr int stages_for(int block_n) {
+  const int stage = A_STAGE_BYTES + block_n * BLOCK_K * 2;
+  const int n = (kSmemBudget - 2 * STAGING_BYTES - 2048) / stage;
+  return n > 8 ? 8 : n;
+}
+__host__ __device__ constexpr int smem_bytes_for(int block_n) {
+  return stages_for(block_n) * (A_STAGE_BYTES + block_n * BLOCK_K * 2) + 2 * STAGING_BYTES + 2048;
+}
+
+struct GemmParams {
+  CUtensorMap tmA, tmB, tmD, tmD2;
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int im2col;
+  int c_blocks;          // Cin / 64
+  int KW, stride, pad_h, pad_w, P, Q;
+  int epi;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  const float* gamma;
+  const float* beta;
+  const float* pos;
+  int pos_rows;
+  int has_d2;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int kStages = stages_for(BLOCK_N);
+  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N);
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
+  uint8_t* smem_out = smem_b + kStages * B_STAGE_BYTES;           // 2 staging boxes
+  float* s_bias = reinterpret_cast<float*>(smem_out + 2 * STAGING_BYTES);   // [BLOCK_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
+  uint64_t* full_bar = bars;                    // [kStages]
+  uint64_t* empty_bar = bars + kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * kStages;     // [2]
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B tiles need 1024-byte alignment
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmB);
+    ptx::prefetch_tmap(&p.tmD);
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        int base_w = 0, base_h = 0, img = 0;
+        if (p.im2col) {
+          const int pq = p.P * p.Q;
+          img = m0 / pq;
+          const int rem = m0 - img * pq;
+          const int op = rem / p.Q, oq = rem - op * p.Q;
+          base_w = oq * p.stride - p.pad_w;
+          base_h = op * p.stride - p.pad_h;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          if (p.im2col) {
+            const int tap = kb / p.c_blocks, cb = kb - tap * p.c_blocks;
+            const int r = tap / p.KW, s = tap - r * p.KW;
+            ptx::tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, cb * BLOCK_K, base_w,
+                                    base_h, img, (uint16_t)s, (uint16_t)r);
+          } else {
+            ptx::tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m0);
+          }
+          ptx::tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) start-address field
+            ptx::umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);   // frees the ring slot once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue (warps 2..5) =====================================
+    const int et = threadIdx.x - 64;            // 0..127
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;        // row of the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t box = 0;                           // running count of output boxes -> staging buffer parity
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+      const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+      const long long m = (long long)m0 + row;
+      const bool row_ok = m < p.M;
+      // bias tile -> smem (the previous tile's readers are past their last barrier)
+      for (int i = et; i < BLOCK_N; i += 128) s_bias[i] = p.bias ? p.bias[n0 + i] : 0.f;
+      ptx::named_bar_sync(1, 128);
+
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after_sync();
+      const uint32_t t_acc = tmem_base + lane_addr + acc * BLOCK_N;
+
+      float mean = 0.f, rstd = 0.f;
+      if (p.epi == EPI_BIAS_RES_LN) {
+        // pass A: v = acc + bias + residual, written back to TMEM; row statistics in fp32
+        float sum = 0.f, sq = 0.f;
+        for (int g = 0; g < BLOCK_N / 32; ++g) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_acc + g * 32, v);
+          ptx::tmem_ld_wait();
+          uint4 rr[4];
+          if (row_ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n0 + g * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rr[j] = __ldg(rp + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0, 0, 0, 0);
+          }
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(v[2 * j]) + s_bias[g * 32 + 2 * j] + ptx::bf16_lo(rw[j]);
+            const float b = __uint_as_float(v[2 * j + 1]) + s_bias[g * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]);
+            sum += a + b;
+            sq += a * a + b * b;
+            v[2 * j] = __float_as_uint(a);
+            v[2 * j + 1] = __float_as_uint(b);
+          }
+          ptx::tmem_st_32x32(t_acc + g * 32, v);
+        }
+        ptx::tmem_st_wait();
+        mean = sum * (1.f / BLOCK_N);
+        const float var = fmaxf(sq * (1.f / BLOCK_N) - mean * mean, 0.f);
+        rstd = rsqrtf(var + 1e-5f);
+      }
+
+      const int n_out = p.has_d2 ? 2 : 1;
+      for (int c = 0; c < BLOCK_N / 64; ++c) {
+        // this thread's 64 output values of the chunk, as fp32, then rounded to bf16 (kept for the D2 pass)
+        uint32_t packed[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int g = c * 2 + h;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_acc + g * 32, v);
+          ptx::tmem_ld_wait();
+          if (p.epi == EPI_BIAS_RES_LN) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = n0 + g * 32 + 2 * j;
+              const float a = (__uint_as_float(v[2 * j]) - mean) * rstd * __ldg(p.gamma + col) + __ldg(p.beta + col);
+              const float b =
+                  (__uint_as_float(v[2 * j + 1]) - mean) * rstd * __ldg(p.gamma + col + 1) + __ldg(p.beta + col + 1);
+              packed[h * 16 + j] = ptx::pack_bf16(a, b);
+            }
+          } else {
+            uint4 rr[4];
+            const bool has_res = p.epi == EPI_BIAS_RES_RELU;
+            if (has_res && row_ok) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n0 + g * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rr[j] = __ldg(rp + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0, 0, 0, 0);
+            }
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
+            const bool relu = p.epi != EPI_BIAS;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = __uint_as_float(v[2 * j]) + s_bias[g * 32 + 2 * j] + ptx::bf16_lo(rw[j]);
+              float b = __uint_as_float(v[2 * j + 1]) + s_bias[g * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]);
+              if (relu) {
+                a = fmaxf(a, 0.f);
+                b = fmaxf(b, 0.f);
+              }
+              packed[h * 16 + j] = ptx::pack_bf16(a, b);
+            }
+          }
+        }
+        for (int o = 0; o < n_out; ++o) {
+          if (o == 1) {
+            // D2 = bf16(D + pos[row % pos_rows]) computed from the ROUNDED D (oracle: act(x + pos))
+            const float* pp = p.pos + (long long)(row_ok ? (m % p.pos_rows) : 0) * p.N + n0 + c * 64;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(pp) + j);
+              packed[2 * j] = ptx::pack_bf16(ptx::bf16_lo(packed[2 * j]) + q.x, ptx::bf16_hi(packed[2 * j]) + q.y);
+              packed[2 * j + 1] =
+                  ptx::pack_bf16(ptx::bf16_lo(packed[2 * j + 1]) + q.z, ptx::bf16_hi(packed[2 * j + 1]) + q.w);
+            }
+          }
+          uint8_t* buf = smem_out + (box & 1) * STAGING_BYTES;
+          uint8_t* rowp = buf + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
+          ptx::fence_proxy_async_smem();
+          if (et == 0) ptx::tma_store_wait_read<0>();   // the other staging buffer is free after the barrier
+          ptx::named_bar_sync(1, 128);
+          if (et == 0) {
+            ptx::tma_store_2d(o == 0 ? &p.tmD : &p.tmD2, buf, n0 + c * 64, m0);
+            ptx::tma_store_commit();
+          }
+          ++box;
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (et == 0) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ----------------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+
+int load_driver_entry_points() {
+  static std::once_flag once;
+  static int rc = OPD_OK;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      rc = fail(OPD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+      return;
+    }
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    fn = nullptr;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      rc = fail(OPD_ERR_CUDA, "cuTensorMapEncodeIm2col is not available from the driver");
+      return;
+    }
+    g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  });
+  return rc;
+}
+
+// 2D bf16 matrix [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle
+int make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  if (int rc = load_driver_entry_points()) return rc;
+  OPD_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0,
+              "tensor map: base pointer and row pitch must be 16-byte aligned (ld=%llu)", (unsigned long long)ld);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(OPD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
+                (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+  return OPD_OK;
+}
+
+int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g) {
+  if (int rc = load_driver_entry_points()) return rc;
+  OPD_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && g.C % 64 == 0, "im2col map: C=%d must be a multiple of 64",
+              g.C);
+  cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+  // Base-pixel bounding box: the first output pixel reads from -pad, the last one from (out - 1) * stride - pad,
+  // which must equal extent + upper - 1 (for symmetric padding: upper = pad - (filter - 1), as in CUTLASS'
+  // conv/collective/detail.hpp compute_upper_corner_whd).
+  int lower[2] = {-g.pad_w, -g.pad_h};
+  auto upper_corner = [&](int extent, int out, int pad_lo, int k) {
+    const int sym = pad_lo - (k - 1);                                   // symmetric padding (CUTLASS formula)
+    if ((extent + sym + pad_lo - 1) / g.stride + 1 == out) return sym;
+    return (out - 1) * g.stride - pad_lo - (extent - 1);               // asymmetric: exact last base pixel
+  };
+  int upper[2] = {upper_corner(g.W, g.Q, g.pad_w, g.KW), upper_corner(g.H, g.P, g.pad_h, g.KH)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+  CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower,
+                               upper, /*channelsPerPixel=*/64, /*pixelsPerColumn=*/BLOCK_M, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(OPD_ERR_CUDA, "cuTensorMapEncodeIm2col failed (%d) B=%d H=%d W=%d C=%d k=%dx%d s=%d p=%d,%d", (int)r, g.B,
+                g.H, g.W, g.C, g.KH, g.KW, g.stride, g.pad_h, g.pad_w);
+  // Driver workaround carried by CUTLASS (cute/atom/copy_traits_sm90_im2col.hpp): for tensors smaller than
+  // 128 KiB, drivers <= 13.1 set a descriptor bit that makes im2col loads of the last pixels fault.
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  const uint64_t bytes = (uint64_t)g.B * g.H * g.W * g.C * 2;
+  if (drv <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return OPD_OK;
+}
+
+template <int BLOCK_N>
+int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
+  static bool configured = false;
+  auto kern = tc_gemm_kernel<BLOCK_N>;
+  if (!configured) {
+    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N)));
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, smem_bytes_for(BLOCK_N), s>>>(p);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int finish_plan(GemmPlan* plan) {
+  const int N = plan->N;
+  OPD_REQUIRE(N % 64 == 0 && plan->K % 64 == 0 && plan->M > 0, "gemm: N=%d and K=%d must be multiples of 64", N,
+              plan->K);
+  int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+  if (plan->epi == EPI_BIAS_RES_LN) OPD_REQUIRE(N == 256, "gemm: the LayerNorm epilogue needs N == 256 (got %d)", N);
+  // small problems: prefer more, narrower tiles so that every SM gets work
+  const long long m_blocks = (plan->M + BLOCK_M - 1) / BLOCK_M;
+  while (bn > 64 && plan->epi != EPI_BIAS_RES_LN && m_blocks * (N / bn) < sm_count() && N % (bn / 2) == 0) bn /= 2;
+  plan->block_n = bn;
+  const long long tiles = m_blocks * (N / bn);
+  plan->grid = (int)std::min<long long>(tiles, sm_count());
+  return OPD_OK;
+}
+
+}  // namespace
+
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int gemm_plan_linear(GemmPlan* plan, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, __nv_bfloat16* D,
+                     int64_t ldd, int M, int N, int K, int epi, const float* bias, const __nv_bfloat16* residual,
+                     int64_t ldr, const float* gamma, const float* beta, __nv_bfloat16* D2, const float* pos,
+                     int pos_rows) {
+  *plan = GemmPlan{};
+  plan->M = M; plan->N = N; plan->K = K; plan->im2col = 0; plan->epi = epi;
+  plan->bias = bias; plan->residual = residual; plan->ldr = (int)ldr;
+  plan->gamma = gamma; plan->beta = beta; plan->pos = pos; plan->pos_rows = pos_rows; plan->has_d2 = D2 != nullptr;
+  if (epi == EPI_BIAS_RES_RELU || epi == EPI_BIAS_RES_LN)
+    OPD_REQUIRE(residual && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && ldr % 8 == 0, "gemm: bad residual");
+  if (epi == EPI_BIAS_RES_LN) OPD_REQUIRE(gamma && beta, "gemm: LayerNorm epilogue needs gamma/beta");
+  if (D2) OPD_REQUIRE(pos && pos_rows > 0, "gemm: D2 needs pos");
+  if (int rc = finish_plan(plan)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmA, A, M, K, lda, BLOCK_M)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB, W, N, K, K, plan->block_n)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmD, D, M, N, ldd, BLOCK_M)) return rc;
+  if (D2) {
+    if (int rc = make_tmap_2d(&plan->tmD2, D2, M, N, ldd, BLOCK_M)) return rc;
+  } else {
+    plan->tmD2 = plan->tmD;
+  }
+  return OPD_OK;
+}
+
+int gemm_plan_conv(GemmPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* W, __nv_bfloat16* D,
+                   int N, int epi, const float* bias, const __nv_bfloat16* residual) {
+  *plan = GemmPlan{};
+  OPD_REQUIRE(g.P > 0 && g.Q > 0 && (g.P - 1) * g.stride - g.pad_h < g.H && (g.Q - 1) * g.stride - g.pad_w < g.W,
+              "conv: inconsistent output size");
+  OPD_REQUIRE(epi != EPI_BIAS_RES_LN, "conv: no LayerNorm epilogue");
+  plan->M = g.B * g.P * g.Q; plan->N = N; plan->K = g.KH * g.KW * g.C; plan->im2col = 1; plan->g = g; plan->epi = epi;
+  plan->bias = bias; plan->residual = residual; plan->ldr = N;
+  if (epi == EPI_BIAS_RES_RELU) OPD_REQUIRE(residual != nullptr, "conv: residual epilogue without a residual");
+  if (int rc = finish_plan(plan)) return rc;
+  if (int rc = make_tmap_im2col(&plan->tmA, x, g)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB, W, N, plan->K, plan->K, plan->block_n)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmD, D, plan->M, N, N, BLOCK_M)) return rc;
+  plan->tmD2 = plan->tmD;
+  return OPD_OK;
+}
+
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  GemmParams p;
+  p.tmA = plan.tmA; p.tmB = plan.tmB; p.tmD = plan.tmD; p.tmD2 = plan.tmD2;
+  p.M = plan.M; p.N = plan.N; p.K = plan.K;
+  p.num_m_blocks = (plan.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_blocks = plan.N / plan.block_n;
+  p.num_k_blocks = plan.K / BLOCK_K;
+  p.im2col = plan.im2col;
+  p.c_blocks = plan.im2col ? plan.g.C / BLOCK_K : 1;
+  p.KW = plan.g.KW; p.stride = plan.g.stride; p.pad_h = plan.g.pad_h; p.pad_w = plan.g.pad_w; p.P = plan.g.P; p.Q = plan.g.Q;
+  p.epi = plan.epi; p.bias = plan.bias; p.residual = plan.residual; p.ldr = plan.ldr;
+  p.gamma = plan.gamma; p.beta = plan.beta; p.pos = plan.pos; p.pos_rows = plan.pos_rows; p.has_d2 = plan.has_d2;
+  switch (plan.block_n) {
+    case 64: return launch_t<64>(p, plan.grid, stream);
+    case 128: return launch_t<128>(p, plan.grid, stream);
+    case 256: return launch_t<256>(p, plan.grid, stream);
+  }
+  return fail(OPD_ERR_INVALID, "gemm: unsupported block_n %d", plan.block_n);
+}
+
+}  // namespace opd
+
+// ----------------------------------------------------------------------------------------------------------
+// C ABI: the two building-block operators (also the unit-test surface of the tensor-core kernel)
+// ----------------------------------------------------------------------------------------------------------
+extern "C" int opd_gemm_bf16(const void* a_dev, int64_t lda, const void* w_dev, void* d_dev, int64_t ldd, int32_t M,
+                             int32_t N, int32_t K, int32_t epilogue, const float* bias_dev, const void* residual_dev,
+                             int64_t ldr, const float* gamma_dev, const float* beta_dev, void* d2_dev,
+                             const float* pos_dev, int32_t pos_rows, void* stream) {
+  opd::GemmPlan plan;
+  if (int rc = opd::gemm_plan_linear(&plan, static_cast<const __nv_bfloat16*>(a_dev), lda,
+                                     static_cast<const __nv_bfloat16*>(w_dev), static_cast<__nv_bfloat16*>(d_dev), ldd, M,
+                                     N, K, epilogue, bias_dev, static_cast<const __nv_bfloat16*>(residual_dev), ldr,
+                                     gamma_dev, beta_dev, static_cast<__nv_bfloat16*>(d2_dev), pos_dev, pos_rows))
+    return rc;
+  return opd::gemm_launch(plan, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int opd_conv2d_nhwc_bf16(const void* x_dev, int32_t B, int32_t H, int32_t W, int32_t C, const void* w_dev,
+                                    int32_t N, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t epilogue,
+                                    const float* bias_dev, const void* residual_dev, void* y_dev, void* stream) {
+  opd::ConvGeom g{B, H, W, C, KH, KW, stride, pad, pad, (H + 2 * pad - KH) / stride + 1, (W + 2 * pad - KW) / stride + 1};
+  opd::GemmPlan plan;
+  if (int rc = opd::gemm_plan_conv(&plan, static_cast<const __nv_bfloat16*>(x_dev), g,
+                                   static_cast<const __nv_bfloat16*>(w_dev), static_cast<__nv_bfloat16*>(y_dev), N,
+                                   epilogue, bias_dev, static_cast<const __nv_bfloat16*>(residual_dev)))
+    return rc;
+  return opd::gemm_launch(plan, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,403 @@
+"""CPU oracle of the DETR-ResNet-50 person detector (Phase 2 of the hot path).  TEST INFRASTRUCTURE ONLY:
+nothing under office_person_detection_vit_b200/ may import this module; only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs use it, as the checker or the timed CPU baseline.
+
+The reference's detector file (src/detection/vit_detector.py) is absent from the snapshot;
+its arithmetic lives in the third-party dependency `transformers` (pinned 4.57.3 in the reference's
+requirements.txt:220; 5.5.0 is what this image has, same architecture).  This module restates that published
+algorithm with plain torch functional ops, citing the transformers file:line each function follows
+(paths relative to site-packages/transformers/):
+
+    preprocess      models/detr/image_processing_detr.py:687-801, image_processing_backends.py:200-252,308-331,
+                    image_transforms.py:206-242
+    frozen BN       models/detr/modeling_detr.py:185-222
+    ResNet-50       models/resnet/modeling_resnet.py:40-240  (v1.5: stride on the 3x3, downsample_in_bottleneck=False)
+    sine pos-embed  models/detr/modeling_detr.py:300-349
+    attention       models/detr/modeling_detr.py:386-557
+    enc/dec layers  models/detr/modeling_detr.py:560-723, 929-1100
+    model forward   models/detr/modeling_detr.py:1142-1272
+    heads           models/detr/modeling_detr.py:1275-1297, 1401-1402
+    postprocess     models/detr/image_processing_detr.py:804-855, image_transforms.py:529-536
+    person filter + xyxy->xywh + foot point: the reference's surviving detector
+                    src/detection/yolov8_detector.py:210-225, 229-241
+
+Pinning: tests/test_detr_oracle.py checks `forward(mode="fp32")` against transformers' own
+DetrForObjectDetection + DetrImageProcessor on identical weights and frames (that IS the reference's
+arithmetic), and against the golden vectors committed under tests/golden/ (made by tests/golden/make_detr_golden.py).
+
+Two arithmetic modes:
+  "fp32"  the reference arithmetic (float32 everywhere);
+  "bf16"  float32 accumulation with the SAME bfloat16 rounding points as the CUDA path:
+          BN folded into the conv weights in float32 and then rounded to bf16, every stored activation rounded
+          to bf16, softmax / LayerNorm statistics / heads in float32.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+STAGE_DEPTHS = (3, 4, 6, 3)
+STAGE_WIDTHS = (256, 512, 1024, 2048)
+EMBED = 64
+D_MODEL = 256
+N_HEADS = 8
+FFN = 2048
+N_ENC = 6
+N_DEC = 6
+N_QUERIES = 100
+N_CLASSES = 91           # logits have N_CLASSES + 1 entries (last = "no object")
+PERSON_LABEL = 1         # COCO id of "person" in facebook/detr-resnet-50
+IMAGE_MEAN = (0.485, 0.456, 0.406)
+IMAGE_STD = (0.229, 0.224, 0.225)
+BN_EPS = 1e-5
+LN_EPS = 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------
+# weights
+# ------------------------------------------------------------------------------------------------------------
+def conv_specs():
+    """(hf_prefix, c_in, c_out, k, stride) of every backbone convolution, in execution order."""
+    specs = [("model.backbone.model.embedder.embedder", 3, EMBED, 7, 2)]
+    c_in = EMBED
+    for s, (depth, width) in enumerate(zip(STAGE_DEPTHS, STAGE_WIDTHS)):
+        mid = width // 4
+        for l in range(depth):
+            stride = 2 if (l == 0 and s > 0) else 1
+            p = f"model.backbone.model.encoder.stages.{s}.layers.{l}"
+            if l == 0:
+                specs.append((p + ".shortcut", c_in, width, 1, stride))
+            specs.append((p + ".layer.0", c_in, mid, 1, 1))
+            specs.append((p + ".layer.1", mid, mid, 3, stride))
+            specs.append((p + ".layer.2", mid, width, 1, 1))
+            c_in = width
+    return specs
+
+
+def make_weights(seed: int = 0) -> dict[str, torch.Tensor]:
+    """Seeded random-init DETR-R50 state dict (transformers key names, float32).
+
+    transformers' default init is degenerate for parity purposes (every query yields the same box, no score
+    crosses 0.5 — SURVEY.md H2), so the variances are re-scaled: He-init convolutions with non-trivial frozen-BN
+    statistics, unit-scale attention / FFN weights, wide query embeddings and heads.  Both sides of every
+    parity test load this same dict.
+    """
+    g = torch.Generator().manual_seed(seed)
+
+    def randn(*shape, std=1.0):
+        return torch.randn(*shape, generator=g, dtype=torch.float32) * std
+
+    def rand(*shape, lo=0.0, hi=1.0):
+        return torch.rand(*shape, generator=g, dtype=torch.float32) * (hi - lo) + lo
+
+    w: dict[str, torch.Tensor] = {}
+    for prefix, c_in, c_out, k, _stride in conv_specs():
+        fan_in = c_in * k * k
+        w[prefix + ".convolution.weight"] = randn(c_out, c_in, k, k, std=math.sqrt(2.0 / fan_in))
+        last_of_block = prefix.endswith(".layer.2")
+        scale = 0.35 if last_of_block else 1.0          # keep the residual stream from blowing up
+        w[prefix + ".normalization.weight"] = rand(c_out, lo=0.6, hi=1.4) * scale
+        w[prefix + ".normalization.bias"] = randn(c_out, std=0.1)
+        w[prefix + ".normalization.running_mean"] = randn(c_out, std=0.1)
+        w[prefix + ".normalization.running_var"] = rand(c_out, lo=0.6, hi=1.4)
+
+    w["model.input_projection.weight"] = randn(D_MODEL, STAGE_WIDTHS[-1], 1, 1, std=0.2 / math.sqrt(STAGE_WIDTHS[-1]))
+    w["model.input_projection.bias"] = randn(D_MODEL, std=0.1)
+    w["model.query_position_embeddings.weight"] = randn(N_QUERIES, D_MODEL, std=1.0)
+
+    def linear(prefix, n_out, n_in, std=None, bias_std=0.05):
+        w[prefix + ".weight"] = randn(n_out, n_in, std=std if std is not None else 1.0 / math.sqrt(n_in))
+        w[prefix + ".bias"] = randn(n_out, std=bias_std)
+
+    def layer_norm(prefix):
+        w[prefix + ".weight"] = rand(D_MODEL, lo=0.8, hi=1.2)
+        w[prefix + ".bias"] = randn(D_MODEL, std=0.05)
+
+    def attn(prefix, qk_gain=1.0, o_gain=1.0):
+        # qk_gain > 1 sharpens the softmax so that different queries attend to different tokens; o_gain < 1 keeps
+        # the residual stream token-specific (random post-norm attention stacks otherwise collapse to one token)
+        for proj in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            gain = qk_gain if proj in ("q_proj", "k_proj") else (o_gain if proj == "o_proj" else 1.0)
+            linear(f"{prefix}.{proj}", D_MODEL, D_MODEL, std=gain / math.sqrt(D_MODEL))
+
+    for i in range(N_ENC):
+        p = f"model.encoder.layers.{i}"
+        attn(p + ".self_attn", qk_gain=1.5, o_gain=0.3)
+        layer_norm(p + ".self_attn_layer_norm")
+        linear(p + ".mlp.fc1", FFN, D_MODEL)
+        linear(p + ".mlp.fc2", D_MODEL, FFN)
+        layer_norm(p + ".final_layer_norm")
+    for i in range(N_DEC):
+        p = f"model.decoder.layers.{i}"
+        attn(p + ".self_attn", qk_gain=1.5, o_gain=0.3)
+        layer_norm(p + ".self_attn_layer_norm")
+        attn(p + ".encoder_attn", qk_gain=3.0)
+        layer_norm(p + ".encoder_attn_layer_norm")
+        linear(p + ".mlp.fc1", FFN, D_MODEL)
+        linear(p + ".mlp.fc2", D_MODEL, FFN)
+        layer_norm(p + ".final_layer_norm")
+    layer_norm("model.decoder.layernorm")
+    linear("class_labels_classifier", N_CLASSES + 1, D_MODEL, std=0.2, bias_std=0.3)
+    # make "person" competitive so that a useful fraction of queries is a person above the usual thresholds
+    w["class_labels_classifier.bias"][PERSON_LABEL] += 13.4   # calibrated on synthetic_frames: person ~ the dominant class
+    linear("bbox_predictor.layers.0", D_MODEL, D_MODEL)
+    linear("bbox_predictor.layers.1", D_MODEL, D_MODEL)
+    linear("bbox_predictor.layers.2", 4, D_MODEL, std=0.12, bias_std=0.3)
+    return w
+
+
+# ------------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------------
+def _bf16(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+class _Mode:
+    def __init__(self, mode: str):
+        if mode not in ("fp32", "bf16"):
+            raise ValueError(mode)
+        self.bf16 = mode == "bf16"
+
+    def act(self, x):      # a stored activation
+        return _bf16(x) if self.bf16 else x
+
+    def wt(self, x):       # a tensor-core weight operand
+        return _bf16(x) if self.bf16 else x
+
+
+def resized_size(h: int, w: int, size: int = 800, max_size: int = 1333) -> tuple[int, int]:
+    """image_transforms.py:206-242 get_size_with_aspect_ratio."""
+    raw = None
+    mn, mx = float(min(h, w)), float(max(h, w))
+    if mx / mn * size > max_size:
+        raw = max_size * mn / mx
+        size = int(round(raw))
+    if (h <= w and h == size) or (w <= h and w == size):
+        return h, w
+    if w < h:
+        return (int(raw * h / w) if raw is not None else int(size * h / w)), size
+    return size, (int(raw * w / h) if raw is not None else int(size * w / h))
+
+
+def preprocess(frames_bgr: np.ndarray | torch.Tensor) -> torch.Tensor:
+    """[B,H0,W0,3] uint8 BGR -> pixel_values [B,3,H,W] float32 (all frames the same size: no padding, mask = 1).
+
+    BGR->RGB (removed ViTDetector._preprocess, coverage.json lines 285-300), uint8 bilinear antialias resize
+    (image_processing_backends.py:200-252 -> torchvision resize on the uint8 tensor), then the fused
+    rescale+normalise (x - 255*mean) / (255*std) in float32 (image_processing_backends.py:308-331).
+    """
+    x = torch.as_tensor(np.ascontiguousarray(frames_bgr)) if not torch.is_tensor(frames_bgr) else frames_bgr
+    assert x.dtype == torch.uint8 and x.ndim == 4 and x.shape[-1] == 3
+    x = x.flip(-1).permute(0, 3, 1, 2).contiguous()          # RGB, CHW
+    h0, w0 = x.shape[-2:]
+    h, w = resized_size(h0, w0)
+    if (h, w) != (h0, w0):
+        x = F.interpolate(x, size=(h, w), mode="bilinear", antialias=True, align_corners=False)
+    mean = torch.tensor(IMAGE_MEAN) * 255.0       # float32, like transformers (tensor(mean) * (1 / rescale_factor))
+    std = torch.tensor(IMAGE_STD) * 255.0
+    return (x.to(torch.float32) - mean[None, :, None, None]) / std[None, :, None, None]
+
+
+def fold_bn(w: dict, prefix: str) -> tuple[torch.Tensor, torch.Tensor]:
+    """modeling_detr.py:211-222: y = conv(x) * scale + (bias - mean * scale), scale = weight * rsqrt(var + eps)."""
+    scale = w[prefix + ".normalization.weight"] * (w[prefix + ".normalization.running_var"] + BN_EPS).rsqrt()
+    shift = w[prefix + ".normalization.bias"] - w[prefix + ".normalization.running_mean"] * scale
+    return w[prefix + ".convolution.weight"] * scale[:, None, None, None], shift
+
+
+def sine_position_embedding(h: int, w: int) -> torch.Tensor:
+    """modeling_detr.py:322-349 with an all-ones mask, num_position_features=128, normalize=True -> [h*w, 256]."""
+    npf = D_MODEL // 2
+    y_embed = torch.arange(1, h + 1, dtype=torch.float32)[:, None].expand(h, w)
+    x_embed = torch.arange(1, w + 1, dtype=torch.float32)[None, :].expand(h, w)
+    eps, scale = 1e-6, 2 * math.pi
+    y_embed = y_embed / (y_embed[-1:, :] + eps) * scale
+    x_embed = x_embed / (x_embed[:, -1:] + eps) * scale
+    dim_t = torch.arange(npf, dtype=torch.int64).to(torch.float32)
+    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / npf)
+    pos_x = x_embed[:, :, None] / dim_t
+    pos_y = y_embed[:, :, None] / dim_t
+    pos_x = torch.stack((pos_x[:, :, 0::2].sin(), pos_x[:, :, 1::2].cos()), dim=3).flatten(2)
+    pos_y = torch.stack((pos_y[:, :, 0::2].sin(), pos_y[:, :, 1::2].cos()), dim=3).flatten(2)
+    return torch.cat((pos_y, pos_x), dim=2).reshape(h * w, D_MODEL)
+
+
+def _linear(m: _Mode, w: dict, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    return F.linear(x, m.wt(w[prefix + ".weight"]), w[prefix + ".bias"])
+
+
+def _mha(m: _Mode, w: dict, prefix: str, q_in, k_in, v_in) -> torch.Tensor:
+    """modeling_detr.py:386-411, 441-477, 508-557: softmax(QK^T / sqrt(d)) V per head, no mask (nothing is padded)."""
+    B, Lq, _ = q_in.shape
+    Lk = k_in.shape[1]
+    dh = D_MODEL // N_HEADS
+    q = m.act(_linear(m, w, prefix + ".q_proj", q_in)).view(B, Lq, N_HEADS, dh).transpose(1, 2)
+    k = m.act(_linear(m, w, prefix + ".k_proj", k_in)).view(B, Lk, N_HEADS, dh).transpose(1, 2)
+    v = m.act(_linear(m, w, prefix + ".v_proj", v_in)).view(B, Lk, N_HEADS, dh).transpose(1, 2)
+    s = torch.matmul(q, k.transpose(2, 3)) * dh ** -0.5
+    if m.bf16:
+        # CUDA path: P is rounded to bf16 for the PV product, the row sum stays float32 (flash-attention style)
+        s = s - s.amax(dim=-1, keepdim=True)
+        p = s.exp()
+        o = torch.matmul(_bf16(p), v) / p.sum(dim=-1, keepdim=True)
+    else:
+        o = torch.matmul(F.softmax(s, dim=-1), v)
+    o = m.act(o.transpose(1, 2).reshape(B, Lq, D_MODEL))
+    return _linear(m, w, prefix + ".o_proj", o)
+
+
+def _ln(w: dict, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    return F.layer_norm(x, (D_MODEL,), w[prefix + ".weight"], w[prefix + ".bias"], LN_EPS)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# forward
+# ------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def backbone(w: dict, pixel_values: torch.Tensor, mode: str = "fp32", taps: dict | None = None) -> torch.Tensor:
+    """ResNet-50 with frozen BN -> stage-4 feature map [B,2048,h,w]."""
+    m = _Mode(mode)
+
+    def conv(prefix, x, stride, k, relu, residual=None):
+        wt, shift = fold_bn(w, prefix)
+        y = F.conv2d(x, m.wt(wt), shift, stride=stride, padding=k // 2)
+        if residual is not None:
+            y = y + residual
+        if relu:
+            y = F.relu(y)
+        return m.act(y)
+
+    x = m.act(pixel_values)
+    x = conv("model.backbone.model.embedder.embedder", x, 2, 7, True)
+    if taps is not None:
+        taps["stem"] = x
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    if taps is not None:
+        taps["pool"] = x
+    for s, depth in enumerate(STAGE_DEPTHS):
+        for l in range(depth):
+            p = f"model.backbone.model.encoder.stages.{s}.layers.{l}"
+            stride = 2 if (l == 0 and s > 0) else 1
+            res = conv(p + ".shortcut", x, stride, 1, False) if l == 0 else x
+            y = conv(p + ".layer.0", x, 1, 1, True)
+            y = conv(p + ".layer.1", y, stride, 3, True)
+            x = conv(p + ".layer.2", y, 1, 1, True, residual=res)
+            if taps is not None:
+                taps[f"stage{s}.{l}"] = x
+    return x
+
+
+@torch.no_grad()
+def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None):
+    """frames [B,H0,W0,3] uint8 BGR -> (logits [B,100,92], boxes cxcywh in [0,1] [B,100,4]), float32."""
+    m = _Mode(mode)
+    pv = preprocess(frames_bgr)
+    if taps is not None:
+        taps["pixel_values"] = pv
+    feat = backbone(w, pv, mode, taps)
+    B, _, h, wd = feat.shape
+    proj = F.conv2d(feat, m.wt(w["model.input_projection.weight"]), w["model.input_projection.bias"])
+    x = m.act(proj.flatten(2).permute(0, 2, 1))                     # [B, S, 256]
+    pos = sine_position_embedding(h, wd)[None]                        # float32 table
+    if taps is not None:
+        taps["enc_in"] = x
+        taps["pos"] = pos[0]
+
+    for i in range(N_ENC):
+        p = f"model.encoder.layers.{i}"
+        qk = m.act(x + pos)
+        a = _mha(m, w, p + ".self_attn", qk, qk, x)
+        x = m.act(_ln(w, p + ".self_attn_layer_norm", x + a))
+        f = m.act(F.relu(_linear(m, w, p + ".mlp.fc1", x)))
+        f = _linear(m, w, p + ".mlp.fc2", f)
+        x = m.act(_ln(w, p + ".final_layer_norm", x + f))
+        if taps is not None:
+            taps[f"enc{i}"] = x
+    memory = x
+    mem_k = m.act(memory + pos)
+
+    qpos = w["model.query_position_embeddings.weight"][None].expand(B, -1, -1)
+    y = torch.zeros(B, N_QUERIES, D_MODEL)
+    for i in range(N_DEC):
+        p = f"model.decoder.layers.{i}"
+        qk = m.act(y + qpos)
+        a = _mha(m, w, p + ".self_attn", qk, qk, y)
+        y = m.act(_ln(w, p + ".self_attn_layer_norm", y + a))
+        a = _mha(m, w, p + ".encoder_attn", m.act(y + qpos), mem_k, memory)
+        y = m.act(_ln(w, p + ".encoder_attn_layer_norm", y + a))
+        f = m.act(F.relu(_linear(m, w, p + ".mlp.fc1", y)))
+        f = _linear(m, w, p + ".mlp.fc2", f)
+        y = m.act(_ln(w, p + ".final_layer_norm", y + f))
+        if taps is not None:
+            taps[f"dec{i}"] = y
+    y = m.act(_ln(w, "model.decoder.layernorm", y))
+    if taps is not None:
+        taps["dec_out"] = y
+
+    # heads stay float32 (weights too) in both modes: modeling_detr.py:1275-1297, 1401-1402
+    logits = F.linear(y, w["class_labels_classifier.weight"], w["class_labels_classifier.bias"])
+    b = F.relu(F.linear(y, w["bbox_predictor.layers.0.weight"], w["bbox_predictor.layers.0.bias"]))
+    b = F.relu(F.linear(b, w["bbox_predictor.layers.1.weight"], w["bbox_predictor.layers.1.bias"]))
+    boxes = F.linear(b, w["bbox_predictor.layers.2.weight"], w["bbox_predictor.layers.2.bias"]).sigmoid()
+    return logits, boxes
+
+
+@torch.no_grad()
+def postprocess(logits: torch.Tensor, boxes: torch.Tensor, h0: int, w0: int):
+    """image_processing_detr.py:826-843 without the threshold: per query (score, label, xyxy in pixels of the
+    ORIGINAL frame)."""
+    prob = F.softmax(logits, -1)
+    scores, labels = prob[..., :-1].max(-1)
+    cx, cy, bw, bh = boxes.unbind(-1)
+    xyxy = torch.stack([cx - 0.5 * bw, cy - 0.5 * bh, cx + 0.5 * bw, cy + 0.5 * bh], dim=-1)
+    xyxy = xyxy * torch.tensor([w0, h0, w0, h0], dtype=torch.float32)
+    return scores, labels, xyxy
+
+
+@torch.no_grad()
+def detections(logits, boxes, h0: int, w0: int, threshold: float, person_label: int = PERSON_LABEL):
+    """Per frame: list of (x, y, w, h, score, foot_x, foot_y) for score > threshold and label == person,
+    in query order (post_process_object_detection + yolov8_detector.py:210-225, 229-241)."""
+    scores, labels, xyxy = postprocess(logits, boxes, h0, w0)
+    out = []
+    for s, l, b in zip(scores, labels, xyxy):
+        keep = (s > threshold) & (l == person_label)
+        rows = []
+        for sc, bb in zip(s[keep].tolist(), b[keep].tolist()):
+            x1, y1, x2, y2 = bb
+            bw, bh = x2 - x1, y2 - y1
+            rows.append((x1, y1, bw, bh, sc, x1 + bw / 2, y1 + bh))
+        out.append(rows)
+    return out
+
+
+def hf_model(w: dict):
+    """transformers' own DetrForObjectDetection loaded with `w` (the arithmetic the reference ran)."""
+    import os
+
+    os.environ.setdefault("HF_HUB_OFFLINE", "1")
+    from transformers import DetrConfig, DetrForObjectDetection, ResNetConfig
+
+    cfg = DetrConfig(backbone_config=ResNetConfig(out_features=["stage4"]), num_labels=N_CLASSES)
+    model = DetrForObjectDetection(cfg).eval()
+    missing, unexpected = model.load_state_dict(w, strict=False)
+    assert not unexpected and all("num_batches_tracked" in k for k in missing), (missing, unexpected)
+    return model
+
+
+def synthetic_frames(batch: int, h: int, w: int, seed: int = 1) -> np.ndarray:
+    """Synthetic BGR frames, uint8: large flat-colour rectangles (so that distant image regions give distinct
+    backbone features) with finer blocks and pixel noise on top."""
+    rng = np.random.default_rng(seed)
+
+    def blocks(size, amp):
+        c = rng.integers(-amp, amp + 1, (batch, (h + size - 1) // size, (w + size - 1) // size, 3), dtype=np.int16)
+        return np.repeat(np.repeat(c, size, axis=1), size, axis=2)[:, :h, :w]
+
+    img = 128 + blocks(192, 110) + blocks(32, 40) + rng.integers(-12, 13, (batch, h, w, 3), dtype=np.int16)
+    return np.clip(img, 0, 255).astype(np.uint8)
