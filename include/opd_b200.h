@@ -106,6 +106,32 @@ int opd_floor_project_classify_count_f64(const opd_floor_params* p, const opd_zo
 int opd_zone_histogram(const int32_t* zone_idx_dev, const uint64_t* zone_mask_dev, const int32_t* slot_dev,
                        int64_t N, int32_t Z, int32_t T, int32_t* hist_dev, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core building blocks of the detector (K4 / K5 / K6).  They are the unit-test surface of
+ * the tcgen05 kernels; opd_detr_forward (below) chains them with pre-built plans.
+ * replaces (third-party `transformers`, the arithmetic the removed src/detection/vit_detector.py drove):
+ *   nn.Linear / 1x1 conv / 3x3 conv + DetrFrozenBatchNorm2d + ReLU / residual  (modeling_detr.py:185-222,
+ *   models/resnet/modeling_resnet.py:40-200), residual + LayerNorm (modeling_detr.py:592-631),
+ *   eager_attention_forward (modeling_detr.py:386-411)
+ * ------------------------------------------------------------------------------------------ */
+
+/* epilogue: 0 bias, 1 bias+ReLU, 2 bias+residual+ReLU, 3 LayerNorm(bias+residual)*gamma+beta (N == 256) */
+/* D[M,N] = epilogue(A[M,K] W[N,K]^T + bias); bf16 in/out, fp32 accumulate; N, K multiples of 64.
+ * d2_dev (optional) receives bf16(D + pos[row % pos_rows]) with pos [pos_rows, N] f32. */
+int opd_gemm_bf16(const void* a_dev, int64_t lda, const void* w_dev, void* d_dev, int64_t ldd, int32_t M,
+                  int32_t N, int32_t K, int32_t epilogue, const float* bias_dev, const void* residual_dev,
+                  int64_t ldr, const float* gamma_dev, const float* beta_dev, void* d2_dev,
+                  const float* pos_dev, int32_t pos_rows, void* stream);
+/* y[B,P,Q,N] = epilogue(conv(x[B,H,W,C] NHWC bf16, w[N,KH,KW,C] bf16, stride, pad) + bias); C, N multiples of 64 */
+int opd_conv2d_nhwc_bf16(const void* x_dev, int32_t B, int32_t H, int32_t W, int32_t C, const void* w_dev,
+                         int32_t N, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t epilogue,
+                         const float* bias_dev, const void* residual_dev, void* y_dev, void* stream);
+/* o = softmax(q k^T / sqrt(32)) v per (batch, head); head h = columns [32h, 32h+32); row strides in elements */
+int opd_attention_bf16(const void* q_dev, int64_t ldq, const void* k_dev, int64_t ldk, const void* v_dev,
+                       int64_t ldv, void* o_dev, int64_t ldo, int32_t B, int32_t heads, int32_t Lq, int32_t Lk,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

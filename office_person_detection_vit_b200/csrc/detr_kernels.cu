@@ -595,3 +595,11 @@ int launch_postprocess(const float* logits, const float* boxes, int B, int Q, in
 }
 
 }  // namespace opd
+
+extern "C" int opd_attention_bf16(const void* q_dev, int64_t ldq, const void* k_dev, int64_t ldk, const void* v_dev,
+                                  int64_t ldv, void* o_dev, int64_t ldo, int32_t B, int32_t heads, int32_t Lq,
+                                  int32_t Lk, void* stream) {
+  return opd::launch_attention(static_cast<const __nv_bfloat16*>(q_dev), ldq, static_cast<const __nv_bfloat16*>(k_dev),
+                               ldk, static_cast<const __nv_bfloat16*>(v_dev), ldv, static_cast<__nv_bfloat16*>(o_dev),
+                               ldo, B, heads, Lq, Lk, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,112 @@
+"""GPU numerics of the tensor-core building blocks (csrc/tc_gemm.cu, attention) through the C ABI, against a plain
+PyTorch fp32 reference of the same op on the same bf16-rounded operands.  Tolerance: the outputs are bf16
+(8 significant bits), the accumulation is fp32 on both sides -> |err| <= 2^-8 * |ref| + small absolute term."""
+
+from __future__ import annotations
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T(built_lib):
+    import torch
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch
+
+
+def _close(torch, got, ref, what):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2 * ref.abs().mean().clamp_min(1e-3)
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} / {bad.numel()} off, max err {float(err.max()):.4g}, " \
+                          f"ref scale {float(ref.abs().mean()):.4g}, first bad {bad.nonzero()[:4].tolist()}"
+
+
+def _rand(torch, *shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 64, 128), (2100, 256, 256), (1000, 2048, 256),
+                                   (1000, 256, 2048), (128 * 150 + 7, 128, 576), (6400, 512, 1024)])
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_gemm_epilogues(T, M, N, K, epi):
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    a, w = _rand(torch, M, K, seed=1), _rand(torch, N, K, seed=2, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    res = _rand(torch, M, N, seed=3) if epi == 2 else None
+    d = ops.gemm(a, w, bias, epilogue=epi, residual=res)
+    ref = a.float() @ w.float().T + bias
+    if epi == 2:
+        ref = ref + res.float()
+    if epi >= 1:
+        ref = ref.relu()
+    _close(torch, d, ref, f"gemm {M}x{N}x{K} epi {epi}")
+
+
+@pytest.mark.parametrize("M,K", [(100, 256), (1050 * 3, 256), (777, 2048)])
+def test_gemm_layernorm_and_pos(T, M, K):
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    N = 256
+    a, w = _rand(torch, M, K, seed=4), _rand(torch, N, K, seed=5, scale=K ** -0.5)
+    bias, gamma, beta = torch.randn(N, device="cuda"), torch.rand(N, device="cuda") + 0.5, torch.randn(N, device="cuda")
+    res = _rand(torch, M, N, seed=6)
+    pos_rows = 50 if M % 50 == 0 else M
+    pos = torch.randn(pos_rows, N, device="cuda")
+    d, d2 = ops.gemm(a, w, bias, epilogue=ops.EPI_BIAS_RES_LN, residual=res, gamma=gamma, beta=beta, pos=pos)
+    ref = torch.nn.functional.layer_norm(a.float() @ w.float().T + bias + res.float(), (N,), gamma, beta, 1e-5)
+    _close(torch, d, ref, "gemm+LN")
+    ref2 = d.float() + pos.repeat(M // pos_rows, 1)
+    _close(torch, d2, ref2, "gemm+LN+pos")
+
+
+@pytest.mark.parametrize("B,H,W,C,N,k,stride,epi", [
+    (2, 20, 31, 64, 64, 3, 1, 1),
+    (1, 50, 84, 128, 128, 3, 2, 1),
+    (3, 25, 42, 256, 256, 3, 2, 1),
+    (2, 25, 42, 512, 512, 3, 1, 1),
+    (2, 50, 83, 256, 512, 1, 2, 0),
+    (2, 17, 23, 64, 256, 1, 1, 2),
+    (1, 200, 334, 64, 64, 3, 1, 1),
+])
+def test_conv_nhwc(T, B, H, W, C, N, k, stride, epi):
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    x = _rand(torch, B, H, W, C, seed=7)
+    w = _rand(torch, N, k, k, C, seed=8, scale=(C * k * k) ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    pad = k // 2
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, stride=stride,
+                                     padding=pad).permute(0, 2, 3, 1)
+    res = _rand(torch, *ref.shape, seed=9) if epi == 2 else None
+    y = ops.conv2d_nhwc(x, w, bias, stride=stride, pad=pad, epilogue=epi, residual=res)
+    if epi == 2:
+        ref = ref + res.float()
+    if epi >= 1:
+        ref = ref.relu()
+    assert y.shape == ref.shape
+    _close(torch, y, ref, f"conv {B}x{H}x{W}x{C}->{N} k{k} s{stride}")
+
+
+@pytest.mark.parametrize("B,Lq,Lk", [(2, 100, 100), (2, 100, 1050), (1, 1050, 1050), (3, 1008, 1008), (1, 7, 65)])
+def test_attention(T, B, Lq, Lk):
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    D, heads = 256, 8
+    q, k, v = _rand(torch, B, Lq, D, seed=10), _rand(torch, B, Lk, D, seed=11), _rand(torch, B, Lk, D, seed=12)
+    o = ops.attention(q, k, v, heads)
+    qh, kh, vh = (t.float().view(B, -1, heads, 32).transpose(1, 2) for t in (q, k, v))
+    ref = torch.softmax(qh @ kh.transpose(2, 3) * 32 ** -0.5, -1) @ vh
+    ref = ref.transpose(1, 2).reshape(B, Lq, D)
+    _close(torch, o, ref, f"attention {B}x{Lq}x{Lk}")
