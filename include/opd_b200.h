@@ -132,6 +132,63 @@ int opd_attention_bf16(const void* q_dev, int64_t ldq, const void* k_dev, int64_
                        int64_t ldv, void* o_dev, int64_t ldo, int32_t B, int32_t heads, int32_t Lq, int32_t Lk,
                        void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * DETR-ResNet-50 person detector  (K1-K8)
+ * replaces: the removed src/detection/vit_detector.py (ViTDetector.detect_batch, _preprocess_batch,
+ *           _postprocess_batch; method table in coverage.json) and the third-party
+ *           arithmetic it drove: transformers DetrImageProcessor + DetrForObjectDetection
+ *           (models/detr/image_processing_detr.py:687-855, models/detr/modeling_detr.py:185-1402,
+ *           models/resnet/modeling_resnet.py:40-240); person filter / xywh / foot point as in
+ *           src/detection/yolov8_detector.py:210-225, 229-241.
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct opd_detr opd_detr;
+
+/* One named float32 host tensor of the model's state dict (transformers key names, e.g.
+ * "model.encoder.layers.0.self_attn.q_proj.weight"). */
+typedef struct opd_tensor_f32 {
+  const char* name;
+  const float* data;
+  int64_t numel;
+} opd_tensor_f32;
+
+/* Builds the device copy of the weights: frozen BN folded into the convolutions in float32, tensor-core
+ * operands rounded to bf16 and laid out [C_out, kh, kw, C_in], heads kept float32.  Synchronous. */
+int opd_detr_create(const opd_tensor_f32* tensors, int32_t n_tensors, int32_t device, opd_detr** out);
+void opd_detr_destroy(opd_detr* m);
+/* debug != 0: every activation gets its own workspace region (no buffer reuse) so that opd_detr_tap can
+ * read any of them after a forward; costs memory, changes no arithmetic. */
+int opd_detr_set_debug(opd_detr* m, int32_t debug);
+/* do_resize = 0 feeds frames at their own size, like DetrImageProcessor(do_resize=False); default 1. */
+int opd_detr_set_resize(opd_detr* m, int32_t do_resize);
+
+/* Model input size for a frame size (DetrImageProcessor shortest-edge 800 / longest-edge 1333 rule,
+ * transformers/image_transforms.py:206-242) and the stage-4 feature map size. */
+int opd_detr_input_shape(int32_t H0, int32_t W0, int32_t* H_in, int32_t* W_in, int32_t* h_feat, int32_t* w_feat);
+int opd_detr_workspace_bytes(const opd_detr* m, int32_t B, int32_t H0, int32_t W0, size_t* bytes);
+/* frames_dev [B,H0,W0,3] uint8 (BGR like cv2 frames, or RGB) -> logits_dev [B,100,92] f32, boxes_dev [B,100,4] f32
+ * (cxcywh in [0,1]).  All frames of a call have the same size (no padding, pixel_mask = 1).  The launch
+ * plan (tensor maps) is cached per (B, H0, W0, workspace_dev).  Enqueues only; CUDA-graph capturable after the
+ * first call with the same arguments. */
+int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t H0, int32_t W0,
+                     int32_t frames_are_bgr, void* workspace_dev, size_t workspace_bytes, float* logits_dev,
+                     float* boxes_dev, void* stream);
+/* Named internal activation of the last forward (tests): "pixel_values", "stem", "pool", "stage{s}.{l}",
+ * "enc_in", "pos", "enc{i}", "dec{i}", "dec_out".  rows x cols, bf16 unless *is_f32. */
+int opd_detr_tap(const opd_detr* m, const char* name, const void** ptr_dev, int64_t* rows, int64_t* cols,
+                 int32_t* is_f32);
+/* Copies that activation into dst_dev (device, `bytes` = rows * cols * element size) on `stream`. */
+int opd_detr_tap_copy(const opd_detr* m, const char* name, void* dst_dev, size_t bytes, void* stream);
+/* post_process_object_detection + person filter (image_processing_detr.py:826-843; yolov8_detector.py:210-241):
+ * per query: scores_dev [B,Q], labels_dev [B,Q], xyxy_dev [B,Q,4] (pixels of the ORIGINAL H0 x W0 frame);
+ * per frame, compacted in query order: det_xywh_dev [B,Q,4], det_score_dev [B,Q], det_foot_dev [B,Q,2] f64,
+ * det_query_dev [B,Q], n_keep_dev [B]  for  score > threshold && label == person_label. */
+int opd_detr_postprocess(const float* logits_dev, const float* boxes_dev, int32_t B, int32_t Q, int32_t C,
+                         int32_t H0, int32_t W0, float threshold, int32_t person_label, float* scores_dev,
+                         int32_t* labels_dev, float* xyxy_dev, float* det_xywh_dev, float* det_score_dev,
+                         double* det_foot_dev, int32_t* det_query_dev, int32_t* n_keep_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,710 @@
+// DETR-ResNet-50 detector engine: weight packing, workspace layout and the launch plan that chains the kernels of
+// tc_gemm.cu (tcgen05 GEMM / implicit-GEMM convolution), attention.cu and detr_kernels.cu into one forward pass.
+//
+// Arithmetic replaced (third-party `transformers`, the code the reference's removed ViTDetector drove; file:line map in
+// oracle/detr_oracle.py): DetrImageProcessor preprocessing, ResNet-50 + DetrFrozenBatchNorm2d, input_projection,
+// DetrSinePositionEmbedding, 6 encoder + 6 decoder layers, class / box heads.
+//
+// Numerics (DESIGN.md "numerics"): frozen BN is folded into the convolution weights in float32 and the product is
+// rounded once to bf16; every stored activation is bf16; accumulation, LayerNorm statistics, softmax, the final
+// LayerNorm input path and both heads are float32.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "detr_kernels.h"
+#include "opd_common.h"
+#include "tc_gemm.h"
+
+namespace opd {
+namespace {
+
+constexpr int kD = 256, kHeads = 8, kFFN = 2048, kEnc = 6, kDec = 6, kQueries = 100, kClasses = 92;
+constexpr int kStageDepth[4] = {3, 4, 6, 3};
+constexpr int kStageWidth[4] = {256, 512, 1024, 2048};
+constexpr float kBnEps = 1e-5f;
+
+using bf16 = __nv_bfloat16;
+
+struct ConvW {
+  bf16* w = nullptr;      // [cout, k, k, cin]
+  float* bias = nullptr;  // folded BN shift
+  int cin = 0, cout = 0, k = 1, stride = 1;
+};
+struct LinW {
+  bf16* w = nullptr;   // [n, k]
+  float* b = nullptr;  // [n]
+  int n = 0, k = 0;
+};
+struct LnW {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+struct BlockW {
+  bool has_shortcut = false;
+  ConvW shortcut, c0, c1, c2;
+};
+struct EncW {
+  LinW qk, v, o, fc1, fc2;
+  LnW ln1, ln2;
+};
+struct DecW {
+  LinW sqk, sv, so, cq, co, fc1, fc2;
+  LnW ln1, ln2, ln3;
+};
+
+struct Tap {
+  const void* ptr;
+  int64_t rows, cols;
+  int is_f32;
+};
+
+struct Plan {
+  int B = 0, H0 = 0, W0 = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<std::function<int(cudaStream_t)>> steps;
+  std::map<std::string, Tap> taps;
+};
+
+}  // namespace
+}  // namespace opd
+
+struct opd_detr {
+  int device = 0;
+  int debug = 0;
+  int do_resize = 1;   // 0: frames are fed at their own size (DetrImageProcessor(do_resize=False))
+  std::vector<void*> allocs;
+  opd::ConvW stem;   // packed as a 4x1 convolution over the 64-channel space-to-depth layout
+  std::vector<opd::BlockW> blocks;
+  opd::LinW input_proj;
+  opd::EncW enc[opd::kEnc];
+  opd::DecW dec[opd::kDec];
+  opd::LinW cross_k_all, cross_v_all;   // the 6 decoder layers' encoder_attn k_proj / v_proj stacked on N
+  opd::LnW dec_norm;
+  float* qpos = nullptr;   // [100, 256]
+  opd::HeadWeights heads{};
+  // per-call arguments read by the plan's steps
+  const uint8_t* cur_frames = nullptr;
+  int cur_bgr = 1;
+  float* cur_logits = nullptr;
+  float* cur_boxes = nullptr;
+  opd::Plan plan;
+};
+
+namespace opd {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// weight loading
+// ------------------------------------------------------------------------------------------------------------
+struct Loader {
+  std::map<std::string, std::pair<const float*, int64_t>> t;
+  opd_detr* m;
+  int rc = OPD_OK;
+
+  const float* get(const std::string& name, int64_t numel) {
+    auto it = t.find(name);
+    if (it == t.end()) {
+      if (rc == OPD_OK) rc = fail(OPD_ERR_INVALID, "detr weights: tensor '%s' is missing", name.c_str());
+      return nullptr;
+    }
+    if (it->second.second != numel) {
+      if (rc == OPD_OK)
+        rc = fail(OPD_ERR_INVALID, "detr weights: tensor '%s' has %lld elements, expected %lld", name.c_str(),
+                  (long long)it->second.second, (long long)numel);
+      return nullptr;
+    }
+    return it->second.first;
+  }
+  template <typename T>
+  T* upload(const std::vector<T>& host) {
+    if (rc != OPD_OK) return nullptr;
+    void* d = nullptr;
+    if (cudaMalloc(&d, host.size() * sizeof(T)) != cudaSuccess) {
+      rc = fail(OPD_ERR_NOMEM, "detr weights: cudaMalloc of %zu bytes failed", host.size() * sizeof(T));
+      return nullptr;
+    }
+    m->allocs.push_back(d);
+    if (cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+      rc = fail(OPD_ERR_CUDA, "detr weights: upload failed");
+      return nullptr;
+    }
+    return static_cast<T*>(d);
+  }
+  float* upload_f32(const float* src, int64_t n) {
+    if (!src) return nullptr;
+    return upload(std::vector<float>(src, src + n));
+  }
+
+  // fold frozen BN: scale = gamma * rsqrt(var + eps); w' = w * scale; shift = beta - mean * scale   (float32)
+  bool folded(const std::string& prefix, int cin, int cout, int k, std::vector<float>* wf, std::vector<float>* shift) {
+    const float* w = get(prefix + ".convolution.weight", (int64_t)cout * cin * k * k);
+    const float* g = get(prefix + ".normalization.weight", cout);
+    const float* b = get(prefix + ".normalization.bias", cout);
+    const float* mu = get(prefix + ".normalization.running_mean", cout);
+    const float* var = get(prefix + ".normalization.running_var", cout);
+    if (rc != OPD_OK) return false;
+    wf->resize((size_t)cout * cin * k * k);
+    shift->resize(cout);
+    for (int n = 0; n < cout; ++n) {
+      const float scale = g[n] * (1.0f / sqrtf(var[n] + kBnEps));
+      (*shift)[n] = b[n] - mu[n] * scale;
+      const float* src = w + (size_t)n * cin * k * k;
+      float* dst = wf->data() + (size_t)n * cin * k * k;
+      for (int i = 0; i < cin * k * k; ++i) dst[i] = src[i] * scale;
+    }
+    return true;
+  }
+
+  ConvW conv(const std::string& prefix, int cin, int cout, int k, int stride) {
+    ConvW c;
+    c.cin = cin; c.cout = cout; c.k = k; c.stride = stride;
+    std::vector<float> wf, shift;
+    if (!folded(prefix, cin, cout, k, &wf, &shift)) return c;
+    std::vector<bf16> packed((size_t)cout * k * k * cin);   // OIHW -> O,kh,kw,I
+    for (int n = 0; n < cout; ++n)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int r = 0; r < k; ++r)
+          for (int s = 0; s < k; ++s)
+            packed[(((size_t)n * k + r) * k + s) * cin + ci] =
+                __float2bfloat16(wf[(((size_t)n * cin + ci) * k + r) * k + s]);
+    c.w = upload(packed);
+    c.bias = upload(shift);
+    return c;
+  }
+
+  // 7x7 / stride 2 / pad 3 stem over RGB  ->  4x1 convolution over the 64-channel layout written by K1:
+  //   channel = kw4 * 16 + (dy * 2 + dx) * 3 + c,  tap row kh4;  original tap (r, s): kh4 = (r+1)/2, dy = (r+1)&1 (same for s)
+  ConvW stem_conv(const std::string& prefix) {
+    ConvW c;
+    c.cin = 64; c.cout = 64; c.k = 4; c.stride = 1;
+    std::vector<float> wf, shift;
+    if (!folded(prefix, 3, 64, 7, &wf, &shift)) return c;
+    std::vector<bf16> packed((size_t)64 * 4 * 64, __float2bfloat16(0.f));
+    for (int n = 0; n < 64; ++n)
+      for (int ci = 0; ci < 3; ++ci)
+        for (int r = 0; r < 7; ++r)
+          for (int s = 0; s < 7; ++s) {
+            const int kh4 = (r + 1) / 2, dy = (r + 1) & 1, kw4 = (s + 1) / 2, dx = (s + 1) & 1;
+            const int ch = kw4 * 16 + (dy * 2 + dx) * 3 + ci;
+            packed[((size_t)n * 4 + kh4) * 64 + ch] = __float2bfloat16(wf[(((size_t)n * 3 + ci) * 7 + r) * 7 + s]);
+          }
+    c.w = upload(packed);
+    c.bias = upload(shift);
+    return c;
+  }
+
+  // rows of several [n_i, k] Linear layers stacked on N
+  LinW linear(const std::vector<std::string>& prefixes, int n_each, int k) {
+    LinW l;
+    l.n = n_each * (int)prefixes.size();
+    l.k = k;
+    std::vector<bf16> w((size_t)l.n * k);
+    std::vector<float> b(l.n);
+    for (size_t i = 0; i < prefixes.size(); ++i) {
+      const float* ws = get(prefixes[i] + ".weight", (int64_t)n_each * k);
+      const float* bs = get(prefixes[i] + ".bias", n_each);
+      if (rc != OPD_OK) return l;
+      for (size_t j = 0; j < (size_t)n_each * k; ++j) w[i * (size_t)n_each * k + j] = __float2bfloat16(ws[j]);
+      for (int j = 0; j < n_each; ++j) b[i * n_each + j] = bs[j];
+    }
+    l.w = upload(w);
+    l.b = upload(b);
+    return l;
+  }
+  LnW layer_norm(const std::string& prefix) {
+    LnW l;
+    l.g = upload_f32(get(prefix + ".weight", kD), kD);
+    l.b = upload_f32(get(prefix + ".bias", kD), kD);
+    return l;
+  }
+  float* transposed(const std::string& name, int n, int k) {   // [n,k] -> [k,n] float32
+    const float* src = get(name, (int64_t)n * k);
+    if (!src) return nullptr;
+    std::vector<float> t((size_t)n * k);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < k; ++j) t[(size_t)j * n + i] = src[(size_t)i * k + j];
+    return upload(t);
+  }
+};
+
+int load_weights(opd_detr* m, const opd_tensor_f32* tensors, int n_tensors) {
+  Loader L;
+  L.m = m;
+  for (int i = 0; i < n_tensors; ++i) {
+    OPD_REQUIRE(tensors[i].name && tensors[i].data, "detr weights: tensor %d has a NULL name or data pointer", i);
+    L.t[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+  }
+  const std::string bb = "model.backbone.model.";
+  m->stem = L.stem_conv(bb + "embedder.embedder");
+  int cin = 64;
+  for (int s = 0; s < 4; ++s) {
+    const int width = kStageWidth[s], mid = width / 4;
+    for (int l = 0; l < kStageDepth[s]; ++l) {
+      const int stride = (l == 0 && s > 0) ? 2 : 1;
+      const std::string p = bb + "encoder.stages." + std::to_string(s) + ".layers." + std::to_string(l);
+      BlockW b;
+      b.has_shortcut = l == 0;
+      if (l == 0) b.shortcut = L.conv(p + ".shortcut", cin, width, 1, stride);
+      b.c0 = L.conv(p + ".layer.0", cin, mid, 1, 1);
+      b.c1 = L.conv(p + ".layer.1", mid, mid, 3, stride);   // v1.5: the stride sits on the 3x3
+      b.c2 = L.conv(p + ".layer.2", mid, width, 1, 1);
+      m->blocks.push_back(b);
+      cin = width;
+    }
+  }
+  m->input_proj = L.linear({"model.input_projection"}, kD, 2048);
+  for (int i = 0; i < kEnc; ++i) {
+    const std::string p = "model.encoder.layers." + std::to_string(i);
+    EncW& e = m->enc[i];
+    e.qk = L.linear({p + ".self_attn.q_proj", p + ".self_attn.k_proj"}, kD, kD);
+    e.v = L.linear({p + ".self_attn.v_proj"}, kD, kD);
+    e.o = L.linear({p + ".self_attn.o_proj"}, kD, kD);
+    e.ln1 = L.layer_norm(p + ".self_attn_layer_norm");
+    e.fc1 = L.linear({p + ".mlp.fc1"}, kFFN, kD);
+    e.fc2 = L.linear({p + ".mlp.fc2"}, kD, kFFN);
+    e.ln2 = L.layer_norm(p + ".final_layer_norm");
+  }
+  std::vector<std::string> ck, cv;
+  for (int i = 0; i < kDec; ++i) {
+    const std::string p = "model.decoder.layers." + std::to_string(i);
+    DecW& d = m->dec[i];
+    d.sqk = L.linear({p + ".self_attn.q_proj", p + ".self_attn.k_proj"}, kD, kD);
+    d.sv = L.linear({p + ".self_attn.v_proj"}, kD, kD);
+    d.so = L.linear({p + ".self_attn.o_proj"}, kD, kD);
+    d.ln1 = L.layer_norm(p + ".self_attn_layer_norm");
+    d.cq = L.linear({p + ".encoder_attn.q_proj"}, kD, kD);
+    d.co = L.linear({p + ".encoder_attn.o_proj"}, kD, kD);
+    d.ln2 = L.layer_norm(p + ".encoder_attn_layer_norm");
+    d.fc1 = L.linear({p + ".mlp.fc1"}, kFFN, kD);
+    d.fc2 = L.linear({p + ".mlp.fc2"}, kD, kFFN);
+    d.ln3 = L.layer_norm(p + ".final_layer_norm");
+    ck.push_back(p + ".encoder_attn.k_proj");
+    cv.push_back(p + ".encoder_attn.v_proj");
+  }
+  m->cross_k_all = L.linear(ck, kD, kD);
+  m->cross_v_all = L.linear(cv, kD, kD);
+  m->dec_norm = L.layer_norm("model.decoder.layernorm");
+  m->qpos = L.upload_f32(L.get("model.query_position_embeddings.weight", (int64_t)kQueries * kD), (int64_t)kQueries * kD);
+  m->heads.wc_t = L.transposed("class_labels_classifier.weight", kClasses, kD);
+  m->heads.bc = L.upload_f32(L.get("class_labels_classifier.bias", kClasses), kClasses);
+  m->heads.w0_t = L.transposed("bbox_predictor.layers.0.weight", kD, kD);
+  m->heads.b0 = L.upload_f32(L.get("bbox_predictor.layers.0.bias", kD), kD);
+  m->heads.w1_t = L.transposed("bbox_predictor.layers.1.weight", kD, kD);
+  m->heads.b1 = L.upload_f32(L.get("bbox_predictor.layers.1.bias", kD), kD);
+  m->heads.w2 = L.upload_f32(L.get("bbox_predictor.layers.2.weight", 4 * kD), 4 * kD);
+  m->heads.b2 = L.upload_f32(L.get("bbox_predictor.layers.2.bias", 4), 4);
+  return L.rc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// shapes
+// ------------------------------------------------------------------------------------------------------------
+// transformers/image_transforms.py:206-242 get_size_with_aspect_ratio(size=800, max_size=1333)
+void resized_size(int h, int w, int* oh, int* ow) {
+  double size = 800.0;
+  const double max_size = 1333.0;
+  const double mn = (double)(h < w ? h : w), mx = (double)(h < w ? w : h);
+  bool has_raw = false;
+  double raw = 0.0;
+  if (mx / mn * size > max_size) {
+    raw = max_size * mn / mx;
+    has_raw = true;
+    size = (double)(long long)nearbyint(raw);   // python round(): half to even
+  }
+  const int isz = (int)size;
+  if ((h <= w && h == isz) || (w <= h && w == isz)) {
+    *oh = h; *ow = w;
+    return;
+  }
+  if (w < h) {
+    *ow = isz;
+    *oh = (int)(has_raw ? raw * h / w : size * h / w);
+  } else {
+    *oh = isz;
+    *ow = (int)(has_raw ? raw * w / h : size * w / h);
+  }
+}
+
+inline int conv_out(int x, int k, int stride, int pad) { return (x + 2 * pad - k) / stride + 1; }
+
+struct Shapes {
+  int Hin, Win;        // model input
+  int Hs, Ws;          // stem output (= space-to-depth grid)
+  int Hp, Wp;          // after max pooling
+  int h[4], w[4];      // stage outputs
+};
+Shapes shapes_for(int H0, int W0, bool do_resize = true) {
+  Shapes s;
+  s.Hin = H0;
+  s.Win = W0;
+  if (do_resize) resized_size(H0, W0, &s.Hin, &s.Win);
+  s.Hs = conv_out(s.Hin, 7, 2, 3);
+  s.Ws = conv_out(s.Win, 7, 2, 3);
+  s.Hp = conv_out(s.Hs, 3, 2, 1);
+  s.Wp = conv_out(s.Ws, 3, 2, 1);
+  int hh = s.Hp, ww = s.Wp;
+  for (int i = 0; i < 4; ++i) {
+    if (i > 0) {
+      hh = conv_out(hh, 3, 2, 1);
+      ww = conv_out(ww, 3, 2, 1);
+    }
+    s.h[i] = hh;
+    s.w[i] = ww;
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// workspace arena: named slots are reused (backbone ping-pong) unless the engine is in debug mode
+// ------------------------------------------------------------------------------------------------------------
+struct Arena {
+  uint8_t* base;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    off = (off + 1023) & ~(size_t)1023;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+// Builds the launch plan.  With ws == nullptr only the workspace size is computed (no tensor maps are encoded).
+int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t* bytes_out) {
+  const bool dry = ws == nullptr;
+  const Shapes sh = shapes_for(H0, W0, m->do_resize != 0);
+  OPD_REQUIRE(sh.Hs >= 4 && sh.h[3] >= 1 && sh.w[3] >= 1, "detr: frames of %dx%d are too small", H0, W0);
+  OPD_REQUIRE(sh.Hin == H0 && sh.Win == W0,
+              "detr: frames of %dx%d need the %dx%d resize, which this build does not implement yet (feed 800x1333-class frames)",
+              H0, W0, sh.Hin, sh.Win);
+  OPD_REQUIRE(sh.Hs == (sh.Hin + 1) / 2 && sh.Ws == (sh.Win + 1) / 2, "detr: unexpected stem geometry");
+  Arena A{static_cast<uint8_t*>(ws)};
+  auto& steps = plan->steps;
+  auto& taps = plan->taps;
+  const bool dbg = m->debug != 0;
+
+  auto act_bytes = [&](long long rows, int ch) { return (size_t)rows * ch * sizeof(bf16); };
+  const long long Ms = (long long)B * sh.Hs * sh.Ws, Mp = (long long)B * sh.Hp * sh.Wp;
+
+  // ---- backbone buffers: 3 big ping-pong slots + 2 mid slots (each sized for its largest user) ----
+  size_t big_bytes = act_bytes(Ms, 64), mid_bytes = 0;
+  {
+    int hh = sh.Hp, ww = sh.Wp;
+    for (int s = 0; s < 4; ++s) {
+      const int width = kStageWidth[s], mid = width / 4;
+      const long long m_in = (long long)B * hh * ww;
+      const long long m_out = (long long)B * sh.h[s] * sh.w[s];
+      big_bytes = std::max(big_bytes, act_bytes(m_out, width));
+      mid_bytes = std::max(mid_bytes, act_bytes(m_in, mid));   // layer.0 of the first block runs at the input size
+      hh = sh.h[s];
+      ww = sh.w[s];
+    }
+  }
+  void* big[3] = {nullptr, nullptr, nullptr};
+  void* mids[2] = {nullptr, nullptr};
+  if (!dbg) {
+    for (auto& b : big) b = A.take(big_bytes);
+    for (auto& b : mids) b = A.take(mid_bytes);
+  }
+  auto big_slot = [&](int i, size_t bytes) { return dbg ? A.take(bytes) : big[i]; };
+  auto mid_slot = [&](int i, size_t bytes) { return dbg ? A.take(bytes) : mids[i]; };
+
+  // ---- K1 preprocess -> X2 [B, Hs, Ws, 64] ----
+  bf16* x2 = static_cast<bf16*>(big_slot(0, act_bytes(Ms, 64)));
+  if (!dry) {
+    steps.push_back([m, B, sh, x2](cudaStream_t s) {
+      return launch_preprocess(m->cur_frames, B, sh.Hin, sh.Win, m->cur_bgr, x2, s);
+    });
+    taps["x2"] = {x2, Ms, 64, 0};
+  }
+
+  auto add_gemm = [&](const GemmPlan& gp) {
+    steps.push_back([gp](cudaStream_t s) { return gemm_launch(gp, s); });
+  };
+  auto conv = [&](const bf16* x, int H, int W, const ConvW& c, bf16* y, int epi, const bf16* res) -> int {
+    if (dry) return OPD_OK;
+    GemmPlan gp;
+    if (c.k == 1 && c.stride == 1) {
+      const int M = B * H * W;
+      if (int rc = gemm_plan_linear(&gp, x, c.cin, c.w, y, c.cout, M, c.cout, c.cin, epi, c.bias, res, c.cout, nullptr,
+                                    nullptr, nullptr, nullptr, 0))
+        return rc;
+    } else {
+      const int pad = c.k / 2;
+      ConvGeom g{B, H, W, c.cin, c.k, c.k, c.stride, pad, pad, conv_out(H, c.k, c.stride, pad), conv_out(W, c.k, c.stride, pad)};
+      if (int rc = gemm_plan_conv(&gp, x, g, c.w, y, c.cout, epi, c.bias, res)) return rc;
+    }
+    add_gemm(gp);
+    return OPD_OK;
+  };
+
+  // ---- K2 stem: 4x1 convolution over X2, pad 2 rows above / 1 below ----
+  bf16* stem_out = static_cast<bf16*>(big_slot(1, act_bytes(Ms, 64)));
+  if (!dry) {
+    GemmPlan gp;
+    ConvGeom g{B, sh.Hs, sh.Ws, 64, 4, 1, 1, 2, 0, sh.Hs, sh.Ws};
+    if (int rc = gemm_plan_conv(&gp, x2, g, m->stem.w, stem_out, 64, EPI_BIAS_RELU, m->stem.bias, nullptr)) return rc;
+    add_gemm(gp);
+    taps["stem"] = {stem_out, Ms, 64, 0};
+  }
+  // ---- K3 max pooling ----
+  bf16* x = static_cast<bf16*>(big_slot(2, act_bytes(Mp, 64)));
+  if (!dry) {
+    steps.push_back([B, sh, stem_out, x](cudaStream_t s) {
+      return launch_maxpool(stem_out, B, sh.Hs, sh.Ws, 64, x, sh.Hp, sh.Wp, s);
+    });
+    taps["pool"] = {x, Mp, 64, 0};
+  }
+  int cur = 2, hh = sh.Hp, ww = sh.Wp, bi = 0;
+  for (int s = 0; s < 4; ++s) {
+    const int width = kStageWidth[s], mid = width / 4;
+    for (int l = 0; l < kStageDepth[s]; ++l, ++bi) {
+      const BlockW& bw = m->blocks[bi];
+      const int stride = bw.c1.stride;
+      const int ho = conv_out(hh, 3, stride, 1), wo = conv_out(ww, 3, stride, 1);
+      const long long m_in = (long long)B * hh * ww, m_out = (long long)B * ho * wo;
+      const bf16* res = x;
+      if (bw.has_shortcut) {
+        bf16* sc = static_cast<bf16*>(big_slot((cur + 1) % 3, act_bytes(m_out, width)));
+        if (int rc = conv(x, hh, ww, bw.shortcut, sc, EPI_BIAS, nullptr)) return rc;
+        res = sc;
+      }
+      bf16* m1 = static_cast<bf16*>(mid_slot(0, act_bytes(m_in, mid)));
+      bf16* m2 = static_cast<bf16*>(mid_slot(1, act_bytes(m_out, mid)));
+      bf16* out = static_cast<bf16*>(big_slot((cur + 2) % 3, act_bytes(m_out, width)));
+      if (int rc = conv(x, hh, ww, bw.c0, m1, EPI_BIAS_RELU, nullptr)) return rc;
+      if (int rc = conv(m1, hh, ww, bw.c1, m2, EPI_BIAS_RELU, nullptr)) return rc;
+      if (int rc = conv(m2, ho, wo, bw.c2, out, EPI_BIAS_RES_RELU, res)) return rc;
+      if (!dry) taps["stage" + std::to_string(s) + "." + std::to_string(l)] = {out, m_out, width, 0};
+      x = out;
+      cur = (cur + 2) % 3;
+      hh = ho;
+      ww = wo;
+    }
+  }
+
+  // ---- transformer ----
+  const int S = hh * ww;
+  const int M = B * S, Mq = B * kQueries;
+  float* pos = static_cast<float*>(A.take((size_t)S * kD * sizeof(float)));
+  bf16* ex = static_cast<bf16*>(A.take(act_bytes(M, kD)));     // encoder stream
+  bf16* ex1 = static_cast<bf16*>(A.take(act_bytes(M, kD)));    // after attention + LN
+  bf16* exp_ = static_cast<bf16*>(A.take(act_bytes(M, kD)));   // stream + pos (q / k input)
+  bf16* eqk = static_cast<bf16*>(A.take(act_bytes(M, 2 * kD)));
+  bf16* ev = static_cast<bf16*>(A.take(act_bytes(M, kD)));
+  bf16* eo = static_cast<bf16*>(A.take(act_bytes(M, kD)));
+  bf16* ef = static_cast<bf16*>(A.take(act_bytes(M, kFFN)));
+  bf16* memk = static_cast<bf16*>(A.take(act_bytes(M, kDec * kD)));
+  bf16* memv = static_cast<bf16*>(A.take(act_bytes(M, kDec * kD)));
+  bf16* dy = static_cast<bf16*>(A.take(act_bytes(Mq, kD)));
+  bf16* dy1 = static_cast<bf16*>(A.take(act_bytes(Mq, kD)));
+  bf16* dy2 = static_cast<bf16*>(A.take(act_bytes(Mq, kD)));
+  bf16* dyp = static_cast<bf16*>(A.take(act_bytes(Mq, kD)));
+  bf16* dqk = static_cast<bf16*>(A.take(act_bytes(Mq, 2 * kD)));
+  bf16* dv = static_cast<bf16*>(A.take(act_bytes(Mq, kD)));
+  bf16* dq = static_cast<bf16*>(A.take(act_bytes(Mq, kD)));
+  bf16* dob = static_cast<bf16*>(A.take(act_bytes(Mq, kD)));
+  bf16* df = static_cast<bf16*>(A.take(act_bytes(Mq, kFFN)));
+  bf16* dout = static_cast<bf16*>(A.take(act_bytes(Mq, kD)));
+  // layer outputs: written in place over the stream buffer, or one buffer per layer when debugging (taps)
+  bf16* enc_out[kEnc];
+  bf16* dec_out[kDec];
+  for (int i = 0; i < kEnc; ++i) enc_out[i] = dbg ? static_cast<bf16*>(A.take(act_bytes(M, kD))) : ex;
+  for (int i = 0; i < kDec; ++i) dec_out[i] = dbg ? static_cast<bf16*>(A.take(act_bytes(Mq, kD))) : dy;
+
+  *bytes_out = (A.off + 1023) & ~(size_t)1023;
+  if (dry) return OPD_OK;
+
+  auto linear = [&](const bf16* a, int rows, const LinW& w, bf16* d, int epi, const bf16* res, const LnW* ln, bf16* d2,
+                    const float* posv, int pos_rows) -> int {
+    GemmPlan gp;
+    if (int rc = gemm_plan_linear(&gp, a, w.k, w.w, d, w.n, rows, w.n, w.k, epi, w.b, res, kD, ln ? ln->g : nullptr,
+                                  ln ? ln->b : nullptr, d2, posv, pos_rows))
+      return rc;
+    add_gemm(gp);
+    return OPD_OK;
+  };
+  auto attn = [&](const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int Lq, int Lk) {
+    steps.push_back([=](cudaStream_t s) { return launch_attention(q, ldq, k, ldk, v, ldv, o, kD, B, kHeads, Lq, Lk, s); });
+  };
+
+  steps.push_back([pos, hh, ww](cudaStream_t s) { return launch_pos_embed(pos, hh, ww, s); });
+  taps["pos"] = {pos, S, kD, 1};
+  // input_projection (+ pos for the first layer's q / k input)
+  if (int rc = linear(x, M, m->input_proj, ex, EPI_BIAS, nullptr, nullptr, exp_, pos, S)) return rc;
+  taps["enc_in"] = {ex, M, kD, 0};
+
+  bf16* xin = ex;
+  for (int i = 0; i < kEnc; ++i) {
+    const EncW& e = m->enc[i];
+    bf16* xout = enc_out[i];   // == xin unless debugging
+    if (int rc = linear(exp_, M, e.qk, eqk, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+    if (int rc = linear(xin, M, e.v, ev, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+    attn(eqk, 2 * kD, eqk + kD, 2 * kD, ev, kD, eo, S, S);
+    if (int rc = linear(eo, M, e.o, ex1, EPI_BIAS_RES_LN, xin, &e.ln1, nullptr, nullptr, 0)) return rc;
+    if (int rc = linear(ex1, M, e.fc1, ef, EPI_BIAS_RELU, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+    // layer output overwrites the layer input stream (its last reader, the o_proj residual, has completed)
+    if (int rc = linear(ef, M, e.fc2, xout, EPI_BIAS_RES_LN, ex1, &e.ln2, exp_, pos, S)) return rc;
+    taps["enc" + std::to_string(i)] = {xout, M, kD, 0};
+    xin = xout;
+  }
+  const bf16* memory = xin;        // encoder output
+  const bf16* memory_pos = exp_;   // + pos: keys of every cross attention
+  if (int rc = linear(memory_pos, M, m->cross_k_all, memk, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+  if (int rc = linear(memory, M, m->cross_v_all, memv, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+
+  steps.push_back([m, dy, dyp, B](cudaStream_t s) { return launch_decoder_init(dy, dyp, m->qpos, B, kQueries, s); });
+  bf16* yin = dy;
+  for (int i = 0; i < kDec; ++i) {
+    const DecW& d = m->dec[i];
+    bf16* yout = dec_out[i];
+    // self attention
+    if (int rc = linear(dyp, Mq, d.sqk, dqk, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+    if (int rc = linear(yin, Mq, d.sv, dv, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+    attn(dqk, 2 * kD, dqk + kD, 2 * kD, dv, kD, dob, kQueries, kQueries);
+    if (int rc = linear(dob, Mq, d.so, dy1, EPI_BIAS_RES_LN, yin, &d.ln1, dyp, m->qpos, kQueries)) return rc;
+    // cross attention
+    if (int rc = linear(dyp, Mq, d.cq, dq, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+    attn(dq, kD, memk + i * kD, kDec * kD, memv + i * kD, kDec * kD, dob, kQueries, S);
+    if (int rc = linear(dob, Mq, d.co, dy2, EPI_BIAS_RES_LN, dy1, &d.ln2, nullptr, nullptr, 0)) return rc;
+    // FFN
+    if (int rc = linear(dy2, Mq, d.fc1, df, EPI_BIAS_RELU, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+    if (int rc = linear(df, Mq, d.fc2, yout, EPI_BIAS_RES_LN, dy2, &d.ln3, dyp, m->qpos, kQueries)) return rc;
+    taps["dec" + std::to_string(i)] = {yout, Mq, kD, 0};
+    yin = yout;
+  }
+  steps.push_back([m, yin, dout, Mq](cudaStream_t s) { return launch_layernorm(yin, m->dec_norm.g, m->dec_norm.b, dout, Mq, s); });
+  taps["dec_out"] = {dout, Mq, kD, 0};
+  steps.push_back([m, dout, Mq](cudaStream_t s) { return launch_heads(dout, m->heads, m->cur_logits, m->cur_boxes, Mq, s); });
+  return OPD_OK;
+}
+
+}  // namespace
+}  // namespace opd
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int opd_detr_create(const opd_tensor_f32* tensors, int32_t n_tensors, int32_t device, opd_detr** out) {
+  OPD_REQUIRE(tensors && n_tensors > 0 && out, "opd_detr_create: NULL argument");
+  OPD_CUDA_OK(cudaSetDevice(device));
+  opd_detr* m = new opd_detr();
+  m->device = device;
+  const int rc = opd::load_weights(m, tensors, n_tensors);
+  if (rc != OPD_OK) {
+    opd_detr_destroy(m);
+    return rc;
+  }
+  OPD_CUDA_OK(cudaDeviceSynchronize());
+  *out = m;
+  return OPD_OK;
+}
+
+void opd_detr_destroy(opd_detr* m) {
+  if (!m) return;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+}
+
+int opd_detr_set_debug(opd_detr* m, int32_t debug) {
+  OPD_REQUIRE(m, "opd_detr_set_debug: NULL handle");
+  m->debug = debug;
+  m->plan = opd::Plan{};
+  return OPD_OK;
+}
+
+int opd_detr_set_resize(opd_detr* m, int32_t do_resize) {
+  OPD_REQUIRE(m, "opd_detr_set_resize: NULL handle");
+  m->do_resize = do_resize;
+  m->plan = opd::Plan{};
+  return OPD_OK;
+}
+
+int opd_detr_input_shape(int32_t H0, int32_t W0, int32_t* H_in, int32_t* W_in, int32_t* h_feat, int32_t* w_feat) {
+  OPD_REQUIRE(H0 > 0 && W0 > 0, "opd_detr_input_shape: bad frame size %dx%d", H0, W0);
+  const opd::Shapes s = opd::shapes_for(H0, W0);
+  if (H_in) *H_in = s.Hin;
+  if (W_in) *W_in = s.Win;
+  if (h_feat) *h_feat = s.h[3];
+  if (w_feat) *w_feat = s.w[3];
+  return OPD_OK;
+}
+
+int opd_detr_workspace_bytes(const opd_detr* m, int32_t B, int32_t H0, int32_t W0, size_t* bytes) {
+  OPD_REQUIRE(m && bytes && B > 0 && H0 > 0 && W0 > 0, "opd_detr_workspace_bytes: bad argument");
+  opd::Plan scratch;
+  return opd::build_plan(const_cast<opd_detr*>(m), B, H0, W0, nullptr, &scratch, bytes);
+}
+
+int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t H0, int32_t W0, int32_t frames_are_bgr,
+                     void* workspace_dev, size_t workspace_bytes, float* logits_dev, float* boxes_dev, void* stream) {
+  OPD_REQUIRE(m && frames_dev && workspace_dev && logits_dev && boxes_dev, "opd_detr_forward: NULL argument");
+  OPD_REQUIRE(B > 0 && (long long)B * opd::kQueries < (1 << 24), "opd_detr_forward: bad batch %d", B);
+  OPD_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) == 0, "opd_detr_forward: workspace must be 1024-byte aligned");
+  opd::Plan& p = m->plan;
+  if (p.B != B || p.H0 != H0 || p.W0 != W0 || p.ws != workspace_dev || p.steps.empty()) {
+    p = opd::Plan{};
+    size_t need = 0;
+    if (int rc = opd::build_plan(m, B, H0, W0, workspace_dev, &p, &need)) {
+      p = opd::Plan{};
+      return rc;
+    }
+    if (need > workspace_bytes) {
+      p = opd::Plan{};
+      return opd::fail(OPD_ERR_INVALID, "opd_detr_forward: workspace of %zu bytes, %zu needed", workspace_bytes, need);
+    }
+    p.B = B; p.H0 = H0; p.W0 = W0; p.ws = workspace_dev; p.ws_bytes = need;
+  }
+  m->cur_frames = frames_dev;
+  m->cur_bgr = frames_are_bgr;
+  m->cur_logits = logits_dev;
+  m->cur_boxes = boxes_dev;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (auto& step : p.steps)
+    if (int rc = step(s)) return rc;
+  return OPD_OK;
+}
+
+int opd_detr_tap(const opd_detr* m, const char* name, const void** ptr_dev, int64_t* rows, int64_t* cols, int32_t* is_f32) {
+  OPD_REQUIRE(m && name && ptr_dev && rows && cols && is_f32, "opd_detr_tap: NULL argument");
+  auto it = m->plan.taps.find(name);
+  OPD_REQUIRE(it != m->plan.taps.end(), "opd_detr_tap: no activation named '%s' (run a forward first)", name);
+  *ptr_dev = it->second.ptr;
+  *rows = it->second.rows;
+  *cols = it->second.cols;
+  *is_f32 = it->second.is_f32;
+  return OPD_OK;
+}
+
+int opd_detr_tap_copy(const opd_detr* m, const char* name, void* dst_dev, size_t bytes, void* stream) {
+  const void* src = nullptr;
+  int64_t rows = 0, cols = 0;
+  int32_t f32 = 0;
+  if (int rc = opd_detr_tap(m, name, &src, &rows, &cols, &f32)) return rc;
+  OPD_REQUIRE(dst_dev && bytes == (size_t)rows * cols * (f32 ? 4 : 2), "opd_detr_tap_copy: '%s' is %lld x %lld (%s)", name,
+              (long long)rows, (long long)cols, f32 ? "f32" : "bf16");
+  OPD_CUDA_OK(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return OPD_OK;
+}
+
+int opd_detr_postprocess(const float* logits_dev, const float* boxes_dev, int32_t B, int32_t Q, int32_t C, int32_t H0,
+                         int32_t W0, float threshold, int32_t person_label, float* scores_dev, int32_t* labels_dev,
+                         float* xyxy_dev, float* det_xywh_dev, float* det_score_dev, double* det_foot_dev,
+                         int32_t* det_query_dev, int32_t* n_keep_dev, void* stream) {
+  OPD_REQUIRE(logits_dev && boxes_dev && scores_dev && labels_dev && xyxy_dev && det_xywh_dev && det_score_dev &&
+                  det_foot_dev && det_query_dev && n_keep_dev,
+              "opd_detr_postprocess: NULL argument");
+  OPD_REQUIRE(B > 0 && Q > 0 && C > 1, "opd_detr_postprocess: bad shape B=%d Q=%d C=%d", B, Q, C);
+  return opd::launch_postprocess(logits_dev, boxes_dev, B, Q, C, H0, W0, threshold, person_label, scores_dev, labels_dev,
+                                 xyxy_dev, det_xywh_dev, det_score_dev, det_foot_dev, det_query_dev, n_keep_dev,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,315 @@
+"""DETR-ResNet-50 person detector on the GPU, with the call surface of the reference's detector.
+
+Surface kept: the removed `src/detection/vit_detector.py` ViTDetector
+(`__init__(model_name, confidence_threshold, device)`, `load_model`, `detect`, `detect_batch`, `_get_foot_position`,
+attributes `model`, `device`, `confidence_threshold`; method table in the reference's coverage.json) and its surviving
+drop-in twin `src/detection/yolov8_detector.py:26-254` (same signatures, `RuntimeError("Model not loaded. Call
+load_model() first.")` before load, `Detection(bbox=(x,y,w,h), confidence, class_id, class_name="person",
+camera_coords=foot)` records).
+
+All arithmetic runs in libopd_b200.so (csrc/detr_engine.cu): preprocessing, ResNet-50, transformer, heads and
+post-processing are hand-written sm_100a kernels; torch tensors are device buffers only.  There is no CPU path.
+
+Tensor entries (north star): `forward_raw(frames_u8)` -> (logits [B,100,92], boxes [B,100,4]) and
+`detect_tensors(frames_u8)` -> compacted per-frame person detections as device tensors (no Python objects).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from pathlib import Path
+from typing import Sequence
+
+import numpy as np
+
+from .. import _lib
+from ..models import Detection
+
+logger = logging.getLogger(__name__)
+
+_P = C.c_void_p
+
+
+class _TensorF32(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_int64)]
+
+
+_lib.register("opd_detr_create", C.c_int, [C.POINTER(_TensorF32), C.c_int32, C.c_int32, C.POINTER(_P)])
+_lib.register("opd_detr_destroy", None, [_P])
+_lib.register("opd_detr_set_debug", C.c_int, [_P, C.c_int32])
+_lib.register("opd_detr_set_resize", C.c_int, [_P, C.c_int32])
+_lib.register("opd_detr_input_shape", C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)])
+_lib.register("opd_detr_workspace_bytes", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
+_lib.register("opd_detr_forward", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_size_t, _P, _P,
+                                           _P])
+_lib.register("opd_detr_tap", C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int32)])
+_lib.register("opd_detr_tap_copy", C.c_int, [_P, C.c_char_p, _P, C.c_size_t, _P])
+_lib.register("opd_detr_postprocess", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                               C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P])
+
+N_QUERIES = 100
+N_LOGITS = 92
+PERSON_LABEL = 1   # COCO id of "person" in facebook/detr-resnet-50 (reference tests use class_id=1)
+
+# transformers 4.x state-dict names -> the 5.x names the library expects (both are accepted by load_model)
+_KEY_RENAMES = (
+    ("model.backbone.conv_encoder.model.", "model.backbone.model."),
+    (".fc1.", ".mlp.fc1."),
+    (".fc2.", ".mlp.fc2."),
+    (".self_attn.out_proj.", ".self_attn.o_proj."),
+    (".encoder_attn.out_proj.", ".encoder_attn.o_proj."),
+)
+
+
+def input_shape(h0: int, w0: int) -> tuple[int, int, int, int]:
+    """(H_in, W_in, h_feat, w_feat): model input size (800/1333 rule) and stage-4 feature map of an h0 x w0 frame."""
+    out = [C.c_int32() for _ in range(4)]
+    _lib.check(_lib.lib().opd_detr_input_shape(h0, w0, *[C.byref(o) for o in out]), "opd_detr_input_shape")
+    return tuple(o.value for o in out)
+
+
+class DetrEngine:
+    """Handle of the device-resident model + a cached workspace per (B, H0, W0)."""
+
+    def __init__(self, state_dict: dict, device_index: int | None = None):
+        torch = _lib.require_cuda()
+        self.device_index = torch.cuda.current_device() if device_index is None else int(device_index)
+        names, arrays = [], []
+        for k, v in state_dict.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            if ".mlp." not in k:
+                for old, new in _KEY_RENAMES:
+                    if old in k:
+                        k = k.replace(old, new)
+            arr = v.detach().to("cpu", torch.float32).contiguous().numpy() if hasattr(v, "detach") else \
+                np.ascontiguousarray(v, dtype=np.float32)
+            names.append(k.encode())
+            arrays.append(arr)
+        tens = (_TensorF32 * len(names))()
+        for i, (n, a) in enumerate(zip(names, arrays)):
+            tens[i].name, tens[i].data, tens[i].numel = n, a.ctypes.data, a.size
+        handle = _P()
+        _lib.check(_lib.lib().opd_detr_create(tens, len(names), self.device_index, C.byref(handle)), "opd_detr_create")
+        self._h = handle.value
+        self._ws: dict[tuple[int, int, int], object] = {}
+        self._torch = torch
+
+    def set_debug(self, on: bool) -> None:
+        _lib.check(_lib.lib().opd_detr_set_debug(self._h, int(on)), "opd_detr_set_debug")
+        self._ws.clear()
+
+    def set_resize(self, on: bool) -> None:
+        """False: frames are fed at their own size, like DetrImageProcessor(do_resize=False)."""
+        _lib.check(_lib.lib().opd_detr_set_resize(self._h, int(on)), "opd_detr_set_resize")
+        self._ws.clear()
+
+    def workspace(self, B: int, H0: int, W0: int):
+        key = (B, H0, W0)
+        ws = self._ws.get(key)
+        if ws is None:
+            n = C.c_size_t()
+            _lib.check(_lib.lib().opd_detr_workspace_bytes(self._h, B, H0, W0, C.byref(n)), "opd_detr_workspace_bytes")
+            ws = self._torch.empty(n.value + 1024, dtype=self._torch.uint8, device=f"cuda:{self.device_index}")
+            self._ws[key] = ws
+        return ws
+
+    def forward(self, frames, bgr: bool = True, logits=None, boxes=None):
+        """frames [B,H0,W0,3] uint8 CUDA tensor -> (logits [B,100,92] f32, boxes [B,100,4] f32 cxcywh in [0,1])."""
+        torch = self._torch
+        if not (frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3
+                and frames.is_contiguous()):
+            raise ValueError("frames must be a contiguous [B,H,W,3] uint8 CUDA tensor")
+        B, H0, W0, _ = frames.shape
+        ws = self.workspace(B, H0, W0)
+        base = (ws.data_ptr() + 1023) & ~1023
+        if logits is None:
+            logits = torch.empty(B, N_QUERIES, N_LOGITS, dtype=torch.float32, device=frames.device)
+        if boxes is None:
+            boxes = torch.empty(B, N_QUERIES, 4, dtype=torch.float32, device=frames.device)
+        rc = _lib.lib().opd_detr_forward(self._h, frames.data_ptr(), B, H0, W0, int(bgr), base,
+                                         ws.numel() - (base - ws.data_ptr()), logits.data_ptr(), boxes.data_ptr(),
+                                         _lib.stream_ptr())
+        _lib.check(rc, "opd_detr_forward")
+        return logits, boxes
+
+    def tap(self, name: str):
+        """Copy of a named internal activation of the last forward (needs set_debug(True) for the reused ones)."""
+        torch = self._torch
+        p, rows, cols, f32 = _P(), C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(_lib.lib().opd_detr_tap(self._h, name.encode(), C.byref(p), C.byref(rows), C.byref(cols), C.byref(f32)),
+                   "opd_detr_tap")
+        dt = torch.float32 if f32.value else torch.bfloat16
+        out = torch.empty(rows.value, cols.value, dtype=dt, device=f"cuda:{self.device_index}")
+        _lib.check(_lib.lib().opd_detr_tap_copy(self._h, name.encode(), out.data_ptr(), out.numel() * out.element_size(),
+                                                _lib.stream_ptr()), "opd_detr_tap_copy")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().opd_detr_destroy(self._h)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+def postprocess_tensors(logits, boxes, h0: int, w0: int, threshold: float, person_label: int = PERSON_LABEL) -> dict:
+    """K8b on device tensors: per-query scores / labels / xyxy and the compacted person detections per frame."""
+    torch = _lib.require_cuda()
+    B, Q, Cn = logits.shape
+    dev = logits.device
+    out = {
+        "scores": torch.empty(B, Q, dtype=torch.float32, device=dev),
+        "labels": torch.empty(B, Q, dtype=torch.int32, device=dev),
+        "xyxy": torch.empty(B, Q, 4, dtype=torch.float32, device=dev),
+        "det_xywh": torch.zeros(B, Q, 4, dtype=torch.float32, device=dev),
+        "det_score": torch.zeros(B, Q, dtype=torch.float32, device=dev),
+        "det_foot": torch.zeros(B, Q, 2, dtype=torch.float64, device=dev),
+        "det_query": torch.full((B, Q), -1, dtype=torch.int32, device=dev),
+        "n_keep": torch.empty(B, dtype=torch.int32, device=dev),
+    }
+    rc = _lib.lib().opd_detr_postprocess(
+        logits.data_ptr(), boxes.data_ptr(), B, Q, Cn, h0, w0, float(threshold), person_label,
+        out["scores"].data_ptr(), out["labels"].data_ptr(), out["xyxy"].data_ptr(), out["det_xywh"].data_ptr(),
+        out["det_score"].data_ptr(), out["det_foot"].data_ptr(), out["det_query"].data_ptr(), out["n_keep"].data_ptr(),
+        _lib.stream_ptr())
+    _lib.check(rc, "opd_detr_postprocess")
+    return out
+
+
+class ViTDetector:
+    """Person detector with the reference's ViTDetector / YOLOv8Detector surface, backed by libopd_b200.so."""
+
+    def __init__(self, model_name: str = "facebook/detr-resnet-50", confidence_threshold: float = 0.5,
+                 device: str | None = None, state_dict: dict | None = None, batch_size: int = 64):
+        self.model_name = model_name
+        self.confidence_threshold = confidence_threshold
+        self.device = self._setup_device(device)
+        self.batch_size = int(batch_size)
+        self.model: DetrEngine | None = None
+        self._state_dict = state_dict
+        logger.info(f"ViTDetector initialized with model: {model_name}")
+        logger.info(f"Using device: {self.device}")
+        logger.info(f"Confidence threshold: {confidence_threshold}")
+
+    def _setup_device(self, device: str | None = None) -> str:
+        """The reference falls back mps -> cuda -> cpu; this implementation is CUDA only and says so loudly."""
+        if device is None:
+            return "cuda"
+        if not str(device).startswith("cuda"):
+            raise ValueError(f"device={device!r}: office_person_detection_vit_b200 runs on CUDA (sm_100a) only")
+        return str(device)
+
+    def _device_index(self) -> int:
+        torch = _lib.require_cuda()
+        return int(self.device.split(":")[1]) if ":" in self.device else torch.cuda.current_device()
+
+    def load_model(self) -> None:
+        """Builds the device copy of the weights.  Weights come from `state_dict=` (transformers DETR key names) or,
+        when `model_name` is a local file / directory, from `pytorch_model.bin` / `*.pt` / `*.safetensors` in it.
+        There is no network in this environment, so a hub id without local weights raises RuntimeError."""
+        try:
+            sd = self._state_dict
+            if sd is None:
+                sd = self._load_local_state_dict(Path(self.model_name))
+            self.model = DetrEngine(sd, self._device_index())
+            logger.info(f"Model loaded: {self.model_name}")
+        except Exception as e:
+            logger.error(f"Failed to load model: {e}")
+            raise RuntimeError(f"Failed to load DETR model: {e}") from e
+
+    @staticmethod
+    def _load_local_state_dict(path: Path) -> dict:
+        import torch
+
+        if path.is_dir():
+            for name in ("model.safetensors", "pytorch_model.bin"):
+                if (path / name).exists():
+                    path = path / name
+                    break
+        if not path.is_file():
+            raise FileNotFoundError(f"no local weights at {path} (pass state_dict= or a local checkpoint; no network access)")
+        if path.suffix == ".safetensors":
+            from safetensors.torch import load_file
+
+            return load_file(str(path))
+        sd = torch.load(str(path), map_location="cpu", weights_only=True)
+        return sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+
+    # ---- tensor entries ------------------------------------------------------------------------------------
+    def forward_raw(self, frames, bgr: bool = True):
+        if self.model is None:
+            raise RuntimeError("Model not loaded. Call load_model() first.")
+        return self.model.forward(frames, bgr=bgr)
+
+    def detect_tensors(self, frames, bgr: bool = True, threshold: float | None = None) -> dict:
+        """frames [B,H,W,3] uint8 CUDA tensor -> dict of device tensors (see postprocess_tensors); no host sync."""
+        logits, boxes = self.forward_raw(frames, bgr=bgr)
+        _, H0, W0, _ = frames.shape
+        thr = self.confidence_threshold if threshold is None else threshold
+        out = postprocess_tensors(logits, boxes, H0, W0, thr)
+        out["logits"], out["boxes"] = logits, boxes
+        return out
+
+    # ---- reference surface ---------------------------------------------------------------------------------
+    def detect(self, frame: np.ndarray) -> list[Detection]:
+        """frame: BGR uint8 ndarray [H,W,3] -> list[Detection]."""
+        if self.model is None:
+            raise RuntimeError("Model not loaded. Call load_model() first.")
+        try:
+            return self.detect_batch([frame])[0]
+        except Exception as e:
+            logger.error(f"Detection failed: {e}")
+            raise
+
+    def detect_batch(self, frames: Sequence[np.ndarray]) -> list[list[Detection]]:
+        """Batched detection.  Frames of equal size run as one device batch (chunks of `batch_size`); frames of
+        different sizes are grouped by size (the reference pads to the batch maximum instead: different arithmetic at
+        the padded borders, so equal-size groups are the faithful choice here)."""
+        if self.model is None:
+            raise RuntimeError("Model not loaded. Call load_model() first.")
+        torch = _lib.require_cuda()
+        results: list[list[Detection] | None] = [None] * len(frames)
+        groups: dict[tuple[int, int], list[int]] = {}
+        for i, f in enumerate(frames):
+            f = np.asarray(f)
+            if f.ndim != 3 or f.shape[2] != 3 or f.dtype != np.uint8:
+                raise ValueError(f"frame {i}: expected a uint8 [H,W,3] BGR array, got {f.dtype} {f.shape}")
+            groups.setdefault((f.shape[0], f.shape[1]), []).append(i)
+        dev = torch.device("cuda", self._device_index())
+        for (h0, w0), idxs in groups.items():
+            for c0 in range(0, len(idxs), self.batch_size):
+                chunk = idxs[c0:c0 + self.batch_size]
+                host = torch.from_numpy(np.stack([np.ascontiguousarray(frames[i]) for i in chunk])).pin_memory()
+                out = self.detect_tensors(host.to(dev, non_blocking=True))
+                n_keep = out["n_keep"].cpu().numpy()
+                xywh = out["det_xywh"].cpu().numpy().astype(np.float64)
+                score = out["det_score"].cpu().numpy()
+                foot = out["det_foot"].cpu().numpy()
+                query = out["det_query"].cpu().numpy()
+                for j, i in enumerate(chunk):
+                    dets = []
+                    for r in range(int(n_keep[j])):
+                        x, y, w, h = (float(v) for v in xywh[j, r])
+                        dets.append(Detection(bbox=(x, y, w, h), confidence=float(score[j, r]), class_id=PERSON_LABEL,
+                                              class_name="person", camera_coords=(float(foot[j, r, 0]), float(foot[j, r, 1])),
+                                              query_index=int(query[j, r])))
+                    results[i] = dets
+        return [r if r is not None else [] for r in results]
+
+    def _get_foot_position(self, bbox: tuple[float, float, float, float]) -> tuple[float, float]:
+        x, y, w, h = bbox
+        return (x + w / 2, y + h)
+
+    def detect_with_features(self, frame: np.ndarray):
+        raise NotImplementedError("encoder ROI features are the next scope row (SURVEY.md §8f.4)")
+
+    def extract_features(self, frame: np.ndarray, detections: list[Detection]):
+        raise NotImplementedError("encoder ROI features are the next scope row (SURVEY.md §8f.4)")
+
+    def get_attention_map(self, _frame: np.ndarray, _layer_index: int = -1):
+        logger.warning("Attention maps are a debug aid of the reference and are not produced by the fused attention kernel")
+        return None

@@ -40,6 +40,10 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+# data generators shared by both sides of every parity test (no arithmetic of the model lives there)
+from office_person_detection_vit_b200.detection.synthetic import (  # noqa: E402,F401
+    conv_specs, random_init_state_dict as make_weights, synthetic_frames)
+
 STAGE_DEPTHS = (3, 4, 6, 3)
 STAGE_WIDTHS = (256, 512, 1024, 2048)
 EMBED = 64
@@ -55,99 +59,6 @@ IMAGE_MEAN = (0.485, 0.456, 0.406)
 IMAGE_STD = (0.229, 0.224, 0.225)
 BN_EPS = 1e-5
 LN_EPS = 1e-5
-
-
-# ------------------------------------------------------------------------------------------------------------
-# weights
-# ------------------------------------------------------------------------------------------------------------
-def conv_specs():
-    """(hf_prefix, c_in, c_out, k, stride) of every backbone convolution, in execution order."""
-    specs = [("model.backbone.model.embedder.embedder", 3, EMBED, 7, 2)]
-    c_in = EMBED
-    for s, (depth, width) in enumerate(zip(STAGE_DEPTHS, STAGE_WIDTHS)):
-        mid = width // 4
-        for l in range(depth):
-            stride = 2 if (l == 0 and s > 0) else 1
-            p = f"model.backbone.model.encoder.stages.{s}.layers.{l}"
-            if l == 0:
-                specs.append((p + ".shortcut", c_in, width, 1, stride))
-            specs.append((p + ".layer.0", c_in, mid, 1, 1))
-            specs.append((p + ".layer.1", mid, mid, 3, stride))
-            specs.append((p + ".layer.2", mid, width, 1, 1))
-            c_in = width
-    return specs
-
-
-def make_weights(seed: int = 0) -> dict[str, torch.Tensor]:
-    """Seeded random-init DETR-R50 state dict (transformers key names, float32).
-
-    transformers' default init is degenerate for parity purposes (every query yields the same box, no score
-    crosses 0.5 — SURVEY.md H2), so the variances are re-scaled: He-init convolutions with non-trivial frozen-BN
-    statistics, unit-scale attention / FFN weights, wide query embeddings and heads.  Both sides of every
-    parity test load this same dict.
-    """
-    g = torch.Generator().manual_seed(seed)
-
-    def randn(*shape, std=1.0):
-        return torch.randn(*shape, generator=g, dtype=torch.float32) * std
-
-    def rand(*shape, lo=0.0, hi=1.0):
-        return torch.rand(*shape, generator=g, dtype=torch.float32) * (hi - lo) + lo
-
-    w: dict[str, torch.Tensor] = {}
-    for prefix, c_in, c_out, k, _stride in conv_specs():
-        fan_in = c_in * k * k
-        w[prefix + ".convolution.weight"] = randn(c_out, c_in, k, k, std=math.sqrt(2.0 / fan_in))
-        last_of_block = prefix.endswith(".layer.2")
-        scale = 0.35 if last_of_block else 1.0          # keep the residual stream from blowing up
-        w[prefix + ".normalization.weight"] = rand(c_out, lo=0.6, hi=1.4) * scale
-        w[prefix + ".normalization.bias"] = randn(c_out, std=0.1)
-        w[prefix + ".normalization.running_mean"] = randn(c_out, std=0.1)
-        w[prefix + ".normalization.running_var"] = rand(c_out, lo=0.6, hi=1.4)
-
-    w["model.input_projection.weight"] = randn(D_MODEL, STAGE_WIDTHS[-1], 1, 1, std=0.2 / math.sqrt(STAGE_WIDTHS[-1]))
-    w["model.input_projection.bias"] = randn(D_MODEL, std=0.1)
-    w["model.query_position_embeddings.weight"] = randn(N_QUERIES, D_MODEL, std=1.0)
-
-    def linear(prefix, n_out, n_in, std=None, bias_std=0.05):
-        w[prefix + ".weight"] = randn(n_out, n_in, std=std if std is not None else 1.0 / math.sqrt(n_in))
-        w[prefix + ".bias"] = randn(n_out, std=bias_std)
-
-    def layer_norm(prefix):
-        w[prefix + ".weight"] = rand(D_MODEL, lo=0.8, hi=1.2)
-        w[prefix + ".bias"] = randn(D_MODEL, std=0.05)
-
-    def attn(prefix, qk_gain=1.0, o_gain=1.0):
-        # qk_gain > 1 sharpens the softmax so that different queries attend to different tokens; o_gain < 1 keeps
-        # the residual stream token-specific (random post-norm attention stacks otherwise collapse to one token)
-        for proj in ("q_proj", "k_proj", "v_proj", "o_proj"):
-            gain = qk_gain if proj in ("q_proj", "k_proj") else (o_gain if proj == "o_proj" else 1.0)
-            linear(f"{prefix}.{proj}", D_MODEL, D_MODEL, std=gain / math.sqrt(D_MODEL))
-
-    for i in range(N_ENC):
-        p = f"model.encoder.layers.{i}"
-        attn(p + ".self_attn", qk_gain=1.5, o_gain=0.3)
-        layer_norm(p + ".self_attn_layer_norm")
-        linear(p + ".mlp.fc1", FFN, D_MODEL)
-        linear(p + ".mlp.fc2", D_MODEL, FFN)
-        layer_norm(p + ".final_layer_norm")
-    for i in range(N_DEC):
-        p = f"model.decoder.layers.{i}"
-        attn(p + ".self_attn", qk_gain=1.5, o_gain=0.3)
-        layer_norm(p + ".self_attn_layer_norm")
-        attn(p + ".encoder_attn", qk_gain=3.0)
-        layer_norm(p + ".encoder_attn_layer_norm")
-        linear(p + ".mlp.fc1", FFN, D_MODEL)
-        linear(p + ".mlp.fc2", D_MODEL, FFN)
-        layer_norm(p + ".final_layer_norm")
-    layer_norm("model.decoder.layernorm")
-    linear("class_labels_classifier", N_CLASSES + 1, D_MODEL, std=0.2, bias_std=0.3)
-    # make "person" competitive so that a useful fraction of queries is a person above the usual thresholds
-    w["class_labels_classifier.bias"][PERSON_LABEL] += 13.4   # calibrated on synthetic_frames: person ~ the dominant class
-    linear("bbox_predictor.layers.0", D_MODEL, D_MODEL)
-    linear("bbox_predictor.layers.1", D_MODEL, D_MODEL)
-    linear("bbox_predictor.layers.2", 4, D_MODEL, std=0.12, bias_std=0.3)
-    return w
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -184,7 +95,7 @@ def resized_size(h: int, w: int, size: int = 800, max_size: int = 1333) -> tuple
     return size, (int(raw * w / h) if raw is not None else int(size * w / h))
 
 
-def preprocess(frames_bgr: np.ndarray | torch.Tensor) -> torch.Tensor:
+def preprocess(frames_bgr: np.ndarray | torch.Tensor, do_resize: bool = True) -> torch.Tensor:
     """[B,H0,W0,3] uint8 BGR -> pixel_values [B,3,H,W] float32 (all frames the same size: no padding, mask = 1).
 
     BGR->RGB (removed ViTDetector._preprocess, coverage.json lines 285-300), uint8 bilinear antialias resize
@@ -195,7 +106,7 @@ def preprocess(frames_bgr: np.ndarray | torch.Tensor) -> torch.Tensor:
     assert x.dtype == torch.uint8 and x.ndim == 4 and x.shape[-1] == 3
     x = x.flip(-1).permute(0, 3, 1, 2).contiguous()          # RGB, CHW
     h0, w0 = x.shape[-2:]
-    h, w = resized_size(h0, w0)
+    h, w = resized_size(h0, w0) if do_resize else (h0, w0)
     if (h, w) != (h0, w0):
         x = F.interpolate(x, size=(h, w), mode="bilinear", antialias=True, align_corners=False)
     mean = torch.tensor(IMAGE_MEAN) * 255.0       # float32, like transformers (tensor(mean) * (1 / rescale_factor))
@@ -293,10 +204,10 @@ def backbone(w: dict, pixel_values: torch.Tensor, mode: str = "fp32", taps: dict
 
 
 @torch.no_grad()
-def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None):
+def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None, do_resize: bool = True):
     """frames [B,H0,W0,3] uint8 BGR -> (logits [B,100,92], boxes cxcywh in [0,1] [B,100,4]), float32."""
     m = _Mode(mode)
-    pv = preprocess(frames_bgr)
+    pv = preprocess(frames_bgr, do_resize)
     if taps is not None:
         taps["pixel_values"] = pv
     feat = backbone(w, pv, mode, taps)
@@ -388,16 +299,3 @@ def hf_model(w: dict):
     missing, unexpected = model.load_state_dict(w, strict=False)
     assert not unexpected and all("num_batches_tracked" in k for k in missing), (missing, unexpected)
     return model
-
-
-def synthetic_frames(batch: int, h: int, w: int, seed: int = 1) -> np.ndarray:
-    """Synthetic BGR frames, uint8: large flat-colour rectangles (so that distant image regions give distinct
-    backbone features) with finer blocks and pixel noise on top."""
-    rng = np.random.default_rng(seed)
-
-    def blocks(size, amp):
-        c = rng.integers(-amp, amp + 1, (batch, (h + size - 1) // size, (w + size - 1) // size, 3), dtype=np.int16)
-        return np.repeat(np.repeat(c, size, axis=1), size, axis=2)[:, :h, :w]
-
-    img = 128 + blocks(192, 110) + blocks(32, 40) + rng.integers(-12, 13, (batch, h, w, 3), dtype=np.int16)
-    return np.clip(img, 0, 255).astype(np.uint8)

@@ -1,0 +1,119 @@
+"""GPU parity of the DETR-ResNet-50 detector (csrc/detr_engine.cu + kernels) through the C ABI and ViTDetector,
+against the CPU oracle (oracle/detr_oracle.py, pinned to transformers' own DetrForObjectDetection in
+tests/test_detr_oracle.py) on identical synthetic frames and identical seeded weights.
+
+Tolerances (DESIGN.md "numerics"): the CUDA path stores bf16 activations; the oracle's "bf16" mode rounds at the same
+points, so the remaining differences are fp32 accumulation order + bf16 rounding flips.  Measured bounds are asserted
+here with margin and written next to each check."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import detr_oracle as do
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return do.make_weights(0)
+
+
+@pytest.fixture(scope="module")
+def detector(weights, built_lib):
+    import torch
+
+    from office_person_detection_vit_b200.detection import ViTDetector
+
+    torch.cuda.init()
+    det = ViTDetector(confidence_threshold=0.5, state_dict=weights)
+    with pytest.raises(RuntimeError, match="Model not loaded"):
+        det.detect(np.zeros((8, 8, 3), np.uint8))
+    det.load_model()
+    return det
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def test_layer_taps_small_frame(detector, weights):
+    """Every stored activation of a small un-resized frame pair against the oracle's bf16 mode."""
+    import torch
+
+    eng = detector.model
+    eng.set_debug(True)
+    eng.set_resize(False)
+    try:
+        frames = do.synthetic_frames(2, 224, 320, seed=5)
+        taps: dict = {}
+        ref_logits, ref_boxes = do.forward(weights, frames, mode="bf16", taps=taps, do_resize=False)
+        logits, boxes = eng.forward(torch.from_numpy(frames).cuda())
+        torch.cuda.synchronize()
+        report = {}
+        for name, ref in taps.items():
+            if name == "pixel_values":
+                continue
+            got = eng.tap(name).float().cpu()
+            if ref.dim() == 4:                      # NCHW -> [B*H*W, C]
+                ref = ref.permute(0, 2, 3, 1).reshape(-1, ref.shape[1])
+            else:
+                ref = ref.reshape(-1, ref.shape[-1])
+            assert got.shape == ref.shape, (name, got.shape, ref.shape)
+            report[name] = _rel(got, ref)
+        print({k: f"{v:.2e}" for k, v in report.items()})
+        assert report["pos"] < 1e-5
+        bad = {k: v for k, v in report.items() if v > 3e-2}
+        assert not bad, bad
+        assert _rel(logits.cpu(), ref_logits) < 3e-2
+        assert float((boxes.cpu() - ref_boxes).abs().max()) < 2e-2
+    finally:
+        eng.set_debug(False)
+        eng.set_resize(True)
+
+
+def test_detections_800x1333(detector, weights):
+    """Config-2 shape (no resize needed): all 100 queries pre-threshold + the thresholded person set."""
+    import torch
+
+    frames = do.synthetic_frames(2, 800, 1333, seed=1)
+    ref_logits, ref_boxes = do.forward(weights, frames, mode="bf16")
+    out = detector.detect_tensors(torch.from_numpy(frames).cuda(), threshold=0.0)
+    torch.cuda.synchronize()
+    sc, lb, xyxy = do.postprocess(ref_logits, ref_boxes, 800, 1333)
+    d_box = float((out["xyxy"].cpu() - xyxy).abs().max())
+    d_score = float((out["scores"].cpu() - sc).abs().max())
+    agree = float((out["labels"].cpu() == lb).float().mean())
+    print(f"max |box| err {d_box:.4f} px, max |score| err {d_score:.5f}, label agreement {agree:.4f}")
+    assert d_box < 8.0 and d_score < 3e-2 and agree > 0.97
+
+    # device post-processing == oracle post-processing on the SAME logits / boxes (fp32, exact up to 1 ulp)
+    from office_person_detection_vit_b200.detection import postprocess_tensors
+
+    thr = float(sc.flatten().median())
+    pp = postprocess_tensors(ref_logits.cuda(), ref_boxes.cuda(), 800, 1333, thr)
+    ref_d = do.detections(ref_logits, ref_boxes, 800, 1333, thr)
+    n_keep = pp["n_keep"].cpu().tolist()
+    assert n_keep == [len(r) for r in ref_d]
+    for b, rows in enumerate(ref_d):
+        got = torch.cat([pp["det_xywh"][b, :n_keep[b]].cpu().double(), pp["det_score"][b, :n_keep[b], None].cpu().double(),
+                         pp["det_foot"][b, :n_keep[b]].cpu()], dim=1)
+        np.testing.assert_allclose(got.numpy(), np.array(rows).reshape(-1, 7), rtol=2e-6, atol=2e-4)
+
+
+def test_detect_batch_surface(detector, weights):
+    frames = do.synthetic_frames(3, 800, 1333, seed=2)
+    res = detector.detect_batch([f for f in frames])
+    assert len(res) == 3
+    one = detector.detect(frames[1])
+    assert [d.bbox for d in one] == [d.bbox for d in res[1]]
+    for dets in res:
+        for d in dets:
+            assert d.class_name == "person" and d.class_id == 1 and d.confidence > 0.5
+            x, y, w, h = d.bbox
+            assert d.camera_coords == pytest.approx((x + w / 2, y + h))
+            assert detector._get_foot_position(d.bbox) == pytest.approx(d.camera_coords)
+    assert detector.detect_batch([]) == []
