@@ -17,7 +17,7 @@ import torch  # noqa: E402
 
 from office_person_detection_vit_b200.transform import FloorMapConfig, HomographyTransformer  # noqa: E402
 from office_person_detection_vit_b200.zone import ZoneClassifier  # noqa: E402
-from oracle.floor_oracle import H_CONFIG, grid_zones, star_zones  # noqa: E402  (workload generators only)
+from office_person_detection_vit_b200.scene import H_CONFIG, grid_zones, star_zones  # noqa: E402
 
 
 def main():

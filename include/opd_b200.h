@@ -174,6 +174,15 @@ int opd_detr_workspace_bytes(const opd_detr* m, int32_t B, int32_t H0, int32_t W
 int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t H0, int32_t W0,
                      int32_t frames_are_bgr, void* workspace_dev, size_t workspace_bytes, float* logits_dev,
                      float* boxes_dev, void* stream);
+/* Per-kernel timing of one more forward with the arguments of the last opd_detr_forward: a CUDA event is recorded
+ * on `stream` between consecutive launches (the kernels still run back to back on that stream).  Synchronises.
+ * Call with max_steps = 0 to get *n_steps.  kinds[i] is an opd_step_kind, flops[i] / bytes[i] are the ALGORITHMIC
+ * figures of launch i (2*M*N*K; operands + result once), names [n, name_stride] chars. */
+typedef enum opd_step_kind {
+  OPD_STEP_ELEMENTWISE = 0, OPD_STEP_GEMM = 1, OPD_STEP_CONV = 2, OPD_STEP_ATTENTION = 3, OPD_STEP_HEADS = 4
+} opd_step_kind;
+int opd_detr_profile(opd_detr* m, void* stream, int32_t max_steps, int32_t* n_steps, int32_t* kinds, double* flops,
+                     double* bytes, float* ms, char* names, int32_t name_stride);
 /* Named internal activation of the last forward (tests): "pixel_values", "stem", "pool", "stage{s}.{l}",
  * "enc_in", "pos", "enc{i}", "dec{i}", "dec_out".  rows x cols, bf16 unless *is_f32. */
 int opd_detr_tap(const opd_detr* m, const char* name, const void** ptr_dev, int64_t* rows, int64_t* cols,
@@ -183,11 +192,14 @@ int opd_detr_tap_copy(const opd_detr* m, const char* name, void* dst_dev, size_t
 /* post_process_object_detection + person filter (image_processing_detr.py:826-843; yolov8_detector.py:210-241):
  * per query: scores_dev [B,Q], labels_dev [B,Q], xyxy_dev [B,Q,4] (pixels of the ORIGINAL H0 x W0 frame);
  * per frame, compacted in query order: det_xywh_dev [B,Q,4], det_score_dev [B,Q], det_foot_dev [B,Q,2] f64,
- * det_query_dev [B,Q], n_keep_dev [B]  for  score > threshold && label == person_label. */
+ * det_query_dev [B,Q], n_keep_dev [B]  for  score > threshold && label == person_label;
+ * det_slot_dev [B,Q] (optional) = slot_base + frame for the compacted rows, -1 for the unused ones: the
+ * `slot_dev` argument of opd_floor_project_classify_count_* when the whole [B*Q] block is projected. */
 int opd_detr_postprocess(const float* logits_dev, const float* boxes_dev, int32_t B, int32_t Q, int32_t C,
                          int32_t H0, int32_t W0, float threshold, int32_t person_label, float* scores_dev,
                          int32_t* labels_dev, float* xyxy_dev, float* det_xywh_dev, float* det_score_dev,
-                         double* det_foot_dev, int32_t* det_query_dev, int32_t* n_keep_dev, void* stream);
+                         double* det_foot_dev, int32_t* det_query_dev, int32_t* n_keep_dev, int32_t* det_slot_dev,
+                         int32_t slot_base, void* stream);
 
 #ifdef __cplusplus
 }

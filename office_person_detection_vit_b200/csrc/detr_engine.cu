@@ -63,11 +63,19 @@ struct Tap {
   int is_f32;
 };
 
+struct Step {
+  std::function<int(cudaStream_t)> run;
+  int kind;          // OPD_STEP_* (include/opd_b200.h)
+  double flops;      // algorithmic: 2 * M * N * K of the contraction (0 for bandwidth-bound kernels)
+  double bytes;      // algorithmic: operands read once + result written once
+  std::string name;
+};
+
 struct Plan {
   int B = 0, H0 = 0, W0 = 0;
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  std::vector<std::function<int(cudaStream_t)>> steps;
+  std::vector<Step> steps;
   std::map<std::string, Tap> taps;
 };
 
@@ -389,6 +397,9 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   const bool dbg = m->debug != 0;
 
   auto act_bytes = [&](long long rows, int ch) { return (size_t)rows * ch * sizeof(bf16); };
+  auto add = [&](int kind, const std::string& name, double flops, double bytes, std::function<int(cudaStream_t)> fn) {
+    steps.push_back(Step{std::move(fn), kind, flops, bytes, name});
+  };
   const long long Ms = (long long)B * sh.Hs * sh.Ws, Mp = (long long)B * sh.Hp * sh.Wp;
 
   // ---- backbone buffers: 3 big ping-pong slots + 2 mid slots (each sized for its largest user) ----
@@ -417,14 +428,19 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   // ---- K1 preprocess -> X2 [B, Hs, Ws, 64] ----
   bf16* x2 = static_cast<bf16*>(big_slot(0, act_bytes(Ms, 64)));
   if (!dry) {
-    steps.push_back([m, B, sh, x2](cudaStream_t s) {
-      return launch_preprocess(m->cur_frames, B, sh.Hin, sh.Win, m->cur_bgr, x2, s);
-    });
+    add(OPD_STEP_ELEMENTWISE, "preprocess", 0.0, (double)B * sh.Hin * sh.Win * 3 + (double)act_bytes(Ms, 64),
+        [m, B, sh, x2](cudaStream_t s) { return launch_preprocess(m->cur_frames, B, sh.Hin, sh.Win, m->cur_bgr, x2, s); });
     taps["x2"] = {x2, Ms, 64, 0};
   }
 
+  std::string cur_name = "gemm";
   auto add_gemm = [&](const GemmPlan& gp) {
-    steps.push_back([gp](cudaStream_t s) { return gemm_launch(gp, s); });
+    // algorithmic traffic: A once (im2col: the input tensor once), W once, D (and D2 / residual) once
+    const double a_bytes = gp.im2col ? 2.0 * gp.g.B * gp.g.H * gp.g.W * gp.g.C / (gp.g.stride * gp.g.stride > 1 && gp.g.KH == 1 ? gp.g.stride * gp.g.stride : 1)
+                                     : 2.0 * gp.M * gp.K;
+    const double bytes = a_bytes + 2.0 * gp.N * gp.K + 2.0 * gp.M * gp.N * (1 + (gp.has_d2 ? 1 : 0) + (gp.residual ? 1 : 0));
+    add(gp.im2col ? OPD_STEP_CONV : OPD_STEP_GEMM, cur_name, 2.0 * gp.M * gp.N * gp.K, bytes,
+        [gp](cudaStream_t s) { return gemm_launch(gp, s); });
   };
   auto conv = [&](const bf16* x, int H, int W, const ConvW& c, bf16* y, int epi, const bf16* res) -> int {
     if (dry) return OPD_OK;
@@ -447,6 +463,7 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   bf16* stem_out = static_cast<bf16*>(big_slot(1, act_bytes(Ms, 64)));
   if (!dry) {
     GemmPlan gp;
+    cur_name = "stem";
     ConvGeom g{B, sh.Hs, sh.Ws, 64, 4, 1, 1, 2, 0, sh.Hs, sh.Ws};
     if (int rc = gemm_plan_conv(&gp, x2, g, m->stem.w, stem_out, 64, EPI_BIAS_RELU, m->stem.bias, nullptr)) return rc;
     add_gemm(gp);
@@ -455,9 +472,8 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   // ---- K3 max pooling ----
   bf16* x = static_cast<bf16*>(big_slot(2, act_bytes(Mp, 64)));
   if (!dry) {
-    steps.push_back([B, sh, stem_out, x](cudaStream_t s) {
-      return launch_maxpool(stem_out, B, sh.Hs, sh.Ws, 64, x, sh.Hp, sh.Wp, s);
-    });
+    add(OPD_STEP_ELEMENTWISE, "maxpool", 0.0, (double)act_bytes(Ms, 64) + (double)act_bytes(Mp, 64),
+        [B, sh, stem_out, x](cudaStream_t s) { return launch_maxpool(stem_out, B, sh.Hs, sh.Ws, 64, x, sh.Hp, sh.Wp, s); });
     taps["pool"] = {x, Mp, 64, 0};
   }
   int cur = 2, hh = sh.Hp, ww = sh.Wp, bi = 0;
@@ -469,7 +485,9 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
       const int ho = conv_out(hh, 3, stride, 1), wo = conv_out(ww, 3, stride, 1);
       const long long m_in = (long long)B * hh * ww, m_out = (long long)B * ho * wo;
       const bf16* res = x;
+      const std::string bname = "stage" + std::to_string(s) + "." + std::to_string(l);
       if (bw.has_shortcut) {
+        cur_name = bname + ".shortcut";
         bf16* sc = static_cast<bf16*>(big_slot((cur + 1) % 3, act_bytes(m_out, width)));
         if (int rc = conv(x, hh, ww, bw.shortcut, sc, EPI_BIAS, nullptr)) return rc;
         res = sc;
@@ -477,8 +495,11 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
       bf16* m1 = static_cast<bf16*>(mid_slot(0, act_bytes(m_in, mid)));
       bf16* m2 = static_cast<bf16*>(mid_slot(1, act_bytes(m_out, mid)));
       bf16* out = static_cast<bf16*>(big_slot((cur + 2) % 3, act_bytes(m_out, width)));
+      cur_name = bname + ".conv1x1a";
       if (int rc = conv(x, hh, ww, bw.c0, m1, EPI_BIAS_RELU, nullptr)) return rc;
+      cur_name = bname + ".conv3x3";
       if (int rc = conv(m1, hh, ww, bw.c1, m2, EPI_BIAS_RELU, nullptr)) return rc;
+      cur_name = bname + ".conv1x1b";
       if (int rc = conv(m2, ho, wo, bw.c2, out, EPI_BIAS_RES_RELU, res)) return rc;
       if (!dry) taps["stage" + std::to_string(s) + "." + std::to_string(l)] = {out, m_out, width, 0};
       x = out;
@@ -530,10 +551,12 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
     return OPD_OK;
   };
   auto attn = [&](const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int Lq, int Lk) {
-    steps.push_back([=](cudaStream_t s) { return launch_attention(q, ldq, k, ldk, v, ldv, o, kD, B, kHeads, Lq, Lk, s); });
+    add(OPD_STEP_ATTENTION, cur_name, 4.0 * B * kHeads * (double)Lq * Lk * 32, 2.0 * B * kD * (2.0 * Lq + 2.0 * Lk),
+        [=](cudaStream_t s) { return launch_attention(q, ldq, k, ldk, v, ldv, o, kD, B, kHeads, Lq, Lk, s); });
   };
 
-  steps.push_back([pos, hh, ww](cudaStream_t s) { return launch_pos_embed(pos, hh, ww, s); });
+  add(OPD_STEP_ELEMENTWISE, "pos_embed", 0.0, 4.0 * S * kD, [pos, hh, ww](cudaStream_t s) { return launch_pos_embed(pos, hh, ww, s); });
+  cur_name = "input_proj";
   taps["pos"] = {pos, S, kD, 1};
   // input_projection (+ pos for the first layer's q / k input)
   if (int rc = linear(x, M, m->input_proj, ex, EPI_BIAS, nullptr, nullptr, exp_, pos, S)) return rc;
@@ -543,26 +566,36 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   for (int i = 0; i < kEnc; ++i) {
     const EncW& e = m->enc[i];
     bf16* xout = enc_out[i];   // == xin unless debugging
+    const std::string ln = "enc" + std::to_string(i);
+    cur_name = ln + ".qk";
     if (int rc = linear(exp_, M, e.qk, eqk, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+    cur_name = ln + ".v";
     if (int rc = linear(xin, M, e.v, ev, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+    cur_name = ln + ".attn";
     attn(eqk, 2 * kD, eqk + kD, 2 * kD, ev, kD, eo, S, S);
+    cur_name = ln + ".o+ln";
     if (int rc = linear(eo, M, e.o, ex1, EPI_BIAS_RES_LN, xin, &e.ln1, nullptr, nullptr, 0)) return rc;
+    cur_name = ln + ".fc1";
     if (int rc = linear(ex1, M, e.fc1, ef, EPI_BIAS_RELU, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
     // layer output overwrites the layer input stream (its last reader, the o_proj residual, has completed)
+    cur_name = ln + ".fc2+ln";
     if (int rc = linear(ef, M, e.fc2, xout, EPI_BIAS_RES_LN, ex1, &e.ln2, exp_, pos, S)) return rc;
     taps["enc" + std::to_string(i)] = {xout, M, kD, 0};
     xin = xout;
   }
+  cur_name = "dec.cross_kv";
   const bf16* memory = xin;        // encoder output
   const bf16* memory_pos = exp_;   // + pos: keys of every cross attention
   if (int rc = linear(memory_pos, M, m->cross_k_all, memk, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
   if (int rc = linear(memory, M, m->cross_v_all, memv, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
 
-  steps.push_back([m, dy, dyp, B](cudaStream_t s) { return launch_decoder_init(dy, dyp, m->qpos, B, kQueries, s); });
+  add(OPD_STEP_ELEMENTWISE, "decoder_init", 0.0, 4.0 * Mq * kD,
+      [m, dy, dyp, B](cudaStream_t s) { return launch_decoder_init(dy, dyp, m->qpos, B, kQueries, s); });
   bf16* yin = dy;
   for (int i = 0; i < kDec; ++i) {
     const DecW& d = m->dec[i];
     bf16* yout = dec_out[i];
+    cur_name = "dec" + std::to_string(i);
     // self attention
     if (int rc = linear(dyp, Mq, d.sqk, dqk, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
     if (int rc = linear(yin, Mq, d.sv, dv, EPI_BIAS, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
@@ -578,9 +611,11 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
     taps["dec" + std::to_string(i)] = {yout, Mq, kD, 0};
     yin = yout;
   }
-  steps.push_back([m, yin, dout, Mq](cudaStream_t s) { return launch_layernorm(yin, m->dec_norm.g, m->dec_norm.b, dout, Mq, s); });
+  add(OPD_STEP_ELEMENTWISE, "dec.final_ln", 0.0, 4.0 * Mq * kD,
+      [m, yin, dout, Mq](cudaStream_t s) { return launch_layernorm(yin, m->dec_norm.g, m->dec_norm.b, dout, Mq, s); });
   taps["dec_out"] = {dout, Mq, kD, 0};
-  steps.push_back([m, dout, Mq](cudaStream_t s) { return launch_heads(dout, m->heads, m->cur_logits, m->cur_boxes, Mq, s); });
+  add(OPD_STEP_HEADS, "heads", 2.0 * Mq * kD * (kClasses + 2 * kD + 4), 2.0 * Mq * kD + 4.0 * Mq * (kClasses + 4),
+      [m, dout, Mq](cudaStream_t s) { return launch_heads(dout, m->heads, m->cur_logits, m->cur_boxes, Mq, s); });
   return OPD_OK;
 }
 
@@ -668,8 +703,41 @@ int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t 
   m->cur_boxes = boxes_dev;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (auto& step : p.steps)
-    if (int rc = step(s)) return rc;
+    if (int rc = step.run(s)) return rc;
   return OPD_OK;
+}
+
+int opd_detr_profile(opd_detr* m, void* stream, int32_t max_steps, int32_t* n_steps, int32_t* kinds, double* flops,
+                     double* bytes, float* ms, char* names, int32_t name_stride) {
+  OPD_REQUIRE(m && n_steps, "opd_detr_profile: NULL argument");
+  opd::Plan& p = m->plan;
+  OPD_REQUIRE(!p.steps.empty() && m->cur_frames, "opd_detr_profile: run opd_detr_forward first");
+  const int n = (int)p.steps.size();
+  *n_steps = n;
+  if (max_steps <= 0) return OPD_OK;
+  OPD_REQUIRE(max_steps >= n && kinds && flops && bytes && ms, "opd_detr_profile: %d steps, room for %d", n, max_steps);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) OPD_CUDA_OK(cudaEventCreate(&e));
+  int rc = OPD_OK;
+  OPD_CUDA_OK(cudaEventRecord(ev[0], s));
+  for (int i = 0; i < n && rc == OPD_OK; ++i) {
+    rc = p.steps[i].run(s);
+    if (cudaEventRecord(ev[i + 1], s) != cudaSuccess && rc == OPD_OK) rc = opd::fail(OPD_ERR_CUDA, "cudaEventRecord failed");
+  }
+  if (rc == OPD_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = opd::fail(OPD_ERR_CUDA, "profile: stream sync failed");
+  for (int i = 0; i < n && rc == OPD_OK; ++i) {
+    kinds[i] = p.steps[i].kind;
+    flops[i] = p.steps[i].flops;
+    bytes[i] = p.steps[i].bytes;
+    cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    if (names && name_stride > 0) {
+      std::strncpy(names + (size_t)i * name_stride, p.steps[i].name.c_str(), name_stride - 1);
+      names[(size_t)i * name_stride + name_stride - 1] = 0;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 int opd_detr_tap(const opd_detr* m, const char* name, const void** ptr_dev, int64_t* rows, int64_t* cols, int32_t* is_f32) {
@@ -697,14 +765,15 @@ int opd_detr_tap_copy(const opd_detr* m, const char* name, void* dst_dev, size_t
 int opd_detr_postprocess(const float* logits_dev, const float* boxes_dev, int32_t B, int32_t Q, int32_t C, int32_t H0,
                          int32_t W0, float threshold, int32_t person_label, float* scores_dev, int32_t* labels_dev,
                          float* xyxy_dev, float* det_xywh_dev, float* det_score_dev, double* det_foot_dev,
-                         int32_t* det_query_dev, int32_t* n_keep_dev, void* stream) {
+                         int32_t* det_query_dev, int32_t* n_keep_dev, int32_t* det_slot_dev, int32_t slot_base,
+                         void* stream) {
   OPD_REQUIRE(logits_dev && boxes_dev && scores_dev && labels_dev && xyxy_dev && det_xywh_dev && det_score_dev &&
                   det_foot_dev && det_query_dev && n_keep_dev,
               "opd_detr_postprocess: NULL argument");
   OPD_REQUIRE(B > 0 && Q > 0 && C > 1, "opd_detr_postprocess: bad shape B=%d Q=%d C=%d", B, Q, C);
   return opd::launch_postprocess(logits_dev, boxes_dev, B, Q, C, H0, W0, threshold, person_label, scores_dev, labels_dev,
-                                 xyxy_dev, det_xywh_dev, det_score_dev, det_foot_dev, det_query_dev, n_keep_dev,
-                                 static_cast<cudaStream_t>(stream));
+                                 xyxy_dev, det_xywh_dev, det_score_dev, det_foot_dev, det_query_dev, n_keep_dev, det_slot_dev,
+                                 slot_base, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(128) postprocess_kernel(const float* __restric
                                                           float* __restrict__ scores, int32_t* __restrict__ labels,
                                                           float* __restrict__ xyxy, float* __restrict__ det_xywh,
                                                           float* __restrict__ det_score, double* __restrict__ det_foot,
-                                                          int32_t* __restrict__ det_query, int32_t* __restrict__ n_keep) {
+                                                          int32_t* __restrict__ det_query, int32_t* __restrict__ n_keep,
+                                                          int32_t* __restrict__ det_slot, int slot_base) {
   __shared__ int s_warp_count[4];
   const int b = blockIdx.x, qi = threadIdx.x;
   const int lane = qi & 31, warp = qi >> 5;
@@ -502,7 +503,10 @@ __global__ void __launch_bounds__(128) postprocess_kernel(const float* __restric
     det_foot[r * 2 + 1] = dy1 + dh;
     det_query[r] = qi;
   }
-  if (qi == 0) n_keep[b] = s_warp_count[0] + s_warp_count[1] + s_warp_count[2] + s_warp_count[3];
+  const int total = s_warp_count[0] + s_warp_count[1] + s_warp_count[2] + s_warp_count[3];
+  if (qi == 0) n_keep[b] = total;
+  // histogram row of every compacted detection row (-1 = unused row, skipped by the floor kernels)
+  if (det_slot && qi < Q) det_slot[(long long)b * Q + qi] = qi < total ? slot_base + b : -1;
 }
 
 int grid_for(long long total, int threads) {
@@ -585,10 +589,11 @@ int launch_heads(const __nv_bfloat16* y, const HeadWeights& w, float* logits, fl
 
 int launch_postprocess(const float* logits, const float* boxes, int B, int Q, int C, int H0, int W0, float threshold,
                        int person_label, float* scores, int32_t* labels, float* xyxy, float* det_xywh, float* det_score,
-                       double* det_foot, int32_t* det_query, int32_t* n_keep, cudaStream_t s) {
+                       double* det_foot, int32_t* det_query, int32_t* n_keep, int32_t* det_slot, int slot_base,
+                       cudaStream_t s) {
   OPD_REQUIRE(Q <= 128, "postprocess: at most 128 queries per frame (got %d)", Q);
   postprocess_kernel<<<B, 128, 0, s>>>(logits, boxes, Q, C, H0, W0, threshold, person_label, scores, labels, xyxy,
-                                       det_xywh, det_score, det_foot, det_query, n_keep);
+                                       det_xywh, det_score, det_foot, det_query, n_keep, det_slot, slot_base);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

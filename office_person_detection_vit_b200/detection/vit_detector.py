@@ -44,11 +44,12 @@ _lib.register("opd_detr_input_shape", C.c_int, [C.c_int32, C.c_int32, C.POINTER(
 _lib.register("opd_detr_workspace_bytes", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
 _lib.register("opd_detr_forward", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_size_t, _P, _P,
                                            _P])
+_lib.register("opd_detr_profile", C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P, _P, _P, C.c_int32])
 _lib.register("opd_detr_tap", C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int32)])
 _lib.register("opd_detr_tap_copy", C.c_int, [_P, C.c_char_p, _P, C.c_size_t, _P])
 _lib.register("opd_detr_postprocess", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
-                                               C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P])
+                                               C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P])
 
 N_QUERIES = 100
 N_LOGITS = 92
@@ -136,6 +137,23 @@ class DetrEngine:
         _lib.check(rc, "opd_detr_forward")
         return logits, boxes
 
+    STEP_KINDS = ("elementwise", "gemm", "conv", "attention", "heads")
+
+    def profile(self) -> list[dict]:
+        """One more forward with the last forward's arguments, a CUDA event between consecutive launches.
+        -> [{name, kind, ms, flops, bytes}] per launch (algorithmic flops / bytes).  Synchronises."""
+        n = C.c_int32()
+        _lib.check(_lib.lib().opd_detr_profile(self._h, _lib.stream_ptr(), 0, C.byref(n), None, None, None, None, None, 0),
+                   "opd_detr_profile")
+        k = n.value
+        kinds, flops, nbytes, ms = (C.c_int32 * k)(), (C.c_double * k)(), (C.c_double * k)(), (C.c_float * k)()
+        names = C.create_string_buffer(k * 48)
+        _lib.check(_lib.lib().opd_detr_profile(self._h, _lib.stream_ptr(), k, C.byref(n), kinds, flops, nbytes, ms, names, 48),
+                   "opd_detr_profile")
+        raw = names.raw
+        return [{"name": raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode(), "kind": self.STEP_KINDS[kinds[i]],
+                 "ms": float(ms[i]), "flops": float(flops[i]), "bytes": float(nbytes[i])} for i in range(k)]
+
     def tap(self, name: str):
         """Copy of a named internal activation of the last forward (needs set_debug(True) for the reused ones)."""
         torch = self._torch
@@ -156,7 +174,8 @@ class DetrEngine:
             pass
 
 
-def postprocess_tensors(logits, boxes, h0: int, w0: int, threshold: float, person_label: int = PERSON_LABEL) -> dict:
+def postprocess_tensors(logits, boxes, h0: int, w0: int, threshold: float, person_label: int = PERSON_LABEL,
+                        slot_base: int = 0) -> dict:
     """K8b on device tensors: per-query scores / labels / xyxy and the compacted person detections per frame."""
     torch = _lib.require_cuda()
     B, Q, Cn = logits.shape
@@ -170,12 +189,13 @@ def postprocess_tensors(logits, boxes, h0: int, w0: int, threshold: float, perso
         "det_foot": torch.zeros(B, Q, 2, dtype=torch.float64, device=dev),
         "det_query": torch.full((B, Q), -1, dtype=torch.int32, device=dev),
         "n_keep": torch.empty(B, dtype=torch.int32, device=dev),
+        "det_slot": torch.empty(B, Q, dtype=torch.int32, device=dev),
     }
     rc = _lib.lib().opd_detr_postprocess(
         logits.data_ptr(), boxes.data_ptr(), B, Q, Cn, h0, w0, float(threshold), person_label,
         out["scores"].data_ptr(), out["labels"].data_ptr(), out["xyxy"].data_ptr(), out["det_xywh"].data_ptr(),
         out["det_score"].data_ptr(), out["det_foot"].data_ptr(), out["det_query"].data_ptr(), out["n_keep"].data_ptr(),
-        _lib.stream_ptr())
+        out["det_slot"].data_ptr(), int(slot_base), _lib.stream_ptr())
     _lib.check(rc, "opd_detr_postprocess")
     return out
 
@@ -245,12 +265,12 @@ class ViTDetector:
             raise RuntimeError("Model not loaded. Call load_model() first.")
         return self.model.forward(frames, bgr=bgr)
 
-    def detect_tensors(self, frames, bgr: bool = True, threshold: float | None = None) -> dict:
+    def detect_tensors(self, frames, bgr: bool = True, threshold: float | None = None, slot_base: int = 0) -> dict:
         """frames [B,H,W,3] uint8 CUDA tensor -> dict of device tensors (see postprocess_tensors); no host sync."""
         logits, boxes = self.forward_raw(frames, bgr=bgr)
         _, H0, W0, _ = frames.shape
         thr = self.confidence_threshold if threshold is None else threshold
-        out = postprocess_tensors(logits, boxes, H0, W0, thr)
+        out = postprocess_tensors(logits, boxes, H0, W0, thr, slot_base=slot_base)
         out["logits"], out["boxes"] = logits, boxes
         return out
 

@@ -1,0 +1,42 @@
+"""Phase 2 -> 3 (+ count) on device tensors: detect -> foot point -> homography -> zone -> per-timestamp histogram.
+
+The reference runs these as three Python loops (src/pipeline/phases/detection.py:56-133, transform.py:257-330,
+aggregation.py:26-91) over lists of Detection objects.  Here the whole chain stays on the GPU: the detector's compacted
+foot points feed the fused projection + classification + histogram kernel directly, one timestamp slot per frame, and the
+only host traffic is whatever the caller reads back.  Multi-GPU: every rank owns a contiguous block of frames / slots
+and `all_reduce(hist)` (NCCL) merges the per-timestamp histograms."""
+
+from __future__ import annotations
+
+from . import _lib
+
+
+class DetectCountPipeline:
+    def __init__(self, detector, transformer, zone_classifier):
+        self.detector = detector
+        self.transformer = transformer
+        self.zones = zone_classifier
+
+    def run_tensors(self, frames, hist=None, slot_base: int = 0, threshold: float | None = None, bgr: bool = True) -> dict:
+        """frames [B,H,W,3] uint8 CUDA -> dict of device tensors: everything `ViTDetector.detect_tensors` returns plus
+        `zone_idx` [B,100] (-1 = unclassified / unused row) and `hist` [T, Z+1] int32, accumulated at rows
+        slot_base .. slot_base+B-1 (allocated as [B, Z+1] when not given).  No host synchronisation."""
+        torch = _lib.require_cuda()
+        B = frames.shape[0]
+        out = self.detector.detect_tensors(frames, bgr=bgr, threshold=threshold, slot_base=slot_base)
+        if hist is None:
+            hist = torch.zeros(slot_base + B, self.zones.get_zone_count() + 1, dtype=torch.int32, device=frames.device)
+        pts = out["det_foot"].view(-1, 2)
+        hist, idx = self.zones.count(pts, slot=out["det_slot"].view(-1), num_slots=hist.shape[0],
+                                     transformer=self.transformer, out=hist, return_index=True)
+        out["hist"] = hist
+        out["zone_idx"] = idx.view(B, -1)
+        return out
+
+    def all_reduce(self, hist):
+        """Sum the per-timestamp histograms over all ranks (the path's only collective)."""
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        return hist

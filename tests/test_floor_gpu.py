@@ -144,8 +144,8 @@ def test_fast_kernel_ragged_tail_and_idempotence(torch_cuda, built_lib):
 
 
 def test_degenerate_points(torch_cuda, built_lib):
-    """Points on the horizon (W = 0), NaN/inf inputs and far-away points are unclassified, as in the
-    reference (every comparison with NaN is False)."""
+    """Points on the horizon (W = 0) and NaN/inf inputs are unclassified, as in the reference (every comparison
+    with NaN is False); a huge finite point still projects to a finite ratio X/W and is classified like the oracle."""
     torch = torch_cuda
     zones = fo.grid_zones(4)
     tr, zc = _engines(fo.H_CONFIG, zones, False)
@@ -157,7 +157,7 @@ def test_degenerate_points(torch_cuda, built_lib):
     idx = zc.classify_points(d, transformer=tr).cpu().numpy()
     with np.errstate(all="ignore"):
         exp_idx, _ = fo.project_classify_count(fo.H_CONFIG, pts, zones)
-    assert (idx[:3] == -1).all()
+    assert (idx[:2] == -1).all()
     assert (idx == exp_idx).all()
 
 
