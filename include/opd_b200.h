@@ -127,6 +127,12 @@ int opd_gemm_bf16(const void* a_dev, int64_t lda, const void* w_dev, void* d_dev
 int opd_conv2d_nhwc_bf16(const void* x_dev, int32_t B, int32_t H, int32_t W, int32_t C, const void* w_dev,
                          int32_t N, int32_t KH, int32_t KW, int32_t stride, int32_t pad, int32_t epilogue,
                          const float* bias_dev, const void* residual_dev, void* y_dev, void* stream);
+/* Fused bottleneck tail: y = relu(conv1x1(relu(conv3x3(x, stride, pad 1) + bias2)) + bias3 + residual) in one kernel
+ * (models/resnet/modeling_resnet.py:134-200, layer.1 + layer.2 + shortcut add, frozen BN folded).
+ * x [B,H,W,mid] NHWC bf16, w2 [mid,3,3,mid], w3 [width,mid], residual / y [B,P,Q,width]; mid 64 or 128, width % 128 == 0. */
+int opd_bottleneck_tail_bf16(const void* x_dev, int32_t B, int32_t H, int32_t W, int32_t mid, const void* w2_dev,
+                             const float* bias2_dev, int32_t stride, const void* w3_dev, const float* bias3_dev,
+                             int32_t width, const void* residual_dev, void* y_dev, void* stream);
 /* o = softmax(q k^T / sqrt(32)) v per (batch, head); head h = columns [32h, 32h+32); row strides in elements */
 int opd_attention_bf16(const void* q_dev, int64_t ldq, const void* k_dev, int64_t ldk, const void* v_dev,
                        int64_t ldv, void* o_dev, int64_t ldo, int32_t B, int32_t heads, int32_t Lq, int32_t Lk,
@@ -162,6 +168,8 @@ void opd_detr_destroy(opd_detr* m);
 int opd_detr_set_debug(opd_detr* m, int32_t debug);
 /* do_resize = 0 feeds frames at their own size, like DetrImageProcessor(do_resize=False); default 1. */
 int opd_detr_set_resize(opd_detr* m, int32_t do_resize);
+/* 0 runs the 3x3 convolution and the 1x1 expansion of ResNet stages 1-2 as separate kernels (default 1: fused). */
+int opd_detr_set_fusion(opd_detr* m, int32_t fuse_bottleneck_tail);
 
 /* Model input size for a frame size (DetrImageProcessor shortest-edge 800 / longest-edge 1333 rule,
  * transformers/image_transforms.py:206-242) and the stage-4 feature map size. */
@@ -184,7 +192,7 @@ typedef enum opd_step_kind {
 int opd_detr_profile(opd_detr* m, void* stream, int32_t max_steps, int32_t* n_steps, int32_t* kinds, double* flops,
                      double* bytes, float* ms, char* names, int32_t name_stride);
 /* Named internal activation of the last forward (tests): "pixel_values", "stem", "pool", "stage{s}.{l}",
- * "enc_in", "pos", "enc{i}", "dec{i}", "dec_out".  rows x cols, bf16 unless *is_f32. */
+ * "enc_in", "pos", "enc{i}", "dec{i}", "dec_out", "resized_u8".  rows x cols; *is_f32: 0 bf16, 1 f32, 2 uint8. */
 int opd_detr_tap(const opd_detr* m, const char* name, const void** ptr_dev, int64_t* rows, int64_t* cols,
                  int32_t* is_f32);
 /* Copies that activation into dst_dev (device, `bytes` = rows * cols * element size) on `stream`. */

@@ -85,6 +85,7 @@ struct Plan {
 struct opd_detr {
   int device = 0;
   int debug = 0;
+  int fuse_tail = 1;   // 0: run the 3x3 and the 1x1 expansion of stages 1-2 as separate kernels (A/B comparison)
   int do_resize = 1;   // 0: frames are fed at their own size (DetrImageProcessor(do_resize=False))
   std::vector<void*> allocs;
   opd::ConvW stem;   // packed as a 4x1 convolution over the 64-channel space-to-depth layout
@@ -339,6 +340,61 @@ void resized_size(int h, int w, int* oh, int* ow) {
   }
 }
 
+// Separable uint8 antialias-bilinear resize tables, restating ATen's CPU kernel (aten/src/ATen/native/cpu/
+// UpSampleKernel.cpp: _compute_indices_min_size_weights_aa + _compute_index_ranges_int16_weights; what torchvision's
+// resize on a uint8 tensor, i.e. transformers' DetrImageProcessor, runs): double-precision triangle-filter weights,
+// normalised, scaled to int16 with the largest precision that keeps the maximum weight below 2^15.
+struct ResizeTable {
+  std::vector<int32_t> x0;
+  std::vector<int16_t> w;   // [out, ksize]
+  int ksize = 0, precision = 0;
+};
+ResizeTable resize_table(int in_size, int out_size) {
+  ResizeTable t;
+  const double scale = (double)in_size / (double)out_size;
+  const double support = scale >= 1.0 ? scale : 1.0;   // interp_size (2) * 0.5 * scale
+  t.ksize = (int)std::ceil(support) * 2 + 1;
+  const double invscale = scale >= 1.0 ? 1.0 / scale : 1.0;
+  std::vector<double> wt((size_t)out_size * t.ksize, 0.0);
+  t.x0.resize(out_size);
+  double wt_max = 0.0;
+  for (int i = 0; i < out_size; ++i) {
+    const double center = scale * (i + 0.5);
+    long long xmin = (long long)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    long long xsize = (long long)(center + support + 0.5);
+    if (xsize > in_size) xsize = in_size;
+    xsize -= xmin;
+    if (xsize < 0) xsize = 0;
+    if (xsize > t.ksize) xsize = t.ksize;
+    double total = 0.0;
+    double* wp = wt.data() + (size_t)i * t.ksize;
+    for (int j = 0; j < xsize; ++j) {
+      double x = ((double)(j + xmin) - center + 0.5) * invscale;
+      if (x < 0.0) x = -x;
+      const double w = x < 1.0 ? 1.0 - x : 0.0;
+      wp[j] = w;
+      total += w;
+    }
+    if (total != 0.0)
+      for (int j = 0; j < xsize; ++j) {
+        wp[j] /= total;
+        if (wp[j] > wt_max) wt_max = wp[j];
+      }
+    t.x0[i] = (int32_t)xmin;
+  }
+  for (t.precision = 0; t.precision < 22; ++t.precision) {
+    const int next_value = (int)(0.5 + wt_max * (double)(1 << (t.precision + 1)));
+    if (next_value >= (1 << 15)) break;
+  }
+  t.w.resize(wt.size());
+  for (size_t i = 0; i < wt.size(); ++i) {
+    const double v = wt[i] * (double)(1 << t.precision);
+    t.w[i] = (int16_t)(v < 0 ? (int)(-0.5 + v) : (int)(0.5 + v));
+  }
+  return t;
+}
+
 inline int conv_out(int x, int k, int stride, int pad) { return (x + 2 * pad - k) / stride + 1; }
 
 struct Shapes {
@@ -387,9 +443,6 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   const bool dry = ws == nullptr;
   const Shapes sh = shapes_for(H0, W0, m->do_resize != 0);
   OPD_REQUIRE(sh.Hs >= 4 && sh.h[3] >= 1 && sh.w[3] >= 1, "detr: frames of %dx%d are too small", H0, W0);
-  OPD_REQUIRE(sh.Hin == H0 && sh.Win == W0,
-              "detr: frames of %dx%d need the %dx%d resize, which this build does not implement yet (feed 800x1333-class frames)",
-              H0, W0, sh.Hin, sh.Win);
   OPD_REQUIRE(sh.Hs == (sh.Hin + 1) / 2 && sh.Ws == (sh.Win + 1) / 2, "detr: unexpected stem geometry");
   Arena A{static_cast<uint8_t*>(ws)};
   auto& steps = plan->steps;
@@ -425,11 +478,40 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   auto big_slot = [&](int i, size_t bytes) { return dbg ? A.take(bytes) : big[i]; };
   auto mid_slot = [&](int i, size_t bytes) { return dbg ? A.take(bytes) : mids[i]; };
 
+  // ---- uint8 antialias resize to the model input size (camera frames: 720x1280 -> 750x1333) ----
+  const bool needs_resize = sh.Hin != H0 || sh.Win != W0;
+  uint8_t* resized = nullptr;
+  if (needs_resize) {
+    const ResizeTable tx = resize_table(W0, sh.Win), ty = resize_table(H0, sh.Hin);
+    uint8_t* tmp = static_cast<uint8_t*>(A.take((size_t)B * H0 * sh.Win * 3));
+    resized = static_cast<uint8_t*>(A.take((size_t)B * sh.Hin * sh.Win * 3));
+    int16_t* wx = static_cast<int16_t*>(A.take(tx.w.size() * sizeof(int16_t)));
+    int32_t* x0 = static_cast<int32_t*>(A.take(tx.x0.size() * sizeof(int32_t)));
+    int16_t* wy = static_cast<int16_t*>(A.take(ty.w.size() * sizeof(int16_t)));
+    int32_t* y0 = static_cast<int32_t*>(A.take(ty.x0.size() * sizeof(int32_t)));
+    if (!dry) {
+      OPD_CUDA_OK(cudaMemcpy(wx, tx.w.data(), tx.w.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+      OPD_CUDA_OK(cudaMemcpy(x0, tx.x0.data(), tx.x0.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      OPD_CUDA_OK(cudaMemcpy(wy, ty.w.data(), ty.w.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+      OPD_CUDA_OK(cudaMemcpy(y0, ty.x0.data(), ty.x0.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      const int kx = tx.ksize, px = tx.precision, ky = ty.ksize, py = ty.precision;
+      add(OPD_STEP_ELEMENTWISE, "resize", 0.0, 3.0 * B * ((double)H0 * W0 + 2.0 * H0 * sh.Win + (double)sh.Hin * sh.Win),
+          [=](cudaStream_t s) {
+            return launch_resize_u8(m->cur_frames, B, H0, W0, m->cur_bgr, tmp, resized, sh.Hin, sh.Win, wx, x0, kx, px, wy,
+                                    y0, ky, py, s);
+          });
+      taps["resized_u8"] = {resized, (long long)B * sh.Hin * sh.Win, 3, 2};
+    }
+  }
+
   // ---- K1 preprocess -> X2 [B, Hs, Ws, 64] ----
   bf16* x2 = static_cast<bf16*>(big_slot(0, act_bytes(Ms, 64)));
   if (!dry) {
     add(OPD_STEP_ELEMENTWISE, "preprocess", 0.0, (double)B * sh.Hin * sh.Win * 3 + (double)act_bytes(Ms, 64),
-        [m, B, sh, x2](cudaStream_t s) { return launch_preprocess(m->cur_frames, B, sh.Hin, sh.Win, m->cur_bgr, x2, s); });
+        [m, B, sh, x2, resized](cudaStream_t s) {
+          return resized ? launch_preprocess(resized, B, sh.Hin, sh.Win, 0, x2, s)
+                         : launch_preprocess(m->cur_frames, B, sh.Hin, sh.Win, m->cur_bgr, x2, s);
+        });
     taps["x2"] = {x2, Ms, 64, 0};
   }
 
@@ -497,10 +579,22 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
       bf16* out = static_cast<bf16*>(big_slot((cur + 2) % 3, act_bytes(m_out, width)));
       cur_name = bname + ".conv1x1a";
       if (int rc = conv(x, hh, ww, bw.c0, m1, EPI_BIAS_RELU, nullptr)) return rc;
-      cur_name = bname + ".conv3x3";
-      if (int rc = conv(m1, hh, ww, bw.c1, m2, EPI_BIAS_RELU, nullptr)) return rc;
-      cur_name = bname + ".conv1x1b";
-      if (int rc = conv(m2, ho, wo, bw.c2, out, EPI_BIAS_RES_RELU, res)) return rc;
+      if (mid <= 128 && m->fuse_tail) {
+        // stages 1-2: 3x3 convolution + 1x1 expansion + residual in one kernel (tc_bottleneck.cu)
+        if (!dry) {
+          BneckPlan bp;
+          ConvGeom g{B, hh, ww, mid, 3, 3, stride, 1, 1, ho, wo};
+          if (int rc = bneck_plan(&bp, m1, g, bw.c1.w, bw.c1.bias, bw.c2.w, bw.c2.bias, width, res, out)) return rc;
+          const double flops = 2.0 * m_out * mid * (9.0 * mid + width);
+          const double bytes = 2.0 * m_in * mid + 4.0 * m_out * width + 2.0 * mid * (9.0 * mid + width);
+          add(OPD_STEP_CONV, bname + ".tail(3x3+1x1b)", flops, bytes, [bp](cudaStream_t s) { return bneck_launch(bp, s); });
+        }
+      } else {
+        cur_name = bname + ".conv3x3";
+        if (int rc = conv(m1, hh, ww, bw.c1, m2, EPI_BIAS_RELU, nullptr)) return rc;
+        cur_name = bname + ".conv1x1b";
+        if (int rc = conv(m2, ho, wo, bw.c2, out, EPI_BIAS_RES_RELU, res)) return rc;
+      }
       if (!dry) taps["stage" + std::to_string(s) + "." + std::to_string(l)] = {out, m_out, width, 0};
       x = out;
       cur = (cur + 2) % 3;
@@ -655,6 +749,13 @@ int opd_detr_set_debug(opd_detr* m, int32_t debug) {
   return OPD_OK;
 }
 
+int opd_detr_set_fusion(opd_detr* m, int32_t fuse_bottleneck_tail) {
+  OPD_REQUIRE(m, "opd_detr_set_fusion: NULL handle");
+  m->fuse_tail = fuse_bottleneck_tail;
+  m->plan = opd::Plan{};
+  return OPD_OK;
+}
+
 int opd_detr_set_resize(opd_detr* m, int32_t do_resize) {
   OPD_REQUIRE(m, "opd_detr_set_resize: NULL handle");
   m->do_resize = do_resize;
@@ -756,8 +857,9 @@ int opd_detr_tap_copy(const opd_detr* m, const char* name, void* dst_dev, size_t
   int64_t rows = 0, cols = 0;
   int32_t f32 = 0;
   if (int rc = opd_detr_tap(m, name, &src, &rows, &cols, &f32)) return rc;
-  OPD_REQUIRE(dst_dev && bytes == (size_t)rows * cols * (f32 ? 4 : 2), "opd_detr_tap_copy: '%s' is %lld x %lld (%s)", name,
-              (long long)rows, (long long)cols, f32 ? "f32" : "bf16");
+  const size_t esz = f32 == 1 ? 4 : (f32 == 2 ? 1 : 2);
+  OPD_REQUIRE(dst_dev && bytes == (size_t)rows * cols * esz, "opd_detr_tap_copy: '%s' is %lld x %lld of %zu-byte elements", name,
+              (long long)rows, (long long)cols, esz);
   OPD_CUDA_OK(cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return OPD_OK;
 }

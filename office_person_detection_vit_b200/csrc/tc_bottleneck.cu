@@ -1,0 +1,429 @@
+// Fused bottleneck tail on the 5th-generation tensor cores:
+//     y = relu( conv1x1( relu(conv3x3(x, stride) + b2) ) + b3 + residual )
+// i.e. layer.1 + layer.2 + shortcut add of a ResNet bottleneck (transformers models/resnet/modeling_resnet.py:134-200,
+// frozen BN folded) in ONE persistent kernel.  The 3x3 convolution is L2-bound (im2col re-reads its input 9 times) and
+// the 1x1 expansion is HBM-bound (residual in, 4x wider tensor out): run back to back they leave HBM, then L2, idle.
+// Fused, the mid activation never leaves the SM (TMEM -> registers -> shared memory as the A operand of the second
+// GEMM) and the two phases of different tiles overlap inside every SM.
+//
+// Per 128-pixel tile t (persistent CTAs, static tile schedule):
+//   G1(t): acc1[128 x MID]  = im2col(x)[128 x 9*MID] * W2^T        tcgen05.mma, TMA im2col A + TMA B1 through the ring
+//   E1(t): A2 = bf16(relu(acc1 + b2))                               TMEM -> regs -> 128B-swizzled smem (K-major operand)
+//   G2(t): acc2[128 x 128] = A2[128 x MID] * W3[n2]^T  per n2 tile  B2 tiles through the same ring
+//   E2(t): y = bf16(relu(acc2 + b3 + residual))                     residual by TMA ring, output by TMA store
+// Warp roles: 0 TMA producer, 1 MMA issuer + TMEM owner, 2-5 epilogue, 6 residual producer.
+// MMA issue order G1(t0) G1(t1) G2(t0) G1(t2) G2(t1) ... so that E1 / E2 of one tile overlap the MMAs of the next.
+#include <algorithm>
+
+#include "opd_common.h"
+#include "sm100_ptx.cuh"
+#include "tc_gemm.h"
+
+namespace opd {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int BLOCK_N2 = 128;
+constexpr int UMMA_K = 16;
+constexpr int CHUNK_BYTES = BLOCK_M * 64 * 2;        // one [128 x 64] bf16 box = 16 KB
+constexpr int kThreads = 224;
+constexpr int kSmemBudget = 232448;
+
+template <int MID>
+struct Cfg {
+  static constexpr int kA2Chunks = MID / 64;
+  static constexpr int kResStages = MID == 64 ? 4 : 2;
+  static constexpr int kStageBytes = 2 * CHUNK_BYTES;               // A slot 16 KB + B slot 16 KB (B1: MID x 64, B2: 128 x 64)
+  static constexpr int kFixed = (kA2Chunks + 2 + kResStages) * CHUNK_BYTES + 2048;
+  static constexpr int kStages = (kSmemBudget - kFixed) / kStageBytes > 6 ? 6 : (kSmemBudget - kFixed) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
+  static constexpr int kTmemCols = 512;                             // acc1 2 x MID + acc2 2 x 128
+  static_assert(MID == 64 || MID == 128, "fused bottleneck tail: MID must be 64 or 128");
+  static_assert(kStages >= 3, "ring too shallow");
+};
+
+struct BneckParams {
+  CUtensorMap tmA, tmB1, tmB2, tmR, tmD;
+  int M, width;
+  int num_m_blocks, num_n2;
+  int KW, stride, pad_h, pad_w, P, Q;
+  const float* bias2;
+  const float* bias3;
+};
+
+template <int MID>
+__global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_constant__ BneckParams p) {
+  using C = Cfg<MID>;
+  constexpr int kStages = C::kStages;
+  constexpr int kResStages = C::kResStages;
+  constexpr int kK1Blocks = 9 * MID / BLOCK_K;      // 3x3 taps x channel blocks
+  constexpr int kCBlocks = MID / BLOCK_K;
+  constexpr uint32_t kIdesc1 = ptx::umma_idesc_bf16(BLOCK_M, MID);
+  constexpr uint32_t kIdesc2 = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N2);
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;                                    // ring: A slots
+  uint8_t* smem_b = smem_a + kStages * CHUNK_BYTES;          // ring: B slots
+  uint8_t* smem_a2 = smem_b + kStages * CHUNK_BYTES;         // A operand of the second GEMM
+  uint8_t* smem_out = smem_a2 + C::kA2Chunks * CHUNK_BYTES;  // 2 output staging boxes
+  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;            // residual ring
+  float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [MID]
+  float* s_bias3 = s_bias2 + 128;                                                   // [128] of the current n2 tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 128);
+  uint64_t* full_bar = bars;                  // [kStages]
+  uint64_t* empty_bar = bars + 8;             // [kStages]
+  uint64_t* acc1_full = bars + 16;            // [2]
+  uint64_t* acc1_empty = bars + 18;           // [2]
+  uint64_t* acc2_full = bars + 20;            // [2]
+  uint64_t* acc2_empty = bars + 22;           // [2]
+  uint64_t* a2_ready = bars + 24;             // [1]
+  uint64_t* a2_free = bars + 25;              // [1]
+  uint64_t* res_full = bars + 26;             // [4]
+  uint64_t* res_empty = bars + 30;            // [4]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 34);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmB1);
+    ptx::prefetch_tmap(&p.tmB2);
+    ptx::prefetch_tmap(&p.tmD);
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc1_full[i], 1);
+      ptx::mbar_init(&acc1_empty[i], 128);
+      ptx::mbar_init(&acc2_full[i], 1);
+      ptx::mbar_init(&acc2_empty[i], 128);
+    }
+    ptx::mbar_init(a2_ready, 128);
+    ptx::mbar_init(a2_free, 1);
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&res_full[i], 1);
+      ptx::mbar_init(&res_empty[i], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_ptr);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_acc1 = tmem_base;                 // 2 x MID columns
+  const uint32_t tmem_acc2 = tmem_base + 2 * MID;       // 2 x 128 columns
+
+  const int first = blockIdx.x, step = gridDim.x, n_mblk = p.num_m_blocks;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      auto load_g1 = [&](int m_blk) {
+        const int m0 = m_blk * BLOCK_M;
+        const int pq = p.P * p.Q;
+        const int img = m0 / pq;
+        const int rem = m0 - img * pq;
+        const int op = rem / p.Q, oq = rem - op * p.Q;
+        const int base_w = oq * p.stride - p.pad_w, base_h = op * p.stride - p.pad_h;
+        for (int kb = 0; kb < kK1Blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], CHUNK_BYTES + MID * BLOCK_K * 2);
+          const int tap = kb / kCBlocks, cb = kb - tap * kCBlocks;
+          const int r = tap / p.KW, s = tap - r * p.KW;
+          ptx::tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * CHUNK_BYTES, cb * BLOCK_K, base_w, base_h, img,
+                                  (uint16_t)s, (uint16_t)r);
+          ptx::tma_load_2d(&p.tmB1, &full_bar[stage], smem_b + stage * CHUNK_BYTES, kb * BLOCK_K, 0);
+          advance();
+        }
+      };
+      auto load_g2 = [&]() {
+        for (int n2 = 0; n2 < p.num_n2; ++n2)
+          for (int kb = 0; kb < kCBlocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_expect_tx(&full_bar[stage], CHUNK_BYTES);
+            ptx::tma_load_2d(&p.tmB2, &full_bar[stage], smem_b + stage * CHUNK_BYTES, kb * BLOCK_K, n2 * BLOCK_N2);
+            advance();
+          }
+      };
+      if (first < n_mblk) load_g1(first);
+      for (int t = first; t < n_mblk; t += step) {
+        if (t + step < n_mblk) load_g1(t + step);
+        load_g2();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() {
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      int a1 = 0, a2 = 0;
+      uint32_t a1_phase = 0, a2_phase = 0, ready_phase = 0;
+      auto g1 = [&]() {
+        ptx::mbar_wait(&acc1_empty[a1], a1_phase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d = tmem_acc1 + a1 * MID;
+        for (int kb = 0; kb < kK1Blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a + stage * CHUNK_BYTES));
+          const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * CHUNK_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) ptx::umma_bf16_ss(d, da + 2 * k, db + 2 * k, kIdesc1, (kb | k) != 0);
+          ptx::umma_commit(&empty_bar[stage]);
+          advance();
+        }
+        ptx::umma_commit(&acc1_full[a1]);
+        if (++a1 == 2) {
+          a1 = 0;
+          a1_phase ^= 1;
+        }
+      };
+      auto g2 = [&]() {
+        ptx::mbar_wait(a2_ready, ready_phase);   // E1 has written A2 (and fenced it for the async proxy)
+        ready_phase ^= 1;
+        ptx::tc_fence_after_sync();
+        for (int n2 = 0; n2 < p.num_n2; ++n2) {
+          ptx::mbar_wait(&acc2_empty[a2], a2_phase ^ 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t d = tmem_acc2 + a2 * BLOCK_N2;
+          for (int kb = 0; kb < kCBlocks; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after_sync();
+            const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a2 + kb * CHUNK_BYTES));
+            const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * CHUNK_BYTES));
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) ptx::umma_bf16_ss(d, da + 2 * k, db + 2 * k, kIdesc2, (kb | k) != 0);
+            ptx::umma_commit(&empty_bar[stage]);
+            advance();
+          }
+          ptx::umma_commit(&acc2_full[a2]);
+          if (++a2 == 2) {
+            a2 = 0;
+            a2_phase ^= 1;
+          }
+        }
+        ptx::umma_commit(a2_free);   // every MMA that reads A2 has completed
+      };
+      if (first < n_mblk) g1();
+      for (int t = first; t < n_mblk; t += step) {
+        if (t + step < n_mblk) g1();
+        g2();
+      }
+    }
+  } else if (warp == 6) {
+    // ===================================== residual TMA producer =====================================
+    if (lane == 0) {
+      ptx::prefetch_tmap(&p.tmR);
+      int rs = 0;
+      uint32_t rphase = 0;
+      for (int t = first; t < n_mblk; t += step)
+        for (int n2 = 0; n2 < p.num_n2; ++n2)
+          for (int c = 0; c < 2; ++c) {
+            ptx::mbar_wait(&res_empty[rs], rphase ^ 1);
+            ptx::mbar_expect_tx(&res_full[rs], CHUNK_BYTES);
+            ptx::tma_load_2d(&p.tmR, &res_full[rs], smem_res + rs * CHUNK_BYTES, n2 * BLOCK_N2 + c * 64, t * BLOCK_M);
+            if (++rs == kResStages) {
+              rs = 0;
+              rphase ^= 1;
+            }
+          }
+    }
+  } else {
+    // ===================================== epilogue (warps 2..5) =====================================
+    const int et = threadIdx.x - 64;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    for (int i = et; i < MID; i += 128) s_bias2[i] = p.bias2[i];
+    ptx::named_bar_sync(1, 128);
+
+    int a1 = 0, a2 = 0, rs = 0;
+    uint32_t a1_phase = 0, a2_phase = 0, rphase = 0, free_phase = 0, box = 0;
+
+    auto e1 = [&]() {
+      ptx::mbar_wait(&acc1_full[a1], a1_phase);
+      ptx::mbar_wait(a2_free, free_phase ^ 1);   // the previous tile's second GEMM no longer reads A2
+      free_phase ^= 1;
+      ptx::tc_fence_after_sync();
+      const uint32_t t_acc = tmem_acc1 + lane_addr + a1 * MID;
+#pragma unroll
+      for (int c = 0; c < MID / 64; ++c) {
+        uint32_t packed[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_acc + c * 64 + h * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = fmaxf(__uint_as_float(v[2 * j]) + s_bias2[c * 64 + h * 32 + 2 * j], 0.f);
+            const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias2[c * 64 + h * 32 + 2 * j + 1], 0.f);
+            packed[h * 16 + j] = ptx::pack_bf16(a, b);
+          }
+        }
+        uint8_t* rowp = smem_a2 + c * CHUNK_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&acc1_empty[a1]);
+      ptx::fence_proxy_async_smem();             // A2 is read by the tensor core through the async proxy
+      ptx::mbar_arrive(a2_ready);
+      if (++a1 == 2) {
+        a1 = 0;
+        a1_phase ^= 1;
+      }
+    };
+
+    auto e2 = [&](int m_blk, int n2) {
+      const int m0 = m_blk * BLOCK_M, n0 = n2 * BLOCK_N2;
+      for (int i = et; i < BLOCK_N2; i += 128) s_bias3[i] = p.bias3[n0 + i];
+      ptx::named_bar_sync(1, 128);
+      ptx::mbar_wait(&acc2_full[a2], a2_phase);
+      ptx::tc_fence_after_sync();
+      const uint32_t t_acc = tmem_acc2 + lane_addr + a2 * BLOCK_N2;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N2 / 64; ++c) {
+        uint32_t packed[32];
+        ptx::mbar_wait(&res_full[rs], rphase);
+        const uint8_t* rrow = smem_res + rs * CHUNK_BYTES + row * 128;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_acc + c * 64 + h * 32, v);
+          uint4 rr[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rrow + (((h * 4 + j) ^ (row & 7)) << 4));
+          ptx::tmem_ld_wait();
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = fmaxf(__uint_as_float(v[2 * j]) + s_bias3[c * 64 + h * 32 + 2 * j] + ptx::bf16_lo(rw[j]), 0.f);
+            const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias3[c * 64 + h * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]), 0.f);
+            packed[h * 16 + j] = ptx::pack_bf16(a, b);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&res_empty[rs]);
+        if (++rs == kResStages) {
+          rs = 0;
+          rphase ^= 1;
+        }
+        uint8_t* buf = smem_out + (box & 1) * CHUNK_BYTES;
+        uint8_t* rowp = buf + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        ptx::fence_proxy_async_smem();
+        if (et == 0) ptx::tma_store_wait_read<0>();
+        ptx::named_bar_sync(1, 128);
+        if (et == 0) {
+          ptx::tma_store_2d(&p.tmD, buf, n0 + c * 64, m0);
+          ptx::tma_store_commit();
+        }
+        ++box;
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&acc2_empty[a2]);
+      if (++a2 == 2) {
+        a2 = 0;
+        a2_phase ^= 1;
+      }
+    };
+
+    if (first < n_mblk) e1();
+    for (int t = first; t < n_mblk; t += step) {
+      for (int n2 = 0; n2 < p.num_n2; ++n2) e2(t, n2);
+      if (t + step < n_mblk) e1();
+    }
+    if (et == 0) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+template <int MID>
+int launch_t(const BneckParams& p, int grid, cudaStream_t s) {
+  static bool configured = false;
+  auto kern = tc_bneck_kernel<MID>;
+  if (!configured) {
+    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MID>::kSmemBytes));
+    configured = true;
+  }
+  kern<<<grid, kThreads, Cfg<MID>::kSmemBytes, s>>>(p);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+}  // namespace
+
+int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
+               const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y) {
+  *plan = BneckPlan{};
+  OPD_REQUIRE(g.KH == 3 && g.KW == 3 && (g.C == 64 || g.C == 128), "bottleneck tail: 3x3 convolution over 64 or 128 channels (C=%d)", g.C);
+  OPD_REQUIRE(width % BLOCK_N2 == 0 && width > 0, "bottleneck tail: width=%d must be a multiple of 128", width);
+  OPD_REQUIRE(bias2 && bias3 && residual && y && x && w2 && w3, "bottleneck tail: NULL argument");
+  plan->M = g.B * g.P * g.Q;
+  plan->mid = g.C;
+  plan->width = width;
+  plan->g = g;
+  plan->bias2 = bias2;
+  plan->bias3 = bias3;
+  if (int rc = make_tmap_im2col(&plan->tmA, x, g)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB1, w2, g.C, 9 * g.C, 9 * g.C, g.C)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB2, w3, width, g.C, g.C, BLOCK_N2)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmR, residual, plan->M, width, width, BLOCK_M)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmD, y, plan->M, width, width, BLOCK_M)) return rc;
+  const int m_blocks = (plan->M + BLOCK_M - 1) / BLOCK_M;
+  plan->grid = std::min(m_blocks, sm_count());
+  return OPD_OK;
+}
+
+int bneck_launch(const BneckPlan& plan, cudaStream_t stream) {
+  BneckParams p;
+  p.tmA = plan.tmA; p.tmB1 = plan.tmB1; p.tmB2 = plan.tmB2; p.tmR = plan.tmR; p.tmD = plan.tmD;
+  p.M = plan.M; p.width = plan.width;
+  p.num_m_blocks = (plan.M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n2 = plan.width / BLOCK_N2;
+  p.KW = plan.g.KW; p.stride = plan.g.stride; p.pad_h = plan.g.pad_h; p.pad_w = plan.g.pad_w; p.P = plan.g.P; p.Q = plan.g.Q;
+  p.bias2 = plan.bias2; p.bias3 = plan.bias3;
+  return plan.mid == 64 ? launch_t<64>(p, plan.grid, stream) : launch_t<128>(p, plan.grid, stream);
+}
+
+}  // namespace opd
+
+extern "C" int opd_bottleneck_tail_bf16(const void* x_dev, int32_t B, int32_t H, int32_t W, int32_t mid, const void* w2_dev,
+                                        const float* bias2_dev, int32_t stride, const void* w3_dev, const float* bias3_dev,
+                                        int32_t width, const void* residual_dev, void* y_dev, void* stream) {
+  opd::ConvGeom g{B, H, W, mid, 3, 3, stride, 1, 1, (H + 2 - 3) / stride + 1, (W + 2 - 3) / stride + 1};
+  opd::BneckPlan plan;
+  if (int rc = opd::bneck_plan(&plan, static_cast<const __nv_bfloat16*>(x_dev), g, static_cast<const __nv_bfloat16*>(w2_dev),
+                               bias2_dev, static_cast<const __nv_bfloat16*>(w3_dev), bias3_dev, width,
+                               static_cast<const __nv_bfloat16*>(residual_dev), static_cast<__nv_bfloat16*>(y_dev)))
+    return rc;
+  return opd::bneck_launch(plan, static_cast<cudaStream_t>(stream));
+}

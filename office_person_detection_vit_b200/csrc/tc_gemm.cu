@@ -28,20 +28,25 @@ constexpr int BLOCK_K = 64;                   // 64 bf16 = 128 bytes = one swizz
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int STAGING_BYTES = BLOCK_M * 64 * 2;   // one 64-column output box
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 224;              // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warp 6 residual TMA
 constexpr int kSmemBudget = 232448;           // 227 KB
 
-__host__ __device__ constexpr int stages_for(int block_n) {
+// residual tiles travel global -> smem by TMA in 64-column chunks (same swizzled layout as the output staging)
+__host__ __device__ constexpr int res_stages_for(int block_n, bool has_res) {
+  return !has_res ? 0 : (block_n >= 256 ? 2 : 4);
+}
+__host__ __device__ constexpr int stages_for(int block_n, bool has_res) {
   const int stage = A_STAGE_BYTES + block_n * BLOCK_K * 2;
-  const int n = (kSmemBudget - 2 * STAGING_BYTES - 2048) / stage;
+  const int n = (kSmemBudget - (2 + res_stages_for(block_n, has_res)) * STAGING_BYTES - 2048) / stage;
   return n > 8 ? 8 : n;
 }
-__host__ __device__ constexpr int smem_bytes_for(int block_n) {
-  return stages_for(block_n) * (A_STAGE_BYTES + block_n * BLOCK_K * 2) + 2 * STAGING_BYTES + 2048;
+__host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res) {
+  return stages_for(block_n, has_res) * (A_STAGE_BYTES + block_n * BLOCK_K * 2) +
+         (2 + res_stages_for(block_n, has_res)) * STAGING_BYTES + 2048;
 }
 
 struct GemmParams {
-  CUtensorMap tmA, tmB, tmD, tmD2;
+  CUtensorMap tmA, tmB, tmD, tmD2, tmR;
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_k_blocks;
   int im2col;
@@ -58,9 +63,10 @@ struct GemmParams {
   int has_d2;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kHasRes>
 __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmParams p) {
-  constexpr int kStages = stages_for(BLOCK_N);
+  constexpr int kStages = stages_for(BLOCK_N, kHasRes);
+  constexpr int kResStages = res_stages_for(BLOCK_N, kHasRes);
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N);
@@ -69,13 +75,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
   uint8_t* smem_out = smem_b + kStages * B_STAGE_BYTES;           // 2 staging boxes
-  float* s_bias = reinterpret_cast<float*>(smem_out + 2 * STAGING_BYTES);   // [BLOCK_N]
+  uint8_t* smem_res = smem_out + 2 * STAGING_BYTES;               // kResStages residual chunks
+  float* s_bias = reinterpret_cast<float*>(smem_res + kResStages * STAGING_BYTES);   // [BLOCK_N]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint64_t* full_bar = bars;                    // [kStages]
   uint64_t* empty_bar = bars + kStages;         // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;     // [2]
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* res_full = bars + 2 * kStages + 4;    // [4]
+  uint64_t* res_empty = bars + 2 * kStages + 8;   // [4]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B tiles need 1024-byte alignment
@@ -91,6 +100,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
       ptx::mbar_init(&tmem_empty[i], 128);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&res_full[i], 1);
+      ptx::mbar_init(&res_empty[i], 4);   // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -172,6 +185,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
         }
       }
     }
+  } else if (warp == 6) {
+    // ===================================== residual TMA producer =====================================
+    if (kHasRes && lane == 0) {
+      ptx::prefetch_tmap(&p.tmR);
+      int rs = 0;
+      uint32_t rphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+        for (int c = 0; c < BLOCK_N / 64; ++c) {
+          ptx::mbar_wait(&res_empty[rs], rphase ^ 1);
+          ptx::mbar_expect_tx(&res_full[rs], STAGING_BYTES);
+          ptx::tma_load_2d(&p.tmR, &res_full[rs], smem_res + rs * STAGING_BYTES, n_blk * BLOCK_N + c * 64, m_blk * BLOCK_M);
+          if (++rs == kResStages) {
+            rs = 0;
+            rphase ^= 1;
+          }
+        }
+      }
+    }
   } else {
     // ===================================== epilogue (warps 2..5) =====================================
     const int et = threadIdx.x - 64;            // 0..127
@@ -181,6 +213,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t box = 0;                           // running count of output boxes -> staging buffer parity
+    int rs = 0;                                 // residual ring position
+    uint32_t rphase = 0;
+    // this thread's 64 B (32 columns, half `h` of a 64-column chunk) of the residual chunk in ring slot `slot`
+    auto load_res = [&](int slot, int h, uint4 (&rr)[4]) {
+      const uint8_t* rowp = smem_res + slot * STAGING_BYTES + row * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rowp + (((h * 4 + j) ^ (row & 7)) << 4));
+    };
+    auto release_res = [&]() {
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&res_empty[rs]);
+      if (++rs == kResStages) {
+        rs = 0;
+        rphase ^= 1;
+      }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
@@ -201,16 +249,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
         for (int g = 0; g < BLOCK_N / 32; ++g) {
           uint32_t v[32];
           ptx::tmem_ld_32x32(t_acc + g * 32, v);
-          ptx::tmem_ld_wait();
           uint4 rr[4];
-          if (row_ok) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n0 + g * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rr[j] = __ldg(rp + j);
+          if constexpr (kHasRes) {
+            if ((g & 1) == 0) ptx::mbar_wait(&res_full[rs], rphase);
+            load_res(rs, g & 1, rr);
+            if (g & 1) release_res();
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0, 0, 0, 0);
           }
+          ptx::tmem_ld_wait();
           const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -250,11 +298,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
             }
           } else {
             uint4 rr[4];
-            const bool has_res = p.epi == EPI_BIAS_RES_RELU;
-            if (has_res && row_ok) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + n0 + g * 32);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rr[j] = __ldg(rp + j);
+            if constexpr (kHasRes) {
+              if (h == 0) ptx::mbar_wait(&res_full[rs], rphase);
+              load_res(rs, h, rr);
+              if (h == 1) release_res();
             } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0, 0, 0, 0);
@@ -355,6 +402,8 @@ int load_driver_entry_points() {
   return rc;
 }
 
+}  // namespace
+
 // 2D bf16 matrix [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   if (int rc = load_driver_entry_points()) return rc;
@@ -406,15 +455,17 @@ int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g) {
   return OPD_OK;
 }
 
-template <int BLOCK_N>
+namespace {
+
+template <int BLOCK_N, bool kHasRes>
 int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BLOCK_N>;
+  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes>;
   if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N)));
+    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes)));
     configured = true;
   }
-  kern<<<grid, kNumThreads, smem_bytes_for(BLOCK_N), s>>>(p);
+  kern<<<grid, kNumThreads, smem_bytes_for(BLOCK_N, kHasRes), s>>>(p);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;
@@ -426,6 +477,8 @@ int finish_plan(GemmPlan* plan) {
               plan->K);
   int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
   if (plan->epi == EPI_BIAS_RES_LN) OPD_REQUIRE(N == 256, "gemm: the LayerNorm epilogue needs N == 256 (got %d)", N);
+  // bottleneck outputs (bias + residual + ReLU) are HBM-bound: narrower tiles leave room for a deeper residual ring
+  if (plan->epi == EPI_BIAS_RES_RELU && bn == 256) bn = 128;
   // small problems: prefer more, narrower tiles so that every SM gets work
   const long long m_blocks = (plan->M + BLOCK_M - 1) / BLOCK_M;
   while (bn > 64 && plan->epi != EPI_BIAS_RES_LN && m_blocks * (N / bn) < sm_count() && N % (bn / 2) == 0) bn /= 2;
@@ -468,6 +521,11 @@ int gemm_plan_linear(GemmPlan* plan, const __nv_bfloat16* A, int64_t lda, const 
   } else {
     plan->tmD2 = plan->tmD;
   }
+  if (epi == EPI_BIAS_RES_RELU || epi == EPI_BIAS_RES_LN) {
+    if (int rc = make_tmap_2d(&plan->tmR, residual, M, N, ldr, BLOCK_M)) return rc;
+  } else {
+    plan->tmR = plan->tmD;
+  }
   return OPD_OK;
 }
 
@@ -485,12 +543,17 @@ int gemm_plan_conv(GemmPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, co
   if (int rc = make_tmap_2d(&plan->tmB, W, N, plan->K, plan->K, plan->block_n)) return rc;
   if (int rc = make_tmap_2d(&plan->tmD, D, plan->M, N, N, BLOCK_M)) return rc;
   plan->tmD2 = plan->tmD;
+  if (epi == EPI_BIAS_RES_RELU) {
+    if (int rc = make_tmap_2d(&plan->tmR, residual, plan->M, N, N, BLOCK_M)) return rc;
+  } else {
+    plan->tmR = plan->tmD;
+  }
   return OPD_OK;
 }
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   GemmParams p;
-  p.tmA = plan.tmA; p.tmB = plan.tmB; p.tmD = plan.tmD; p.tmD2 = plan.tmD2;
+  p.tmA = plan.tmA; p.tmB = plan.tmB; p.tmD = plan.tmD; p.tmD2 = plan.tmD2; p.tmR = plan.tmR;
   p.M = plan.M; p.N = plan.N; p.K = plan.K;
   p.num_m_blocks = (plan.M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_blocks = plan.N / plan.block_n;
@@ -500,10 +563,11 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   p.KW = plan.g.KW; p.stride = plan.g.stride; p.pad_h = plan.g.pad_h; p.pad_w = plan.g.pad_w; p.P = plan.g.P; p.Q = plan.g.Q;
   p.epi = plan.epi; p.bias = plan.bias; p.residual = plan.residual; p.ldr = plan.ldr;
   p.gamma = plan.gamma; p.beta = plan.beta; p.pos = plan.pos; p.pos_rows = plan.pos_rows; p.has_d2 = plan.has_d2;
+  const bool has_res = plan.epi == EPI_BIAS_RES_RELU || plan.epi == EPI_BIAS_RES_LN;
   switch (plan.block_n) {
-    case 64: return launch_t<64>(p, plan.grid, stream);
-    case 128: return launch_t<128>(p, plan.grid, stream);
-    case 256: return launch_t<256>(p, plan.grid, stream);
+    case 64: return has_res ? launch_t<64, true>(p, plan.grid, stream) : launch_t<64, false>(p, plan.grid, stream);
+    case 128: return has_res ? launch_t<128, true>(p, plan.grid, stream) : launch_t<128, false>(p, plan.grid, stream);
+    case 256: return has_res ? launch_t<256, true>(p, plan.grid, stream) : launch_t<256, false>(p, plan.grid, stream);
   }
   return fail(OPD_ERR_INVALID, "gemm: unsupported block_n %d", plan.block_n);
 }

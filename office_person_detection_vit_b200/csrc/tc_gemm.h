@@ -28,7 +28,7 @@ struct ConvGeom {
 };
 
 struct GemmPlan {
-  CUtensorMap tmA, tmB, tmD, tmD2;
+  CUtensorMap tmA, tmB, tmD, tmD2, tmR;   // tmR: residual, read by TMA in 64-column chunks
   int M, N, K;
   int block_n;
   int im2col;          // 0: A is [M,K] rows; 1: A is NHWC through im2col TMA
@@ -56,5 +56,24 @@ int gemm_plan_conv(GemmPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, co
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 
 int sm_count();
+
+// Tensor maps (128-byte swizzle): 2D bf16 matrix [rows, cols] with row pitch ld elements, box = [box_rows, 64 columns];
+// NHWC activation in im2col mode, box = 128 output pixels x 64 channels of one filter tap.
+int make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g);
+
+// Fused bottleneck tail (tc_bottleneck.cu): y = relu(conv1x1(relu(conv3x3(x, stride) + b2)) + b3 + residual).
+// x [B,H,W,MID] NHWC, w2 [MID,3,3,MID], w3 [WIDTH,MID], residual / y [B,P,Q,WIDTH]; MID in {64, 128}, WIDTH % 128 == 0.
+struct BneckPlan {
+  CUtensorMap tmA, tmB1, tmB2, tmR, tmD;
+  int M, mid, width;
+  ConvGeom g;
+  const float* bias2;
+  const float* bias3;
+  int grid;
+};
+int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
+               const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y);
+int bneck_launch(const BneckPlan& plan, cudaStream_t stream);
 
 }  // namespace opd

@@ -16,6 +16,9 @@ _lib.register("opd_conv2d_nhwc_bf16", C.c_int, [_P, C.c_int32, C.c_int32, C.c_in
 _lib.register("opd_attention_bf16", C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int32,
                                              C.c_int32, C.c_int32, C.c_int32, _P])
 
+_lib.register("opd_bottleneck_tail_bf16", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P,
+                                                   C.c_int32, _P, _P, _P])
+
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_BIAS_RES_LN = 0, 1, 2, 3
 
 
@@ -57,3 +60,16 @@ def attention(q, k, v, heads=8):
                                        _lib.ptr(o), D, B, heads, Lq, Lk, _lib.stream_ptr())
     _lib.check(rc, "opd_attention_bf16")
     return o
+
+
+def bottleneck_tail(x, w2, bias2, w3, bias3, residual, stride=1):
+    """y = relu(conv1x1(relu(conv3x3(x, stride) + bias2), w3) + bias3 + residual), one fused kernel.
+    x [B,H,W,mid], w2 [mid,3,3,mid], w3 [width,mid], residual [B,P,Q,width] (all bf16) -> y like residual."""
+    torch = _lib.require_cuda()
+    B, H, W, mid = x.shape
+    width = w3.shape[0]
+    y = torch.empty_like(residual)
+    rc = _lib.lib().opd_bottleneck_tail_bf16(_lib.ptr(x), B, H, W, mid, _lib.ptr(w2), _lib.ptr(bias2), stride, _lib.ptr(w3),
+                                             _lib.ptr(bias3), width, _lib.ptr(residual), _lib.ptr(y), _lib.stream_ptr())
+    _lib.check(rc, "opd_bottleneck_tail_bf16")
+    return y

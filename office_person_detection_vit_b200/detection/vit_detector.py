@@ -39,6 +39,7 @@ _lib.register("opd_detr_create", C.c_int, [C.POINTER(_TensorF32), C.c_int32, C.c
 _lib.register("opd_detr_destroy", None, [_P])
 _lib.register("opd_detr_set_debug", C.c_int, [_P, C.c_int32])
 _lib.register("opd_detr_set_resize", C.c_int, [_P, C.c_int32])
+_lib.register("opd_detr_set_fusion", C.c_int, [_P, C.c_int32])
 _lib.register("opd_detr_input_shape", C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                C.POINTER(C.c_int32), C.POINTER(C.c_int32)])
 _lib.register("opd_detr_workspace_bytes", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)])
@@ -108,6 +109,10 @@ class DetrEngine:
         _lib.check(_lib.lib().opd_detr_set_resize(self._h, int(on)), "opd_detr_set_resize")
         self._ws.clear()
 
+    def set_fusion(self, on: bool) -> None:
+        """False: stages 1-2 run their 3x3 and 1x1-expansion convolutions as separate kernels (A/B comparison)."""
+        _lib.check(_lib.lib().opd_detr_set_fusion(self._h, int(on)), "opd_detr_set_fusion")
+
     def workspace(self, B: int, H0: int, W0: int):
         key = (B, H0, W0)
         ws = self._ws.get(key)
@@ -160,7 +165,7 @@ class DetrEngine:
         p, rows, cols, f32 = _P(), C.c_int64(), C.c_int64(), C.c_int32()
         _lib.check(_lib.lib().opd_detr_tap(self._h, name.encode(), C.byref(p), C.byref(rows), C.byref(cols), C.byref(f32)),
                    "opd_detr_tap")
-        dt = torch.float32 if f32.value else torch.bfloat16
+        dt = {0: torch.bfloat16, 1: torch.float32, 2: torch.uint8}[f32.value]
         out = torch.empty(rows.value, cols.value, dtype=dt, device=f"cuda:{self.device_index}")
         _lib.check(_lib.lib().opd_detr_tap_copy(self._h, name.encode(), out.data_ptr(), out.numel() * out.element_size(),
                                                 _lib.stream_ptr()), "opd_detr_tap_copy")

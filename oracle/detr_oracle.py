@@ -95,6 +95,54 @@ def resized_size(h: int, w: int, size: int = 800, max_size: int = 1333) -> tuple
     return size, (int(raw * w / h) if raw is not None else int(size * w / h))
 
 
+def _aa_table(in_size: int, out_size: int):
+    """ATen aten/src/ATen/native/cpu/UpSampleKernel.cpp (_compute_indices_min_size_weights_aa,
+    _compute_index_ranges_int16_weights), bilinear: first source index, int16 weights [out, ksize], precision."""
+    scale = in_size / out_size
+    support = scale if scale >= 1.0 else 1.0
+    ksize = int(math.ceil(support)) * 2 + 1
+    invscale = 1.0 / scale if scale >= 1.0 else 1.0
+    x0 = np.zeros(out_size, np.int64)
+    wt = np.zeros((out_size, ksize), np.float64)
+    wt_max = 0.0
+    for i in range(out_size):
+        center = scale * (i + 0.5)
+        xmin = max(int(center - support + 0.5), 0)
+        xsize = min(max(min(int(center + support + 0.5), in_size) - xmin, 0), ksize)
+        w = np.array([max(0.0, 1.0 - abs((j + xmin - center + 0.5) * invscale)) for j in range(xsize)], np.float64)
+        total = w.sum() if xsize else 0.0
+        if total != 0.0:
+            w = w / total
+            wt_max = max(wt_max, float(w.max()))
+        wt[i, :xsize] = w
+        x0[i] = xmin
+    precision = 0
+    while precision < 22 and int(0.5 + wt_max * (1 << (precision + 1))) < (1 << 15):
+        precision += 1
+    v = wt * (1 << precision)
+    w16 = np.where(v < 0, (-0.5 + v).astype(np.int64), (0.5 + v).astype(np.int64))
+    return x0, w16, ksize, precision
+
+
+def resize_u8_antialias(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """[..., H, W] uint8 -> [..., out_h, out_w] uint8: the separable fixed-point kernel torch runs for
+    F.interpolate(uint8, mode="bilinear", antialias=True) on the CPU (horizontal pass, uint8 intermediate, vertical
+    pass).  Independent numpy restatement used to pin the CUDA resize; checked bit-exact against torch in tests."""
+    def one_axis(a, axis, out_size):
+        in_size = a.shape[axis]
+        if in_size == out_size:
+            return a
+        x0, w16, ksize, prec = _aa_table(in_size, out_size)
+        src = np.moveaxis(a, axis, 0).astype(np.int64)
+        idx = np.minimum(x0[:, None] + np.arange(ksize)[None, :], in_size - 1)          # [out, k]
+        acc = np.full((out_size,) + src.shape[1:], 1 << (prec - 1), np.int64)
+        for j in range(ksize):
+            acc += src[idx[:, j]] * w16[:, j].reshape((-1,) + (1,) * (src.ndim - 1))
+        return np.moveaxis(np.clip(acc >> prec, 0, 255).astype(np.uint8), 0, axis)
+
+    return one_axis(one_axis(np.asarray(img), -1, out_w), -2, out_h)
+
+
 def preprocess(frames_bgr: np.ndarray | torch.Tensor, do_resize: bool = True) -> torch.Tensor:
     """[B,H0,W0,3] uint8 BGR -> pixel_values [B,3,H,W] float32 (all frames the same size: no padding, mask = 1).
 

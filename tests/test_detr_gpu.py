@@ -88,7 +88,7 @@ def test_detections_800x1333(detector, weights):
     d_score = float((out["scores"].cpu() - sc).abs().max())
     agree = float((out["labels"].cpu() == lb).float().mean())
     print(f"max |box| err {d_box:.4f} px, max |score| err {d_score:.5f}, label agreement {agree:.4f}")
-    assert d_box < 8.0 and d_score < 3e-2 and agree > 0.97
+    assert d_box < 0.015 * 1333 and d_score < 3e-2 and agree > 0.97
 
     # device post-processing == oracle post-processing on the SAME logits / boxes (fp32, exact up to 1 ulp)
     from office_person_detection_vit_b200.detection import postprocess_tensors
@@ -117,3 +117,26 @@ def test_detect_batch_surface(detector, weights):
             assert d.camera_coords == pytest.approx((x + w / 2, y + h))
             assert detector._get_foot_position(d.bbox) == pytest.approx(d.camera_coords)
     assert detector.detect_batch([]) == []
+
+
+def test_camera_frame_resize_path(detector, weights):
+    """1280x720 camera frames (config 1): uint8 antialias resize to 750x1333 is bit-exact against torch's CPU kernel
+    (= DetrImageProcessor), and detections follow the oracle."""
+    import torch
+
+    frames = do.synthetic_frames(2, 720, 1280, seed=4)
+    eng = detector.model
+    out = detector.detect_tensors(torch.from_numpy(frames).cuda(), threshold=0.0)
+    got = eng.tap("resized_u8").cpu().numpy().reshape(2, 750, 1333, 3)
+    rgb_chw = np.ascontiguousarray(frames[..., ::-1].transpose(0, 3, 1, 2))
+    ref = torch.nn.functional.interpolate(torch.from_numpy(rgb_chw), size=(750, 1333), mode="bilinear", antialias=True,
+                                          align_corners=False).numpy().transpose(0, 2, 3, 1)
+    assert (got == ref).all()
+    ref_logits, ref_boxes = do.forward(weights, frames, mode="bf16")
+    sc, lb, xyxy = do.postprocess(ref_logits, ref_boxes, 720, 1280)
+    d_box = float((out["xyxy"].cpu() - xyxy).abs().max())
+    d_score = float((out["scores"].cpu() - sc).abs().max())
+    agree = float((out["labels"].cpu() == lb).float().mean())
+    print(f"720x1280: max |box| err {d_box:.4f} px, max |score| err {d_score:.5f}, label agreement {agree:.4f}")
+    assert out["logits"].shape == (2, 100, 92)
+    assert d_box < 0.015 * 1280 and d_score < 3e-2 and agree > 0.97

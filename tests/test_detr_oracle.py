@@ -67,3 +67,12 @@ def test_weights_are_non_degenerate(golden):
     prob = torch.softmax(torch.from_numpy(golden["small_logits"]), -1)[..., :-1]
     frac_person = float((prob.argmax(-1) == do.PERSON_LABEL).float().mean())
     assert 0.2 < frac_person <= 1.0
+
+
+@pytest.mark.parametrize("h0,w0,h1,w1", [(72, 128, 75, 133), (90, 160, 94, 167), (100, 90, 40, 37), (64, 64, 64, 200)])
+def test_resize_restatement_is_bit_exact(h0, w0, h1, w1):
+    """The numpy restatement of ATen's uint8 antialias kernel (which the CUDA resize is checked against on the GPU)."""
+    img = np.random.default_rng(h0 * w1).integers(0, 256, (2, 3, h0, w0), dtype=np.uint8)
+    ref = torch.nn.functional.interpolate(torch.from_numpy(img), size=(h1, w1), mode="bilinear", antialias=True,
+                                          align_corners=False).numpy()
+    assert (do.resize_u8_antialias(img, h1, w1) == ref).all()

@@ -110,3 +110,29 @@ def test_attention(T, B, Lq, Lk):
     ref = torch.softmax(qh @ kh.transpose(2, 3) * 32 ** -0.5, -1) @ vh
     ref = ref.transpose(1, 2).reshape(B, Lq, D)
     _close(torch, o, ref, f"attention {B}x{Lq}x{Lk}")
+
+
+@pytest.mark.parametrize("B,H,W,mid,width,stride", [
+    (1, 16, 16, 64, 256, 1),
+    (2, 50, 83, 64, 256, 1),
+    (3, 40, 67, 128, 512, 1),
+    (2, 51, 84, 128, 512, 2),
+    (1, 200, 334, 64, 256, 1),
+    (4, 100, 167, 128, 512, 1),
+])
+def test_fused_bottleneck_tail(T, B, H, W, mid, width, stride):
+    """conv3x3 + ReLU -> (bf16 in shared memory) -> conv1x1 + bias + residual + ReLU in one kernel."""
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    x = _rand(torch, B, H, W, mid, seed=20)
+    w2 = _rand(torch, mid, 3, 3, mid, seed=21, scale=(9 * mid) ** -0.5)
+    w3 = _rand(torch, width, mid, seed=22, scale=mid ** -0.5)
+    b2, b3 = torch.randn(mid, device="cuda") * 0.3, torch.randn(width, device="cuda") * 0.3
+    m = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w2.float().permute(0, 3, 1, 2), b2, stride=stride, padding=1)
+    m = m.relu().to(torch.bfloat16).float().permute(0, 2, 3, 1)          # the mid activation is rounded to bf16
+    res = _rand(torch, *m.shape[:3], width, seed=23)
+    ref = (m @ w3.float().T + b3 + res.float()).relu()
+    y = ops.bottleneck_tail(x, w2, b2, w3, b3, res, stride=stride)
+    assert y.shape == ref.shape
+    _close(torch, y, ref, f"bottleneck tail {B}x{H}x{W} mid {mid} width {width} s{stride}")
