@@ -11,7 +11,8 @@
 //   E1(t): A2 = bf16(relu(acc1 + b2))                               TMEM -> regs -> 128B-swizzled smem (K-major operand)
 //   G2(t): acc2[128 x 128] = A2[128 x MID] * W3[n2]^T  per n2 tile  B2 tiles through the same ring
 //   E2(t): y = bf16(relu(acc2 + b3 + residual))                     residual by TMA ring, output by TMA store
-// Warp roles: 0 TMA producer, 1 MMA issuer + TMEM owner, 2-5 epilogue, 6 residual producer.
+// Warp roles: 0 TMA producer, 1 MMA issuer + TMEM owner, 2 residual producer, 4-11 epilogue (two warpgroups that
+// split the columns: the epilogue, not the tensor pipe, paces these HBM-bound layers).
 // MMA issue order G1(t0) G1(t1) G2(t0) G1(t2) G2(t1) ... so that E1 / E2 of one tile overlap the MMAs of the next.
 #include <algorithm>
 
@@ -27,15 +28,15 @@ constexpr int BLOCK_K = 64;
 constexpr int BLOCK_N2 = 128;
 constexpr int UMMA_K = 16;
 constexpr int CHUNK_BYTES = BLOCK_M * 64 * 2;        // one [128 x 64] bf16 box = 16 KB
-constexpr int kThreads = 224;
+constexpr int kThreads = 384;   // warps: 0 TMA, 1 MMA, 2 residual TMA, 3 idle, 4-11 epilogue (two warpgroups)
 constexpr int kSmemBudget = 232448;
 
 template <int MID>
 struct Cfg {
   static constexpr int kA2Chunks = MID / 64;
-  static constexpr int kResStages = MID == 64 ? 4 : 2;
+  static constexpr int kResStages = 2;                               // one residual chunk slot per epilogue warpgroup
   static constexpr int kStageBytes = 2 * CHUNK_BYTES;               // A slot 16 KB + B slot 16 KB (B1: MID x 64, B2: 128 x 64)
-  static constexpr int kFixed = (kA2Chunks + 2 + kResStages) * CHUNK_BYTES + 2048;
+  static constexpr int kFixed = (kA2Chunks + 4 + kResStages) * CHUNK_BYTES + 2048;
   static constexpr int kStages = (kSmemBudget - kFixed) / kStageBytes > 6 ? 6 : (kSmemBudget - kFixed) / kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
   static constexpr int kTmemCols = 512;                             // acc1 2 x MID + acc2 2 x 128
@@ -66,8 +67,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
   uint8_t* smem_a = smem;                                    // ring: A slots
   uint8_t* smem_b = smem_a + kStages * CHUNK_BYTES;          // ring: B slots
   uint8_t* smem_a2 = smem_b + kStages * CHUNK_BYTES;         // A operand of the second GEMM
-  uint8_t* smem_out = smem_a2 + C::kA2Chunks * CHUNK_BYTES;  // 2 output staging boxes
-  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;            // residual ring
+  uint8_t* smem_out = smem_a2 + C::kA2Chunks * CHUNK_BYTES;  // 2 output staging boxes per epilogue warpgroup
+  uint8_t* smem_res = smem_out + 4 * CHUNK_BYTES;            // residual ring
   float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [MID]
   float* s_bias3 = s_bias2 + 128;                                                   // [128] of the current n2 tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 128);
@@ -97,11 +98,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc1_full[i], 1);
-      ptx::mbar_init(&acc1_empty[i], 128);
+      ptx::mbar_init(&acc1_empty[i], 256);
       ptx::mbar_init(&acc2_full[i], 1);
-      ptx::mbar_init(&acc2_empty[i], 128);
+      ptx::mbar_init(&acc2_empty[i], 256);
     }
-    ptx::mbar_init(a2_ready, 128);
+    ptx::mbar_init(a2_ready, 256);
     ptx::mbar_init(a2_free, 1);
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&res_full[i], 1);
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
         g2();
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     // ===================================== residual TMA producer =====================================
     if (lane == 0) {
       ptx::prefetch_tmap(&p.tmR);
@@ -246,17 +247,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
             }
           }
     }
-  } else {
-    // ===================================== epilogue (warps 2..5) =====================================
-    const int et = threadIdx.x - 64;
+  } else if (warp >= 4) {
+    // ============================ epilogue: two warpgroups (warps 4-7, 8-11) ============================
+    // Both warpgroups cover all 128 rows (TMEM lane quarter = warp % 4) and split the COLUMNS: in E1 each converts
+    // half of acc1, in E2 warpgroup g owns the 64-column chunk g of every 128-column n2 tile (its own residual
+    // ring slots, bias slice, staging buffers and TMA stores).
+    const int wg = (warp - 4) >> 2;             // 0 or 1
+    const int et = threadIdx.x - 128 - wg * 128;   // 0..127 inside the warpgroup
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    for (int i = et; i < MID; i += 128) s_bias2[i] = p.bias2[i];
-    ptx::named_bar_sync(1, 128);
+    const int bar_id = 1 + wg;
+    for (int i = threadIdx.x - 128; i < MID; i += 256) s_bias2[i] = p.bias2[i];
+    ptx::named_bar_sync(3, 256);
 
-    int a1 = 0, a2 = 0, rs = 0;
+    int a1 = 0, a2 = 0, rs = wg;
     uint32_t a1_phase = 0, a2_phase = 0, rphase = 0, free_phase = 0, box = 0;
+    float* my_bias3 = s_bias3 + wg * 64;
+    uint8_t* my_out = smem_out + wg * 2 * CHUNK_BYTES;
 
     auto e1 = [&]() {
       ptx::mbar_wait(&acc1_full[a1], a1_phase);
@@ -264,25 +272,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
       free_phase ^= 1;
       ptx::tc_fence_after_sync();
       const uint32_t t_acc = tmem_acc1 + lane_addr + a1 * MID;
+      constexpr int kUnits = MID / 64;           // 32-column units per warpgroup
 #pragma unroll
-      for (int c = 0; c < MID / 64; ++c) {
-        uint32_t packed[32];
+      for (int uu = 0; uu < kUnits; ++uu) {
+        const int u = wg * kUnits + uu;          // global 32-column unit: chunk u / 2, half u % 2
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_acc + u * 32, v);
+        ptx::tmem_ld_wait();
+        uint32_t packed[16];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(t_acc + c * 64 + h * 32, v);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = fmaxf(__uint_as_float(v[2 * j]) + s_bias2[c * 64 + h * 32 + 2 * j], 0.f);
-            const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias2[c * 64 + h * 32 + 2 * j + 1], 0.f);
-            packed[h * 16 + j] = ptx::pack_bf16(a, b);
-          }
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaxf(__uint_as_float(v[2 * j]) + s_bias2[u * 32 + 2 * j], 0.f);
+          const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias2[u * 32 + 2 * j + 1], 0.f);
+          packed[j] = ptx::pack_bf16(a, b);
         }
-        uint8_t* rowp = smem_a2 + c * CHUNK_BYTES + row * 128;
+        uint8_t* rowp = smem_a2 + (u >> 1) * CHUNK_BYTES + row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(rowp + ((((u & 1) * 4 + j) ^ (row & 7)) << 4)) =
               make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
       }
       ptx::tc_fence_before_sync();
@@ -296,60 +303,59 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     };
 
     auto e2 = [&](int m_blk, int n2) {
-      const int m0 = m_blk * BLOCK_M, n0 = n2 * BLOCK_N2;
-      for (int i = et; i < BLOCK_N2; i += 128) s_bias3[i] = p.bias3[n0 + i];
-      ptx::named_bar_sync(1, 128);
+      const int m0 = m_blk * BLOCK_M, n0 = n2 * BLOCK_N2 + wg * 64;
+      if (et < 64) my_bias3[et] = p.bias3[n0 + et];
+      ptx::named_bar_sync(bar_id, 128);
       ptx::mbar_wait(&acc2_full[a2], a2_phase);
       ptx::tc_fence_after_sync();
-      const uint32_t t_acc = tmem_acc2 + lane_addr + a2 * BLOCK_N2;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N2 / 64; ++c) {
-        uint32_t packed[32];
-        ptx::mbar_wait(&res_full[rs], rphase);
-        const uint8_t* rrow = smem_res + rs * CHUNK_BYTES + row * 128;
+      const uint32_t t_acc = tmem_acc2 + lane_addr + a2 * BLOCK_N2 + wg * 64;
+      uint32_t packed[32];
+      ptx::mbar_wait(&res_full[rs], rphase);
+      const uint8_t* rrow = smem_res + rs * CHUNK_BYTES + row * 128;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(t_acc + c * 64 + h * 32, v);
-          uint4 rr[4];
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_acc + h * 32, v);
+        uint4 rr[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rrow + (((h * 4 + j) ^ (row & 7)) << 4));
-          ptx::tmem_ld_wait();
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
+        for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rrow + (((h * 4 + j) ^ (row & 7)) << 4));
+        ptx::tmem_ld_wait();
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = fmaxf(__uint_as_float(v[2 * j]) + s_bias3[c * 64 + h * 32 + 2 * j] + ptx::bf16_lo(rw[j]), 0.f);
-            const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias3[c * 64 + h * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]), 0.f);
-            packed[h * 16 + j] = ptx::pack_bf16(a, b);
-          }
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaxf(__uint_as_float(v[2 * j]) + my_bias3[h * 32 + 2 * j] + ptx::bf16_lo(rw[j]), 0.f);
+          const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + my_bias3[h * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]), 0.f);
+          packed[h * 16 + j] = ptx::pack_bf16(a, b);
         }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&res_empty[rs]);
-        if (++rs == kResStages) {
-          rs = 0;
-          rphase ^= 1;
-        }
-        uint8_t* buf = smem_out + (box & 1) * CHUNK_BYTES;
-        uint8_t* rowp = buf + row * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
-              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        ptx::fence_proxy_async_smem();
-        if (et == 0) ptx::tma_store_wait_read<0>();
-        ptx::named_bar_sync(1, 128);
-        if (et == 0) {
-          ptx::tma_store_2d(&p.tmD, buf, n0 + c * 64, m0);
-          ptx::tma_store_commit();
-        }
-        ++box;
       }
+      // accumulator and residual chunk are in registers: hand both back before the store path
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&acc2_empty[a2]);
       if (++a2 == 2) {
         a2 = 0;
         a2_phase ^= 1;
       }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&res_empty[rs]);
+      rs += 2;
+      if (rs >= kResStages) {
+        rs = wg;
+        rphase ^= 1;
+      }
+      uint8_t* buf = my_out + (box & 1) * CHUNK_BYTES;
+      uint8_t* rowp = buf + row * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      ptx::fence_proxy_async_smem();
+      if (et == 0) ptx::tma_store_wait_read<0>();
+      ptx::named_bar_sync(bar_id, 128);
+      if (et == 0) {
+        ptx::tma_store_2d(&p.tmD, buf, n0, m0);
+        ptx::tma_store_commit();
+      }
+      ++box;
     };
 
     if (first < n_mblk) e1();
