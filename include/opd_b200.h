@@ -41,6 +41,9 @@ int opd_version(void);
 const char* opd_last_error(void);
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t opd_launch_count(void);
+/* Kernel-selection knobs for A/B measurements (plans built afterwards see the new value):
+ *   "bneck_halo"  1 (default): 64-channel stride-1 bottleneck tails load one halo patch per tile; 0: im2col TMA. */
+int opd_set_option(const char* name, int32_t value);
 
 /* ------------------------------------------------------------------------------------------
  * Floor projection + zone classification + counting  (K9 + K10 + K11)

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "opd_version": (C.c_int, []),
     "opd_last_error": (C.c_char_p, []),
     "opd_launch_count": (C.c_int64, []),
+    "opd_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
     "opd_zone_table_create": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "opd_zone_table_destroy": (None, [_P]),
     "opd_zone_table_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),

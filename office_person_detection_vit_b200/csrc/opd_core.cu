@@ -7,10 +7,18 @@ std::string& last_error_ref() {
   return s;
 }
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_option_bneck_halo{1};
 }  // namespace opd
 
 extern "C" {
 int opd_version(void) { return OPD_ABI_VERSION; }
 const char* opd_last_error(void) { return opd::last_error_ref().c_str(); }
 int64_t opd_launch_count(void) { return opd::g_launches.load(); }
+int opd_set_option(const char* name, int32_t value) {
+  if (name && std::string(name) == "bneck_halo") {
+    opd::g_option_bneck_halo.store(value);
+    return OPD_OK;
+  }
+  return opd::fail(OPD_ERR_INVALID, "opd_set_option: unknown option '%s'", name ? name : "(null)");
+}
 }

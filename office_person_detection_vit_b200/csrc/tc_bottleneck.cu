@@ -34,9 +34,9 @@ constexpr int kSmemBudget = 232448;
 template <int MID>
 struct Cfg {
   static constexpr int kA2Chunks = MID / 64;
-  static constexpr int kResStages = 2;                               // one residual chunk slot per epilogue warpgroup
+  static constexpr int kResStages = 4;                               // two residual chunk slots per epilogue warpgroup
   static constexpr int kStageBytes = 2 * CHUNK_BYTES;               // A slot 16 KB + B slot 16 KB (B1: MID x 64, B2: 128 x 64)
-  static constexpr int kFixed = (kA2Chunks + 4 + kResStages) * CHUNK_BYTES + 2048;
+  static constexpr int kFixed = (kA2Chunks + 2 + kResStages) * CHUNK_BYTES + 2048;
   static constexpr int kStages = (kSmemBudget - kFixed) / kStageBytes > 6 ? 6 : (kSmemBudget - kFixed) / kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
   static constexpr int kTmemCols = 512;                             // acc1 2 x MID + acc2 2 x 128
@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
   uint8_t* smem_a = smem;                                    // ring: A slots
   uint8_t* smem_b = smem_a + kStages * CHUNK_BYTES;          // ring: B slots
   uint8_t* smem_a2 = smem_b + kStages * CHUNK_BYTES;         // A operand of the second GEMM
-  uint8_t* smem_out = smem_a2 + C::kA2Chunks * CHUNK_BYTES;  // 2 output staging boxes per epilogue warpgroup
-  uint8_t* smem_res = smem_out + 4 * CHUNK_BYTES;            // residual ring
+  uint8_t* smem_out = smem_a2 + C::kA2Chunks * CHUNK_BYTES;  // one output staging box per epilogue warpgroup
+  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;            // residual slots
   float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [MID]
   float* s_bias3 = s_bias2 + 128;                                                   // [128] of the current n2 tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 128);
@@ -233,18 +233,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     // ===================================== residual TMA producer =====================================
     if (lane == 0) {
       ptx::prefetch_tmap(&p.tmR);
-      int rs = 0;
-      uint32_t rphase = 0;
+      uint32_t k = 0;   // chunk counter per warpgroup: slot = wg * 2 + (k & 1), parity = (k >> 1) & 1
       for (int t = first; t < n_mblk; t += step)
-        for (int n2 = 0; n2 < p.num_n2; ++n2)
-          for (int c = 0; c < 2; ++c) {
-            ptx::mbar_wait(&res_empty[rs], rphase ^ 1);
-            ptx::mbar_expect_tx(&res_full[rs], CHUNK_BYTES);
-            ptx::tma_load_2d(&p.tmR, &res_full[rs], smem_res + rs * CHUNK_BYTES, n2 * BLOCK_N2 + c * 64, t * BLOCK_M);
-            if (++rs == kResStages) {
-              rs = 0;
-              rphase ^= 1;
-            }
+        for (int n2 = 0; n2 < p.num_n2; ++n2, ++k)
+          for (int c = 0; c < 2; ++c) {   // chunk c of the n2 tile belongs to epilogue warpgroup c
+            const int slot = c * 2 + (k & 1);
+            ptx::mbar_wait(&res_empty[slot], ((k >> 1) & 1) ^ 1);
+            ptx::mbar_expect_tx(&res_full[slot], CHUNK_BYTES);
+            ptx::tma_load_2d(&p.tmR, &res_full[slot], smem_res + slot * CHUNK_BYTES, n2 * BLOCK_N2 + c * 64, t * BLOCK_M);
           }
     }
   } else if (warp >= 4) {
@@ -261,10 +257,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     for (int i = threadIdx.x - 128; i < MID; i += 256) s_bias2[i] = p.bias2[i];
     ptx::named_bar_sync(3, 256);
 
-    int a1 = 0, a2 = 0, rs = wg;
-    uint32_t a1_phase = 0, a2_phase = 0, rphase = 0, free_phase = 0, box = 0;
+    int a1 = 0, a2 = 0;
+    uint32_t a1_phase = 0, a2_phase = 0, rk = 0, free_phase = 0;
     float* my_bias3 = s_bias3 + wg * 64;
-    uint8_t* my_out = smem_out + wg * 2 * CHUNK_BYTES;
+    uint8_t* my_out = smem_out + wg * CHUNK_BYTES;
 
     auto e1 = [&]() {
       ptx::mbar_wait(&acc1_full[a1], a1_phase);
@@ -305,12 +301,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     auto e2 = [&](int m_blk, int n2) {
       const int m0 = m_blk * BLOCK_M, n0 = n2 * BLOCK_N2 + wg * 64;
       if (et < 64) my_bias3[et] = p.bias3[n0 + et];
+      if (et == 0) ptx::tma_store_wait_read<0>();     // my staging box: the previous store has finished reading it
       ptx::named_bar_sync(bar_id, 128);
       ptx::mbar_wait(&acc2_full[a2], a2_phase);
       ptx::tc_fence_after_sync();
       const uint32_t t_acc = tmem_acc2 + lane_addr + a2 * BLOCK_N2 + wg * 64;
       uint32_t packed[32];
-      ptx::mbar_wait(&res_full[rs], rphase);
+      const int rs = wg * 2 + (rk & 1);
+      ptx::mbar_wait(&res_full[rs], (rk >> 1) & 1);
+      ++rk;
       const uint8_t* rrow = smem_res + rs * CHUNK_BYTES + row * 128;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -337,31 +336,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&res_empty[rs]);
-      rs += 2;
-      if (rs >= kResStages) {
-        rs = wg;
-        rphase ^= 1;
-      }
-      uint8_t* buf = my_out + (box & 1) * CHUNK_BYTES;
+      uint8_t* buf = my_out;
       uint8_t* rowp = buf + row * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
             make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
       ptx::fence_proxy_async_smem();
-      if (et == 0) ptx::tma_store_wait_read<0>();
       ptx::named_bar_sync(bar_id, 128);
       if (et == 0) {
         ptx::tma_store_2d(&p.tmD, buf, n0, m0);
         ptx::tma_store_commit();
       }
-      ++box;
     };
 
+    // E1 of the NEXT tile runs before E2 of this one, so that the next tile's second GEMM overlaps this tile's output phase
+    // (G2 of a tile needs both acc2 buffers back for its n2 >= 2 tiles, so E1(next) goes before the LAST TWO E2's.)
     if (first < n_mblk) e1();
+    const int pre = p.num_n2 > 2 ? p.num_n2 - 2 : 0;
     for (int t = first; t < n_mblk; t += step) {
-      for (int n2 = 0; n2 < p.num_n2; ++n2) e2(t, n2);
+      for (int n2 = 0; n2 < pre; ++n2) e2(t, n2);
       if (t + step < n_mblk) e1();
+      for (int n2 = pre; n2 < p.num_n2; ++n2) e2(t, n2);
     }
     if (et == 0) ptx::tma_store_wait_all<0>();
   }
@@ -389,6 +385,8 @@ int launch_t(const BneckParams& p, int grid, cudaStream_t s) {
 
 int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
                const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y) {
+  if (g_option_bneck_halo.load() && g.C == 64 && g.stride == 1 && g.KH == 3 && g.KW == 3 && g.pad_h == 1 && g.pad_w == 1)
+    return bneck_halo_plan(plan, x, g, w2, bias2, w3, bias3, width, residual, y);
   *plan = BneckPlan{};
   OPD_REQUIRE(g.KH == 3 && g.KW == 3 && (g.C == 64 || g.C == 128), "bottleneck tail: 3x3 convolution over 64 or 128 channels (C=%d)", g.C);
   OPD_REQUIRE(width % BLOCK_N2 == 0 && width > 0, "bottleneck tail: width=%d must be a multiple of 128", width);
@@ -410,6 +408,7 @@ int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const
 }
 
 int bneck_launch(const BneckPlan& plan, cudaStream_t stream) {
+  if (plan.halo) return bneck_halo_launch(plan, stream);
   BneckParams p;
   p.tmA = plan.tmA; p.tmB1 = plan.tmB1; p.tmB2 = plan.tmB2; p.tmR = plan.tmR; p.tmD = plan.tmD;
   p.M = plan.M; p.width = plan.width;

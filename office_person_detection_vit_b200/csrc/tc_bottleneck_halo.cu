@@ -1,0 +1,442 @@
+// Fused bottleneck tail, halo variant (3x3 stride 1, MID = 64 channels: ResNet stage 1):
+//     y = relu( conv1x1( relu(conv3x3(x) + b2) ) + b3 + residual )
+// Same pipeline as tc_bottleneck.cu, but the A operand of the 3x3 convolution is NOT nine im2col copies: one output
+// tile is a 16-row x 8-column pixel patch, its 18 x 10 x 64-channel input halo is loaded ONCE by a tiled TMA (zero fill
+// = the convolution's padding) and every filter tap reads it through a shifted shared-memory descriptor
+// (start + (r * 10 + s) * 128 B, 8-pixel groups one patch row = 1280 B apart; the 128-byte swizzle is a function of the
+// absolute shared-memory address, so shifted views stay consistent with what TMA wrote).  L2 -> SM traffic per tile
+// drops from 144 KB (im2col) to 23 KB, which is what bounded the im2col version (profiles/README.md).
+// Output and residual tiles are the same 16 x 8 patches, moved by 4D TMA boxes [64 ch, 8, 16, 1].
+//
+// Warps: 0 TMA producer (patches + W2 / W3 tiles), 1 MMA issuer + TMEM owner, 2 residual producer,
+//        4-11 epilogue (two warpgroups splitting the columns).
+#include <algorithm>
+
+#include "opd_common.h"
+#include "sm100_ptx.cuh"
+#include "tc_gemm.h"
+
+namespace opd {
+namespace {
+
+constexpr int MID = 64;
+constexpr int BLOCK_M = 128, BLOCK_N2 = 128, UMMA_K = 16;
+constexpr int TILE_W = 8, TILE_H = 16, PATCH_W = TILE_W + 2, PATCH_H = TILE_H + 2;
+constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 128;   // 23040
+constexpr int PATCH_SLOT = 24576;
+constexpr int CHUNK_BYTES = BLOCK_M * 64 * 2;          // 16 KB: one [128 x 64] bf16 box
+constexpr int kPatchStages = 2, kBStages = 3, kResStages = 4;   // residual: two slots per epilogue warpgroup
+constexpr int kThreads = 384;
+constexpr int kSmemBytes = kPatchStages * PATCH_SLOT + kBStages * CHUNK_BYTES + 2 * CHUNK_BYTES /*A2 x2*/ + 2 * CHUNK_BYTES /*staging*/ +
+                           kResStages * CHUNK_BYTES + 2048;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+constexpr int kTmemCols = 512;   // acc1 2 x 64 + acc2 2 x 128
+
+struct HaloParams {
+  CUtensorMap tmA, tmB1, tmB2, tmR, tmD;
+  int tiles_x, tiles_y, num_tiles, num_n2;
+  const float* bias2;
+  const float* bias3;
+};
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// K-major, 128-byte swizzle, explicit stride between 8-row groups
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid_constant__ HaloParams p) {
+  constexpr uint32_t kIdesc1 = ptx::umma_idesc_bf16(BLOCK_M, MID);
+  constexpr uint32_t kIdesc2 = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N2);
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_patch = smem;                                      // [kPatchStages] halo patches
+  uint8_t* smem_b = smem_patch + kPatchStages * PATCH_SLOT;        // [kBStages] W2 tap tiles (8 KB used) / W3 tiles (16 KB)
+  uint8_t* smem_a2 = smem_b + kBStages * CHUNK_BYTES;              // A operand of the second GEMM, double buffered
+  uint8_t* smem_out = smem_a2 + 2 * CHUNK_BYTES;                   // one staging box per epilogue warpgroup
+  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;                  // two residual slots per epilogue warpgroup
+  float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [64]
+  float* s_bias3 = s_bias2 + 64;                                                    // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 128);
+  uint64_t* patch_full = bars;          // [kPatchStages]
+  uint64_t* patch_empty = bars + 4;     // [kPatchStages]
+  uint64_t* b_full = bars + 8;          // [kBStages]
+  uint64_t* b_empty = bars + 12;        // [kBStages]
+  uint64_t* acc1_full = bars + 16;      // [2]
+  uint64_t* acc1_empty = bars + 18;     // [2]
+  uint64_t* acc2_full = bars + 20;      // [2]
+  uint64_t* acc2_empty = bars + 22;     // [2]
+  uint64_t* a2_ready = bars + 24;       // [2]
+  uint64_t* a2_free = bars + 26;        // [2]
+  uint64_t* res_full = bars + 28;       // [4]
+  uint64_t* res_empty = bars + 32;      // [4]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 36);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmB1);
+    ptx::prefetch_tmap(&p.tmB2);
+    ptx::prefetch_tmap(&p.tmD);
+    for (int i = 0; i < kPatchStages; ++i) {
+      ptx::mbar_init(&patch_full[i], 1);
+      ptx::mbar_init(&patch_empty[i], 1);
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      ptx::mbar_init(&b_full[i], 1);
+      ptx::mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc1_full[i], 1);
+      ptx::mbar_init(&acc1_empty[i], 256);
+      ptx::mbar_init(&acc2_full[i], 1);
+      ptx::mbar_init(&acc2_empty[i], 256);
+    }
+    for (int i = 0; i < kResStages; ++i) {
+      ptx::mbar_init(&res_full[i], 1);
+      ptx::mbar_init(&res_empty[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&a2_ready[i], 256);
+      ptx::mbar_init(&a2_free[i], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_acc1 = tmem_base;             // 2 x 64 columns
+  const uint32_t tmem_acc2 = tmem_base + 2 * MID;   // 2 x 128 columns
+
+  const int first = blockIdx.x, step = gridDim.x, n_tiles = p.num_tiles;
+  auto tile_origin = [&](int t, int& b, int& y0, int& x0) {
+    const int tx = t % p.tiles_x;
+    const int r = t / p.tiles_x;
+    x0 = tx * TILE_W;
+    y0 = (r % p.tiles_y) * TILE_H;
+    b = r / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int ps = 0, bs = 0;
+      uint32_t pphase = 0, bphase = 0;
+      auto load_g1 = [&](int t) {
+        int b, y0, x0;
+        tile_origin(t, b, y0, x0);
+        ptx::mbar_wait(&patch_empty[ps], pphase ^ 1);
+        ptx::mbar_expect_tx(&patch_full[ps], PATCH_BYTES);
+        tma_load_4d(&p.tmA, &patch_full[ps], smem_patch + ps * PATCH_SLOT, 0, x0 - 1, y0 - 1, b);
+        if (++ps == kPatchStages) {
+          ps = 0;
+          pphase ^= 1;
+        }
+        for (int tap = 0; tap < 9; tap += 2) {   // two 8 KB tap tiles of W2 per 16 KB slot (the last slot holds one)
+          const int n_taps = tap + 1 < 9 ? 2 : 1;
+          ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
+          ptx::mbar_expect_tx(&b_full[bs], n_taps * MID * 128);
+          for (int j = 0; j < n_taps; ++j)
+            ptx::tma_load_2d(&p.tmB1, &b_full[bs], smem_b + bs * CHUNK_BYTES + j * (MID * 128), (tap + j) * 64, 0);
+          if (++bs == kBStages) {
+            bs = 0;
+            bphase ^= 1;
+          }
+        }
+      };
+      auto load_g2 = [&]() {
+        for (int n2 = 0; n2 < p.num_n2; ++n2) {
+          ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
+          ptx::mbar_expect_tx(&b_full[bs], CHUNK_BYTES);
+          ptx::tma_load_2d(&p.tmB2, &b_full[bs], smem_b + bs * CHUNK_BYTES, 0, n2 * BLOCK_N2);
+          if (++bs == kBStages) {
+            bs = 0;
+            bphase ^= 1;
+          }
+        }
+      };
+      if (first < n_tiles) load_g1(first);
+      for (int t = first; t < n_tiles; t += step) {
+        if (t + step < n_tiles) load_g1(t + step);
+        load_g2();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      int ps = 0, bs = 0, a1 = 0, a2 = 0, ab = 0;
+      uint32_t pphase = 0, bphase = 0, a1_phase = 0, a2_phase = 0, ready_phase = 0;
+      auto next_b = [&]() {
+        if (++bs == kBStages) {
+          bs = 0;
+          bphase ^= 1;
+        }
+      };
+      auto g1 = [&]() {
+        ptx::mbar_wait(&acc1_empty[a1], a1_phase ^ 1);
+        ptx::mbar_wait(&patch_full[ps], pphase);
+        ptx::tc_fence_after_sync();
+        const uint32_t d = tmem_acc1 + a1 * MID;
+        const uint32_t patch = ptx::smem_u32(smem_patch + ps * PATCH_SLOT);
+        for (int tap0 = 0; tap0 < 9; tap0 += 2) {
+          ptx::mbar_wait(&b_full[bs], bphase);
+          ptx::tc_fence_after_sync();
+          for (int tap = tap0; tap < tap0 + 2 && tap < 9; ++tap) {
+            const int r = tap / 3, s = tap - r * 3;
+            const uint32_t a_addr = patch + (r * PATCH_W + s) * 128;
+            const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES + (tap - tap0) * (MID * 128));
+#pragma unroll
+            for (int k = 0; k < 64 / UMMA_K; ++k)
+              ptx::umma_bf16_ss(d, desc_sw128(a_addr + k * 32, PATCH_W * 128), desc_sw128(b_addr + k * 32, 1024), kIdesc1,
+                                (tap | k) != 0);
+          }
+          ptx::umma_commit(&b_empty[bs]);
+          next_b();
+        }
+        ptx::umma_commit(&patch_empty[ps]);
+        ptx::umma_commit(&acc1_full[a1]);
+        if (++ps == kPatchStages) {
+          ps = 0;
+          pphase ^= 1;
+        }
+        if (++a1 == 2) {
+          a1 = 0;
+          a1_phase ^= 1;
+        }
+      };
+      auto g2 = [&]() {
+        ptx::mbar_wait(&a2_ready[ab], ready_phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = ptx::smem_u32(smem_a2 + ab * CHUNK_BYTES);
+        for (int n2 = 0; n2 < p.num_n2; ++n2) {
+          ptx::mbar_wait(&acc2_empty[a2], a2_phase ^ 1);
+          ptx::mbar_wait(&b_full[bs], bphase);
+          ptx::tc_fence_after_sync();
+          const uint32_t d = tmem_acc2 + a2 * BLOCK_N2;
+          const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES);
+#pragma unroll
+          for (int k = 0; k < 64 / UMMA_K; ++k)
+            ptx::umma_bf16_ss(d, desc_sw128(a_addr + k * 32, 1024), desc_sw128(b_addr + k * 32, 1024), kIdesc2, k != 0);
+          ptx::umma_commit(&b_empty[bs]);
+          next_b();
+          ptx::umma_commit(&acc2_full[a2]);
+          if (++a2 == 2) {
+            a2 = 0;
+            a2_phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&a2_free[ab]);
+        if (++ab == 2) {
+          ab = 0;
+          ready_phase ^= 1;
+        }
+      };
+      if (first < n_tiles) g1();
+      for (int t = first; t < n_tiles; t += step) {
+        if (t + step < n_tiles) g1();
+        g2();
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================== residual TMA producer =====================================
+    if (lane == 0) {
+      ptx::prefetch_tmap(&p.tmR);
+      uint32_t k = 0;   // chunk counter per warpgroup: slot = wg * 2 + (k & 1), parity = (k >> 1) & 1
+      for (int t = first; t < n_tiles; t += step) {
+        int b, y0, x0;
+        tile_origin(t, b, y0, x0);
+        for (int n2 = 0; n2 < p.num_n2; ++n2, ++k) {
+          for (int c = 0; c < 2; ++c) {   // chunk c of the n2 tile belongs to epilogue warpgroup c
+            const int slot = c * 2 + (k & 1);
+            ptx::mbar_wait(&res_empty[slot], ((k >> 1) & 1) ^ 1);
+            ptx::mbar_expect_tx(&res_full[slot], CHUNK_BYTES);
+            tma_load_4d(&p.tmR, &res_full[slot], smem_res + slot * CHUNK_BYTES, n2 * BLOCK_N2 + c * 64, x0, y0, b);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================ epilogue: two warpgroups (warps 4-7, 8-11) ============================
+    const int wg = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128 - wg * 128;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;           // tile row = pixel (row / 8, row % 8) = TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int bar_id = 1 + wg;
+    if (threadIdx.x - 128 < MID) s_bias2[threadIdx.x - 128] = p.bias2[threadIdx.x - 128];
+    ptx::named_bar_sync(3, 256);
+
+    int a1 = 0, a2 = 0, ab = 0;
+    uint32_t a1_phase = 0, a2_phase = 0, rk = 0, free_phase = 0;
+    float* my_bias3 = s_bias3 + wg * 64;
+    uint8_t* my_out = smem_out + wg * CHUNK_BYTES;
+
+    auto e1 = [&]() {
+      ptx::mbar_wait(&acc1_full[a1], a1_phase);
+      ptx::mbar_wait(&a2_free[ab], free_phase ^ 1);   // the second GEMM two tiles back no longer reads this A2 buffer
+      ptx::tc_fence_after_sync();
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_acc1 + lane_addr + a1 * MID + wg * 32, v);   // warpgroup g converts columns [32g, 32g+32)
+      ptx::tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = fmaxf(__uint_as_float(v[2 * j]) + s_bias2[wg * 32 + 2 * j], 0.f);
+        const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias2[wg * 32 + 2 * j + 1], 0.f);
+        packed[j] = ptx::pack_bf16(a, b);
+      }
+      uint8_t* rowp = smem_a2 + ab * CHUNK_BYTES + row * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(rowp + (((wg * 4 + j) ^ (row & 7)) << 4)) =
+            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&acc1_empty[a1]);
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&a2_ready[ab]);
+      if (++ab == 2) {
+        ab = 0;
+        free_phase ^= 1;
+      }
+      if (++a1 == 2) {
+        a1 = 0;
+        a1_phase ^= 1;
+      }
+    };
+
+    auto e2 = [&](int b, int y0, int x0, int n2) {
+      const int n0 = n2 * BLOCK_N2 + wg * 64;
+      if (et < 64) my_bias3[et] = p.bias3[n0 + et];
+      if (et == 0) ptx::tma_store_wait_read<0>();     // my staging box: the previous store has finished reading it
+      ptx::named_bar_sync(bar_id, 128);
+      ptx::mbar_wait(&acc2_full[a2], a2_phase);
+      ptx::tc_fence_after_sync();
+      const uint32_t t_acc = tmem_acc2 + lane_addr + a2 * BLOCK_N2 + wg * 64;
+      uint32_t packed[32];
+      const int rslot = wg * 2 + (rk & 1);
+      ptx::mbar_wait(&res_full[rslot], (rk >> 1) & 1);
+      ++rk;
+      const uint8_t* rrow = smem_res + rslot * CHUNK_BYTES + row * 128;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_acc + h * 32, v);
+        uint4 rr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rrow + (((h * 4 + j) ^ (row & 7)) << 4));
+        ptx::tmem_ld_wait();
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaxf(__uint_as_float(v[2 * j]) + my_bias3[h * 32 + 2 * j] + ptx::bf16_lo(rw[j]), 0.f);
+          const float bb = fmaxf(__uint_as_float(v[2 * j + 1]) + my_bias3[h * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]), 0.f);
+          packed[h * 16 + j] = ptx::pack_bf16(a, bb);
+        }
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&acc2_empty[a2]);
+      if (++a2 == 2) {
+        a2 = 0;
+        a2_phase ^= 1;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&res_empty[rslot]);
+      uint8_t* rowp = my_out + row * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(bar_id, 128);
+      if (et == 0) {
+        tma_store_4d(&p.tmD, my_out, n0, x0, y0, b);
+        ptx::tma_store_commit();
+      }
+    };
+
+    // E1 of the NEXT tile runs before E2 of this one: the second GEMM of the next tile (which needs A2) then overlaps
+    // this tile's HBM-bound output phase instead of stalling the epilogue warps
+    if (first < n_tiles) e1();
+    for (int t = first; t < n_tiles; t += step) {
+      int b, y0, x0;
+      tile_origin(t, b, y0, x0);
+      const int pre = p.num_n2 > 2 ? p.num_n2 - 2 : 0;   // G2 needs both acc2 buffers back for its n2 >= 2 tiles
+      for (int n2 = 0; n2 < pre; ++n2) e2(b, y0, x0, n2);
+      if (t + step < n_tiles) e1();
+      for (int n2 = pre; n2 < p.num_n2; ++n2) e2(b, y0, x0, n2);
+    }
+    if (et == 0) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+}  // namespace
+
+int bneck_halo_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
+                    const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y) {
+  *plan = BneckPlan{};
+  OPD_REQUIRE(g.KH == 3 && g.KW == 3 && g.C == MID && g.stride == 1 && g.pad_h == 1 && g.pad_w == 1 && g.P == g.H && g.Q == g.W,
+              "bottleneck tail (halo): 3x3 / stride 1 / pad 1 over 64 channels only");
+  OPD_REQUIRE(width % BLOCK_N2 == 0 && width > 0, "bottleneck tail (halo): width=%d must be a multiple of 128", width);
+  OPD_REQUIRE(bias2 && bias3 && residual && y && x && w2 && w3, "bottleneck tail (halo): NULL argument");
+  plan->halo = 1;
+  plan->M = g.B * g.P * g.Q;
+  plan->mid = g.C;
+  plan->width = width;
+  plan->g = g;
+  plan->bias2 = bias2;
+  plan->bias3 = bias3;
+  if (int rc = make_tmap_nhwc_patch(&plan->tmA, x, g.B, g.H, g.W, MID, PATCH_W, PATCH_H)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB1, w2, MID, 9 * MID, 9 * MID, MID)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB2, w3, width, MID, MID, BLOCK_N2)) return rc;
+  if (int rc = make_tmap_nhwc_patch(&plan->tmR, residual, g.B, g.P, g.Q, width, TILE_W, TILE_H)) return rc;
+  if (int rc = make_tmap_nhwc_patch(&plan->tmD, y, g.B, g.P, g.Q, width, TILE_W, TILE_H)) return rc;
+  const int tiles = g.B * ((g.P + TILE_H - 1) / TILE_H) * ((g.Q + TILE_W - 1) / TILE_W);
+  plan->grid = std::min(tiles, sm_count());
+  return OPD_OK;
+}
+
+int bneck_halo_launch(const BneckPlan& plan, cudaStream_t stream) {
+  HaloParams p;
+  p.tmA = plan.tmA; p.tmB1 = plan.tmB1; p.tmB2 = plan.tmB2; p.tmR = plan.tmR; p.tmD = plan.tmD;
+  p.tiles_x = (plan.g.Q + TILE_W - 1) / TILE_W;
+  p.tiles_y = (plan.g.P + TILE_H - 1) / TILE_H;
+  p.num_tiles = plan.g.B * p.tiles_x * p.tiles_y;
+  p.num_n2 = plan.width / BLOCK_N2;
+  p.bias2 = plan.bias2;
+  p.bias3 = plan.bias3;
+  static bool configured = false;
+  if (!configured) {
+    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  tc_bneck_halo_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+}  // namespace opd

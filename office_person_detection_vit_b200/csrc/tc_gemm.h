@@ -64,8 +64,12 @@ int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g);
 
 // Fused bottleneck tail (tc_bottleneck.cu): y = relu(conv1x1(relu(conv3x3(x, stride) + b2)) + b3 + residual).
 // x [B,H,W,MID] NHWC, w2 [MID,3,3,MID], w3 [WIDTH,MID], residual / y [B,P,Q,WIDTH]; MID in {64, 128}, WIDTH % 128 == 0.
+// 4D tiled map over an NHWC bf16 tensor: box = [64 channels, box_w, box_h, 1 image], 128-byte swizzle, zero fill
+int make_tmap_nhwc_patch(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h);
+
 struct BneckPlan {
   CUtensorMap tmA, tmB1, tmB2, tmR, tmD;
+  int halo;            // 1: stride-1, MID = 64 variant (tc_bottleneck_halo.cu): 16 x 8 pixel tiles, A = one halo patch per tile
   int M, mid, width;
   ConvGeom g;
   const float* bias2;
@@ -75,5 +79,8 @@ struct BneckPlan {
 int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
                const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y);
 int bneck_launch(const BneckPlan& plan, cudaStream_t stream);
+int bneck_halo_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
+                    const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y);
+int bneck_halo_launch(const BneckPlan& plan, cudaStream_t stream);
 
 }  // namespace opd

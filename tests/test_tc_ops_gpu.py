@@ -118,11 +118,17 @@ def test_attention(T, B, Lq, Lk):
     (3, 40, 67, 128, 512, 1),
     (2, 51, 84, 128, 512, 2),
     (1, 200, 334, 64, 256, 1),
+    (3, 33, 47, 64, 256, 1),
     (4, 100, 167, 128, 512, 1),
 ])
-def test_fused_bottleneck_tail(T, B, H, W, mid, width, stride):
-    """conv3x3 + ReLU -> (bf16 in shared memory) -> conv1x1 + bias + residual + ReLU in one kernel."""
+@pytest.mark.parametrize("halo", [1, 0])
+def test_fused_bottleneck_tail(T, B, H, W, mid, width, stride, halo):
+    """conv3x3 + ReLU -> (bf16 in shared memory) -> conv1x1 + bias + residual + ReLU in one kernel; halo = 1 uses the
+    halo-patch variant where it applies (64 channels, stride 1), halo = 0 the im2col variant everywhere."""
+    from office_person_detection_vit_b200 import _lib
     from office_person_detection_vit_b200.detection import ops
+
+    _lib.check(_lib.lib().opd_set_option(b"bneck_halo", halo))
 
     torch = T
     x = _rand(torch, B, H, W, mid, seed=20)
@@ -133,6 +139,9 @@ def test_fused_bottleneck_tail(T, B, H, W, mid, width, stride):
     m = m.relu().to(torch.bfloat16).float().permute(0, 2, 3, 1)          # the mid activation is rounded to bf16
     res = _rand(torch, *m.shape[:3], width, seed=23)
     ref = (m @ w3.float().T + b3 + res.float()).relu()
-    y = ops.bottleneck_tail(x, w2, b2, w3, b3, res, stride=stride)
+    try:
+        y = ops.bottleneck_tail(x, w2, b2, w3, b3, res, stride=stride)
+    finally:
+        _lib.lib().opd_set_option(b"bneck_halo", 1)
     assert y.shape == ref.shape
     _close(torch, y, ref, f"bottleneck tail {B}x{H}x{W} mid {mid} width {width} s{stride}")
