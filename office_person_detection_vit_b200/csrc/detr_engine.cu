@@ -88,7 +88,9 @@ struct opd_detr {
   int fuse_tail = 1;   // 0: run the 3x3 and the 1x1 expansion of stages 1-2 as separate kernels (A/B comparison)
   int do_resize = 1;   // 0: frames are fed at their own size (DetrImageProcessor(do_resize=False))
   std::vector<void*> allocs;
-  opd::ConvW stem;   // packed as a 4x1 convolution over the 64-channel space-to-depth layout
+  opd::ConvW stem;   // packed as a 4x1 convolution over the 64-channel space-to-depth layout (im2col fallback path)
+  opd::bf16* stem_taps = nullptr;   // [64, 16 taps x 16 lanes]: 4x4 convolution over the 16-lane space-to-depth tensor
+  int stem_halo = 1;
   std::vector<opd::BlockW> blocks;
   opd::LinW input_proj;
   opd::EncW enc[opd::kEnc];
@@ -205,6 +207,17 @@ struct Loader {
           }
     c.w = upload(packed);
     c.bias = upload(shift);
+    // tap layout of stem_conv.cu: column (kh4 * 4 + kw4) * 16 + (dy * 2 + dx) * 3 + ci
+    std::vector<bf16> taps((size_t)64 * 256, __float2bfloat16(0.f));
+    for (int n = 0; n < 64; ++n)
+      for (int ci = 0; ci < 3; ++ci)
+        for (int r = 0; r < 7; ++r)
+          for (int s = 0; s < 7; ++s) {
+            const int kh4 = (r + 1) / 2, dy = (r + 1) & 1, kw4 = (s + 1) / 2, dx = (s + 1) & 1;
+            taps[(size_t)n * 256 + (kh4 * 4 + kw4) * 16 + (dy * 2 + dx) * 3 + ci] =
+                __float2bfloat16(wf[(((size_t)n * 3 + ci) * 7 + r) * 7 + s]);
+          }
+    m->stem_taps = upload(taps);
     return c;
   }
 
@@ -504,15 +517,25 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
     }
   }
 
-  // ---- K1 preprocess -> X2 [B, Hs, Ws, 64] ----
-  bf16* x2 = static_cast<bf16*>(big_slot(0, act_bytes(Ms, 64)));
+  // ---- K1 preprocess: -> S [B, Hs, Ws, 16] (stem_conv.cu) or, on the im2col fallback path, X2 [B, Hs, Ws, 64] ----
+  const bool stem_halo = m->stem_halo != 0;
+  bf16* x2 = static_cast<bf16*>(big_slot(0, act_bytes(Ms, stem_halo ? 16 : 64)));
   if (!dry) {
-    add(OPD_STEP_ELEMENTWISE, "preprocess", 0.0, (double)B * sh.Hin * sh.Win * 3 + (double)act_bytes(Ms, 64),
-        [m, B, sh, x2, resized](cudaStream_t s) {
-          return resized ? launch_preprocess(resized, B, sh.Hin, sh.Win, 0, x2, s)
-                         : launch_preprocess(m->cur_frames, B, sh.Hin, sh.Win, m->cur_bgr, x2, s);
-        });
-    taps["x2"] = {x2, Ms, 64, 0};
+    const uint8_t* fixed_src = resized;
+    if (stem_halo) {
+      add(OPD_STEP_ELEMENTWISE, "preprocess", 0.0, (double)B * sh.Hin * sh.Win * 3 + (double)act_bytes(Ms, 16),
+          [m, B, sh, x2, fixed_src](cudaStream_t s) {
+            return fixed_src ? launch_preprocess_s2d(fixed_src, B, sh.Hin, sh.Win, 0, x2, s)
+                             : launch_preprocess_s2d(m->cur_frames, B, sh.Hin, sh.Win, m->cur_bgr, x2, s);
+          });
+    } else {
+      add(OPD_STEP_ELEMENTWISE, "preprocess", 0.0, (double)B * sh.Hin * sh.Win * 3 + (double)act_bytes(Ms, 64),
+          [m, B, sh, x2, fixed_src](cudaStream_t s) {
+            return fixed_src ? launch_preprocess(fixed_src, B, sh.Hin, sh.Win, 0, x2, s)
+                             : launch_preprocess(m->cur_frames, B, sh.Hin, sh.Win, m->cur_bgr, x2, s);
+          });
+    }
+    taps["x2"] = {x2, Ms, stem_halo ? 16 : 64, 0};
   }
 
   std::string cur_name = "gemm";
@@ -544,11 +567,18 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   // ---- K2 stem: 4x1 convolution over X2, pad 2 rows above / 1 below ----
   bf16* stem_out = static_cast<bf16*>(big_slot(1, act_bytes(Ms, 64)));
   if (!dry) {
-    GemmPlan gp;
-    cur_name = "stem";
-    ConvGeom g{B, sh.Hs, sh.Ws, 64, 4, 1, 1, 2, 0, sh.Hs, sh.Ws};
-    if (int rc = gemm_plan_conv(&gp, x2, g, m->stem.w, stem_out, 64, EPI_BIAS_RELU, m->stem.bias, nullptr)) return rc;
-    add_gemm(gp);
+    if (stem_halo) {
+      StemPlan sp;
+      if (int rc = stem_plan(&sp, x2, B, sh.Hs, sh.Ws, m->stem_taps, m->stem.bias, stem_out)) return rc;
+      add(OPD_STEP_CONV, "stem", 2.0 * Ms * 64 * 147, (double)act_bytes(Ms, 16) + (double)act_bytes(Ms, 64),
+          [sp](cudaStream_t s) { return stem_launch(sp, s); });
+    } else {
+      GemmPlan gp;
+      cur_name = "stem";
+      ConvGeom g{B, sh.Hs, sh.Ws, 64, 4, 1, 1, 2, 0, sh.Hs, sh.Ws};
+      if (int rc = gemm_plan_conv(&gp, x2, g, m->stem.w, stem_out, 64, EPI_BIAS_RELU, m->stem.bias, nullptr)) return rc;
+      add_gemm(gp);
+    }
     taps["stem"] = {stem_out, Ms, 64, 0};
   }
   // ---- K3 max pooling ----
@@ -751,7 +781,8 @@ int opd_detr_set_debug(opd_detr* m, int32_t debug) {
 
 int opd_detr_set_fusion(opd_detr* m, int32_t fuse_bottleneck_tail) {
   OPD_REQUIRE(m, "opd_detr_set_fusion: NULL handle");
-  m->fuse_tail = fuse_bottleneck_tail;
+  m->fuse_tail = fuse_bottleneck_tail & 1;
+  m->stem_halo = (fuse_bottleneck_tail & 2) ? 0 : 1;   // bit 1 set: im2col stem over the 64-lane layout (A/B comparison)
   m->plan = opd::Plan{};
   return OPD_OK;
 }

@@ -12,6 +12,8 @@ namespace opd {
 //   X2[b, y, x, kw*16 + (dy*2+dx)*3 + c] = norm(src[b, 2y+dy, 2(x+kw-2)+dx, c])   (0 outside the image, 0 for the 4 pad lanes)
 // so that the 7x7/s2 stem convolution is a 4x1 convolution over 64 channels (K = 256) on the tensor cores.
 int launch_preprocess(const uint8_t* src, int B, int Hs, int Ws, int src_is_bgr, __nv_bfloat16* x2, cudaStream_t s);
+// K1 (stem_conv.cu): uint8 frames -> normalised bf16 space-to-depth tensor S[B, (Hs+1)/2, (Ws+1)/2, 16]
+int launch_preprocess_s2d(const uint8_t* src, int B, int Hs, int Ws, int src_is_bgr, __nv_bfloat16* s2d, cudaStream_t s);
 // uint8 bilinear resize with antialias (ATen's separable uint8 kernel: horizontal pass, then vertical pass,
 // fixed-point weights); src [B,H0,W0,3] (BGR or RGB) -> dst [B,H1,W1,3] RGB
 int launch_resize_u8(const uint8_t* src, int B, int H0, int W0, int src_is_bgr, uint8_t* tmp, uint8_t* dst, int H1,

@@ -1,0 +1,317 @@
+// K1 + K2: preprocessing and the ResNet stem (7x7 / stride 2 / pad 3 convolution, 3 -> 64, + frozen BN + ReLU) on the
+// tensor cores without an im2col buffer.
+//
+//   K1  s2d_preprocess_kernel: uint8 frame -> normalised bf16 "space-to-depth" tensor S[B, H/2, W/2, 16]:
+//       channel (dy*2+dx)*3 + c = pixel (2y+dy, 2x+dx), colour c (12 real channels, 4 zero lanes; 32 B per pixel).
+//       (BGR->RGB and (u8 - 255*mean) / (255*std): transformers image_processing_backends.py:308-331.)
+//   K2  stem_kernel: in S space the 7x7/s2 convolution is a 4x4 convolution with pad (2 before, 1 after) and
+//       K = 16 taps x 16 channels.  One output tile = 16 rows x 8 columns; its 19 x 11 pixel halo (6.7 KB) is loaded ONCE
+//       by a tiled TMA (32-byte swizzle, zero fill = padding) and each of the 16 taps is ONE tcgen05.mma (M 128, N 64,
+//       K 16) whose A descriptor points into the patch at (r * 11 + s) * 32 B with 8-pixel groups one patch row (352 B)
+//       apart.  The 32 KB of weights stay resident in shared memory.  Two epilogue warpgroups alternate tiles:
+//       TMEM -> +shift, ReLU -> bf16 -> swizzled staging -> 4D TMA store into the NHWC stem output.
+// Arithmetic replaced: transformers models/resnet/modeling_resnet.py:57-88 (ResNetEmbeddings) with DetrFrozenBatchNorm2d
+// (models/detr/modeling_detr.py:185-222) folded into the weights.
+#include <algorithm>
+
+#include "detr_kernels.h"
+#include "opd_common.h"
+#include "sm100_ptx.cuh"
+#include "tc_gemm.h"
+
+namespace opd {
+namespace {
+
+constexpr int TILE_W = 8, TILE_H = 16, PATCH_W = TILE_W + 3, PATCH_H = TILE_H + 3;
+constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 32;   // 6688
+constexpr int PATCH_SLOT = 7168;
+constexpr int kPatchStages = 8;
+constexpr int W_TAP_BYTES = 64 * 32;                   // one tap: 64 output channels x 16 input lanes
+constexpr int OUT_BYTES = 128 * 128;                   // staging box: 128 pixels x 64 channels bf16
+constexpr int kAccStages = 4;
+constexpr int kThreads = 384;
+constexpr int kSmemBytes = 16 * W_TAP_BYTES + kPatchStages * PATCH_SLOT + 4 * OUT_BYTES + 1024;
+
+struct StemParams {
+  CUtensorMap tmS, tmW, tmD;
+  int tiles_x, tiles_y, num_tiles;
+  const float* bias;
+};
+
+__global__ void s2d_preprocess_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, int bgr,
+                                      __nv_bfloat16* __restrict__ S, int H2, int W2) {
+  const float mean[3] = {0.485f * 255.0f, 0.456f * 255.0f, 0.406f * 255.0f};
+  const float stdv[3] = {0.229f * 255.0f, 0.224f * 255.0f, 0.225f * 255.0f};
+  const long long total = (long long)B * H2 * W2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W2);
+    long long r = i / W2;
+    const int y = (int)(r % H2);
+    const int b = (int)(r / H2);
+    float v[12];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = 2 * y + dy, ix = 2 * x + dx;
+        const bool ok = iy < Hs && ix < Ws;
+        const uint8_t* px = src + (((long long)b * Hs + (ok ? iy : 0)) * Ws + (ok ? ix : 0)) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float u = (float)px[bgr ? 2 - c : c];
+          v[(dy * 2 + dx) * 3 + c] = ok ? (u - mean[c]) / stdv[c] : 0.f;
+        }
+      }
+    uint4 o0, o1;
+    o0.x = ptx::pack_bf16(v[0], v[1]); o0.y = ptx::pack_bf16(v[2], v[3]); o0.z = ptx::pack_bf16(v[4], v[5]); o0.w = ptx::pack_bf16(v[6], v[7]);
+    o1.x = ptx::pack_bf16(v[8], v[9]); o1.y = ptx::pack_bf16(v[10], v[11]); o1.z = 0u; o1.w = 0u;
+    uint4* dst = reinterpret_cast<uint4*>(S + i * 16);
+    dst[0] = o0;
+    dst[1] = o1;
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// K-major operand with 32-byte rows and the 32-byte swizzle; sbo = byte distance between 8-row groups
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;   // SWIZZLE_32B
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant__ StemParams p) {
+  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(128, 64);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_w = smem;                                   // 16 taps x [64 x 32 B]
+  uint8_t* smem_patch = smem_w + 16 * W_TAP_BYTES;          // [kPatchStages]
+  uint8_t* smem_out = smem_patch + kPatchStages * PATCH_SLOT;   // 2 staging boxes per epilogue warpgroup
+  float* s_bias = reinterpret_cast<float*>(smem_out + 4 * OUT_BYTES);   // [64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
+  uint64_t* patch_full = bars;           // [8]
+  uint64_t* patch_empty = bars + 8;      // [8]
+  uint64_t* acc_full = bars + 16;        // [4]
+  uint64_t* acc_empty = bars + 20;       // [4]
+  uint64_t* w_full = bars + 24;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 25);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmS);
+    ptx::prefetch_tmap(&p.tmW);
+    ptx::prefetch_tmap(&p.tmD);
+    for (int i = 0; i < kPatchStages; ++i) {
+      ptx::mbar_init(&patch_full[i], 1);
+      ptx::mbar_init(&patch_empty[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_empty[i], 128);
+    }
+    ptx::mbar_init(w_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<256>(tmem_ptr);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int first = blockIdx.x, step = gridDim.x, n_tiles = p.num_tiles;
+  auto tile_origin = [&](int t, int& b, int& y0, int& x0) {
+    const int tx = t % p.tiles_x;
+    const int r = t / p.tiles_x;
+    x0 = tx * TILE_W;
+    y0 = (r % p.tiles_y) * TILE_H;
+    b = r / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(w_full, 16 * W_TAP_BYTES);
+      for (int tap = 0; tap < 16; ++tap) ptx::tma_load_2d(&p.tmW, w_full, smem_w + tap * W_TAP_BYTES, tap * 16, 0);
+      int ps = 0;
+      uint32_t pphase = 0;
+      for (int t = first; t < n_tiles; t += step) {
+        int b, y0, x0;
+        tile_origin(t, b, y0, x0);
+        ptx::mbar_wait(&patch_empty[ps], pphase ^ 1);
+        ptx::mbar_expect_tx(&patch_full[ps], PATCH_BYTES);
+        tma_load_4d(&p.tmS, &patch_full[ps], smem_patch + ps * PATCH_SLOT, 0, x0 - 2, y0 - 2, b);
+        if (++ps == kPatchStages) {
+          ps = 0;
+          pphase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      ptx::mbar_wait(w_full, 0);
+      int ps = 0, as = 0;
+      uint32_t pphase = 0, aphase = 0;
+      const uint32_t w_addr = ptx::smem_u32(smem_w);
+      for (int t = first; t < n_tiles; t += step) {
+        ptx::mbar_wait(&acc_empty[as], aphase ^ 1);
+        ptx::mbar_wait(&patch_full[ps], pphase);
+        ptx::tc_fence_after_sync();
+        const uint32_t d = tmem_base + as * 64;
+        const uint32_t patch = ptx::smem_u32(smem_patch + ps * PATCH_SLOT);
+#pragma unroll
+        for (int tap = 0; tap < 16; ++tap) {
+          const int r = tap >> 2, s = tap & 3;
+          ptx::umma_bf16_ss(d, desc_sw32(patch + (r * PATCH_W + s) * 32, PATCH_W * 32), desc_sw32(w_addr + tap * W_TAP_BYTES, 256),
+                            kIdesc, tap != 0);
+        }
+        ptx::umma_commit(&patch_empty[ps]);
+        ptx::umma_commit(&acc_full[as]);
+        if (++ps == kPatchStages) {
+          ps = 0;
+          pphase ^= 1;
+        }
+        if (++as == kAccStages) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // two epilogue warpgroups; warpgroup g handles this CTA's tiles number g, g + 2, ... (accumulator stages g, g + 2)
+    const int wg = (warp - 4) >> 2;
+    const int et = threadIdx.x - 128 - wg * 128;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    if (threadIdx.x - 128 < 64) s_bias[threadIdx.x - 128] = p.bias[threadIdx.x - 128];
+    ptx::named_bar_sync(3, 256);
+    uint8_t* my_out = smem_out + wg * 2 * OUT_BYTES;
+    uint32_t k = 0;   // tiles processed by this warpgroup: accumulator stage = wg + 2 * (k & 1), parity = (k >> 1) & 1
+    int n = 0;
+    for (int t = first; t < n_tiles; t += step, ++n) {
+      if ((n & 1) != wg) continue;
+      int b, y0, x0;
+      tile_origin(t, b, y0, x0);
+      const int as = wg + 2 * (k & 1);
+      ptx::mbar_wait(&acc_full[as], (k >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      uint32_t packed[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + lane_addr + as * 64 + h * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          packed[h * 16 + j] = ptx::pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + s_bias[h * 32 + 2 * j], 0.f),
+                                              fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias[h * 32 + 2 * j + 1], 0.f));
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&acc_empty[as]);
+      uint8_t* buf = my_out + (k & 1) * OUT_BYTES;
+      if (et == 0) ptx::tma_store_wait_read<1>();   // the store issued two tiles ago (same buffer) has read its data
+      ptx::named_bar_sync(1 + wg, 128);
+      uint8_t* rowp = buf + row * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(1 + wg, 128);
+      if (et == 0) {
+        tma_store_4d(&p.tmD, buf, 0, x0, y0, b);
+        ptx::tma_store_commit();
+      }
+      ++k;
+    }
+    if (et == 0) ptx::tma_store_wait_all<0>();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<256>(tmem_base);
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+           CUtensorMapSwizzle swz) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  OPD_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  OPD_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides,
+                                                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OPD_ERR_CUDA, "cuTensorMapEncodeTiled (stem) failed (%d)", (int)r);
+  return OPD_OK;
+}
+
+}  // namespace
+
+int stem_plan(StemPlan* plan, const __nv_bfloat16* s2d, int B, int H2, int W2, const __nv_bfloat16* w_taps, const float* bias,
+              __nv_bfloat16* y) {
+  *plan = StemPlan{};
+  plan->B = B; plan->H2 = H2; plan->W2 = W2;
+  plan->bias = bias;
+  {
+    cuuint64_t dims[4] = {16, (cuuint64_t)W2, (cuuint64_t)H2, (cuuint64_t)B};
+    cuuint64_t strides[3] = {32, (cuuint64_t)W2 * 32, (cuuint64_t)H2 * W2 * 32};
+    cuuint32_t box[4] = {16, PATCH_W, PATCH_H, 1};
+    if (int rc = encode(&plan->tmS, s2d, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {256, 64};
+    cuuint64_t strides[1] = {512};
+    cuuint32_t box[2] = {16, 64};
+    if (int rc = encode(&plan->tmW, w_taps, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+  }
+  if (int rc = make_tmap_nhwc_patch(&plan->tmD, y, B, H2, W2, 64, TILE_W, TILE_H)) return rc;
+  const int tiles = B * ((H2 + TILE_H - 1) / TILE_H) * ((W2 + TILE_W - 1) / TILE_W);
+  plan->grid = std::min(tiles, sm_count());
+  return OPD_OK;
+}
+
+int stem_launch(const StemPlan& plan, cudaStream_t stream) {
+  StemParams p;
+  p.tmS = plan.tmS; p.tmW = plan.tmW; p.tmD = plan.tmD;
+  p.tiles_x = (plan.W2 + TILE_W - 1) / TILE_W;
+  p.tiles_y = (plan.H2 + TILE_H - 1) / TILE_H;
+  p.num_tiles = plan.B * p.tiles_x * p.tiles_y;
+  p.bias = plan.bias;
+  static bool configured = false;
+  if (!configured) {
+    OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  stem_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_preprocess_s2d(const uint8_t* src, int B, int Hs, int Ws, int src_is_bgr, __nv_bfloat16* s2d, cudaStream_t s) {
+  const int H2 = (Hs + 1) / 2, W2 = (Ws + 1) / 2;
+  const long long total = (long long)B * H2 * W2;
+  const long long blocks = (total + 255) / 256;
+  s2d_preprocess_kernel<<<(int)std::min<long long>(blocks, 148LL * 16), 256, 0, s>>>(src, B, Hs, Ws, src_is_bgr, s2d, H2, W2);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+}  // namespace opd

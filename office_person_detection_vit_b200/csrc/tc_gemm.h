@@ -67,6 +67,17 @@ int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g);
 // 4D tiled map over an NHWC bf16 tensor: box = [64 channels, box_w, box_h, 1 image], 128-byte swizzle, zero fill
 int make_tmap_nhwc_patch(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h);
 
+// Stem (stem_conv.cu): 4x4-tap convolution over the space-to-depth tensor S[B,H2,W2,16] -> y[B,H2,W2,64], bias + ReLU.
+struct StemPlan {
+  CUtensorMap tmS, tmW, tmD;
+  int B, H2, W2;
+  const float* bias;
+  int grid;
+};
+int stem_plan(StemPlan* plan, const __nv_bfloat16* s2d, int B, int H2, int W2, const __nv_bfloat16* w_taps, const float* bias,
+              __nv_bfloat16* y);
+int stem_launch(const StemPlan& plan, cudaStream_t stream);
+
 struct BneckPlan {
   CUtensorMap tmA, tmB1, tmB2, tmR, tmD;
   int halo;            // 1: stride-1, MID = 64 variant (tc_bottleneck_halo.cu): 16 x 8 pixel tiles, A = one halo patch per tile
