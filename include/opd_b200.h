@@ -42,6 +42,7 @@ const char* opd_last_error(void);
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t opd_launch_count(void);
 /* Kernel-selection knobs for A/B measurements (plans built afterwards see the new value):
+ *   "attention_tc" 1 (default): fused attention on tcgen05 / TMEM; 0: the mma.sync flash kernel
  *   "bneck_halo"  1 (default): 64-channel stride-1 bottleneck tails load one halo patch per tile; 0: im2col TMA. */
 int opd_set_option(const char* name, int32_t value);
 

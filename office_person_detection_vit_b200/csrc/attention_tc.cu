@@ -1,0 +1,301 @@
+// K6: fused multi-head attention on the 5th-generation tensor cores (head_dim 32, bf16 in, fp32 softmax):
+//     o = softmax(q k^T / sqrt(32)) v          per (batch, head)
+// replaces transformers models/detr/modeling_detr.py:386-411 (eager_attention_forward) inside DetrSelfAttention /
+// DetrCrossAttention (:414-557); no key-padding mask (all frames of a batch have one size).
+//
+// One CTA = 128 query rows of one (batch, head); key/value tiles of 128 stream through a 2-stage TMA ring.
+//   warp 0   TMA producer: Q tile once, then K_j / V_j tiles ([128 x 32] bf16, 64-byte rows, 64-byte swizzle)
+//   warp 1   MMA issuer:   S = Q K_j^T   (2 x tcgen05.mma 128x128x16, K-major operands)          -> TMEM columns [0,128)
+//                          O += P V_j    (8 x tcgen05.mma 128x32x16, A = P from shared memory, B = V_j MN-major) -> [128,160)
+//   warps 2-5 softmax:     thread = query row: TMEM -> registers, online max / exp2 / sum in fp32, P -> bf16 -> 128B-swizzled
+//                          shared memory (the A operand of the second MMA), O rescaled in TMEM when the row maximum moves
+// S_{j+1} is issued ahead of P V_j so the next tile's softmax overlaps the value MMA; TMEM use is 256 columns, shared
+// memory 73 KB, so two CTAs share an SM and cover each other's barrier latencies.
+#include <algorithm>
+
+#include "detr_kernels.h"
+#include "opd_common.h"
+#include "sm100_ptx.cuh"
+#include "tc_gemm.h"
+
+namespace opd {
+namespace {
+
+constexpr int kQ = 128, kKV = 128, kD = 32;
+constexpr int TILE_BYTES = 128 * 64;          // [128 rows x 32 bf16]
+constexpr int P_CHUNK = 128 * 128;            // [128 rows x 64 bf16]
+constexpr int kThreads = 192;
+constexpr int kSmemBytes = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + 2 * P_CHUNK /*P*/ + 1024;
+constexpr int kTmemCols = 256;
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmV;
+  __nv_bfloat16* o;
+  long long ldo;
+  int Lq, Lk;
+};
+
+// shared-memory descriptors: 64-byte swizzle (rows of 32 bf16), 8-row groups 512 B apart; 128-byte swizzle for P
+__device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+constexpr uint32_t kSw64 = 4, kSw128 = 2;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+  constexpr uint32_t kIdescS = ptx::umma_idesc_bf16(128, 128);
+  constexpr uint32_t kIdescPV = ptx::umma_idesc_bf16(128, 32) | (1u << 16);   // B (= V tile) is MN-major
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_q = smem;
+  uint8_t* s_k = s_q + TILE_BYTES;          // [2]
+  uint8_t* s_v = s_k + 2 * TILE_BYTES;      // [2]
+  uint8_t* s_p = s_v + 2 * TILE_BYTES;      // 2 chunks of 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * P_CHUNK);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* k_empty = bars + 3;    // [2]
+  uint64_t* v_full = bars + 5;     // [2]
+  uint64_t* v_empty = bars + 7;    // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_ready = bars + 10;
+  uint64_t* pv_done = bars + 11;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQ, head = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.Lk + kKV - 1) / kKV;
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmQ);
+    ptx::prefetch_tmap(&p.tmK);
+    ptx::prefetch_tmap(&p.tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_ready, 128);
+    ptx::mbar_init(pv_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      ptx::mbar_expect_tx(q_full, TILE_BYTES);
+      ptx::tma_load_2d(&p.tmQ, q_full, s_q, head * kD, b * p.Lq + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        ptx::mbar_wait(&k_empty[st], ph ^ 1);
+        ptx::mbar_expect_tx(&k_full[st], TILE_BYTES);
+        ptx::tma_load_2d(&p.tmK, &k_full[st], s_k + st * TILE_BYTES, head * kD, b * p.Lk + j * kKV);
+        ptx::mbar_wait(&v_empty[st], ph ^ 1);
+        ptx::mbar_expect_tx(&v_full[st], TILE_BYTES);
+        ptx::tma_load_2d(&p.tmV, &v_full[st], s_v + st * TILE_BYTES, head * kD, b * p.Lk + j * kKV);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t q_addr = ptx::smem_u32(s_q), p_addr = ptx::smem_u32(s_p);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&k_full[st], (j >> 1) & 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t k_addr = ptx::smem_u32(s_k + st * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          ptx::umma_bf16_ss(tmem_s, desc(q_addr + k * 32, 512, kSw64), desc(k_addr + k * 32, 512, kSw64), kIdescS, k != 0);
+        ptx::umma_commit(&k_empty[st]);
+        ptx::umma_commit(s_full);
+      };
+      ptx::mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        ptx::mbar_wait(p_ready, j & 1);          // softmax_j: S consumed, P written, O rescaled
+        ptx::tc_fence_after_sync();
+        if (j + 1 < n_tiles) issue_s(j + 1);     // next scores first: their softmax overlaps P V_j
+        ptx::mbar_wait(&v_full[st], (j >> 1) & 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t v_addr = ptx::smem_u32(s_v + st * TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          ptx::umma_bf16_ss(tmem_o, desc(p_addr + (kk >> 2) * P_CHUNK + (kk & 3) * 32, 1024, kSw128),
+                            desc(v_addr + kk * 1024, 512, kSw64), kIdescPV, (j | kk) != 0);
+        ptx::umma_commit(&v_empty[st]);
+        ptx::umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ===================================== softmax warps (thread = query row) =====================================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
+    float m = -INFINITY, l = 0.f;
+    uint8_t* prow = s_p + row * 128;
+    for (int j = 0; j < n_tiles; ++j) {
+      ptx::mbar_wait(s_full, j & 1);
+      ptx::tc_fence_after_sync();
+      const int valid = p.Lk - j * kKV;           // keys of this tile that exist (>= 128: all)
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (valid >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx * sl2);
+      const float alpha = ex2(m - m_new);         // first tile: ex2(-inf) = 0
+      // P and O belong to the previous tile's value MMA until it has completed
+      if (j > 0) {
+        ptx::mbar_wait(pv_done, (j - 1) & 1);
+        ptx::tc_fence_after_sync();
+      }
+      // pass 2: p = 2^(s * sl2 - m_new) -> bf16 -> shared memory (K-major A operand, 128-byte swizzle)
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
+        ptx::tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, -m_new));
+          float bb = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_new));
+          if (c * 32 + 2 * i >= valid) a = 0.f;
+          if (c * 32 + 2 * i + 1 >= valid) bb = 0.f;
+          lsum += a + bb;
+          packed[i] = ptx::pack_bf16(a, bb);
+        }
+        uint8_t* chunk = prow + (c >> 1) * P_CHUNK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(chunk + ((((c & 1) * 4 + i) ^ (row & 7)) << 4)) =
+              make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+      }
+      l = l * alpha + lsum;
+      m = m_new;
+      // rescale the running output when any row of this warp moved its maximum
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        uint32_t o[32];
+        ptx::tmem_ld_32x32(tmem_o + lane_addr, o);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        ptx::tmem_st_32x32(tmem_o + lane_addr, o);
+        ptx::tmem_st_wait();
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(p_ready);
+    }
+    // epilogue: O / l -> bf16 -> global
+    ptx::mbar_wait(pv_done, (n_tiles - 1) & 1);
+    ptx::tc_fence_after_sync();
+    uint32_t o[32];
+    ptx::tmem_ld_32x32(tmem_o + lane_addr, o);
+    ptx::tmem_ld_wait();
+    if (q0 + row < p.Lq) {
+      const float inv = 1.f / l;
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = ptx::pack_bf16(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+      uint4* dst = reinterpret_cast<uint4*>(p.o + ((long long)b * p.Lq + q0 + row) * p.ldo + head * kD);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// [rows, cols] bf16 with row pitch ld; box = [32 columns, 128 rows], 64-byte swizzle
+int make_tmap_head(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  OPD_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  OPD_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+  OPD_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, "attention: operand not 16-byte aligned");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OPD_ERR_CUDA, "cuTensorMapEncodeTiled (attention) failed (%d)", (int)r);
+  return OPD_OK;
+}
+
+}  // namespace
+
+int attn_plan(AttnPlan* plan, const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v,
+              int64_t ldv, __nv_bfloat16* o, int64_t ldo, int B, int heads, int Lq, int Lk) {
+  *plan = AttnPlan{};
+  OPD_REQUIRE(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "attention: bad shape");
+  OPD_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention: output not 16-byte aligned");
+  const uint64_t cols = (uint64_t)heads * kD;
+  if (int rc = make_tmap_head(&plan->tmQ, q, (uint64_t)B * Lq, cols, ldq)) return rc;
+  if (int rc = make_tmap_head(&plan->tmK, k, (uint64_t)B * Lk, cols, ldk)) return rc;
+  if (int rc = make_tmap_head(&plan->tmV, v, (uint64_t)B * Lk, cols, ldv)) return rc;
+  plan->o = o; plan->ldo = ldo; plan->B = B; plan->heads = heads; plan->Lq = Lq; plan->Lk = Lk;
+  return OPD_OK;
+}
+
+int attn_launch(const AttnPlan& plan, cudaStream_t stream) {
+  AttnParams p;
+  p.tmQ = plan.tmQ; p.tmK = plan.tmK; p.tmV = plan.tmV;
+  p.o = plan.o; p.ldo = plan.ldo; p.Lq = plan.Lq; p.Lk = plan.Lk;
+  static bool configured = false;
+  if (!configured) {
+    OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  dim3 grid((plan.Lq + kQ - 1) / kQ, plan.heads, plan.B);
+  attention_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+}  // namespace opd

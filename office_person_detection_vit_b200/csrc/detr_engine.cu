@@ -674,9 +674,17 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
     add_gemm(gp);
     return OPD_OK;
   };
+  int attn_rc = OPD_OK;
   auto attn = [&](const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int Lq, int Lk) {
-    add(OPD_STEP_ATTENTION, cur_name, 4.0 * B * kHeads * (double)Lq * Lk * 32, 2.0 * B * kD * (2.0 * Lq + 2.0 * Lk),
-        [=](cudaStream_t s) { return launch_attention(q, ldq, k, ldk, v, ldv, o, kD, B, kHeads, Lq, Lk, s); });
+    const double flops = 4.0 * B * kHeads * (double)Lq * Lk * 32, bytes = 2.0 * B * kD * (2.0 * Lq + 2.0 * Lk);
+    if (g_option_attention_tc.load()) {
+      AttnPlan ap;
+      attn_rc = attn_plan(&ap, q, ldq, k, ldk, v, ldv, o, kD, B, kHeads, Lq, Lk);
+      add(OPD_STEP_ATTENTION, cur_name, flops, bytes, [ap](cudaStream_t s) { return attn_launch(ap, s); });
+    } else {
+      add(OPD_STEP_ATTENTION, cur_name, flops, bytes,
+          [=](cudaStream_t s) { return launch_attention(q, ldq, k, ldk, v, ldv, o, kD, B, kHeads, Lq, Lk, s); });
+    }
   };
 
   add(OPD_STEP_ELEMENTWISE, "pos_embed", 0.0, 4.0 * S * kD, [pos, hh, ww](cudaStream_t s) { return launch_pos_embed(pos, hh, ww, s); });
@@ -738,6 +746,7 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   add(OPD_STEP_ELEMENTWISE, "dec.final_ln", 0.0, 4.0 * Mq * kD,
       [m, yin, dout, Mq](cudaStream_t s) { return launch_layernorm(yin, m->dec_norm.g, m->dec_norm.b, dout, Mq, s); });
   taps["dec_out"] = {dout, Mq, kD, 0};
+  if (attn_rc != OPD_OK) return attn_rc;
   add(OPD_STEP_HEADS, "heads", 2.0 * Mq * kD * (kClasses + 2 * kD + 4), 2.0 * Mq * kD + 4.0 * Mq * (kClasses + 4),
       [m, dout, Mq](cudaStream_t s) { return launch_heads(dout, m->heads, m->cur_logits, m->cur_boxes, Mq, s); });
   return OPD_OK;

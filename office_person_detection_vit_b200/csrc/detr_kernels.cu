@@ -7,6 +7,7 @@
 #include <cmath>
 
 #include "opd_common.h"
+#include "tc_gemm.h"
 
 namespace opd {
 
@@ -604,6 +605,13 @@ int launch_postprocess(const float* logits, const float* boxes, int B, int Q, in
 extern "C" int opd_attention_bf16(const void* q_dev, int64_t ldq, const void* k_dev, int64_t ldk, const void* v_dev,
                                   int64_t ldv, void* o_dev, int64_t ldo, int32_t B, int32_t heads, int32_t Lq,
                                   int32_t Lk, void* stream) {
+  if (opd::g_option_attention_tc.load()) {
+    opd::AttnPlan plan;
+    if (int rc = opd::attn_plan(&plan, static_cast<const __nv_bfloat16*>(q_dev), ldq, static_cast<const __nv_bfloat16*>(k_dev), ldk,
+                                static_cast<const __nv_bfloat16*>(v_dev), ldv, static_cast<__nv_bfloat16*>(o_dev), ldo, B, heads, Lq, Lk))
+      return rc;
+    return opd::attn_launch(plan, static_cast<cudaStream_t>(stream));
+  }
   return opd::launch_attention(static_cast<const __nv_bfloat16*>(q_dev), ldq, static_cast<const __nv_bfloat16*>(k_dev),
                                ldk, static_cast<const __nv_bfloat16*>(v_dev), ldv, static_cast<__nv_bfloat16*>(o_dev),
                                ldo, B, heads, Lq, Lk, static_cast<cudaStream_t>(stream));

@@ -8,6 +8,7 @@ std::string& last_error_ref() {
 }
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_option_bneck_halo{1};
+std::atomic<int> g_option_attention_tc{1};
 }  // namespace opd
 
 extern "C" {
@@ -17,6 +18,10 @@ int64_t opd_launch_count(void) { return opd::g_launches.load(); }
 int opd_set_option(const char* name, int32_t value) {
   if (name && std::string(name) == "bneck_halo") {
     opd::g_option_bneck_halo.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "attention_tc") {
+    opd::g_option_attention_tc.store(value);
     return OPD_OK;
   }
   return opd::fail(OPD_ERR_INVALID, "opd_set_option: unknown option '%s'", name ? name : "(null)");

@@ -67,6 +67,17 @@ int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g);
 // 4D tiled map over an NHWC bf16 tensor: box = [64 channels, box_w, box_h, 1 image], 128-byte swizzle, zero fill
 int make_tmap_nhwc_patch(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h);
 
+// Fused attention on tcgen05 (attention_tc.cu): o = softmax(q k^T / sqrt(32)) v, head h = columns [32h, 32h + 32).
+struct AttnPlan {
+  CUtensorMap tmQ, tmK, tmV;
+  __nv_bfloat16* o;
+  int64_t ldo;
+  int B, heads, Lq, Lk;
+};
+int attn_plan(AttnPlan* plan, const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v,
+              int64_t ldv, __nv_bfloat16* o, int64_t ldo, int B, int heads, int Lq, int Lk);
+int attn_launch(const AttnPlan& plan, cudaStream_t stream);
+
 // Stem (stem_conv.cu): 4x4-tap convolution over the space-to-depth tensor S[B,H2,W2,16] -> y[B,H2,W2,64], bias + ReLU.
 struct StemPlan {
   CUtensorMap tmS, tmW, tmD;
