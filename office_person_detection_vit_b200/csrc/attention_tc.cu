@@ -47,6 +47,28 @@ __device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t sbo_bytes, uint
 }
 constexpr uint32_t kSw64 = 4, kSw128 = 2;
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// packed fp32 pairs (Blackwell FFMA2 / FADD2): two lanes per instruction
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -162,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc_kernel(const __grid_
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after_sync();
       const int valid = p.Lk - j * kKV;           // keys of this tile that exist (>= 128: all)
-      // pass 1: row maximum
+      // pass 1: row maximum (3-input max; only the last tile of a row of tiles needs the key mask)
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -171,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc_kernel(const __grid_
         ptx::tmem_ld_wait();
         if (valid >= (c + 1) * 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -187,26 +209,44 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc_kernel(const __grid_
       }
       // pass 2: p = 2^(s * sl2 - m_new) -> bf16 -> shared memory (K-major A operand, 128-byte swizzle)
       float lsum = 0.f;
+      const uint64_t sl2_2 = pack2f(sl2, sl2), neg_m2 = pack2f(-m_new, -m_new);
+      uint64_t sum2 = pack2f(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
         ptx::tmem_ld_wait();
         uint32_t packed[16];
+        if (valid >= (c + 1) * 32) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, -m_new));
-          float bb = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_new));
-          if (c * 32 + 2 * i >= valid) a = 0.f;
-          if (c * 32 + 2 * i + 1 >= valid) bb = 0.f;
-          lsum += a + bb;
-          packed[i] = ptx::pack_bf16(a, bb);
+          for (int i = 0; i < 16; ++i) {
+            float x0, x1;
+            unpack2f(fma2(pack2f(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2, neg_m2), x0, x1);
+            const float a = ex2(x0), bb = ex2(x1);
+            sum2 = add2(sum2, pack2f(a, bb));
+            packed[i] = ptx::pack_bf16(a, bb);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, -m_new));
+            float bb = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_new));
+            if (c * 32 + 2 * i >= valid) a = 0.f;
+            if (c * 32 + 2 * i + 1 >= valid) bb = 0.f;
+            lsum += a + bb;
+            packed[i] = ptx::pack_bf16(a, bb);
+          }
         }
         uint8_t* chunk = prow + (c >> 1) * P_CHUNK;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           *reinterpret_cast<uint4*>(chunk + ((((c & 1) * 4 + i) ^ (row & 7)) << 4)) =
               make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+      }
+      {
+        float s0, s1;
+        unpack2f(sum2, s0, s1);
+        lsum += s0 + s1;
       }
       l = l * alpha + lsum;
       m = m_new;
