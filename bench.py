@@ -291,7 +291,7 @@ def main_gpu(args) -> None:
     tc_flops = by_kind.get("gemm", {"flops": 0})["flops"] + by_kind.get("conv", {"flops": 0})["flops"]
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel (implicit-GEMM convolutions + linear layers)",
+    roofline = {"bound": "tensor", "kernel": "tcgen05 GEMM / convolution kernels: tc_gemm_kernel, tc_bneck_kernel, tc_bneck_halo_kernel, stem_kernel",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "traffic": None, "peak_source": f"{pk_kind} bf16_tflops_sustained",
                 "launches_per_step": by_kind.get("gemm", {"launches": 0})["launches"] + by_kind.get("conv", {"launches": 0})["launches"],
