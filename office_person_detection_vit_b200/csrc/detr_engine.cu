@@ -47,6 +47,8 @@ struct LnW {
 struct BlockW {
   bool has_shortcut = false;
   ConvW shortcut, c0, c1, c2;
+  bf16* w3sc = nullptr;      // [width, 2 * mid] = [layer.2 | shortcut] weights (64-channel, stride-1 first block only)
+  float* bias3sc = nullptr;  // layer.2 shift + shortcut shift
 };
 struct EncW {
   LinW qk, v, o, fc1, fc2;
@@ -85,6 +87,7 @@ struct Plan {
 struct opd_detr {
   int device = 0;
   int debug = 0;
+  int fuse_shortcut = 1;   // stage-1 first block: projection shortcut computed inside the fused tail
   int fuse_tail = 1;   // 0: run the 3x3 and the 1x1 expansion of stages 1-2 as separate kernels (A/B comparison)
   int do_resize = 1;   // 0: frames are fed at their own size (DetrImageProcessor(do_resize=False))
   std::vector<void*> allocs;
@@ -186,8 +189,12 @@ struct Loader {
                 __float2bfloat16(wf[(((size_t)n * cin + ci) * k + r) * k + s]);
     c.w = upload(packed);
     c.bias = upload(shift);
+    last_packed = packed;
+    last_shift = shift;
     return c;
   }
+  std::vector<bf16> last_packed;   // host copies of the most recent conv() (for fused weight layouts)
+  std::vector<float> last_shift;
 
   // 7x7 / stride 2 / pad 3 stem over RGB  ->  4x1 convolution over the 64-channel layout written by K1:
   //   channel = kw4 * 16 + (dy * 2 + dx) * 3 + c,  tap row kh4;  original tap (r, s): kh4 = (r+1)/2, dy = (r+1)&1 (same for s)
@@ -272,10 +279,30 @@ int load_weights(opd_detr* m, const opd_tensor_f32* tensors, int n_tensors) {
       const std::string p = bb + "encoder.stages." + std::to_string(s) + ".layers." + std::to_string(l);
       BlockW b;
       b.has_shortcut = l == 0;
-      if (l == 0) b.shortcut = L.conv(p + ".shortcut", cin, width, 1, stride);
+      std::vector<bf16> sc_w;
+      std::vector<float> sc_b;
+      if (l == 0) {
+        b.shortcut = L.conv(p + ".shortcut", cin, width, 1, stride);
+        sc_w = L.last_packed;
+        sc_b = L.last_shift;
+      }
       b.c0 = L.conv(p + ".layer.0", cin, mid, 1, 1);
       b.c1 = L.conv(p + ".layer.1", mid, mid, 3, stride);   // v1.5: the stride sits on the 3x3
       b.c2 = L.conv(p + ".layer.2", mid, width, 1, 1);
+      if (l == 0 && cin == 64 && mid == 64 && stride == 1 && L.rc == OPD_OK) {
+        // fused projection shortcut (tc_bottleneck_halo.cu): one [width, 128] operand, K = [layer.2 input | block input]
+        std::vector<bf16> cat((size_t)width * 128);
+        std::vector<float> bias(width);
+        for (int n = 0; n < width; ++n) {
+          for (int k = 0; k < 64; ++k) {
+            cat[(size_t)n * 128 + k] = L.last_packed[(size_t)n * 64 + k];
+            cat[(size_t)n * 128 + 64 + k] = sc_w[(size_t)n * 64 + k];
+          }
+          bias[n] = L.last_shift[n] + sc_b[n];
+        }
+        b.w3sc = L.upload(cat);
+        b.bias3sc = L.upload(bias);
+      }
       m->blocks.push_back(b);
       cin = width;
     }
@@ -598,7 +625,8 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
       const long long m_in = (long long)B * hh * ww, m_out = (long long)B * ho * wo;
       const bf16* res = x;
       const std::string bname = "stage" + std::to_string(s) + "." + std::to_string(l);
-      if (bw.has_shortcut) {
+      const bool fuse_sc = bw.has_shortcut && bw.w3sc && m->fuse_tail && m->fuse_shortcut && g_option_bneck_halo.load();
+      if (bw.has_shortcut && !fuse_sc) {
         cur_name = bname + ".shortcut";
         bf16* sc = static_cast<bf16*>(big_slot((cur + 1) % 3, act_bytes(m_out, width)));
         if (int rc = conv(x, hh, ww, bw.shortcut, sc, EPI_BIAS, nullptr)) return rc;
@@ -614,10 +642,17 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
         if (!dry) {
           BneckPlan bp;
           ConvGeom g{B, hh, ww, mid, 3, 3, stride, 1, 1, ho, wo};
-          if (int rc = bneck_plan(&bp, m1, g, bw.c1.w, bw.c1.bias, bw.c2.w, bw.c2.bias, width, res, out)) return rc;
-          const double flops = 2.0 * m_out * mid * (9.0 * mid + width);
-          const double bytes = 2.0 * m_in * mid + 4.0 * m_out * width + 2.0 * mid * (9.0 * mid + width);
-          add(OPD_STEP_CONV, bname + ".tail(3x3+1x1b)", flops, bytes, [bp](cudaStream_t s) { return bneck_launch(bp, s); });
+          if (fuse_sc) {
+            if (int rc = bneck_halo_plan(&bp, m1, g, bw.c1.w, bw.c1.bias, bw.w3sc, bw.bias3sc, width, nullptr, out, x)) return rc;
+            const double flops = 2.0 * m_out * mid * (9.0 * mid + 2.0 * width);
+            const double bytes = 2.0 * m_in * mid * 2 + 2.0 * m_out * width + 2.0 * mid * (9.0 * mid + 2.0 * width);
+            add(OPD_STEP_CONV, bname + ".tail(3x3+1x1b+shortcut)", flops, bytes, [bp](cudaStream_t s) { return bneck_launch(bp, s); });
+          } else {
+            if (int rc = bneck_plan(&bp, m1, g, bw.c1.w, bw.c1.bias, bw.c2.w, bw.c2.bias, width, res, out)) return rc;
+            const double flops = 2.0 * m_out * mid * (9.0 * mid + width);
+            const double bytes = 2.0 * m_in * mid + 4.0 * m_out * width + 2.0 * mid * (9.0 * mid + width);
+            add(OPD_STEP_CONV, bname + ".tail(3x3+1x1b)", flops, bytes, [bp](cudaStream_t s) { return bneck_launch(bp, s); });
+          }
         }
       } else {
         cur_name = bname + ".conv3x3";
@@ -791,7 +826,8 @@ int opd_detr_set_debug(opd_detr* m, int32_t debug) {
 int opd_detr_set_fusion(opd_detr* m, int32_t fuse_bottleneck_tail) {
   OPD_REQUIRE(m, "opd_detr_set_fusion: NULL handle");
   m->fuse_tail = fuse_bottleneck_tail & 1;
-  m->stem_halo = (fuse_bottleneck_tail & 2) ? 0 : 1;   // bit 1 set: im2col stem over the 64-lane layout (A/B comparison)
+  m->stem_halo = (fuse_bottleneck_tail & 2) ? 0 : 1;
+  m->fuse_shortcut = (fuse_bottleneck_tail & 4) ? 0 : 1;   // bit 2 set: separate shortcut kernel   // bit 1 set: im2col stem over the 64-lane layout (A/B comparison)
   m->plan = opd::Plan{};
   return OPD_OK;
 }

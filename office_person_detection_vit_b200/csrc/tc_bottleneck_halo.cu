@@ -61,6 +61,9 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr, uint32_t sbo_bytes
   return d;
 }
 
+// kSC: the block's 1x1 projection shortcut is computed here too (second k-block of the second GEMM: the block input
+// tile times Wsc), so the residual tensor is neither written by a separate kernel nor read back.
+template <bool kSC>
 __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr uint32_t kIdesc1 = ptx::umma_idesc_bf16(BLOCK_M, MID);
   constexpr uint32_t kIdesc2 = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N2);
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     }
     for (int i = 0; i < kResStages; ++i) {
       ptx::mbar_init(&res_full[i], 1);
-      ptx::mbar_init(&res_empty[i], 4);
+      ptx::mbar_init(&res_empty[i], kSC ? 1 : 4);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&a2_ready[i], 256);
@@ -165,15 +168,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
         }
       };
       auto load_g2 = [&]() {
-        for (int n2 = 0; n2 < p.num_n2; ++n2) {
-          ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
-          ptx::mbar_expect_tx(&b_full[bs], CHUNK_BYTES);
-          ptx::tma_load_2d(&p.tmB2, &b_full[bs], smem_b + bs * CHUNK_BYTES, 0, n2 * BLOCK_N2);
-          if (++bs == kBStages) {
-            bs = 0;
-            bphase ^= 1;
+        for (int n2 = 0; n2 < p.num_n2; ++n2)
+          for (int kb = 0; kb < (kSC ? 2 : 1); ++kb) {   // kb 1: the shortcut weights (columns 64..127 of [W3 | Wsc])
+            ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
+            ptx::mbar_expect_tx(&b_full[bs], CHUNK_BYTES);
+            ptx::tma_load_2d(&p.tmB2, &b_full[bs], smem_b + bs * CHUNK_BYTES, kb * 64, n2 * BLOCK_N2);
+            if (++bs == kBStages) {
+              bs = 0;
+              bphase ^= 1;
+            }
           }
-        }
       };
       if (first < n_tiles) load_g1(first);
       for (int t = first; t < n_tiles; t += step) {
@@ -184,8 +188,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
-      int ps = 0, bs = 0, a1 = 0, a2 = 0, ab = 0;
-      uint32_t pphase = 0, bphase = 0, a1_phase = 0, a2_phase = 0, ready_phase = 0;
+      int ps = 0, bs = 0, a1 = 0, a2 = 0, ab = 0, xs = 0;
+      uint32_t pphase = 0, bphase = 0, a1_phase = 0, a2_phase = 0, ready_phase = 0, xphase = 0;
       auto next_b = [&]() {
         if (++bs == kBStages) {
           bs = 0;
@@ -228,17 +232,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
         ptx::mbar_wait(&a2_ready[ab], ready_phase);
         ptx::tc_fence_after_sync();
         const uint32_t a_addr = ptx::smem_u32(smem_a2 + ab * CHUNK_BYTES);
+        const uint32_t x_addr = ptx::smem_u32(smem_res + xs * CHUNK_BYTES);
+        if (kSC) {
+          ptx::mbar_wait(&res_full[xs], xphase);   // block input tile (A operand of the shortcut k-block)
+          ptx::tc_fence_after_sync();
+        }
         for (int n2 = 0; n2 < p.num_n2; ++n2) {
           ptx::mbar_wait(&acc2_empty[a2], a2_phase ^ 1);
-          ptx::mbar_wait(&b_full[bs], bphase);
-          ptx::tc_fence_after_sync();
           const uint32_t d = tmem_acc2 + a2 * BLOCK_N2;
-          const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES);
+          for (int kb = 0; kb < (kSC ? 2 : 1); ++kb) {
+            ptx::mbar_wait(&b_full[bs], bphase);
+            ptx::tc_fence_after_sync();
+            const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES);
+            const uint32_t aa = kb == 0 ? a_addr : x_addr;
 #pragma unroll
-          for (int k = 0; k < 64 / UMMA_K; ++k)
-            ptx::umma_bf16_ss(d, desc_sw128(a_addr + k * 32, 1024), desc_sw128(b_addr + k * 32, 1024), kIdesc2, k != 0);
-          ptx::umma_commit(&b_empty[bs]);
-          next_b();
+            for (int k = 0; k < 64 / UMMA_K; ++k)
+              ptx::umma_bf16_ss(d, desc_sw128(aa + k * 32, 1024), desc_sw128(b_addr + k * 32, 1024), kIdesc2, (kb | k) != 0);
+            ptx::umma_commit(&b_empty[bs]);
+            next_b();
+          }
           ptx::umma_commit(&acc2_full[a2]);
           if (++a2 == 2) {
             a2 = 0;
@@ -246,6 +258,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           }
         }
         ptx::umma_commit(&a2_free[ab]);
+        if (kSC) {
+          ptx::umma_commit(&res_empty[xs]);
+          if (++xs == 2) {
+            xs = 0;
+            xphase ^= 1;
+          }
+        }
         if (++ab == 2) {
           ab = 0;
           ready_phase ^= 1;
@@ -265,6 +284,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       for (int t = first; t < n_tiles; t += step) {
         int b, y0, x0;
         tile_origin(t, b, y0, x0);
+        if (kSC) {   // one block-input tile per output tile, slots 0 / 1 (released by the MMA warp's commit)
+          const int slot = k & 1;
+          ptx::mbar_wait(&res_empty[slot], ((k >> 1) & 1) ^ 1);
+          ptx::mbar_expect_tx(&res_full[slot], CHUNK_BYTES);
+          tma_load_4d(&p.tmR, &res_full[slot], smem_res + slot * CHUNK_BYTES, 0, x0, y0, b);
+          ++k;
+          continue;
+        }
         for (int n2 = 0; n2 < p.num_n2; ++n2, ++k) {
           for (int c = 0; c < 2; ++c) {   // chunk c of the n2 tile belongs to epilogue warpgroup c
             const int slot = c * 2 + (k & 1);
@@ -334,16 +361,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       const uint32_t t_acc = tmem_acc2 + lane_addr + a2 * BLOCK_N2 + wg * 64;
       uint32_t packed[32];
       const int rslot = wg * 2 + (rk & 1);
-      ptx::mbar_wait(&res_full[rslot], (rk >> 1) & 1);
-      ++rk;
       const uint8_t* rrow = smem_res + rslot * CHUNK_BYTES + row * 128;
+      if (!kSC) {
+        ptx::mbar_wait(&res_full[rslot], (rk >> 1) & 1);
+        ++rk;
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(t_acc + h * 32, v);
         uint4 rr[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rrow + (((h * 4 + j) ^ (row & 7)) << 4));
+        for (int j = 0; j < 4; ++j)
+          rr[j] = kSC ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(rrow + (((h * 4 + j) ^ (row & 7)) << 4));
         ptx::tmem_ld_wait();
         const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
 #pragma unroll
@@ -360,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
         a2_phase ^= 1;
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&res_empty[rslot]);
+      if (!kSC && lane == 0) ptx::mbar_arrive(&res_empty[rslot]);
       uint8_t* rowp = my_out + row * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -395,9 +425,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
 
 }  // namespace
 
+// shortcut_in != nullptr: fused projection shortcut; then w3 is [width, 128] = [W3 | Wsc], bias3 = b3 + b_sc, `residual` is
+// ignored and shortcut_in is the block input [B, P, Q, 64].
 int bneck_halo_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
-                    const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y) {
+                    const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y,
+                    const __nv_bfloat16* shortcut_in) {
   *plan = BneckPlan{};
+  if (shortcut_in) residual = shortcut_in;
   OPD_REQUIRE(g.KH == 3 && g.KW == 3 && g.C == MID && g.stride == 1 && g.pad_h == 1 && g.pad_w == 1 && g.P == g.H && g.Q == g.W,
               "bottleneck tail (halo): 3x3 / stride 1 / pad 1 over 64 channels only");
   OPD_REQUIRE(width % BLOCK_N2 == 0 && width > 0, "bottleneck tail (halo): width=%d must be a multiple of 128", width);
@@ -411,8 +445,10 @@ int bneck_halo_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, 
   plan->bias3 = bias3;
   if (int rc = make_tmap_nhwc_patch(&plan->tmA, x, g.B, g.H, g.W, MID, PATCH_W, PATCH_H)) return rc;
   if (int rc = make_tmap_2d(&plan->tmB1, w2, MID, 9 * MID, 9 * MID, MID)) return rc;
-  if (int rc = make_tmap_2d(&plan->tmB2, w3, width, MID, MID, BLOCK_N2)) return rc;
-  if (int rc = make_tmap_nhwc_patch(&plan->tmR, residual, g.B, g.P, g.Q, width, TILE_W, TILE_H)) return rc;
+  plan->fused_shortcut = shortcut_in != nullptr;
+  const int k2 = shortcut_in ? 2 * MID : MID;
+  if (int rc = make_tmap_2d(&plan->tmB2, w3, width, k2, k2, BLOCK_N2)) return rc;
+  if (int rc = make_tmap_nhwc_patch(&plan->tmR, residual, g.B, g.P, g.Q, shortcut_in ? MID : width, TILE_W, TILE_H)) return rc;
   if (int rc = make_tmap_nhwc_patch(&plan->tmD, y, g.B, g.P, g.Q, width, TILE_W, TILE_H)) return rc;
   const int tiles = g.B * ((g.P + TILE_H - 1) / TILE_H) * ((g.Q + TILE_W - 1) / TILE_W);
   plan->grid = std::min(tiles, sm_count());
@@ -430,10 +466,14 @@ int bneck_halo_launch(const BneckPlan& plan, cudaStream_t stream) {
   p.bias3 = plan.bias3;
   static bool configured = false;
   if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  tc_bneck_halo_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
+  if (plan.fused_shortcut)
+    tc_bneck_halo_kernel<true><<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
+  else
+    tc_bneck_halo_kernel<false><<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

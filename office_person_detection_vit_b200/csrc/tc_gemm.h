@@ -91,6 +91,7 @@ int stem_launch(const StemPlan& plan, cudaStream_t stream);
 
 struct BneckPlan {
   CUtensorMap tmA, tmB1, tmB2, tmR, tmD;
+  int fused_shortcut;  // halo variant only: the projection shortcut is a second k-block of the 1x1 expansion
   int halo;            // 1: stride-1, MID = 64 variant (tc_bottleneck_halo.cu): 16 x 8 pixel tiles, A = one halo patch per tile
   int M, mid, width;
   ConvGeom g;
@@ -102,7 +103,8 @@ int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const
                const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y);
 int bneck_launch(const BneckPlan& plan, cudaStream_t stream);
 int bneck_halo_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
-                    const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y);
+                    const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y,
+                    const __nv_bfloat16* shortcut_in = nullptr);
 int bneck_halo_launch(const BneckPlan& plan, cudaStream_t stream);
 
 }  // namespace opd

@@ -222,14 +222,14 @@ def backbone(w: dict, pixel_values: torch.Tensor, mode: str = "fp32", taps: dict
     """ResNet-50 with frozen BN -> stage-4 feature map [B,2048,h,w]."""
     m = _Mode(mode)
 
-    def conv(prefix, x, stride, k, relu, residual=None):
+    def conv(prefix, x, stride, k, relu, residual=None, rounded=True):
         wt, shift = fold_bn(w, prefix)
         y = F.conv2d(x, m.wt(wt), shift, stride=stride, padding=k // 2)
         if residual is not None:
             y = y + residual
         if relu:
             y = F.relu(y)
-        return m.act(y)
+        return m.act(y) if rounded else y
 
     x = m.act(pixel_values)
     x = conv("model.backbone.model.embedder.embedder", x, 2, 7, True)
@@ -242,7 +242,8 @@ def backbone(w: dict, pixel_values: torch.Tensor, mode: str = "fp32", taps: dict
         for l in range(depth):
             p = f"model.backbone.model.encoder.stages.{s}.layers.{l}"
             stride = 2 if (l == 0 and s > 0) else 1
-            res = conv(p + ".shortcut", x, stride, 1, False) if l == 0 else x
+            # CUDA path: the stage-1 projection shortcut is accumulated in fp32 inside the fused tail kernel (never stored)
+            res = conv(p + ".shortcut", x, stride, 1, False, rounded=not (s == 0)) if l == 0 else x
             y = conv(p + ".layer.0", x, 1, 1, True)
             y = conv(p + ".layer.1", y, stride, 3, True)
             x = conv(p + ".layer.2", y, 1, 1, True, residual=res)
