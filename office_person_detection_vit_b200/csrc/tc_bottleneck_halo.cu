@@ -1,15 +1,16 @@
 // Fused bottleneck tail, halo variant (3x3 stride 1, MID = 64 channels: ResNet stage 1):
-//     y = relu( conv1x1( relu(conv3x3(x) + b2) ) + b3 + residual )
-// Same pipeline as tc_bottleneck.cu, but the A operand of the 3x3 convolution is NOT nine im2col copies: one output
-// tile is a 16-row x 8-column pixel patch, its 18 x 10 x 64-channel input halo is loaded ONCE by a tiled TMA (zero fill
-// = the convolution's padding) and every filter tap reads it through a shifted shared-memory descriptor
-// (start + (r * 10 + s) * 128 B, 8-pixel groups one patch row = 1280 B apart; the 128-byte swizzle is a function of the
-// absolute shared-memory address, so shifted views stay consistent with what TMA wrote).  L2 -> SM traffic per tile
-// drops from 144 KB (im2col) to 23 KB, which is what bounded the im2col version (profiles/README.md).
-// Output and residual tiles are the same 16 x 8 patches, moved by 4D TMA boxes [64 ch, 8, 16, 1].
+//     y = relu( conv1x1( relu(conv3x3(x) + b2) ) + b3 + residual )            (or + Wsc * block_input: fused projection shortcut)
+// Same pipeline as tc_bottleneck.cu, but the A operand of the 3x3 convolution is NOT nine im2col copies.  One work tile is
+// a 16-row x 16-column pixel patch = two 128-pixel MMA tiles side by side (h = 0: columns 0-7, h = 1: columns 8-15).  Its
+// 18 x 18 x 64-channel input halo is loaded ONCE by a tiled TMA (zero fill = the convolution's padding) and every filter
+// tap reads it through a shifted shared-memory descriptor (start + (r * 18 + s + 8h) * 128 B, 8-pixel groups one patch row
+// = 2304 B apart; the 128-byte swizzle is a function of the absolute shared-memory address, so shifted views stay
+// consistent with what TMA wrote).  Both half tiles share every weight tile that streams through the B ring, which halves
+// the L2 -> SM weight traffic that paced the one-tile version (profiles/README.md).
+// Output, residual and shortcut-input tiles are 16 x 8 pixel patches moved by 4D TMA boxes [64 ch, 8, 16, 1].
 //
-// Warps: 0 TMA producer (patches + W2 / W3 tiles), 1 MMA issuer + TMEM owner, 2 residual producer,
-//        4-11 epilogue (two warpgroups splitting the columns).
+// Warps: 0 TMA producer (patch + W2 / W3 tiles), 1 MMA issuer + TMEM owner, 2 residual (or shortcut-input) producer,
+//        4-11 epilogue: two warpgroups; E1: warpgroup g converts half tile g; E2: warpgroup g owns 64-column chunk g.
 #include <algorithm>
 
 #include "opd_common.h"
@@ -21,16 +22,16 @@ namespace {
 
 constexpr int MID = 64;
 constexpr int BLOCK_M = 128, BLOCK_N2 = 128, UMMA_K = 16;
-constexpr int TILE_W = 8, TILE_H = 16, PATCH_W = TILE_W + 2, PATCH_H = TILE_H + 2;
-constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 128;   // 23040
-constexpr int PATCH_SLOT = 24576;
+constexpr int SUB_W = 8, TILE_W = 16, TILE_H = 16, PATCH_W = TILE_W + 2, PATCH_H = TILE_H + 2;
+constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 128;   // 41472
+constexpr int PATCH_SLOT = 41984;                      // 41 KB
 constexpr int CHUNK_BYTES = BLOCK_M * 64 * 2;          // 16 KB: one [128 x 64] bf16 box
-constexpr int kPatchStages = 2, kBStages = 3, kResStages = 4;   // residual: two slots per epilogue warpgroup
+constexpr int kBStages = 3, kResStages = 4;
 constexpr int kThreads = 384;
-constexpr int kSmemBytes = kPatchStages * PATCH_SLOT + kBStages * CHUNK_BYTES + 2 * CHUNK_BYTES /*A2 x2*/ + 2 * CHUNK_BYTES /*staging*/ +
+constexpr int kSmemBytes = PATCH_SLOT + kBStages * CHUNK_BYTES + 2 * CHUNK_BYTES /*A2[h]*/ + 2 * CHUNK_BYTES /*staging*/ +
                            kResStages * CHUNK_BYTES + 2048;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
-constexpr int kTmemCols = 512;   // acc1 2 x 64 + acc2 2 x 128
+constexpr int kTmemCols = 512;   // acc1[h] 2 x 64 + acc2[h] 2 x 128
 
 struct HaloParams {
   CUtensorMap tmA, tmB1, tmB2, tmR, tmD;
@@ -67,29 +68,30 @@ template <bool kSC>
 __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid_constant__ HaloParams p) {
   constexpr uint32_t kIdesc1 = ptx::umma_idesc_bf16(BLOCK_M, MID);
   constexpr uint32_t kIdesc2 = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N2);
+  constexpr int kB2Blocks = kSC ? 2 : 1;   // k-blocks of the second GEMM: [W3 | Wsc]
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* smem_patch = smem;                                      // [kPatchStages] halo patches
-  uint8_t* smem_b = smem_patch + kPatchStages * PATCH_SLOT;        // [kBStages] W2 tap tiles (8 KB used) / W3 tiles (16 KB)
-  uint8_t* smem_a2 = smem_b + kBStages * CHUNK_BYTES;              // A operand of the second GEMM, double buffered
+  uint8_t* smem_patch = smem;                                      // one halo patch (the next one loads during E2)
+  uint8_t* smem_b = smem_patch + PATCH_SLOT;                       // [kBStages] W2 tap pairs / W3 tiles
+  uint8_t* smem_a2 = smem_b + kBStages * CHUNK_BYTES;              // [2] A operand of the second GEMM, one per half tile
   uint8_t* smem_out = smem_a2 + 2 * CHUNK_BYTES;                   // one staging box per epilogue warpgroup
-  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;                  // two residual slots per epilogue warpgroup
+  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;                  // residual: 2 slots per warpgroup; kSC: X[h] in slots 0, 1
   float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [64]
   float* s_bias3 = s_bias2 + 64;                                                    // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 128);
-  uint64_t* patch_full = bars;          // [kPatchStages]
-  uint64_t* patch_empty = bars + 4;     // [kPatchStages]
-  uint64_t* b_full = bars + 8;          // [kBStages]
-  uint64_t* b_empty = bars + 12;        // [kBStages]
-  uint64_t* acc1_full = bars + 16;      // [2]
-  uint64_t* acc1_empty = bars + 18;     // [2]
-  uint64_t* acc2_full = bars + 20;      // [2]
-  uint64_t* acc2_empty = bars + 22;     // [2]
-  uint64_t* a2_ready = bars + 24;       // [2]
-  uint64_t* a2_free = bars + 26;        // [2]
-  uint64_t* res_full = bars + 28;       // [4]
-  uint64_t* res_empty = bars + 32;      // [4]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 36);
+  uint64_t* patch_full = bars;          // [1]
+  uint64_t* patch_empty = bars + 1;     // [1]
+  uint64_t* b_full = bars + 2;          // [kBStages]
+  uint64_t* b_empty = bars + 6;         // [kBStages]
+  uint64_t* acc1_full = bars + 10;      // [1]  (both halves)
+  uint64_t* acc1_empty = bars + 11;     // [1]
+  uint64_t* acc2_full = bars + 12;      // [2]  per half tile
+  uint64_t* acc2_empty = bars + 14;     // [2]
+  uint64_t* a2_ready = bars + 16;       // [1]
+  uint64_t* a2_free = bars + 17;        // [1]
+  uint64_t* res_full = bars + 18;       // [4]
+  uint64_t* res_empty = bars + 22;      // [4]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -99,27 +101,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     ptx::prefetch_tmap(&p.tmB1);
     ptx::prefetch_tmap(&p.tmB2);
     ptx::prefetch_tmap(&p.tmD);
-    for (int i = 0; i < kPatchStages; ++i) {
-      ptx::mbar_init(&patch_full[i], 1);
-      ptx::mbar_init(&patch_empty[i], 1);
-    }
+    ptx::mbar_init(patch_full, 1);
+    ptx::mbar_init(patch_empty, 1);
     for (int i = 0; i < kBStages; ++i) {
       ptx::mbar_init(&b_full[i], 1);
       ptx::mbar_init(&b_empty[i], 1);
     }
+    ptx::mbar_init(acc1_full, 1);
+    ptx::mbar_init(acc1_empty, 256);
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&acc1_full[i], 1);
-      ptx::mbar_init(&acc1_empty[i], 256);
       ptx::mbar_init(&acc2_full[i], 1);
       ptx::mbar_init(&acc2_empty[i], 256);
     }
+    ptx::mbar_init(a2_ready, 256);
+    ptx::mbar_init(a2_free, 1);
     for (int i = 0; i < kResStages; ++i) {
       ptx::mbar_init(&res_full[i], 1);
       ptx::mbar_init(&res_empty[i], kSC ? 1 : 4);
-    }
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&a2_ready[i], 256);
-      ptx::mbar_init(&a2_free[i], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -128,8 +126,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_acc1 = tmem_base;             // 2 x 64 columns
-  const uint32_t tmem_acc2 = tmem_base + 2 * MID;   // 2 x 128 columns
+  const uint32_t tmem_acc1 = tmem_base;             // [h] 64 columns each
+  const uint32_t tmem_acc2 = tmem_base + 2 * MID;   // [h] 128 columns each
 
   const int first = blockIdx.x, step = gridDim.x, n_tiles = p.num_tiles;
   auto tile_origin = [&](int t, int& b, int& y0, int& x0) {
@@ -143,163 +141,135 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      int ps = 0, bs = 0;
-      uint32_t pphase = 0, bphase = 0;
-      auto load_g1 = [&](int t) {
-        int b, y0, x0;
-        tile_origin(t, b, y0, x0);
-        ptx::mbar_wait(&patch_empty[ps], pphase ^ 1);
-        ptx::mbar_expect_tx(&patch_full[ps], PATCH_BYTES);
-        tma_load_4d(&p.tmA, &patch_full[ps], smem_patch + ps * PATCH_SLOT, 0, x0 - 1, y0 - 1, b);
-        if (++ps == kPatchStages) {
-          ps = 0;
-          pphase ^= 1;
-        }
-        for (int tap = 0; tap < 9; tap += 2) {   // two 8 KB tap tiles of W2 per 16 KB slot (the last slot holds one)
-          const int n_taps = tap + 1 < 9 ? 2 : 1;
-          ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
-          ptx::mbar_expect_tx(&b_full[bs], n_taps * MID * 128);
-          for (int j = 0; j < n_taps; ++j)
-            ptx::tma_load_2d(&p.tmB1, &b_full[bs], smem_b + bs * CHUNK_BYTES + j * (MID * 128), (tap + j) * 64, 0);
-          if (++bs == kBStages) {
-            bs = 0;
-            bphase ^= 1;
-          }
-        }
-      };
-      auto load_g2 = [&]() {
-        for (int n2 = 0; n2 < p.num_n2; ++n2)
-          for (int kb = 0; kb < (kSC ? 2 : 1); ++kb) {   // kb 1: the shortcut weights (columns 64..127 of [W3 | Wsc])
-            ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
-            ptx::mbar_expect_tx(&b_full[bs], CHUNK_BYTES);
-            ptx::tma_load_2d(&p.tmB2, &b_full[bs], smem_b + bs * CHUNK_BYTES, kb * 64, n2 * BLOCK_N2);
-            if (++bs == kBStages) {
-              bs = 0;
-              bphase ^= 1;
-            }
-          }
-      };
-      if (first < n_tiles) load_g1(first);
-      for (int t = first; t < n_tiles; t += step) {
-        if (t + step < n_tiles) load_g1(t + step);
-        load_g2();
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      int ps = 0, bs = 0, a1 = 0, a2 = 0, ab = 0, xs = 0;
-      uint32_t pphase = 0, bphase = 0, a1_phase = 0, a2_phase = 0, ready_phase = 0, xphase = 0;
+      int bs = 0;
+      uint32_t bphase = 0, n = 0;
       auto next_b = [&]() {
         if (++bs == kBStages) {
           bs = 0;
           bphase ^= 1;
         }
       };
-      auto g1 = [&]() {
-        ptx::mbar_wait(&acc1_empty[a1], a1_phase ^ 1);
-        ptx::mbar_wait(&patch_full[ps], pphase);
+      for (int t = first; t < n_tiles; t += step, ++n) {
+        int b, y0, x0;
+        tile_origin(t, b, y0, x0);
+        ptx::mbar_wait(patch_empty, (n & 1) ^ 1);
+        ptx::mbar_expect_tx(patch_full, PATCH_BYTES);
+        tma_load_4d(&p.tmA, patch_full, smem_patch, 0, x0 - 1, y0 - 1, b);
+        for (int tap = 0; tap < 9; tap += 2) {   // two 8 KB tap tiles of W2 per 16 KB slot (the last slot holds one)
+          const int n_taps = tap + 1 < 9 ? 2 : 1;
+          ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
+          ptx::mbar_expect_tx(&b_full[bs], n_taps * MID * 128);
+          for (int j = 0; j < n_taps; ++j)
+            ptx::tma_load_2d(&p.tmB1, &b_full[bs], smem_b + bs * CHUNK_BYTES + j * (MID * 128), (tap + j) * 64, 0);
+          next_b();
+        }
+        for (int n2 = 0; n2 < p.num_n2; ++n2)
+          for (int kb = 0; kb < kB2Blocks; ++kb) {   // kb 1: the shortcut weights (columns 64..127 of [W3 | Wsc])
+            ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
+            ptx::mbar_expect_tx(&b_full[bs], CHUNK_BYTES);
+            ptx::tma_load_2d(&p.tmB2, &b_full[bs], smem_b + bs * CHUNK_BYTES, kb * 64, n2 * BLOCK_N2);
+            next_b();
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      int bs = 0;
+      uint32_t bphase = 0, n = 0, acc2_phase[2] = {0, 0};
+      auto next_b = [&]() {
+        if (++bs == kBStages) {
+          bs = 0;
+          bphase ^= 1;
+        }
+      };
+      const uint32_t patch = ptx::smem_u32(smem_patch);
+      for (int t = first; t < n_tiles; t += step, ++n) {
+        const uint32_t par = n & 1;
+        // ---- G1: both half tiles, every W2 tap tile used twice ----
+        ptx::mbar_wait(acc1_empty, par ^ 1);
+        ptx::mbar_wait(patch_full, par);
         ptx::tc_fence_after_sync();
-        const uint32_t d = tmem_acc1 + a1 * MID;
-        const uint32_t patch = ptx::smem_u32(smem_patch + ps * PATCH_SLOT);
         for (int tap0 = 0; tap0 < 9; tap0 += 2) {
           ptx::mbar_wait(&b_full[bs], bphase);
           ptx::tc_fence_after_sync();
           for (int tap = tap0; tap < tap0 + 2 && tap < 9; ++tap) {
             const int r = tap / 3, s = tap - r * 3;
-            const uint32_t a_addr = patch + (r * PATCH_W + s) * 128;
             const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES + (tap - tap0) * (MID * 128));
 #pragma unroll
-            for (int k = 0; k < 64 / UMMA_K; ++k)
-              ptx::umma_bf16_ss(d, desc_sw128(a_addr + k * 32, PATCH_W * 128), desc_sw128(b_addr + k * 32, 1024), kIdesc1,
-                                (tap | k) != 0);
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t a_addr = patch + (r * PATCH_W + s + h * SUB_W) * 128;
+#pragma unroll
+              for (int k = 0; k < 64 / UMMA_K; ++k)
+                ptx::umma_bf16_ss(tmem_acc1 + h * MID, desc_sw128(a_addr + k * 32, PATCH_W * 128), desc_sw128(b_addr + k * 32, 1024),
+                                  kIdesc1, (tap | k) != 0);
+            }
           }
           ptx::umma_commit(&b_empty[bs]);
           next_b();
         }
-        ptx::umma_commit(&patch_empty[ps]);
-        ptx::umma_commit(&acc1_full[a1]);
-        if (++ps == kPatchStages) {
-          ps = 0;
-          pphase ^= 1;
-        }
-        if (++a1 == 2) {
-          a1 = 0;
-          a1_phase ^= 1;
-        }
-      };
-      auto g2 = [&]() {
-        ptx::mbar_wait(&a2_ready[ab], ready_phase);
-        ptx::tc_fence_after_sync();
-        const uint32_t a_addr = ptx::smem_u32(smem_a2 + ab * CHUNK_BYTES);
-        const uint32_t x_addr = ptx::smem_u32(smem_res + xs * CHUNK_BYTES);
+        ptx::umma_commit(patch_empty);
+        ptx::umma_commit(acc1_full);
+        // ---- G2: per n2 tile both half tiles share the W3 (and Wsc) tile ----
+        ptx::mbar_wait(a2_ready, par);
         if (kSC) {
-          ptx::mbar_wait(&res_full[xs], xphase);   // block input tile (A operand of the shortcut k-block)
-          ptx::tc_fence_after_sync();
+          ptx::mbar_wait(&res_full[0], par);
+          ptx::mbar_wait(&res_full[1], par);
         }
+        ptx::tc_fence_after_sync();
         for (int n2 = 0; n2 < p.num_n2; ++n2) {
-          ptx::mbar_wait(&acc2_empty[a2], a2_phase ^ 1);
-          const uint32_t d = tmem_acc2 + a2 * BLOCK_N2;
-          for (int kb = 0; kb < (kSC ? 2 : 1); ++kb) {
+          for (int kb = 0; kb < kB2Blocks; ++kb) {
             ptx::mbar_wait(&b_full[bs], bphase);
-            ptx::tc_fence_after_sync();
             const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES);
-            const uint32_t aa = kb == 0 ? a_addr : x_addr;
 #pragma unroll
-            for (int k = 0; k < 64 / UMMA_K; ++k)
-              ptx::umma_bf16_ss(d, desc_sw128(aa + k * 32, 1024), desc_sw128(b_addr + k * 32, 1024), kIdesc2, (kb | k) != 0);
+            for (int h = 0; h < 2; ++h) {
+              if (kb == 0) {
+                ptx::mbar_wait(&acc2_empty[h], acc2_phase[h] ^ 1);
+                acc2_phase[h] ^= 1;
+              }
+              ptx::tc_fence_after_sync();
+              const uint32_t a_addr = ptx::smem_u32((kb == 0 ? smem_a2 : smem_res) + h * CHUNK_BYTES);
+#pragma unroll
+              for (int k = 0; k < 64 / UMMA_K; ++k)
+                ptx::umma_bf16_ss(tmem_acc2 + h * BLOCK_N2, desc_sw128(a_addr + k * 32, 1024), desc_sw128(b_addr + k * 32, 1024),
+                                  kIdesc2, (kb | k) != 0);
+              if (kb == kB2Blocks - 1) ptx::umma_commit(&acc2_full[h]);
+            }
             ptx::umma_commit(&b_empty[bs]);
             next_b();
           }
-          ptx::umma_commit(&acc2_full[a2]);
-          if (++a2 == 2) {
-            a2 = 0;
-            a2_phase ^= 1;
-          }
         }
-        ptx::umma_commit(&a2_free[ab]);
+        ptx::umma_commit(a2_free);
         if (kSC) {
-          ptx::umma_commit(&res_empty[xs]);
-          if (++xs == 2) {
-            xs = 0;
-            xphase ^= 1;
-          }
+          ptx::umma_commit(&res_empty[0]);
+          ptx::umma_commit(&res_empty[1]);
         }
-        if (++ab == 2) {
-          ab = 0;
-          ready_phase ^= 1;
-        }
-      };
-      if (first < n_tiles) g1();
-      for (int t = first; t < n_tiles; t += step) {
-        if (t + step < n_tiles) g1();
-        g2();
       }
     }
   } else if (warp == 2) {
-    // ===================================== residual TMA producer =====================================
+    // ===================================== residual / shortcut-input TMA producer =====================================
     if (lane == 0) {
       ptx::prefetch_tmap(&p.tmR);
-      uint32_t k = 0;   // chunk counter per warpgroup: slot = wg * 2 + (k & 1), parity = (k >> 1) & 1
-      for (int t = first; t < n_tiles; t += step) {
+      uint32_t k = 0, n = 0;   // k: chunk counter per warpgroup: slot = wg * 2 + (k & 1), parity = (k >> 1) & 1
+      for (int t = first; t < n_tiles; t += step, ++n) {
         int b, y0, x0;
         tile_origin(t, b, y0, x0);
-        if (kSC) {   // one block-input tile per output tile, slots 0 / 1 (released by the MMA warp's commit)
-          const int slot = k & 1;
-          ptx::mbar_wait(&res_empty[slot], ((k >> 1) & 1) ^ 1);
-          ptx::mbar_expect_tx(&res_full[slot], CHUNK_BYTES);
-          tma_load_4d(&p.tmR, &res_full[slot], smem_res + slot * CHUNK_BYTES, 0, x0, y0, b);
-          ++k;
+        if (kSC) {   // block-input tile of each half tile (slots 0 / 1, released by the MMA warp's commit)
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&res_empty[h], (n & 1) ^ 1);
+            ptx::mbar_expect_tx(&res_full[h], CHUNK_BYTES);
+            tma_load_4d(&p.tmR, &res_full[h], smem_res + h * CHUNK_BYTES, 0, x0 + h * SUB_W, y0, b);
+          }
           continue;
         }
-        for (int n2 = 0; n2 < p.num_n2; ++n2, ++k) {
-          for (int c = 0; c < 2; ++c) {   // chunk c of the n2 tile belongs to epilogue warpgroup c
-            const int slot = c * 2 + (k & 1);
-            ptx::mbar_wait(&res_empty[slot], ((k >> 1) & 1) ^ 1);
-            ptx::mbar_expect_tx(&res_full[slot], CHUNK_BYTES);
-            tma_load_4d(&p.tmR, &res_full[slot], smem_res + slot * CHUNK_BYTES, n2 * BLOCK_N2 + c * 64, x0, y0, b);
-          }
-        }
+        for (int n2 = 0; n2 < p.num_n2; ++n2)
+          for (int h = 0; h < 2; ++h, ++k)
+            for (int c = 0; c < 2; ++c) {   // chunk c of the n2 tile belongs to epilogue warpgroup c
+              const int slot = c * 2 + (k & 1);
+              ptx::mbar_wait(&res_empty[slot], ((k >> 1) & 1) ^ 1);
+              ptx::mbar_expect_tx(&res_full[slot], CHUNK_BYTES);
+              tma_load_4d(&p.tmR, &res_full[slot], smem_res + slot * CHUNK_BYTES, n2 * BLOCK_N2 + c * 64, x0 + h * SUB_W, y0, b);
+            }
       }
     }
   } else if (warp >= 4) {
@@ -307,113 +277,99 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     const int wg = (warp - 4) >> 2;
     const int et = threadIdx.x - 128 - wg * 128;
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;           // tile row = pixel (row / 8, row % 8) = TMEM lane
+    const int row = quarter * 32 + lane;           // half-tile row = pixel (row / 8, row % 8) = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int bar_id = 1 + wg;
     if (threadIdx.x - 128 < MID) s_bias2[threadIdx.x - 128] = p.bias2[threadIdx.x - 128];
     ptx::named_bar_sync(3, 256);
 
-    int a1 = 0, a2 = 0, ab = 0;
-    uint32_t a1_phase = 0, a2_phase = 0, rk = 0, free_phase = 0;
+    uint32_t rk = 0, n = 0, acc2_phase[2] = {0, 0};
     float* my_bias3 = s_bias3 + wg * 64;
     uint8_t* my_out = smem_out + wg * CHUNK_BYTES;
 
-    auto e1 = [&]() {
-      ptx::mbar_wait(&acc1_full[a1], a1_phase);
-      ptx::mbar_wait(&a2_free[ab], free_phase ^ 1);   // the second GEMM two tiles back no longer reads this A2 buffer
+    for (int t = first; t < n_tiles; t += step, ++n) {
+      int b, y0, x0;
+      tile_origin(t, b, y0, x0);
+      const uint32_t par = n & 1;
+      // ---- E1: warpgroup g converts half tile g: acc1[g] -> +b2, ReLU -> bf16 -> A2[g] ----
+      ptx::mbar_wait(acc1_full, par);
+      ptx::mbar_wait(a2_free, par ^ 1);           // the previous tile's second GEMM no longer reads A2
       ptx::tc_fence_after_sync();
-      uint32_t v[32];
-      ptx::tmem_ld_32x32(tmem_acc1 + lane_addr + a1 * MID + wg * 32, v);   // warpgroup g converts columns [32g, 32g+32)
-      ptx::tmem_ld_wait();
-      uint32_t packed[16];
+      {
+        uint8_t* rowp = smem_a2 + wg * CHUNK_BYTES + row * 128;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float a = fmaxf(__uint_as_float(v[2 * j]) + s_bias2[wg * 32 + 2 * j], 0.f);
-        const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias2[wg * 32 + 2 * j + 1], 0.f);
-        packed[j] = ptx::pack_bf16(a, b);
-      }
-      uint8_t* rowp = smem_a2 + ab * CHUNK_BYTES + row * 128;
+        for (int u = 0; u < 2; ++u) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_acc1 + lane_addr + wg * MID + u * 32, v);
+          ptx::tmem_ld_wait();
+          uint32_t packed[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(rowp + (((wg * 4 + j) ^ (row & 7)) << 4)) =
-            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&acc1_empty[a1]);
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&a2_ready[ab]);
-      if (++ab == 2) {
-        ab = 0;
-        free_phase ^= 1;
-      }
-      if (++a1 == 2) {
-        a1 = 0;
-        a1_phase ^= 1;
-      }
-    };
-
-    auto e2 = [&](int b, int y0, int x0, int n2) {
-      const int n0 = n2 * BLOCK_N2 + wg * 64;
-      if (et < 64) my_bias3[et] = p.bias3[n0 + et];
-      if (et == 0) ptx::tma_store_wait_read<0>();     // my staging box: the previous store has finished reading it
-      ptx::named_bar_sync(bar_id, 128);
-      ptx::mbar_wait(&acc2_full[a2], a2_phase);
-      ptx::tc_fence_after_sync();
-      const uint32_t t_acc = tmem_acc2 + lane_addr + a2 * BLOCK_N2 + wg * 64;
-      uint32_t packed[32];
-      const int rslot = wg * 2 + (rk & 1);
-      const uint8_t* rrow = smem_res + rslot * CHUNK_BYTES + row * 128;
-      if (!kSC) {
-        ptx::mbar_wait(&res_full[rslot], (rk >> 1) & 1);
-        ++rk;
-      }
+          for (int j = 0; j < 16; ++j)
+            packed[j] = ptx::pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + s_bias2[u * 32 + 2 * j], 0.f),
+                                       fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias2[u * 32 + 2 * j + 1], 0.f));
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_acc + h * 32, v);
-        uint4 rr[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          rr[j] = kSC ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(rrow + (((h * 4 + j) ^ (row & 7)) << 4));
-        ptx::tmem_ld_wait();
-        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = fmaxf(__uint_as_float(v[2 * j]) + my_bias3[h * 32 + 2 * j] + ptx::bf16_lo(rw[j]), 0.f);
-          const float bb = fmaxf(__uint_as_float(v[2 * j + 1]) + my_bias3[h * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]), 0.f);
-          packed[h * 16 + j] = ptx::pack_bf16(a, bb);
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(rowp + (((u * 4 + j) ^ (row & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
         }
       }
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&acc2_empty[a2]);
-      if (++a2 == 2) {
-        a2 = 0;
-        a2_phase ^= 1;
-      }
-      __syncwarp();
-      if (!kSC && lane == 0) ptx::mbar_arrive(&res_empty[rslot]);
-      uint8_t* rowp = my_out + row * 128;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
-            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(bar_id, 128);
-      if (et == 0) {
-        tma_store_4d(&p.tmD, my_out, n0, x0, y0, b);
-        ptx::tma_store_commit();
-      }
-    };
+      ptx::mbar_arrive(acc1_empty);
+      ptx::fence_proxy_async_smem();             // A2 is read by the tensor core through the async proxy
+      ptx::mbar_arrive(a2_ready);
 
-    // E1 of the NEXT tile runs before E2 of this one: the second GEMM of the next tile (which needs A2) then overlaps
-    // this tile's HBM-bound output phase instead of stalling the epilogue warps
-    if (first < n_tiles) e1();
-    for (int t = first; t < n_tiles; t += step) {
-      int b, y0, x0;
-      tile_origin(t, b, y0, x0);
-      const int pre = p.num_n2 > 2 ? p.num_n2 - 2 : 0;   // G2 needs both acc2 buffers back for its n2 >= 2 tiles
-      for (int n2 = 0; n2 < pre; ++n2) e2(b, y0, x0, n2);
-      if (t + step < n_tiles) e1();
-      for (int n2 = pre; n2 < p.num_n2; ++n2) e2(b, y0, x0, n2);
+      // ---- E2: (n2, h) in MMA order; warpgroup g owns columns [n2 * 128 + 64 g, + 64) ----
+      for (int n2 = 0; n2 < p.num_n2; ++n2) {
+        const int n0 = n2 * BLOCK_N2 + wg * 64;
+        if (et < 64) my_bias3[et] = p.bias3[n0 + et];
+        for (int h = 0; h < 2; ++h) {
+          if (et == 0) ptx::tma_store_wait_read<0>();     // my staging box: the previous store has finished reading it
+          ptx::named_bar_sync(bar_id, 128);
+          ptx::mbar_wait(&acc2_full[h], acc2_phase[h]);
+          acc2_phase[h] ^= 1;
+          ptx::tc_fence_after_sync();
+          const uint32_t t_acc = tmem_acc2 + lane_addr + h * BLOCK_N2 + wg * 64;
+          uint32_t packed[32];
+          const int rslot = wg * 2 + (rk & 1);
+          const uint8_t* rrow = smem_res + rslot * CHUNK_BYTES + row * 128;
+          if (!kSC) {
+            ptx::mbar_wait(&res_full[rslot], (rk >> 1) & 1);
+            ++rk;
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(t_acc + u * 32, v);
+            uint4 rr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              rr[j] = kSC ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(rrow + (((u * 4 + j) ^ (row & 7)) << 4));
+            ptx::tmem_ld_wait();
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = fmaxf(__uint_as_float(v[2 * j]) + my_bias3[u * 32 + 2 * j] + ptx::bf16_lo(rw[j]), 0.f);
+              const float bb = fmaxf(__uint_as_float(v[2 * j + 1]) + my_bias3[u * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]), 0.f);
+              packed[u * 16 + j] = ptx::pack_bf16(a, bb);
+            }
+          }
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&acc2_empty[h]);
+          __syncwarp();
+          if (!kSC && lane == 0) ptx::mbar_arrive(&res_empty[rslot]);
+          uint8_t* rowp = my_out + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(bar_id, 128);
+          if (et == 0) {
+            tma_store_4d(&p.tmD, my_out, n0, x0 + h * SUB_W, y0, b);
+            ptx::tma_store_commit();
+          }
+        }
+      }
     }
     if (et == 0) ptx::tma_store_wait_all<0>();
   }
@@ -448,8 +404,8 @@ int bneck_halo_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, 
   plan->fused_shortcut = shortcut_in != nullptr;
   const int k2 = shortcut_in ? 2 * MID : MID;
   if (int rc = make_tmap_2d(&plan->tmB2, w3, width, k2, k2, BLOCK_N2)) return rc;
-  if (int rc = make_tmap_nhwc_patch(&plan->tmR, residual, g.B, g.P, g.Q, shortcut_in ? MID : width, TILE_W, TILE_H)) return rc;
-  if (int rc = make_tmap_nhwc_patch(&plan->tmD, y, g.B, g.P, g.Q, width, TILE_W, TILE_H)) return rc;
+  if (int rc = make_tmap_nhwc_patch(&plan->tmR, residual, g.B, g.P, g.Q, shortcut_in ? MID : width, SUB_W, TILE_H)) return rc;
+  if (int rc = make_tmap_nhwc_patch(&plan->tmD, y, g.B, g.P, g.Q, width, SUB_W, TILE_H)) return rc;
   const int tiles = g.B * ((g.P + TILE_H - 1) / TILE_H) * ((g.Q + TILE_W - 1) / TILE_W);
   plan->grid = std::min(tiles, sm_count());
   return OPD_OK;
