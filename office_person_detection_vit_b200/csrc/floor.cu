@@ -52,6 +52,13 @@ __host__ __device__ inline bool point_in_polygon_ref(double x, double y, const d
     if (y > ymin && y <= ymax && x <= xmax) {
       // here p1y != p2y (ymin < ymax), so the reference always (re)computes xinters (:187-189)
 #ifdef __CUDA_ARCH__
+      // vertical edge: `p1x == p2x or ...` is True whatever xinters is; skip the float64 division (same result)
+      if (p1x == p2x) {
+        inside = !inside;
+        p1x = p2x;
+        p1y = p2y;
+        continue;
+      }
       const double xinters =
           __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(y, p1y), __dsub_rn(p2x, p1x)), __dsub_rn(p2y, p1y)), p1x);
 #else
@@ -402,54 +409,90 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
     }
   };
 
-  const long long n_units = (p.N + 127) / 128;
-  const long long w_stride = (long long)gridDim.x * (kFastThreads / 32);
-  long long unit = (long long)blockIdx.x * (kFastThreads / 32) + warp;
+  // ---- main loop: branch-free float32 filter (arithmetic and bound of filter_point above), constants in registers ----
+  const float h0 = p.Hf[0], h1 = p.Hf[1], h2 = p.Hf[2], h3 = p.Hf[3], h4 = p.Hf[4], h5 = p.Hf[5], h6 = p.Hf[6], h7 = p.Hf[7],
+              h8 = p.Hf[8];
+  const float sxy0 = p.Sxy[0], sxy1 = p.Sxy[1], sxy2 = p.Sxy[2], sw0 = p.Sw[0], sw1 = p.Sw[1], sw2 = p.Sw[2];
+  const float gx0 = p.gx0_f, gy0 = p.gy0_f, icw = p.inv_cw_f, ich = p.inv_ch_f, err_max = p.err_max;
+  const float gwf = (float)p.gw, ghf = (float)p.gh, gw1 = (float)(p.gw + 1), gh1 = (float)(p.gh + 1);
+  const int gw = p.gw;
+  const uint8_t* s_grid = t.grid;
+  const int32_t* s_winner = t.class_winner;
+  int32_t* const out_idx = p.zone_idx;
+  const unsigned n_points = (unsigned)p.N;
+  const unsigned n_units = (n_points + 127u) / 128u;
+  const unsigned w_stride = gridDim.x * (kFastThreads / 32);
+  unsigned unit = blockIdx.x * (kFastThreads / 32) + warp;
   // software prefetch: the next unit's two 16-byte loads are in flight while this unit is processed
   float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
-  auto prefetch = [&](long long u) {
-    const long long base = u * 128 + lane * 4;
-    if (u < n_units && base + 4 <= p.N) {
-      na = ldg_stream(reinterpret_cast<const float4*>(in + 2 * base));
-      nb = ldg_stream(reinterpret_cast<const float4*>(in + 2 * base) + 1);
+  auto prefetch = [&](unsigned u) {
+    const unsigned base = u * 128u + lane * 4u;
+    if (u < n_units && base + 4u <= n_points) {
+      const float4* src = reinterpret_cast<const float4*>(in + 2ull * base);
+      na = ldg_stream(src);
+      nb = ldg_stream(src + 1);
     }
   };
   prefetch(unit);
   for (; unit < n_units; unit += w_stride) {
-    const long long base = unit * 128 + lane * 4;
+    const unsigned base = unit * 128u + lane * 4u;
     float xs[4], ys[4];
     int n_live;
-    if (base + 4 <= p.N) {
+    if (base + 4u <= n_points) {
       xs[0] = na.x; ys[0] = na.y; xs[1] = na.z; ys[1] = na.w;
       xs[2] = nb.x; ys[2] = nb.y; xs[3] = nb.z; ys[3] = nb.w;
       n_live = 4;
     } else {
-      n_live = base < p.N ? (int)(p.N - base) : 0;
+      n_live = base < n_points ? (int)(n_points - base) : 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        xs[j] = j < n_live ? in[2 * (base + j) + 0] : 0.f;
-        ys[j] = j < n_live ? in[2 * (base + j) + 1] : 0.f;
+        xs[j] = j < n_live ? in[2ull * (base + j) + 0] : 0.f;
+        ys[j] = j < n_live ? in[2ull * (base + j) + 1] : 0.f;
       }
     }
     prefetch(unit + w_stride);
     int zi[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int code = j < n_live ? filter_point(p, t.grid, xs[j], ys[j]) : -2;
-      const bool slow = code == -1;
+      const float x = xs[j], y = ys[j];
+      const float X = fmaf(h0, x, fmaf(h1, y, h2));
+      const float Y = fmaf(h3, x, fmaf(h4, y, h5));
+      const float W = fmaf(h6, x, fmaf(h7, y, h8));
+      const float r = rcp_approx(W);
+      const float px = X * r, py = Y * r;
+      const float ax = fabsf(x), ay = fabsf(y);
+      const float sxy = fmaf(sxy0, ax, fmaf(sxy1, ay, sxy2));
+      const float sw = fmaf(sw0, ax, fmaf(sw1, ay, sw2));
+      const float pm = fmaxf(fabsf(px), fabsf(py));
+      const float err = (16.0f * 5.9604645e-8f) * fmaf(fabsf(r), fmaf(pm, sw, sxy), pm);
+      const float fx = (px - gx0) * icw, fy = (py - gy0) * ich;
+      const float ex = err * icw, ey = err * ich;
+      // the whole error box misses the (margin-padded) grid: certainly no zone
+      const bool outside = (fx + ex < -1.0f) | (fx - ex > gw1) | (fy + ey < -1.0f) | (fy - ey > gh1);
+      const bool err_ok = err <= err_max;                                        // false for NaN / inf
+      const bool in_grid = (fx >= 0.0f) & (fx < gwf) & (fy >= 0.0f) & (fy < ghf);
+      const bool live = j < n_live;
+      int code = kBoundary;
+      if (in_grid) code = s_grid[(int)fy * gw + (int)fx];
+      const bool bnd = code == kBoundary;
+      // exact path: bound too loose, or a boundary cell; not for points that certainly miss every zone
+      const bool slow = live & !outside & (!err_ok | (in_grid & bnd));
+      const bool fast = live & err_ok & in_grid & !bnd & !outside;
+      int z = -1;
+      if (fast) z = s_winner[code];
+      zi[j] = z;
       const unsigned sb = __ballot_sync(0xffffffffu, slow);
       if (sb) {
-        if (slow) q[qn + __popc(sb & lt_mask)] = (unsigned)(base + j);
+        if (slow) q[qn + __popc(sb & lt_mask)] = base + j;
         qn += __popc(sb);
       }
-      zi[j] = code >= 0 ? t.class_winner[code] : -1;
-      if (do_hist) wc.add<kWide>(zi[j]);
+      if (do_hist) wc.add<kWide>(z);
     }
-    if (p.zone_idx) {
+    if (out_idx) {
       if (n_live == 4) {
-        *reinterpret_cast<int4*>(p.zone_idx + base) = make_int4(zi[0], zi[1], zi[2], zi[3]);
+        *reinterpret_cast<int4*>(out_idx + base) = make_int4(zi[0], zi[1], zi[2], zi[3]);
       } else {
-        for (int j = 0; j < n_live; ++j) p.zone_idx[base + j] = zi[j];
+        for (int j = 0; j < n_live; ++j) out_idx[base + j] = zi[j];
       }
     }
     __syncwarp();  // queue entries and placeholder stores are ordered before the drain's loads / stores
