@@ -275,7 +275,7 @@ def main_gpu(args) -> None:
 
     # ---- roofline of the dominant kernel (tc_gemm_kernel: every convolution and linear layer), CUDA events between launches ----
     pk, pk_kind = peaks()
-    step(frames)
+    pipe.run_tensors(frames, hist=hist, slot_base=rank * B)   # local only: the other ranks have left, no collective here
     torch.cuda.synchronize()
     profs = [det.model.profile() for _ in range(3)]
     n_steps = len(profs[0])
