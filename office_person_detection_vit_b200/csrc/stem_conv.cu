@@ -163,18 +163,18 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
       ptx::mbar_wait(w_full, 0);
       int ps = 0, as = 0;
       uint32_t pphase = 0, aphase = 0;
-      const uint32_t w_addr = ptx::smem_u32(smem_w);
+      const uint64_t w0 = desc_sw32(ptx::smem_u32(smem_w), 256);
       for (int t = first; t < n_tiles; t += step) {
         ptx::mbar_wait(&acc_empty[as], aphase ^ 1);
         ptx::mbar_wait(&patch_full[ps], pphase);
         ptx::tc_fence_after_sync();
         const uint32_t d = tmem_base + as * 64;
-        const uint32_t patch = ptx::smem_u32(smem_patch + ps * PATCH_SLOT);
+        // descriptors differ only in the 16-byte-granular start address field: base descriptor + constant per tap
+        const uint64_t a0 = desc_sw32(ptx::smem_u32(smem_patch + ps * PATCH_SLOT), PATCH_W * 32);
 #pragma unroll
         for (int tap = 0; tap < 16; ++tap) {
           const int r = tap >> 2, s = tap & 3;
-          ptx::umma_bf16_ss(d, desc_sw32(patch + (r * PATCH_W + s) * 32, PATCH_W * 32), desc_sw32(w_addr + tap * W_TAP_BYTES, 256),
-                            kIdesc, tap != 0);
+          ptx::umma_bf16_ss(d, a0 + (uint64_t)(((r * PATCH_W + s) * 32) >> 4), w0 + (uint64_t)((tap * W_TAP_BYTES) >> 4), kIdesc, tap != 0);
         }
         ptx::umma_commit(&patch_empty[ps]);
         ptx::umma_commit(&acc_full[as]);

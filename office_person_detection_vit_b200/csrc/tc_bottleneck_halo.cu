@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           bphase ^= 1;
         }
       };
-      const uint32_t patch = ptx::smem_u32(smem_patch);
+      const uint64_t patch_desc = desc_sw128(ptx::smem_u32(smem_patch), PATCH_W * 128);
       for (int t = first; t < n_tiles; t += step, ++n) {
         const uint32_t par = n & 1;
         // ---- G1: both half tiles, every W2 tap tile used twice ----
@@ -195,15 +195,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           ptx::tc_fence_after_sync();
           for (int tap = tap0; tap < tap0 + 2 && tap < 9; ++tap) {
             const int r = tap / 3, s = tap - r * 3;
-            const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES + (tap - tap0) * (MID * 128));
+            // descriptors differ only in the 16-byte-granular start address field: base descriptor + small offsets
+            const uint64_t db = desc_sw128(ptx::smem_u32(smem_b + bs * CHUNK_BYTES + (tap - tap0) * (MID * 128)), 1024);
+            const uint64_t da = patch_desc + (uint64_t)(((r * PATCH_W + s) * 128) >> 4);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t a_addr = patch + (r * PATCH_W + s + h * SUB_W) * 128;
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
               for (int k = 0; k < 64 / UMMA_K; ++k)
-                ptx::umma_bf16_ss(tmem_acc1 + h * MID, desc_sw128(a_addr + k * 32, PATCH_W * 128), desc_sw128(b_addr + k * 32, 1024),
-                                  kIdesc1, (tap | k) != 0);
-            }
+                ptx::umma_bf16_ss(tmem_acc1 + h * MID, da + (uint64_t)((h * SUB_W * 128 + k * 32) >> 4), db + (uint64_t)(2 * k), kIdesc1,
+                                  (tap | k) != 0);
           }
           ptx::umma_commit(&b_empty[bs]);
           next_b();
@@ -228,11 +228,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
                 acc2_phase[h] ^= 1;
               }
               ptx::tc_fence_after_sync();
-              const uint32_t a_addr = ptx::smem_u32((kb == 0 ? smem_a2 : smem_res) + h * CHUNK_BYTES);
+              const uint64_t da = desc_sw128(ptx::smem_u32((kb == 0 ? smem_a2 : smem_res) + h * CHUNK_BYTES), 1024);
+              const uint64_t db = desc_sw128(b_addr, 1024);
 #pragma unroll
               for (int k = 0; k < 64 / UMMA_K; ++k)
-                ptx::umma_bf16_ss(tmem_acc2 + h * BLOCK_N2, desc_sw128(a_addr + k * 32, 1024), desc_sw128(b_addr + k * 32, 1024),
-                                  kIdesc2, (kb | k) != 0);
+                ptx::umma_bf16_ss(tmem_acc2 + h * BLOCK_N2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | k) != 0);
               if (kb == kB2Blocks - 1) ptx::umma_commit(&acc2_full[h]);
             }
             ptx::umma_commit(&b_empty[bs]);
