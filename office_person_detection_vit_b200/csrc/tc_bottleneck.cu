@@ -301,7 +301,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     auto e2 = [&](int m_blk, int n2) {
       const int m0 = m_blk * BLOCK_M, n0 = n2 * BLOCK_N2 + wg * 64;
       if (et < 64) my_bias3[et] = p.bias3[n0 + et];
-      if (et == 0) ptx::tma_store_wait_read<0>();     // my staging box: the previous store has finished reading it
       ptx::named_bar_sync(bar_id, 128);
       ptx::mbar_wait(&acc2_full[a2], a2_phase);
       ptx::tc_fence_after_sync();
@@ -336,6 +335,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&res_empty[rs]);
+      // my staging box: its previous TMA store must have finished reading it (waited for here, after the arithmetic)
+      if (et == 0) ptx::tma_store_wait_read<0>();
+      ptx::named_bar_sync(bar_id, 128);
       uint8_t* buf = my_out;
       uint8_t* rowp = buf + row * 128;
 #pragma unroll
@@ -385,7 +387,7 @@ int launch_t(const BneckParams& p, int grid, cudaStream_t s) {
 
 int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
                const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y) {
-  if (g_option_bneck_halo.load() && g.C == 64 && g.stride == 1 && g.KH == 3 && g.KW == 3 && g.pad_h == 1 && g.pad_w == 1)
+  if (g_option_bneck_halo.load() && (g.C == 64 || (g.C == 128 && g_option_bneck_halo.load() > 1)) && g.stride == 1 && g.KH == 3 && g.KW == 3 && g.pad_h == 1 && g.pad_w == 1)
     return bneck_halo_plan(plan, x, g, w2, bias2, w3, bias3, width, residual, y);
   *plan = BneckPlan{};
   OPD_REQUIRE(g.KH == 3 && g.KW == 3 && (g.C == 64 || g.C == 128), "bottleneck tail: 3x3 convolution over 64 or 128 channels (C=%d)", g.C);

@@ -20,18 +20,29 @@
 namespace opd {
 namespace {
 
-constexpr int MID = 64;
 constexpr int BLOCK_M = 128, BLOCK_N2 = 128, UMMA_K = 16;
 constexpr int SUB_W = 8, TILE_W = 16, TILE_H = 16, PATCH_W = TILE_W + 2, PATCH_H = TILE_H + 2;
 constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 128;   // 41472
 constexpr int PATCH_SLOT = 41984;                      // 41 KB
 constexpr int CHUNK_BYTES = BLOCK_M * 64 * 2;          // 16 KB: one [128 x 64] bf16 box
-constexpr int kBStages = 3, kResStages = 4;
+constexpr int kBStages = 3;
 constexpr int kThreads = 384;
-constexpr int kSmemBytes = PATCH_SLOT + kBStages * CHUNK_BYTES + 2 * CHUNK_BYTES /*A2[h]*/ + 2 * CHUNK_BYTES /*staging*/ +
-                           kResStages * CHUNK_BYTES + 2048;
-static_assert(kSmemBytes <= 232448, "shared memory budget");
-constexpr int kTmemCols = 512;   // acc1[h] 2 x 64 + acc2[h] 2 x 128
+constexpr int kTmemCols = 512;   // acc1[h] 2 x MID + acc2[h] 2 x 128
+// MID = 64: A2[h] one chunk each, residual 2 slots per warpgroup.  MID = 128 (stage 2): two 64-channel patch slabs per
+// tile through the same patch buffer, A2[h] two chunks each, residual 1 slot per warpgroup.  Same shared-memory total.
+template <int MID>
+struct HaloCfg {
+  static constexpr int kCB = MID / 64;                    // 64-channel blocks
+  static constexpr int kA2Chunks = 2 * kCB;               // both half tiles
+  static constexpr int kResStages = MID == 64 ? 4 : 2;
+  static constexpr int kResPerWg = kResStages / 2;
+  static constexpr int kTapBytes = MID * 128;             // one W2 tap tile [MID x 64] bf16
+  static constexpr int kTapsPerSlot = CHUNK_BYTES / kTapBytes;
+  static constexpr int kSmemBytes = PATCH_SLOT + kBStages * CHUNK_BYTES + kA2Chunks * CHUNK_BYTES + 2 * CHUNK_BYTES /*staging*/ +
+                                    kResStages * CHUNK_BYTES + 2048;
+  static_assert(MID == 64 || MID == 128, "halo bottleneck tail: MID must be 64 or 128");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
 
 struct HaloParams {
   CUtensorMap tmA, tmB1, tmB2, tmR, tmD;
@@ -64,20 +75,23 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr, uint32_t sbo_bytes
 
 // kSC: the block's 1x1 projection shortcut is computed here too (second k-block of the second GEMM: the block input
 // tile times Wsc), so the residual tensor is neither written by a separate kernel nor read back.
-template <bool kSC>
+template <int MID, bool kSC>
 __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid_constant__ HaloParams p) {
+  using C = HaloCfg<MID>;
+  constexpr int kCB = C::kCB, kResStages = C::kResStages, kResPerWg = C::kResPerWg;
   constexpr uint32_t kIdesc1 = ptx::umma_idesc_bf16(BLOCK_M, MID);
   constexpr uint32_t kIdesc2 = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N2);
-  constexpr int kB2Blocks = kSC ? 2 : 1;   // k-blocks of the second GEMM: [W3 | Wsc]
+  constexpr int kB2Blocks = kCB + (kSC ? 1 : 0);   // k-blocks of the second GEMM: W3 (kCB) [+ Wsc]
+  static_assert(!kSC || MID == 64, "fused shortcut: 64-channel blocks only");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_patch = smem;                                      // one halo patch (the next one loads during E2)
   uint8_t* smem_b = smem_patch + PATCH_SLOT;                       // [kBStages] W2 tap pairs / W3 tiles
-  uint8_t* smem_a2 = smem_b + kBStages * CHUNK_BYTES;              // [2] A operand of the second GEMM, one per half tile
-  uint8_t* smem_out = smem_a2 + 2 * CHUNK_BYTES;                   // one staging box per epilogue warpgroup
-  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;                  // residual: 2 slots per warpgroup; kSC: X[h] in slots 0, 1
-  float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [64]
-  float* s_bias3 = s_bias2 + 64;                                                    // [128]
+  uint8_t* smem_a2 = smem_b + kBStages * CHUNK_BYTES;              // [2 halves][kCB chunks] A operand of the second GEMM
+  uint8_t* smem_out = smem_a2 + C::kA2Chunks * CHUNK_BYTES;        // one staging box per epilogue warpgroup
+  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;                  // residual slots per warpgroup; kSC: X[h] in slots 0, 1
+  float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [MID]
+  float* s_bias3 = s_bias2 + 128;                                                   // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 128);
   uint64_t* patch_full = bars;          // [1]
   uint64_t* patch_empty = bars + 1;     // [1]
@@ -142,29 +156,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int bs = 0;
-      uint32_t bphase = 0, n = 0;
+      uint32_t bphase = 0, pc = 0;
       auto next_b = [&]() {
         if (++bs == kBStages) {
           bs = 0;
           bphase ^= 1;
         }
       };
-      for (int t = first; t < n_tiles; t += step, ++n) {
+      for (int t = first; t < n_tiles; t += step) {
         int b, y0, x0;
         tile_origin(t, b, y0, x0);
-        ptx::mbar_wait(patch_empty, (n & 1) ^ 1);
-        ptx::mbar_expect_tx(patch_full, PATCH_BYTES);
-        tma_load_4d(&p.tmA, patch_full, smem_patch, 0, x0 - 1, y0 - 1, b);
-        for (int tap = 0; tap < 9; tap += 2) {   // two 8 KB tap tiles of W2 per 16 KB slot (the last slot holds one)
-          const int n_taps = tap + 1 < 9 ? 2 : 1;
-          ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
-          ptx::mbar_expect_tx(&b_full[bs], n_taps * MID * 128);
-          for (int j = 0; j < n_taps; ++j)
-            ptx::tma_load_2d(&p.tmB1, &b_full[bs], smem_b + bs * CHUNK_BYTES + j * (MID * 128), (tap + j) * 64, 0);
-          next_b();
+        for (int cb = 0; cb < kCB; ++cb, ++pc) {
+          ptx::mbar_wait(patch_empty, (pc & 1) ^ 1);
+          ptx::mbar_expect_tx(patch_full, PATCH_BYTES);
+          tma_load_4d(&p.tmA, patch_full, smem_patch, cb * 64, x0 - 1, y0 - 1, b);
+          for (int tap = 0; tap < 9; tap += C::kTapsPerSlot) {   // W2 tap tiles [MID x 64]: two per 16 KB slot when MID = 64
+            const int n_taps = tap + C::kTapsPerSlot <= 9 ? C::kTapsPerSlot : 9 - tap;
+            ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
+            ptx::mbar_expect_tx(&b_full[bs], n_taps * C::kTapBytes);
+            for (int j = 0; j < n_taps; ++j)
+              ptx::tma_load_2d(&p.tmB1, &b_full[bs], smem_b + bs * CHUNK_BYTES + j * C::kTapBytes, (tap + j) * MID + cb * 64, 0);
+            next_b();
+          }
         }
         for (int n2 = 0; n2 < p.num_n2; ++n2)
-          for (int kb = 0; kb < kB2Blocks; ++kb) {   // kb 1: the shortcut weights (columns 64..127 of [W3 | Wsc])
+          for (int kb = 0; kb < kB2Blocks; ++kb) {   // kb >= kCB: the shortcut weights (last 64 columns of [W3 | Wsc])
             ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
             ptx::mbar_expect_tx(&b_full[bs], CHUNK_BYTES);
             ptx::tma_load_2d(&p.tmB2, &b_full[bs], smem_b + bs * CHUNK_BYTES, kb * 64, n2 * BLOCK_N2);
@@ -176,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
       int bs = 0;
-      uint32_t bphase = 0, n = 0, acc2_phase[2] = {0, 0};
+      uint32_t bphase = 0, n = 0, pc = 0, acc2_phase[2] = {0, 0};
       auto next_b = [&]() {
         if (++bs == kBStages) {
           bs = 0;
@@ -186,29 +202,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       const uint64_t patch_desc = desc_sw128(ptx::smem_u32(smem_patch), PATCH_W * 128);
       for (int t = first; t < n_tiles; t += step, ++n) {
         const uint32_t par = n & 1;
-        // ---- G1: both half tiles, every W2 tap tile used twice ----
+        // ---- G1: both half tiles, every W2 tap tile used twice; one 64-channel patch slab at a time ----
         ptx::mbar_wait(acc1_empty, par ^ 1);
-        ptx::mbar_wait(patch_full, par);
-        ptx::tc_fence_after_sync();
-        for (int tap0 = 0; tap0 < 9; tap0 += 2) {
-          ptx::mbar_wait(&b_full[bs], bphase);
+        for (int cb = 0; cb < kCB; ++cb, ++pc) {
+          ptx::mbar_wait(patch_full, pc & 1);
           ptx::tc_fence_after_sync();
-          for (int tap = tap0; tap < tap0 + 2 && tap < 9; ++tap) {
-            const int r = tap / 3, s = tap - r * 3;
-            // descriptors differ only in the 16-byte-granular start address field: base descriptor + small offsets
-            const uint64_t db = desc_sw128(ptx::smem_u32(smem_b + bs * CHUNK_BYTES + (tap - tap0) * (MID * 128)), 1024);
-            const uint64_t da = patch_desc + (uint64_t)(((r * PATCH_W + s) * 128) >> 4);
+          for (int tap0 = 0; tap0 < 9; tap0 += C::kTapsPerSlot) {
+            ptx::mbar_wait(&b_full[bs], bphase);
+            ptx::tc_fence_after_sync();
+            for (int tap = tap0; tap < tap0 + C::kTapsPerSlot && tap < 9; ++tap) {
+              const int r = tap / 3, s = tap - r * 3;
+              // descriptors differ only in the 16-byte-granular start address field: base descriptor + small offsets
+              const uint64_t db = desc_sw128(ptx::smem_u32(smem_b + bs * CHUNK_BYTES + (tap - tap0) * C::kTapBytes), 1024);
+              const uint64_t da = patch_desc + (uint64_t)(((r * PATCH_W + s) * 128) >> 4);
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+              for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int k = 0; k < 64 / UMMA_K; ++k)
-                ptx::umma_bf16_ss(tmem_acc1 + h * MID, da + (uint64_t)((h * SUB_W * 128 + k * 32) >> 4), db + (uint64_t)(2 * k), kIdesc1,
-                                  (tap | k) != 0);
+                for (int k = 0; k < 64 / UMMA_K; ++k)
+                  ptx::umma_bf16_ss(tmem_acc1 + h * MID, da + (uint64_t)((h * SUB_W * 128 + k * 32) >> 4), db + (uint64_t)(2 * k), kIdesc1,
+                                    (cb | tap | k) != 0);
+            }
+            ptx::umma_commit(&b_empty[bs]);
+            next_b();
           }
-          ptx::umma_commit(&b_empty[bs]);
-          next_b();
+          ptx::umma_commit(patch_empty);   // the slab may be overwritten once these MMAs have read it
         }
-        ptx::umma_commit(patch_empty);
         ptx::umma_commit(acc1_full);
         // ---- G2: per n2 tile both half tiles share the W3 (and Wsc) tile ----
         ptx::mbar_wait(a2_ready, par);
@@ -228,7 +246,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
                 acc2_phase[h] ^= 1;
               }
               ptx::tc_fence_after_sync();
-              const uint64_t da = desc_sw128(ptx::smem_u32((kb == 0 ? smem_a2 : smem_res) + h * CHUNK_BYTES), 1024);
+              const uint64_t da = desc_sw128(
+                  ptx::smem_u32(kb < kCB ? smem_a2 + (h * kCB + kb) * CHUNK_BYTES : smem_res + h * CHUNK_BYTES), 1024);
               const uint64_t db = desc_sw128(b_addr, 1024);
 #pragma unroll
               for (int k = 0; k < 64 / UMMA_K; ++k)
@@ -265,8 +284,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
         for (int n2 = 0; n2 < p.num_n2; ++n2)
           for (int h = 0; h < 2; ++h, ++k)
             for (int c = 0; c < 2; ++c) {   // chunk c of the n2 tile belongs to epilogue warpgroup c
-              const int slot = c * 2 + (k & 1);
-              ptx::mbar_wait(&res_empty[slot], ((k >> 1) & 1) ^ 1);
+              const int slot = c * kResPerWg + (k % kResPerWg);
+              ptx::mbar_wait(&res_empty[slot], ((k / kResPerWg) & 1) ^ 1);
               ptx::mbar_expect_tx(&res_full[slot], CHUNK_BYTES);
               tma_load_4d(&p.tmR, &res_full[slot], smem_res + slot * CHUNK_BYTES, n2 * BLOCK_N2 + c * 64, x0 + h * SUB_W, y0, b);
             }
@@ -280,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     const int row = quarter * 32 + lane;           // half-tile row = pixel (row / 8, row % 8) = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int bar_id = 1 + wg;
-    if (threadIdx.x - 128 < MID) s_bias2[threadIdx.x - 128] = p.bias2[threadIdx.x - 128];
+    if (threadIdx.x - 128 < MID) s_bias2[threadIdx.x - 128] = p.bias2[threadIdx.x - 128];   // 256 epilogue threads >= MID
     ptx::named_bar_sync(3, 256);
 
     uint32_t rk = 0, n = 0, acc2_phase[2] = {0, 0};
@@ -296,9 +315,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       ptx::mbar_wait(a2_free, par ^ 1);           // the previous tile's second GEMM no longer reads A2
       ptx::tc_fence_after_sync();
       {
-        uint8_t* rowp = smem_a2 + wg * CHUNK_BYTES + row * 128;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < MID / 32; ++u) {   // 32-column units: chunk u / 2, half u % 2
           uint32_t v[32];
           ptx::tmem_ld_32x32(tmem_acc1 + lane_addr + wg * MID + u * 32, v);
           ptx::tmem_ld_wait();
@@ -307,9 +325,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           for (int j = 0; j < 16; ++j)
             packed[j] = ptx::pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + s_bias2[u * 32 + 2 * j], 0.f),
                                        fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias2[u * 32 + 2 * j + 1], 0.f));
+          uint8_t* rowp = smem_a2 + (wg * kCB + (u >> 1)) * CHUNK_BYTES + row * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(rowp + (((u * 4 + j) ^ (row & 7)) << 4)) =
+            *reinterpret_cast<uint4*>(rowp + ((((u & 1) * 4 + j) ^ (row & 7)) << 4)) =
                 make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
         }
       }
@@ -322,18 +341,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       for (int n2 = 0; n2 < p.num_n2; ++n2) {
         const int n0 = n2 * BLOCK_N2 + wg * 64;
         if (et < 64) my_bias3[et] = p.bias3[n0 + et];
+        ptx::named_bar_sync(bar_id, 128);                 // bias slice visible to the warpgroup
         for (int h = 0; h < 2; ++h) {
-          if (et == 0) ptx::tma_store_wait_read<0>();     // my staging box: the previous store has finished reading it
-          ptx::named_bar_sync(bar_id, 128);
           ptx::mbar_wait(&acc2_full[h], acc2_phase[h]);
           acc2_phase[h] ^= 1;
           ptx::tc_fence_after_sync();
           const uint32_t t_acc = tmem_acc2 + lane_addr + h * BLOCK_N2 + wg * 64;
           uint32_t packed[32];
-          const int rslot = wg * 2 + (rk & 1);
+          const int rslot = wg * kResPerWg + (rk % kResPerWg);
           const uint8_t* rrow = smem_res + rslot * CHUNK_BYTES + row * 128;
           if (!kSC) {
-            ptx::mbar_wait(&res_full[rslot], (rk >> 1) & 1);
+            ptx::mbar_wait(&res_full[rslot], (rk / kResPerWg) & 1);
             ++rk;
           }
 #pragma unroll
@@ -357,6 +375,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           ptx::mbar_arrive(&acc2_empty[h]);
           __syncwarp();
           if (!kSC && lane == 0) ptx::mbar_arrive(&res_empty[rslot]);
+          // my staging box: its previous TMA store must have finished READING it; the wait sits here, after the TMEM loads
+          // and the arithmetic, so that the store engine's read overlaps them instead of stalling the warpgroup
+          if (et == 0) ptx::tma_store_wait_read<0>();
+          ptx::named_bar_sync(bar_id, 128);
           uint8_t* rowp = my_out + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -388,8 +410,11 @@ int bneck_halo_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, 
                     const __nv_bfloat16* shortcut_in) {
   *plan = BneckPlan{};
   if (shortcut_in) residual = shortcut_in;
-  OPD_REQUIRE(g.KH == 3 && g.KW == 3 && g.C == MID && g.stride == 1 && g.pad_h == 1 && g.pad_w == 1 && g.P == g.H && g.Q == g.W,
-              "bottleneck tail (halo): 3x3 / stride 1 / pad 1 over 64 channels only");
+  const int MID = g.C;
+  OPD_REQUIRE(g.KH == 3 && g.KW == 3 && (MID == 64 || MID == 128) && g.stride == 1 && g.pad_h == 1 && g.pad_w == 1 && g.P == g.H &&
+                  g.Q == g.W,
+              "bottleneck tail (halo): 3x3 / stride 1 / pad 1 over 64 or 128 channels only");
+  OPD_REQUIRE(!shortcut_in || MID == 64, "bottleneck tail (halo): fused shortcut needs 64 channels");
   OPD_REQUIRE(width % BLOCK_N2 == 0 && width > 0, "bottleneck tail (halo): width=%d must be a multiple of 128", width);
   OPD_REQUIRE(bias2 && bias3 && residual && y && x && w2 && w3, "bottleneck tail (halo): NULL argument");
   plan->halo = 1;
@@ -422,14 +447,17 @@ int bneck_halo_launch(const BneckPlan& plan, cudaStream_t stream) {
   p.bias3 = plan.bias3;
   static bool configured = false;
   if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<128>::kSmemBytes));
     configured = true;
   }
-  if (plan.fused_shortcut)
-    tc_bneck_halo_kernel<true><<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
+  if (plan.mid == 128)
+    tc_bneck_halo_kernel<128, false><<<plan.grid, kThreads, HaloCfg<128>::kSmemBytes, stream>>>(p);
+  else if (plan.fused_shortcut)
+    tc_bneck_halo_kernel<64, true><<<plan.grid, kThreads, HaloCfg<64>::kSmemBytes, stream>>>(p);
   else
-    tc_bneck_halo_kernel<false><<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
+    tc_bneck_halo_kernel<64, false><<<plan.grid, kThreads, HaloCfg<64>::kSmemBytes, stream>>>(p);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

@@ -128,7 +128,7 @@ def test_attention(T, B, Lq, Lk, tc):
     (3, 33, 47, 64, 256, 1),
     (4, 100, 167, 128, 512, 1),
 ])
-@pytest.mark.parametrize("halo", [1, 0])
+@pytest.mark.parametrize("halo", [2, 1, 0])
 def test_fused_bottleneck_tail(T, B, H, W, mid, width, stride, halo):
     """conv3x3 + ReLU -> (bf16 in shared memory) -> conv1x1 + bias + residual + ReLU in one kernel; halo = 1 uses the
     halo-patch variant where it applies (64 channels, stride 1), halo = 0 the im2col variant everywhere."""
