@@ -36,7 +36,8 @@ struct Cfg {
   static constexpr int kA2Chunks = MID / 64;
   static constexpr int kResStages = 4;                               // two residual chunk slots per epilogue warpgroup
   static constexpr int kStageBytes = 2 * CHUNK_BYTES;               // A slot 16 KB + B slot 16 KB (B1: MID x 64, B2: 128 x 64)
-  static constexpr int kFixed = (kA2Chunks + 2 + kResStages) * CHUNK_BYTES + 2048;
+  static constexpr int kB2Stages = 2;                                // ring of W3 tiles (second GEMM), fed by its own producer
+  static constexpr int kFixed = (kA2Chunks + kResStages + kB2Stages) * CHUNK_BYTES + 2048;   // residual slots double as output staging
   static constexpr int kStages = (kSmemBudget - kFixed) / kStageBytes > 6 ? 6 : (kSmemBudget - kFixed) / kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
   static constexpr int kTmemCols = 512;                             // acc1 2 x MID + acc2 2 x 128
@@ -51,7 +52,17 @@ struct BneckParams {
   int KW, stride, pad_h, pad_w, P, Q;
   const float* bias2;
   const float* bias3;
+  unsigned long long* trace;   // debug timeline (CTA 0): [0] = count, then (event id << 48 | globaltimer ns) records
 };
+
+__device__ __forceinline__ void trace_ev(unsigned long long* tr, int id) {
+  if (tr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(tr, 1ull);
+    if (i < 4000) tr[1 + i] = ((unsigned long long)id << 48) | (t & 0xFFFFFFFFFFFFull);
+  }
+}
 
 template <int MID>
 __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_constant__ BneckParams p) {
@@ -66,9 +77,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;                                    // ring: A slots
   uint8_t* smem_b = smem_a + kStages * CHUNK_BYTES;          // ring: B slots
-  uint8_t* smem_a2 = smem_b + kStages * CHUNK_BYTES;         // A operand of the second GEMM
-  uint8_t* smem_out = smem_a2 + C::kA2Chunks * CHUNK_BYTES;  // one output staging box per epilogue warpgroup
-  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;            // residual slots
+  uint8_t* smem_b2 = smem_b + kStages * CHUNK_BYTES;         // ring: W3 tiles of the second GEMM
+  uint8_t* smem_a2 = smem_b2 + C::kB2Stages * CHUNK_BYTES;   // A operand of the second GEMM
+  uint8_t* smem_res = smem_a2 + C::kA2Chunks * CHUNK_BYTES;  // residual slots; the output chunk is written in place and stored from there
   float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [MID]
   float* s_bias3 = s_bias2 + 128;                                                   // [128] of the current n2 tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 128);
@@ -82,7 +93,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
   uint64_t* a2_free = bars + 25;              // [1]
   uint64_t* res_full = bars + 26;             // [4]
   uint64_t* res_empty = bars + 30;            // [4]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 34);
+  uint64_t* b2_full = bars + 34;              // [2]
+  uint64_t* b2_empty = bars + 36;             // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 38);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -104,9 +117,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     }
     ptx::mbar_init(a2_ready, 256);
     ptx::mbar_init(a2_free, 1);
+    for (int i = 0; i < C::kB2Stages; ++i) {
+      ptx::mbar_init(&b2_full[i], 1);
+      ptx::mbar_init(&b2_empty[i], 1);
+    }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&res_full[i], 1);
-      ptx::mbar_init(&res_empty[i], 4);
+      ptx::mbar_init(&res_empty[i], 1);   // released by the warpgroup's store thread once the TMA store has read the slot
     }
     ptx::fence_barrier_init();
   }
@@ -149,84 +166,115 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
           advance();
         }
       };
-      auto load_g2 = [&]() {
+      for (int t = first; t < n_mblk; t += step) load_g1(t);
+    }
+  } else if (warp == 3) {
+    // ===================================== W3 tile producer (second GEMM) =====================================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = first; t < n_mblk; t += step)
         for (int n2 = 0; n2 < p.num_n2; ++n2)
           for (int kb = 0; kb < kCBlocks; ++kb) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            ptx::mbar_expect_tx(&full_bar[stage], CHUNK_BYTES);
-            ptx::tma_load_2d(&p.tmB2, &full_bar[stage], smem_b + stage * CHUNK_BYTES, kb * BLOCK_K, n2 * BLOCK_N2);
-            advance();
+            ptx::mbar_wait(&b2_empty[st], ph ^ 1);
+            ptx::mbar_expect_tx(&b2_full[st], CHUNK_BYTES);
+            ptx::tma_load_2d(&p.tmB2, &b2_full[st], smem_b2 + st * CHUNK_BYTES, kb * BLOCK_K, n2 * BLOCK_N2);
+            if (++st == C::kB2Stages) {
+              st = 0;
+              ph ^= 1;
+            }
           }
-      };
-      if (first < n_mblk) load_g1(first);
-      for (int t = first; t < n_mblk; t += step) {
-        if (t + step < n_mblk) load_g1(t + step);
-        load_g2();
-      }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
+    // One thread interleaves two streams of work so that neither blocks the other:
+    //   G1(i1): the 3x3 convolution of this CTA's tile number i1 (L2 -> SM bound: 18 x 32 KB through the main ring),
+    //   G2(i2): the 1x1 expansion of tile i2 <= i1 (paced by the epilogue: it needs A2 from E1 and free acc2 buffers).
+    // G2 steps have priority (they unblock the epilogue); whenever G2 cannot advance, G1 of the next tile keeps the ring
+    // draining, so the fabric-bound phase of tile i+1 overlaps the HBM / epilogue-bound phase of tile i.
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() {
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      };
-      int a1 = 0, a2 = 0;
-      uint32_t a1_phase = 0, a2_phase = 0, ready_phase = 0;
-      auto g1 = [&]() {
-        ptx::mbar_wait(&acc1_empty[a1], a1_phase ^ 1);
-        ptx::tc_fence_after_sync();
-        const uint32_t d = tmem_acc1 + a1 * MID;
-        for (int kb = 0; kb < kK1Blocks; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after_sync();
-          const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a + stage * CHUNK_BYTES));
-          const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * CHUNK_BYTES));
+      const int n_my = first < n_mblk ? (n_mblk - first + step - 1) / step : 0;
+      int i1 = 0, kb1 = 0, stage = 0, a1 = 0;          // G1 cursor, main ring, acc1 buffer
+      uint32_t phase = 0, a1_phase = 0;
+      bool acc1_ok = false;
+      int i2 = 0, n2 = 0, kb2 = 0, st2 = 0, a2 = 0;      // G2 cursor, W3 ring, acc2 buffer
+      uint32_t ph2 = 0, a2_phase = 0, ready_phase = 0;
+      bool ready_seen = false, acc2_ok = false;
+      uint32_t idle = 0;
+      while (i2 < n_my) {
+        bool progressed = false;
+        // ---- one k-block of G2(i2) ----
+        if (i2 < i1) {   // G1(i2) fully issued (acc1_full committed), E1 can have run
+          if (!ready_seen && ptx::mbar_try_wait(a2_ready, ready_phase)) {
+            ready_seen = true;
+            trace_ev(p.trace, 13);
+          }
+          if (ready_seen) {
+            if (!acc2_ok && ptx::mbar_try_wait(&acc2_empty[a2], a2_phase ^ 1)) acc2_ok = true;
+            if (acc2_ok && ptx::mbar_try_wait(&b2_full[st2], ph2)) {
+              ptx::tc_fence_after_sync();
+              const uint32_t d = tmem_acc2 + a2 * BLOCK_N2;
+              const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a2 + kb2 * CHUNK_BYTES));
+              const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b2 + st2 * CHUNK_BYTES));
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) ptx::umma_bf16_ss(d, da + 2 * k, db + 2 * k, kIdesc1, (kb | k) != 0);
-          ptx::umma_commit(&empty_bar[stage]);
-          advance();
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) ptx::umma_bf16_ss(d, da + 2 * k, db + 2 * k, kIdesc2, (kb2 | k) != 0);
+              ptx::umma_commit(&b2_empty[st2]);
+              if (++st2 == C::kB2Stages) {
+                st2 = 0;
+                ph2 ^= 1;
+              }
+              if (++kb2 == kCBlocks) {
+                kb2 = 0;
+                ptx::umma_commit(&acc2_full[a2]);
+                acc2_ok = false;
+                if (++a2 == 2) {
+                  a2 = 0;
+                  a2_phase ^= 1;
+                }
+                if (++n2 == p.num_n2) {
+                  n2 = 0;
+                  ptx::umma_commit(a2_free);   // every MMA that reads A2 has completed
+                  trace_ev(p.trace, 12);
+                  ready_seen = false;
+                  ready_phase ^= 1;
+                  ++i2;
+                }
+              }
+              progressed = true;
+            }
+          }
         }
-        ptx::umma_commit(&acc1_full[a1]);
-        if (++a1 == 2) {
-          a1 = 0;
-          a1_phase ^= 1;
-        }
-      };
-      auto g2 = [&]() {
-        ptx::mbar_wait(a2_ready, ready_phase);   // E1 has written A2 (and fenced it for the async proxy)
-        ready_phase ^= 1;
-        ptx::tc_fence_after_sync();
-        for (int n2 = 0; n2 < p.num_n2; ++n2) {
-          ptx::mbar_wait(&acc2_empty[a2], a2_phase ^ 1);
-          ptx::tc_fence_after_sync();
-          const uint32_t d = tmem_acc2 + a2 * BLOCK_N2;
-          for (int kb = 0; kb < kCBlocks; ++kb) {
-            ptx::mbar_wait(&full_bar[stage], phase);
+        // ---- one k-block of G1(i1) ----
+        if (i1 < n_my) {
+          if (!acc1_ok && ptx::mbar_try_wait(&acc1_empty[a1], a1_phase ^ 1)) acc1_ok = true;
+          if (acc1_ok && ptx::mbar_try_wait(&full_bar[stage], phase)) {
             ptx::tc_fence_after_sync();
-            const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a2 + kb * CHUNK_BYTES));
+            const uint32_t d = tmem_acc1 + a1 * MID;
+            const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a + stage * CHUNK_BYTES));
             const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * CHUNK_BYTES));
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) ptx::umma_bf16_ss(d, da + 2 * k, db + 2 * k, kIdesc2, (kb | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) ptx::umma_bf16_ss(d, da + 2 * k, db + 2 * k, kIdesc1, (kb1 | k) != 0);
             ptx::umma_commit(&empty_bar[stage]);
-            advance();
-          }
-          ptx::umma_commit(&acc2_full[a2]);
-          if (++a2 == 2) {
-            a2 = 0;
-            a2_phase ^= 1;
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            if (++kb1 == kK1Blocks) {
+              kb1 = 0;
+              ptx::umma_commit(&acc1_full[a1]);
+              trace_ev(p.trace, 11);
+              acc1_ok = false;
+              if (++a1 == 2) {
+                a1 = 0;
+                a1_phase ^= 1;
+              }
+              ++i1;
+            }
+            progressed = true;
           }
         }
-        ptx::umma_commit(a2_free);   // every MMA that reads A2 has completed
-      };
-      if (first < n_mblk) g1();
-      for (int t = first; t < n_mblk; t += step) {
-        if (t + step < n_mblk) g1();
-        g2();
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 26)) __trap();   // protocol bug: fail the launch instead of hanging the GPU
       }
     }
   } else if (warp == 2) {
@@ -260,11 +308,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     int a1 = 0, a2 = 0;
     uint32_t a1_phase = 0, a2_phase = 0, rk = 0, free_phase = 0;
     float* my_bias3 = s_bias3 + wg * 64;
-    uint8_t* my_out = smem_out + wg * CHUNK_BYTES;
+    int prev_slot = -1;   // slot whose TMA store may still be reading it
 
     auto e1 = [&]() {
+      if (wg == 0 && et == 0) trace_ev(p.trace, 20);
       ptx::mbar_wait(&acc1_full[a1], a1_phase);
+      if (wg == 0 && et == 0) trace_ev(p.trace, 21);
       ptx::mbar_wait(a2_free, free_phase ^ 1);   // the previous tile's second GEMM no longer reads A2
+      if (wg == 0 && et == 0) trace_ev(p.trace, 22);
       free_phase ^= 1;
       ptx::tc_fence_after_sync();
       const uint32_t t_acc = tmem_acc1 + lane_addr + a1 * MID;
@@ -292,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
       ptx::mbar_arrive(&acc1_empty[a1]);
       ptx::fence_proxy_async_smem();             // A2 is read by the tensor core through the async proxy
       ptx::mbar_arrive(a2_ready);
+      if (wg == 0 && et == 0) trace_ev(p.trace, 23);
       if (++a1 == 2) {
         a1 = 0;
         a1_phase ^= 1;
@@ -302,12 +354,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
       const int m0 = m_blk * BLOCK_M, n0 = n2 * BLOCK_N2 + wg * 64;
       if (et < 64) my_bias3[et] = p.bias3[n0 + et];
       ptx::named_bar_sync(bar_id, 128);
+      if (wg == 0 && et == 0) trace_ev(p.trace, 30);
       ptx::mbar_wait(&acc2_full[a2], a2_phase);
+      if (wg == 0 && et == 0) trace_ev(p.trace, 31);
       ptx::tc_fence_after_sync();
       const uint32_t t_acc = tmem_acc2 + lane_addr + a2 * BLOCK_N2 + wg * 64;
       uint32_t packed[32];
       const int rs = wg * 2 + (rk & 1);
       ptx::mbar_wait(&res_full[rs], (rk >> 1) & 1);
+      if (wg == 0 && et == 0) trace_ev(p.trace, 32);
       ++rk;
       const uint8_t* rrow = smem_res + rs * CHUNK_BYTES + row * 128;
 #pragma unroll
@@ -333,13 +388,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
         a2 = 0;
         a2_phase ^= 1;
       }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&res_empty[rs]);
-      // my staging box: its previous TMA store must have finished reading it (waited for here, after the arithmetic)
-      if (et == 0) ptx::tma_store_wait_read<0>();
-      ptx::named_bar_sync(bar_id, 128);
-      uint8_t* buf = my_out;
-      uint8_t* rowp = buf + row * 128;
+      // The output chunk overwrites the residual chunk in place (every thread rewrites exactly the 128 bytes it has just
+      // read) and is stored from there; the slot goes back to the residual producer once the store has read it.
+      uint8_t* rowp = smem_res + rs * CHUNK_BYTES + row * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
@@ -347,9 +398,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(bar_id, 128);
       if (et == 0) {
-        ptx::tma_store_2d(&p.tmD, buf, n0, m0);
+        ptx::tma_store_2d(&p.tmD, smem_res + rs * CHUNK_BYTES, n0, m0);
         ptx::tma_store_commit();
+        if (prev_slot >= 0) {
+          ptx::tma_store_wait_read<1>();   // every store but the one just issued has finished reading shared memory
+          ptx::mbar_arrive(&res_empty[prev_slot]);
+        }
       }
+      prev_slot = rs;
+      if (wg == 0 && et == 0) trace_ev(p.trace, 33);
     };
 
     // E1 of the NEXT tile runs before E2 of this one, so that the next tile's second GEMM overlaps this tile's output phase
@@ -369,6 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
   if (warp == 1) ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
+unsigned long long* g_bneck_trace = nullptr;
+
 template <int MID>
 int launch_t(const BneckParams& p, int grid, cudaStream_t s) {
   static bool configured = false;
@@ -384,6 +443,8 @@ int launch_t(const BneckParams& p, int grid, cudaStream_t s) {
 }
 
 }  // namespace
+
+void g_bneck_trace_set(unsigned long long* p) { g_bneck_trace = p; }
 
 int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
                const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y) {
@@ -418,6 +479,7 @@ int bneck_launch(const BneckPlan& plan, cudaStream_t stream) {
   p.num_n2 = plan.width / BLOCK_N2;
   p.KW = plan.g.KW; p.stride = plan.g.stride; p.pad_h = plan.g.pad_h; p.pad_w = plan.g.pad_w; p.P = plan.g.P; p.Q = plan.g.Q;
   p.bias2 = plan.bias2; p.bias3 = plan.bias3;
+  p.trace = g_bneck_trace;
   return plan.mid == 64 ? launch_t<64>(p, plan.grid, stream) : launch_t<128>(p, plan.grid, stream);
 }
 
@@ -433,4 +495,10 @@ extern "C" int opd_bottleneck_tail_bf16(const void* x_dev, int32_t B, int32_t H,
                                static_cast<const __nv_bfloat16*>(residual_dev), static_cast<__nv_bfloat16*>(y_dev)))
     return rc;
   return opd::bneck_launch(plan, static_cast<cudaStream_t>(stream));
+}
+
+// debug: timeline trace of CTA 0 of the next tc_bneck_kernel launches (device buffer of >= 4001 uint64, [0] zeroed)
+extern "C" int opd_debug_set_bneck_trace(unsigned long long* buf_dev) {
+  opd::g_bneck_trace_set(buf_dev);
+  return 0;
 }

@@ -102,6 +102,7 @@ struct BneckPlan {
 int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
                const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y);
 int bneck_launch(const BneckPlan& plan, cudaStream_t stream);
+void g_bneck_trace_set(unsigned long long* p);   // debug timeline of tc_bneck_kernel (see opd_debug_set_bneck_trace)
 int bneck_halo_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* w2, const float* bias2,
                     const __nv_bfloat16* w3, const float* bias3, int width, const __nv_bfloat16* residual, __nv_bfloat16* y,
                     const __nv_bfloat16* shortcut_in = nullptr);
