@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&p.tmS);
     ptx::prefetch_tmap(&p.tmW);
     ptx::prefetch_tmap(&p.tmD);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
     ptx::mbar_init(w_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<256>(tmem_ptr);
+  if (warp == 9) ptx::tmem_alloc<256>(tmem_ptr);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
     b = r / p.tiles_y;
   };
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       ptx::mbar_expect_tx(w_full, 16 * W_TAP_BYTES);
       for (int tap = 0; tap < 16; ++tap) ptx::tma_load_2d(&p.tmW, w_full, smem_w + tap * W_TAP_BYTES, tap * 16, 0);
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0) {
       ptx::mbar_wait(w_full, 0);
       int ps = 0, as = 0;
@@ -188,14 +188,14 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // two epilogue warpgroups; warpgroup g handles this CTA's tiles number g, g + 2, ... (accumulator stages g, g + 2)
-    const int wg = (warp - 4) >> 2;
-    const int et = threadIdx.x - 128 - wg * 128;
+    const int wg = warp >> 2;
+    const int et = threadIdx.x - wg * 128;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    if (threadIdx.x - 128 < 64) s_bias[threadIdx.x - 128] = p.bias[threadIdx.x - 128];
+    if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
     ptx::named_bar_sync(3, 256);
     uint8_t* my_out = smem_out + wg * 2 * OUT_BYTES;
     uint32_t k = 0;   // tiles processed by this warpgroup: accumulator stage = wg + 2 * (k & 1), parity = (k >> 1) & 1
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<256>(tmem_base);
+  if (warp == 9) ptx::tmem_dealloc<256>(tmem_base);
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

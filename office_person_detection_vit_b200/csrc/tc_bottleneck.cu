@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB1);
     ptx::prefetch_tmap(&p.tmB2);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_ptr);
+  if (warp == 9) ptx::tmem_alloc<C::kTmemCols>(tmem_ptr);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
 
   const int first = blockIdx.x, step = gridDim.x, n_mblk = p.num_m_blocks;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
       };
       for (int t = first; t < n_mblk; t += step) load_g1(t);
     }
-  } else if (warp == 3) {
+  } else if (warp == 11) {
     // ===================================== W3 tile producer (second GEMM) =====================================
     if (lane == 0) {
       int st = 0;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
             }
           }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ===================================== MMA issuer =====================================
     // One thread interleaves two streams of work so that neither blocks the other:
     //   G1(i1): the 3x3 convolution of this CTA's tile number i1 (L2 -> SM bound: 18 x 32 KB through the main ring),
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
         else if (++idle > (1u << 26)) __trap();   // protocol bug: fail the launch instead of hanging the GPU
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == 10) {
     // ===================================== residual TMA producer =====================================
     if (lane == 0) {
       ptx::prefetch_tmap(&p.tmR);
@@ -291,18 +291,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
             ptx::tma_load_2d(&p.tmR, &res_full[slot], smem_res + slot * CHUNK_BYTES, n2 * BLOCK_N2 + c * 64, t * BLOCK_M);
           }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ============================ epilogue: two warpgroups (warps 4-7, 8-11) ============================
     // Both warpgroups cover all 128 rows (TMEM lane quarter = warp % 4) and split the COLUMNS: in E1 each converts
     // half of acc1, in E2 warpgroup g owns the 64-column chunk g of every 128-column n2 tile (its own residual
     // ring slots, bias slice, staging buffers and TMA stores).
-    const int wg = (warp - 4) >> 2;             // 0 or 1
-    const int et = threadIdx.x - 128 - wg * 128;   // 0..127 inside the warpgroup
+    const int wg = warp >> 2;             // 0 or 1
+    const int et = threadIdx.x - wg * 128;   // 0..127 inside the warpgroup
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int bar_id = 1 + wg;
-    for (int i = threadIdx.x - 128; i < MID; i += 256) s_bias2[i] = p.bias2[i];
+    for (int i = threadIdx.x; i < MID; i += 256) s_bias2[i] = p.bias2[i];
     ptx::named_bar_sync(3, 256);
 
     int a1 = 0, a2 = 0;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  if (warp == 9) ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
 unsigned long long* g_bneck_trace = nullptr;

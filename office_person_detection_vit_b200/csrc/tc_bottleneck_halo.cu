@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB1);
     ptx::prefetch_tmap(&p.tmB2);
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 9) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     b = r / p.tiles_y;
   };
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int bs = 0;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
       int bs = 0;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
         }
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == 10) {
     // ===================================== residual / shortcut-input TMA producer =====================================
     if (lane == 0) {
       ptx::prefetch_tmap(&p.tmR);
@@ -291,15 +291,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
             }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ============================ epilogue: two warpgroups (warps 4-7, 8-11) ============================
-    const int wg = (warp - 4) >> 2;
-    const int et = threadIdx.x - 128 - wg * 128;
+    const int wg = warp >> 2;
+    const int et = threadIdx.x - wg * 128;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;           // half-tile row = pixel (row / 8, row % 8) = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int bar_id = 1 + wg;
-    if (threadIdx.x - 128 < MID) s_bias2[threadIdx.x - 128] = p.bias2[threadIdx.x - 128];   // 256 epilogue threads >= MID
+    if (threadIdx.x < MID) s_bias2[threadIdx.x] = p.bias2[threadIdx.x];   // 256 epilogue threads >= MID
     ptx::named_bar_sync(3, 256);
 
     uint32_t rk = 0, n = 0, acc2_phase[2] = {0, 0};
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == 9) ptx::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 }  // namespace
