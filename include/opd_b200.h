@@ -43,6 +43,7 @@ const char* opd_last_error(void);
 int64_t opd_launch_count(void);
 /* Kernel-selection knobs for A/B measurements (plans built afterwards see the new value):
  *   "attention_tc" 1 (default): fused attention on tcgen05 / TMEM; 0: the mma.sync flash kernel
+ *   "attention_kv" 64 (default) or 128: keys per tile of the tcgen05 attention kernel (4 or 2 CTAs per SM)
  *   "bneck_halo"  1 (default): 64-channel stride-1 bottleneck tails load one halo patch per tile; 0: im2col TMA. */
 int opd_set_option(const char* name, int32_t value);
 

@@ -21,12 +21,20 @@
 namespace opd {
 namespace {
 
-constexpr int kQ = 128, kKV = 128, kD = 32;
-constexpr int TILE_BYTES = 128 * 64;          // [128 rows x 32 bf16]
+constexpr int kQ = 128, kD = 32;
+constexpr int Q_BYTES = 128 * 64;             // [128 rows x 32 bf16]
 constexpr int P_CHUNK = 128 * 128;            // [128 rows x 64 bf16]
 constexpr int kThreads = 192;
-constexpr int kSmemBytes = TILE_BYTES /*Q*/ + 2 * TILE_BYTES /*K*/ + 2 * TILE_BYTES /*V*/ + 2 * P_CHUNK /*P*/ + 1024;
-constexpr int kTmemCols = 256;
+// kKV = keys per tile.  128: TMEM 128 + 32 -> 256 columns, 2 CTAs per SM.  64: TMEM 64 + 32 -> 128 columns, 41 KB of
+// shared memory, 4 CTAs per SM: each CTA's S -> softmax -> PV chain is serial, more co-resident CTAs hide it better.
+template <int kKV>
+struct AttnCfg {
+  static constexpr int kTileBytes = kKV * 64;                  // K / V tile [kKV rows x 32 bf16]
+  static constexpr int kPChunks = kKV / 64;
+  static constexpr int kSmemBytes = Q_BYTES + 4 * kTileBytes + kPChunks * P_CHUNK + 1024;
+  static constexpr int kTmemCols = kKV == 128 ? 256 : 128;
+  static constexpr int kCtasPerSm = kKV == 128 ? 2 : 4;
+};
 
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmV;
@@ -75,16 +83,20 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) attention_tc_kernel(const __grid_constant__ AttnParams p) {
-  constexpr uint32_t kIdescS = ptx::umma_idesc_bf16(128, 128);
+template <int kKV>
+__global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+  using C = AttnCfg<kKV>;
+  constexpr int TILE_BYTES = C::kTileBytes;
+  constexpr int kTmemCols = C::kTmemCols;
+  constexpr uint32_t kIdescS = ptx::umma_idesc_bf16(128, kKV);
   constexpr uint32_t kIdescPV = ptx::umma_idesc_bf16(128, 32) | (1u << 16);   // B (= V tile) is MN-major
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_q = smem;
-  uint8_t* s_k = s_q + TILE_BYTES;          // [2]
+  uint8_t* s_k = s_q + Q_BYTES;             // [2]
   uint8_t* s_v = s_k + 2 * TILE_BYTES;      // [2]
-  uint8_t* s_p = s_v + 2 * TILE_BYTES;      // 2 chunks of 64 keys
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * P_CHUNK);
+  uint8_t* s_p = s_v + 2 * TILE_BYTES;      // chunks of 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + C::kPChunks * P_CHUNK);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;     // [2]
   uint64_t* k_empty = bars + 3;    // [2]
@@ -121,12 +133,12 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc_kernel(const __grid_
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + kKV;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      ptx::mbar_expect_tx(q_full, TILE_BYTES);
+      ptx::mbar_expect_tx(q_full, Q_BYTES);
       ptx::tma_load_2d(&p.tmQ, q_full, s_q, head * kD, b * p.Lq + q0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc_kernel(const __grid_
         ptx::tc_fence_after_sync();
         const uint32_t v_addr = ptx::smem_u32(s_v + st * TILE_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
+        for (int kk = 0; kk < kKV / 16; ++kk)
           ptx::umma_bf16_ss(tmem_o, desc(p_addr + (kk >> 2) * P_CHUNK + (kk & 3) * 32, 1024, kSw128),
                             desc(v_addr + kk * 1024, 512, kSw64), kIdescPV, (j | kk) != 0);
         ptx::umma_commit(&v_empty[st]);
@@ -183,11 +195,11 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc_kernel(const __grid_
     for (int j = 0; j < n_tiles; ++j) {
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after_sync();
-      const int valid = p.Lk - j * kKV;           // keys of this tile that exist (>= 128: all)
+      const int valid = p.Lk - j * kKV;           // keys of this tile that exist (>= kKV: all)
       // pass 1: row maximum (3-input max; only the last tile of a row of tiles needs the key mask)
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kKV / 32; ++c) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
         ptx::tmem_ld_wait();
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc_kernel(const __grid_
       const uint64_t sl2_2 = pack2f(sl2, sl2), neg_m2 = pack2f(-m_new, -m_new);
       uint64_t sum2 = pack2f(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kKV / 32; ++c) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
         ptx::tmem_ld_wait();
@@ -290,7 +302,7 @@ using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // [rows, cols] bf16 with row pitch ld; box = [32 columns, 128 rows], 64-byte swizzle
-int make_tmap_head(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+int make_tmap_head(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   OPD_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -298,7 +310,7 @@ int make_tmap_head(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t col
   OPD_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, "attention: operand not 16-byte aligned");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {32, 128};
+  cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
                                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -315,9 +327,10 @@ int attn_plan(AttnPlan* plan, const __nv_bfloat16* q, int64_t ldq, const __nv_bf
   OPD_REQUIRE(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "attention: bad shape");
   OPD_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention: output not 16-byte aligned");
   const uint64_t cols = (uint64_t)heads * kD;
-  if (int rc = make_tmap_head(&plan->tmQ, q, (uint64_t)B * Lq, cols, ldq)) return rc;
-  if (int rc = make_tmap_head(&plan->tmK, k, (uint64_t)B * Lk, cols, ldk)) return rc;
-  if (int rc = make_tmap_head(&plan->tmV, v, (uint64_t)B * Lk, cols, ldv)) return rc;
+  plan->kv_tile = g_option_attention_kv.load() == 128 ? 128 : 64;
+  if (int rc = make_tmap_head(&plan->tmQ, q, (uint64_t)B * Lq, cols, ldq, 128)) return rc;
+  if (int rc = make_tmap_head(&plan->tmK, k, (uint64_t)B * Lk, cols, ldk, plan->kv_tile)) return rc;
+  if (int rc = make_tmap_head(&plan->tmV, v, (uint64_t)B * Lk, cols, ldv, plan->kv_tile)) return rc;
   plan->o = o; plan->ldo = ldo; plan->B = B; plan->heads = heads; plan->Lq = Lq; plan->Lk = Lk;
   return OPD_OK;
 }
@@ -328,11 +341,15 @@ int attn_launch(const AttnPlan& plan, cudaStream_t stream) {
   p.o = plan.o; p.ldo = plan.ldo; p.Lq = plan.Lq; p.Lk = plan.Lk;
   static bool configured = false;
   if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128>::kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::kSmemBytes));
     configured = true;
   }
   dim3 grid((plan.Lq + kQ - 1) / kQ, plan.heads, plan.B);
-  attention_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  if (plan.kv_tile == 128)
+    attention_tc_kernel<128><<<grid, kThreads, AttnCfg<128>::kSmemBytes, stream>>>(p);
+  else
+    attention_tc_kernel<64><<<grid, kThreads, AttnCfg<64>::kSmemBytes, stream>>>(p);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

@@ -9,6 +9,7 @@ std::string& last_error_ref() {
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_option_bneck_halo{1};
 std::atomic<int> g_option_attention_tc{1};
+std::atomic<int> g_option_attention_kv{64};
 }  // namespace opd
 
 extern "C" {
@@ -18,6 +19,10 @@ int64_t opd_launch_count(void) { return opd::g_launches.load(); }
 int opd_set_option(const char* name, int32_t value) {
   if (name && std::string(name) == "bneck_halo") {
     opd::g_option_bneck_halo.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "attention_kv") {
+    opd::g_option_attention_kv.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "attention_tc") {

@@ -73,6 +73,7 @@ struct AttnPlan {
   __nv_bfloat16* o;
   int64_t ldo;
   int B, heads, Lq, Lk;
+  int kv_tile;   // keys per tile: 64 (4 CTAs per SM) or 128 (2 CTAs per SM)
 };
 int attn_plan(AttnPlan* plan, const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v,
               int64_t ldv, __nv_bfloat16* o, int64_t ldo, int B, int heads, int Lq, int Lk);
