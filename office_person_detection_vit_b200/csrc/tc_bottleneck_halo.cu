@@ -34,12 +34,14 @@ template <int MID>
 struct HaloCfg {
   static constexpr int kCB = MID / 64;                    // 64-channel blocks
   static constexpr int kA2Chunks = 2 * kCB;               // both half tiles
-  static constexpr int kResStages = MID == 64 ? 4 : 2;
-  static constexpr int kResPerWg = kResStages / 2;
+  // pool of [128 x 64] chunk slots after A2: residual chunks land here and the output chunk is written IN PLACE over the
+  // residual it has just consumed, then stored from there (kSC, no residual: 2 staging boxes + the 2 block-input tiles)
+  static constexpr int kPool = MID == 64 ? 6 : 4;
+  static constexpr int kResStages = kPool;
+  static constexpr int kResPerWg = kPool / 2;
   static constexpr int kTapBytes = MID * 128;             // one W2 tap tile [MID x 64] bf16
   static constexpr int kTapsPerSlot = CHUNK_BYTES / kTapBytes;
-  static constexpr int kSmemBytes = PATCH_SLOT + kBStages * CHUNK_BYTES + kA2Chunks * CHUNK_BYTES + 2 * CHUNK_BYTES /*staging*/ +
-                                    kResStages * CHUNK_BYTES + 2048;
+  static constexpr int kSmemBytes = PATCH_SLOT + kBStages * CHUNK_BYTES + kA2Chunks * CHUNK_BYTES + kPool * CHUNK_BYTES + 4096;
   static_assert(MID == 64 || MID == 128, "halo bottleneck tail: MID must be 64 or 128");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -88,11 +90,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
   uint8_t* smem_patch = smem;                                      // one halo patch (the next one loads during E2)
   uint8_t* smem_b = smem_patch + PATCH_SLOT;                       // [kBStages] W2 tap pairs / W3 tiles
   uint8_t* smem_a2 = smem_b + kBStages * CHUNK_BYTES;              // [2 halves][kCB chunks] A operand of the second GEMM
-  uint8_t* smem_out = smem_a2 + C::kA2Chunks * CHUNK_BYTES;        // one staging box per epilogue warpgroup
-  uint8_t* smem_res = smem_out + 2 * CHUNK_BYTES;                  // residual slots per warpgroup; kSC: X[h] in slots 0, 1
-  float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [MID]
-  float* s_bias3 = s_bias2 + 128;                                                   // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 128);
+  uint8_t* smem_pool = smem_a2 + C::kA2Chunks * CHUNK_BYTES;       // chunk slots (see HaloCfg::kPool)
+  uint8_t* smem_out = smem_pool;                                   // kSC: one staging box per epilogue warpgroup (slots 0, 1)
+  uint8_t* smem_res = kSC ? smem_pool + 2 * CHUNK_BYTES : smem_pool;   // kSC: X[h] in pool slots 2, 3; else all slots = residual ring
+  float* s_bias2 = reinterpret_cast<float*>(smem_pool + C::kPool * CHUNK_BYTES);    // [MID]
+  float* s_bias3 = s_bias2 + 128;                                                   // [width <= 512]: whole layer, loaded once
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 512);
   uint64_t* patch_full = bars;          // [1]
   uint64_t* patch_empty = bars + 1;     // [1]
   uint64_t* b_full = bars + 2;          // [kBStages]
@@ -103,9 +106,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
   uint64_t* acc2_empty = bars + 14;     // [2]
   uint64_t* a2_ready = bars + 16;       // [1]
   uint64_t* a2_free = bars + 17;        // [1]
-  uint64_t* res_full = bars + 18;       // [4]
-  uint64_t* res_empty = bars + 22;      // [4]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* res_full = bars + 18;       // [kPool]
+  uint64_t* res_empty = bars + 24;      // [kPool]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 30);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     ptx::mbar_init(a2_free, 1);
     for (int i = 0; i < kResStages; ++i) {
       ptx::mbar_init(&res_full[i], 1);
-      ptx::mbar_init(&res_empty[i], kSC ? 1 : 4);
+      ptx::mbar_init(&res_empty[i], 1);   // kSC: MMA commit; else: the warpgroup's store thread, once the TMA store has read the slot
     }
     ptx::fence_barrier_init();
   }
@@ -300,11 +303,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int bar_id = 1 + wg;
     if (threadIdx.x < MID) s_bias2[threadIdx.x] = p.bias2[threadIdx.x];   // 256 epilogue threads >= MID
+    for (int i = threadIdx.x; i < p.num_n2 * BLOCK_N2; i += 256) s_bias3[i] = p.bias3[i];
     ptx::named_bar_sync(3, 256);
 
     uint32_t rk = 0, n = 0, acc2_phase[2] = {0, 0};
-    float* my_bias3 = s_bias3 + wg * 64;
     uint8_t* my_out = smem_out + wg * CHUNK_BYTES;
+    int prev_slot = -1;   // residual slot whose TMA store may still be reading it
 
     for (int t = first; t < n_tiles; t += step, ++n) {
       int b, y0, x0;
@@ -340,8 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       // ---- E2: (n2, h) in MMA order; warpgroup g owns columns [n2 * 128 + 64 g, + 64) ----
       for (int n2 = 0; n2 < p.num_n2; ++n2) {
         const int n0 = n2 * BLOCK_N2 + wg * 64;
-        if (et < 64) my_bias3[et] = p.bias3[n0 + et];
-        ptx::named_bar_sync(bar_id, 128);                 // bias slice visible to the warpgroup
+        const float* my_bias3 = s_bias3 + n0;
         for (int h = 0; h < 2; ++h) {
           ptx::mbar_wait(&acc2_full[h], acc2_phase[h]);
           acc2_phase[h] ^= 1;
@@ -373,13 +376,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           }
           ptx::tc_fence_before_sync();
           ptx::mbar_arrive(&acc2_empty[h]);
-          __syncwarp();
-          if (!kSC && lane == 0) ptx::mbar_arrive(&res_empty[rslot]);
-          // my staging box: its previous TMA store must have finished READING it; the wait sits here, after the TMEM loads
-          // and the arithmetic, so that the store engine's read overlaps them instead of stalling the warpgroup
-          if (et == 0) ptx::tma_store_wait_read<0>();
-          ptx::named_bar_sync(bar_id, 128);
-          uint8_t* rowp = my_out + row * 128;
+          if (kSC) {
+            // staging box: its previous TMA store must have finished READING it; waited for here, after the arithmetic
+            if (et == 0) ptx::tma_store_wait_read<0>();
+            ptx::named_bar_sync(bar_id, 128);
+          }
+          // non-kSC: the output chunk overwrites the residual chunk in place (every thread rewrites exactly the 128 bytes it
+          // has just read) and is stored from there; the slot returns to the residual producer once the store has read it
+          uint8_t* obuf = kSC ? my_out : smem_res + rslot * CHUNK_BYTES;
+          uint8_t* rowp = obuf + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
@@ -387,9 +392,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_id, 128);
           if (et == 0) {
-            tma_store_4d(&p.tmD, my_out, n0, x0 + h * SUB_W, y0, b);
+            tma_store_4d(&p.tmD, obuf, n0, x0 + h * SUB_W, y0, b);
             ptx::tma_store_commit();
+            if (!kSC && prev_slot >= 0) {
+              ptx::tma_store_wait_read<1>();   // every store but the one just issued has finished reading shared memory
+              ptx::mbar_arrive(&res_empty[prev_slot]);
+            }
           }
+          prev_slot = rslot;
         }
       }
     }
@@ -415,7 +425,7 @@ int bneck_halo_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, 
                   g.Q == g.W,
               "bottleneck tail (halo): 3x3 / stride 1 / pad 1 over 64 or 128 channels only");
   OPD_REQUIRE(!shortcut_in || MID == 64, "bottleneck tail (halo): fused shortcut needs 64 channels");
-  OPD_REQUIRE(width % BLOCK_N2 == 0 && width > 0, "bottleneck tail (halo): width=%d must be a multiple of 128", width);
+  OPD_REQUIRE(width % BLOCK_N2 == 0 && width > 0 && width <= 512, "bottleneck tail (halo): width=%d must be a multiple of 128, <= 512", width);
   OPD_REQUIRE(bias2 && bias3 && residual && y && x && w2 && w3, "bottleneck tail (halo): NULL argument");
   plan->halo = 1;
   plan->M = g.B * g.P * g.Q;
