@@ -204,13 +204,14 @@ int opd_detr_tap(const opd_detr* m, const char* name, const void** ptr_dev, int6
 int opd_detr_tap_copy(const opd_detr* m, const char* name, void* dst_dev, size_t bytes, void* stream);
 /* post_process_object_detection + person filter (image_processing_detr.py:826-843; yolov8_detector.py:210-241):
  * per query: scores_dev [B,Q], labels_dev [B,Q], xyxy_dev [B,Q,4] (pixels of the ORIGINAL H0 x W0 frame);
- * per frame, compacted in query order: det_xywh_dev [B,Q,4], det_score_dev [B,Q], det_foot_dev [B,Q,2] f64,
+ * per frame, compacted in query order: det_xywh_dev [B,Q,4] f64 (x1, y1, x2 - x1, y2 - y1 like the reference's Python
+ * floats), det_score_dev [B,Q], det_foot_dev [B,Q,2] f64,
  * det_query_dev [B,Q], n_keep_dev [B]  for  score > threshold && label == person_label;
  * det_slot_dev [B,Q] (optional) = slot_base + frame for the compacted rows, -1 for the unused ones: the
  * `slot_dev` argument of opd_floor_project_classify_count_* when the whole [B*Q] block is projected. */
 int opd_detr_postprocess(const float* logits_dev, const float* boxes_dev, int32_t B, int32_t Q, int32_t C,
                          int32_t H0, int32_t W0, float threshold, int32_t person_label, float* scores_dev,
-                         int32_t* labels_dev, float* xyxy_dev, float* det_xywh_dev, float* det_score_dev,
+                         int32_t* labels_dev, float* xyxy_dev, double* det_xywh_dev, float* det_score_dev,
                          double* det_foot_dev, int32_t* det_query_dev, int32_t* n_keep_dev, int32_t* det_slot_dev,
                          int32_t slot_base, void* stream);
 

@@ -942,7 +942,7 @@ int opd_detr_tap_copy(const opd_detr* m, const char* name, void* dst_dev, size_t
 
 int opd_detr_postprocess(const float* logits_dev, const float* boxes_dev, int32_t B, int32_t Q, int32_t C, int32_t H0,
                          int32_t W0, float threshold, int32_t person_label, float* scores_dev, int32_t* labels_dev,
-                         float* xyxy_dev, float* det_xywh_dev, float* det_score_dev, double* det_foot_dev,
+                         float* xyxy_dev, double* det_xywh_dev, float* det_score_dev, double* det_foot_dev,
                          int32_t* det_query_dev, int32_t* n_keep_dev, int32_t* det_slot_dev, int32_t slot_base,
                          void* stream) {
   OPD_REQUIRE(logits_dev && boxes_dev && scores_dev && labels_dev && xyxy_dev && det_xywh_dev && det_score_dev &&

@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
 __global__ void __launch_bounds__(128) postprocess_kernel(const float* __restrict__ logits, const float* __restrict__ boxes,
                                                           int Q, int C, int H0, int W0, float threshold, int person_label,
                                                           float* __restrict__ scores, int32_t* __restrict__ labels,
-                                                          float* __restrict__ xyxy, float* __restrict__ det_xywh,
+                                                          float* __restrict__ xyxy, double* __restrict__ det_xywh,
                                                           float* __restrict__ det_score, double* __restrict__ det_foot,
                                                           int32_t* __restrict__ det_query, int32_t* __restrict__ n_keep,
                                                           int32_t* __restrict__ det_slot, int slot_base) {
@@ -495,10 +495,10 @@ __global__ void __launch_bounds__(128) postprocess_kernel(const float* __restric
     const int slot = base + __popc(bal & ((1u << lane) - 1));
     const long long r = (long long)b * Q + slot;
     const double dx1 = x1, dy1 = y1, dw = (double)x2 - (double)x1, dh = (double)y2 - (double)y1;
-    det_xywh[r * 4 + 0] = x1;
-    det_xywh[r * 4 + 1] = y1;
-    det_xywh[r * 4 + 2] = (float)dw;
-    det_xywh[r * 4 + 3] = (float)dh;
+    det_xywh[r * 4 + 0] = dx1;   // Python floats in the reference (yolov8_detector.py:214-218): float64, x2 - x1 exact
+    det_xywh[r * 4 + 1] = dy1;
+    det_xywh[r * 4 + 2] = dw;
+    det_xywh[r * 4 + 3] = dh;
     det_score[r] = sc;
     det_foot[r * 2 + 0] = dx1 + dw / 2.0;   // python floats in the reference: float64
     det_foot[r * 2 + 1] = dy1 + dh;
@@ -589,7 +589,7 @@ int launch_heads(const __nv_bfloat16* y, const HeadWeights& w, float* logits, fl
 }
 
 int launch_postprocess(const float* logits, const float* boxes, int B, int Q, int C, int H0, int W0, float threshold,
-                       int person_label, float* scores, int32_t* labels, float* xyxy, float* det_xywh, float* det_score,
+                       int person_label, float* scores, int32_t* labels, float* xyxy, double* det_xywh, float* det_score,
                        double* det_foot, int32_t* det_query, int32_t* n_keep, int32_t* det_slot, int slot_base,
                        cudaStream_t s) {
   OPD_REQUIRE(Q <= 128, "postprocess: at most 128 queries per frame (got %d)", Q);

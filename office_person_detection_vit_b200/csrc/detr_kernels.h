@@ -48,7 +48,7 @@ int launch_heads(const __nv_bfloat16* y, const HeadWeights& w, float* logits, fl
 // K8b: softmax + best class over the first C-1 logits + threshold + person filter + cxcywh -> xyxy -> pixel xywh +
 // foot point + per-frame stable compaction
 int launch_postprocess(const float* logits, const float* boxes, int B, int Q, int C, int H0, int W0, float threshold,
-                       int person_label, float* scores, int32_t* labels, float* xyxy, float* det_xywh, float* det_score,
+                       int person_label, float* scores, int32_t* labels, float* xyxy, double* det_xywh, float* det_score,
                        double* det_foot, int32_t* det_query, int32_t* n_keep, int32_t* det_slot, int slot_base,
                        cudaStream_t s);
 

@@ -189,7 +189,7 @@ def postprocess_tensors(logits, boxes, h0: int, w0: int, threshold: float, perso
         "scores": torch.empty(B, Q, dtype=torch.float32, device=dev),
         "labels": torch.empty(B, Q, dtype=torch.int32, device=dev),
         "xyxy": torch.empty(B, Q, 4, dtype=torch.float32, device=dev),
-        "det_xywh": torch.zeros(B, Q, 4, dtype=torch.float32, device=dev),
+        "det_xywh": torch.zeros(B, Q, 4, dtype=torch.float64, device=dev),
         "det_score": torch.zeros(B, Q, dtype=torch.float32, device=dev),
         "det_foot": torch.zeros(B, Q, 2, dtype=torch.float64, device=dev),
         "det_query": torch.full((B, Q), -1, dtype=torch.int32, device=dev),

@@ -1,0 +1,80 @@
+"""GPU: the Phase 2 -> 3 -> count flow end to end, two ways that must agree:
+  (1) the reference-shaped objects a Phase would drive (src/pipeline/phases/detection.py:91-103, transform.py:279-308,
+      aggregation.py:38-43): ViTDetector.detect_batch -> HomographyTransformer.transform_batch -> ZoneClassifier.classify ->
+      Aggregator.get_zone_counts, one Python object per detection;
+  (2) the tensor pipeline (DetectCountPipeline.run_tensors) + the tensor-side exporter."""
+
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import pytest
+
+from oracle import detr_oracle as do
+from oracle import floor_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+def test_object_flow_equals_tensor_flow(built_lib, tmp_path):
+    import torch
+
+    from office_person_detection_vit_b200.aggregation import Aggregator
+    from office_person_detection_vit_b200.detection import ViTDetector
+    from office_person_detection_vit_b200.export import export_results, frame_results_from_tensors
+    from office_person_detection_vit_b200.pipeline import DetectCountPipeline
+    from office_person_detection_vit_b200.transform import FloorMapConfig, HomographyTransformer
+    from office_person_detection_vit_b200.zone import ZoneClassifier
+
+    torch.cuda.init()
+    zones = fo.star_zones(16, seed=2)
+    zone_ids = [z["id"] for z in zones]
+    det = ViTDetector(confidence_threshold=0.3, state_dict=do.make_weights(0))
+    det.load_model()
+    det.model.set_resize(False)          # small frames fed as they are (DetrImageProcessor(do_resize=False))
+    tr = HomographyTransformer(fo.H_CONFIG, FloorMapConfig())
+    zc = ZoneClassifier(zones, allow_overlap=False)
+    frames = do.synthetic_frames(3, 192, 256, seed=9)
+    timestamps = [f"2025/08/26 16:0{i}:00" for i in range(3)]
+
+    # (1) object flow
+    agg = Aggregator()
+    per_frame = det.detect_batch(list(frames))
+    counts_obj = []
+    for ts, dets in zip(timestamps, per_frame):
+        for d, res in zip(dets, tr.transform_batch([d.bbox for d in dets])):
+            d.floor_coords, d.floor_coords_mm = res.floor_coords_px, res.floor_coords_mm
+            d.zone_ids = zc.classify(res.floor_coords_px)
+        counts_obj.append(agg.aggregate_frame(ts, dets))
+    assert sum(len(d) for d in per_frame) > 10
+
+    # (2) tensor flow
+    pipe = DetectCountPipeline(det, tr, zc)
+    out = pipe.run_tensors(torch.from_numpy(frames).cuda())
+    torch.cuda.synchronize()
+    assert out["n_keep"].cpu().tolist() == [len(d) for d in per_frame]
+    counts_tensor = zc.counts_to_dicts(out["hist"])
+    assert [dict(sorted(c.items())) for c in counts_tensor] == [dict(sorted(c.items())) for c in counts_obj]
+
+    # records and JSON from the tensors == records from the object flow
+    frs = frame_results_from_tensors(out, [10, 11, 12], timestamps, tr, zone_ids)
+    for fr, dets in zip(frs, per_frame):
+        assert len(fr.detections) == len(dets)
+        for a, b in zip(fr.detections, dets):
+            assert a.bbox == pytest.approx(b.bbox) and a.zone_ids == b.zone_ids
+            assert a.floor_coords == pytest.approx(b.floor_coords, rel=1e-12, abs=1e-9)
+            assert a.floor_coords_mm == pytest.approx(b.floor_coords_mm, rel=1e-12, abs=1e-7)
+    path = export_results(out, [10, 11, 12], timestamps, tr, zone_ids, tmp_path)
+    data = json.loads(path.read_text(encoding="utf-8"))
+    assert data["transform_method"] == "homography" and len(data["frames"]) == 3
+    d0 = data["frames"][0]["detections"][0]
+    assert set(d0) >= {"bbox", "confidence", "camera_coords", "floor_coords_px", "floor_coords_mm"}
+    assert d0["bbox"]["x"] == round(per_frame[0][0].bbox[0], 6)
+
+    # CSV through the aggregator's dense-histogram entry
+    agg2 = Aggregator()
+    agg2.aggregate_histogram(timestamps, out["hist"], zone_ids)
+    agg.export_csv(str(tmp_path / "a.csv"), zone_ids)
+    agg2.export_csv(str(tmp_path / "b.csv"), zone_ids)
+    assert (tmp_path / "a.csv").read_text() == (tmp_path / "b.csv").read_text()
