@@ -215,6 +215,16 @@ int opd_detr_postprocess(const float* logits_dev, const float* boxes_dev, int32_
                          double* det_foot_dev, int32_t* det_query_dev, int32_t* n_keep_dev, int32_t* det_slot_dev,
                          int32_t slot_base, void* stream);
 
+/* ROI features of the compacted detections (the removed ViTDetector.extract_features / _extract_features_from_outputs,
+ * coverage.json method table; arithmetic of FeatureExtractor.extract_roi_features + normalize_features,
+ * src/tracking/feature_extractor.py:39-88, :21-37): feat_dev [B, fh, fw, D] bf16 = the encoder output of the last
+ * forward (opd_detr_tap "enc5"), boxes det_xywh_dev [B,Q,4] f64 in pixels of the img_h x img_w frame, rows
+ * r < n_keep_dev[b] valid -> out_dev [B,Q,D] f32: mean over the box's feature cells, divided by (L2 norm + 1e-8);
+ * unused rows are zero. */
+int opd_roi_features_bf16(const void* feat_dev, int32_t B, int32_t fh, int32_t fw, int32_t D,
+                          const double* det_xywh_dev, const int32_t* n_keep_dev, int32_t Q, int32_t img_h,
+                          int32_t img_w, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

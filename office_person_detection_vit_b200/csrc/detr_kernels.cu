@@ -407,40 +407,104 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const floa
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K8a heads: one CTA (256 threads) per decoder row; fp32 weights, fp32 math
+// K8a heads: one CTA (256 threads) per kHeadRows decoder rows; fp32 weights, fp32 math.  Every weight element is loaded
+// once per CTA and used for all of its rows (the one-row version re-read 0.6 MB of weights from L2 per row).
 //   logits = y Wc^T + bc ; boxes = sigmoid(W2 relu(W1 relu(W0 y + b0) + b1) + b2)   (modeling_detr.py:1275-1297, 1401-1402)
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kHeadRows = 8;
 __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ y, HeadWeights w,
-                                                    float* __restrict__ logits, float* __restrict__ boxes, int n_cls) {
-  __shared__ float s_y[kD], s_h0[kD], s_h1[kD];
-  const int row = blockIdx.x, j = threadIdx.x;
-  s_y[j] = __bfloat162float(y[(long long)row * kD + j]);
+                                                    float* __restrict__ logits, float* __restrict__ boxes, int n_cls, int rows) {
+  __shared__ float s_y[kHeadRows][kD], s_h0[kHeadRows][kD], s_h1[kHeadRows][kD];
+  const int row0 = blockIdx.x * kHeadRows, j = threadIdx.x;
+  const int nr = min(kHeadRows, rows - row0);
+#pragma unroll
+  for (int r = 0; r < kHeadRows; ++r) s_y[r][j] = r < nr ? __bfloat162float(y[(long long)(row0 + r) * kD + j]) : 0.f;
   __syncthreads();
   if (j < n_cls) {
-    float acc = 0.f;
-    for (int k = 0; k < kD; ++k) acc = fmaf(s_y[k], w.wc_t[k * n_cls + j], acc);
-    logits[(long long)row * n_cls + j] = acc + w.bc[j];
-  }
-  {
-    float acc = 0.f;
-    for (int k = 0; k < kD; ++k) acc = fmaf(s_y[k], w.w0_t[k * kD + j], acc);
-    s_h0[j] = fmaxf(acc + w.b0[j], 0.f);
-  }
-  __syncthreads();
-  {
-    float acc = 0.f;
-    for (int k = 0; k < kD; ++k) acc = fmaf(s_h0[k], w.w1_t[k * kD + j], acc);
-    s_h1[j] = fmaxf(acc + w.b1[j], 0.f);
-  }
-  __syncthreads();
-  const int warp = j >> 5, lane = j & 31;
-  if (warp < 4) {
-    float acc = 0.f;
-    for (int k = lane; k < kD; k += 32) acc = fmaf(s_h1[k], w.w2[warp * kD + k], acc);
+    float acc[kHeadRows] = {};
+    for (int k = 0; k < kD; ++k) {
+      const float wv = w.wc_t[k * n_cls + j];
 #pragma unroll
-    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if (lane == 0) boxes[(long long)row * 4 + warp] = 1.f / (1.f + expf(-(acc + w.b2[warp])));
+      for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(s_y[r][k], wv, acc[r]);
+    }
+    for (int r = 0; r < nr; ++r) logits[(long long)(row0 + r) * n_cls + j] = acc[r] + w.bc[j];
   }
+  {
+    float acc[kHeadRows] = {};
+    for (int k = 0; k < kD; ++k) {
+      const float wv = w.w0_t[k * kD + j];
+#pragma unroll
+      for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(s_y[r][k], wv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) s_h0[r][j] = fmaxf(acc[r] + w.b0[j], 0.f);
+  }
+  __syncthreads();
+  {
+    float acc[kHeadRows] = {};
+    for (int k = 0; k < kD; ++k) {
+      const float wv = w.w1_t[k * kD + j];
+#pragma unroll
+      for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(s_h0[r][k], wv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) s_h1[r][j] = fmaxf(acc[r] + w.b1[j], 0.f);
+  }
+  __syncthreads();
+  // 8 warps x 4 outputs: warp = row, each lane strides the 256 hidden values
+  const int warp = j >> 5, lane = j & 31;
+  if (warp < nr) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float acc = 0.f;
+      for (int k = lane; k < kD; k += 32) acc = fmaf(s_h1[warp][k], w.w2[o * kD + k], acc);
+#pragma unroll
+      for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+      if (lane == 0) boxes[(long long)(row0 + warp) * 4 + o] = 1.f / (1.f + expf(-(acc + w.b2[o])));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ROI features of the detections (detect_with_features / extract_features): mean of the encoder map over the box,
+// L2-normalised.  Restates FeatureExtractor.extract_roi_features + normalize_features
+// (src/tracking/feature_extractor.py:39-88, :21-37): box -> feature-map cells with Python-float arithmetic and int()
+// truncation, clamps, mean over [y_min:y_max, x_min:x_max], v / (|v| + 1e-8).
+// One CTA per (detection row, frame), thread = channel (coalesced 2-byte loads of one cell's D channels).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) roi_features_kernel(const __nv_bfloat16* __restrict__ feat, int fh, int fw, int D,
+                                                            const double* __restrict__ xywh, const int32_t* __restrict__ n_keep,
+                                                            int Q, double img_h, double img_w, float* __restrict__ out) {
+  __shared__ float s_part[32];
+  const int b = blockIdx.y, r = blockIdx.x, c = threadIdx.x;
+  float* o = out + ((long long)b * Q + r) * D;
+  if (r >= n_keep[b]) {
+    if (c < D) o[c] = 0.f;
+    return;
+  }
+  const double* bb = xywh + ((long long)b * Q + r) * 4;
+  const double x = bb[0], y = bb[1], w = bb[2], h = bb[3];
+  int x_min = (int)((x / img_w) * fw), y_min = (int)((y / img_h) * fh);
+  int x_max = (int)(((x + w) / img_w) * fw), y_max = (int)(((y + h) / img_h) * fh);
+  x_min = max(0, min(x_min, fw - 1));
+  y_min = max(0, min(y_min, fh - 1));
+  x_max = max(x_min + 1, min(x_max, fw));
+  y_max = max(y_min + 1, min(y_max, fh));
+  float acc = 0.f;
+  if (c < D) {
+    const __nv_bfloat16* base = feat + (long long)b * fh * fw * D + c;
+    for (int yy = y_min; yy < y_max; ++yy)
+      for (int xx = x_min; xx < x_max; ++xx) acc += __bfloat162float(base[((long long)yy * fw + xx) * D]);
+    acc /= (float)((y_max - y_min) * (x_max - x_min));
+  }
+  float sq = acc * acc;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
+  if ((c & 31) == 0) s_part[c >> 5] = sq;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += s_part[i];
+  if (c < D) o[c] = acc / (sqrtf(tot) + 1e-8f);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -573,6 +637,15 @@ int launch_decoder_init(__nv_bfloat16* y, __nv_bfloat16* yp, const float* qpos, 
   return OPD_OK;
 }
 
+int launch_roi_features(const __nv_bfloat16* feat, int B, int fh, int fw, int D, const double* xywh, const int32_t* n_keep,
+                        int Q, int img_h, int img_w, float* out, cudaStream_t s) {
+  OPD_REQUIRE(D > 0 && D <= 1024 && D % 32 == 0, "roi features: D=%d must be a multiple of 32, at most 1024", D);
+  roi_features_kernel<<<dim3(Q, B), D, 0, s>>>(feat, fh, fw, D, xywh, n_keep, Q, (double)img_h, (double)img_w, out);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
 int launch_layernorm(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, int rows,
                      cudaStream_t s) {
   layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, rows);
@@ -582,7 +655,7 @@ int launch_layernorm(const __nv_bfloat16* x, const float* gamma, const float* be
 }
 
 int launch_heads(const __nv_bfloat16* y, const HeadWeights& w, float* logits, float* boxes, int rows, cudaStream_t s) {
-  heads_kernel<<<rows, 256, 0, s>>>(y, w, logits, boxes, 92);
+  heads_kernel<<<(rows + kHeadRows - 1) / kHeadRows, 256, 0, s>>>(y, w, logits, boxes, 92, rows);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;
@@ -615,4 +688,13 @@ extern "C" int opd_attention_bf16(const void* q_dev, int64_t ldq, const void* k_
   return opd::launch_attention(static_cast<const __nv_bfloat16*>(q_dev), ldq, static_cast<const __nv_bfloat16*>(k_dev),
                                ldk, static_cast<const __nv_bfloat16*>(v_dev), ldv, static_cast<__nv_bfloat16*>(o_dev),
                                ldo, B, heads, Lq, Lk, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int opd_roi_features_bf16(const void* feat_dev, int32_t B, int32_t fh, int32_t fw, int32_t D, const double* det_xywh_dev,
+                                     const int32_t* n_keep_dev, int32_t Q, int32_t img_h, int32_t img_w, float* out_dev,
+                                     void* stream) {
+  OPD_REQUIRE(feat_dev && det_xywh_dev && n_keep_dev && out_dev, "opd_roi_features_bf16: NULL argument");
+  OPD_REQUIRE(B > 0 && fh > 0 && fw > 0 && Q > 0 && img_h > 0 && img_w > 0, "opd_roi_features_bf16: bad shape");
+  return opd::launch_roi_features(static_cast<const __nv_bfloat16*>(feat_dev), B, fh, fw, D, det_xywh_dev, n_keep_dev, Q, img_h,
+                                  img_w, out_dev, static_cast<cudaStream_t>(stream));
 }

@@ -45,6 +45,10 @@ struct HeadWeights {
 };
 // K8a: class logits [rows, 92] and sigmoid boxes [rows, 4] from the decoder output, fp32
 int launch_heads(const __nv_bfloat16* y, const HeadWeights& w, float* logits, float* boxes, int rows, cudaStream_t s);
+// ROI mean-pool + L2 norm of the encoder map over each compacted detection box (feature_extractor.py:39-88)
+int launch_roi_features(const __nv_bfloat16* feat, int B, int fh, int fw, int D, const double* xywh, const int32_t* n_keep,
+                        int Q, int img_h, int img_w, float* out, cudaStream_t s);
+
 // K8b: softmax + best class over the first C-1 logits + threshold + person filter + cxcywh -> xyxy -> pixel xywh +
 // foot point + per-frame stable compaction
 int launch_postprocess(const float* logits, const float* boxes, int B, int Q, int C, int H0, int W0, float threshold,

@@ -49,6 +49,8 @@ _lib.register("opd_detr_profile", C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int
 _lib.register("opd_detr_tap", C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int32)])
 _lib.register("opd_detr_tap_copy", C.c_int, [_P, C.c_char_p, _P, C.c_size_t, _P])
+_lib.register("opd_roi_features_bf16", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32,
+                                                C.c_int32, _P, _P])
 _lib.register("opd_detr_postprocess", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                                C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P])
 
@@ -71,6 +73,13 @@ def input_shape(h0: int, w0: int) -> tuple[int, int, int, int]:
     out = [C.c_int32() for _ in range(4)]
     _lib.check(_lib.lib().opd_detr_input_shape(h0, w0, *[C.byref(o) for o in out]), "opd_detr_input_shape")
     return tuple(o.value for o in out)
+
+
+def input_shape_noresize(h0: int, w0: int) -> tuple[int, int]:
+    """Stage-4 feature map of an h0 x w0 model input (every stride-2 layer: out = (in - 1) // 2 + 1, five times)."""
+    for _ in range(5):
+        h0, w0 = (h0 - 1) // 2 + 1, (w0 - 1) // 2 + 1
+    return h0, w0
 
 
 class DetrEngine:
@@ -99,6 +108,7 @@ class DetrEngine:
         self._h = handle.value
         self._ws: dict[tuple[int, int, int], object] = {}
         self._torch = torch
+        self.do_resize = True
 
     def set_debug(self, on: bool) -> None:
         _lib.check(_lib.lib().opd_detr_set_debug(self._h, int(on)), "opd_detr_set_debug")
@@ -107,6 +117,7 @@ class DetrEngine:
     def set_resize(self, on: bool) -> None:
         """False: frames are fed at their own size, like DetrImageProcessor(do_resize=False)."""
         _lib.check(_lib.lib().opd_detr_set_resize(self._h, int(on)), "opd_detr_set_resize")
+        self.do_resize = bool(on)
         self._ws.clear()
 
     def set_fusion(self, on: bool) -> None:
@@ -169,6 +180,24 @@ class DetrEngine:
         out = torch.empty(rows.value, cols.value, dtype=dt, device=f"cuda:{self.device_index}")
         _lib.check(_lib.lib().opd_detr_tap_copy(self._h, name.encode(), out.data_ptr(), out.numel() * out.element_size(),
                                                 _lib.stream_ptr()), "opd_detr_tap_copy")
+        return out
+
+    def roi_features(self, det_xywh, n_keep, h0: int, w0: int):
+        """ROI mean-pool + L2 norm of the LAST forward's encoder output over the compacted boxes
+        det_xywh [B,Q,4] f64 / n_keep [B] i32 (device) -> [B,Q,256] f32 (rows >= n_keep are zero).  No host sync."""
+        torch = self._torch
+        p, rows, cols, kind = _P(), C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(_lib.lib().opd_detr_tap(self._h, b"enc5", C.byref(p), C.byref(rows), C.byref(cols), C.byref(kind)), "opd_detr_tap")
+        B, Q = det_xywh.shape[0], det_xywh.shape[1]
+        _, _, fh, fw = input_shape(h0, w0) if self.do_resize else (0, 0, *input_shape_noresize(h0, w0))
+        if rows.value != B * fh * fw:
+            raise ValueError(f"roi_features: the last forward was not a batch of {B} frames of {h0}x{w0}")
+        if not (det_xywh.is_cuda and det_xywh.dtype == torch.float64 and det_xywh.is_contiguous() and n_keep.dtype == torch.int32):
+            raise ValueError("roi_features: det_xywh must be a contiguous float64 CUDA tensor, n_keep int32")
+        out = torch.empty(B, Q, cols.value, dtype=torch.float32, device=det_xywh.device)
+        rc = _lib.lib().opd_roi_features_bf16(p.value, B, fh, fw, cols.value, det_xywh.data_ptr(), n_keep.data_ptr(), Q, h0, w0,
+                                              out.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "opd_roi_features_bf16")
         return out
 
     def __del__(self):
@@ -294,10 +323,14 @@ class ViTDetector:
         """Batched detection.  Frames of equal size run as one device batch (chunks of `batch_size`); frames of
         different sizes are grouped by size (the reference pads to the batch maximum instead: different arithmetic at
         the padded borders, so equal-size groups are the faithful choice here)."""
+        return self._detect_batch(frames, with_features=False)[0]
+
+    def _detect_batch(self, frames: Sequence[np.ndarray], with_features: bool):
         if self.model is None:
             raise RuntimeError("Model not loaded. Call load_model() first.")
         torch = _lib.require_cuda()
         results: list[list[Detection] | None] = [None] * len(frames)
+        feats: list[np.ndarray | None] = [None] * len(frames)
         groups: dict[tuple[int, int], list[int]] = {}
         for i, f in enumerate(frames):
             f = np.asarray(f)
@@ -310,11 +343,13 @@ class ViTDetector:
                 chunk = idxs[c0:c0 + self.batch_size]
                 host = torch.from_numpy(np.stack([np.ascontiguousarray(frames[i]) for i in chunk])).pin_memory()
                 out = self.detect_tensors(host.to(dev, non_blocking=True))
+                f_dev = self.model.roi_features(out["det_xywh"], out["n_keep"], h0, w0) if with_features else None
                 n_keep = out["n_keep"].cpu().numpy()
                 xywh = out["det_xywh"].cpu().numpy().astype(np.float64)
                 score = out["det_score"].cpu().numpy()
                 foot = out["det_foot"].cpu().numpy()
                 query = out["det_query"].cpu().numpy()
+                f_host = f_dev.cpu().numpy() if with_features else None
                 for j, i in enumerate(chunk):
                     dets = []
                     for r in range(int(n_keep[j])):
@@ -323,17 +358,47 @@ class ViTDetector:
                                               class_name="person", camera_coords=(float(foot[j, r, 0]), float(foot[j, r, 1])),
                                               query_index=int(query[j, r])))
                     results[i] = dets
-        return [r if r is not None else [] for r in results]
+                    if with_features:
+                        feats[i] = f_host[j, :int(n_keep[j])].copy()
+                        for r, d in enumerate(dets):      # like the YOLO twin (yolov8_detector.py:153-156)
+                            d.features = feats[i][r]
+        return [r if r is not None else [] for r in results], feats
 
     def _get_foot_position(self, bbox: tuple[float, float, float, float]) -> tuple[float, float]:
         x, y, w, h = bbox
         return (x + w / 2, y + h)
 
-    def detect_with_features(self, frame: np.ndarray):
-        raise NotImplementedError("encoder ROI features are the next scope row (SURVEY.md §8f.4)")
+    def detect_with_features(self, frame: np.ndarray) -> tuple[list[Detection], np.ndarray]:
+        """(detections, features [n, 256] float32): the call DetectionPhase.execute makes per frame
+        (src/pipeline/phases/detection.py:94).  Features = ROI mean-pool of the DETR encoder output over each box,
+        L2-normalised (the removed ViTDetector._extract_features_from_outputs; arithmetic of
+        src/tracking/feature_extractor.py:39-88), computed on the device from the same forward."""
+        dets, feats = self.detect_batch_with_features([frame])
+        return dets[0], feats[0]
 
-    def extract_features(self, frame: np.ndarray, detections: list[Detection]):
-        raise NotImplementedError("encoder ROI features are the next scope row (SURVEY.md §8f.4)")
+    def detect_batch_with_features(self, frames: Sequence[np.ndarray]) -> tuple[list[list[Detection]], list[np.ndarray]]:
+        """Batched detect_with_features: one forward per device batch, features for every kept box."""
+        dets, feats = self._detect_batch(frames, with_features=True)
+        return dets, [f if f is not None else np.zeros((0, 256), np.float32) for f in feats]
+
+    def extract_features(self, frame: np.ndarray, detections: list[Detection]) -> np.ndarray:
+        """Encoder ROI features [len(detections), 256] float32 of GIVEN boxes on `frame` (one forward of the frame)."""
+        if self.model is None:
+            raise RuntimeError("Model not loaded. Call load_model() first.")
+        if len(detections) == 0:
+            return np.zeros((0, 256), np.float32)
+        torch = _lib.require_cuda()
+        f = np.ascontiguousarray(frame)
+        dev = torch.device("cuda", self._device_index())
+        self.forward_raw(torch.from_numpy(f[None]).to(dev))
+        out = []
+        for c0 in range(0, len(detections), N_QUERIES):      # rows of one [1, Q, 4] box table
+            chunk = detections[c0:c0 + N_QUERIES]
+            xywh = torch.zeros(1, N_QUERIES, 4, dtype=torch.float64)
+            xywh[0, :len(chunk)] = torch.tensor([list(d.bbox) for d in chunk], dtype=torch.float64)
+            n = torch.tensor([len(chunk)], dtype=torch.int32)
+            out.append(self.model.roi_features(xywh.to(dev), n.to(dev), f.shape[0], f.shape[1])[0, :len(chunk)].cpu().numpy())
+        return np.concatenate(out, axis=0)
 
     def get_attention_map(self, _frame: np.ndarray, _layer_index: int = -1):
         logger.warning("Attention maps are a debug aid of the reference and are not produced by the fused attention kernel")

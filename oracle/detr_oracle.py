@@ -336,6 +336,29 @@ def detections(logits, boxes, h0: int, w0: int, threshold: float, person_label: 
     return out
 
 
+def roi_features(encoder_features: np.ndarray, bboxes, image_shape: tuple[int, int]) -> np.ndarray:
+    """ROI mean-pool + L2 normalisation of the encoder map (the removed ViTDetector.extract_features): restates
+    FeatureExtractor.extract_roi_features (src/tracking/feature_extractor.py:39-88) and normalize_features (:21-37).
+    encoder_features [h, w, D]; bboxes (x, y, width, height) in pixels of image_shape = (height, width)."""
+    h, w, dim = encoder_features.shape
+    img_h, img_w = image_shape
+    rows = []
+    for x, y, width, height in bboxes:
+        x_min = int((x / img_w) * w)
+        y_min = int((y / img_h) * h)
+        x_max = int(((x + width) / img_w) * w)
+        y_max = int(((y + height) / img_h) * h)
+        x_min = max(0, min(x_min, w - 1))
+        y_min = max(0, min(y_min, h - 1))
+        x_max = max(x_min + 1, min(x_max, w))
+        y_max = max(y_min + 1, min(y_max, h))
+        rows.append(encoder_features[y_min:y_max, x_min:x_max, :].mean(axis=(0, 1)))
+    if not rows:
+        return np.array([]).reshape(0, dim)
+    f = np.array(rows)
+    return f / (np.linalg.norm(f, axis=1, keepdims=True) + 1e-8)
+
+
 def hf_model(w: dict):
     """transformers' own DetrForObjectDetection loaded with `w` (the arithmetic the reference ran)."""
     import os

@@ -157,3 +157,70 @@ def test_camera_frame_resize_path(detector, weights):
           f"label agreement {agree:.4f}")
     assert out["logits"].shape == (2, 100, 92)
     assert d_box < 0.015 * 1280 and d_score < 5e-2 and agree > 0.97 and m_box < 2.5 and m_score < 1e-2
+
+
+def test_roi_features_kernel_matches_reference_golden(built_lib):
+    """opd_roi_features_bf16 on the golden feature map (bf16 on the device) against the reference's own
+    FeatureExtractor output for the same boxes; fp32 sums in a different order + bf16 storage of the map: atol 2e-3
+    against the reference on the float32 map, 1e-5 against the oracle on the bf16-rounded map."""
+    import ctypes as C
+
+    import torch
+
+    from office_person_detection_vit_b200 import _lib
+    from office_person_detection_vit_b200.detection import vit_detector  # noqa: F401  (registers the symbol)
+
+    from .conftest import GOLDEN
+
+    g = np.load(GOLDEN / "roi_golden.npz")
+    img_h, img_w = (int(v) for v in g["image_shape"])
+    feat = torch.from_numpy(g["feat"]).to(torch.bfloat16)
+    fh, fw, D = feat.shape
+    n, Q = len(g["boxes"]), 40
+    xywh = torch.zeros(2, Q, 4, dtype=torch.float64)
+    xywh[0, :n] = torch.from_numpy(g["boxes"])
+    xywh[1, :5] = torch.from_numpy(g["boxes"][:5])
+    n_keep = torch.tensor([n, 5], dtype=torch.int32)
+    feat2 = torch.stack([feat, feat.flip(0)]).contiguous().cuda()
+    out = torch.full((2, Q, D), 7.0, dtype=torch.float32, device="cuda")
+    xy_d, nk_d = xywh.cuda(), n_keep.cuda()
+    rc = _lib.lib().opd_roi_features_bf16(feat2.data_ptr(), 2, fh, fw, D, xy_d.data_ptr(), nk_d.data_ptr(), Q, img_h, img_w,
+                                          out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "opd_roi_features_bf16")
+    out = out.cpu().numpy()
+    ref0 = do.roi_features(feat.float().numpy(), [tuple(b) for b in g["boxes"]], (img_h, img_w))
+    ref1 = do.roi_features(feat.flip(0).float().numpy(), [tuple(b) for b in g["boxes"][:5]], (img_h, img_w))
+    np.testing.assert_allclose(out[0, :n], ref0, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out[1, :5], ref1, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out[0, :n], g["features"], rtol=0, atol=2e-3)     # reference output, float32 map
+    assert (out[0, n:] == 0).all() and (out[1, 5:] == 0).all()
+
+
+def test_detect_with_features(detector, weights):
+    """detect_with_features / extract_features (DetectionPhase's per-frame call, detection.py:94): same detections as
+    detect(), one unit-norm 256-vector per detection, equal to the oracle's ROI pooling of the device's encoder output."""
+    import torch
+
+    eng = detector.model
+    eng.set_resize(False)
+    old = detector.confidence_threshold
+    try:
+        frame = do.synthetic_frames(1, 224, 320, seed=12)[0]
+        logits, boxes = eng.forward(torch.from_numpy(frame[None]).cuda())
+        sc, _, _ = do.postprocess(logits.cpu(), boxes.cpu(), 224, 320)
+        detector.confidence_threshold = float(sc.flatten().quantile(0.4))
+        dets, feats = detector.detect_with_features(frame)
+        plain = detector.detect(frame)
+        assert len(dets) == len(plain) > 3 and [d.bbox for d in dets] == [d.bbox for d in plain]
+        assert feats.shape == (len(dets), 256) and feats.dtype == np.float32
+        np.testing.assert_allclose(np.linalg.norm(feats, axis=1), 1.0, atol=1e-5)
+        assert all(d.features is not None and np.array_equal(d.features, feats[i]) for i, d in enumerate(dets))
+        enc = eng.tap("enc5").float().cpu().numpy().reshape(7, 10, 256)       # 224x320 -> 7x10 feature map
+        ref = do.roi_features(enc, [d.bbox for d in dets], (224, 320))
+        np.testing.assert_allclose(feats, ref, rtol=0, atol=1e-5)
+        again = detector.extract_features(frame, dets)
+        np.testing.assert_allclose(again, feats, rtol=0, atol=1e-6)
+        assert detector.extract_features(frame, []).shape == (0, 256)
+    finally:
+        detector.confidence_threshold = old
+        eng.set_resize(True)

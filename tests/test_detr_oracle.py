@@ -76,3 +76,13 @@ def test_resize_restatement_is_bit_exact(h0, w0, h1, w1):
     ref = torch.nn.functional.interpolate(torch.from_numpy(img), size=(h1, w1), mode="bilinear", antialias=True,
                                           align_corners=False).numpy()
     assert (do.resize_u8_antialias(img, h1, w1) == ref).all()
+
+
+def test_roi_features_match_the_reference_feature_extractor():
+    """oracle.roi_features == the reference's own FeatureExtractor.extract_roi_features output
+    (tests/golden/make_roi_golden.py imports src/tracking/feature_extractor.py): inside / clipped / degenerate boxes."""
+    g = np.load(GOLDEN / "roi_golden.npz")
+    got = do.roi_features(g["feat"], [tuple(b) for b in g["boxes"]], tuple(int(v) for v in g["image_shape"]))
+    assert got.dtype == g["features"].dtype and got.shape == g["features"].shape
+    np.testing.assert_array_equal(got, g["features"])
+    assert do.roi_features(g["feat"], [], (720, 1280)).shape == (0, 64)
