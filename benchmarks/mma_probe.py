@@ -1,0 +1,35 @@
+"""Cycles per tcgen05.mma (128 x N x 16) by shape, swizzle, accumulator rotation and A-operand view (csrc/mma_probe.cu)."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch  # noqa: E402
+
+from office_person_detection_vit_b200 import _lib  # noqa: E402
+
+_lib.register("opd_debug_mma_probe", C.c_int, [C.c_int32] * 8 + [C.c_void_p, C.c_void_p])
+out = torch.zeros(148, dtype=torch.int64, device="cuda")
+iters, grid = 2048, 148
+
+
+def run(N, sw32, n_acc, walk, sbo=0, step=0):
+    for _ in range(2):
+        _lib.check(_lib.lib().opd_debug_mma_probe(N, sw32, n_acc, iters, walk, grid, sbo, step, out.data_ptr(), None), "probe")
+    torch.cuda.synchronize()
+    return out[:grid].float().median().item() / iters
+
+
+print("N  swizzle  n_acc  cycles/MMA   (math floor N/2; operand floor (4096 + 32 N) / 128)")
+for sw32 in (0, 1):
+    for N in (32, 64, 128, 256):
+        for n_acc in (1, 2):
+            print(f"{N:3d}  {'32B ' if sw32 else '128B'}  {n_acc}  {run(N, sw32, n_acc, 1):7.1f}   {N / 2:.0f}  {(4096 + 32 * N) / 128:.0f}")
+print("shifted views (A = halo patch): ")
+print(f"stem   N=64  32B-swizzle  sbo 352  step 32:   {run(64, 1, 2, 0, 352, 32):7.1f}")
+print(f"stem   N=64  32B-swizzle  sbo 384  step 32:   {run(64, 1, 2, 0, 384, 32):7.1f}")
+print(f"stem   N=64  32B-swizzle  sbo 256  step 32:   {run(64, 1, 2, 0, 256, 32):7.1f}")
+print(f"halo   N=64  128B-swizzle sbo 2304 step 128:  {run(64, 0, 2, 0, 2304, 128):7.1f}")
+print(f"halo   N=64  128B-swizzle sbo 2304 step 32:   {run(64, 0, 2, 0, 2304, 32):7.1f}")
+print(f"halo   N=128 128B-swizzle sbo 2304 step 128:  {run(128, 0, 2, 0, 2304, 128):7.1f}")
+print(f"plain  N=64  128B-swizzle sbo 1024 step 32:   {run(64, 0, 2, 0, 1024, 32):7.1f}")

@@ -225,6 +225,13 @@ int opd_roi_features_bf16(const void* feat_dev, int32_t B, int32_t fh, int32_t f
                           const double* det_xywh_dev, const int32_t* n_keep_dev, int32_t Q, int32_t img_h,
                           int32_t img_w, float* out_dev, void* stream);
 
+/* Measurement probe (benchmarks/mma_probe.py), not on the product path: `iters` tcgen05.mma 128 x N x 16 issued by one
+ * thread per CTA, rotating over n_acc TMEM accumulators, operands with 32-byte (swizzle32 = 1) or 128-byte swizzled rows;
+ * a_sbo / a_step != 0: A is a shifted view (8-row groups a_sbo bytes apart, consecutive MMAs a_step bytes apart);
+ * cycles_dev[grid] receives clock64 ticks from the first issue to the completion of the last. */
+int opd_debug_mma_probe(int32_t N, int32_t swizzle32, int32_t n_acc, int32_t iters, int32_t walk, int32_t grid,
+                        int32_t a_sbo, int32_t a_step, uint64_t* cycles_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

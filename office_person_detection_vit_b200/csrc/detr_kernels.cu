@@ -412,43 +412,40 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const floa
 //   logits = y Wc^T + bc ; boxes = sigmoid(W2 relu(W1 relu(W0 y + b0) + b1) + b2)   (modeling_detr.py:1275-1297, 1401-1402)
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kHeadRows = 8;
+// acc[r] += x[k][r] * wv for the CTA's 8 rows: the row values of one k sit in 32 consecutive bytes (two LDS.128, broadcast)
+__device__ __forceinline__ void head_fma8(float (&acc)[kHeadRows], const float* xk, float wv) {
+  const float4 a = *reinterpret_cast<const float4*>(xk), b = *reinterpret_cast<const float4*>(xk + 4);
+  acc[0] = fmaf(a.x, wv, acc[0]); acc[1] = fmaf(a.y, wv, acc[1]); acc[2] = fmaf(a.z, wv, acc[2]); acc[3] = fmaf(a.w, wv, acc[3]);
+  acc[4] = fmaf(b.x, wv, acc[4]); acc[5] = fmaf(b.y, wv, acc[5]); acc[6] = fmaf(b.z, wv, acc[6]); acc[7] = fmaf(b.w, wv, acc[7]);
+}
 __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ y, HeadWeights w,
                                                     float* __restrict__ logits, float* __restrict__ boxes, int n_cls, int rows) {
-  __shared__ float s_y[kHeadRows][kD], s_h0[kHeadRows][kD], s_h1[kHeadRows][kD];
+  __shared__ __align__(16) float s_y[kD][kHeadRows], s_h0[kD][kHeadRows], s_h1[kD][kHeadRows];   // [k][row]
   const int row0 = blockIdx.x * kHeadRows, j = threadIdx.x;
   const int nr = min(kHeadRows, rows - row0);
 #pragma unroll
-  for (int r = 0; r < kHeadRows; ++r) s_y[r][j] = r < nr ? __bfloat162float(y[(long long)(row0 + r) * kD + j]) : 0.f;
+  for (int r = 0; r < kHeadRows; ++r) s_y[j][r] = r < nr ? __bfloat162float(y[(long long)(row0 + r) * kD + j]) : 0.f;
   __syncthreads();
   if (j < n_cls) {
     float acc[kHeadRows] = {};
-    for (int k = 0; k < kD; ++k) {
-      const float wv = w.wc_t[k * n_cls + j];
-#pragma unroll
-      for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(s_y[r][k], wv, acc[r]);
-    }
+#pragma unroll 8
+    for (int k = 0; k < kD; ++k) head_fma8(acc, s_y[k], w.wc_t[k * n_cls + j]);
     for (int r = 0; r < nr; ++r) logits[(long long)(row0 + r) * n_cls + j] = acc[r] + w.bc[j];
   }
   {
     float acc[kHeadRows] = {};
-    for (int k = 0; k < kD; ++k) {
-      const float wv = w.w0_t[k * kD + j];
+#pragma unroll 8
+    for (int k = 0; k < kD; ++k) head_fma8(acc, s_y[k], w.w0_t[k * kD + j]);
 #pragma unroll
-      for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(s_y[r][k], wv, acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < kHeadRows; ++r) s_h0[r][j] = fmaxf(acc[r] + w.b0[j], 0.f);
+    for (int r = 0; r < kHeadRows; ++r) s_h0[j][r] = fmaxf(acc[r] + w.b0[j], 0.f);
   }
   __syncthreads();
   {
     float acc[kHeadRows] = {};
-    for (int k = 0; k < kD; ++k) {
-      const float wv = w.w1_t[k * kD + j];
+#pragma unroll 8
+    for (int k = 0; k < kD; ++k) head_fma8(acc, s_h0[k], w.w1_t[k * kD + j]);
 #pragma unroll
-      for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(s_h0[r][k], wv, acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < kHeadRows; ++r) s_h1[r][j] = fmaxf(acc[r] + w.b1[j], 0.f);
+    for (int r = 0; r < kHeadRows; ++r) s_h1[j][r] = fmaxf(acc[r] + w.b1[j], 0.f);
   }
   __syncthreads();
   // 8 warps x 4 outputs: warp = row, each lane strides the 256 hidden values
@@ -457,7 +454,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       float acc = 0.f;
-      for (int k = lane; k < kD; k += 32) acc = fmaf(s_h1[warp][k], w.w2[o * kD + k], acc);
+      for (int k = lane; k < kD; k += 32) acc = fmaf(s_h1[k][warp], w.w2[o * kD + k], acc);
 #pragma unroll
       for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
       if (lane == 0) boxes[(long long)(row0 + warp) * 4 + o] = 1.f / (1.f + expf(-(acc + w.b2[o])));

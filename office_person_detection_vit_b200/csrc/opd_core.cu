@@ -10,6 +10,7 @@ std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_option_bneck_halo{1};
 std::atomic<int> g_option_attention_tc{1};
 std::atomic<int> g_option_attention_kv{64};
+std::atomic<int> g_option_probe{0};
 }  // namespace opd
 
 extern "C" {
@@ -23,6 +24,10 @@ int opd_set_option(const char* name, int32_t value) {
   }
   if (name && std::string(name) == "attention_kv") {
     opd::g_option_attention_kv.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "probe") {   // measurement probes (benchmarks/step_times.py): results are WRONG when set
+    opd::g_option_probe.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "attention_tc") {

@@ -28,7 +28,8 @@ constexpr int PATCH_SLOT = 7168;
 constexpr int kPatchStages = 8;
 constexpr int W_TAP_BYTES = 64 * 32;                   // one tap: 64 output channels x 16 input lanes
 constexpr int OUT_BYTES = 128 * 128;                   // staging box: 128 pixels x 64 channels bf16
-constexpr int kAccStages = 4;
+constexpr int kAccStages = 8;
+constexpr int kMmaGroup = 4;   // tiles whose MMAs are interleaved: consecutive MMAs never accumulate into the same TMEM tile
 constexpr int kThreads = 384;
 constexpr int kSmemBytes = 16 * W_TAP_BYTES + kPatchStages * PATCH_SLOT + 4 * OUT_BYTES + 1024;
 
@@ -36,6 +37,7 @@ struct StemParams {
   CUtensorMap tmS, tmW, tmD;
   int tiles_x, tiles_y, num_tiles;
   const float* bias;
+  int probe;   // measurement probes (opd_set_option("probe")): bit 0 no patch reloads, bit 1 no output stores
 };
 
 __global__ void s2d_preprocess_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, int bgr,
@@ -103,10 +105,10 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
   uint64_t* patch_full = bars;           // [8]
   uint64_t* patch_empty = bars + 8;      // [8]
-  uint64_t* acc_full = bars + 16;        // [4]
-  uint64_t* acc_empty = bars + 20;       // [4]
-  uint64_t* w_full = bars + 24;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 25);
+  uint64_t* acc_full = bars + 16;        // [8]
+  uint64_t* acc_empty = bars + 24;       // [8]
+  uint64_t* w_full = bars + 32;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 33);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
     ptx::mbar_init(w_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 9) ptx::tmem_alloc<256>(tmem_ptr);
+  if (warp == 9) ptx::tmem_alloc<kAccStages * 64>(tmem_ptr);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -146,7 +148,9 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
       for (int tap = 0; tap < 16; ++tap) ptx::tma_load_2d(&p.tmW, w_full, smem_w + tap * W_TAP_BYTES, tap * 16, 0);
       int ps = 0;
       uint32_t pphase = 0;
-      for (int t = first; t < n_tiles; t += step) {
+      int n = 0;
+      for (int t = first; t < n_tiles; t += step, ++n) {
+        if ((p.probe & 1) && n >= kPatchStages) break;
         int b, y0, x0;
         tile_origin(t, b, y0, x0);
         ptx::mbar_wait(&patch_empty[ps], pphase ^ 1);
@@ -161,31 +165,45 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
   } else if (warp == 9) {
     if (lane == 0) {
       ptx::mbar_wait(w_full, 0);
-      int ps = 0, as = 0;
-      uint32_t pphase = 0, aphase = 0;
       const uint64_t w0 = desc_sw32(ptx::smem_u32(smem_w), 256);
-      for (int t = first; t < n_tiles; t += step) {
-        ptx::mbar_wait(&acc_empty[as], aphase ^ 1);
-        ptx::mbar_wait(&patch_full[ps], pphase);
+      // Tiles are issued in groups of kMmaGroup with their MMAs interleaved tap by tap: a 128x64x16 MMA occupies the
+      // tensor pipe for 32 cycles but a dependent accumulate into the SAME TMEM tile waits ~100 cycles for the previous
+      // one, so back-to-back taps of one tile ran at a third of the pipe rate (measured: 16 MMAs = 1700 cycles).
+      uint32_t n = 0;   // tiles issued so far by this CTA: patch slot n % kPatchStages, accumulator stage n % kAccStages
+      for (int t = first; t < n_tiles;) {
+        uint32_t d[kMmaGroup];
+        uint64_t a[kMmaGroup];
+        int g = 0;
+#pragma unroll
+        for (int j = 0; j < kMmaGroup; ++j) {
+          if (t + j * step < n_tiles) {
+            const uint32_t m = n + j, as = m % kAccStages, ps = m % kPatchStages;
+            ptx::mbar_wait(&acc_empty[as], ((m / kAccStages) & 1) ^ 1);
+            if (!(p.probe & 1) || m < kPatchStages) ptx::mbar_wait(&patch_full[ps], (m / kPatchStages) & 1);
+            d[j] = tmem_base + as * 64;
+            // descriptors differ only in the 16-byte-granular start address field: base descriptor + constant per tap
+            a[j] = desc_sw32(ptx::smem_u32(smem_patch + ps * PATCH_SLOT), PATCH_W * 32);
+            g = j + 1;
+          }
+        }
         ptx::tc_fence_after_sync();
-        const uint32_t d = tmem_base + as * 64;
-        // descriptors differ only in the 16-byte-granular start address field: base descriptor + constant per tap
-        const uint64_t a0 = desc_sw32(ptx::smem_u32(smem_patch + ps * PATCH_SLOT), PATCH_W * 32);
 #pragma unroll
         for (int tap = 0; tap < 16; ++tap) {
-          const int r = tap >> 2, s = tap & 3;
-          ptx::umma_bf16_ss(d, a0 + (uint64_t)(((r * PATCH_W + s) * 32) >> 4), w0 + (uint64_t)((tap * W_TAP_BYTES) >> 4), kIdesc, tap != 0);
+          const int r = tap >> 2, sx = tap & 3;
+#pragma unroll
+          for (int j = 0; j < kMmaGroup; ++j)
+            if (j < g)
+              ptx::umma_bf16_ss(d[j], a[j] + (uint64_t)(((r * PATCH_W + sx) * 32) >> 4), w0 + (uint64_t)((tap * W_TAP_BYTES) >> 4), kIdesc,
+                                tap != 0);
         }
-        ptx::umma_commit(&patch_empty[ps]);
-        ptx::umma_commit(&acc_full[as]);
-        if (++ps == kPatchStages) {
-          ps = 0;
-          pphase ^= 1;
-        }
-        if (++as == kAccStages) {
-          as = 0;
-          aphase ^= 1;
-        }
+#pragma unroll
+        for (int j = 0; j < kMmaGroup; ++j)
+          if (j < g) {
+            ptx::umma_commit(&patch_empty[(n + j) % kPatchStages]);
+            ptx::umma_commit(&acc_full[(n + j) % kAccStages]);
+          }
+        n += g;
+        t += g * step;
       }
     }
   } else if (warp < 8) {
@@ -198,14 +216,14 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
     if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
     ptx::named_bar_sync(3, 256);
     uint8_t* my_out = smem_out + wg * 2 * OUT_BYTES;
-    uint32_t k = 0;   // tiles processed by this warpgroup: accumulator stage = wg + 2 * (k & 1), parity = (k >> 1) & 1
+    uint32_t k = 0;   // tiles processed by this warpgroup; its k-th tile is the CTA's tile n = 2k + wg: stage n % kAccStages
     int n = 0;
     for (int t = first; t < n_tiles; t += step, ++n) {
       if ((n & 1) != wg) continue;
       int b, y0, x0;
       tile_origin(t, b, y0, x0);
-      const int as = wg + 2 * (k & 1);
-      ptx::mbar_wait(&acc_full[as], (k >> 1) & 1);
+      const int as = (2 * k + wg) % kAccStages;
+      ptx::mbar_wait(&acc_full[as], ((2 * k + wg) / kAccStages) & 1);
       ptx::tc_fence_after_sync();
       uint32_t packed[32];
 #pragma unroll
@@ -230,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
             make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(1 + wg, 128);
-      if (et == 0) {
+      if (et == 0 && !(p.probe & 2)) {
         tma_store_4d(&p.tmD, buf, 0, x0, y0, b);
         ptx::tma_store_commit();
       }
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc<256>(tmem_base);
+  if (warp == 9) ptx::tmem_dealloc<kAccStages * 64>(tmem_base);
 }
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -293,6 +311,7 @@ int stem_launch(const StemPlan& plan, cudaStream_t stream) {
   p.tiles_y = (plan.H2 + TILE_H - 1) / TILE_H;
   p.num_tiles = plan.B * p.tiles_x * p.tiles_y;
   p.bias = plan.bias;
+  p.probe = g_option_probe.load();
   static bool configured = false;
   if (!configured) {
     OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

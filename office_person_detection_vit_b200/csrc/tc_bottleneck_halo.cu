@@ -218,10 +218,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
               // descriptors differ only in the 16-byte-granular start address field: base descriptor + small offsets
               const uint64_t db = desc_sw128(ptx::smem_u32(smem_b + bs * CHUNK_BYTES + (tap - tap0) * C::kTapBytes), 1024);
               const uint64_t da = patch_desc + (uint64_t)(((r * PATCH_W + s) * 128) >> 4);
+              // the two half tiles alternate MMA by MMA: a dependent accumulate into the same TMEM tile waits for the
+              // previous MMA's full latency (~100 cycles), three times the 32 cycles a 128x64x16 MMA occupies the pipe
 #pragma unroll
-              for (int h = 0; h < 2; ++h)
+              for (int k = 0; k < 64 / UMMA_K; ++k)
 #pragma unroll
-                for (int k = 0; k < 64 / UMMA_K; ++k)
+                for (int h = 0; h < 2; ++h)
                   ptx::umma_bf16_ss(tmem_acc1 + h * MID, da + (uint64_t)((h * SUB_W * 128 + k * 32) >> 4), db + (uint64_t)(2 * k), kIdesc1,
                                     (cb | tap | k) != 0);
             }
@@ -242,20 +244,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           for (int kb = 0; kb < kB2Blocks; ++kb) {
             ptx::mbar_wait(&b_full[bs], bphase);
             const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES);
+            uint64_t da[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               if (kb == 0) {
                 ptx::mbar_wait(&acc2_empty[h], acc2_phase[h] ^ 1);
                 acc2_phase[h] ^= 1;
               }
-              ptx::tc_fence_after_sync();
-              const uint64_t da = desc_sw128(
-                  ptx::smem_u32(kb < kCB ? smem_a2 + (h * kCB + kb) * CHUNK_BYTES : smem_res + h * CHUNK_BYTES), 1024);
-              const uint64_t db = desc_sw128(b_addr, 1024);
+              da[h] = desc_sw128(ptx::smem_u32(kb < kCB ? smem_a2 + (h * kCB + kb) * CHUNK_BYTES : smem_res + h * CHUNK_BYTES), 1024);
+            }
+            ptx::tc_fence_after_sync();
+            const uint64_t db = desc_sw128(b_addr, 1024);
 #pragma unroll
-              for (int k = 0; k < 64 / UMMA_K; ++k)
-                ptx::umma_bf16_ss(tmem_acc2 + h * BLOCK_N2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | k) != 0);
-              if (kb == kB2Blocks - 1) ptx::umma_commit(&acc2_full[h]);
+            for (int k = 0; k < 64 / UMMA_K; ++k)
+#pragma unroll
+              for (int h = 0; h < 2; ++h)   // alternate the two accumulators (see G1)
+                ptx::umma_bf16_ss(tmem_acc2 + h * BLOCK_N2, da[h] + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | k) != 0);
+            if (kb == kB2Blocks - 1) {
+              ptx::umma_commit(&acc2_full[0]);
+              ptx::umma_commit(&acc2_full[1]);
             }
             ptx::umma_commit(&b_empty[bs]);
             next_b();
