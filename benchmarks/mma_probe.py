@@ -1,5 +1,4 @@
 """Cycles per tcgen05.mma (128 x N x 16) by shape, swizzle, accumulator rotation and A-operand view (csrc/mma_probe.cu)."""
-import ctypes as C
 import sys
 from pathlib import Path
 
@@ -7,8 +6,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch  # noqa: E402
 
 from office_person_detection_vit_b200 import _lib  # noqa: E402
+from office_person_detection_vit_b200.detection import ops  # noqa: E402,F401  (registers opd_debug_mma_probe)
 
-_lib.register("opd_debug_mma_probe", C.c_int, [C.c_int32] * 8 + [C.c_void_p, C.c_void_p])
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 iters, grid = 2048, 148
 

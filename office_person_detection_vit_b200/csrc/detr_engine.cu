@@ -47,7 +47,7 @@ struct LnW {
 struct BlockW {
   bool has_shortcut = false;
   ConvW shortcut, c0, c1, c2;
-  bf16* w3sc = nullptr;      // [width, 2 * mid] = [layer.2 | shortcut] weights (64-channel, stride-1 first block only)
+  bf16* w3sc = nullptr;      // [width, mid + cin] = [layer.2 | shortcut] weights (first block of stages 1, 3 and 4)
   float* bias3sc = nullptr;  // layer.2 shift + shortcut shift
 };
 struct EncW {
@@ -298,6 +298,19 @@ int load_weights(opd_detr* m, const opd_tensor_f32* tensors, int n_tensors) {
             cat[(size_t)n * 128 + k] = L.last_packed[(size_t)n * 64 + k];
             cat[(size_t)n * 128 + 64 + k] = sc_w[(size_t)n * 64 + k];
           }
+          bias[n] = L.last_shift[n] + sc_b[n];
+        }
+        b.w3sc = L.upload(cat);
+        b.bias3sc = L.upload(bias);
+      }
+      if (l == 0 && mid >= 256 && L.rc == OPD_OK) {
+        // stages 3-4: [layer.2 | shortcut] along K for the dual-source GEMM (tc_gemm.cu gemm_plan_linear_plus_shortcut)
+        const int kk = mid + cin;
+        std::vector<bf16> cat((size_t)width * kk);
+        std::vector<float> bias(width);
+        for (int n = 0; n < width; ++n) {
+          for (int k = 0; k < mid; ++k) cat[(size_t)n * kk + k] = L.last_packed[(size_t)n * mid + k];
+          for (int k = 0; k < cin; ++k) cat[(size_t)n * kk + mid + k] = sc_w[(size_t)n * cin + k];
           bias[n] = L.last_shift[n] + sc_b[n];
         }
         b.w3sc = L.upload(cat);
@@ -625,8 +638,10 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
       const long long m_in = (long long)B * hh * ww, m_out = (long long)B * ho * wo;
       const bf16* res = x;
       const std::string bname = "stage" + std::to_string(s) + "." + std::to_string(l);
-      const bool fuse_sc = bw.has_shortcut && bw.w3sc && m->fuse_tail && m->fuse_shortcut && g_option_bneck_halo.load();
-      if (bw.has_shortcut && !fuse_sc) {
+      const bool fuse_sc = bw.has_shortcut && bw.w3sc && mid == 64 && m->fuse_tail && m->fuse_shortcut && g_option_bneck_halo.load();
+      // stages 3-4: the strided projection shortcut is a second A source of the 1x1 expansion GEMM (no shortcut tensor)
+      const bool dual_sc = bw.has_shortcut && bw.w3sc && mid >= 256 && m->fuse_shortcut;
+      if (bw.has_shortcut && !fuse_sc && !dual_sc) {
         cur_name = bname + ".shortcut";
         bf16* sc = static_cast<bf16*>(big_slot((cur + 1) % 3, act_bytes(m_out, width)));
         if (int rc = conv(x, hh, ww, bw.shortcut, sc, EPI_BIAS, nullptr)) return rc;
@@ -657,8 +672,20 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
       } else {
         cur_name = bname + ".conv3x3";
         if (int rc = conv(m1, hh, ww, bw.c1, m2, EPI_BIAS_RELU, nullptr)) return rc;
-        cur_name = bname + ".conv1x1b";
-        if (int rc = conv(m2, ho, wo, bw.c2, out, EPI_BIAS_RES_RELU, res)) return rc;
+        if (dual_sc) {
+          cur_name = bname + ".conv1x1b+shortcut";
+          if (!dry) {
+            GemmPlan gp;
+            ConvGeom g2{B, hh, ww, bw.shortcut.cin, 1, 1, stride, 0, 0, ho, wo};
+            if (int rc = gemm_plan_linear_plus_shortcut(&gp, m2, mid, x, g2, bw.w3sc, out, width, EPI_BIAS_RELU, bw.bias3sc)) return rc;
+            add(OPD_STEP_GEMM, cur_name, 2.0 * gp.M * gp.N * gp.K,
+                2.0 * gp.M * mid + 2.0 * gp.M * g2.C + 2.0 * gp.N * gp.K + 2.0 * gp.M * gp.N,
+                [gp](cudaStream_t st) { return gemm_launch(gp, st); });
+          }
+        } else {
+          cur_name = bname + ".conv1x1b";
+          if (int rc = conv(m2, ho, wo, bw.c2, out, EPI_BIAS_RES_RELU, res)) return rc;
+        }
       }
       if (!dry) taps["stage" + std::to_string(s) + "." + std::to_string(l)] = {out, m_out, width, 0};
       x = out;

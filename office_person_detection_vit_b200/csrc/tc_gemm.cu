@@ -51,9 +51,10 @@ __host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res) {
 }
 
 struct GemmParams {
-  CUtensorMap tmA, tmB, tmD, tmD2, tmR;
+  CUtensorMap tmA, tmB, tmD, tmD2, tmR, tmA2;
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_k_blocks;
+  int k_split;           // k-blocks >= k_split come from tmA2 (1x1 strided im2col of a second tensor; geometry in P, Q, stride)
   int im2col;
   int c_blocks;          // Cin / 64
   int KW, stride, pad_h, pad_w, P, Q;
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
     ptx::prefetch_tmap(&p.tmD);
+    if (p.k_split < p.num_k_blocks) ptx::prefetch_tmap(&p.tmA2);
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
         const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
         int base_w = 0, base_h = 0, img = 0;
-        if (p.im2col) {
+        if (p.im2col || p.k_split < p.num_k_blocks) {
           const int pq = p.P * p.Q;
           img = m0 / pq;
           const int rem = m0 - img * pq;
@@ -141,7 +143,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-          if (p.im2col) {
+          if (kb >= p.k_split) {
+            ptx::tma_load_im2col_4d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, (kb - p.k_split) * BLOCK_K, base_w,
+                                    base_h, img, (uint16_t)0, (uint16_t)0);
+          } else if (p.im2col) {
             const int tap = kb / p.c_blocks, cb = kb - tap * p.c_blocks;
             const int r = tap / p.KW, s = tap - r * p.KW;
             ptx::tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, cb * BLOCK_K, base_w,
@@ -534,6 +539,7 @@ int gemm_plan_linear(GemmPlan* plan, const __nv_bfloat16* A, int64_t lda, const 
   if (epi == EPI_BIAS_RES_LN) OPD_REQUIRE(gamma && beta, "gemm: LayerNorm epilogue needs gamma/beta");
   if (D2) OPD_REQUIRE(pos && pos_rows > 0, "gemm: D2 needs pos");
   if (int rc = finish_plan(plan)) return rc;
+  plan->k_split = K / BLOCK_K;
   if (int rc = make_tmap_2d(&plan->tmA, A, M, K, lda, BLOCK_M)) return rc;
   if (int rc = make_tmap_2d(&plan->tmB, W, N, K, K, plan->block_n)) return rc;
   if (int rc = make_tmap_2d(&plan->tmD, D, M, N, ldd, BLOCK_M)) return rc;
@@ -560,6 +566,7 @@ int gemm_plan_conv(GemmPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, co
   plan->bias = bias; plan->residual = residual; plan->ldr = N;
   if (epi == EPI_BIAS_RES_RELU) OPD_REQUIRE(residual != nullptr, "conv: residual epilogue without a residual");
   if (int rc = finish_plan(plan)) return rc;
+  plan->k_split = plan->K / BLOCK_K;
   if (int rc = make_tmap_im2col(&plan->tmA, x, g)) return rc;
   if (int rc = make_tmap_2d(&plan->tmB, W, N, plan->K, plan->K, plan->block_n)) return rc;
   if (int rc = make_tmap_2d(&plan->tmD, D, plan->M, N, N, BLOCK_M)) return rc;
@@ -569,6 +576,25 @@ int gemm_plan_conv(GemmPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, co
   } else {
     plan->tmR = plan->tmD;
   }
+  return OPD_OK;
+}
+
+int gemm_plan_linear_plus_shortcut(GemmPlan* plan, const __nv_bfloat16* A, int K1, const __nv_bfloat16* x2, const ConvGeom& g2,
+                                   const __nv_bfloat16* W, __nv_bfloat16* D, int N, int epi, const float* bias) {
+  *plan = GemmPlan{};
+  OPD_REQUIRE(g2.KH == 1 && g2.KW == 1 && g2.pad_h == 0 && g2.pad_w == 0 && g2.C % BLOCK_K == 0 && K1 % BLOCK_K == 0,
+              "gemm + shortcut: the second source must be a 1x1 / pad 0 convolution over a multiple of 64 channels");
+  OPD_REQUIRE(epi == EPI_BIAS || epi == EPI_BIAS_RELU, "gemm + shortcut: bias (+ ReLU) epilogues only");
+  plan->M = g2.B * g2.P * g2.Q; plan->N = N; plan->K = K1 + g2.C; plan->im2col = 0; plan->g2 = g2; plan->epi = epi;
+  plan->bias = bias;
+  if (int rc = finish_plan(plan)) return rc;
+  plan->k_split = K1 / BLOCK_K;
+  if (int rc = make_tmap_2d(&plan->tmA, A, plan->M, K1, K1, BLOCK_M)) return rc;
+  if (int rc = make_tmap_im2col(&plan->tmA2, x2, g2)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB, W, N, plan->K, plan->K, plan->block_n)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmD, D, plan->M, N, N, BLOCK_M)) return rc;
+  plan->tmD2 = plan->tmD;
+  plan->tmR = plan->tmD;
   return OPD_OK;
 }
 
@@ -582,6 +608,12 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   p.im2col = plan.im2col;
   p.c_blocks = plan.im2col ? plan.g.C / BLOCK_K : 1;
   p.KW = plan.g.KW; p.stride = plan.g.stride; p.pad_h = plan.g.pad_h; p.pad_w = plan.g.pad_w; p.P = plan.g.P; p.Q = plan.g.Q;
+  p.k_split = plan.k_split;
+  p.tmA2 = plan.tmA;
+  if (plan.k_split < p.num_k_blocks) {   // second source: its output geometry drives the base-pixel arithmetic
+    p.tmA2 = plan.tmA2;
+    p.KW = 1; p.stride = plan.g2.stride; p.pad_h = 0; p.pad_w = 0; p.P = plan.g2.P; p.Q = plan.g2.Q;
+  }
   p.epi = plan.epi; p.bias = plan.bias; p.residual = plan.residual; p.ldr = plan.ldr;
   p.gamma = plan.gamma; p.beta = plan.beta; p.pos = plan.pos; p.pos_rows = plan.pos_rows; p.has_d2 = plan.has_d2;
   const bool has_res = plan.epi == EPI_BIAS_RES_RELU || plan.epi == EPI_BIAS_RES_LN;

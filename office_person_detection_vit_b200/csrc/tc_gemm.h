@@ -29,6 +29,9 @@ struct ConvGeom {
 
 struct GemmPlan {
   CUtensorMap tmA, tmB, tmD, tmD2, tmR;   // tmR: residual, read by TMA in 64-column chunks
+  CUtensorMap tmA2;    // second A source (k-blocks >= k_split): NHWC tensor through a 1x1 / stride-s im2col map
+  int k_split;         // k-blocks served by tmA; == K / 64 without a second source
+  ConvGeom g2;         // geometry of the second source (1x1, stride s, pad 0)
   int M, N, K;
   int block_n;
   int im2col;          // 0: A is [M,K] rows; 1: A is NHWC through im2col TMA
@@ -53,6 +56,10 @@ int gemm_plan_linear(GemmPlan* plan, const __nv_bfloat16* A, int64_t lda, const 
 // NHWC x [B,H,W,C]; W [N, KH*KW*C] with K ordered (kh, kw, c); D [B*P*Q, N].
 int gemm_plan_conv(GemmPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const __nv_bfloat16* W, __nv_bfloat16* D,
                    int N, int epi, const float* bias, const __nv_bfloat16* residual);
+// D = epi( A[M,K1] * W[:, :K1]^T + im2col_1x1(x2; stride)[M,K2] * W[:, K1:]^T + bias ): a bottleneck's 1x1 expansion and its
+// strided projection shortcut accumulated into the same TMEM tile (no shortcut tensor).  W [N, K1 + K2]; g2: 1x1 geometry.
+int gemm_plan_linear_plus_shortcut(GemmPlan* plan, const __nv_bfloat16* A, int K1, const __nv_bfloat16* x2, const ConvGeom& g2,
+                                   const __nv_bfloat16* W, __nv_bfloat16* D, int N, int epi, const float* bias);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 
 int sm_count();

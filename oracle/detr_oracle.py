@@ -242,8 +242,9 @@ def backbone(w: dict, pixel_values: torch.Tensor, mode: str = "fp32", taps: dict
         for l in range(depth):
             p = f"model.backbone.model.encoder.stages.{s}.layers.{l}"
             stride = 2 if (l == 0 and s > 0) else 1
-            # CUDA path: the stage-1 projection shortcut is accumulated in fp32 inside the fused tail kernel (never stored)
-            res = conv(p + ".shortcut", x, stride, 1, False, rounded=not (s == 0)) if l == 0 else x
+            # CUDA path: the projection shortcut of stages 1, 3 and 4 is accumulated in fp32 together with layer.2 (second
+            # k-range of the same GEMM) and never stored; stage 2's is a stored bf16 tensor
+            res = conv(p + ".shortcut", x, stride, 1, False, rounded=(s == 1)) if l == 0 else x
             y = conv(p + ".layer.0", x, 1, 1, True)
             y = conv(p + ".layer.1", y, stride, 3, True)
             x = conv(p + ".layer.2", y, 1, 1, True, residual=res)
