@@ -8,15 +8,18 @@ import torch  # noqa: E402
 from office_person_detection_vit_b200 import _lib  # noqa: E402
 from office_person_detection_vit_b200.detection import ops  # noqa: E402,F401  (registers opd_debug_mma_probe)
 
-out = torch.zeros(148, dtype=torch.int64, device="cuda")
+out = torch.zeros(296, dtype=torch.int64, device="cuda")
 iters, grid = 2048, 148
 
 
-def run(N, sw32, n_acc, walk, sbo=0, step=0):
+def run(N, sw32, n_acc, walk, sbo=0, step=0, ld_iters=0, both=False, commit_every=0):
     for _ in range(2):
-        _lib.check(_lib.lib().opd_debug_mma_probe(N, sw32, n_acc, iters, walk, grid, sbo, step, out.data_ptr(), None), "probe")
+        _lib.check(_lib.lib().opd_debug_mma_probe(N, sw32, n_acc, iters, walk, grid, sbo, step, ld_iters, commit_every, out.data_ptr(), None), "probe")
     torch.cuda.synchronize()
-    return out[:grid].float().median().item() / iters
+    mma = out[:grid].float().median().item() / iters
+    if both:
+        return mma, out[grid:2 * grid].float().median().item() / max(ld_iters, 1)
+    return mma
 
 
 print("N  swizzle  n_acc  cycles/MMA   (math floor N/2; operand floor (4096 + 32 N) / 128)")
@@ -32,3 +35,10 @@ print(f"halo   N=64  128B-swizzle sbo 2304 step 128:  {run(64, 0, 2, 0, 2304, 12
 print(f"halo   N=64  128B-swizzle sbo 2304 step 32:   {run(64, 0, 2, 0, 2304, 32):7.1f}")
 print(f"halo   N=128 128B-swizzle sbo 2304 step 128:  {run(128, 0, 2, 0, 2304, 128):7.1f}")
 print(f"plain  N=64  128B-swizzle sbo 1024 step 32:   {run(64, 0, 2, 0, 1024, 32):7.1f}")
+print("TMEM reads against the MMAs (4 warps x tcgen05.ld 32x32b.x32 + wait = 16 KB per round):")
+for N, n_ld in ((64, 2048 * 48 // 150), (256, 2048 * 128 // 150), (64, 16), (256, 16)):
+    mma, ld = run(N, 0, 2, 1, ld_iters=n_ld, both=True)
+    print(f"  N={N:3d}: {mma:6.1f} cycles / MMA with {n_ld} loads per warp in flight, {ld:6.1f} cycles per load round")
+print("two tcgen05.commit every k MMAs (N = 64):")
+for k in (8, 16, 64, 256):
+    print(f"  every {k:3d} MMAs: {run(64, 0, 2, 1, commit_every=k):6.1f} cycles / MMA")

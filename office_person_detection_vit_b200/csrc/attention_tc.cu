@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(q_full, Q_BYTES);
       ptx::tma_load_2d(&p.tmQ, q_full, s_q, head * kD, b * p.Lq + q0);
       for (int j = 0; j < n_tiles; ++j) {
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t q_addr = ptx::smem_u32(s_q), p_addr = ptx::smem_u32(s_p);
       auto issue_s = [&](int j) {
         const int st = j & 1;

@@ -13,6 +13,7 @@
 // Arithmetic replaced: transformers models/resnet/modeling_resnet.py:57-88 (ResNetEmbeddings) with DetrFrozenBatchNorm2d
 // (models/detr/modeling_detr.py:185-222) folded into the weights.
 #include <algorithm>
+#include <cstdio>
 
 #include "detr_kernels.h"
 #include "opd_common.h"
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
   };
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(w_full, 16 * W_TAP_BYTES);
       for (int tap = 0; tap < 16; ++tap) ptx::tma_load_2d(&p.tmW, w_full, smem_w + tap * W_TAP_BYTES, tap * 16, 0);
       int ps = 0;
@@ -163,13 +164,14 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_wait(w_full, 0);
       const uint64_t w0 = desc_sw32(ptx::smem_u32(smem_w), 256);
       // Tiles are issued in groups of kMmaGroup with their MMAs interleaved tap by tap: a 128x64x16 MMA occupies the
       // tensor pipe for 32 cycles but a dependent accumulate into the SAME TMEM tile waits ~100 cycles for the previous
       // one, so back-to-back taps of one tile ran at a third of the pipe rate (measured: 16 MMAs = 1700 cycles).
       uint32_t n = 0;   // tiles issued so far by this CTA: patch slot n % kPatchStages, accumulator stage n % kAccStages
+      long long w_acc = 0, w_patch = 0, t_begin = clock64();   // probe bit 2: where the issuing thread waits
       for (int t = first; t < n_tiles;) {
         uint32_t d[kMmaGroup];
         uint64_t a[kMmaGroup];
@@ -178,8 +180,12 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
         for (int j = 0; j < kMmaGroup; ++j) {
           if (t + j * step < n_tiles) {
             const uint32_t m = n + j, as = m % kAccStages, ps = m % kPatchStages;
+            const long long c0 = clock64();
             ptx::mbar_wait(&acc_empty[as], ((m / kAccStages) & 1) ^ 1);
+            const long long c1 = clock64();
             if (!(p.probe & 1) || m < kPatchStages) ptx::mbar_wait(&patch_full[ps], (m / kPatchStages) & 1);
+            w_acc += c1 - c0;
+            w_patch += clock64() - c1;
             d[j] = tmem_base + as * 64;
             // descriptors differ only in the 16-byte-granular start address field: base descriptor + constant per tap
             a[j] = desc_sw32(ptx::smem_u32(smem_patch + ps * PATCH_SLOT), PATCH_W * 32);
@@ -205,6 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
         n += g;
         t += g * step;
       }
+      if ((p.probe & 4) && blockIdx.x == 0)
+        printf("stem CTA 0 MMA thread: %u tiles, %lld cycles total, %lld waiting for accumulators, %lld waiting for patches\n", n,
+               clock64() - t_begin, w_acc, w_patch);
     }
   } else if (warp < 8) {
     // two epilogue warpgroups; warpgroup g handles this CTA's tiles number g, g + 2, ... (accumulator stages g, g + 2)
@@ -218,12 +227,15 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
     uint8_t* my_out = smem_out + wg * 2 * OUT_BYTES;
     uint32_t k = 0;   // tiles processed by this warpgroup; its k-th tile is the CTA's tile n = 2k + wg: stage n % kAccStages
     int n = 0;
+    long long w_full = 0, t_begin = clock64();
     for (int t = first; t < n_tiles; t += step, ++n) {
       if ((n & 1) != wg) continue;
       int b, y0, x0;
       tile_origin(t, b, y0, x0);
       const int as = (2 * k + wg) % kAccStages;
+      const long long c0 = clock64();
       ptx::mbar_wait(&acc_full[as], ((2 * k + wg) / kAccStages) & 1);
+      w_full += clock64() - c0;
       ptx::tc_fence_after_sync();
       uint32_t packed[32];
 #pragma unroll
@@ -255,6 +267,9 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
       ++k;
     }
     if (et == 0) ptx::tma_store_wait_all<0>();
+    if ((p.probe & 4) && blockIdx.x == 0 && et == 0)
+      printf("stem CTA 0 epilogue warpgroup %d: %u tiles, %lld cycles total, %lld waiting for accumulators\n", wg, k, clock64() - t_begin,
+             w_full);
   }
   ptx::tc_fence_before_sync();
   __syncthreads();

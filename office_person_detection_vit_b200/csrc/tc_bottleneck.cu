@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
 
   if (warp == 8) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       auto advance = [&]() {
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     }
   } else if (warp == 11) {
     // ===================================== W3 tile producer (second GEMM) =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int st = 0;
       uint32_t ph = 0;
       for (int t = first; t < n_mblk; t += step)
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     //   G2(i2): the 1x1 expansion of tile i2 <= i1 (paced by the epilogue: it needs A2 from E1 and free acc2 buffers).
     // G2 steps have priority (they unblock the epilogue); whenever G2 cannot advance, G1 of the next tile keeps the ring
     // draining, so the fabric-bound phase of tile i+1 overlaps the HBM / epilogue-bound phase of tile i.
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const int n_my = first < n_mblk ? (n_mblk - first + step - 1) / step : 0;
       int i1 = 0, kb1 = 0, stage = 0, a1 = 0;          // G1 cursor, main ring, acc1 buffer
       uint32_t phase = 0, a1_phase = 0;
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     }
   } else if (warp == 10) {
     // ===================================== residual TMA producer =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::prefetch_tmap(&p.tmR);
       uint32_t k = 0;   // chunk counter per warpgroup: slot = wg * 2 + (k & 1), parity = (k >> 1) & 1
       for (int t = first; t < n_mblk; t += step)

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
 
   if (warp == 8) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int bs = 0;
       uint32_t bphase = 0, pc = 0;
       auto next_b = [&]() {
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     }
   } else if (warp == 9) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int bs = 0;
       uint32_t bphase = 0, n = 0, pc = 0, acc2_phase[2] = {0, 0};
       auto next_b = [&]() {
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     }
   } else if (warp == 10) {
     // ===================================== residual / shortcut-input TMA producer =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::prefetch_tmap(&p.tmR);
       uint32_t k = 0, n = 0;   // k: chunk counter per warpgroup: slot = wg * 2 + (k & 1), parity = (k >> 1) & 1
       for (int t = first; t < n_tiles; t += step, ++n) {

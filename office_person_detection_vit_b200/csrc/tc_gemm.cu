@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
 
   if (warp == 8) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     }
   } else if (warp == 9) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     }
   } else if (warp == 10) {
     // ===================================== residual TMA producer =====================================
-    if (kHasRes && lane == 0) {
+    if (kHasRes && ptx::elect_one()) {
       ptx::prefetch_tmap(&p.tmR);
       int rs = 0;
       uint32_t rphase = 0;
