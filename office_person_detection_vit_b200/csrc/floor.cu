@@ -84,6 +84,9 @@ struct FloorK {
   float Sxy[3];       // max(|H0j|, |H1j|) — magnitude bound of the X and Y rows
   float Sw[3];        // |H2j|
   float err_max;      // Δ/2
+  float fk[3];        // fast filter: K(x, y) = fk0 |x| + fk1 |y| + fk2 >= Sxy + PMAX Sw
+  float fT1, fT2;     // thresholds on |r̂| K for in-grid / out-of-grid points (floor_fast_kernel)
+  float fgx, fgy;     // -gx0 * inv_cw, -gy0 * inv_ch
   // grid
   double gx0, gy0, inv_cw, inv_ch;
   float gx0_f, gy0_f, inv_cw_f, inv_ch_f;
@@ -295,32 +298,6 @@ __global__ void __launch_bounds__(256) floor_exact_kernel(const FloorK p, int ce
 // one 16-byte store).  Warps never synchronise with each other inside the loop: every warp owns a private
 // slow-path queue in shared memory and drains it, 32 points at a time, through the float64 exact path.
 // ---------------------------------------------------------------------------------------------------------
-struct WarpCounter {
-  unsigned m[5];   // m[k] = lane bit k set ? 0 : ~0  (XOR mask so that (ballot ^ m) selects "bit k equals mine")
-  unsigned c0, c1; // counts of zones `lane` and `lane + 32`
-  __device__ __forceinline__ void init(int lane) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) m[k] = ((lane >> k) & 1) ? 0u : 0xffffffffu;
-    c0 = c1 = 0;
-  }
-  // zi < 0: not counted here.  All 32 lanes must call.
-  template <bool kWide>
-  __device__ __forceinline__ void add(int zi) {
-    const unsigned valid = __ballot_sync(0xffffffffu, zi >= 0);
-    if (valid == 0) return;
-    unsigned common = valid;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) common &= __ballot_sync(0xffffffffu, (zi >> k) & 1) ^ m[k];
-    if (kWide) {
-      const unsigned hi = __ballot_sync(0xffffffffu, (zi >> 5) & 1);
-      c0 += __popc(common & ~hi);
-      c1 += __popc(common & hi);
-    } else {
-      c0 += __popc(common);
-    }
-  }
-};
-
 __device__ __forceinline__ float4 ldg_stream(const float4* ptr) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -335,57 +312,62 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-// float32 filter.  Returns the class code of the point's cell (0..254), -1 when the point must take the float64
-// path, -2 when it is certainly in no zone (outside the grid by more than its error bound).
-//
-// Error bound (u = 2^-24): X̂, Ŷ, Ŵ carry <= 4u·S (two fma roundings + the float32 rounding of H), the
-// approximate reciprocal 2u and the products u, hence
-//   |p̂ - p| <= 16u·(|r̂|·(Sxy + max|p̂|·Sw) + max|p̂|)        (constants rounded up generously)
-// with Sxy >= |H0·|(|x|,|y|,1), |H1·|(...), Sw = |H2·|(|x|,|y|,1).
-__device__ __forceinline__ int filter_point(const FloorK& p, const uint8_t* s_grid, float x, float y) {
-  const float X = fmaf(p.Hf[0], x, fmaf(p.Hf[1], y, p.Hf[2]));
-  const float Y = fmaf(p.Hf[3], x, fmaf(p.Hf[4], y, p.Hf[5]));
-  const float W = fmaf(p.Hf[6], x, fmaf(p.Hf[7], y, p.Hf[8]));
-  const float r = rcp_approx(W);
-  const float px = X * r, py = Y * r;
-  const float ax = fabsf(x), ay = fabsf(y);
-  const float sxy = fmaf(p.Sxy[0], ax, fmaf(p.Sxy[1], ay, p.Sxy[2]));
-  const float sw = fmaf(p.Sw[0], ax, fmaf(p.Sw[1], ay, p.Sw[2]));
-  const float pm = fmaxf(fabsf(px), fabsf(py));
-  const float err = (16.0f * 5.9604645e-8f) * fmaf(fabsf(r), fmaf(pm, sw, sxy), pm);
-  // grid coordinates of p̂ and of its error box (cells)
-  const float fx = (px - p.gx0_f) * p.inv_cw_f;
-  const float fy = (py - p.gy0_f) * p.inv_ch_f;
-  const float ex = err * p.inv_cw_f, ey = err * p.inv_ch_f;
-  if (fx + ex < -1.0f || fx - ex > (float)(p.gw + 1) || fy + ey < -1.0f || fy - ey > (float)(p.gh + 1))
-    return -2;                        // the whole error box misses the (margin-padded) grid: no zone
-  if (!(err <= p.err_max)) return -1; // bound too loose (near the horizon), NaN or inf: exact path decides
-  if (!(fx >= 0.0f && fx < (float)p.gw && fy >= 0.0f && fy < (float)p.gh))
-    return -2;                        // within err_max of the grid border, which lies >= 1 px outside every polygon
-  const int code = s_grid[(int)fy * p.gw + (int)fx];
-  return code == kBoundary ? -1 : code;
-}
+// The float32 filter.  p̂ = (X̂ r̂, Ŷ r̂) with r̂ = rcp(Ŵ) satisfies, per coordinate (u = 2^-24; X̂, Ŷ, Ŵ carry <= 4u·S from
+// two fma roundings and the float32 rounding of H, the approximate reciprocal 2u, the products u; constants generous):
+//   |p̂ - p| <= 16u·(|r̂|·(Sxy + max|p̂|·Sw) + max|p̂|),   Sxy >= |H0·|(|x|,|y|,1), |H1·|(|x|,|y|,1),  Sw = |H2·|(|x|,|y|,1).
+// With PMAX = the largest |coordinate| of the grid box and K(x, y) = Sxy + PMAX·Sw (three multiply-adds with constants
+// from the host) the per-point decision needs ONE product q = |r̂|·K:
+//   p̂ inside the grid box (max|p̂| <= PMAX):  |p̂ - p| <= 16u·(q + PMAX) <= Δ/2  <=>  q <= T1 = Δ/(32u) - PMAX
+//       -> the cell of p̂ answers for p unless it is a boundary cell (cells within Δ of an edge are boundary cells);
+//   p̂ outside the grid box by d >= 0 (max|p̂| <= PMAX + d), m = the box's margin around every polygon (>= 1 px):
+//       |p̂ - p| <= 16u·(q + PMAX) + 16u·d·(|r̂|·Sw + 1) <= m/2 + d/2 < m + d   when  q <= T2 = min(m/(32u), PMAX/(32u)) - PMAX
+//       (|r̂|·Sw <= q/PMAX), so p is outside every polygon's bounding box -> no zone.
+// Everything else (q too large, NaN / inf, boundary cells) is decided by the float64 path, so the result never depends
+// on float32 rounding.  The constants are computed in float64 by fast_consts() and rounded toward the safe side.
+constexpr int kWarpQueue = 256;  // slow-path queue entries per warp (a unit adds at most 128)
+constexpr int kNoZone = 254;     // winner-grid byte of a uniform cell outside every zone (kBoundary = 255: float64 path)
 
-constexpr int kWarpQueue = 256;  // entries per warp (a unit adds at most 128)
-
-template <bool kWide>
 __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const FloorK p, int cells_rounded) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const SmemTables t = stage_tables(p, smem, cells_rounded);
-  unsigned char* cur = smem + (tables_smem_bytes(1, cells_rounded, p.stage_verts, p.n_verts) + 15) / 16 * 16;
+  FloorK pg = p;
+  pg.stage_grid = 0;   // the float64 path reads the CLASS grid from global memory (L2); shared memory holds the WINNER grid
+  const SmemTables t = stage_tables(pg, smem + cells_rounded, cells_rounded);
+  uint8_t* s_wgrid = smem;                                                              // [cells_rounded] winner per cell
+  unsigned char* cur = smem + cells_rounded + (tables_smem_bytes(0, cells_rounded, p.stage_verts, p.n_verts) + 15) / 16 * 16;
   unsigned* s_queue = reinterpret_cast<unsigned*>(cur);  // [32 warps][kWarpQueue]
   cur += (kFastThreads / 32) * kWarpQueue * 4;
-  unsigned* s_hist = reinterpret_cast<unsigned*>(cur);   // [64]
-  if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
+  unsigned* s_whist = reinterpret_cast<unsigned*>(cur);  // [32 warps][64]: private counters, ATOMS.POPC.INC per point
+  for (int i = threadIdx.x; i < (kFastThreads / 32) * 64; i += kFastThreads) s_whist[i] = 0;
+  __syncthreads();   // class_winner is staged
+  {
+    // winner grid: byte = selected zone of a uniform cell (kNoZone: none), kBoundary stays kBoundary
+    const uint4* src = reinterpret_cast<const uint4*>(p.grid);
+    uint4* dst = reinterpret_cast<uint4*>(s_wgrid);
+    for (int i = threadIdx.x; i < cells_rounded / 16; i += kFastThreads) {
+      uint4 v = src[i];
+      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t code = (w[j] >> (8 * b)) & 255u;
+          const int win = code == (uint32_t)kBoundary ? kBoundary : t.class_winner[code];
+          o |= (uint32_t)(win < 0 ? kNoZone : win) << (8 * b);
+        }
+        w[j] = o;
+      }
+      dst[i] = v;
+    }
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1;
   unsigned* q = s_queue + warp * kWarpQueue;
+  unsigned* wh = s_whist + warp * 64;
   unsigned qn = 0;  // warp-uniform
   const bool do_hist = p.hist != nullptr;
-  WarpCounter wc;
-  wc.init(lane);
 
   const float* in = static_cast<const float*>(p.in);
   const float2* in2 = reinterpret_cast<const float2*>(in);
@@ -395,29 +377,26 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
     while (qn > keep) {
       const unsigned take = qn < 32u ? qn : 32u;
       qn -= take;
-      int win = -1;
       if ((unsigned)lane < take) {
         const unsigned i = q[qn + lane];
         const float2 xy = in2[i];
         double px, py;
+        int win = -1;
         project_exact(p, (double)xy.x, (double)xy.y, &px, &py);
-        classify_exact(p, t, px, py, &win);
+        classify_exact(pg, t, px, py, &win);
         if (p.zone_idx) p.zone_idx[i] = win;
+        if (do_hist && win >= 0) atomicAdd(&wh[win], 1u);
       }
       __syncwarp();
-      if (do_hist) wc.add<kWide>(win);
     }
   };
 
-  // ---- main loop: branch-free float32 filter (arithmetic and bound of filter_point above), constants in registers ----
+  // ---- main loop: branch-free float32 filter, constants in registers ----
   const float h0 = p.Hf[0], h1 = p.Hf[1], h2 = p.Hf[2], h3 = p.Hf[3], h4 = p.Hf[4], h5 = p.Hf[5], h6 = p.Hf[6], h7 = p.Hf[7],
               h8 = p.Hf[8];
-  const float sxy0 = p.Sxy[0], sxy1 = p.Sxy[1], sxy2 = p.Sxy[2], sw0 = p.Sw[0], sw1 = p.Sw[1], sw2 = p.Sw[2];
-  const float gx0 = p.gx0_f, gy0 = p.gy0_f, icw = p.inv_cw_f, ich = p.inv_ch_f, err_max = p.err_max;
-  const float gwf = (float)p.gw, ghf = (float)p.gh, gw1 = (float)(p.gw + 1), gh1 = (float)(p.gh + 1);
-  const int gw = p.gw;
-  const uint8_t* s_grid = t.grid;
-  const int32_t* s_winner = t.class_winner;
+  const float k0 = p.fk[0], k1 = p.fk[1], k2 = p.fk[2], T1 = p.fT1, T2 = p.fT2;
+  const float icw = p.inv_cw_f, ich = p.inv_ch_f, ox = p.fgx, oy = p.fgy;   // fx = px * icw - gx0 * icw
+  const unsigned gw = (unsigned)p.gw, gh = (unsigned)p.gh;
   int32_t* const out_idx = p.zone_idx;
   const unsigned n_points = (unsigned)p.N;
   const unsigned n_units = (n_points + 127u) / 128u;
@@ -433,8 +412,17 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
       nb = ldg_stream(src + 1);
     }
   };
+  // Memory-level parallelism: one unit per warp in registers is 32 KB in flight per SM, a third of what HBM latency needs.
+  // The units kL2Ahead strides ahead are pulled into L2 (one 128-byte line per lane 0..7) so the register prefetch hits L2.
+  constexpr unsigned kL2Ahead = 4;
+  auto prefetch_l2 = [&](unsigned u) {
+    if (lane < 8 && u < n_units)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(in + 2ull * (u * 128ull) + lane * 32u));
+  };
+  for (unsigned a = 1; a < kL2Ahead; ++a) prefetch_l2(unit + a * w_stride);
   prefetch(unit);
   for (; unit < n_units; unit += w_stride) {
+    prefetch_l2(unit + kL2Ahead * w_stride);
     const unsigned base = unit * 128u + lane * 4u;
     float xs[4], ys[4];
     int n_live;
@@ -452,6 +440,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
     }
     prefetch(unit + w_stride);
     int zi[4];
+    unsigned slow_bits = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float x = xs[j], y = ys[j];
@@ -460,33 +449,19 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
       const float W = fmaf(h6, x, fmaf(h7, y, h8));
       const float r = rcp_approx(W);
       const float px = X * r, py = Y * r;
-      const float ax = fabsf(x), ay = fabsf(y);
-      const float sxy = fmaf(sxy0, ax, fmaf(sxy1, ay, sxy2));
-      const float sw = fmaf(sw0, ax, fmaf(sw1, ay, sw2));
-      const float pm = fmaxf(fabsf(px), fabsf(py));
-      const float err = (16.0f * 5.9604645e-8f) * fmaf(fabsf(r), fmaf(pm, sw, sxy), pm);
-      const float fx = (px - gx0) * icw, fy = (py - gy0) * ich;
-      const float ex = err * icw, ey = err * ich;
-      // the whole error box misses the (margin-padded) grid: certainly no zone
-      const bool outside = (fx + ex < -1.0f) | (fx - ex > gw1) | (fy + ey < -1.0f) | (fy - ey > gh1);
-      const bool err_ok = err <= err_max;                                        // false for NaN / inf
-      const bool in_grid = (fx >= 0.0f) & (fx < gwf) & (fy >= 0.0f) & (fy < ghf);
-      const bool live = j < n_live;
+      const float K = fabsf(x) * k0 + (fabsf(y) * k1 + k2);
+      const float qq = fabsf(r) * K;
+      const bool ok_in = qq <= T1, ok_out = qq <= T2;                      // false for NaN / inf
+      const int ix = __float2int_rd(fmaf(px, icw, ox)), iy = __float2int_rd(fmaf(py, ich, oy));
+      const bool in_grid = ((unsigned)ix < gw) & ((unsigned)iy < gh);      // NaN -> 0, guarded by ok_in
       int code = kBoundary;
-      if (in_grid) code = s_grid[(int)fy * gw + (int)fx];
-      const bool bnd = code == kBoundary;
-      // exact path: bound too loose, or a boundary cell; not for points that certainly miss every zone
-      const bool slow = live & !outside & (!err_ok | (in_grid & bnd));
-      const bool fast = live & err_ok & in_grid & !bnd & !outside;
-      int z = -1;
-      if (fast) z = s_winner[code];
+      if (in_grid & ok_in) code = s_wgrid[(unsigned)iy * gw + (unsigned)ix];
+      const bool live = j < n_live;
+      const bool decided = (code != kBoundary) | (!in_grid & ok_out);
+      const int z = code < kNoZone ? code : -1;
       zi[j] = z;
-      const unsigned sb = __ballot_sync(0xffffffffu, slow);
-      if (sb) {
-        if (slow) q[qn + __popc(sb & lt_mask)] = base + j;
-        qn += __popc(sb);
-      }
-      if (do_hist) wc.add<kWide>(z);
+      if (live & !decided) slow_bits |= 1u << j;
+      if (do_hist && live && z >= 0) atomicAdd(&wh[z], 1u);
     }
     if (out_idx) {
       if (n_live == 4) {
@@ -495,20 +470,31 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
         for (int j = 0; j < n_live; ++j) out_idx[base + j] = zi[j];
       }
     }
-    __syncwarp();  // queue entries and placeholder stores are ordered before the drain's loads / stores
-    if (qn > kWarpQueue - 128) drain(kWarpQueue - 128 - 32);
+    if (__any_sync(0xffffffffu, slow_bits != 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool slow = (slow_bits >> j) & 1u;
+        const unsigned sb = __ballot_sync(0xffffffffu, slow);
+        if (slow) q[qn + __popc(sb & lt_mask)] = base + j;
+        qn += __popc(sb);
+      }
+      __syncwarp();  // queue entries and placeholder stores are ordered before the drain's loads / stores
+      if (qn > kWarpQueue - 128) drain(kWarpQueue - 128 - 32);
+    }
   }
   __syncwarp();
   drain(0);
 
   if (do_hist) {
-    atomicAdd(&s_hist[lane], wc.c0);
-    if (kWide) atomicAdd(&s_hist[lane + 32], wc.c1);
     __syncthreads();
     // classified counts go to their bins; bin Z receives (points handled) - (classified), summed over CTAs
-    if (threadIdx.x < 64 && threadIdx.x < p.Z && s_hist[threadIdx.x]) {
-      atomicAdd(p.hist + threadIdx.x, (int)s_hist[threadIdx.x]);
-      atomicSub(p.hist + p.Z, (int)s_hist[threadIdx.x]);
+    if (threadIdx.x < 64 && threadIdx.x < p.Z) {
+      unsigned c = 0;
+      for (int w = 0; w < kFastThreads / 32; ++w) c += s_whist[w * 64 + threadIdx.x];
+      if (c) {
+        atomicAdd(p.hist + threadIdx.x, (int)c);
+        atomicSub(p.hist + p.Z, (int)c);
+      }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.hist + p.Z, (int)p.N);
   }
@@ -571,6 +557,7 @@ struct opd_zone_table {
   int device = 0, Z = 0, allow_overlap = 0;
   int gw = 1, gh = 1, cells_rounded = 16;
   double gx0 = 0, gy0 = 0, inv_cw = 1, inv_ch = 1, delta = 0.125;
+  double margin = 1.0;   // the grid box extends at least this far beyond every polygon's bounding box
   int n_classes = 1, n_boundary = 0, n_verts = 0;
   bool fast_ok = false;
   unsigned char* d_blob = nullptr;  // one allocation, carved below
@@ -648,6 +635,7 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
     }
     const double mx = std::max(1.0, 0.01 * (maxx - minx)), my = std::max(1.0, 0.01 * (maxy - miny));
     minx -= mx; maxx += mx; miny -= my; maxy += my;
+    zt->margin = std::min(mx, my) * (1.0 - 1e-9);
     const double ex = maxx - minx, ey = maxy - miny;
     int gw = (int)std::floor(std::sqrt((double)kGridCellBudget * ex / ey));
     gw = std::max(1, std::min(gw, kGridCellBudget));
@@ -889,12 +877,24 @@ extern "C" int opd_floor_project_classify_count_f32(const opd_floor_params* p, c
                     (zone_idx_dev || hist_dev) && (reinterpret_cast<uintptr_t>(in_dev) % 16 == 0) &&
                     (zone_idx_dev == nullptr || reinterpret_cast<uintptr_t>(zone_idx_dev) % 16 == 0);
   if (!fast) return launch_exact<float>(k, zt, s);
+  // constants of the float32 filter (derivation above floor_fast_kernel), float64 on the host, rounded to the safe side
+  const double u32 = 32.0 * 5.9604645e-8;
+  const double gx1 = zt->gx0 + zt->gw / zt->inv_cw, gy1 = zt->gy0 + zt->gh / zt->inv_ch;
+  const double pmax = 1.0001 * std::max(std::max(std::fabs(zt->gx0), std::fabs(gx1)), std::max(std::fabs(zt->gy0), std::fabs(gy1))) + 1.0;
+  const double t1 = zt->delta / u32 - pmax;
+  const double t2 = std::min(zt->margin, pmax * 0.99) / u32 - pmax;
+  if (!(t1 > 0.0 && t2 > 0.0)) return launch_exact<float>(k, zt, s);
+  for (int j = 0; j < 3; ++j) k.fk[j] = nextafterf((float)(((double)k.Sxy[j] + pmax * (double)k.Sw[j]) * (1.0 + 1e-6)), INFINITY);
+  k.fT1 = nextafterf((float)(t1 * (1.0 - 1e-6)), 0.0f);
+  k.fT2 = nextafterf((float)(t2 * (1.0 - 1e-6)), 0.0f);
+  k.fgx = (float)(-zt->gx0 * zt->inv_cw);
+  k.fgy = (float)(-zt->gy0 * zt->inv_ch);
   int sms = 148;
   if (int rc = device_sm_count(zt->device, &sms)) return rc;
   k.stage_grid = 1;
-  const size_t smem = (tables_smem_bytes(1, zt->cells_rounded, k.stage_verts, k.n_verts) + 15) / 16 * 16 +
-                      (kFastThreads / 32) * kWarpQueue * 4 + 64 * 4 + 16;
-  auto kern = zt->Z > 32 ? floor_fast_kernel<true> : floor_fast_kernel<false>;
+  const size_t smem = (size_t)zt->cells_rounded + (tables_smem_bytes(0, zt->cells_rounded, k.stage_verts, k.n_verts) + 15) / 16 * 16 +
+                      (kFastThreads / 32) * kWarpQueue * 4 + (kFastThreads / 32) * 64 * 4 + 16;
+  auto kern = floor_fast_kernel;
   OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long chunks = (N + kFastChunk - 1) / kFastChunk;
   const unsigned blocks = (unsigned)std::min<long long>(chunks, sms);
