@@ -399,77 +399,24 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
   const unsigned gw = (unsigned)p.gw, gh = (unsigned)p.gh;
   int32_t* const out_idx = p.zone_idx;
   const unsigned n_points = (unsigned)p.N;
-  const unsigned n_units = (n_points + 127u) / 128u;
-  const unsigned w_stride = gridDim.x * (kFastThreads / 32);
-  unsigned unit = blockIdx.x * (kFastThreads / 32) + warp;
-  // software prefetch: the next unit's two 16-byte loads are in flight while this unit is processed
-  float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
-  auto prefetch = [&](unsigned u) {
-    const unsigned base = u * 128u + lane * 4u;
-    if (u < n_units && base + 4u <= n_points) {
-      const float4* src = reinterpret_cast<const float4*>(in + 2ull * base);
-      na = ldg_stream(src);
-      nb = ldg_stream(src + 1);
-    }
+  // one point: zone (or -1) from the winner grid, `slow` when the float64 path must decide
+  auto filter = [&](float x, float y, bool& slow) -> int {
+    const float X = fmaf(h0, x, fmaf(h1, y, h2));
+    const float Y = fmaf(h3, x, fmaf(h4, y, h5));
+    const float W = fmaf(h6, x, fmaf(h7, y, h8));
+    const float r = rcp_approx(W);
+    const float px = X * r, py = Y * r;
+    const float K = fabsf(x) * k0 + (fabsf(y) * k1 + k2);
+    const float qq = fabsf(r) * K;
+    const bool ok_in = qq <= T1, ok_out = qq <= T2;                      // false for NaN / inf
+    const int ix = __float2int_rd(fmaf(px, icw, ox)), iy = __float2int_rd(fmaf(py, ich, oy));
+    const bool in_grid = ((unsigned)ix < gw) & ((unsigned)iy < gh);      // NaN -> 0, guarded by ok_in
+    int code = kBoundary;
+    if (in_grid & ok_in) code = s_wgrid[(unsigned)iy * gw + (unsigned)ix];
+    slow = !((code != kBoundary) | (!in_grid & ok_out));
+    return code < kNoZone ? code : -1;
   };
-  // Memory-level parallelism: one unit per warp in registers is 32 KB in flight per SM, a third of what HBM latency needs.
-  // The units kL2Ahead strides ahead are pulled into L2 (one 128-byte line per lane 0..7) so the register prefetch hits L2.
-  constexpr unsigned kL2Ahead = 4;
-  auto prefetch_l2 = [&](unsigned u) {
-    if (lane < 8 && u < n_units)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(in + 2ull * (u * 128ull) + lane * 32u));
-  };
-  for (unsigned a = 1; a < kL2Ahead; ++a) prefetch_l2(unit + a * w_stride);
-  prefetch(unit);
-  for (; unit < n_units; unit += w_stride) {
-    prefetch_l2(unit + kL2Ahead * w_stride);
-    const unsigned base = unit * 128u + lane * 4u;
-    float xs[4], ys[4];
-    int n_live;
-    if (base + 4u <= n_points) {
-      xs[0] = na.x; ys[0] = na.y; xs[1] = na.z; ys[1] = na.w;
-      xs[2] = nb.x; ys[2] = nb.y; xs[3] = nb.z; ys[3] = nb.w;
-      n_live = 4;
-    } else {
-      n_live = base < n_points ? (int)(n_points - base) : 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        xs[j] = j < n_live ? in[2ull * (base + j) + 0] : 0.f;
-        ys[j] = j < n_live ? in[2ull * (base + j) + 1] : 0.f;
-      }
-    }
-    prefetch(unit + w_stride);
-    int zi[4];
-    unsigned slow_bits = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x = xs[j], y = ys[j];
-      const float X = fmaf(h0, x, fmaf(h1, y, h2));
-      const float Y = fmaf(h3, x, fmaf(h4, y, h5));
-      const float W = fmaf(h6, x, fmaf(h7, y, h8));
-      const float r = rcp_approx(W);
-      const float px = X * r, py = Y * r;
-      const float K = fabsf(x) * k0 + (fabsf(y) * k1 + k2);
-      const float qq = fabsf(r) * K;
-      const bool ok_in = qq <= T1, ok_out = qq <= T2;                      // false for NaN / inf
-      const int ix = __float2int_rd(fmaf(px, icw, ox)), iy = __float2int_rd(fmaf(py, ich, oy));
-      const bool in_grid = ((unsigned)ix < gw) & ((unsigned)iy < gh);      // NaN -> 0, guarded by ok_in
-      int code = kBoundary;
-      if (in_grid & ok_in) code = s_wgrid[(unsigned)iy * gw + (unsigned)ix];
-      const bool live = j < n_live;
-      const bool decided = (code != kBoundary) | (!in_grid & ok_out);
-      const int z = code < kNoZone ? code : -1;
-      zi[j] = z;
-      if (live & !decided) slow_bits |= 1u << j;
-      if (do_hist && live && z >= 0) atomicAdd(&wh[z], 1u);
-    }
-    if (out_idx) {
-      if (n_live == 4) {
-        *reinterpret_cast<int4*>(out_idx + base) = make_int4(zi[0], zi[1], zi[2], zi[3]);
-      } else {
-        for (int j = 0; j < n_live; ++j) out_idx[base + j] = zi[j];
-      }
-    }
+  auto enqueue = [&](unsigned slow_bits, unsigned base) {
     if (__any_sync(0xffffffffu, slow_bits != 0)) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -481,6 +428,64 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
       __syncwarp();  // queue entries and placeholder stores are ordered before the drain's loads / stores
       if (qn > kWarpQueue - 128) drain(kWarpQueue - 128 - 32);
     }
+  };
+
+  // Full units: 128 consecutive points per warp and iteration, lane l owns points 4l .. 4l+3 (two 16-byte loads, one
+  // 16-byte store).  The next unit's loads are in flight while this one is processed, and the units kL2Ahead strides
+  // ahead are pulled into L2 (one 128-byte line per lane 0..7): one unit per warp in registers is only 32 KB in flight
+  // per SM, a third of what the HBM latency needs.
+  const unsigned n_full = n_points / 128u;
+  const unsigned w_stride = gridDim.x * (kFastThreads / 32);
+  constexpr unsigned kL2Ahead = 4;
+  unsigned unit = blockIdx.x * (kFastThreads / 32) + warp;
+  const float4* src = reinterpret_cast<const float4*>(in) + ((size_t)unit * 64u + lane * 2u);
+  const size_t src_stride = (size_t)w_stride * 64u;
+  const char* l2p = reinterpret_cast<const char*>(in) + ((size_t)unit * 1024u + (lane & 7) * 128u);
+  const bool l2_lane = lane < 8;
+  for (unsigned a = 1; a < kL2Ahead; ++a)
+    if (l2_lane && unit + a * w_stride < n_full) asm volatile("prefetch.global.L2 [%0];" ::"l"(l2p + a * (src_stride * 16u)));
+  float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+  if (unit < n_full) {
+    na = ldg_stream(src);
+    nb = ldg_stream(src + 1);
+  }
+  for (; unit < n_full; unit += w_stride) {
+    const float4 a = na, b = nb;
+    src += src_stride;
+    l2p += src_stride * 16u;
+    if (unit + w_stride < n_full) {
+      na = ldg_stream(src);
+      nb = ldg_stream(src + 1);
+    }
+    if (l2_lane && unit + kL2Ahead * w_stride < n_full)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(l2p + (kL2Ahead - 1) * (src_stride * 16u)));
+    bool s0, s1, s2, s3;
+    const int z0 = filter(a.x, a.y, s0), z1 = filter(a.z, a.w, s1), z2 = filter(b.x, b.y, s2), z3 = filter(b.z, b.w, s3);
+    const unsigned base = unit * 128u + lane * 4u;
+    if (out_idx) *reinterpret_cast<int4*>(out_idx + base) = make_int4(z0, z1, z2, z3);
+    if (do_hist) {
+      if (z0 >= 0) atomicAdd(&wh[z0], 1u);
+      if (z1 >= 0) atomicAdd(&wh[z1], 1u);
+      if (z2 >= 0) atomicAdd(&wh[z2], 1u);
+      if (z3 >= 0) atomicAdd(&wh[z3], 1u);
+    }
+    enqueue((unsigned)s0 | ((unsigned)s1 << 1) | ((unsigned)s2 << 2) | ((unsigned)s3 << 3), base);
+  }
+  // ragged tail (< 128 points): the warp that would own unit n_full, one point per lane and pass
+  if (unit == n_full && (n_points & 127u)) {
+    const unsigned base = n_full * 128u + lane * 4u;
+    int zi[4];
+    unsigned slow_bits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool live = base + j < n_points;
+      bool slow = false;
+      zi[j] = live ? filter(in[2ull * (base + j)], in[2ull * (base + j) + 1], slow) : -1;
+      if (live && slow) slow_bits |= 1u << j;
+      if (live && out_idx) out_idx[base + j] = zi[j];
+      if (do_hist && live && zi[j] >= 0) atomicAdd(&wh[zi[j]], 1u);
+    }
+    enqueue(slow_bits, base);
   }
   __syncwarp();
   drain(0);
