@@ -606,8 +606,14 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
 
   // ---- K2 stem: 4x1 convolution over X2, pad 2 rows above / 1 below ----
   bf16* stem_out = static_cast<bf16*>(big_slot(1, act_bytes(Ms, 64)));
+  // max pooling fused into the stem's epilogue (stem_conv.cu): the stem output never reaches memory.  Debug plans keep the
+  // two kernels (the "stem" tap) unless opd_set_option("stem_pool", 2) forces the fused kernel.
+  const int sp_opt = g_option_stem_pool.load();
+  const bool fuse_pool = stem_halo && (sp_opt == 2 || (sp_opt == 1 && !dbg));
   if (!dry) {
-    if (stem_halo) {
+    if (fuse_pool) {
+      // issued below, once the pooled buffer is known
+    } else if (stem_halo) {
       StemPlan sp;
       if (int rc = stem_plan(&sp, x2, B, sh.Hs, sh.Ws, m->stem_taps, m->stem.bias, stem_out)) return rc;
       add(OPD_STEP_CONV, "stem", 2.0 * Ms * 64 * 147, (double)act_bytes(Ms, 16) + (double)act_bytes(Ms, 64),
@@ -619,13 +625,21 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
       if (int rc = gemm_plan_conv(&gp, x2, g, m->stem.w, stem_out, 64, EPI_BIAS_RELU, m->stem.bias, nullptr)) return rc;
       add_gemm(gp);
     }
-    taps["stem"] = {stem_out, Ms, 64, 0};
+    if (!fuse_pool) taps["stem"] = {stem_out, Ms, 64, 0};
   }
   // ---- K3 max pooling ----
   bf16* x = static_cast<bf16*>(big_slot(2, act_bytes(Mp, 64)));
   if (!dry) {
-    add(OPD_STEP_ELEMENTWISE, "maxpool", 0.0, (double)act_bytes(Ms, 64) + (double)act_bytes(Mp, 64),
-        [B, sh, stem_out, x](cudaStream_t s) { return launch_maxpool(stem_out, B, sh.Hs, sh.Ws, 64, x, sh.Hp, sh.Wp, s); });
+    if (fuse_pool) {
+      StemPlan sp;
+      if (int rc = stem_plan(&sp, x2, B, sh.Hs, sh.Ws, m->stem_taps, m->stem.bias, stem_out, x)) return rc;
+      OPD_REQUIRE(sp.P == sh.Hp && sp.Q == sh.Wp, "stem + pool: pooled size %dx%d, expected %dx%d", sp.P, sp.Q, sh.Hp, sh.Wp);
+      add(OPD_STEP_CONV, "stem+maxpool", 2.0 * Ms * 64 * 147, (double)act_bytes(Ms, 16) + (double)act_bytes(Mp, 64),
+          [sp](cudaStream_t s) { return stem_launch(sp, s); });
+    } else {
+      add(OPD_STEP_ELEMENTWISE, "maxpool", 0.0, (double)act_bytes(Ms, 64) + (double)act_bytes(Mp, 64),
+          [B, sh, stem_out, x](cudaStream_t s) { return launch_maxpool(stem_out, B, sh.Hs, sh.Ws, 64, x, sh.Hp, sh.Wp, s); });
+    }
     taps["pool"] = {x, Mp, 64, 0};
   }
   int cur = 2, hh = sh.Hp, ww = sh.Wp, bi = 0;

@@ -11,6 +11,7 @@ std::atomic<int> g_option_bneck_halo{1};
 std::atomic<int> g_option_attention_tc{1};
 std::atomic<int> g_option_attention_kv{64};
 std::atomic<int> g_option_probe{0};
+std::atomic<int> g_option_stem_pool{1};
 }  // namespace opd
 
 extern "C" {
@@ -28,6 +29,10 @@ int opd_set_option(const char* name, int32_t value) {
   }
   if (name && std::string(name) == "probe") {   // measurement probes (benchmarks/step_times.py): results are WRONG when set
     opd::g_option_probe.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "stem_pool") {   // 0: stem and max pooling as two kernels; 1: fused (default); 2: fused in debug plans too
+    opd::g_option_stem_pool.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "attention_tc") {

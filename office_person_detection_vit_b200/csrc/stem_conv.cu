@@ -38,6 +38,8 @@ struct StemParams {
   CUtensorMap tmS, tmW, tmD;
   int tiles_x, tiles_y, num_tiles;
   const float* bias;
+  __nv_bfloat16* pooled;   // kPool: max-pool output [B, P, Q, 64]
+  int H2, W2, P, Q;        // stem output size, pooled size
   int probe;   // measurement probes (opd_set_option("probe")): bit 0 no patch reloads, bit 1 no output stores
 };
 
@@ -96,6 +98,14 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t addr, uint32_t sbo_bytes)
   return d;
 }
 
+// kPool: the 3x3 / stride 2 / pad 1 max pooling (modeling_resnet.py:69, nn.MaxPool2d) runs in the epilogue.  A work tile is a
+// 16 x 16 block of stem outputs = two MMA tiles side by side (columns 0-7 / 8-15, one per epilogue warpgroup) whose origin
+// is (14 ty - 1, 14 tx - 1): it holds every input of pooled outputs (7 ty .. 7 ty + 6, 7 tx .. 7 tx + 6).  Both warpgroups
+// write bias + ReLU'd bf16 pixels (zeros outside the image, which is what the pooling's -inf padding amounts to after a
+// ReLU) into a shared-memory block, and the 256 epilogue threads reduce it to 7 x 7 x 64 pooled values stored straight to
+// global memory.  The stem output (2.2 GB per 64 frames) is never written or read back; the price is (16/14)^2 = 1.31x
+// the MMA work, on a kernel whose tensor pipe was two thirds idle.
+template <bool kPool>
 __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant__ StemParams p) {
   constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(128, 64);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -135,13 +145,26 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   const int first = blockIdx.x, step = gridDim.x, n_tiles = p.num_tiles;
+  // MMA tile t -> image b and the stem-output coordinates of its first pixel.  kPool: t = 2 * work tile + half.
   auto tile_origin = [&](int t, int& b, int& y0, int& x0) {
-    const int tx = t % p.tiles_x;
-    const int r = t / p.tiles_x;
-    x0 = tx * TILE_W;
-    y0 = (r % p.tiles_y) * TILE_H;
+    const int w = kPool ? t >> 1 : t;
+    const int tx = w % p.tiles_x;
+    const int r = w / p.tiles_x;
+    const int ty = r % p.tiles_y;
     b = r / p.tiles_y;
+    if (kPool) {
+      x0 = tx * 14 - 1 + (t & 1) * TILE_W;
+      y0 = ty * 14 - 1;
+    } else {
+      x0 = tx * TILE_W;
+      y0 = ty * TILE_H;
+    }
   };
+
+  // this CTA's n-th MMA tile.  kPool: both halves of a work tile belong to the same CTA (n = 2 * local work tile + half)
+  const int n_units = kPool ? n_tiles / 2 : n_tiles;
+  const uint32_t n_my = first < n_units ? (uint32_t)((n_units - first + step - 1) / step) * (kPool ? 2u : 1u) : 0u;
+  auto tile_of = [&](uint32_t n) -> int { return kPool ? 2 * (first + (int)(n >> 1) * step) + (int)(n & 1) : first + (int)n * step; };
 
   if (warp == 8) {
     if (ptx::elect_one()) {
@@ -149,11 +172,10 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
       for (int tap = 0; tap < 16; ++tap) ptx::tma_load_2d(&p.tmW, w_full, smem_w + tap * W_TAP_BYTES, tap * 16, 0);
       int ps = 0;
       uint32_t pphase = 0;
-      int n = 0;
-      for (int t = first; t < n_tiles; t += step, ++n) {
+      for (uint32_t n = 0; n < n_my; ++n) {
         if ((p.probe & 1) && n >= kPatchStages) break;
         int b, y0, x0;
-        tile_origin(t, b, y0, x0);
+        tile_origin(tile_of(n), b, y0, x0);
         ptx::mbar_wait(&patch_empty[ps], pphase ^ 1);
         ptx::mbar_expect_tx(&patch_full[ps], PATCH_BYTES);
         tma_load_4d(&p.tmS, &patch_full[ps], smem_patch + ps * PATCH_SLOT, 0, x0 - 2, y0 - 2, b);
@@ -172,13 +194,13 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
       // one, so back-to-back taps of one tile ran at a third of the pipe rate (measured: 16 MMAs = 1700 cycles).
       uint32_t n = 0;   // tiles issued so far by this CTA: patch slot n % kPatchStages, accumulator stage n % kAccStages
       long long w_acc = 0, w_patch = 0, t_begin = clock64();   // probe bit 2: where the issuing thread waits
-      for (int t = first; t < n_tiles;) {
+      while (n < n_my) {
         uint32_t d[kMmaGroup];
         uint64_t a[kMmaGroup];
         int g = 0;
 #pragma unroll
         for (int j = 0; j < kMmaGroup; ++j) {
-          if (t + j * step < n_tiles) {
+          if (n + j < n_my) {
             const uint32_t m = n + j, as = m % kAccStages, ps = m % kPatchStages;
             const long long c0 = clock64();
             ptx::mbar_wait(&acc_empty[as], ((m / kAccStages) & 1) ^ 1);
@@ -209,7 +231,6 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
             ptx::umma_commit(&acc_full[(n + j) % kAccStages]);
           }
         n += g;
-        t += g * step;
       }
       if ((p.probe & 4) && blockIdx.x == 0)
         printf("stem CTA 0 MMA thread: %u tiles, %lld cycles total, %lld waiting for accumulators, %lld waiting for patches\n", n,
@@ -226,10 +247,10 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
     ptx::named_bar_sync(3, 256);
     uint8_t* my_out = smem_out + wg * 2 * OUT_BYTES;
     uint32_t k = 0;   // tiles processed by this warpgroup; its k-th tile is the CTA's tile n = 2k + wg: stage n % kAccStages
-    int n = 0;
     long long w_full = 0, t_begin = clock64();
-    for (int t = first; t < n_tiles; t += step, ++n) {
-      if ((n & 1) != wg) continue;
+    for (uint32_t n = 0; n < n_my; ++n) {
+      if ((int)(n & 1) != wg) continue;
+      const int t = tile_of(n);
       int b, y0, x0;
       tile_origin(t, b, y0, x0);
       const int as = (2 * k + wg) % kAccStages;
@@ -250,6 +271,42 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&acc_empty[as]);
+      if constexpr (kPool) {
+        // this thread's stem pixel: local (ly, lx) of the 16 x 16 block; zero outside the image
+        const int ly = row >> 3, lx = wg * 8 + (row & 7);
+        const bool inside = (unsigned)(y0 + ly) < (unsigned)p.H2 && (unsigned)(x0 + (row & 7)) < (unsigned)p.W2;
+        uint8_t* blk = smem_out + (k & 1) * (2 * OUT_BYTES);          // [16][16] pixels x 128 B, 16-byte chunks XOR (lx & 7)
+        uint8_t* rowp = blk + (ly * 16 + lx) * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (lx & 7)) << 4)) =
+              inside ? make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]) : make_uint4(0, 0, 0, 0);
+        ptx::named_bar_sync(4, 256);   // both halves of the block are in shared memory (the other warpgroup's tile n ^ 1)
+        const int pi0 = ((t >> 1) / p.tiles_x % p.tiles_y) * 7, pj0 = ((t >> 1) % p.tiles_x) * 7;
+        for (int item = threadIdx.x; item < 49 * 8; item += 256) {
+          const int px = item >> 3, ch = item & 7;
+          const int i = px / 7, j = px - i * 7;
+          if (pi0 + i < p.P && pj0 + j < p.Q) {
+            __nv_bfloat162 m[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m[e] = __floats2bfloat162_rn(0.f, 0.f);   // inputs are >= 0
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const int cx = 2 * j + dx;
+                const uint4 v = *reinterpret_cast<const uint4*>(blk + ((2 * i + dy) * 16 + cx) * 128 + ((ch ^ (cx & 7)) << 4));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], h[e]);
+              }
+            *reinterpret_cast<uint4*>(p.pooled + ((((long long)b * p.P + pi0 + i) * p.Q + pj0 + j) * 64 + ch * 8)) =
+                *reinterpret_cast<const uint4*>(m);
+          }
+        }
+        ++k;
+        continue;
+      }
       uint8_t* buf = my_out + (k & 1) * OUT_BYTES;
       if (et == 0) ptx::tma_store_wait_read<1>();   // the store issued two tiles ago (same buffer) has read its data
       ptx::named_bar_sync(1 + wg, 128);
@@ -297,10 +354,13 @@ int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, c
 }  // namespace
 
 int stem_plan(StemPlan* plan, const __nv_bfloat16* s2d, int B, int H2, int W2, const __nv_bfloat16* w_taps, const float* bias,
-              __nv_bfloat16* y) {
+              __nv_bfloat16* y, __nv_bfloat16* pooled) {
   *plan = StemPlan{};
   plan->B = B; plan->H2 = H2; plan->W2 = W2;
   plan->bias = bias;
+  plan->pooled = pooled;
+  plan->P = (H2 - 1) / 2 + 1;
+  plan->Q = (W2 - 1) / 2 + 1;
   {
     cuuint64_t dims[4] = {16, (cuuint64_t)W2, (cuuint64_t)H2, (cuuint64_t)B};
     cuuint64_t strides[3] = {32, (cuuint64_t)W2 * 32, (cuuint64_t)H2 * W2 * 32};
@@ -313,6 +373,12 @@ int stem_plan(StemPlan* plan, const __nv_bfloat16* s2d, int B, int H2, int W2, c
     cuuint32_t box[2] = {16, 64};
     if (int rc = encode(&plan->tmW, w_taps, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
   }
+  if (pooled) {
+    plan->tmD = plan->tmS;   // unused
+    const int tiles = B * ((plan->P + 6) / 7) * ((plan->Q + 6) / 7);
+    plan->grid = std::min(tiles, sm_count());
+    return OPD_OK;
+  }
   if (int rc = make_tmap_nhwc_patch(&plan->tmD, y, B, H2, W2, 64, TILE_W, TILE_H)) return rc;
   const int tiles = B * ((H2 + TILE_H - 1) / TILE_H) * ((W2 + TILE_W - 1) / TILE_W);
   plan->grid = std::min(tiles, sm_count());
@@ -322,17 +388,24 @@ int stem_plan(StemPlan* plan, const __nv_bfloat16* s2d, int B, int H2, int W2, c
 int stem_launch(const StemPlan& plan, cudaStream_t stream) {
   StemParams p;
   p.tmS = plan.tmS; p.tmW = plan.tmW; p.tmD = plan.tmD;
-  p.tiles_x = (plan.W2 + TILE_W - 1) / TILE_W;
-  p.tiles_y = (plan.H2 + TILE_H - 1) / TILE_H;
-  p.num_tiles = plan.B * p.tiles_x * p.tiles_y;
+  const bool pool = plan.pooled != nullptr;
+  p.tiles_x = pool ? (plan.Q + 6) / 7 : (plan.W2 + TILE_W - 1) / TILE_W;
+  p.tiles_y = pool ? (plan.P + 6) / 7 : (plan.H2 + TILE_H - 1) / TILE_H;
+  p.num_tiles = plan.B * p.tiles_x * p.tiles_y * (pool ? 2 : 1);
   p.bias = plan.bias;
+  p.pooled = plan.pooled;
+  p.H2 = plan.H2; p.W2 = plan.W2; p.P = plan.P; p.Q = plan.Q;
   p.probe = g_option_probe.load();
   static bool configured = false;
   if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  stem_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
+  if (pool)
+    stem_kernel<true><<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
+  else
+    stem_kernel<false><<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

@@ -89,12 +89,14 @@ int attn_launch(const AttnPlan& plan, cudaStream_t stream);
 // Stem (stem_conv.cu): 4x4-tap convolution over the space-to-depth tensor S[B,H2,W2,16] -> y[B,H2,W2,64], bias + ReLU.
 struct StemPlan {
   CUtensorMap tmS, tmW, tmD;
-  int B, H2, W2;
+  int B, H2, W2, P, Q;
   const float* bias;
+  __nv_bfloat16* pooled;   // != nullptr: the 3x3 / stride 2 max pooling is fused; y is not written
   int grid;
 };
+// pooled != nullptr: y[B,P,Q,64] = maxpool3x3s2(relu(stem)) in one kernel (y_stem unused)
 int stem_plan(StemPlan* plan, const __nv_bfloat16* s2d, int B, int H2, int W2, const __nv_bfloat16* w_taps, const float* bias,
-              __nv_bfloat16* y);
+              __nv_bfloat16* y, __nv_bfloat16* pooled = nullptr);
 int stem_launch(const StemPlan& plan, cudaStream_t stream);
 
 struct BneckPlan {

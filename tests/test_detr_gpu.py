@@ -224,3 +224,32 @@ def test_detect_with_features(detector, weights):
     finally:
         detector.confidence_threshold = old
         eng.set_resize(True)
+
+
+@pytest.mark.parametrize("size", [(224, 320), (200, 334), (197, 331)])
+def test_fused_stem_maxpool_is_bit_identical(detector, size):
+    """The stem kernel with the 3x3 / stride 2 max pooling fused into its epilogue (the default outside debug plans)
+    writes exactly the pooled tensor of the two-kernel path: odd / even sizes, partial work tiles at every border."""
+    import torch
+
+    from office_person_detection_vit_b200 import _lib
+
+    eng = detector.model
+    eng.set_resize(False)
+    frames = torch.from_numpy(do.synthetic_frames(2, size[0], size[1], seed=21)).cuda()
+    try:
+        eng.set_debug(True)                                   # two kernels: "stem" and "pool" taps
+        eng.forward(frames)
+        torch.cuda.synchronize()
+        ref = eng.tap("pool").clone()
+        _lib.check(_lib.lib().opd_set_option(b"stem_pool", 2), "opd_set_option")
+        eng.set_debug(True)                                   # rebuild the plan: fused kernel, private buffers
+        eng.forward(frames)
+        torch.cuda.synchronize()
+        got = eng.tap("pool")
+        assert got.shape == ref.shape and float(ref.float().abs().max()) > 0
+        assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    finally:
+        _lib.lib().opd_set_option(b"stem_pool", 1)
+        eng.set_debug(False)
+        eng.set_resize(True)
