@@ -26,13 +26,21 @@ namespace {
 constexpr int TILE_W = 8, TILE_H = 16, PATCH_W = TILE_W + 3, PATCH_H = TILE_H + 3;
 constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 32;   // 6688
 constexpr int PATCH_SLOT = 7168;
-constexpr int kPatchStages = 8;
+constexpr int kPatchStages = 12;
 constexpr int W_TAP_BYTES = 64 * 32;                   // one tap: 64 output channels x 16 input lanes
 constexpr int OUT_BYTES = 128 * 128;                   // staging box: 128 pixels x 64 channels bf16
 constexpr int kAccStages = 8;
-constexpr int kMmaGroup = 4;   // tiles whose MMAs are interleaved: consecutive MMAs never accumulate into the same TMEM tile
 constexpr int kThreads = 384;
+#ifdef OPD_STEM_PROBE
+constexpr bool kCounters = true;    // per-role clock64 counters printed by CTA 0 when opd_set_option("probe", 4)
+#else
+constexpr bool kCounters = false;   // clock64 reads cost ~30 cycles each on the single-thread roles: compiled out
+#endif
+__device__ __forceinline__ long long probe_clock() { return kCounters ? clock64() : 0; }
 constexpr int kSmemBytes = 16 * W_TAP_BYTES + kPatchStages * PATCH_SLOT + 4 * OUT_BYTES + 1024;
+// fused pooling: 8 more warps (12-19) reduce the 16 x 16 blocks the epilogue warpgroups leave in a ring of kBlkSlots
+constexpr int kPoolThreads = 640, kBlkSlots = 3, BLK_BYTES = 2 * OUT_BYTES;
+constexpr int kPoolSmemBytes = 16 * W_TAP_BYTES + kPatchStages * PATCH_SLOT + kBlkSlots * BLK_BYTES + 1024;
 
 struct StemParams {
   CUtensorMap tmS, tmW, tmD;
@@ -106,20 +114,22 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t addr, uint32_t sbo_bytes)
 // global memory.  The stem output (2.2 GB per 64 frames) is never written or read back; the price is (16/14)^2 = 1.31x
 // the MMA work, on a kernel whose tensor pipe was two thirds idle.
 template <bool kPool>
-__global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant__ StemParams p) {
+__global__ void __launch_bounds__(kPool ? kPoolThreads : kThreads, 1) stem_kernel(const __grid_constant__ StemParams p) {
   constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(128, 64);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_w = smem;                                   // 16 taps x [64 x 32 B]
   uint8_t* smem_patch = smem_w + 16 * W_TAP_BYTES;          // [kPatchStages]
   uint8_t* smem_out = smem_patch + kPatchStages * PATCH_SLOT;   // 2 staging boxes per epilogue warpgroup
-  float* s_bias = reinterpret_cast<float*>(smem_out + 4 * OUT_BYTES);   // [64]
+  float* s_bias = reinterpret_cast<float*>(smem_out + (kPool ? kBlkSlots * BLK_BYTES : 4 * OUT_BYTES));   // [64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 64);
-  uint64_t* patch_full = bars;           // [8]
-  uint64_t* patch_empty = bars + 8;      // [8]
-  uint64_t* acc_full = bars + 16;        // [8]
-  uint64_t* acc_empty = bars + 24;       // [8]
-  uint64_t* w_full = bars + 32;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 33);
+  uint64_t* patch_full = bars;           // [kPatchStages <= 12]
+  uint64_t* patch_empty = bars + 12;     // [kPatchStages]
+  uint64_t* acc_full = bars + 24;        // [8]
+  uint64_t* acc_empty = bars + 32;       // [8]
+  uint64_t* w_full = bars + 40;
+  uint64_t* blk_full = bars + 41;        // [kBlkSlots]  kPool: block written by both epilogue warpgroups
+  uint64_t* blk_empty = bars + 44;       // [kBlkSlots]  kPool: block reduced by the pooling warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 48);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -133,9 +143,13 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
     }
     for (int i = 0; i < kAccStages; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&acc_empty[i], 128);
+      ptx::mbar_init(&acc_empty[i], 4);    // one arrival per epilogue warp (32 per-thread arrivals serialise on the barrier word)
     }
     ptx::mbar_init(w_full, 1);
+    for (int i = 0; i < kBlkSlots; ++i) {
+      ptx::mbar_init(&blk_full[i], 8);     // one arrival per warp, after __syncwarp()
+      ptx::mbar_init(&blk_empty[i], 8);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 9) ptx::tmem_alloc<kAccStages * 64>(tmem_ptr);
@@ -145,26 +159,47 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   const int first = blockIdx.x, step = gridDim.x, n_tiles = p.num_tiles;
-  // MMA tile t -> image b and the stem-output coordinates of its first pixel.  kPool: t = 2 * work tile + half.
-  auto tile_origin = [&](int t, int& b, int& y0, int& x0) {
-    const int w = kPool ? t >> 1 : t;
-    const int tx = w % p.tiles_x;
-    const int r = w / p.tiles_x;
-    const int ty = r % p.tiles_y;
-    b = r / p.tiles_y;
-    if (kPool) {
-      x0 = tx * 14 - 1 + (t & 1) * TILE_W;
-      y0 = ty * 14 - 1;
-    } else {
-      x0 = tx * TILE_W;
-      y0 = ty * TILE_H;
-    }
-  };
-
-  // this CTA's n-th MMA tile.  kPool: both halves of a work tile belong to the same CTA (n = 2 * local work tile + half)
+  // Work units (kPool: 16 x 16 blocks = two MMA tiles; else single MMA tiles) are dealt round-robin: unit first + i * step.
+  // Every role walks them with a cursor (tile column, tile row, image) advanced by the precomputed decomposition of `step`:
+  // the three integer divisions per tile of the obvious formula were a third of the epilogue's instruction stream.
   const int n_units = kPool ? n_tiles / 2 : n_tiles;
   const uint32_t n_my = first < n_units ? (uint32_t)((n_units - first + step - 1) / step) * (kPool ? 2u : 1u) : 0u;
-  auto tile_of = [&](uint32_t n) -> int { return kPool ? 2 * (first + (int)(n >> 1) * step) + (int)(n & 1) : first + (int)n * step; };
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int step_b = step / per_img, step_y = (step - step_b * per_img) / p.tiles_x, step_x = step - step_b * per_img - step_y * p.tiles_x;
+  struct Cursor {
+    int tx, ty, b;
+  };
+  auto cursor_at = [&](int unit) {
+    Cursor c;
+    c.b = unit / per_img;
+    const int r = unit - c.b * per_img;
+    c.ty = r / p.tiles_x;
+    c.tx = r - c.ty * p.tiles_x;
+    return c;
+  };
+  auto advance = [&](Cursor& c) {
+    c.tx += step_x;
+    c.ty += step_y;
+    c.b += step_b;
+    if (c.tx >= p.tiles_x) {
+      c.tx -= p.tiles_x;
+      ++c.ty;
+    }
+    if (c.ty >= p.tiles_y) {
+      c.ty -= p.tiles_y;
+      ++c.b;
+    }
+  };
+  // stem-output coordinates of the first pixel of the unit's MMA tile `half` (kPool: 0 / 1; else 0)
+  auto origin = [&](const Cursor& c, int half, int& y0, int& x0) {
+    if (kPool) {
+      x0 = c.tx * 14 - 1 + half * TILE_W;
+      y0 = c.ty * 14 - 1;
+    } else {
+      x0 = c.tx * TILE_W;
+      y0 = c.ty * TILE_H;
+    }
+  };
 
   if (warp == 8) {
     if (ptx::elect_one()) {
@@ -172,10 +207,13 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
       for (int tap = 0; tap < 16; ++tap) ptx::tma_load_2d(&p.tmW, w_full, smem_w + tap * W_TAP_BYTES, tap * 16, 0);
       int ps = 0;
       uint32_t pphase = 0;
+      Cursor cur = cursor_at(first);
       for (uint32_t n = 0; n < n_my; ++n) {
         if ((p.probe & 1) && n >= kPatchStages) break;
-        int b, y0, x0;
-        tile_origin(tile_of(n), b, y0, x0);
+        int y0, x0;
+        origin(cur, kPool ? (int)(n & 1) : 0, y0, x0);
+        const int b = cur.b;
+        if (!kPool || (n & 1)) advance(cur);
         ptx::mbar_wait(&patch_empty[ps], pphase ^ 1);
         ptx::mbar_expect_tx(&patch_full[ps], PATCH_BYTES);
         tma_load_4d(&p.tmS, &patch_full[ps], smem_patch + ps * PATCH_SLOT, 0, x0 - 2, y0 - 2, b);
@@ -189,52 +227,50 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
     if (ptx::elect_one()) {
       ptx::mbar_wait(w_full, 0);
       const uint64_t w0 = desc_sw32(ptx::smem_u32(smem_w), 256);
-      // Tiles are issued in groups of kMmaGroup with their MMAs interleaved tap by tap: a 128x64x16 MMA occupies the
-      // tensor pipe for 32 cycles but a dependent accumulate into the SAME TMEM tile waits ~100 cycles for the previous
-      // one, so back-to-back taps of one tile ran at a third of the pipe rate (measured: 16 MMAs = 1700 cycles).
-      uint32_t n = 0;   // tiles issued so far by this CTA: patch slot n % kPatchStages, accumulator stage n % kAccStages
-      long long w_acc = 0, w_patch = 0, t_begin = clock64();   // probe bit 2: where the issuing thread waits
-      while (n < n_my) {
-        uint32_t d[kMmaGroup];
-        uint64_t a[kMmaGroup];
-        int g = 0;
-#pragma unroll
-        for (int j = 0; j < kMmaGroup; ++j) {
-          if (n + j < n_my) {
-            const uint32_t m = n + j, as = m % kAccStages, ps = m % kPatchStages;
-            const long long c0 = clock64();
-            ptx::mbar_wait(&acc_empty[as], ((m / kAccStages) & 1) ^ 1);
-            const long long c1 = clock64();
-            if (!(p.probe & 1) || m < kPatchStages) ptx::mbar_wait(&patch_full[ps], (m / kPatchStages) & 1);
-            w_acc += c1 - c0;
-            w_patch += clock64() - c1;
-            d[j] = tmem_base + as * 64;
-            // descriptors differ only in the 16-byte-granular start address field: base descriptor + constant per tap
-            a[j] = desc_sw32(ptx::smem_u32(smem_patch + ps * PATCH_SLOT), PATCH_W * 32);
-            g = j + 1;
-          }
+      // One tile = 16 MMAs (128 x 64 x 16, ~45 cycles each: operand-fetch bound, benchmarks/mma_probe.py).  A successful
+      // mbarrier test costs ~100 cycles of latency, so the two barriers of tile n + 1 are tested BEFORE the MMAs of tile n
+      // are issued and the results consumed afterwards; the blocking wait only runs when that early test failed.
+      long long w_acc = 0, w_patch = 0, t_begin = probe_clock();   // probe bit 2: where the issuing thread waits
+      int nr_acc = 0, nr_patch = 0;                            // early tests that found the barrier not ready
+      auto acc_par = [&](uint32_t m) { return ((m / kAccStages) & 1) ^ 1; };
+      auto patch_par = [&](uint32_t m) { return (m / kPatchStages) & 1; };
+      const bool no_patch_wait = (p.probe & 1) != 0;
+      bool acc_ok = n_my > 0 && ptx::mbar_try_wait(&acc_empty[0], acc_par(0));
+      bool patch_ok = n_my > 0 && ptx::mbar_try_wait(&patch_full[0], patch_par(0));
+      uint32_t n = 0;
+      for (; n < n_my; ++n) {
+        const uint32_t as = n % kAccStages, ps = n % kPatchStages;
+        const long long c0 = probe_clock();
+        if (!acc_ok) {
+          ++nr_acc;
+          ptx::mbar_wait(&acc_empty[as], acc_par(n));
         }
+        const long long c1 = probe_clock();
+        if (!patch_ok && !(no_patch_wait && n >= kPatchStages)) {
+          ++nr_patch;
+          ptx::mbar_wait(&patch_full[ps], patch_par(n));
+        }
+        w_acc += c1 - c0;
+        w_patch += probe_clock() - c1;
         ptx::tc_fence_after_sync();
+        if (n + 1 < n_my) {
+          acc_ok = ptx::mbar_try_wait(&acc_empty[(n + 1) % kAccStages], acc_par(n + 1));
+          patch_ok = ptx::mbar_try_wait(&patch_full[(n + 1) % kPatchStages], patch_par(n + 1));
+        }
+        const uint32_t d = tmem_base + as * 64;
+        // descriptors differ only in the 16-byte-granular start address field: base descriptor + constant per tap
+        const uint64_t a0 = desc_sw32(ptx::smem_u32(smem_patch + ps * PATCH_SLOT), PATCH_W * 32);
 #pragma unroll
         for (int tap = 0; tap < 16; ++tap) {
           const int r = tap >> 2, sx = tap & 3;
-#pragma unroll
-          for (int j = 0; j < kMmaGroup; ++j)
-            if (j < g)
-              ptx::umma_bf16_ss(d[j], a[j] + (uint64_t)(((r * PATCH_W + sx) * 32) >> 4), w0 + (uint64_t)((tap * W_TAP_BYTES) >> 4), kIdesc,
-                                tap != 0);
+          ptx::umma_bf16_ss(d, a0 + (uint64_t)(((r * PATCH_W + sx) * 32) >> 4), w0 + (uint64_t)((tap * W_TAP_BYTES) >> 4), kIdesc, tap != 0);
         }
-#pragma unroll
-        for (int j = 0; j < kMmaGroup; ++j)
-          if (j < g) {
-            ptx::umma_commit(&patch_empty[(n + j) % kPatchStages]);
-            ptx::umma_commit(&acc_full[(n + j) % kAccStages]);
-          }
-        n += g;
+        ptx::umma_commit(&patch_empty[ps]);
+        ptx::umma_commit(&acc_full[as]);
       }
-      if ((p.probe & 4) && blockIdx.x == 0)
-        printf("stem CTA 0 MMA thread: %u tiles, %lld cycles total, %lld waiting for accumulators, %lld waiting for patches\n", n,
-               clock64() - t_begin, w_acc, w_patch);
+      if (kCounters && (p.probe & 4) && blockIdx.x == 0)
+        printf("stem CTA 0 MMA thread: %u tiles, %lld cycles total, %lld waiting for accumulators (%d not ready), %lld waiting for patches (%d not ready)\n",
+               n, probe_clock() - t_begin, w_acc, nr_acc, w_patch, nr_patch);
     }
   } else if (warp < 8) {
     // two epilogue warpgroups; warpgroup g handles this CTA's tiles number g, g + 2, ... (accumulator stages g, g + 2)
@@ -247,16 +283,18 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
     ptx::named_bar_sync(3, 256);
     uint8_t* my_out = smem_out + wg * 2 * OUT_BYTES;
     uint32_t k = 0;   // tiles processed by this warpgroup; its k-th tile is the CTA's tile n = 2k + wg: stage n % kAccStages
-    long long w_full = 0, t_begin = clock64();
-    for (uint32_t n = 0; n < n_my; ++n) {
-      if ((int)(n & 1) != wg) continue;
-      const int t = tile_of(n);
-      int b, y0, x0;
-      tile_origin(t, b, y0, x0);
+    long long w_full = 0, t_begin = probe_clock();
+    Cursor cur = cursor_at(kPool ? first : first + wg * step);   // !kPool: warpgroup g owns units g, g + 2, ...: two steps at a time
+    for (uint32_t n = wg; n < n_my; n += 2) {
+      int y0, x0;
+      origin(cur, kPool ? wg : 0, y0, x0);
+      const int b = cur.b;
+      advance(cur);
+      if (!kPool) advance(cur);
       const int as = (2 * k + wg) % kAccStages;
-      const long long c0 = clock64();
+      const long long c0 = probe_clock();
       ptx::mbar_wait(&acc_full[as], ((2 * k + wg) / kAccStages) & 1);
-      w_full += clock64() - c0;
+      w_full += probe_clock() - c0;
       ptx::tc_fence_after_sync();
       uint32_t packed[32];
 #pragma unroll
@@ -270,40 +308,21 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
                                               fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias[h * 32 + 2 * j + 1], 0.f));
       }
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&acc_empty[as]);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
       if constexpr (kPool) {
         // this thread's stem pixel: local (ly, lx) of the 16 x 16 block; zero outside the image
         const int ly = row >> 3, lx = wg * 8 + (row & 7);
         const bool inside = (unsigned)(y0 + ly) < (unsigned)p.H2 && (unsigned)(x0 + (row & 7)) < (unsigned)p.W2;
-        uint8_t* blk = smem_out + (k & 1) * (2 * OUT_BYTES);          // [16][16] pixels x 128 B, 16-byte chunks XOR (lx & 7)
-        uint8_t* rowp = blk + (ly * 16 + lx) * 128;
+        const uint32_t slot = k % kBlkSlots;
+        ptx::mbar_wait(&blk_empty[slot], ((k / kBlkSlots) & 1) ^ 1);     // the pooling warps are done with this slot
+        uint8_t* rowp = smem_out + slot * BLK_BYTES + (ly * 16 + lx) * 128;   // [16][16] pixels x 128 B, 16-byte chunks XOR (lx & 7)
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<uint4*>(rowp + ((j ^ (lx & 7)) << 4)) =
               inside ? make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]) : make_uint4(0, 0, 0, 0);
-        ptx::named_bar_sync(4, 256);   // both halves of the block are in shared memory (the other warpgroup's tile n ^ 1)
-        const int pi0 = ((t >> 1) / p.tiles_x % p.tiles_y) * 7, pj0 = ((t >> 1) % p.tiles_x) * 7;
-        for (int item = threadIdx.x; item < 49 * 8; item += 256) {
-          const int px = item >> 3, ch = item & 7;
-          const int i = px / 7, j = px - i * 7;
-          if (pi0 + i < p.P && pj0 + j < p.Q) {
-            __nv_bfloat162 m[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) m[e] = __floats2bfloat162_rn(0.f, 0.f);   // inputs are >= 0
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                const int cx = 2 * j + dx;
-                const uint4 v = *reinterpret_cast<const uint4*>(blk + ((2 * i + dy) * 16 + cx) * 128 + ((ch ^ (cx & 7)) << 4));
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], h[e]);
-              }
-            *reinterpret_cast<uint4*>(p.pooled + ((((long long)b * p.P + pi0 + i) * p.Q + pj0 + j) * 64 + ch * 8)) =
-                *reinterpret_cast<const uint4*>(m);
-          }
-        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&blk_full[slot]);
         ++k;
         continue;
       }
@@ -324,9 +343,68 @@ __global__ void __launch_bounds__(kThreads, 1) stem_kernel(const __grid_constant
       ++k;
     }
     if (et == 0) ptx::tma_store_wait_all<0>();
-    if ((p.probe & 4) && blockIdx.x == 0 && et == 0)
-      printf("stem CTA 0 epilogue warpgroup %d: %u tiles, %lld cycles total, %lld waiting for accumulators\n", wg, k, clock64() - t_begin,
+    if (kCounters && (p.probe & 4) && blockIdx.x == 0 && et == 0)
+      printf("stem CTA 0 epilogue warpgroup %d: %u tiles, %lld cycles total, %lld waiting for accumulators\n", wg, k, probe_clock() - t_begin,
              w_full);
+  }
+  if (kPool && warp >= 12) {
+    // ===== pooling warps: 224 of 256 threads = (pooled column j, 16-byte channel chunk, row pair rg); pooled rows 2 rg and
+    // 2 rg + 1 share stem row 4 rg + 2, so five stem rows x three columns serve two outputs =====
+    const int tid = threadIdx.x - 384;
+    const int ch = tid & 7, jr = tid >> 3;      // jr = rg * 7 + j
+    const int rg = (jr * 37) >> 8, j = jr - rg * 7;
+    long long w_blk = 0, t_begin = probe_clock();
+    Cursor cur = cursor_at(first);
+    for (uint32_t kk = 0; 2 * kk < n_my; ++kk) {
+      int y0, x0;
+      origin(cur, 0, y0, x0);
+      const int b = cur.b;
+      advance(cur);
+      const int pi0 = (y0 + 1) >> 1, pj0 = (x0 + 1) >> 1;   // first pooled row / column of the block
+      const uint32_t slot = kk % kBlkSlots;
+      const long long c0 = probe_clock();
+      ptx::mbar_wait(&blk_full[slot], (kk / kBlkSlots) & 1);
+      w_blk += probe_clock() - c0;
+      const uint8_t* blk = smem_out + slot * BLK_BYTES;
+      if (tid < 224 && !(p.probe & 8)) {
+        __nv_bfloat162 hm[5][4];                     // horizontal 3-max of stem rows 4 rg .. 4 rg + 4
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const int sy = 4 * rg + r;
+          if (sy < 15) {
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const int cx = 2 * j + dx;
+              const uint4 v = *reinterpret_cast<const uint4*>(blk + (sy * 16 + cx) * 128 + ((ch ^ (cx & 7)) << 4));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) hm[r][e] = dx == 0 ? h[e] : __hmax2(hm[r][e], h[e]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hm[r][e] = __floats2bfloat162_rn(0.f, 0.f);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&blk_empty[slot]);          // every read of the slot has returned
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int i = 2 * rg + o;
+          if (i < 7 && pi0 + i < p.P && pj0 + j < p.Q && !(p.probe & 16)) {
+            __nv_bfloat162 m[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m[e] = __hmax2(__hmax2(hm[2 * o][e], hm[2 * o + 1][e]), hm[2 * o + 2][e]);
+            *reinterpret_cast<uint4*>(p.pooled + ((((long long)b * p.P + pi0 + i) * p.Q + pj0 + j) * 64 + ch * 8)) =
+                *reinterpret_cast<const uint4*>(m);
+          }
+        }
+      } else {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&blk_empty[slot]);
+      }
+    }
+    if (kCounters && (p.probe & 4) && blockIdx.x == 0 && tid == 0)
+      printf("stem CTA 0 pooling warps: %lld cycles total, %lld waiting for blocks\n", probe_clock() - t_begin, w_blk);
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -399,11 +477,11 @@ int stem_launch(const StemPlan& plan, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBytes));
     configured = true;
   }
   if (pool)
-    stem_kernel<true><<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
+    stem_kernel<true><<<plan.grid, kPoolThreads, kPoolSmemBytes, stream>>>(p);
   else
     stem_kernel<false><<<plan.grid, kThreads, kSmemBytes, stream>>>(p);
   count_launch();
