@@ -12,6 +12,7 @@ std::atomic<int> g_option_attention_tc{1};
 std::atomic<int> g_option_attention_kv{64};
 std::atomic<int> g_option_probe{0};
 std::atomic<int> g_option_stem_pool{1};
+std::atomic<int> g_option_gemm_bres{1};
 }  // namespace opd
 
 extern "C" {
@@ -29,6 +30,10 @@ int opd_set_option(const char* name, int32_t value) {
   }
   if (name && std::string(name) == "probe") {   // measurement probes (benchmarks/step_times.py): results are WRONG when set
     opd::g_option_probe.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "gemm_bres") {   // 0: never use the weight-stationary GEMM variant (A/B runs; new plans only)
+    opd::g_option_gemm_bres.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "stem_pool") {   // 0: stem and max pooling as two kernels; 1: fused (default); 2: fused in debug plans too

@@ -40,14 +40,24 @@ __host__ __device__ constexpr int res_stages_for(int block_n, bool has_res) {
 }
 // bias tile [256 floats] + barriers (+ LayerNorm partial sums [2][128][2] floats for the residual / LayerNorm epilogues)
 __host__ __device__ constexpr int tail_bytes_for(bool has_res) { return has_res ? 4096 : 2048; }
-__host__ __device__ constexpr int stages_for(int block_n, bool has_res) {
+// kBRes (weight-stationary, K <= 256): the CTA keeps ONE n-block's weights [BLOCK_N x K] in shared memory for all of its
+// tiles and only A tiles stream through the ring.  The 1x1 expansions of ResNet stage 3 (K = 256, N = 1024) re-read
+// 64 KB of weights per 128 x 128 tile otherwise and ran at the L2 -> SM limit (10 TB/s), not at the HBM roofline.
+constexpr int kBResKBlocks = 4;
+__host__ __device__ constexpr int stages_for(int block_n, bool has_res, bool b_res = false) {
+  const int fixed = (2 + res_stages_for(block_n, has_res)) * STAGING_BYTES + tail_bytes_for(has_res);
+  if (b_res) {
+    const int n = (kSmemBudget - fixed - kBResKBlocks * block_n * BLOCK_K * 2) / A_STAGE_BYTES;
+    return n > 8 ? 8 : n;
+  }
   const int stage = A_STAGE_BYTES + block_n * BLOCK_K * 2;
-  const int n = (kSmemBudget - (2 + res_stages_for(block_n, has_res)) * STAGING_BYTES - tail_bytes_for(has_res)) / stage;
+  const int n = (kSmemBudget - fixed) / stage;
   return n > 8 ? 8 : n;
 }
-__host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res) {
-  return stages_for(block_n, has_res) * (A_STAGE_BYTES + block_n * BLOCK_K * 2) +
-         (2 + res_stages_for(block_n, has_res)) * STAGING_BYTES + tail_bytes_for(has_res);
+__host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res, bool b_res = false) {
+  return stages_for(block_n, has_res, b_res) * (A_STAGE_BYTES + (b_res ? 0 : block_n * BLOCK_K * 2)) +
+         (b_res ? kBResKBlocks * block_n * BLOCK_K * 2 : 0) + (2 + res_stages_for(block_n, has_res)) * STAGING_BYTES +
+         tail_bytes_for(has_res);
 }
 
 struct GemmParams {
@@ -69,9 +79,9 @@ struct GemmParams {
   int has_d2;
 };
 
-template <int BLOCK_N, bool kHasRes>
+template <int BLOCK_N, bool kHasRes, bool kBRes = false>
 __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmParams p) {
-  constexpr int kStages = stages_for(BLOCK_N, kHasRes);
+  constexpr int kStages = stages_for(BLOCK_N, kHasRes, kBRes);
   constexpr int kResStages = res_stages_for(BLOCK_N, kHasRes);
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -80,7 +90,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
-  uint8_t* smem_out = smem_b + kStages * B_STAGE_BYTES;           // 2 staging boxes
+  uint8_t* smem_out = smem_b + (kBRes ? kBResKBlocks : kStages) * B_STAGE_BYTES;   // 2 staging boxes (kBRes: smem_b = resident weights)
   uint8_t* smem_res = smem_out + 2 * STAGING_BYTES;               // kResStages residual chunks
   float* s_bias = reinterpret_cast<float*>(smem_res + kResStages * STAGING_BYTES);   // [BLOCK_N]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
@@ -91,7 +101,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
   uint64_t* res_full = bars + 2 * kStages + 4;    // [4]
   uint64_t* res_empty = bars + 2 * kStages + 8;   // [4]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
+  uint64_t* b_res_full = bars + 2 * kStages + 12;   // kBRes: the resident weights have landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();   // swizzle-128B tiles need 1024-byte alignment
@@ -113,6 +124,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       ptx::mbar_init(&res_full[i], 1);
       ptx::mbar_init(&res_empty[i], 4);   // one arrive per epilogue warp
     }
+    ptx::mbar_init(b_res_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 9) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
@@ -122,14 +134,38 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_ptr;
 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  // tile sequence of this CTA.  Default: tile = blockIdx.x + i * gridDim.x, n innermost (CTAs that run together share the A
+  // tile through L2).  kBRes: the CTA is pinned to n-block blockIdx.x % num_n_blocks and walks m-blocks
+  // blockIdx.x / num_n_blocks + i * (CTAs pinned to that n-block).
+  const int br_n = kBRes ? (int)blockIdx.x % p.num_n_blocks : 0;
+  const int br_m0 = kBRes ? (int)blockIdx.x / p.num_n_blocks : 0;
+  const int br_step = kBRes ? ((int)gridDim.x - br_n + p.num_n_blocks - 1) / p.num_n_blocks : 1;
+  const int n_my = kBRes ? (br_m0 < p.num_m_blocks ? (p.num_m_blocks - br_m0 + br_step - 1) / br_step : 0)
+                         : ((int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+  auto tile_mn = [&](int i, int& m_blk, int& n_blk) {
+    if (kBRes) {
+      m_blk = br_m0 + i * br_step;
+      n_blk = br_n;
+    } else {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      m_blk = tile / p.num_n_blocks;
+      n_blk = tile - m_blk * p.num_n_blocks;
+    }
+  };
 
   if (warp == 8) {
     // ===================================== TMA producer =====================================
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+      if (kBRes && n_my > 0) {
+        ptx::mbar_expect_tx(b_res_full, p.num_k_blocks * B_STAGE_BYTES);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb)
+          ptx::tma_load_2d(&p.tmB, b_res_full, smem_b + kb * B_STAGE_BYTES, kb * BLOCK_K, br_n * BLOCK_N);
+      }
+      for (int it = 0; it < n_my; ++it) {
+        int m_blk, n_blk;
+        tile_mn(it, m_blk, n_blk);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
         int base_w = 0, base_h = 0, img = 0;
         if (p.im2col || p.k_split < p.num_k_blocks) {
@@ -142,7 +178,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (kBRes ? 0 : B_STAGE_BYTES));
           if (kb >= p.k_split) {
             ptx::tma_load_im2col_4d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, (kb - p.k_split) * BLOCK_K, base_w,
                                     base_h, img, (uint16_t)0, (uint16_t)0);
@@ -154,7 +190,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
           } else {
             ptx::tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m0);
           }
-          ptx::tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
+          if (!kBRes) ptx::tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -169,7 +205,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (kBRes && n_my > 0) ptx::mbar_wait(b_res_full, 0);
+      for (int it = 0; it < n_my; ++it) {
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -177,7 +214,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
           const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
+          const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + (kBRes ? kb : stage) * B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) start-address field
@@ -202,8 +239,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       ptx::prefetch_tmap(&p.tmR);
       int rs = 0;
       uint32_t rphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+      for (int it = 0; it < n_my; ++it) {
+        int m_blk, n_blk;
+        tile_mn(it, m_blk, n_blk);
         for (int c = 0; c < BLOCK_N / 64; ++c) {
           ptx::mbar_wait(&res_empty[rs], rphase ^ 1);
           ptx::mbar_expect_tx(&res_full[rs], STAGING_BYTES);
@@ -244,8 +282,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       if (lane == 0) ptx::mbar_arrive(&res_empty[rq % kResStages]);
       rq += (kChunks > 1 ? 2 : 1);
     };
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+    for (int it = 0; it < n_my; ++it) {
+      int m_blk, n_blk;
+      tile_mn(it, m_blk, n_blk);
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
       const long long m = (long long)m0 + row;
       const bool row_ok = m < p.M;
@@ -483,15 +522,15 @@ int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g) {
 
 namespace {
 
-template <int BLOCK_N, bool kHasRes>
+template <int BLOCK_N, bool kHasRes, bool kBRes = false>
 int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes>;
+  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, kBRes>;
   if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes)));
+    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes, kBRes)));
     configured = true;
   }
-  kern<<<grid, kNumThreads, smem_bytes_for(BLOCK_N, kHasRes), s>>>(p);
+  kern<<<grid, kNumThreads, smem_bytes_for(BLOCK_N, kHasRes, kBRes), s>>>(p);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;
@@ -511,6 +550,10 @@ int finish_plan(GemmPlan* plan) {
   plan->block_n = bn;
   const long long tiles = m_blocks * (N / bn);
   plan->grid = (int)std::min<long long>(tiles, sm_count());
+  // weight-stationary variant: bottleneck outputs with a short K and many m-blocks per CTA (ResNet stage-3 1x1 expansions)
+  const int bres = g_option_gemm_bres.load();   // 2: whenever the shape allows it (tests)
+  plan->b_resident = bres && plan->epi == EPI_BIAS_RES_RELU && bn == 128 && plan->K / BLOCK_K <= kBResKBlocks && !plan->im2col &&
+                     N / bn <= 16 && (bres == 2 || m_blocks >= 8LL * sm_count());
   return OPD_OK;
 }
 
@@ -619,7 +662,9 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   const bool has_res = plan.epi == EPI_BIAS_RES_RELU || plan.epi == EPI_BIAS_RES_LN;
   switch (plan.block_n) {
     case 64: return has_res ? launch_t<64, true>(p, plan.grid, stream) : launch_t<64, false>(p, plan.grid, stream);
-    case 128: return has_res ? launch_t<128, true>(p, plan.grid, stream) : launch_t<128, false>(p, plan.grid, stream);
+    case 128:
+      if (has_res && plan.b_resident) return launch_t<128, true, true>(p, plan.grid, stream);
+      return has_res ? launch_t<128, true>(p, plan.grid, stream) : launch_t<128, false>(p, plan.grid, stream);
     case 256: return has_res ? launch_t<256, true>(p, plan.grid, stream) : launch_t<256, false>(p, plan.grid, stream);
   }
   return fail(OPD_ERR_INVALID, "gemm: unsupported block_n %d", plan.block_n);

@@ -34,6 +34,7 @@ struct GemmPlan {
   ConvGeom g2;         // geometry of the second source (1x1, stride s, pad 0)
   int M, N, K;
   int block_n;
+  int b_resident;      // 1: weight-stationary kernel variant (one n-block per CTA, its weights resident in shared memory)
   int im2col;          // 0: A is [M,K] rows; 1: A is NHWC through im2col TMA
   ConvGeom g;
   int epi;

@@ -51,6 +51,29 @@ def test_gemm_epilogues(T, M, N, K, epi):
     _close(torch, d, ref, f"gemm {M}x{N}x{K} epi {epi}")
 
 
+@pytest.mark.parametrize("M,N,K", [(128 * 40 + 5, 1024, 256), (128 * 21, 512, 128), (128 * 300 + 77, 256, 256), (200, 1024, 64)])
+def test_gemm_weight_stationary_variant_is_bit_identical(T, M, N, K):
+    """The weight-stationary kernel variant (one n-block per CTA, its weights resident in shared memory; chosen for the
+    short-K bottleneck outputs of the batch-64 forward) accumulates in the same order as the streaming variant: the
+    outputs must be bit-identical, whatever the number of m-blocks per CTA (including CTAs without work)."""
+    from office_person_detection_vit_b200 import _lib
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    a, w = _rand(torch, M, K, seed=11), _rand(torch, N, K, seed=12, scale=K ** -0.5)
+    bias, res = torch.randn(N, device="cuda"), _rand(torch, M, N, seed=13)
+    try:
+        _lib.check(_lib.lib().opd_set_option(b"gemm_bres", 0), "opd_set_option")
+        ref = ops.gemm(a, w, bias, epilogue=2, residual=res)
+        _lib.check(_lib.lib().opd_set_option(b"gemm_bres", 2), "opd_set_option")
+        got = ops.gemm(a, w, bias, epilogue=2, residual=res)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().opd_set_option(b"gemm_bres", 1)
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    _close(torch, got, (a.float() @ w.float().T + bias + res.float()).relu(), f"weight-stationary gemm {M}x{N}x{K}")
+
+
 @pytest.mark.parametrize("M,K", [(100, 256), (1050 * 3, 256), (777, 2048)])
 def test_gemm_layernorm_and_pos(T, M, K):
     from office_person_detection_vit_b200.detection import ops
