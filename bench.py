@@ -289,11 +289,21 @@ def main_gpu(args) -> None:
         k["launches"] += 1
     tc_ms = by_kind.get("gemm", {"ms": 0})["ms"] + by_kind.get("conv", {"ms": 0})["ms"]
     tc_flops = by_kind.get("gemm", {"flops": 0})["flops"] + by_kind.get("conv", {"flops": 0})["flops"]
+    tc_bytes = by_kind.get("gemm", {"bytes": 0})["bytes"] + by_kind.get("conv", {"bytes": 0})["bytes"]
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    # DRAM traffic of the family: dram__bytes_read.sum + dram__bytes_write.sum summed over its launches in one step, from the
+    # committed ncu capture of this same command (profiles/README.md); null when the capture is not there or is of another batch
+    traffic, traffic_src = None, None
+    tpath = Path(__file__).resolve().parent / "profiles" / "r01_traffic.json"
+    if tpath.exists() and B == BATCH:
+        tj = json.loads(tpath.read_text())
+        traffic, traffic_src = tj["family_dram_bytes_per_step"], "profiles/r01_traffic.json (ncu, one step at batch 64)"
     peak = pk["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "kernel": "tcgen05 GEMM / convolution kernels: tc_gemm_kernel, tc_bneck_kernel, tc_bneck_halo_kernel, stem_kernel",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": f"{pk_kind} bf16_tflops_sustained",
+                "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per step over the family's launches (algorithmic: "
+                                                    f"{tc_bytes:.3e})",
+                "traffic_source": traffic_src, "peak_source": f"{pk_kind} bf16_tflops_sustained",
                 "launches_per_step": by_kind.get("gemm", {"launches": 0})["launches"] + by_kind.get("conv", {"launches": 0})["launches"],
                 "share_of_step": round(tc_ms / sum(med), 4),
                 "whole_forward_tflops": round(value / world * GFLOP_PER_FRAME / 1e3, 1),
