@@ -38,8 +38,11 @@ constexpr int kSmemBudget = 232448;           // 227 KB
 __host__ __device__ constexpr int res_stages_for(int block_n, bool has_res) {
   return !has_res ? 0 : (block_n >= 256 ? 2 : 4);
 }
-// bias tile [256 floats] + barriers (+ LayerNorm partial sums [2][128][2] floats for the residual / LayerNorm epilogues)
-__host__ __device__ constexpr int tail_bytes_for(bool has_res) { return has_res ? 4096 : 2048; }
+// bias of the WHOLE layer [kMaxN floats, loaded once per CTA] + barriers (+ LayerNorm partial sums [2][128][2] floats for the
+// residual / LayerNorm epilogues, double-buffered by tile parity: no
+// barrier separates consecutive tiles)
+constexpr int kMaxN = 2048;
+__host__ __device__ constexpr int tail_bytes_for(bool has_res) { return kMaxN * 4 + 256 + (has_res ? 4096 : 0) + 256; }
 // kBRes (weight-stationary, K <= 256): the CTA keeps ONE n-block's weights [BLOCK_N x K] in shared memory for all of its
 // tiles and only A tiles stream through the ring.  The 1x1 expansions of ResNet stage 3 (K = 256, N = 1024) re-read
 // 64 KB of weights per 128 x 128 tile otherwise and ran at the L2 -> SM limit (10 TB/s), not at the HBM roofline.
@@ -92,9 +95,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
   uint8_t* smem_out = smem_b + (kBRes ? kBResKBlocks : kStages) * B_STAGE_BYTES;   // 2 staging boxes (kBRes: smem_b = resident weights)
   uint8_t* smem_res = smem_out + 2 * STAGING_BYTES;               // kResStages residual chunks
-  float* s_bias = reinterpret_cast<float*>(smem_res + kResStages * STAGING_BYTES);   // [BLOCK_N]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
-  float* s_stat = s_bias + 256 + 64;   // after the barriers (kHasRes kernels only): LayerNorm partials [2][128][2]
+  float* s_bias = reinterpret_cast<float*>(smem_res + kResStages * STAGING_BYTES);   // [N]: the whole layer's bias
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kMaxN);
+  float* s_stat = s_bias + kMaxN + 64;   // after the barriers (kHasRes kernels only): LayerNorm partials [2][128][2]
   uint64_t* full_bar = bars;                    // [kStages]
   uint64_t* empty_bar = bars + kStages;         // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;     // [2]
@@ -282,15 +285,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       if (lane == 0) ptx::mbar_arrive(&res_empty[rq % kResStages]);
       rq += (kChunks > 1 ? 2 : 1);
     };
+    // the layer's bias -> shared memory once (was a global load + a 256-thread barrier at the head of every tile)
+    for (int i = e256; i < p.N; i += 256) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    ptx::named_bar_sync(3, 256);
     for (int it = 0; it < n_my; ++it) {
       int m_blk, n_blk;
       tile_mn(it, m_blk, n_blk);
       const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
       const long long m = (long long)m0 + row;
       const bool row_ok = m < p.M;
-      // bias tile -> smem (the previous tile's readers are past their last barrier)
-      for (int i = e256; i < BLOCK_N; i += 256) s_bias[i] = p.bias ? p.bias[n0 + i] : 0.f;
-      ptx::named_bar_sync(3, 256);
+      const float* t_bias = s_bias + n0;   // this tile's slice of the layer bias
 
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after_sync();
@@ -318,8 +322,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float a = __uint_as_float(v[2 * j]) + s_bias[g * 32 + 2 * j] + ptx::bf16_lo(rw[j]);
-              const float b = __uint_as_float(v[2 * j + 1]) + s_bias[g * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]);
+              const float a = __uint_as_float(v[2 * j]) + t_bias[g * 32 + 2 * j] + ptx::bf16_lo(rw[j]);
+              const float b = __uint_as_float(v[2 * j + 1]) + t_bias[g * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]);
               sum += a + b;
               sq += a * a + b * b;
               v[2 * j] = __float_as_uint(a);
@@ -330,11 +334,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
           if constexpr (kHasRes) res_release();
         }
         ptx::tmem_st_wait();
-        s_stat[(wg * 128 + row) * 2 + 0] = sum;
-        s_stat[(wg * 128 + row) * 2 + 1] = sq;
+        float* st = s_stat + (it & 1) * 512;   // [2 warpgroups][128 rows][sum, sum of squares] of this tile
+        st[(wg * 128 + row) * 2 + 0] = sum;
+        st[(wg * 128 + row) * 2 + 1] = sq;
         ptx::named_bar_sync(3, 256);
-        sum += s_stat[((wg ^ 1) * 128 + row) * 2 + 0];
-        sq += s_stat[((wg ^ 1) * 128 + row) * 2 + 1];
+        sum += st[((wg ^ 1) * 128 + row) * 2 + 0];
+        sq += st[((wg ^ 1) * 128 + row) * 2 + 1];
         mean = sum * (1.f / BLOCK_N);
         const float var = fmaxf(sq * (1.f / BLOCK_N) - mean * mean, 0.f);
         rstd = rsqrtf(var + 1e-5f);
@@ -374,8 +379,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
             const bool relu = p.epi != EPI_BIAS;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float a = __uint_as_float(v[2 * j]) + s_bias[g * 32 + 2 * j] + ptx::bf16_lo(rw[j]);
-              float b = __uint_as_float(v[2 * j + 1]) + s_bias[g * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]);
+              float a = __uint_as_float(v[2 * j]) + t_bias[g * 32 + 2 * j] + ptx::bf16_lo(rw[j]);
+              float b = __uint_as_float(v[2 * j + 1]) + t_bias[g * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]);
               if (relu) {
                 a = fmaxf(a, 0.f);
                 b = fmaxf(b, 0.f);
@@ -540,6 +545,7 @@ int finish_plan(GemmPlan* plan) {
   const int N = plan->N;
   OPD_REQUIRE(N % 64 == 0 && plan->K % 64 == 0 && plan->M > 0, "gemm: N=%d and K=%d must be multiples of 64", N,
               plan->K);
+  OPD_REQUIRE(N <= kMaxN, "gemm: N=%d exceeds the %d columns whose bias fits the kernel's shared-memory table", N, kMaxN);
   int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
   if (plan->epi == EPI_BIAS_RES_LN) OPD_REQUIRE(N == 256, "gemm: the LayerNorm epilogue needs N == 256 (got %d)", N);
   // bottleneck outputs (bias + residual + ReLU) are HBM-bound: narrower tiles leave room for a deeper residual ring

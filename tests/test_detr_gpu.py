@@ -253,3 +253,23 @@ def test_fused_stem_maxpool_is_bit_identical(detector, size):
         _lib.lib().opd_set_option(b"stem_pool", 1)
         eng.set_debug(False)
         eng.set_resize(True)
+
+
+def test_full_size_batch_invariance_and_determinism(detector):
+    """Size-independent properties at BASELINE's frame size (800x1333, where no oracle run fits a test): a frame's raw
+    outputs do not depend on its batch neighbours or its position in the batch (frames are independent through the whole
+    path and no kernel's accumulation order depends on B), and two runs of the same batch are bit-identical (no atomics
+    on the DETR path)."""
+    import torch
+
+    eng = detector.model
+    frames = torch.from_numpy(do.synthetic_frames(5, 800, 1333, seed=31)).cuda()
+    l5, b5 = (t.clone() for t in eng.forward(frames))
+    l5b, b5b = (t.clone() for t in eng.forward(frames))
+    assert torch.equal(l5, l5b) and torch.equal(b5, b5b)
+    perm = torch.tensor([3, 0, 4, 1, 2], device="cuda")
+    lp, bp = eng.forward(frames[perm].contiguous())
+    assert torch.equal(lp, l5[perm]) and torch.equal(bp, b5[perm])
+    l2, b2 = eng.forward(frames[1:3].contiguous())
+    assert torch.equal(l2, l5[1:3]) and torch.equal(b2, b5[1:3])
+    assert torch.isfinite(l5).all() and float(b5.min()) >= 0.0 and float(b5.max()) <= 1.0
