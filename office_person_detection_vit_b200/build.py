@@ -19,7 +19,8 @@ CSRC = PKG / "csrc"
 LIB = PKG / "libopd_b200.so"
 OBJ_DIR = PKG / "build"
 
-NVCC_FLAGS = [
+# measurement builds: OPD_EXTRA_NVCC_FLAGS="-DOPD_GEMM_PROBE -DOPD_STEM_PROBE" python -m office_person_detection_vit_b200.build
+NVCC_FLAGS = os.environ.get("OPD_EXTRA_NVCC_FLAGS", "").split() + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

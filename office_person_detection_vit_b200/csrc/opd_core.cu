@@ -13,6 +13,8 @@ std::atomic<int> g_option_attention_kv{64};
 std::atomic<int> g_option_probe{0};
 std::atomic<int> g_option_stem_pool{1};
 std::atomic<int> g_option_gemm_bres{1};
+std::atomic<int> g_option_gemm_cluster{0};
+std::atomic<int> g_option_gemm_outbufs{1};
 }  // namespace opd
 
 extern "C" {
@@ -34,6 +36,14 @@ int opd_set_option(const char* name, int32_t value) {
   }
   if (name && std::string(name) == "gemm_bres") {   // 0: never use the weight-stationary GEMM variant (A/B runs; new plans only)
     opd::g_option_gemm_bres.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "gemm_cluster") {   // 0 (default): no clusters; 1: 2-CTA clusters for the big BLOCK_N = 256 layers; 2: whenever BLOCK_N = 256 (tests); new plans only
+    opd::g_option_gemm_cluster.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "gemm_outbufs") {   // 0: one staging box per epilogue warpgroup everywhere (A/B runs; new plans only)
+    opd::g_option_gemm_outbufs.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "stem_pool") {   // 0: stem and max pooling as two kernels; 1: fused (default); 2: fused in debug plans too

@@ -14,6 +14,9 @@
 #include "tc_gemm.h"
 
 #include <algorithm>
+#include <type_traits>
+#include <cmath>
+#include <cstdio>
 #include <mutex>
 
 #include "opd_common.h"
@@ -47,8 +50,8 @@ __host__ __device__ constexpr int tail_bytes_for(bool has_res) { return kMaxN * 
 // tiles and only A tiles stream through the ring.  The 1x1 expansions of ResNet stage 3 (K = 256, N = 1024) re-read
 // 64 KB of weights per 128 x 128 tile otherwise and ran at the L2 -> SM limit (10 TB/s), not at the HBM roofline.
 constexpr int kBResKBlocks = 4;
-__host__ __device__ constexpr int stages_for(int block_n, bool has_res, bool b_res = false) {
-  const int fixed = (2 + res_stages_for(block_n, has_res)) * STAGING_BYTES + tail_bytes_for(has_res);
+__host__ __device__ constexpr int stages_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1) {
+  const int fixed = (2 * out_bufs + res_stages_for(block_n, has_res)) * STAGING_BYTES + tail_bytes_for(has_res);
   if (b_res) {
     const int n = (kSmemBudget - fixed - kBResKBlocks * block_n * BLOCK_K * 2) / A_STAGE_BYTES;
     return n > 8 ? 8 : n;
@@ -57,11 +60,18 @@ __host__ __device__ constexpr int stages_for(int block_n, bool has_res, bool b_r
   const int n = (kSmemBudget - fixed) / stage;
   return n > 8 ? 8 : n;
 }
-__host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res, bool b_res = false) {
-  return stages_for(block_n, has_res, b_res) * (A_STAGE_BYTES + (b_res ? 0 : block_n * BLOCK_K * 2)) +
-         (b_res ? kBResKBlocks * block_n * BLOCK_K * 2 : 0) + (2 + res_stages_for(block_n, has_res)) * STAGING_BYTES +
+__host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1) {
+  return stages_for(block_n, has_res, b_res, out_bufs) * (A_STAGE_BYTES + (b_res ? 0 : block_n * BLOCK_K * 2)) +
+         (b_res ? kBResKBlocks * block_n * BLOCK_K * 2 : 0) + (2 * out_bufs + res_stages_for(block_n, has_res)) * STAGING_BYTES +
          tail_bytes_for(has_res);
 }
+
+#ifdef OPD_GEMM_PROBE
+constexpr bool kGemmCounters = true;    // clock64 counters of CTA 0's MMA thread and epilogue warpgroup 0, printed at kernel end
+#else
+constexpr bool kGemmCounters = false;
+#endif
+__device__ __forceinline__ long long gclk() { return kGemmCounters ? clock64() : 0; }
 
 struct GemmParams {
   CUtensorMap tmA, tmB, tmD, tmD2, tmR, tmA2;
@@ -79,12 +89,22 @@ struct GemmParams {
   const float* beta;
   const float* pos;
   int pos_rows;
+  int pos_row0;          // row of `pos` that belongs to row 0 of this GEMM (a GEMM over a row range of a larger matrix)
   int has_d2;
 };
 
-template <int BLOCK_N, bool kHasRes, bool kBRes = false>
+// kCluster = 2: thread-block clusters of two CTAs that work on the two m-blocks of a PAIR with the same n-block.  Each CTA
+// loads its own A tile and HALF of the shared weight tile, multicast into both CTAs' ring slots: the L2 -> SM weight
+// reads of the weight tiles are halved.  MEASURED (round 1): no gain - the layers are not bound by L2 reads (multicast still
+// delivers the full tile to every SM) and a device with odd-sized GPCs fits fewer than SMs / 2 clusters, so the variant is
+// off by default (opd_set_option("gemm_cluster", 1)); it stays as the tested starting point for cta_group::2 tiles.  A ring slot is free once BOTH CTAs' MMAs have read it (tcgen05.commit multicast to both empty barriers).
+// kOutBufs = 2 (short-K layers, where the epilogue and not the MMAs paces the kernel: reading a 128 x 256 fp32 accumulator
+// out of TMEM alone takes as long as the four k-blocks of MMAs): two staging boxes per epilogue warpgroup, so a chunk is
+// written while the TMA store of the previous one still reads its box.
+template <int BLOCK_N, bool kHasRes, bool kBRes = false, int kCluster = 1, int kOutBufs = 1>
 __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmParams p) {
-  constexpr int kStages = stages_for(BLOCK_N, kHasRes, kBRes);
+  static_assert(kCluster == 1 || (kCluster == 2 && !kBRes), "clusters of two, not combined with the weight-stationary variant");
+  constexpr int kStages = stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs);
   constexpr int kResStages = res_stages_for(BLOCK_N, kHasRes);
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -94,7 +114,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
   uint8_t* smem_out = smem_b + (kBRes ? kBResKBlocks : kStages) * B_STAGE_BYTES;   // 2 staging boxes (kBRes: smem_b = resident weights)
-  uint8_t* smem_res = smem_out + 2 * STAGING_BYTES;               // kResStages residual chunks
+  uint8_t* smem_res = smem_out + 2 * kOutBufs * STAGING_BYTES;    // kResStages residual chunks
   float* s_bias = reinterpret_cast<float*>(smem_res + kResStages * STAGING_BYTES);   // [N]: the whole layer's bias
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kMaxN);
   float* s_stat = s_bias + kMaxN + 64;   // after the barriers (kHasRes kernels only): LayerNorm partials [2][128][2]
@@ -117,7 +137,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     if (p.k_split < p.num_k_blocks) ptx::prefetch_tmap(&p.tmA2);
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], kCluster);   // one tcgen05.commit per CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
@@ -133,8 +153,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   if (warp == 9) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (kCluster > 1) ptx::cluster_sync();   // the peer's barriers are initialised before anything is multicast to them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  const int cta_rank = kCluster > 1 ? (int)ptx::cluster_ctarank() : 0;
 
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   // tile sequence of this CTA.  Default: tile = blockIdx.x + i * gridDim.x, n innermost (CTAs that run together share the A
@@ -143,10 +165,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   const int br_n = kBRes ? (int)blockIdx.x % p.num_n_blocks : 0;
   const int br_m0 = kBRes ? (int)blockIdx.x / p.num_n_blocks : 0;
   const int br_step = kBRes ? ((int)gridDim.x - br_n + p.num_n_blocks - 1) / p.num_n_blocks : 1;
-  const int n_my = kBRes ? (br_m0 < p.num_m_blocks ? (p.num_m_blocks - br_m0 + br_step - 1) / br_step : 0)
-                         : ((int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+  // kCluster = 2: cluster c works on pairs c + i * (clusters); pair -> (m-block pair, n-block), this CTA's m-block = 2 * pair_m +
+  // rank.  Both CTAs run the same number of iterations (with an odd number of m-blocks rank 1 recomputes the last one).
+  const int cl_pairs = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks, cl_id = (int)blockIdx.x / 2, cl_n = (int)gridDim.x / 2;
+  const int n_my = kCluster > 1 ? (cl_id < cl_pairs ? (cl_pairs - cl_id + cl_n - 1) / cl_n : 0)
+                   : kBRes      ? (br_m0 < p.num_m_blocks ? (p.num_m_blocks - br_m0 + br_step - 1) / br_step : 0)
+                                : ((int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
   auto tile_mn = [&](int i, int& m_blk, int& n_blk) {
-    if (kBRes) {
+    if (kCluster > 1) {
+      const int pair = cl_id + i * cl_n;
+      const int pm = pair / p.num_n_blocks;
+      n_blk = pair - pm * p.num_n_blocks;
+      m_blk = min(2 * pm + cta_rank, p.num_m_blocks - 1);   // odd tail: rank 1 repeats the last m-block (identical stores)
+    } else if (kBRes) {
       m_blk = br_m0 + i * br_step;
       n_blk = br_n;
     } else {
@@ -193,7 +224,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
           } else {
             ptx::tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m0);
           }
-          if (!kBRes) ptx::tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
+          if (kCluster > 1) {   // my half of the weight tile, into both CTAs' slots (tmB box = BLOCK_N / 2 rows)
+            ptx::tma_load_2d_multicast(&p.tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + cta_rank * (B_STAGE_BYTES / 2),
+                                       kb * BLOCK_K, n0 + cta_rank * (BLOCK_N / 2), (uint16_t)0x3);
+          } else if (!kBRes) {
+            ptx::tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -209,12 +245,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       int acc = 0;
       uint32_t acc_phase = 0;
       if (kBRes && n_my > 0) ptx::mbar_wait(b_res_full, 0);
+      long long w_acc = 0, w_full = 0, t_begin = gclk();
       for (int it = 0; it < n_my; ++it) {
+        const long long c0 = gclk();
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        w_acc += gclk() - c0;
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          const long long c1 = gclk();
           ptx::mbar_wait(&full_bar[stage], phase);
+          w_full += gclk() - c1;
           ptx::tc_fence_after_sync();
           const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + (kBRes ? kb : stage) * B_STAGE_BYTES));
@@ -223,7 +264,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
             // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) start-address field
             ptx::umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
           }
-          ptx::umma_commit(&empty_bar[stage]);   // frees the ring slot once these MMAs have read it
+          if (kCluster > 1) ptx::umma_commit_multicast(&empty_bar[stage], (uint16_t)0x3);   // both CTAs' producers write this slot
+          else ptx::umma_commit(&empty_bar[stage]);   // frees the ring slot once these MMAs have read it
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -235,6 +277,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
           acc_phase ^= 1;
         }
       }
+      if (kGemmCounters && blockIdx.x == 0)
+        printf("gemm CTA 0 MMA thread: %d tiles x %d k-blocks, %lld cycles, %lld waiting for a free accumulator, %lld waiting for operands\n",
+               n_my, p.num_k_blocks, gclk() - t_begin, w_acc, w_full);
     }
   } else if (warp == 10) {
     // ===================================== residual TMA producer =====================================
@@ -271,7 +316,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t rq = wg;                              // residual chunk sequence number of my next chunk (ring order = chunk order)
-    uint8_t* my_out = smem_out + wg * STAGING_BYTES;
+    uint8_t* const my_out0 = smem_out + wg * kOutBufs * STAGING_BYTES;   // this warpgroup's kOutBufs staging boxes
+    uint32_t out_n = 0;                                                   // boxes written so far
     // this thread's 64 B (32 columns, half `h` of a 64-column chunk) of the residual chunk in ring slot `slot`
     auto load_res = [&](int slot, int h, uint4 (&rr)[4]) {
       const uint8_t* rowp = smem_res + slot * STAGING_BYTES + row * 128;
@@ -288,6 +334,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     // the layer's bias -> shared memory once (was a global load + a 256-thread barrier at the head of every tile)
     for (int i = e256; i < p.N; i += 256) s_bias[i] = p.bias ? p.bias[i] : 0.f;
     ptx::named_bar_sync(3, 256);
+    long long e_full = 0, e_ld = 0, e_math = 0, e_wait = 0, e_sts = 0, e_fence = 0, e_begin = gclk();
     for (int it = 0; it < n_my; ++it) {
       int m_blk, n_blk;
       tile_mn(it, m_blk, n_blk);
@@ -296,7 +343,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       const bool row_ok = m < p.M;
       const float* t_bias = s_bias + n0;   // this tile's slice of the layer bias
 
+      const long long q0 = gclk();
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      e_full += gclk() - q0;
       ptx::tc_fence_after_sync();
       const uint32_t t_acc = tmem_base + lane_addr + acc * BLOCK_N;
 
@@ -374,26 +423,45 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
 #pragma unroll
               for (int j = 0; j < 4; ++j) rr[j] = make_uint4(0, 0, 0, 0);
             }
+            const long long q1 = gclk();
             ptx::tmem_ld_wait();
+            const long long q2 = gclk();
+            e_ld += q2 - q1;
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
-            const bool relu = p.epi != EPI_BIAS;
+            const float4* bias4 = reinterpret_cast<const float4*>(t_bias + g * 32);   // 8 broadcast LDS.128 instead of 32 LDS
+            auto convert = [&](auto relu_tag) {
+              constexpr bool kRelu = decltype(relu_tag)::value;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = __uint_as_float(v[2 * j]) + t_bias[g * 32 + 2 * j] + ptx::bf16_lo(rw[j]);
-              float b = __uint_as_float(v[2 * j + 1]) + t_bias[g * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]);
-              if (relu) {
-                a = fmaxf(a, 0.f);
-                b = fmaxf(b, 0.f);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 bq = bias4[j4];
+                float a0 = __uint_as_float(v[4 * j4]) + bq.x, a1 = __uint_as_float(v[4 * j4 + 1]) + bq.y;
+                float a2 = __uint_as_float(v[4 * j4 + 2]) + bq.z, a3 = __uint_as_float(v[4 * j4 + 3]) + bq.w;
+                if (use_res) {   // compile-time false in the kernels without a residual ring: no "+ 0.f" left behind
+                  a0 += ptx::bf16_lo(rw[2 * j4]);
+                  a1 += ptx::bf16_hi(rw[2 * j4]);
+                  a2 += ptx::bf16_lo(rw[2 * j4 + 1]);
+                  a3 += ptx::bf16_hi(rw[2 * j4 + 1]);
+                }
+                if (kRelu) {
+                  a0 = fmaxf(a0, 0.f);
+                  a1 = fmaxf(a1, 0.f);
+                  a2 = fmaxf(a2, 0.f);
+                  a3 = fmaxf(a3, 0.f);
+                }
+                packed[h * 16 + 2 * j4] = ptx::pack_bf16(a0, a1);
+                packed[h * 16 + 2 * j4 + 1] = ptx::pack_bf16(a2, a3);
               }
-              packed[h * 16 + j] = ptx::pack_bf16(a, b);
-            }
+            };
+            if (p.epi != EPI_BIAS) convert(std::true_type{});   // warp-uniform: one branch per 32 columns, none per element
+            else convert(std::false_type{});
+            e_math += gclk() - q2;
           }
         }
         if (use_res) res_release();
         for (int o = 0; o < n_out; ++o) {
           if (o == 1) {
             // D2 = bf16(D + pos[row % pos_rows]) computed from the ROUNDED D (oracle: act(x + pos))
-            const float* pp = p.pos + (long long)(row_ok ? (m % p.pos_rows) : 0) * p.N + n0 + c * 64;
+            const float* pp = p.pos + (long long)(row_ok ? ((m + p.pos_row0) % p.pos_rows) : 0) * p.N + n0 + c * 64;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float4 q = __ldg(reinterpret_cast<const float4*>(pp) + j);
@@ -403,20 +471,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
             }
           }
           // my staging box: its previous store has finished reading (waited for here, after the arithmetic)
-          if (et == 0) ptx::tma_store_wait_read<0>();
+          uint8_t* my_out = my_out0 + (out_n % kOutBufs) * STAGING_BYTES;
+          ++out_n;
+          const long long q3 = gclk();
+          if (et == 0) ptx::tma_store_wait_read<kOutBufs - 1>();   // the store that last used this box has read it
           ptx::named_bar_sync(bar_id, 128);
+          const long long q4 = gclk();
+          e_wait += q4 - q3;
           uint8_t* rowp = my_out + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
                 make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
           }
+          const long long q5 = gclk();
+          e_sts += q5 - q4;
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(bar_id, 128);
           if (et == 0) {
             ptx::tma_store_2d(o == 0 ? &p.tmD : &p.tmD2, my_out, n0 + c * 64, m0);
             ptx::tma_store_commit();
           }
+          e_fence += gclk() - q5;
         }
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
@@ -427,11 +503,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
         acc_phase ^= 1;
       }
     }
+    if (kGemmCounters && blockIdx.x == 0 && threadIdx.x == 0)
+      printf("gemm CTA 0 epilogue thread 0: %d tiles, %lld cycles: accumulator wait %lld, tcgen05.wait::ld %lld, math %lld, store-read wait + barrier %lld, "
+             "st.shared %lld, fence + barrier + TMA store %lld\n",
+             n_my, gclk() - e_begin, e_full, e_ld, e_math, e_wait, e_sts, e_fence);
     if (et == 0) ptx::tma_store_wait_all<0>();
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (kCluster > 1) ptx::cluster_sync();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 9) ptx::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
@@ -527,15 +608,47 @@ int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g) {
 
 namespace {
 
-template <int BLOCK_N, bool kHasRes, bool kBRes = false>
+template <int BLOCK_N, bool kHasRes, bool kBRes = false, int kOutBufs = 1>
 int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, kBRes>;
+  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, kBRes, 1, kOutBufs>;
+  constexpr int smem = smem_bytes_for(BLOCK_N, kHasRes, kBRes, kOutBufs);
+  static_assert(stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs) >= 2, "ring too shallow");
   if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes, kBRes)));
+    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, kNumThreads, smem_bytes_for(BLOCK_N, kHasRes, kBRes), s>>>(p);
+  kern<<<grid, kNumThreads, smem, s>>>(p);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+template <int BLOCK_N, bool kHasRes>
+int launch_cluster2(const GemmParams& p, int grid, cudaStream_t s) {
+  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, false, 2>;
+  static int max_clusters = -1;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem_bytes_for(BLOCK_N, kHasRes);
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes)));
+    cfg.gridDim = dim3(sm_count() / 2 * 2);
+    int n = 0;
+    OPD_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));   // GPCs with an odd SM count leave one SM without a partner
+    max_clusters = n;
+  }
+  OPD_REQUIRE(max_clusters > 0, "gemm: no 2-CTA cluster of the tensor-core kernel fits on this device");
+  cfg.gridDim = dim3(2 * std::min(grid / 2, max_clusters));
+  OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;
@@ -557,6 +670,10 @@ int finish_plan(GemmPlan* plan) {
   const long long tiles = m_blocks * (N / bn);
   plan->grid = (int)std::min<long long>(tiles, sm_count());
   // weight-stationary variant: bottleneck outputs with a short K and many m-blocks per CTA (ResNet stage-3 1x1 expansions)
+  // 2-CTA clusters with multicast weight tiles: the wide-tile layers with enough tile pairs to keep every cluster busy
+  const int clus = g_option_gemm_cluster.load();   // 2: whenever the shape allows it (tests)
+  plan->cluster = clus && bn == 256 && m_blocks >= 2 && (clus == 2 || ((m_blocks + 1) / 2) * (N / bn) >= 2LL * (sm_count() / 2));
+  plan->out_bufs = (g_option_gemm_outbufs.load() && plan->K / BLOCK_K <= 8 && bn >= 128) ? 2 : 1;   // short K: epilogue-paced
   const int bres = g_option_gemm_bres.load();   // 2: whenever the shape allows it (tests)
   plan->b_resident = bres && plan->epi == EPI_BIAS_RES_RELU && bn == 128 && plan->K / BLOCK_K <= kBResKBlocks && !plan->im2col &&
                      N / bn <= 16 && (bres == 2 || m_blocks >= 8LL * sm_count());
@@ -590,7 +707,7 @@ int gemm_plan_linear(GemmPlan* plan, const __nv_bfloat16* A, int64_t lda, const 
   if (int rc = finish_plan(plan)) return rc;
   plan->k_split = K / BLOCK_K;
   if (int rc = make_tmap_2d(&plan->tmA, A, M, K, lda, BLOCK_M)) return rc;
-  if (int rc = make_tmap_2d(&plan->tmB, W, N, K, K, plan->block_n)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB, W, N, K, K, plan->block_n / (plan->cluster ? 2 : 1))) return rc;
   if (int rc = make_tmap_2d(&plan->tmD, D, M, N, ldd, BLOCK_M)) return rc;
   if (D2) {
     if (int rc = make_tmap_2d(&plan->tmD2, D2, M, N, ldd, BLOCK_M)) return rc;
@@ -617,7 +734,7 @@ int gemm_plan_conv(GemmPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, co
   if (int rc = finish_plan(plan)) return rc;
   plan->k_split = plan->K / BLOCK_K;
   if (int rc = make_tmap_im2col(&plan->tmA, x, g)) return rc;
-  if (int rc = make_tmap_2d(&plan->tmB, W, N, plan->K, plan->K, plan->block_n)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB, W, N, plan->K, plan->K, plan->block_n / (plan->cluster ? 2 : 1))) return rc;
   if (int rc = make_tmap_2d(&plan->tmD, D, plan->M, N, N, BLOCK_M)) return rc;
   plan->tmD2 = plan->tmD;
   if (epi == EPI_BIAS_RES_RELU) {
@@ -640,7 +757,7 @@ int gemm_plan_linear_plus_shortcut(GemmPlan* plan, const __nv_bfloat16* A, int K
   plan->k_split = K1 / BLOCK_K;
   if (int rc = make_tmap_2d(&plan->tmA, A, plan->M, K1, K1, BLOCK_M)) return rc;
   if (int rc = make_tmap_im2col(&plan->tmA2, x2, g2)) return rc;
-  if (int rc = make_tmap_2d(&plan->tmB, W, N, plan->K, plan->K, plan->block_n)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmB, W, N, plan->K, plan->K, plan->block_n / (plan->cluster ? 2 : 1))) return rc;
   if (int rc = make_tmap_2d(&plan->tmD, D, plan->M, N, N, BLOCK_M)) return rc;
   plan->tmD2 = plan->tmD;
   plan->tmR = plan->tmD;
@@ -664,14 +781,18 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     p.KW = 1; p.stride = plan.g2.stride; p.pad_h = 0; p.pad_w = 0; p.P = plan.g2.P; p.Q = plan.g2.Q;
   }
   p.epi = plan.epi; p.bias = plan.bias; p.residual = plan.residual; p.ldr = plan.ldr;
-  p.gamma = plan.gamma; p.beta = plan.beta; p.pos = plan.pos; p.pos_rows = plan.pos_rows; p.has_d2 = plan.has_d2;
+  p.gamma = plan.gamma; p.beta = plan.beta; p.pos = plan.pos; p.pos_rows = plan.pos_rows; p.pos_row0 = plan.pos_row0; p.has_d2 = plan.has_d2;
   const bool has_res = plan.epi == EPI_BIAS_RES_RELU || plan.epi == EPI_BIAS_RES_LN;
   switch (plan.block_n) {
     case 64: return has_res ? launch_t<64, true>(p, plan.grid, stream) : launch_t<64, false>(p, plan.grid, stream);
     case 128:
       if (has_res && plan.b_resident) return launch_t<128, true, true>(p, plan.grid, stream);
+      if (plan.out_bufs == 2) return has_res ? launch_t<128, true, false, 2>(p, plan.grid, stream) : launch_t<128, false, false, 2>(p, plan.grid, stream);
       return has_res ? launch_t<128, true>(p, plan.grid, stream) : launch_t<128, false>(p, plan.grid, stream);
-    case 256: return has_res ? launch_t<256, true>(p, plan.grid, stream) : launch_t<256, false>(p, plan.grid, stream);
+    case 256:
+      if (plan.cluster) return has_res ? launch_cluster2<256, true>(p, plan.grid, stream) : launch_cluster2<256, false>(p, plan.grid, stream);
+      if (plan.out_bufs == 2) return has_res ? launch_t<256, true, false, 2>(p, plan.grid, stream) : launch_t<256, false, false, 2>(p, plan.grid, stream);
+      return has_res ? launch_t<256, true>(p, plan.grid, stream) : launch_t<256, false>(p, plan.grid, stream);
   }
   return fail(OPD_ERR_INVALID, "gemm: unsupported block_n %d", plan.block_n);
 }

@@ -34,6 +34,8 @@ struct GemmPlan {
   ConvGeom g2;         // geometry of the second source (1x1, stride s, pad 0)
   int M, N, K;
   int block_n;
+  int out_bufs;        // staging boxes per epilogue warpgroup (2 for short-K layers)
+  int cluster;         // 1: 2-CTA cluster variant (weight tiles multicast to both CTAs)
   int b_resident;      // 1: weight-stationary kernel variant (one n-block per CTA, its weights resident in shared memory)
   int im2col;          // 0: A is [M,K] rows; 1: A is NHWC through im2col TMA
   ConvGeom g;
@@ -45,6 +47,7 @@ struct GemmPlan {
   const float* beta;
   const float* pos;
   int pos_rows;
+  int pos_row0;        // pos row of this GEMM's row 0 (row-range GEMMs); 0 by default
   int has_d2;
   int grid;
 };
