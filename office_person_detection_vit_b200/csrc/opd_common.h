@@ -21,6 +21,7 @@ extern std::atomic<int> g_option_attention_tc;  // 1 (default): tcgen05 attentio
 extern std::atomic<int> g_option_probe;        // measurement probes, 0 in production: bit 0 stem without patch reloads, bit 1 stem without stores
 extern std::atomic<int> g_option_gemm_cluster; // 0 (default) / 1: BLOCK_N = 256 layers as 2-CTA clusters with multicast weight tiles (measured: no gain)
 extern std::atomic<int> g_option_gemm_outbufs; // 1 (default): short-K GEMMs double-buffer the epilogue's staging boxes
+extern std::atomic<int> g_option_pdl;          // 1: GEMM launches allow programmatic dependent launch (default 0: launch gaps are not what the step waits on)
 extern std::atomic<int> g_option_gemm_bres;    // 1 (default): short-K bottleneck outputs use the weight-stationary GEMM variant
 extern std::atomic<int> g_option_stem_pool;    // 1 (default): max pooling fused into the stem kernel's epilogue
 extern std::atomic<int> g_option_bneck_halo;   // 1 (default): stride-1 / 64-channel bottleneck tails use the halo-patch kernel

@@ -15,6 +15,7 @@ std::atomic<int> g_option_stem_pool{1};
 std::atomic<int> g_option_gemm_bres{1};
 std::atomic<int> g_option_gemm_cluster{0};
 std::atomic<int> g_option_gemm_outbufs{1};
+std::atomic<int> g_option_pdl{0};
 }  // namespace opd
 
 extern "C" {
@@ -44,6 +45,10 @@ int opd_set_option(const char* name, int32_t value) {
   }
   if (name && std::string(name) == "gemm_outbufs") {   // 0: one staging box per epilogue warpgroup everywhere (A/B runs; new plans only)
     opd::g_option_gemm_outbufs.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "pdl") {   // 1: GEMM launches allow programmatic dependent launch (default 0: measured, no gain)
+    opd::g_option_pdl.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "stem_pool") {   // 0: stem and max pooling as two kernels; 1: fused (default); 2: fused in debug plans too

@@ -157,6 +157,9 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
                ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
+// ---- programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// the previous kernel of the stream drains; everything it reads or writes in global memory must come after this wait ----
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // ---- thread-block clusters ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (kCluster > 1) ptx::cluster_sync();   // the peer's barriers are initialised before anything is multicast to them
+  // PDL: barriers, TMEM and tensor-map prefetches above overlap the previous kernel's last wave; its results are visible below
+  ptx::grid_dependency_wait();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   const int cta_rank = kCluster > 1 ? (int)ptx::cluster_ctarank() : 0;
@@ -618,7 +620,21 @@ int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
     OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, kNumThreads, smem, s>>>(p);
+  if (g_option_pdl.load()) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    kern<<<grid, kNumThreads, smem, s>>>(p);
+  }
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;
