@@ -50,18 +50,18 @@ __host__ __device__ constexpr int tail_bytes_for(bool has_res) { return kMaxN * 
 // tiles and only A tiles stream through the ring.  The 1x1 expansions of ResNet stage 3 (K = 256, N = 1024) re-read
 // 64 KB of weights per 128 x 128 tile otherwise and ran at the L2 -> SM limit (10 TB/s), not at the HBM roofline.
 constexpr int kBResKBlocks = 4;
-__host__ __device__ constexpr int stages_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1) {
+__host__ __device__ constexpr int stages_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1, int m_tiles = 1) {
   const int fixed = (2 * out_bufs + res_stages_for(block_n, has_res)) * STAGING_BYTES + tail_bytes_for(has_res);
   if (b_res) {
     const int n = (kSmemBudget - fixed - kBResKBlocks * block_n * BLOCK_K * 2) / A_STAGE_BYTES;
     return n > 8 ? 8 : n;
   }
-  const int stage = A_STAGE_BYTES + block_n * BLOCK_K * 2;
+  const int stage = m_tiles * A_STAGE_BYTES + block_n * BLOCK_K * 2;
   const int n = (kSmemBudget - fixed) / stage;
   return n > 8 ? 8 : n;
 }
-__host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1) {
-  return stages_for(block_n, has_res, b_res, out_bufs) * (A_STAGE_BYTES + (b_res ? 0 : block_n * BLOCK_K * 2)) +
+__host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1, int m_tiles = 1) {
+  return stages_for(block_n, has_res, b_res, out_bufs, m_tiles) * (m_tiles * A_STAGE_BYTES + (b_res ? 0 : block_n * BLOCK_K * 2)) +
          (b_res ? kBResKBlocks * block_n * BLOCK_K * 2 : 0) + (2 * out_bufs + res_stages_for(block_n, has_res)) * STAGING_BYTES +
          tail_bytes_for(has_res);
 }
@@ -101,10 +101,19 @@ struct GemmParams {
 // kOutBufs = 2 (short-K layers, where the epilogue and not the MMAs paces the kernel: reading a 128 x 256 fp32 accumulator
 // out of TMEM alone takes as long as the four k-blocks of MMAs): two staging boxes per epilogue warpgroup, so a chunk is
 // written while the TMA store of the previous one still reads its box.
-template <int BLOCK_N, bool kHasRes, bool kBRes = false, int kCluster = 1, int kOutBufs = 1>
+// kMTiles = 2 (long-K layers with BLOCK_N = 256, where the MMA thread waits for operands 80-90 % of the time): the CTA works
+// on PAIRS of m-blocks with the same n-block.  Every ring slot carries two A tiles and ONE weight tile that both use, so the
+// bytes per flop drop by a third (K = 2048: 3 MB -> 2 MB per 256 rows).  The two accumulators are the two TMEM stages: the
+// epilogue sees the same alternating sequence of tiles as before; what is lost is the overlap of a pair's first MMAs with the
+// previous pair's epilogue (a few thousand cycles against >= 16 k-blocks x 1024 cycles of MMAs).
+// MEASURED (round 1): 10-40 % SLOWER on every layer it applies to - three 64 KB ring slots hide less latency than four 48 KB
+// ones and the LayerNorm epilogue no longer overlaps - so it is off by default (opd_set_option("gemm_mpairs", 1)).
+template <int BLOCK_N, bool kHasRes, bool kBRes = false, int kCluster = 1, int kOutBufs = 1, int kMTiles = 1>
 __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmParams p) {
+  static_assert(kMTiles == 1 || (kMTiles == 2 && !kBRes && kCluster == 1), "m-block pairs: plain variant only");
+  constexpr int A_SLOT_BYTES = kMTiles * A_STAGE_BYTES;
   static_assert(kCluster == 1 || (kCluster == 2 && !kBRes), "clusters of two, not combined with the weight-stationary variant");
-  constexpr int kStages = stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs);
+  constexpr int kStages = stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs, kMTiles);
   constexpr int kResStages = res_stages_for(BLOCK_N, kHasRes);
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * A_STAGE_BYTES;
+  uint8_t* smem_b = smem + kStages * A_SLOT_BYTES;
   uint8_t* smem_out = smem_b + (kBRes ? kBResKBlocks : kStages) * B_STAGE_BYTES;   // 2 staging boxes (kBRes: smem_b = resident weights)
   uint8_t* smem_res = smem_out + 2 * kOutBufs * STAGING_BYTES;    // kResStages residual chunks
   float* s_bias = reinterpret_cast<float*>(smem_res + kResStages * STAGING_BYTES);   // [N]: the whole layer's bias
@@ -170,11 +179,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   // kCluster = 2: cluster c works on pairs c + i * (clusters); pair -> (m-block pair, n-block), this CTA's m-block = 2 * pair_m +
   // rank.  Both CTAs run the same number of iterations (with an odd number of m-blocks rank 1 recomputes the last one).
   const int cl_pairs = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks, cl_id = (int)blockIdx.x / 2, cl_n = (int)gridDim.x / 2;
-  const int n_my = kCluster > 1 ? (cl_id < cl_pairs ? (cl_pairs - cl_id + cl_n - 1) / cl_n : 0)
-                   : kBRes      ? (br_m0 < p.num_m_blocks ? (p.num_m_blocks - br_m0 + br_step - 1) / br_step : 0)
-                                : ((int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+  // kMTiles = 2: the CTA's units are pairs blockIdx.x + u * gridDim.x; tile i of the epilogue = sub-tile i & 1 of unit i >> 1
+  const int n_units = kMTiles == 2 ? ((int)blockIdx.x < cl_pairs ? (cl_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0) : 0;
+  const int n_my = kMTiles == 2   ? 2 * n_units
+                   : kCluster > 1 ? (cl_id < cl_pairs ? (cl_pairs - cl_id + cl_n - 1) / cl_n : 0)
+                   : kBRes        ? (br_m0 < p.num_m_blocks ? (p.num_m_blocks - br_m0 + br_step - 1) / br_step : 0)
+                                  : ((int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
   auto tile_mn = [&](int i, int& m_blk, int& n_blk) {
-    if (kCluster > 1) {
+    if (kMTiles == 2) {
+      const int pair = (int)blockIdx.x + (i >> 1) * (int)gridDim.x;
+      const int pm = pair / p.num_n_blocks;
+      n_blk = pair - pm * p.num_n_blocks;
+      m_blk = min(2 * pm + (i & 1), p.num_m_blocks - 1);   // odd tail: the second sub-tile repeats the last m-block
+    } else if (kCluster > 1) {
       const int pair = cl_id + i * cl_n;
       const int pm = pair / p.num_n_blocks;
       n_blk = pair - pm * p.num_n_blocks;
@@ -199,32 +216,41 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
         for (int kb = 0; kb < p.num_k_blocks; ++kb)
           ptx::tma_load_2d(&p.tmB, b_res_full, smem_b + kb * B_STAGE_BYTES, kb * BLOCK_K, br_n * BLOCK_N);
       }
-      for (int it = 0; it < n_my; ++it) {
-        int m_blk, n_blk;
-        tile_mn(it, m_blk, n_blk);
-        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
-        int base_w = 0, base_h = 0, img = 0;
-        if (p.im2col || p.k_split < p.num_k_blocks) {
-          const int pq = p.P * p.Q;
-          img = m0 / pq;
-          const int rem = m0 - img * pq;
-          const int op = rem / p.Q, oq = rem - op * p.Q;
-          base_w = oq * p.stride - p.pad_w;
-          base_h = op * p.stride - p.pad_h;
+      for (int it = 0; it < n_my; it += kMTiles) {
+        int m0[kMTiles], base_w[kMTiles], base_h[kMTiles], img[kMTiles], n0 = 0;
+#pragma unroll
+        for (int sub = 0; sub < kMTiles; ++sub) {
+          int m_blk, n_blk;
+          tile_mn(it + sub, m_blk, n_blk);
+          m0[sub] = m_blk * BLOCK_M;
+          n0 = n_blk * BLOCK_N;
+          base_w[sub] = base_h[sub] = img[sub] = 0;
+          if (p.im2col || p.k_split < p.num_k_blocks) {
+            const int pq = p.P * p.Q;
+            img[sub] = m0[sub] / pq;
+            const int rem = m0[sub] - img[sub] * pq;
+            const int op = rem / p.Q, oq = rem - op * p.Q;
+            base_w[sub] = oq * p.stride - p.pad_w;
+            base_h[sub] = op * p.stride - p.pad_h;
+          }
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (kBRes ? 0 : B_STAGE_BYTES));
-          if (kb >= p.k_split) {
-            ptx::tma_load_im2col_4d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, (kb - p.k_split) * BLOCK_K, base_w,
-                                    base_h, img, (uint16_t)0, (uint16_t)0);
-          } else if (p.im2col) {
-            const int tap = kb / p.c_blocks, cb = kb - tap * p.c_blocks;
-            const int r = tap / p.KW, s = tap - r * p.KW;
-            ptx::tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, cb * BLOCK_K, base_w,
-                                    base_h, img, (uint16_t)s, (uint16_t)r);
-          } else {
-            ptx::tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m0);
+          ptx::mbar_expect_tx(&full_bar[stage], A_SLOT_BYTES + (kBRes ? 0 : B_STAGE_BYTES));
+#pragma unroll
+          for (int sub = 0; sub < kMTiles; ++sub) {
+            uint8_t* dst = smem_a + stage * A_SLOT_BYTES + sub * A_STAGE_BYTES;
+            if (kb >= p.k_split) {
+              ptx::tma_load_im2col_4d(&p.tmA2, &full_bar[stage], dst, (kb - p.k_split) * BLOCK_K, base_w[sub], base_h[sub], img[sub],
+                                      (uint16_t)0, (uint16_t)0);
+            } else if (p.im2col) {
+              const int tap = kb / p.c_blocks, cb = kb - tap * p.c_blocks;
+              const int r = tap / p.KW, sx = tap - r * p.KW;
+              ptx::tma_load_im2col_4d(&p.tmA, &full_bar[stage], dst, cb * BLOCK_K, base_w[sub], base_h[sub], img[sub], (uint16_t)sx,
+                                      (uint16_t)r);
+            } else {
+              ptx::tma_load_2d(&p.tmA, &full_bar[stage], dst, kb * BLOCK_K, m0[sub]);
+            }
           }
           if (kCluster > 1) {   // my half of the weight tile, into both CTAs' slots (tmB box = BLOCK_N / 2 rows)
             ptx::tma_load_2d_multicast(&p.tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + cta_rank * (B_STAGE_BYTES / 2),
@@ -248,23 +274,36 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       uint32_t acc_phase = 0;
       if (kBRes && n_my > 0) ptx::mbar_wait(b_res_full, 0);
       long long w_acc = 0, w_full = 0, t_begin = gclk();
-      for (int it = 0; it < n_my; ++it) {
-        const long long c0 = gclk();
-        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        w_acc += gclk() - c0;
-        ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int it = 0; it < n_my; it += kMTiles) {
+        if (kMTiles == 1) {
+          const long long c0 = gclk();
+          ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          w_acc += gclk() - c0;
+          ptx::tc_fence_after_sync();
+        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           const long long c1 = gclk();
           ptx::mbar_wait(&full_bar[stage], phase);
           w_full += gclk() - c1;
           ptx::tc_fence_after_sync();
-          const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
           const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + (kBRes ? kb : stage) * B_STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) start-address field
-            ptx::umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+          for (int sub = 0; sub < kMTiles; ++sub) {
+            const int a_idx = kMTiles == 2 ? sub : acc;   // pairs: sub-tile = TMEM stage
+            if (kMTiles == 2 && kb == 0) {
+              const long long c0 = gclk();
+              ptx::mbar_wait(&tmem_empty[a_idx], acc_phase ^ 1);
+              w_acc += gclk() - c0;
+              ptx::tc_fence_after_sync();
+            }
+            const uint32_t d_tmem = tmem_base + a_idx * BLOCK_N;
+            const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a + stage * A_SLOT_BYTES + sub * A_STAGE_BYTES));
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) start-address field
+              ptx::umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+            }
+            if (kMTiles == 2 && kb == p.num_k_blocks - 1) ptx::umma_commit(&tmem_full[a_idx]);   // this sub-tile's accumulator is complete
           }
           if (kCluster > 1) ptx::umma_commit_multicast(&empty_bar[stage], (uint16_t)0x3);   // both CTAs' producers write this slot
           else ptx::umma_commit(&empty_bar[stage]);   // frees the ring slot once these MMAs have read it
@@ -273,10 +312,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
             phase ^= 1;
           }
         }
-        ptx::umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
-        if (++acc == 2) {
-          acc = 0;
+        if (kMTiles == 2) {
           acc_phase ^= 1;
+        } else {
+          ptx::umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
         }
       }
       if (kGemmCounters && blockIdx.x == 0)
@@ -610,12 +653,12 @@ int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g) {
 
 namespace {
 
-template <int BLOCK_N, bool kHasRes, bool kBRes = false, int kOutBufs = 1>
+template <int BLOCK_N, bool kHasRes, bool kBRes = false, int kOutBufs = 1, int kMTiles = 1>
 int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, kBRes, 1, kOutBufs>;
-  constexpr int smem = smem_bytes_for(BLOCK_N, kHasRes, kBRes, kOutBufs);
-  static_assert(stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs) >= 2, "ring too shallow");
+  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, kBRes, 1, kOutBufs, kMTiles>;
+  constexpr int smem = smem_bytes_for(BLOCK_N, kHasRes, kBRes, kOutBufs, kMTiles);
+  static_assert(stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs, kMTiles) >= 2, "ring too shallow");
   if (!configured) {
     OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
@@ -689,7 +732,12 @@ int finish_plan(GemmPlan* plan) {
   // 2-CTA clusters with multicast weight tiles: the wide-tile layers with enough tile pairs to keep every cluster busy
   const int clus = g_option_gemm_cluster.load();   // 2: whenever the shape allows it (tests)
   plan->cluster = clus && bn == 256 && m_blocks >= 2 && (clus == 2 || ((m_blocks + 1) / 2) * (N / bn) >= 2LL * (sm_count() / 2));
-  plan->out_bufs = (g_option_gemm_outbufs.load() && plan->K / BLOCK_K <= 8 && bn >= 128) ? 2 : 1;   // short K: epilogue-paced
+  // pairs of m-blocks per CTA for the long-K wide-tile layers (operand-feed bound): 2: whenever the shape allows it (tests)
+  const int mt = g_option_gemm_mpairs.load();
+  const long long pairs = ((m_blocks + 1) / 2) * (N / bn);
+  plan->m_tiles = (mt && bn == 256 && !plan->cluster && m_blocks >= 2 && (mt == 2 || (plan->K / BLOCK_K >= 16 && pairs >= sm_count()))) ? 2 : 1;
+  if (plan->m_tiles == 2) plan->grid = (int)std::min<long long>(pairs, sm_count());
+  plan->out_bufs = (plan->m_tiles == 1 && g_option_gemm_outbufs.load() && plan->K / BLOCK_K <= 8 && bn >= 128) ? 2 : 1;   // short K: epilogue-paced
   const int bres = g_option_gemm_bres.load();   // 2: whenever the shape allows it (tests)
   plan->b_resident = bres && plan->epi == EPI_BIAS_RES_RELU && bn == 128 && plan->K / BLOCK_K <= kBResKBlocks && !plan->im2col &&
                      N / bn <= 16 && (bres == 2 || m_blocks >= 8LL * sm_count());
@@ -807,6 +855,7 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
       return has_res ? launch_t<128, true>(p, plan.grid, stream) : launch_t<128, false>(p, plan.grid, stream);
     case 256:
       if (plan.cluster) return has_res ? launch_cluster2<256, true>(p, plan.grid, stream) : launch_cluster2<256, false>(p, plan.grid, stream);
+      if (plan.m_tiles == 2) return has_res ? launch_t<256, true, false, 1, 2>(p, plan.grid, stream) : launch_t<256, false, false, 1, 2>(p, plan.grid, stream);
       if (plan.out_bufs == 2) return has_res ? launch_t<256, true, false, 2>(p, plan.grid, stream) : launch_t<256, false, false, 2>(p, plan.grid, stream);
       return has_res ? launch_t<256, true>(p, plan.grid, stream) : launch_t<256, false>(p, plan.grid, stream);
   }

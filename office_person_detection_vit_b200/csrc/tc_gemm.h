@@ -34,6 +34,7 @@ struct GemmPlan {
   ConvGeom g2;         // geometry of the second source (1x1, stride s, pad 0)
   int M, N, K;
   int block_n;
+  int m_tiles;         // 2: the CTA works on pairs of m-blocks that share every weight tile (long-K layers)
   int out_bufs;        // staging boxes per epilogue warpgroup (2 for short-K layers)
   int cluster;         // 1: 2-CTA cluster variant (weight tiles multicast to both CTAs)
   int b_resident;      // 1: weight-stationary kernel variant (one n-block per CTA, its weights resident in shared memory)
