@@ -27,6 +27,7 @@ for variant in [[]] + [[s] for s in args.set]:
     for s in variant:
         k, v = s.split("=")
         _lib.check(_lib.lib().opd_set_option(k.encode(), int(v)), "opd_set_option")
+    det.model.set_debug(False)   # drops the cached launch plan: plan-time options take effect
     for _ in range(2):
         det.model.forward(frames)
     torch.cuda.synchronize()

@@ -16,6 +16,7 @@ std::atomic<int> g_option_gemm_bres{1};
 std::atomic<int> g_option_gemm_cluster{0};
 std::atomic<int> g_option_gemm_outbufs{1};
 std::atomic<int> g_option_pdl{0};
+std::atomic<int> g_option_gemm_pair{1};
 std::atomic<int> g_option_gemm_mpairs{0};
 }  // namespace opd
 
@@ -54,6 +55,10 @@ int opd_set_option(const char* name, int32_t value) {
   }
   if (name && std::string(name) == "gemm_mpairs") {   // 0 (default): no m-block pairs; 1: long-K BLOCK_N = 256 layers; 2: whenever BLOCK_N = 256 (tests); new plans only
     opd::g_option_gemm_mpairs.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "gemm_pair") {   // cta_group::2 GEMM: 0 off, 1 (default) BLOCK_N = 256 layers with a tile pair per cluster, 3 whenever BLOCK_N = 256 (tests); new plans only
+    opd::g_option_gemm_pair.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "stem_pool") {   // 0: stem and max pooling as two kernels; 1: fused (default); 2: fused in debug plans too

@@ -50,18 +50,21 @@ __host__ __device__ constexpr int tail_bytes_for(bool has_res) { return kMaxN * 
 // tiles and only A tiles stream through the ring.  The 1x1 expansions of ResNet stage 3 (K = 256, N = 1024) re-read
 // 64 KB of weights per 128 x 128 tile otherwise and ran at the L2 -> SM limit (10 TB/s), not at the HBM roofline.
 constexpr int kBResKBlocks = 4;
-__host__ __device__ constexpr int stages_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1, int m_tiles = 1) {
+__host__ __device__ constexpr int stages_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1, int m_tiles = 1,
+                                             bool pair = false) {
   const int fixed = (2 * out_bufs + res_stages_for(block_n, has_res)) * STAGING_BYTES + tail_bytes_for(has_res);
   if (b_res) {
     const int n = (kSmemBudget - fixed - kBResKBlocks * block_n * BLOCK_K * 2) / A_STAGE_BYTES;
     return n > 8 ? 8 : n;
   }
-  const int stage = m_tiles * A_STAGE_BYTES + block_n * BLOCK_K * 2;
+  const int stage = m_tiles * A_STAGE_BYTES + block_n * BLOCK_K * 2 / (pair ? 2 : 1);
   const int n = (kSmemBudget - fixed) / stage;
   return n > 8 ? 8 : n;
 }
-__host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1, int m_tiles = 1) {
-  return stages_for(block_n, has_res, b_res, out_bufs, m_tiles) * (m_tiles * A_STAGE_BYTES + (b_res ? 0 : block_n * BLOCK_K * 2)) +
+__host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1, int m_tiles = 1,
+                                                 bool pair = false) {
+  return stages_for(block_n, has_res, b_res, out_bufs, m_tiles, pair) *
+             (m_tiles * A_STAGE_BYTES + (b_res ? 0 : block_n * BLOCK_K * 2 / (pair ? 2 : 1))) +
          (b_res ? kBResKBlocks * block_n * BLOCK_K * 2 : 0) + (2 * out_bufs + res_stages_for(block_n, has_res)) * STAGING_BYTES +
          tail_bytes_for(has_res);
 }
@@ -108,16 +111,24 @@ struct GemmParams {
 // previous pair's epilogue (a few thousand cycles against >= 16 k-blocks x 1024 cycles of MMAs).
 // MEASURED (round 1): 10-40 % SLOWER on every layer it applies to - three 64 KB ring slots hide less latency than four 48 KB
 // ones and the LayerNorm epilogue no longer overlaps - so it is off by default (opd_set_option("gemm_mpairs", 1)).
-template <int BLOCK_N, bool kHasRes, bool kBRes = false, int kCluster = 1, int kOutBufs = 1, int kMTiles = 1>
+// kPair (cta_group::2, with kCluster = 2): the two CTAs of the cluster form ONE 256 x BLOCK_N MMA.  Each CTA stores its own
+// 128 A rows and HALF of the weight tile (BLOCK_N / 2 rows) per ring slot; the leader (rank 0) issues tcgen05.mma.cta_group::2,
+// which reads both halves from both shared memories and accumulates each CTA's 128 rows into that CTA's TMEM.  Per 512
+// math-cycles a shared memory now takes 32 KB of TMA writes and 32 KB of operand reads instead of 48 + 48: the port that
+// capped the single-CTA kernel at 67 % of the tensor pipe is no longer the limit.  Both CTAs' TMA loads signal the LEADER's
+// full barrier; the leader's tcgen05.commit is multicast to both CTAs' empty / accumulator-full barriers; both CTAs'
+// epilogue warps arrive on the leader's accumulator-empty barrier.
+template <int BLOCK_N, bool kHasRes, bool kBRes = false, int kCluster = 1, int kOutBufs = 1, int kMTiles = 1, bool kPair = false>
 __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmParams p) {
+  static_assert(!kPair || (kCluster == 2 && kMTiles == 1 && !kBRes), "cta_group::2 needs the 2-CTA cluster variant");
   static_assert(kMTiles == 1 || (kMTiles == 2 && !kBRes && kCluster == 1), "m-block pairs: plain variant only");
   constexpr int A_SLOT_BYTES = kMTiles * A_STAGE_BYTES;
   static_assert(kCluster == 1 || (kCluster == 2 && !kBRes), "clusters of two, not combined with the weight-stationary variant");
-  constexpr int kStages = stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs, kMTiles);
+  constexpr int kStages = stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs, kMTiles, kPair);
   constexpr int kResStages = res_stages_for(BLOCK_N, kHasRes);
-  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2 / (kPair ? 2 : 1);   // kPair: this CTA's half of the weight tile
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N);
+  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kPair ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
@@ -146,11 +157,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     if (p.k_split < p.num_k_blocks) ptx::prefetch_tmap(&p.tmA2);
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], kCluster);   // one tcgen05.commit per CTA of the cluster
+      ptx::mbar_init(&empty_bar[i], kPair ? 1 : kCluster);   // one tcgen05.commit per issuing CTA (kPair: the leader's, multicast)
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
-      ptx::mbar_init(&tmem_empty[i], 256);
+      ptx::mbar_init(&tmem_empty[i], kPair ? 16 : 256);   // kPair: one arrival per epilogue warp of BOTH CTAs, on the leader
     }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&res_full[i], 1);
@@ -159,7 +170,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     ptx::mbar_init(b_res_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 9) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 9) {
+    if (kPair) ptx::tmem_alloc_2sm<kTmemCols>(tmem_ptr);
+    else ptx::tmem_alloc<kTmemCols>(tmem_ptr);
+  }
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (kCluster > 1) ptx::cluster_sync();   // the peer's barriers are initialised before anything is multicast to them
@@ -236,23 +250,31 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], A_SLOT_BYTES + (kBRes ? 0 : B_STAGE_BYTES));
+          if (!kPair) ptx::mbar_expect_tx(&full_bar[stage], A_SLOT_BYTES + (kBRes ? 0 : B_STAGE_BYTES));
+          else if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * (A_SLOT_BYTES + B_STAGE_BYTES));   // both CTAs' bytes land here
 #pragma unroll
           for (int sub = 0; sub < kMTiles; ++sub) {
             uint8_t* dst = smem_a + stage * A_SLOT_BYTES + sub * A_STAGE_BYTES;
             if (kb >= p.k_split) {
-              ptx::tma_load_im2col_4d(&p.tmA2, &full_bar[stage], dst, (kb - p.k_split) * BLOCK_K, base_w[sub], base_h[sub], img[sub],
-                                      (uint16_t)0, (uint16_t)0);
+              if (kPair) ptx::tma_load_im2col_4d_2sm(&p.tmA2, &full_bar[stage], dst, (kb - p.k_split) * BLOCK_K, base_w[sub], base_h[sub],
+                                                     img[sub], (uint16_t)0, (uint16_t)0);
+              else ptx::tma_load_im2col_4d(&p.tmA2, &full_bar[stage], dst, (kb - p.k_split) * BLOCK_K, base_w[sub], base_h[sub], img[sub],
+                                           (uint16_t)0, (uint16_t)0);
             } else if (p.im2col) {
               const int tap = kb / p.c_blocks, cb = kb - tap * p.c_blocks;
               const int r = tap / p.KW, sx = tap - r * p.KW;
-              ptx::tma_load_im2col_4d(&p.tmA, &full_bar[stage], dst, cb * BLOCK_K, base_w[sub], base_h[sub], img[sub], (uint16_t)sx,
-                                      (uint16_t)r);
+              if (kPair) ptx::tma_load_im2col_4d_2sm(&p.tmA, &full_bar[stage], dst, cb * BLOCK_K, base_w[sub], base_h[sub], img[sub],
+                                                     (uint16_t)sx, (uint16_t)r);
+              else ptx::tma_load_im2col_4d(&p.tmA, &full_bar[stage], dst, cb * BLOCK_K, base_w[sub], base_h[sub], img[sub], (uint16_t)sx,
+                                           (uint16_t)r);
             } else {
-              ptx::tma_load_2d(&p.tmA, &full_bar[stage], dst, kb * BLOCK_K, m0[sub]);
+              if (kPair) ptx::tma_load_2d_2sm(&p.tmA, &full_bar[stage], dst, kb * BLOCK_K, m0[sub]);
+              else ptx::tma_load_2d(&p.tmA, &full_bar[stage], dst, kb * BLOCK_K, m0[sub]);
             }
           }
-          if (kCluster > 1) {   // my half of the weight tile, into both CTAs' slots (tmB box = BLOCK_N / 2 rows)
+          if (kPair) {   // my half of the weight tile, into MY slot only; the leader's barrier counts the bytes
+            ptx::tma_load_2d_2sm(&p.tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, kb * BLOCK_K, n0 + cta_rank * (BLOCK_N / 2));
+          } else if (kCluster > 1) {   // my half of the weight tile, into both CTAs' slots (tmB box = BLOCK_N / 2 rows)
             ptx::tma_load_2d_multicast(&p.tmB, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + cta_rank * (B_STAGE_BYTES / 2),
                                        kb * BLOCK_K, n0 + cta_rank * (BLOCK_N / 2), (uint16_t)0x3);
           } else if (!kBRes) {
@@ -267,7 +289,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     }
   } else if (warp == 9) {
     // ===================================== MMA issuer =====================================
-    if (ptx::elect_one()) {
+    if ((!kPair || cta_rank == 0) && ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -301,11 +323,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               // advancing K by 16 bf16 = 32 bytes inside the swizzle row: +2 in the (>>4) start-address field
-              ptx::umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+              if (kPair) ptx::umma_bf16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+              else ptx::umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
             }
             if (kMTiles == 2 && kb == p.num_k_blocks - 1) ptx::umma_commit(&tmem_full[a_idx]);   // this sub-tile's accumulator is complete
           }
-          if (kCluster > 1) ptx::umma_commit_multicast(&empty_bar[stage], (uint16_t)0x3);   // both CTAs' producers write this slot
+          if (kPair) ptx::umma_commit_2sm(&empty_bar[stage], (uint16_t)0x3);   // both CTAs' slots are free once the pair's MMAs have read them
+          else if (kCluster > 1) ptx::umma_commit_multicast(&empty_bar[stage], (uint16_t)0x3);   // both CTAs' producers write this slot
           else ptx::umma_commit(&empty_bar[stage]);   // frees the ring slot once these MMAs have read it
           if (++stage == kStages) {
             stage = 0;
@@ -315,7 +339,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
         if (kMTiles == 2) {
           acc_phase ^= 1;
         } else {
-          ptx::umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+          if (kPair) ptx::umma_commit_2sm(&tmem_full[acc], (uint16_t)0x3);   // each CTA's epilogue drains its own 128 rows
+          else ptx::umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
@@ -542,7 +567,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&tmem_empty[acc]);
+      if (kPair) {   // one arrival per warp, on the leader's barrier (the leader's MMA thread owns both CTAs' accumulators)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+      } else {
+        ptx::mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -558,7 +588,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (kCluster > 1) ptx::cluster_sync();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
-  if (warp == 9) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == 9) {
+    if (kPair) ptx::tmem_dealloc_2sm<kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -683,9 +716,9 @@ int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
   return OPD_OK;
 }
 
-template <int BLOCK_N, bool kHasRes>
+template <int BLOCK_N, bool kHasRes, bool kPair = false>
 int launch_cluster2(const GemmParams& p, int grid, cudaStream_t s) {
-  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, false, 2>;
+  auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, false, 2, 1, 1, kPair>;
   static int max_clusters = -1;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -694,12 +727,12 @@ int launch_cluster2(const GemmParams& p, int grid, cudaStream_t s) {
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = smem_bytes_for(BLOCK_N, kHasRes);
+  cfg.dynamicSmemBytes = smem_bytes_for(BLOCK_N, kHasRes, false, 1, 1, kPair);
   cfg.stream = s;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (max_clusters < 0) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes)));
+    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes, false, 1, 1, kPair)));
     cfg.gridDim = dim3(sm_count() / 2 * 2);
     int n = 0;
     OPD_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));   // GPCs with an odd SM count leave one SM without a partner
@@ -732,6 +765,10 @@ int finish_plan(GemmPlan* plan) {
   // 2-CTA clusters with multicast weight tiles: the wide-tile layers with enough tile pairs to keep every cluster busy
   const int clus = g_option_gemm_cluster.load();   // 2: whenever the shape allows it (tests)
   plan->cluster = clus && bn == 256 && m_blocks >= 2 && (clus == 2 || ((m_blocks + 1) / 2) * (N / bn) >= 2LL * (sm_count() / 2));
+  // cta_group::2 pairs (plan->cluster = 2): 1 (default) = every BLOCK_N = 256 layer with at least one tile pair per cluster,
+  // 3 = whenever the shape allows it (tests)
+  const int pr = g_option_gemm_pair.load();
+  if (pr && bn == 256 && m_blocks >= 2 && (pr == 3 || ((m_blocks + 1) / 2) * (N / bn) >= sm_count() / 2)) plan->cluster = 2;
   // pairs of m-blocks per CTA for the long-K wide-tile layers (operand-feed bound): 2: whenever the shape allows it (tests)
   const int mt = g_option_gemm_mpairs.load();
   const long long pairs = ((m_blocks + 1) / 2) * (N / bn);
@@ -854,6 +891,7 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
       if (plan.out_bufs == 2) return has_res ? launch_t<128, true, false, 2>(p, plan.grid, stream) : launch_t<128, false, false, 2>(p, plan.grid, stream);
       return has_res ? launch_t<128, true>(p, plan.grid, stream) : launch_t<128, false>(p, plan.grid, stream);
     case 256:
+      if (plan.cluster == 2) return has_res ? launch_cluster2<256, true, true>(p, plan.grid, stream) : launch_cluster2<256, false, true>(p, plan.grid, stream);
       if (plan.cluster) return has_res ? launch_cluster2<256, true>(p, plan.grid, stream) : launch_cluster2<256, false>(p, plan.grid, stream);
       if (plan.m_tiles == 2) return has_res ? launch_t<256, true, false, 1, 2>(p, plan.grid, stream) : launch_t<256, false, false, 1, 2>(p, plan.grid, stream);
       if (plan.out_bufs == 2) return has_res ? launch_t<256, true, false, 2>(p, plan.grid, stream) : launch_t<256, false, false, 2>(p, plan.grid, stream);

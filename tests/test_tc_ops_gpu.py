@@ -7,6 +7,7 @@ from __future__ import annotations
 import pytest
 
 pytestmark = pytest.mark.gpu
+PAIR_DEFAULT = 1   # library default of opd_set_option("gemm_pair")
 
 
 @pytest.fixture(scope="module")
@@ -76,7 +77,7 @@ def test_gemm_weight_stationary_variant_is_bit_identical(T, M, N, K):
 
 @pytest.mark.parametrize("M,N,K,epi", [(128 * 7 + 9, 256, 256, 0), (128 * 40, 512, 1024, 1), (128 * 301 + 77, 2048, 256, 1),
                                        (128 * 33, 256, 2048, 2), (128 * 150 + 5, 256, 256, 3), (300, 256, 128, 0)])
-@pytest.mark.parametrize("option", [b"gemm_cluster", b"gemm_mpairs"])
+@pytest.mark.parametrize("option", [b"gemm_cluster", b"gemm_mpairs", b"gemm_pair"])
 def test_gemm_cluster_variant_is_bit_identical(T, M, N, K, epi, option):
     """(gemm_mpairs: the CTA works on pairs of m-blocks that share every weight tile.)  The 2-CTA cluster variant (each CTA loads half of every weight tile and multicasts it to both) against the
     single-CTA kernel: same accumulation order, so the outputs must be bit-identical - even and odd numbers of m-blocks,
@@ -92,22 +93,23 @@ def test_gemm_cluster_variant_is_bit_identical(T, M, N, K, epi, option):
     if epi == 3:
         kw.update(gamma=torch.randn(N, device="cuda"), beta=torch.randn(N, device="cuda"), pos=torch.randn(50, N, device="cuda"))
     try:
-        for o in (b"gemm_cluster", b"gemm_mpairs"):
+        for o in (b"gemm_cluster", b"gemm_mpairs", b"gemm_pair"):
             _lib.check(_lib.lib().opd_set_option(o, 0), "opd_set_option")
         ref = ops.gemm(a, w, **kw)
-        _lib.check(_lib.lib().opd_set_option(option, 2), "opd_set_option")
+        _lib.check(_lib.lib().opd_set_option(option, 3 if option == b"gemm_pair" else 2), "opd_set_option")
         got = ops.gemm(a, w, **kw)
         torch.cuda.synchronize()
     finally:
         _lib.lib().opd_set_option(b"gemm_cluster", 0)
         _lib.lib().opd_set_option(b"gemm_mpairs", 0)
+        _lib.lib().opd_set_option(b"gemm_pair", PAIR_DEFAULT)
     ref, got = (ref, got) if isinstance(ref, tuple) else ((ref,), (got,))
     for r, g in zip(ref, got):
         assert torch.equal(g.view(torch.int16), r.view(torch.int16))
 
 
 @pytest.mark.parametrize("B,H,W,C,N,k,stride", [(3, 40, 56, 256, 256, 3, 1), (2, 50, 84, 512, 256, 1, 2)])
-@pytest.mark.parametrize("option", [b"gemm_cluster", b"gemm_mpairs"])
+@pytest.mark.parametrize("option", [b"gemm_cluster", b"gemm_mpairs", b"gemm_pair"])
 def test_conv_cluster_variant_is_bit_identical(T, B, H, W, C, N, k, stride, option):
     from office_person_detection_vit_b200 import _lib
     from office_person_detection_vit_b200.detection import ops
@@ -116,15 +118,16 @@ def test_conv_cluster_variant_is_bit_identical(T, B, H, W, C, N, k, stride, opti
     x, w = _rand(torch, B, H, W, C, seed=31), _rand(torch, N, k, k, C, seed=32, scale=(k * k * C) ** -0.5)
     bias = torch.randn(N, device="cuda")
     try:
-        for o in (b"gemm_cluster", b"gemm_mpairs"):
+        for o in (b"gemm_cluster", b"gemm_mpairs", b"gemm_pair"):
             _lib.check(_lib.lib().opd_set_option(o, 0), "opd_set_option")
         ref = ops.conv2d_nhwc(x, w, bias, stride=stride, pad=k // 2, epilogue=1)
-        _lib.check(_lib.lib().opd_set_option(option, 2), "opd_set_option")
+        _lib.check(_lib.lib().opd_set_option(option, 3 if option == b"gemm_pair" else 2), "opd_set_option")
         got = ops.conv2d_nhwc(x, w, bias, stride=stride, pad=k // 2, epilogue=1)
         torch.cuda.synchronize()
     finally:
         _lib.lib().opd_set_option(b"gemm_cluster", 0)
         _lib.lib().opd_set_option(b"gemm_mpairs", 0)
+        _lib.lib().opd_set_option(b"gemm_pair", PAIR_DEFAULT)
     assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
 
 
