@@ -225,6 +225,25 @@ int opd_roi_features_bf16(const void* feat_dev, int32_t B, int32_t fh, int32_t f
                           const double* det_xywh_dev, const int32_t* n_keep_dev, int32_t Q, int32_t img_h,
                           int32_t img_w, float* out_dev, void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Piecewise-affine transform (the reference's shipped default, config.yaml:91)
+ * Replaces: src/transform/piecewise_affine.py:155-236 (transform_pixel / transform_detection / transform_batch).
+ * The table is built from what the reference builds on the host: scipy.spatial.Delaunay(src).transform [T,3,2]
+ * (barycentric transforms), the first two rows of every lstsq affine matrix [T,2,3] (piecewise_affine.py:102-125) and
+ * the triangle centroids [T,2] (:146-150); eps = 100 * DBL_EPSILON is scipy's find_simplex tolerance.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct opd_pwa_table opd_pwa_table;
+int opd_pwa_table_create(const double* bary, const double* affine, const double* centroids, int32_t T, double eps,
+                         int32_t device, opd_pwa_table** out);
+void opd_pwa_table_destroy(opd_pwa_table* t);
+/* in_dev [N,2] points or [N,4] (x, y, w, h) boxes (foot point x + w / 2, y + h), float64 -> floor_px_dev [N,2],
+ * optional floor_mm_dev [N,2], in_bounds_dev [N], tri_idx_dev [N] (triangle used), extrapolated_dev [N] (1: outside the
+ * triangulation, nearest-centroid triangle).  Enqueues one kernel on `stream`. */
+int opd_pwa_transform_f64(const opd_pwa_table* t, const double* in_dev, int32_t input_is_bbox, int64_t N,
+                          double scale_x_mm, double scale_y_mm, double map_w_px, double map_h_px,
+                          double* floor_px_dev, double* floor_mm_dev, uint8_t* in_bounds_dev, int32_t* tri_idx_dev,
+                          uint8_t* extrapolated_dev, void* stream);
+
 /* Measurement probe (benchmarks/mma_probe.py), not on the product path: `iters` tcgen05.mma 128 x N x 16 issued by one
  * thread per CTA, rotating over n_acc TMEM accumulators, operands with 32-byte (swizzle32 = 1) or 128-byte swizzled rows;
  * a_sbo / a_step != 0: A is a shifted view (8-row groups a_sbo bytes apart, consecutive MMAs a_step bytes apart);

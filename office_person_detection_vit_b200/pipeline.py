@@ -27,8 +27,16 @@ class DetectCountPipeline:
         if hist is None:
             hist = torch.zeros(slot_base + B, self.zones.get_zone_count() + 1, dtype=torch.int32, device=frames.device)
         pts = out["det_foot"].view(-1, 2)
-        hist, idx = self.zones.count(pts, slot=out["det_slot"].view(-1), num_slots=hist.shape[0],
-                                     transformer=self.transformer, out=hist, return_index=True)
+        if hasattr(self.transformer, "floor_params"):
+            # homography: projection, classification and counting are one fused kernel (csrc/floor.cu)
+            hist, idx = self.zones.count(pts, slot=out["det_slot"].view(-1), num_slots=hist.shape[0],
+                                         transformer=self.transformer, out=hist, return_index=True)
+        else:
+            # piecewise-affine (the reference's default transform.method): its own kernel (csrc/pwa.cu), then classification +
+            # counting on the floor points without a projection
+            out["floor_px"] = self.transformer.transform_points(pts)
+            hist, idx = self.zones.count(out["floor_px"], slot=out["det_slot"].view(-1), num_slots=hist.shape[0], transformer=None,
+                                         out=hist, return_index=True)
         out["hist"] = hist
         out["zone_idx"] = idx.view(B, -1)
         return out

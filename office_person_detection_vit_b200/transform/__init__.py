@@ -1,4 +1,5 @@
 from .floormap_config import FloorMapConfig
 from .homography import HomographyTransformer, TransformResult
+from .piecewise_affine import PiecewiseAffineTransformer, PWATransformResult
 
-__all__ = ["FloorMapConfig", "HomographyTransformer", "TransformResult"]
+__all__ = ["FloorMapConfig", "HomographyTransformer", "TransformResult", "PiecewiseAffineTransformer", "PWATransformResult"]

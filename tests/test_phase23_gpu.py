@@ -78,3 +78,40 @@ def test_object_flow_equals_tensor_flow(built_lib, tmp_path):
     agg.export_csv(str(tmp_path / "a.csv"), zone_ids)
     agg2.export_csv(str(tmp_path / "b.csv"), zone_ids)
     assert (tmp_path / "a.csv").read_text() == (tmp_path / "b.csv").read_text()
+
+
+def test_piecewise_affine_pipeline(built_lib):
+    """The reference's default transform.method on the tensor path: detector -> PiecewiseAffineTransformer -> zones -> counts,
+    against the object flow (transform_batch + classify + get_zone_counts on Detection records)."""
+    import torch
+
+    from office_person_detection_vit_b200.aggregation import Aggregator
+    from office_person_detection_vit_b200.detection import ViTDetector
+    from office_person_detection_vit_b200.pipeline import DetectCountPipeline
+    from office_person_detection_vit_b200.transform import FloorMapConfig, PiecewiseAffineTransformer
+    from office_person_detection_vit_b200.zone import ZoneClassifier
+
+    from .conftest import GOLDEN
+
+    g = np.load(GOLDEN / "pwa_golden.npz")
+    # correspondences scaled from the 1280x720 camera frame of the golden set to the 256x192 test frames
+    src = g["src"] * np.array([256 / 1280, 192 / 720])
+    tr = PiecewiseAffineTransformer(src, g["dst"], FloorMapConfig())
+    zones = fo.grid_zones(16)
+    zc = ZoneClassifier(zones, allow_overlap=False)
+    det = ViTDetector(confidence_threshold=0.3, state_dict=do.make_weights(0))
+    det.load_model()
+    det.model.set_resize(False)
+    frames = do.synthetic_frames(2, 192, 256, seed=9)
+    out = DetectCountPipeline(det, tr, zc).run_tensors(torch.from_numpy(frames).cuda())
+    torch.cuda.synchronize()
+    agg = Aggregator()
+    per_frame = det.detect_batch(list(frames))
+    assert out["n_keep"].cpu().tolist() == [len(d) for d in per_frame] and sum(len(d) for d in per_frame) > 10
+    counts = []
+    for dets in per_frame:
+        for d, res in zip(dets, tr.transform_batch([d.bbox for d in dets])):
+            d.zone_ids = zc.classify(res.floor_coords_px)
+        counts.append(agg.get_zone_counts(dets))
+    got = zc.counts_to_dicts(out["hist"])
+    assert [dict(sorted(c.items())) for c in got] == [dict(sorted(c.items())) for c in counts]

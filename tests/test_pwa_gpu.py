@@ -1,0 +1,91 @@
+"""GPU: PiecewiseAffineTransformer (csrc/pwa.cu through the C ABI) against the reference's own outputs
+(tests/golden/pwa_golden.npz) and the NumPy oracle: floor coordinates to 1e-9 px (float64 fma vs NumPy's dot), the
+extrapolation flag and bounds exactly, the triangle index exactly away from triangle edges; the reference's object surface
+(transform_pixel / transform_detection / transform_batch / get_info / save / load) and the tensor flow into the zone kernel."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import floor_oracle as fo
+from oracle import pwa_oracle as po
+
+from .conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return dict(np.load(GOLDEN / "pwa_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def transformer(golden, built_lib):
+    import torch
+
+    from office_person_detection_vit_b200.transform import FloorMapConfig, PiecewiseAffineTransformer
+
+    torch.cuda.init()
+    return PiecewiseAffineTransformer(golden["src"], golden["dst"], FloorMapConfig())
+
+
+def test_points_match_reference_and_oracle(golden, transformer):
+    import torch
+
+    pts = torch.from_numpy(golden["points"]).cuda()
+    px, mm, inb, tri, ext = (t.cpu().numpy() for t in transformer.transform_points(pts, with_mm=True, with_bounds=True, with_triangles=True))
+    np.testing.assert_allclose(px, golden["px"], rtol=0, atol=1e-7)             # on shared edges / vertices the maps agree to ~1e-9
+    np.testing.assert_allclose(mm, golden["mm"], rtol=0, atol=1e-5)
+    assert (ext.astype(bool) == golden["extrapolated"]).all()
+    assert (inb.astype(bool) == golden["within"]).all()
+    tb = po.build(golden["src"], golden["dst"])
+    o_px, _, _, o_tri, o_ext = po.transform_points(tb, golden["points"])
+    assert (tri == o_tri).all() and (ext.astype(bool) == o_ext).all()          # same restatement: identical decisions
+    far = po.edge_distance(tb, golden["points"]) > 1e-6
+    assert (tri[far] == golden["tri"][far]).all()                               # the reference's find_simplex away from edges
+    np.testing.assert_allclose(px[far], golden["px"][far], rtol=1e-12, atol=1e-9)
+
+
+def test_reference_surface(golden, transformer, tmp_path):
+    from office_person_detection_vit_b200.transform import FloorMapConfig, PiecewiseAffineTransformer
+
+    res = transformer.transform_batch([tuple(float(v) for v in b) for b in golden["boxes"]])
+    assert len(res) == len(golden["boxes"]) and all(r.is_valid for r in res)
+    np.testing.assert_allclose(np.array([r.floor_coords_px for r in res]), golden["box_px"], rtol=1e-12, atol=1e-9)
+    one = transformer.transform_detection(tuple(float(v) for v in golden["boxes"][3]))
+    assert one.floor_coords_px == pytest.approx(tuple(golden["box_px"][3]), abs=1e-9) and one.floor_coords_mm is not None
+    p = transformer.transform_pixel((float(golden["points"][0, 0]), float(golden["points"][0, 1])))
+    assert p.floor_coords_px == pytest.approx(tuple(golden["px"][0]), abs=1e-9) and p.triangle_index == int(golden["tri"][0])
+    assert transformer.transform_batch([]) == []
+    info = transformer.get_info()
+    assert info["method"] == "piecewise_affine" and info["num_triangles"] == int(golden["num_triangles"]) and info["num_points"] == 24
+    assert info["training_error"]["rmse"] < 1e-6 and info["training_error"]["num_points"] == 24
+    transformer.save(tmp_path / "pwa.pkl")
+    again = PiecewiseAffineTransformer.load(tmp_path / "pwa.pkl", FloorMapConfig())
+    assert again.transform_pixel((640.0, 360.0)).floor_coords_px == transformer.transform_pixel((640.0, 360.0)).floor_coords_px
+    with pytest.raises(ValueError, match="最低3点"):
+        PiecewiseAffineTransformer(golden["src"][:2], golden["dst"][:2])
+    with pytest.raises(ValueError, match="一致しません"):
+        PiecewiseAffineTransformer(golden["src"], golden["dst"][:5])
+
+
+def test_pwa_points_feed_the_zone_kernel(golden, transformer):
+    """PWA variant of Phase 3 on tensors: transform_points -> ZoneClassifier.count (no projection) == oracle counts."""
+    import torch
+
+    from office_person_detection_vit_b200.zone import ZoneClassifier
+
+    zones = fo.grid_zones(16)
+    zc = ZoneClassifier(zones, allow_overlap=False)
+    rng = np.random.default_rng(5)
+    pts = rng.uniform([0, 0], [1280, 720], (20000, 2))
+    px = transformer.transform_points(torch.from_numpy(pts).cuda())
+    hist, idx = zc.count(px, return_index=True)
+    tb = po.build(golden["src"], golden["dst"])
+    o_px, *_ = po.transform_points(tb, pts[:2000])
+    np.testing.assert_allclose(px[:2000].cpu().numpy(), o_px, rtol=1e-12, atol=1e-9)
+    o_idx, _ = fo.classify(px.cpu().numpy(), zones)
+    assert (idx.cpu().numpy() == o_idx).all()
+    assert (hist.cpu().numpy()[0] == fo.count(zone_idx=o_idx, Z=16)[0]).all()
