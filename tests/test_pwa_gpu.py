@@ -89,3 +89,25 @@ def test_pwa_points_feed_the_zone_kernel(golden, transformer):
     o_idx, _ = fo.classify(px.cpu().numpy(), zones)
     assert (idx.cpu().numpy() == o_idx).all()
     assert (hist.cpu().numpy()[0] == fo.count(zone_idx=o_idx, Z=16)[0]).all()
+
+
+def test_lookup_grid_equals_full_search(golden, transformer):
+    """The cell lookup (strictly-inside cells, outside cells with a unique nearest centroid) must reproduce the full search
+    bit for bit: floor coordinates, triangle index and extrapolation flag, inside, around and far outside the grid."""
+    import torch
+
+    from office_person_detection_vit_b200 import _lib
+
+    rng = np.random.default_rng(23)
+    pts = np.concatenate([rng.uniform([-700, -500], [2000, 1300], (150000, 2)), rng.uniform([-1e5, -1e5], [1e5, 1e5], (2000, 2)),
+                          golden["src"], np.array([[np.nan, 1.0], [np.inf, -np.inf], [0.0, 0.0]])])
+    t = torch.from_numpy(pts).cuda()
+    a = transformer.transform_points(t, with_triangles=True)
+    try:
+        _lib.check(_lib.lib().opd_set_option(b"probe", 64), "opd_set_option")
+        b = transformer.transform_points(t, with_triangles=True)
+    finally:
+        _lib.lib().opd_set_option(b"probe", 0)
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x.view(torch.int64) if x.dtype == torch.float64 else x, y.view(torch.int64) if y.dtype == torch.float64 else y)
