@@ -41,6 +41,58 @@ class DetectCountPipeline:
         out["zone_idx"] = idx.view(B, -1)
         return out
 
+    def run_stream(self, batches, hist=None, slot_base: int = 0, threshold: float | None = None, bgr: bool = True):
+        """Frame ingest (the reference hands Phase 2 a Python list of cv2 frames one by one,
+        src/pipeline/orchestrator.py:155-202, src/pipeline/phases/detection.py:91-94): `batches` yields host batches - uint8
+        [B,H,W,3] NumPy arrays or torch tensors of one size - and this generator yields `run_tensors` results, with batch i+1
+        staged into pinned memory and copied to the device on a second stream while batch i runs (two pinned and two device
+        buffers).  Batch i's timestamp rows are slot_base + i * B ..; `hist` (if given) must hold every batch's rows."""
+        torch = _lib.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream()
+        pinned, device_bufs = [None, None], [None, None]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        for c in consumed:
+            c.record(main)
+
+        def stage(i, batch):
+            t = torch.as_tensor(batch)
+            if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3:
+                raise ValueError(f"batch {i}: expected uint8 [B,H,W,3], got {t.dtype} {tuple(t.shape)}")
+            k = i % 2
+            if device_bufs[k] is None or device_bufs[k].shape != t.shape:
+                device_bufs[k] = torch.empty(t.shape, dtype=torch.uint8, device=dev)
+            consumed[k].synchronize()          # batch i - 2 has been consumed: device_bufs[k] (and pinned[k]) may be overwritten
+            if t.is_pinned():
+                src = t                        # the producer already writes pinned memory (bench.py): no staging copy
+            else:
+                if pinned[k] is None or pinned[k].shape != t.shape:
+                    pinned[k] = torch.empty(t.shape, dtype=torch.uint8).pin_memory()
+                pinned[k].copy_(t)
+                src = pinned[k]
+            with torch.cuda.stream(copy_stream):
+                device_bufs[k].copy_(src, non_blocking=True)
+                ready[k].record(copy_stream)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        i = 0
+        if nxt is not None:
+            stage(0, nxt)
+        while nxt is not None:
+            cur_k = i % 2
+            nxt = next(it, None)
+            if nxt is not None:
+                stage(i + 1, nxt)
+            main.wait_event(ready[cur_k])
+            B = device_bufs[cur_k].shape[0]
+            out = self.run_tensors(device_bufs[cur_k], hist=hist, slot_base=slot_base + i * B, threshold=threshold, bgr=bgr)
+            consumed[cur_k].record(main)
+            yield out
+            i += 1
+
     def all_reduce(self, hist):
         """Sum the per-timestamp histograms over all ranks (the path's only collective)."""
         import torch.distributed as dist

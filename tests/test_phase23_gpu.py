@@ -115,3 +115,29 @@ def test_piecewise_affine_pipeline(built_lib):
         counts.append(agg.get_zone_counts(dets))
     got = zc.counts_to_dicts(out["hist"])
     assert [dict(sorted(c.items())) for c in got] == [dict(sorted(c.items())) for c in counts]
+
+
+def test_run_stream_equals_run_tensors(built_lib):
+    """Double-buffered ingest (pinned staging + copy stream) yields exactly what run_tensors yields on the same batches, in
+    order, with each batch's counts in its own timestamp rows."""
+    import torch
+
+    from office_person_detection_vit_b200.detection import ViTDetector
+    from office_person_detection_vit_b200.pipeline import DetectCountPipeline
+    from office_person_detection_vit_b200.transform import FloorMapConfig, HomographyTransformer
+    from office_person_detection_vit_b200.zone import ZoneClassifier
+
+    det = ViTDetector(confidence_threshold=0.3, state_dict=do.make_weights(0))
+    det.load_model()
+    det.model.set_resize(False)
+    pipe = DetectCountPipeline(det, HomographyTransformer(fo.H_CONFIG, FloorMapConfig()), ZoneClassifier(fo.grid_zones(16), allow_overlap=False))
+    batches = [do.synthetic_frames(2, 160, 224, seed=40 + i) for i in range(5)]
+    hist = torch.zeros(10, 17, dtype=torch.int32, device="cuda")
+    got = [(o["n_keep"].clone(), o["det_xywh"].clone(), o["zone_idx"].clone()) for o in pipe.run_stream(iter(batches), hist=hist)]
+    torch.cuda.synchronize()
+    assert len(got) == 5
+    ref_hist = torch.zeros(10, 17, dtype=torch.int32, device="cuda")
+    for i, b in enumerate(batches):
+        o = pipe.run_tensors(torch.from_numpy(b).cuda(), hist=ref_hist, slot_base=2 * i)
+        assert torch.equal(got[i][0], o["n_keep"]) and torch.equal(got[i][1], o["det_xywh"]) and torch.equal(got[i][2], o["zone_idx"])
+    assert torch.equal(hist, ref_hist) and int(hist.sum()) == int(sum(int(g[0].sum()) for g in got))
