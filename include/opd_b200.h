@@ -244,6 +244,17 @@ int opd_pwa_transform_f64(const opd_pwa_table* t, const double* in_dev, int32_t 
                           double* floor_px_dev, double* floor_mm_dev, uint8_t* in_bounds_dev, int32_t* tri_idx_dev,
                           uint8_t* extrapolated_dev, void* stream);
 
+/* Thin-plate-spline transform (src/transform/piecewise_affine.py:398-545): control points src_points [n,2], the solved
+ * weights_x / weights_y [n] and affine_x / affine_y [3] (order: constant, x, y) as the reference computes them (:445-485).
+ * Same point / box inputs and optional outputs as opd_pwa_transform_f64 (no triangle outputs). */
+typedef struct opd_tps_table opd_tps_table;
+int opd_tps_table_create(const double* src_points, const double* weights_x, const double* weights_y, const double* affine_x,
+                         const double* affine_y, int32_t n, int32_t device, opd_tps_table** out);
+void opd_tps_table_destroy(opd_tps_table* t);
+int opd_tps_transform_f64(const opd_tps_table* t, const double* in_dev, int32_t input_is_bbox, int64_t N, double scale_x_mm,
+                          double scale_y_mm, double map_w_px, double map_h_px, double* floor_px_dev, double* floor_mm_dev,
+                          uint8_t* in_bounds_dev, void* stream);
+
 /* Measurement probe (benchmarks/mma_probe.py), not on the product path: `iters` tcgen05.mma 128 x N x 16 issued by one
  * thread per CTA, rotating over n_acc TMEM accumulators, operands with 32-byte (swizzle32 = 1) or 128-byte swizzled rows;
  * a_sbo / a_step != 0: A is a shifted view (8-row groups a_sbo bytes apart, consecutive MMAs a_step bytes apart);

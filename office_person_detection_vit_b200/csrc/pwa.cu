@@ -308,3 +308,125 @@ extern "C" int opd_pwa_transform_f64(const opd_pwa_table* t, const double* in_de
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Thin-plate-spline transform (src/transform/piecewise_affine.py:398-545): f(p) = a0 + a1 x + a2 y + sum_i w_i U(|p - c_i|),
+// U(r) = r^2 log r (0 at r = 0), one such function per output coordinate; the coefficients are solved on the host exactly as
+// the reference solves them (:445-485).  The sum runs in the reference's order (i = 0 .. n-1, product rounded, then added:
+// Python floats) with explicit float64 roundings; only log() may differ from NumPy's by an ulp.
+// ------------------------------------------------------------------------------------------------------------
+struct opd_tps_table {
+  int device = 0;
+  int n = 0;
+  double* d_ctrl = nullptr;   // [n][4]: cx cy wx wy
+  double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0};
+};
+
+namespace {
+
+struct TpsK {
+  const double* ctrl;
+  int n;
+  double ax0, ax1, ax2, ay0, ay1, ay2;
+  const double* in;
+  int input_is_bbox;
+  long long N;
+  double sx, sy, mw, mh;
+  double* floor_px;
+  double* floor_mm;
+  uint8_t* in_bounds;
+};
+
+__global__ void __launch_bounds__(256) tps_transform_kernel(const TpsK p) {
+  extern __shared__ __align__(16) double s_ctrl[];
+  for (int i = threadIdx.x; i < p.n * 4; i += blockDim.x) s_ctrl[i] = p.ctrl[i];
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.N; i += stride) {
+    double x, y;
+    if (p.input_is_bbox) {
+      x = __dadd_rn(p.in[4 * i + 0], __ddiv_rn(p.in[4 * i + 2], 2.0));   // :531-533 foot point
+      y = __dadd_rn(p.in[4 * i + 1], p.in[4 * i + 3]);
+    } else {
+      x = p.in[2 * i + 0];
+      y = p.in[2 * i + 1];
+    }
+    double rx = 0.0, ry = 0.0;
+    for (int k = 0; k < p.n; ++k) {
+      const double* c = s_ctrl + 4 * k;
+      const double dx = __dsub_rn(x, c[0]), dy = __dsub_rn(y, c[1]);
+      const double r = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));   // np.linalg.norm of a 2-vector
+      const double u = r > 0.0 ? __dmul_rn(__dmul_rn(r, r), log(r)) : 0.0;            // _radial_basis (:437-443)
+      rx = __dadd_rn(rx, __dmul_rn(c[2], u));
+      ry = __dadd_rn(ry, __dmul_rn(c[3], u));
+    }
+    const double fx = __dadd_rn(__dadd_rn(__dadd_rn(p.ax0, __dmul_rn(p.ax1, x)), __dmul_rn(p.ax2, y)), rx);   // :504-505, left to right
+    const double fy = __dadd_rn(__dadd_rn(__dadd_rn(p.ay0, __dmul_rn(p.ay1, x)), __dmul_rn(p.ay2, y)), ry);
+    if (p.floor_px) {
+      p.floor_px[2 * i + 0] = fx;
+      p.floor_px[2 * i + 1] = fy;
+    }
+    if (p.floor_mm) {
+      p.floor_mm[2 * i + 0] = __dmul_rn(fx, p.sx);
+      p.floor_mm[2 * i + 1] = __dmul_rn(fy, p.sy);
+    }
+    if (p.in_bounds) p.in_bounds[i] = (0.0 <= fx && fx < p.mw && 0.0 <= fy && fy < p.mh) ? 1 : 0;
+  }
+}
+
+}  // namespace
+
+extern "C" int opd_tps_table_create(const double* src_points /*[n,2]*/, const double* weights_x, const double* weights_y,
+                                    const double* affine_x /*[3]*/, const double* affine_y /*[3]*/, int32_t n, int32_t device,
+                                    opd_tps_table** out) {
+  OPD_REQUIRE(src_points && weights_x && weights_y && affine_x && affine_y && out && n > 0 && n <= 4096,
+              "opd_tps_table_create: bad argument (n=%d, at most 4096 control points)", n);
+  OPD_CUDA_OK(cudaSetDevice(device));
+  std::vector<double> h((size_t)n * 4);
+  for (int i = 0; i < n; ++i) {
+    h[4 * i + 0] = src_points[2 * i];
+    h[4 * i + 1] = src_points[2 * i + 1];
+    h[4 * i + 2] = weights_x[i];
+    h[4 * i + 3] = weights_y[i];
+  }
+  opd_tps_table* tb = new opd_tps_table();
+  tb->device = device;
+  tb->n = n;
+  for (int j = 0; j < 3; ++j) {
+    tb->ax[j] = affine_x[j];
+    tb->ay[j] = affine_y[j];
+  }
+  if (cudaMalloc(&tb->d_ctrl, h.size() * sizeof(double)) != cudaSuccess) {
+    delete tb;
+    return opd::fail(OPD_ERR_CUDA, "opd_tps_table_create: cudaMalloc failed");
+  }
+  OPD_CUDA_OK(cudaMemcpy(tb->d_ctrl, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  *out = tb;
+  return OPD_OK;
+}
+
+extern "C" void opd_tps_table_destroy(opd_tps_table* t) {
+  if (!t) return;
+  cudaFree(t->d_ctrl);
+  delete t;
+}
+
+extern "C" int opd_tps_transform_f64(const opd_tps_table* t, const double* in_dev, int32_t input_is_bbox, int64_t N, double scale_x_mm,
+                                     double scale_y_mm, double map_w_px, double map_h_px, double* floor_px_dev, double* floor_mm_dev,
+                                     uint8_t* in_bounds_dev, void* stream) {
+  OPD_REQUIRE(t && N >= 0 && (N == 0 || in_dev), "opd_tps_transform_f64: bad argument");
+  if (N == 0) return OPD_OK;
+  TpsK k{t->d_ctrl, t->n, t->ax[0], t->ax[1], t->ax[2], t->ay[0], t->ay[1], t->ay[2], in_dev, input_is_bbox, (long long)N,
+         scale_x_mm, scale_y_mm, map_w_px, map_h_px, floor_px_dev, floor_mm_dev, in_bounds_dev};
+  const size_t smem = (size_t)t->n * 4 * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    OPD_CUDA_OK(cudaFuncSetAttribute(tps_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 4 * 8));
+    configured = true;
+  }
+  const long long blocks = std::min<long long>((N + 255) / 256, 148LL * 8);
+  tps_transform_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(k);
+  opd::count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}

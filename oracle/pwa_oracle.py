@@ -77,3 +77,43 @@ def edge_distance(tb: dict, pts) -> np.ndarray:
             t = np.clip((w @ v) / (v @ v), 0.0, 1.0)
             d = np.minimum(d, np.linalg.norm(w - t[:, None] * v, axis=1))
     return d
+
+
+# ---- thin-plate spline (src/transform/piecewise_affine.py:398-545) -------------------------------------------------------
+def tps_build(src_points, dst_points, regularization: float = 0.0) -> dict:
+    """:445-485: kernel matrix of U(r) = r^2 log r, [K + lambda I, P; P^T, 0] solved once per output coordinate."""
+    src = np.array(src_points, dtype=np.float64)
+    dst = np.array(dst_points, dtype=np.float64)
+    n = len(src)
+    K = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            if i != j:
+                r = np.linalg.norm(src[i] - src[j])
+                K[i, j] = r ** 2 * np.log(r) if r > 0 else 0.0
+    P = np.hstack([np.ones((n, 1)), src])
+    L = np.zeros((n + 3, n + 3))
+    L[:n, :n] = K + regularization * np.eye(n)
+    L[:n, n:] = P
+    L[n:, :n] = P.T
+    vx, vy = np.zeros(n + 3), np.zeros(n + 3)
+    vx[:n], vy[:n] = dst[:, 0], dst[:, 1]
+    cx, cy = np.linalg.solve(L, vx), np.linalg.solve(L, vy)
+    return {"src": src, "wx": cx[:n], "wy": cy[:n], "ax": cx[n:], "ay": cy[n:]}
+
+
+def tps_transform_points(tb: dict, pts, is_bbox: bool = False) -> np.ndarray:
+    """:487-527: the radial-basis sum in index order with Python floats, then the affine part left to right."""
+    pts = np.asarray(pts, dtype=np.float64)
+    out = np.zeros((len(pts), 2))
+    for k, row in enumerate(pts):
+        x, y = (row[0] + row[2] / 2, row[1] + row[3]) if is_bbox else (row[0], row[1])
+        rx = ry = 0.0
+        for i, c in enumerate(tb["src"]):
+            r = float(np.linalg.norm(np.array([x, y]) - c))
+            u = r ** 2 * float(np.log(r)) if r > 0 else 0.0
+            rx += float(tb["wx"][i]) * u
+            ry += float(tb["wy"][i]) * u
+        out[k] = (float(tb["ax"][0]) + float(tb["ax"][1]) * x + float(tb["ax"][2]) * y + rx,
+                  float(tb["ay"][0]) + float(tb["ay"][1]) * x + float(tb["ay"][2]) * y + ry)
+    return out

@@ -10,7 +10,7 @@ import numpy as np
 
 sys.path.insert(0, "/root/reference")
 from src.transform.floormap_config import FloorMapConfig  # noqa: E402
-from src.transform.piecewise_affine import PiecewiseAffineTransformer  # noqa: E402
+from src.transform.piecewise_affine import PiecewiseAffineTransformer, ThinPlateSplineTransformer  # noqa: E402
 
 
 def main():
@@ -27,12 +27,17 @@ def main():
     boxes = np.concatenate([rng.uniform([0, 0], [1200, 600], (60, 2)), rng.uniform([10, 20], [200, 300], (60, 2))], axis=1)
     bres = tr.transform_batch([tuple(float(v) for v in b) for b in boxes])
     info = tr.get_info()
+    tps = ThinPlateSplineTransformer(src, dst, fm)
+    tres = [tps.transform_pixel((float(p[0]), float(p[1]))) for p in pts[:200]]
+    tbres = tps.transform_batch([tuple(float(v) for v in b) for b in boxes[:40]])
     np.savez_compressed(
         Path(__file__).resolve().parent / "pwa_golden.npz", src=src, dst=dst, points=pts,
         px=np.array([r.floor_coords_px for r in res]), mm=np.array([r.floor_coords_mm for r in res]),
         within=np.array([r.is_within_bounds for r in res]), tri=np.array([r.triangle_index for r in res]),
         extrapolated=np.array([r.is_extrapolated for r in res]), boxes=boxes,
         box_px=np.array([r.floor_coords_px for r in bres]), box_tri=np.array([r.triangle_index for r in bres]),
+        tps_px=np.array([r.floor_coords_px for r in tres]), tps_within=np.array([r.is_within_bounds for r in tres]),
+        tps_box_px=np.array([r.floor_coords_px for r in tbres]), tps_rmse=np.array(tps.get_info()["training_error"]["rmse"]),
         num_triangles=np.array(info["num_triangles"]), rmse=np.array(info["training_error"]["rmse"]))
     print(len(pts), "points,", int(np.sum([r.is_extrapolated for r in res])), "extrapolated,", info["num_triangles"], "triangles, rmse",
           info["training_error"]["rmse"])

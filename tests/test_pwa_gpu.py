@@ -111,3 +111,25 @@ def test_lookup_grid_equals_full_search(golden, transformer):
     torch.cuda.synchronize()
     for x, y in zip(a, b):
         assert torch.equal(x.view(torch.int64) if x.dtype == torch.float64 else x, y.view(torch.int64) if y.dtype == torch.float64 else y)
+
+
+def test_thin_plate_spline(golden, built_lib):
+    """ThinPlateSplineTransformer (tps_transform_kernel) against the reference's own outputs: same coefficients (host solve as
+    in the reference), same summation order, float64; CUDA's log() may differ from NumPy's by an ulp per term, which the
+    24-term sum of magnitudes ~1e6 turns into <= 1e-8 px."""
+    import torch
+
+    from office_person_detection_vit_b200.transform import FloorMapConfig, ThinPlateSplineTransformer
+
+    tps = ThinPlateSplineTransformer(golden["src"], golden["dst"], FloorMapConfig())
+    px, mm, inb = (t.cpu().numpy() for t in tps.transform_points(torch.from_numpy(golden["points"][:200]).cuda(), with_mm=True, with_bounds=True))
+    np.testing.assert_allclose(px, golden["tps_px"], rtol=0, atol=1e-8)
+    assert (inb.astype(bool) == golden["tps_within"]).all()
+    np.testing.assert_allclose(mm, px * np.array([28.1926406926406, 28.241430700447]), rtol=1e-15)
+    res = tps.transform_batch([tuple(float(v) for v in b) for b in golden["boxes"][:40]])
+    np.testing.assert_allclose(np.array([r.floor_coords_px for r in res]), golden["tps_box_px"], rtol=0, atol=1e-8)
+    info = tps.get_info()
+    assert info["method"] == "thin_plate_spline" and info["num_points"] == 24 and info["training_error"]["rmse"] < 1e-6
+    assert tps.transform_batch([]) == []
+    with pytest.raises(ValueError, match="最低3点"):
+        ThinPlateSplineTransformer(golden["src"][:2], golden["dst"][:2])

@@ -41,3 +41,11 @@ def test_training_points_map_onto_their_targets(golden):
     tb = po.build(golden["src"], golden["dst"])
     px, *_ = po.transform_points(tb, golden["src"])
     np.testing.assert_allclose(px, golden["dst"], atol=1e-7)   # piecewise_affine.py docstring: RMSE 0 on the training data
+
+
+def test_tps_oracle_matches_reference(golden):
+    """oracle.tps_* == the reference's ThinPlateSplineTransformer (bit for bit: same solves, same summation order)."""
+    tb = po.tps_build(golden["src"], golden["dst"])
+    np.testing.assert_array_equal(po.tps_transform_points(tb, golden["points"][:200]), golden["tps_px"])
+    np.testing.assert_array_equal(po.tps_transform_points(tb, golden["boxes"][:40], is_bbox=True), golden["tps_box_px"])
+    np.testing.assert_allclose(po.tps_transform_points(tb, golden["src"]), golden["dst"], atol=1e-7)   # exact interpolation
