@@ -209,12 +209,7 @@ def main_gpu(args) -> None:
     graph = None
     if not args.no_graph:
         try:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                hist.zero_()
-                out = pipe.run_tensors(frames, hist=hist, slot_base=rank * B)
-            graph = g
+            graph = pipe.capture(frames, hist=hist, slot_base=rank * B, zero_hist=True)   # the library's own capture API
         except Exception as e:   # capture is an optimisation, never a requirement
             print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {e}); timing plain launches", file=sys.stderr)
             graph = None
@@ -223,9 +218,9 @@ def main_gpu(args) -> None:
     def timed_step():
         if graph is None:
             return step(frames)
-        graph.replay()
+        o = graph()
         pipe.all_reduce(hist)
-        return out
+        return o
 
     for _ in range(2):
         timed_step()
@@ -262,6 +257,22 @@ def main_gpu(args) -> None:
             dev_bufs[i % 2].copy_(host, non_blocking=True)
             ready[i % 2].record(copy_stream)
 
+    e2e_graphs = [None, None]
+    if graph is not None:
+        try:
+            e2e_graphs = [pipe.capture(dev_bufs[k], hist=hist, slot_base=rank * B, zero_hist=True) for k in range(2)]
+        except Exception as e:
+            print(f"bench.py: CUDA graph capture (e2e) failed ({type(e).__name__}: {e}); plain launches", file=sys.stderr)
+            e2e_graphs = [None, None]
+            torch.cuda.synchronize()
+
+    def e2e_step(k):
+        if e2e_graphs[k] is None:
+            return step(dev_bufs[k])
+        o = e2e_graphs[k]()
+        pipe.all_reduce(hist)
+        return o
+
     def e2e_run(n):
         nonlocal results
         results = []
@@ -272,7 +283,7 @@ def main_gpu(args) -> None:
             if i + 1 < n:
                 upload(i + 1)
             torch.cuda.current_stream().wait_event(ready[i % 2])
-            o = step(dev_bufs[i % 2])
+            o = e2e_step(i % 2)
             consumed[i % 2].record()
             # the step's result: per-frame zone counts + detection count (reference: FrameResult.zone_counts)
             results.append((hist[rank * B:(rank + 1) * B].to("cpu", non_blocking=True), o["n_keep"].to("cpu", non_blocking=True)))

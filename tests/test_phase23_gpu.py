@@ -141,3 +141,31 @@ def test_run_stream_equals_run_tensors(built_lib):
         o = pipe.run_tensors(torch.from_numpy(b).cuda(), hist=ref_hist, slot_base=2 * i)
         assert torch.equal(got[i][0], o["n_keep"]) and torch.equal(got[i][1], o["det_xywh"]) and torch.equal(got[i][2], o["zone_idx"])
     assert torch.equal(hist, ref_hist) and int(hist.sum()) == int(sum(int(g[0].sum()) for g in got))
+
+
+def test_captured_step_equals_run_tensors(built_lib):
+    """DetectCountPipeline.capture: replaying the CUDA graph on refilled input buffers gives what run_tensors gives."""
+    import torch
+
+    from office_person_detection_vit_b200.detection import ViTDetector
+    from office_person_detection_vit_b200.pipeline import DetectCountPipeline
+    from office_person_detection_vit_b200.transform import FloorMapConfig, HomographyTransformer
+    from office_person_detection_vit_b200.zone import ZoneClassifier
+
+    det = ViTDetector(confidence_threshold=0.3, state_dict=do.make_weights(0))
+    det.load_model()
+    det.model.set_resize(False)
+    pipe = DetectCountPipeline(det, HomographyTransformer(fo.H_CONFIG, FloorMapConfig()), ZoneClassifier(fo.grid_zones(16), allow_overlap=False))
+    buf = torch.from_numpy(do.synthetic_frames(2, 160, 224, seed=50)).cuda()
+    hist = torch.zeros(2, 17, dtype=torch.int32, device="cuda")
+    replay = pipe.capture(buf, hist=hist, zero_hist=True)
+    for seed in (51, 52, 53):
+        frames = torch.from_numpy(do.synthetic_frames(2, 160, 224, seed=seed)).cuda()
+        buf.copy_(frames)
+        out = replay()
+        got = (out["n_keep"].clone(), out["det_xywh"].clone(), out["zone_idx"].clone(), hist.clone())
+        ref_hist = torch.zeros(2, 17, dtype=torch.int32, device="cuda")
+        ref = pipe.run_tensors(frames, hist=ref_hist)
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], ref["n_keep"]) and torch.equal(got[1], ref["det_xywh"]) and torch.equal(got[2], ref["zone_idx"])
+        assert torch.equal(got[3], ref_hist) and int(ref_hist.sum()) > 0
