@@ -11,7 +11,8 @@
 //   E1(t): A2 = bf16(relu(acc1 + b2))                               TMEM -> regs -> 128B-swizzled smem (K-major operand)
 //   G2(t): acc2[128 x 128] = A2[128 x MID] * W3[n2]^T  per n2 tile  B2 tiles through the same ring
 //   E2(t): y = bf16(relu(acc2 + b3 + residual))                     residual by TMA ring, output by TMA store
-// Warp roles: 0 TMA producer, 1 MMA issuer + TMEM owner, 2 residual producer, 4-11 epilogue (two warpgroups that
+// Warp roles: 0-7 epilogue (two warpgroups), 8 TMA producer, 9 MMA issuer + TMEM owner, 10 residual producer, 11 W3 tile
+// producer; the single-thread roles are elected with elect.sync (the epilogue warpgroups
 // split the columns: the epilogue, not the tensor pipe, paces these HBM-bound layers).
 // MMA issue order G1(t0) G1(t1) G2(t0) G1(t2) G2(t1) ... so that E1 / E2 of one tile overlap the MMAs of the next.
 #include <algorithm>
@@ -28,7 +29,7 @@ constexpr int BLOCK_K = 64;
 constexpr int BLOCK_N2 = 128;
 constexpr int UMMA_K = 16;
 constexpr int CHUNK_BYTES = BLOCK_M * 64 * 2;        // one [128 x 64] bf16 box = 16 KB
-constexpr int kThreads = 384;   // warps: 0 TMA, 1 MMA, 2 residual TMA, 3 idle, 4-11 epilogue (two warpgroups)
+constexpr int kThreads = 384;   // warps: 0-7 epilogue (two warpgroups), 8 TMA, 9 MMA, 10 residual TMA, 11 W3 TMA
 constexpr int kSmemBudget = 232448;
 
 template <int MID>

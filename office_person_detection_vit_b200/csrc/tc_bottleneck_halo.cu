@@ -9,8 +9,9 @@
 // the L2 -> SM weight traffic that paced the one-tile version (profiles/README.md).
 // Output, residual and shortcut-input tiles are 16 x 8 pixel patches moved by 4D TMA boxes [64 ch, 8, 16, 1].
 //
-// Warps: 0 TMA producer (patch + W2 / W3 tiles), 1 MMA issuer + TMEM owner, 2 residual (or shortcut-input) producer,
-//        4-11 epilogue: two warpgroups; E1: warpgroup g converts half tile g; E2: warpgroup g owns 64-column chunk g.
+// Warps: 0-7 epilogue (two warpgroups; E1: warpgroup g converts half tile g; E2: warpgroup g owns 64-column chunk g),
+//        8 TMA producer (patch + W2 / W3 tiles), 9 MMA issuer + TMEM owner, 10 residual (or shortcut-input) producer;
+//        the single-thread roles are elected with elect.sync.
 #include <algorithm>
 
 #include "opd_common.h"
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       }
     }
   } else if (warp < 8) {
-    // ============================ epilogue: two warpgroups (warps 4-7, 8-11) ============================
+    // ============================ epilogue: two warpgroups (warps 0-3, 4-7) ============================
     const int wg = warp >> 2;
     const int et = threadIdx.x - wg * 128;
     const int quarter = warp & 3;

@@ -6,11 +6,17 @@
 //   ResNet-50 bottleneck convolutions + frozen BN (+ReLU, +residual), input_projection, every Linear of the
 //   encoder / decoder layers, the post-attention and post-FFN residual + LayerNorm.
 //
-// Kernel shape: persistent, one CTA per SM, 6 warps:
-//   warp 0   TMA producer (one lane)         global -> smem ring (kStages x [A 128x64 | B BLOCK_Nx64], 128B swizzle)
-//   warp 1   MMA issuer (one lane) + TMEM owner   4 x tcgen05.mma (128 x BLOCK_N x 16) per ring slot
-//   warps 2-5 epilogue: tcgen05.ld -> fp32 math -> bf16 -> swizzled smem staging -> TMA store (64-column boxes)
+// Kernel shape: persistent, one CTA per SM, 12 warps (384 threads):
+//   warps 0-7  epilogue, two warpgroups that split the 64-column chunks of a tile: tcgen05.ld -> fp32 math -> bf16 ->
+//              swizzled smem staging -> TMA store (64-column boxes)
+//   warp 8     TMA producer (one elected lane): global -> smem ring (kStages x [A 128x64 | B BLOCK_Nx64], 128B swizzle)
+//   warp 9     MMA issuer (one elected lane) + TMEM owner: 4 x tcgen05.mma (128 x BLOCK_N x 16) per ring slot
+//   warp 10    residual TMA producer (kHasRes kernels)
 // TMEM holds two accumulator stages (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Variants (template parameters; every one is bit-identical to the plain kernel, tests/test_tc_ops_gpu.py):
+//   kPair      cta_group::2: two CTAs = one 256-row MMA, half a weight tile per SM (default for BLOCK_N = 256 layers)
+//   kBRes      weight-stationary (short-K bottleneck outputs);   kOutBufs = 2  double-buffered staging (short-K layers)
+//   kCluster=2 without kPair (multicast weight tiles) and kMTiles = 2 (m-block pairs per CTA): measured, off by default
 #include "tc_gemm.h"
 
 #include <algorithm>
