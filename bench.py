@@ -172,6 +172,8 @@ def main_gpu(args) -> None:
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU path)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set on the box: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
