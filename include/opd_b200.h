@@ -255,6 +255,11 @@ int opd_tps_transform_f64(const opd_tps_table* t, const double* in_dev, int32_t 
                           double scale_y_mm, double map_w_px, double map_h_px, double* floor_px_dev, double* floor_mm_dev,
                           uint8_t* in_bounds_dev, void* stream);
 
+/* Lens-distortion correction of points (src/calibration/lens_distortion.py:156-203: cv2.undistortPoints(pts, K, dist, P = K)):
+ * in_dev [N,2] points (or [N,4] boxes: foot point) float64 -> out_dev [N,2] corrected pixel coordinates. */
+int opd_undistort_points_f64(double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2, double k3,
+                             const double* in_dev, int32_t input_is_bbox, int64_t N, double* out_dev, void* stream);
+
 /* Measurement probe (benchmarks/mma_probe.py), not on the product path: `iters` tcgen05.mma 128 x N x 16 issued by one
  * thread per CTA, rotating over n_acc TMEM accumulators, operands with 32-byte (swizzle32 = 1) or 128-byte swizzled rows;
  * a_sbo / a_step != 0: A is a shifted view (8-row groups a_sbo bytes apart, consecutive MMAs a_step bytes apart);

@@ -7,6 +7,8 @@ The public classes keep the reference's engine surfaces:
     detection.ViTDetector                 <- src/detection (ViTDetector / YOLOv8Detector surface)
     transform.HomographyTransformer       <- src/transform/homography.py
     transform.FloorMapConfig              <- src/transform/floormap_config.py
+    transform.PiecewiseAffineTransformer / ThinPlateSplineTransformer <- src/transform/piecewise_affine.py
+    calibration.LensDistortionCorrector   <- src/calibration/lens_distortion.py (points only)
     zone.ZoneClassifier                   <- src/zone/zone_classifier.py
     aggregation.Aggregator                <- src/aggregation/aggregator.py
     models.Detection / FrameResult / ...  <- src/models/data_models.py

@@ -430,3 +430,64 @@ extern "C" int opd_tps_transform_f64(const opd_tps_table* t, const double* in_de
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Lens-distortion correction of points (src/calibration/lens_distortion.py:156-203 -> cv2.undistortPoints(pts, K, dist, P=K)):
+// OpenCV's fixed-point iteration with its default criteria (exactly 5 iterations), distortion model (k1, k2, p1, p2, k3),
+// output re-projected with the same camera matrix.  Restated from OpenCV's cvUndistortPointsInternal; float64.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct UndistortK {
+  double fx, fy, cx, cy, k1, k2, p1, p2, k3;
+  const double* in;
+  int input_is_bbox;
+  long long N;
+  double* out;
+};
+
+__global__ void __launch_bounds__(256) undistort_points_kernel(const UndistortK p) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.N; i += stride) {
+    double u, v;
+    if (p.input_is_bbox) {
+      u = __dadd_rn(p.in[4 * i + 0], __ddiv_rn(p.in[4 * i + 2], 2.0));   // foot point of an (x, y, w, h) box
+      v = __dadd_rn(p.in[4 * i + 1], p.in[4 * i + 3]);
+    } else {
+      u = p.in[2 * i + 0];
+      v = p.in[2 * i + 1];
+    }
+    const double ifx = 1.0 / p.fx, ify = 1.0 / p.fy;
+    double x = (u - p.cx) * ifx, y = (v - p.cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; ++j) {
+      const double r2 = x * x + y * y;
+      const double icdist = 1.0 / (1.0 + ((p.k3 * r2 + p.k2) * r2 + p.k1) * r2);
+      if (icdist < 0.0) {
+        x = (u - p.cx) * ifx;
+        y = (v - p.cy) * ify;
+        break;
+      }
+      const double dx = 2.0 * p.p1 * x * y + p.p2 * (r2 + 2.0 * x * x);
+      const double dy = p.p1 * (r2 + 2.0 * y * y) + 2.0 * p.p2 * x * y;
+      x = (x0 - dx) * icdist;
+      y = (y0 - dy) * icdist;
+    }
+    p.out[2 * i + 0] = p.fx * x + p.cx;
+    p.out[2 * i + 1] = p.fy * y + p.cy;
+  }
+}
+
+}  // namespace
+
+extern "C" int opd_undistort_points_f64(double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2, double k3,
+                                        const double* in_dev, int32_t input_is_bbox, int64_t N, double* out_dev, void* stream) {
+  OPD_REQUIRE(N >= 0 && (N == 0 || (in_dev && out_dev)) && fx != 0.0 && fy != 0.0, "opd_undistort_points_f64: bad argument");
+  if (N == 0) return OPD_OK;
+  UndistortK k{fx, fy, cx, cy, k1, k2, p1, p2, k3, in_dev, input_is_bbox, (long long)N, out_dev};
+  const long long blocks = std::min<long long>((N + 255) / 256, 148LL * 8);
+  undistort_points_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(k);
+  opd::count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}

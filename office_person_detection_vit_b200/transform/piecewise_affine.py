@@ -10,8 +10,8 @@ point location, the nearest-centroid extrapolation (:138-153), the affine map, b
 
 `transform_points` is the tensor entry: [N,2] float64 CUDA points (or [N,4] boxes) in, [N,2] floor pixels out; its output feeds
 `ZoneClassifier.count(points, transformer=None)` directly, so the PWA variant of the Phase 2 -> 3 path stays on the device.
-Lens-distortion correction (src/calibration/lens_distortion.py, disabled in the shipped config) is not built: passing a
-corrector raises NotImplementedError instead of silently skipping it."""
+A `distortion_corrector` (calibration.LensDistortionCorrector; disabled in the shipped config) is applied on the device before the
+transform, as the reference applies it per point (:163-167)."""
 
 from __future__ import annotations
 
@@ -26,6 +26,7 @@ from typing import TYPE_CHECKING, Sequence
 import numpy as np
 
 from .. import _lib
+from ..calibration import lens_distortion as _lens_distortion  # noqa: F401  (registers opd_undistort_points_f64)
 
 if TYPE_CHECKING:
     from .floormap_config import FloorMapConfig
@@ -65,12 +66,10 @@ class PiecewiseAffineTransformer:
     def __init__(self, src_points, dst_points, floormap_config: "FloorMapConfig | None" = None, distortion_corrector=None):
         from scipy.spatial import Delaunay
 
-        if distortion_corrector is not None:
-            raise NotImplementedError("lens-distortion correction is not part of the B200 path (disabled in the reference's shipped config)")
         self.src_points = np.array(src_points, dtype=np.float64)
         self.dst_points = np.array(dst_points, dtype=np.float64)
         self.floormap_config = floormap_config
-        self.distortion_corrector = None
+        self.distortion_corrector = distortion_corrector
         if len(self.src_points) < 3:
             raise ValueError("最低3点の対応点が必要です")
         if len(self.src_points) != len(self.dst_points):
@@ -121,6 +120,8 @@ class PiecewiseAffineTransformer:
         if points.dim() != 2 or points.shape[1] != cols or not points.is_cuda or points.dtype != torch.float64:
             raise ValueError(f"points must be a float64 CUDA tensor of shape [N,{cols}]")
         pts = points.contiguous()
+        if self.distortion_corrector is not None and self.distortion_corrector.enabled:
+            pts, is_bbox = self.distortion_corrector.undistort_tensor(pts, is_bbox=is_bbox), False   # :163-167, foot point first
         n, dev = pts.shape[0], pts.device
         px = torch.empty((n, 2), dtype=torch.float64, device=dev)
         mm = torch.empty((n, 2), dtype=torch.float64, device=dev) if with_mm else None
@@ -180,7 +181,8 @@ class PiecewiseAffineTransformer:
 
     def get_info(self) -> dict:
         return {"method": "piecewise_affine", "num_points": len(self.src_points), "num_triangles": len(self.delaunay.simplices),
-                "training_error": self.evaluate_training_error(), "distortion_correction_enabled": False}
+                "training_error": self.evaluate_training_error(), "distortion_correction_enabled": self.distortion_corrector is not None,
+                **({"distortion_params": self.distortion_corrector.intrinsics.distortion.to_dict()} if self.distortion_corrector is not None else {})}
 
     def save(self, path: Path | str) -> None:
         with open(path, "wb") as f:
@@ -211,13 +213,11 @@ class ThinPlateSplineTransformer:
 
     def __init__(self, src_points, dst_points, floormap_config: "FloorMapConfig | None" = None, regularization: float = 0.0,
                  distortion_corrector=None):
-        if distortion_corrector is not None:
-            raise NotImplementedError("lens-distortion correction is not part of the B200 path (disabled in the reference's shipped config)")
         self.src_points = np.array(src_points, dtype=np.float64)
         self.dst_points = np.array(dst_points, dtype=np.float64)
         self.floormap_config = floormap_config
         self.regularization = regularization
-        self.distortion_corrector = None
+        self.distortion_corrector = distortion_corrector
         if len(self.src_points) < 3:
             raise ValueError("最低3点の対応点が必要です")
         self.weights_x, self.weights_y, self.affine_x, self.affine_y = self._compute_tps_coefficients()
@@ -275,6 +275,8 @@ class ThinPlateSplineTransformer:
         if points.dim() != 2 or points.shape[1] != cols or not points.is_cuda or points.dtype != torch.float64:
             raise ValueError(f"points must be a float64 CUDA tensor of shape [N,{cols}]")
         pts = points.contiguous()
+        if self.distortion_corrector is not None and self.distortion_corrector.enabled:
+            pts, is_bbox = self.distortion_corrector.undistort_tensor(pts, is_bbox=is_bbox), False   # :490-494
         n, dev = pts.shape[0], pts.device
         px = torch.empty((n, 2), dtype=torch.float64, device=dev)
         mm = torch.empty((n, 2), dtype=torch.float64, device=dev) if with_mm else None
@@ -319,7 +321,8 @@ class ThinPlateSplineTransformer:
 
     def get_info(self) -> dict:
         return {"method": "thin_plate_spline", "num_points": len(self.src_points), "regularization": self.regularization,
-                "training_error": self.evaluate_training_error(), "distortion_correction_enabled": False}
+                "training_error": self.evaluate_training_error(), "distortion_correction_enabled": self.distortion_corrector is not None,
+                **({"distortion_params": self.distortion_corrector.intrinsics.distortion.to_dict()} if self.distortion_corrector is not None else {})}
 
     @classmethod
     def from_correspondence_file(cls, file_path: Path | str, floormap_config=None, regularization: float = 0.0,
