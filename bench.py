@@ -177,6 +177,10 @@ def main_gpu(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
+    # development A/B switch: OPD_OPTIONS="name=value,..." -> opd_set_option before the plans are built; recorded in `config`
+    options = dict(kv.split("=") for kv in os.environ.get("OPD_OPTIONS", "").split(",") if kv)
+    for k, v in options.items():
+        _lib.check(_lib.lib().opd_set_option(k.encode(), int(v)), f"opd_set_option({k})")
     det = ViTDetector(confidence_threshold=0.5, state_dict=random_init_state_dict(0), device=f"cuda:{local}",
                       batch_size=BATCH)
     det.load_model()
@@ -357,7 +361,8 @@ def main_gpu(args) -> None:
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world) | {"batch_per_gpu": B, "global_batch": B * world,
-                                                "launch": "cuda graph replay" if graph is not None else "stream launches"},
+                                                "launch": "cuda graph replay" if graph is not None else "stream launches",
+                                                **({"library_options": options} if options else {})},
             "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "detections_last_step": n_det,

@@ -14,7 +14,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--iters", type=int, default=30)
 ap.add_argument("--stage", type=int, default=0)
+ap.add_argument("--set", action="append", default=[], help="library option k=v (opd_set_option)")
 args = ap.parse_args()
+from office_person_detection_vit_b200 import _lib  # noqa: E402
+for kv in args.set:
+    k, v = kv.split("=")
+    _lib.check(_lib.lib().opd_set_option(k.encode(), int(v)), "opd_set_option")
 B = args.batch
 H, W, mid, width = ((200, 334, 64, 256), (100, 167, 128, 512))[args.stage]
 g = torch.Generator(device="cuda").manual_seed(0)

@@ -17,6 +17,8 @@ std::atomic<int> g_option_gemm_cluster{0};
 std::atomic<int> g_option_gemm_outbufs{1};
 std::atomic<int> g_option_pdl{0};
 std::atomic<int> g_option_gemm_pair{1};
+std::atomic<int> g_option_bneck_pair{1};
+std::atomic<int> g_option_bneck_release{1};
 std::atomic<int> g_option_gemm_mpairs{0};
 }  // namespace opd
 
@@ -55,6 +57,14 @@ int opd_set_option(const char* name, int32_t value) {
   }
   if (name && std::string(name) == "gemm_mpairs") {   // 0 (default): no m-block pairs; 1: long-K BLOCK_N = 256 layers; 2: whenever BLOCK_N = 256 (tests); new plans only
     opd::g_option_gemm_mpairs.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "bneck_release") {   // fused bottleneck tails: residual / output slots are released early in the next epilogue step (bit 0: im2col kernel - default, 23 % faster; bit 1: halo kernel - measured 1-3 % slower, off) or at its end
+    opd::g_option_bneck_release.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "bneck_pair") {   // cta_group::2 fused bottleneck tail (MID = 128): 0 off, 1 (default) layers of at least one tile per SM, 3 whenever the tile count is even (tests); new plans only
+    opd::g_option_bneck_pair.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "gemm_pair") {   // cta_group::2 GEMM: 0 off, 1 (default) BLOCK_N = 256 layers with a tile pair per cluster, 3 whenever BLOCK_N = 256 (tests); new plans only

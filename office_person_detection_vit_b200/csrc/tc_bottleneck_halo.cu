@@ -52,6 +52,7 @@ struct HaloParams {
   int tiles_x, tiles_y, num_tiles, num_n2;
   const float* bias2;
   const float* bias3;
+  int early_release;   // residual / output slots go back to the producer early in the next epilogue step (see tc_bottleneck.cu)
 };
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
@@ -317,6 +318,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
     uint32_t rk = 0, n = 0, acc2_phase[2] = {0, 0};
     uint8_t* my_out = smem_out + wg * CHUNK_BYTES;
     int prev_slot = -1;   // residual slot whose TMA store may still be reading it
+    const bool early_release = !kSC && p.early_release != 0;
+    // The slot an output chunk was stored from is released as soon as the store has read it: early in the NEXT step, not at its
+    // end, so that the slot's next residual chunk is requested a whole step earlier (tc_bottleneck.cu: the residual wait was
+    // 43 % of that kernel).
+    auto release_prev = [&]() {
+      if (early_release && et == 0 && prev_slot >= 0) {
+        ptx::tma_store_wait_read<0>();
+        ptx::mbar_arrive(&res_empty[prev_slot]);
+      }
+      if (early_release) prev_slot = -1;
+    };
 
     for (int t = first; t < n_tiles; t += step, ++n) {
       int b, y0, x0;
@@ -324,6 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       const uint32_t par = n & 1;
       // ---- E1: warpgroup g converts half tile g: acc1[g] -> +b2, ReLU -> bf16 -> A2[g] ----
       ptx::mbar_wait(acc1_full, par);
+      release_prev();
       ptx::mbar_wait(a2_free, par ^ 1);           // the previous tile's second GEMM no longer reads A2
       ptx::tc_fence_after_sync();
       {
@@ -356,6 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
         for (int h = 0; h < 2; ++h) {
           ptx::mbar_wait(&acc2_full[h], acc2_phase[h]);
           acc2_phase[h] ^= 1;
+          release_prev();
           ptx::tc_fence_after_sync();
           const uint32_t t_acc = tmem_acc2 + lane_addr + h * BLOCK_N2 + wg * 64;
           uint32_t packed[32];
@@ -402,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           if (et == 0) {
             tma_store_4d(&p.tmD, obuf, n0, x0 + h * SUB_W, y0, b);
             ptx::tma_store_commit();
-            if (!kSC && prev_slot >= 0) {
+            if (!kSC && !early_release && prev_slot >= 0) {
               ptx::tma_store_wait_read<1>();   // every store but the one just issued has finished reading shared memory
               ptx::mbar_arrive(&res_empty[prev_slot]);
             }
@@ -463,6 +477,7 @@ int bneck_halo_launch(const BneckPlan& plan, cudaStream_t stream) {
   p.num_n2 = plan.width / BLOCK_N2;
   p.bias2 = plan.bias2;
   p.bias3 = plan.bias3;
+  p.early_release = (g_option_bneck_release.load() & 2) != 0;
   static bool configured = false;
   if (!configured) {
     OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::kSmemBytes));

@@ -107,6 +107,7 @@ int stem_launch(const StemPlan& plan, cudaStream_t stream);
 struct BneckPlan {
   CUtensorMap tmA, tmB1, tmB2, tmR, tmD;
   int fused_shortcut;  // halo variant only: the projection shortcut is a second k-block of the 1x1 expansion
+  int pair;            // 1: cta_group::2 variant of tc_bneck_kernel<128> (two CTAs = one 256-pixel MMA, half a weight tile per SM)
   int halo;            // 1: stride-1, MID = 64 variant (tc_bottleneck_halo.cu): 16 x 8 pixel tiles, A = one halo patch per tile
   int M, mid, width;
   ConvGeom g;

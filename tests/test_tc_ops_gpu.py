@@ -8,6 +8,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 PAIR_DEFAULT = 1   # library default of opd_set_option("gemm_pair")
+BNECK_PAIR_DEFAULT = 1   # library default of opd_set_option("bneck_pair")
 
 
 @pytest.fixture(scope="module")
@@ -234,3 +235,35 @@ def test_fused_bottleneck_tail(T, B, H, W, mid, width, stride, halo):
         _lib.lib().opd_set_option(b"bneck_halo", 1)
     assert y.shape == ref.shape
     _close(torch, y, ref, f"bottleneck tail {B}x{H}x{W} mid {mid} width {width} s{stride}")
+
+
+@pytest.mark.parametrize("B,H,W,width,stride", [
+    (1, 16, 16, 512, 1),        # one pair of tiles
+    (2, 51, 84, 512, 2),        # 18 tiles, the last one partial
+    (2, 64, 64, 512, 1),
+    (4, 100, 167, 512, 1),      # 522 tiles: several per pair
+    (1, 32, 48, 256, 1),
+])
+def test_fused_bottleneck_tail_pair_variant_is_bit_identical(T, B, H, W, width, stride):
+    """cta_group::2 variant of the im2col bottleneck tail (MID = 128, two CTAs = one 256-pixel MMA, half a weight tile per SM):
+    same arithmetic in the same order as the one-CTA kernel, so the outputs must be equal bit for bit."""
+    from office_person_detection_vit_b200 import _lib
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    mid = 128
+    x = _rand(torch, B, H, W, mid, seed=30)
+    w2 = _rand(torch, mid, 3, 3, mid, seed=31, scale=(9 * mid) ** -0.5)
+    w3 = _rand(torch, width, mid, seed=32, scale=mid ** -0.5)
+    b2, b3 = torch.randn(mid, device="cuda") * 0.3, torch.randn(width, device="cuda") * 0.3
+    P, Q = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    res = _rand(torch, B, P, Q, width, seed=33)
+    try:
+        _lib.check(_lib.lib().opd_set_option(b"bneck_pair", 0), "opd_set_option")
+        a = ops.bottleneck_tail(x, w2, b2, w3, b3, res, stride=stride)
+        _lib.check(_lib.lib().opd_set_option(b"bneck_pair", 3), "opd_set_option")
+        b = ops.bottleneck_tail(x, w2, b2, w3, b3, res, stride=stride)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().opd_set_option(b"bneck_pair", BNECK_PAIR_DEFAULT)
+    assert torch.equal(a, b)
