@@ -249,6 +249,39 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// Epilogue arithmetic on column PAIRS (bit-identical to the scalar form): the two fp32 additions as packed pairs (FADD2,
+// Blackwell), the ReLU on the packed bf16 pair after rounding (rounding is monotonic and sign-preserving, max(-0, +0) = +0 and
+// max(NaN, 0) = 0 in both forms).  The scalar form issued 9 instructions per pair, this one 6 - and the fused bottleneck
+// epilogues are issue-bound (two epilogue warps per scheduler; -DOPD_BNECK_PROBE).
+__device__ __forceinline__ uint64_t f32x2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(0u));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {   // {lo, hi} fp32 pair -> packed bf16 (lo in the low half), round to nearest even
+  uint32_t lo, hi, d;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
+}
+// relu(acc + bias) and relu(acc + bias + residual) for two adjacent columns; bias2 = {bias[c], bias[c + 1]}
+__device__ __forceinline__ uint32_t epi_bias_relu2(uint32_t acc_lo, uint32_t acc_hi, float2 bias2) {
+  return relu_bf16x2(cvt_bf16x2(add_f32x2(f32x2(acc_lo, acc_hi), f32x2(__float_as_uint(bias2.x), __float_as_uint(bias2.y)))));
+}
+__device__ __forceinline__ uint32_t epi_bias_res_relu2(uint32_t acc_lo, uint32_t acc_hi, float2 bias2, uint32_t res_bf16x2) {
+  const uint64_t s = add_f32x2(f32x2(acc_lo, acc_hi), f32x2(__float_as_uint(bias2.x), __float_as_uint(bias2.y)));
+  return relu_bf16x2(cvt_bf16x2(add_f32x2(s, f32x2(res_bf16x2 << 16, res_bf16x2 & 0xffff0000u))));
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 

@@ -399,11 +399,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
         ptx::tmem_ld_wait();
         uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = fmaxf(__uint_as_float(v[2 * j]) + s_bias2[u * 32 + 2 * j], 0.f);
-          const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias2[u * 32 + 2 * j + 1], 0.f);
-          packed[j] = ptx::pack_bf16(a, b);
-        }
+        for (int j = 0; j < 16; ++j)
+          packed[j] = ptx::epi_bias_relu2(v[2 * j], v[2 * j + 1], *reinterpret_cast<const float2*>(s_bias2 + u * 32 + 2 * j));
         uint8_t* rowp = smem_a2 + (u >> 1) * CHUNK_BYTES + row * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -464,11 +461,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
         ptx::tmem_ld_wait();
         const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = fmaxf(__uint_as_float(v[2 * j]) + my_bias3[h * 32 + 2 * j] + ptx::bf16_lo(rw[j]), 0.f);
-          const float b = fmaxf(__uint_as_float(v[2 * j + 1]) + my_bias3[h * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]), 0.f);
-          packed[h * 16 + j] = ptx::pack_bf16(a, b);
-        }
+        for (int j = 0; j < 16; ++j)
+          packed[h * 16 + j] = ptx::epi_bias_res_relu2(v[2 * j], v[2 * j + 1], *reinterpret_cast<const float2*>(my_bias3 + h * 32 + 2 * j), rw[j]);
       }
       // accumulator and residual chunk are in registers: hand both back before the store path
       ptx::tc_fence_before_sync();

@@ -55,6 +55,13 @@ struct HaloParams {
   int early_release;   // residual / output slots go back to the producer early in the next epilogue step (see tc_bottleneck.cu)
 };
 
+#ifdef OPD_BNECK_PROBE
+constexpr bool kHaloProbe = true;
+#else
+constexpr bool kHaloProbe = false;   // -DOPD_BNECK_PROBE: clock64 counters of the epilogue's waits, printed by two CTAs
+#endif
+__device__ __forceinline__ long long hclk() { return kHaloProbe ? clock64() : 0; }
+
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -330,14 +337,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       if (early_release) prev_slot = -1;
     };
 
+    long long c_acc1 = 0, c_free = 0, c_e1 = 0, c_acc2 = 0, c_res = 0, c_math = 0, c_store = 0;
+    const long long c_begin = hclk();
     for (int t = first; t < n_tiles; t += step, ++n) {
       int b, y0, x0;
       tile_origin(t, b, y0, x0);
       const uint32_t par = n & 1;
+      const long long q0 = hclk();
       // ---- E1: warpgroup g converts half tile g: acc1[g] -> +b2, ReLU -> bf16 -> A2[g] ----
       ptx::mbar_wait(acc1_full, par);
       release_prev();
+      const long long q1 = hclk();
       ptx::mbar_wait(a2_free, par ^ 1);           // the previous tile's second GEMM no longer reads A2
+      const long long q2 = hclk();
+      c_acc1 += q1 - q0;
+      c_free += q2 - q1;
       ptx::tc_fence_after_sync();
       {
 #pragma unroll
@@ -348,8 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           uint32_t packed[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            packed[j] = ptx::pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + s_bias2[u * 32 + 2 * j], 0.f),
-                                       fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias2[u * 32 + 2 * j + 1], 0.f));
+            packed[j] = ptx::epi_bias_relu2(v[2 * j], v[2 * j + 1], *reinterpret_cast<const float2*>(s_bias2 + u * 32 + 2 * j));
           uint8_t* rowp = smem_a2 + (wg * kCB + (u >> 1)) * CHUNK_BYTES + row * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -361,15 +374,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       ptx::mbar_arrive(acc1_empty);
       ptx::fence_proxy_async_smem();             // A2 is read by the tensor core through the async proxy
       ptx::mbar_arrive(a2_ready);
+      c_e1 += hclk() - q2;
 
       // ---- E2: (n2, h) in MMA order; warpgroup g owns columns [n2 * 128 + 64 g, + 64) ----
       for (int n2 = 0; n2 < p.num_n2; ++n2) {
         const int n0 = n2 * BLOCK_N2 + wg * 64;
         const float* my_bias3 = s_bias3 + n0;
         for (int h = 0; h < 2; ++h) {
+          const long long r0 = hclk();
           ptx::mbar_wait(&acc2_full[h], acc2_phase[h]);
           acc2_phase[h] ^= 1;
           release_prev();
+          const long long r1 = hclk();
           ptx::tc_fence_after_sync();
           const uint32_t t_acc = tmem_acc2 + lane_addr + h * BLOCK_N2 + wg * 64;
           uint32_t packed[32];
@@ -379,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
             ptx::mbar_wait(&res_full[rslot], (rk / kResPerWg) & 1);
             ++rk;
           }
+          const long long r2 = hclk();
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             uint32_t v[32];
@@ -391,13 +408,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float a = fmaxf(__uint_as_float(v[2 * j]) + my_bias3[u * 32 + 2 * j] + ptx::bf16_lo(rw[j]), 0.f);
-              const float bb = fmaxf(__uint_as_float(v[2 * j + 1]) + my_bias3[u * 32 + 2 * j + 1] + ptx::bf16_hi(rw[j]), 0.f);
-              packed[u * 16 + j] = ptx::pack_bf16(a, bb);
+              const float2 b2 = *reinterpret_cast<const float2*>(my_bias3 + u * 32 + 2 * j);
+              packed[u * 16 + j] = kSC ? ptx::epi_bias_relu2(v[2 * j], v[2 * j + 1], b2) : ptx::epi_bias_res_relu2(v[2 * j], v[2 * j + 1], b2, rw[j]);
             }
           }
           ptx::tc_fence_before_sync();
           ptx::mbar_arrive(&acc2_empty[h]);
+          const long long r3 = hclk();
           if (kSC) {
             // staging box: its previous TMA store must have finished READING it; waited for here, after the arithmetic
             if (et == 0) ptx::tma_store_wait_read<0>();
@@ -422,9 +439,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
             }
           }
           prev_slot = rslot;
+          c_acc2 += r1 - r0;
+          c_res += r2 - r1;
+          c_math += r3 - r2;
+          c_store += hclk() - r3;
         }
       }
     }
+    if (kHaloProbe && (blockIdx.x == 0 || blockIdx.x == 77) && et == 0)
+      printf("halo<%d,%d> CTA %d wg %d: %lld cycles, %u tiles; E1: acc1_full wait %lld, a2_free wait %lld, convert %lld; E2: acc2_full wait %lld, res_full wait %lld, "
+             "math %lld, st.shared + barrier + store (+ read wait) %lld\n",
+             MID, (int)kSC, (int)blockIdx.x, wg, hclk() - c_begin, n, c_acc1, c_free, c_e1, c_acc2, c_res, c_math, c_store);
     if (et == 0) ptx::tma_store_wait_all<0>();
   }
 
