@@ -510,22 +510,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 bq = bias4[j4];
-                float a0 = __uint_as_float(v[4 * j4]) + bq.x, a1 = __uint_as_float(v[4 * j4 + 1]) + bq.y;
-                float a2 = __uint_as_float(v[4 * j4 + 2]) + bq.z, a3 = __uint_as_float(v[4 * j4 + 3]) + bq.w;
+                // packed fp32 pairs (FADD2) and the ReLU on the rounded bf16 pair: bit-identical to the scalar form, 6 instead
+                // of 9 instructions per column pair (sm100_ptx.cuh)
+                uint64_t s0 = ptx::add_f32x2(ptx::f32x2(v[4 * j4], v[4 * j4 + 1]), ptx::f32x2(__float_as_uint(bq.x), __float_as_uint(bq.y)));
+                uint64_t s1 = ptx::add_f32x2(ptx::f32x2(v[4 * j4 + 2], v[4 * j4 + 3]), ptx::f32x2(__float_as_uint(bq.z), __float_as_uint(bq.w)));
                 if (use_res) {   // compile-time false in the kernels without a residual ring: no "+ 0.f" left behind
-                  a0 += ptx::bf16_lo(rw[2 * j4]);
-                  a1 += ptx::bf16_hi(rw[2 * j4]);
-                  a2 += ptx::bf16_lo(rw[2 * j4 + 1]);
-                  a3 += ptx::bf16_hi(rw[2 * j4 + 1]);
+                  const uint32_t r0 = rw[2 * j4], r1 = rw[2 * j4 + 1];
+                  s0 = ptx::add_f32x2(s0, ptx::f32x2(r0 << 16, r0 & 0xffff0000u));
+                  s1 = ptx::add_f32x2(s1, ptx::f32x2(r1 << 16, r1 & 0xffff0000u));
                 }
-                if (kRelu) {
-                  a0 = fmaxf(a0, 0.f);
-                  a1 = fmaxf(a1, 0.f);
-                  a2 = fmaxf(a2, 0.f);
-                  a3 = fmaxf(a3, 0.f);
-                }
-                packed[h * 16 + 2 * j4] = ptx::pack_bf16(a0, a1);
-                packed[h * 16 + 2 * j4 + 1] = ptx::pack_bf16(a2, a3);
+                const uint32_t o0 = ptx::cvt_bf16x2(s0), o1 = ptx::cvt_bf16x2(s1);
+                packed[h * 16 + 2 * j4] = kRelu ? ptx::relu_bf16x2(o0) : o0;
+                packed[h * 16 + 2 * j4 + 1] = kRelu ? ptx::relu_bf16x2(o1) : o1;
               }
             };
             if (p.epi != EPI_BIAS) convert(std::true_type{});   // warp-uniform: one branch per 32 columns, none per element
