@@ -46,7 +46,7 @@ struct Cfg {
   static constexpr int kBSlot = CHUNK_BYTES / (kPair ? 2 : 1);       // B1: MID x 64, B2: 128 x 64; kPair: this CTA's half of the rows
   static constexpr int kStageBytes = CHUNK_BYTES + kBSlot;          // A slot 16 KB + B slot
   static constexpr int kB2Stages = kPair ? 4 : 2;                    // ring of W3 tiles (second GEMM), fed by its own producer
-  static constexpr int kFixed = (kA2Chunks + kResStages) * CHUNK_BYTES + kB2Stages * kBSlot + 2048;   // residual slots double as output staging
+  static constexpr int kFixed = (kA2Chunks + kResStages) * CHUNK_BYTES + kB2Stages * kBSlot + 3072;   // residual slots double as output staging
   static constexpr int kStages = (kSmemBudget - kFixed) / kStageBytes > 6 ? 6 : (kSmemBudget - kFixed) / kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kFixed;
   static constexpr int kTmemCols = 512;                             // acc1 2 x MID + acc2 2 x 128
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
   uint8_t* smem_a2 = smem_b2 + C::kB2Stages * C::kBSlot;     // A operand of the second GEMM
   uint8_t* smem_res = smem_a2 + C::kA2Chunks * CHUNK_BYTES;  // residual slots; the output chunk is written in place and stored from there
   float* s_bias2 = reinterpret_cast<float*>(smem_res + kResStages * CHUNK_BYTES);   // [MID]
-  float* s_bias3 = s_bias2 + 128;                                                   // [128] of the current n2 tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 128);
+  float* s_bias3 = s_bias2 + 128;                                                   // [width <= 512]: whole layer, loaded once
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 512);
   uint64_t* full_bar = bars;                  // [kStages]
   uint64_t* empty_bar = bars + 8;             // [kStages]
   uint64_t* acc1_full = bars + 16;            // [2]
@@ -352,11 +352,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int bar_id = 1 + wg;
     for (int i = threadIdx.x; i < MID; i += 256) s_bias2[i] = p.bias2[i];
+    for (int i = threadIdx.x; i < p.width; i += 256) s_bias3[i] = p.bias3[i];   // (was reloaded per n2 tile behind a 128-thread barrier)
     ptx::named_bar_sync(3, 256);
 
     int a1 = 0, a2 = 0;
     uint32_t a1_phase = 0, a2_phase = 0, rk = 0, free_phase = 0;
-    float* my_bias3 = s_bias3 + wg * 64;
     int prev_slot = -1;   // slot whose TMA store may still be reading it
     const bool early_release = p.early_release != 0;
     long long c_acc1 = 0, c_free = 0, c_e1 = 0, c_bar = 0, c_acc2 = 0, c_res = 0, c_math = 0, c_store = 0;
@@ -434,8 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_kernel(const __grid_cons
     auto e2 = [&](int m_blk, int n2) {
       const int m0 = m_blk * BLOCK_M, n0 = n2 * BLOCK_N2 + wg * 64;
       const long long q0 = pclk();
-      if (et < 64) my_bias3[et] = p.bias3[n0 + et];
-      ptx::named_bar_sync(bar_id, 128);
+      const float* my_bias3 = s_bias3 + n0;
       if (wg == 0 && et == 0) trace_ev(p.trace, 30);
       const long long q1 = pclk();
       ptx::mbar_wait(&acc2_full[a2], a2_phase);
@@ -584,7 +583,7 @@ int bneck_plan(BneckPlan* plan, const __nv_bfloat16* x, const ConvGeom& g, const
     return bneck_halo_plan(plan, x, g, w2, bias2, w3, bias3, width, residual, y);
   *plan = BneckPlan{};
   OPD_REQUIRE(g.KH == 3 && g.KW == 3 && (g.C == 64 || g.C == 128), "bottleneck tail: 3x3 convolution over 64 or 128 channels (C=%d)", g.C);
-  OPD_REQUIRE(width % BLOCK_N2 == 0 && width > 0, "bottleneck tail: width=%d must be a multiple of 128", width);
+  OPD_REQUIRE(width % BLOCK_N2 == 0 && width > 0 && width <= 512, "bottleneck tail: width=%d must be a multiple of 128, <= 512", width);
   OPD_REQUIRE(bias2 && bias3 && residual && y && x && w2 && w3, "bottleneck tail: NULL argument");
   plan->M = g.B * g.P * g.Q;
   plan->mid = g.C;
