@@ -273,3 +273,34 @@ def test_full_size_batch_invariance_and_determinism(detector):
     l2, b2 = eng.forward(frames[1:3].contiguous())
     assert torch.equal(l2, l5[1:3]) and torch.equal(b2, b5[1:3])
     assert torch.isfinite(l5).all() and float(b5.min()) >= 0.0 and float(b5.max()) <= 1.0
+
+
+def test_decoder_layer0_prologue_is_bit_identical(detector):
+    """Decoder layer 0's self-attention block does not depend on the frame (the queries enter as zeros + query positions): by
+    default it runs once per plan (six launches fewer per step).  Same kernels on the same inputs: logits and boxes must equal
+    those of a plan that runs the block in every step, bit for bit, for several batches in a row."""
+    import torch
+
+    from office_person_detection_vit_b200 import _lib
+
+    eng = detector.model
+    a = torch.from_numpy(do.synthetic_frames(3, 480, 640, seed=41)).cuda()
+    b = torch.from_numpy(do.synthetic_frames(3, 480, 640, seed=42)).cuda()
+    try:
+        _lib.check(_lib.lib().opd_set_option(b"dec0_const", 0), "opd_set_option")
+        eng.set_debug(False)                                  # drops the plan: the next forward plans with the option
+        n0 = _lib.lib().opd_launch_count()
+        ref = [tuple(t.clone() for t in eng.forward(x)) for x in (a, b)]
+        per_step_all = (_lib.lib().opd_launch_count() - n0) // 2
+        _lib.check(_lib.lib().opd_set_option(b"dec0_const", 1), "opd_set_option")
+        eng.set_debug(False)
+        eng.forward(a)                                        # prologue + first step
+        n0 = _lib.lib().opd_launch_count()
+        got = [tuple(t.clone() for t in eng.forward(x)) for x in (a, b, a)]
+        per_step = (_lib.lib().opd_launch_count() - n0) // 3
+    finally:
+        _lib.lib().opd_set_option(b"dec0_const", 1)
+        eng.set_debug(False)
+    assert per_step == per_step_all - 6
+    for (l, bx), (rl, rb) in zip(got, ref + ref[:1]):
+        assert torch.equal(l, rl) and torch.equal(bx, rb)
