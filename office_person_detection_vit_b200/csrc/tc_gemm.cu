@@ -409,6 +409,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
     };
     // the layer's bias -> shared memory once (was a global load + a 256-thread barrier at the head of every tile)
     for (int i = e256; i < p.N; i += 256) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    // LayerNorm epilogue (N == BLOCK_N == 256): gamma / beta next to the bias.  They were two __ldg per output element: at
+    // M = 6400 (one tile per CTA, cold L1) those loads were ~4000 of the ~9000 cycles of the tile's epilogue (-DOPD_GEMM_PROBE).
+    float* const s_gamma = s_bias + 256;
+    float* const s_beta = s_bias + 512;
+    if (p.epi == EPI_BIAS_RES_LN)
+      for (int i = e256; i < 256; i += 256) {
+        s_gamma[i] = p.gamma[i];
+        s_beta[i] = p.beta[i];
+      }
     ptx::named_bar_sync(3, 256);
     long long e_full = 0, e_ld = 0, e_math = 0, e_wait = 0, e_sts = 0, e_fence = 0, e_begin = gclk();
     for (int it = 0; it < n_my; ++it) {
@@ -483,13 +492,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
           ptx::tmem_ld_32x32(t_acc + g * 32, v);
           if (p.epi == EPI_BIAS_RES_LN) {
             ptx::tmem_ld_wait();
+            // ((v - mean) * rstd) * gamma + beta on column pairs: FADD2, FMUL2, FFMA2 - the scalar form's operations in its order
+            const uint64_t nmean2 = ptx::f32x2(__float_as_uint(-mean), __float_as_uint(-mean));
+            const uint64_t rstd2 = ptx::f32x2(__float_as_uint(rstd), __float_as_uint(rstd));
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + g * 32);
+            const float4* b4 = reinterpret_cast<const float4*>(s_beta + g * 32);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int col = n0 + g * 32 + 2 * j;
-              const float a = (__uint_as_float(v[2 * j]) - mean) * rstd * __ldg(p.gamma + col) + __ldg(p.beta + col);
-              const float b =
-                  (__uint_as_float(v[2 * j + 1]) - mean) * rstd * __ldg(p.gamma + col + 1) + __ldg(p.beta + col + 1);
-              packed[h * 16 + j] = ptx::pack_bf16(a, b);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 gq = g4[j4], bq = b4[j4];
+              uint64_t x0 = ptx::mul_f32x2(ptx::add_f32x2(ptx::f32x2(v[4 * j4], v[4 * j4 + 1]), nmean2), rstd2);
+              uint64_t x1 = ptx::mul_f32x2(ptx::add_f32x2(ptx::f32x2(v[4 * j4 + 2], v[4 * j4 + 3]), nmean2), rstd2);
+              x0 = ptx::fma_f32x2(x0, ptx::f32x2(__float_as_uint(gq.x), __float_as_uint(gq.y)), ptx::f32x2(__float_as_uint(bq.x), __float_as_uint(bq.y)));
+              x1 = ptx::fma_f32x2(x1, ptx::f32x2(__float_as_uint(gq.z), __float_as_uint(gq.w)), ptx::f32x2(__float_as_uint(bq.z), __float_as_uint(bq.w)));
+              packed[h * 16 + 2 * j4] = ptx::cvt_bf16x2(x0);
+              packed[h * 16 + 2 * j4 + 1] = ptx::cvt_bf16x2(x1);
             }
           } else {
             uint4 rr[4];
