@@ -312,8 +312,7 @@ __global__ void __launch_bounds__(kPool ? kPoolThreads : kThreads, 1) stem_kerne
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          packed[h * 16 + j] = ptx::pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + s_bias[h * 32 + 2 * j], 0.f),
-                                              fmaxf(__uint_as_float(v[2 * j + 1]) + s_bias[h * 32 + 2 * j + 1], 0.f));
+          packed[h * 16 + j] = ptx::epi_bias_relu2(v[2 * j], v[2 * j + 1], *reinterpret_cast<const float2*>(s_bias + h * 32 + 2 * j));
       }
       ptx::tc_fence_before_sync();
       __syncwarp();

@@ -27,6 +27,8 @@ def test_header_symbols_exported(built_lib):
 def test_python_binding_covers_header(built_lib):
     from office_person_detection_vit_b200 import _lib
     import office_person_detection_vit_b200.detection  # noqa: F401  (registers the detector entry points)
+    import office_person_detection_vit_b200.transform  # noqa: F401  (homography / piecewise-affine / TPS / undistortion entry points)
+    import office_person_detection_vit_b200.zone  # noqa: F401
 
     assert set(_lib.exported_symbols()) == _declared_symbols()
     assert _lib.lib().opd_version() == 1
