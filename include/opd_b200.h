@@ -46,7 +46,7 @@ int64_t opd_launch_count(void);
  *   "attention_kv" 64 (default) or 128: keys per tile of the tcgen05 attention kernel (4 or 2 CTAs per SM)
  *   "bneck_halo"  1 (default): 64-channel stride-1 bottleneck tails load one halo patch per tile; 0: im2col TMA.
  *   "bneck_pair"  1 (default): 128-channel bottleneck tails run as cta_group::2 pairs; 0: one CTA per tile; 3: tests
- *   "bneck_release" bit 0 (default 1): im2col tail hands residual slots back early in the next epilogue step; bit 1: halo tail too
+ *   "bneck_release" 3 (default): the fused tails hand a residual slot back early in the next epilogue step (bit 0 im2col, bit 1 halo kernel)
  *   "gemm_pair"   1 (default): BLOCK_N = 256 GEMM / convolution layers run as cta_group::2 pairs; 0: off; 3: tests
  *   "dec0_const"  1 (default): decoder layer 0's frame-independent self-attention block runs once per plan; 0: every step
  *   (further measurement variants are listed in csrc/opd_core.cu). */

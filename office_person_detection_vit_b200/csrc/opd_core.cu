@@ -19,7 +19,7 @@ std::atomic<int> g_option_pdl{0};
 std::atomic<int> g_option_gemm_pair{1};
 std::atomic<int> g_option_dec0_const{1};
 std::atomic<int> g_option_bneck_pair{1};
-std::atomic<int> g_option_bneck_release{1};
+std::atomic<int> g_option_bneck_release{3};
 std::atomic<int> g_option_gemm_mpairs{0};
 }  // namespace opd
 
@@ -60,7 +60,7 @@ int opd_set_option(const char* name, int32_t value) {
     opd::g_option_gemm_mpairs.store(value);
     return OPD_OK;
   }
-  if (name && std::string(name) == "bneck_release") {   // fused bottleneck tails: residual / output slots are released early in the next epilogue step (bit 0: im2col kernel - default, 23 % faster; bit 1: halo kernel - measured 1-3 % slower, off) or at its end
+  if (name && std::string(name) == "bneck_release") {   // fused bottleneck tails: residual / output slots are released early in the next epilogue step (bit 0: im2col kernel, right after the accumulator wait: 23 % faster; bit 1: halo kernel, after the step's arithmetic: 3 % faster in the pipeline; default 3) or at its end
     opd::g_option_bneck_release.store(value);
     return OPD_OK;
   }

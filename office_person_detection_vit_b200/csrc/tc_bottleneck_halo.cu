@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           bphase ^= 1;
         }
       };
-      for (int t = first; t < n_tiles; t += step) {
+      auto load_g1 = [&](int t) {   // the tile's halo patch (per 64-channel slab) and its W2 tap tiles
         int b, y0, x0;
         tile_origin(t, b, y0, x0);
         for (int cb = 0; cb < kCB; ++cb, ++pc) {
@@ -191,13 +191,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
             next_b();
           }
         }
-        for (int n2 = 0; n2 < p.num_n2; ++n2)
-          for (int kb = 0; kb < kB2Blocks; ++kb) {   // kb >= kCB: the shortcut weights (last 64 columns of [W3 | Wsc])
-            ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
-            ptx::mbar_expect_tx(&b_full[bs], CHUNK_BYTES);
-            ptx::tma_load_2d(&p.tmB2, &b_full[bs], smem_b + bs * CHUNK_BYTES, kb * 64, n2 * BLOCK_N2);
-            next_b();
-          }
+      };
+      auto load_g2 = [&](int n2) {
+        for (int kb = 0; kb < kB2Blocks; ++kb) {   // kb >= kCB: the shortcut weights (last 64 columns of [W3 | Wsc])
+          ptx::mbar_wait(&b_empty[bs], bphase ^ 1);
+          ptx::mbar_expect_tx(&b_full[bs], CHUNK_BYTES);
+          ptx::tma_load_2d(&p.tmB2, &b_full[bs], smem_b + bs * CHUNK_BYTES, kb * 64, n2 * BLOCK_N2);
+          next_b();
+        }
+      };
+      // Same order as the MMA issuer consumes the ring (see there): G1 of the next tile goes before the last n2 tile of this one.
+      if (first < n_tiles) load_g1(first);
+      for (int t = first; t < n_tiles; t += step) {
+        for (int n2 = 0; n2 < p.num_n2 - 1; ++n2) load_g2(n2);
+        if (t + step < n_tiles) load_g1(t + step);
+        load_g2(p.num_n2 - 1);
       }
     }
   } else if (warp == 9) {
@@ -212,10 +220,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
         }
       };
       const uint64_t patch_desc = desc_sw128(ptx::smem_u32(smem_patch), PATCH_W * 128);
-      for (int t = first; t < n_tiles; t += step, ++n) {
-        const uint32_t par = n & 1;
+      // Issue order per tile i:  G2(i, 0 .. last-1)  G1(i+1)  G2(i, last)   (G1(0) first).
+      // The epilogue converts tile i+1's mid activation (E1) between the two half tiles of tile i's last n2 tile, so G2(i+1, 0)
+      // can start while the epilogue is still on tile i: with the strict G1(i) G2(i) order every tile ended in a bubble of
+      // about 1600 cycles (E1, then the first second-GEMM tile, with the epilogue idle; -DOPD_BNECK_PROBE: acc2_full wait 13 %).
+      uint32_t n1 = 0;   // tiles whose G1 has been issued
+      auto g1 = [&]() {
         // ---- G1: both half tiles, every W2 tap tile used twice; one 64-channel patch slab at a time ----
-        ptx::mbar_wait(acc1_empty, par ^ 1);
+        ptx::mbar_wait(acc1_empty, (n1 & 1) ^ 1);
         for (int cb = 0; cb < kCB; ++cb, ++pc) {
           ptx::mbar_wait(patch_full, pc & 1);
           ptx::tc_fence_after_sync();
@@ -242,41 +254,70 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           ptx::umma_commit(patch_empty);   // the slab may be overwritten once these MMAs have read it
         }
         ptx::umma_commit(acc1_full);
-        // ---- G2: per n2 tile both half tiles share the W3 (and Wsc) tile ----
-        ptx::mbar_wait(a2_ready, par);
-        if (kSC) {
-          ptx::mbar_wait(&res_full[0], par);
-          ptx::mbar_wait(&res_full[1], par);
+        ++n1;
+      };
+      // ---- G2: per n2 tile both half tiles share the W3 (and Wsc) tile ----
+      auto g2 = [&](int n2, uint32_t par) {
+        if (n2 == 0) {
+          ptx::mbar_wait(a2_ready, par);
+          if (kSC) {
+            ptx::mbar_wait(&res_full[0], par);
+            ptx::mbar_wait(&res_full[1], par);
+          }
+          ptx::tc_fence_after_sync();
         }
-        ptx::tc_fence_after_sync();
-        for (int n2 = 0; n2 < p.num_n2; ++n2) {
-          for (int kb = 0; kb < kB2Blocks; ++kb) {
-            ptx::mbar_wait(&b_full[bs], bphase);
-            const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES);
-            uint64_t da[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (kb == 0) {
-                ptx::mbar_wait(&acc2_empty[h], acc2_phase[h] ^ 1);
-                acc2_phase[h] ^= 1;
-              }
-              da[h] = desc_sw128(ptx::smem_u32(kb < kCB ? smem_a2 + (h * kCB + kb) * CHUNK_BYTES : smem_res + h * CHUNK_BYTES), 1024);
-            }
+        if (kB2Blocks == 1 && n2 == 0) {
+          // first n2 tile of a tile: half tile 0's accumulator is free one epilogue step before half tile 1's - issue (and
+          // commit) the halves separately so that the epilogue's first step of the tile does not wait for both
+          ptx::mbar_wait(&b_full[bs], bphase);
+          const uint64_t db = desc_sw128(ptx::smem_u32(smem_b + bs * CHUNK_BYTES), 1024);
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&acc2_empty[h], acc2_phase[h] ^ 1);
+            acc2_phase[h] ^= 1;
             ptx::tc_fence_after_sync();
-            const uint64_t db = desc_sw128(b_addr, 1024);
+            const uint64_t da = desc_sw128(ptx::smem_u32(smem_a2 + (h * kCB) * CHUNK_BYTES), 1024);
 #pragma unroll
             for (int k = 0; k < 64 / UMMA_K; ++k)
-#pragma unroll
-              for (int h = 0; h < 2; ++h)   // alternate the two accumulators (see G1)
-                ptx::umma_bf16_ss(tmem_acc2 + h * BLOCK_N2, da[h] + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | k) != 0);
-            if (kb == kB2Blocks - 1) {
-              ptx::umma_commit(&acc2_full[0]);
-              ptx::umma_commit(&acc2_full[1]);
-            }
-            ptx::umma_commit(&b_empty[bs]);
-            next_b();
+              ptx::umma_bf16_ss(tmem_acc2 + h * BLOCK_N2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, k != 0);
+            ptx::umma_commit(&acc2_full[h]);
           }
+          ptx::umma_commit(&b_empty[bs]);
+          next_b();
+          return;
         }
+        for (int kb = 0; kb < kB2Blocks; ++kb) {
+          ptx::mbar_wait(&b_full[bs], bphase);
+          const uint32_t b_addr = ptx::smem_u32(smem_b + bs * CHUNK_BYTES);
+          uint64_t da[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (kb == 0) {
+              ptx::mbar_wait(&acc2_empty[h], acc2_phase[h] ^ 1);
+              acc2_phase[h] ^= 1;
+            }
+            da[h] = desc_sw128(ptx::smem_u32(kb < kCB ? smem_a2 + (h * kCB + kb) * CHUNK_BYTES : smem_res + h * CHUNK_BYTES), 1024);
+          }
+          ptx::tc_fence_after_sync();
+          const uint64_t db = desc_sw128(b_addr, 1024);
+#pragma unroll
+          for (int k = 0; k < 64 / UMMA_K; ++k)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)   // alternate the two accumulators (see G1)
+              ptx::umma_bf16_ss(tmem_acc2 + h * BLOCK_N2, da[h] + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc2, (kb | k) != 0);
+          if (kb == kB2Blocks - 1) {
+            ptx::umma_commit(&acc2_full[0]);
+            ptx::umma_commit(&acc2_full[1]);
+          }
+          ptx::umma_commit(&b_empty[bs]);
+          next_b();
+        }
+      };
+      if (first < n_tiles) g1();
+      for (int t = first; t < n_tiles; t += step, ++n) {
+        const uint32_t par = n & 1;
+        for (int n2 = 0; n2 < p.num_n2 - 1; ++n2) g2(n2, par);
+        if (t + step < n_tiles) g1();
+        g2(p.num_n2 - 1, par);
         ptx::umma_commit(a2_free);
         if (kSC) {
           ptx::umma_commit(&res_empty[0]);
@@ -339,12 +380,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
 
     long long c_acc1 = 0, c_free = 0, c_e1 = 0, c_acc2 = 0, c_res = 0, c_math = 0, c_store = 0;
     const long long c_begin = hclk();
-    for (int t = first; t < n_tiles; t += step, ++n) {
-      int b, y0, x0;
-      tile_origin(t, b, y0, x0);
-      const uint32_t par = n & 1;
+    // ---- E1: warpgroup g converts half tile g: acc1[g] -> +b2, ReLU -> bf16 -> A2[g] ----
+    auto e1 = [&](uint32_t par) {
       const long long q0 = hclk();
-      // ---- E1: warpgroup g converts half tile g: acc1[g] -> +b2, ReLU -> bf16 -> A2[g] ----
       ptx::mbar_wait(acc1_full, par);
       release_prev();
       const long long q1 = hclk();
@@ -375,16 +413,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
       ptx::fence_proxy_async_smem();             // A2 is read by the tensor core through the async proxy
       ptx::mbar_arrive(a2_ready);
       c_e1 += hclk() - q2;
+    };
 
-      // ---- E2: (n2, h) in MMA order; warpgroup g owns columns [n2 * 128 + 64 g, + 64) ----
-      for (int n2 = 0; n2 < p.num_n2; ++n2) {
+    // ---- E2 step (n2, h), in MMA order; warpgroup g owns columns [n2 * 128 + 64 g, + 64) ----
+    auto e2 = [&](int n2, int h, int b, int y0, int x0) {
         const int n0 = n2 * BLOCK_N2 + wg * 64;
         const float* my_bias3 = s_bias3 + n0;
-        for (int h = 0; h < 2; ++h) {
+        {
           const long long r0 = hclk();
           ptx::mbar_wait(&acc2_full[h], acc2_phase[h]);
           acc2_phase[h] ^= 1;
-          release_prev();
           const long long r1 = hclk();
           ptx::tc_fence_after_sync();
           const uint32_t t_acc = tmem_acc2 + lane_addr + h * BLOCK_N2 + wg * 64;
@@ -414,6 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           }
           ptx::tc_fence_before_sync();
           ptx::mbar_arrive(&acc2_empty[h]);
+          release_prev();   // after this step's arithmetic: the previous store has had that long to read its slot
           const long long r3 = hclk();
           if (kSC) {
             // staging box: its previous TMA store must have finished READING it; waited for here, after the arithmetic
@@ -444,7 +483,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bneck_halo_kernel(const __grid
           c_math += r3 - r2;
           c_store += hclk() - r3;
         }
+    };
+
+    // Tile i+1's conversion (E1) runs between the two half tiles of tile i's last n2 tile: its A2 hand-off lets the second GEMM of
+    // tile i+1 start while the epilogue still has a step of tile i to do (the MMA issuer's order matches: see there).
+    if (first < n_tiles) e1(0);
+    for (int t = first; t < n_tiles; t += step, ++n) {
+      int b, y0, x0;
+      tile_origin(t, b, y0, x0);
+      const int last = p.num_n2 - 1;
+      for (int n2 = 0; n2 < last; ++n2) {
+        e2(n2, 0, b, y0, x0);
+        e2(n2, 1, b, y0, x0);
       }
+      e2(last, 0, b, y0, x0);
+      if (t + step < n_tiles) e1((n + 1) & 1);
+      e2(last, 1, b, y0, x0);
     }
     if (kHaloProbe && (blockIdx.x == 0 || blockIdx.x == 77) && et == 0)
       printf("halo<%d,%d> CTA %d wg %d: %lld cycles, %u tiles; E1: acc1_full wait %lld, a2_free wait %lld, convert %lld; E2: acc2_full wait %lld, res_full wait %lld, "
