@@ -48,6 +48,7 @@ int64_t opd_launch_count(void);
  *   "bneck_pair"  1 (default): 128-channel bottleneck tails run as cta_group::2 pairs; 0: one CTA per tile; 3: tests
  *   "bneck_release" 3 (default): the fused tails hand a residual slot back early in the next epilogue step (bit 0 im2col, bit 1 halo kernel)
  *   "gemm_pair"   1 (default): BLOCK_N = 256 GEMM / convolution layers run as cta_group::2 pairs; 0: off; 3: tests
+ *   "gemm_reverse" 1 (default): a GEMM layer walks its row blocks opposite to the launch before it (L2 reuse); 0: always ascending
  *   "dec0_const"  1 (default): decoder layer 0's frame-independent self-attention block runs once per plan; 0: every step
  *   (further measurement variants are listed in csrc/opd_core.cu). */
 int opd_set_option(const char* name, int32_t value);

@@ -508,8 +508,12 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
 
   auto act_bytes = [&](long long rows, int ch) { return (size_t)rows * ch * sizeof(bf16); };
   std::vector<Step>* sink = &steps;   // &plan->once while the frame-independent prologue is being planned
+  // Direction in which the previous launch walked its rows (false: ascending).  A GEMM layer walks the other way, so that it starts
+  // with the rows its producer wrote last, which are still in L2 (opd_set_option("gemm_reverse", 0): always ascending).
+  bool prev_reversed = false;
   auto add = [&](int kind, const std::string& name, double flops, double bytes, std::function<int(cudaStream_t)> fn) {
     sink->push_back(Step{std::move(fn), kind, flops, bytes, name});
+    prev_reversed = false;
   };
   const long long Ms = (long long)B * sh.Hs * sh.Ws, Mp = (long long)B * sh.Hp * sh.Wp;
 
@@ -584,13 +588,17 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   }
 
   std::string cur_name = "gemm";
-  auto add_gemm = [&](const GemmPlan& gp) {
+  auto add_gemm = [&](const GemmPlan& gp_in) {
+    GemmPlan gp = gp_in;
+    gp.reverse = g_option_gemm_reverse.load() && !prev_reversed;
+    const bool rev = gp.reverse != 0;
     // algorithmic traffic: A once (im2col: the input tensor once), W once, D (and D2 / residual) once
     const double a_bytes = gp.im2col ? 2.0 * gp.g.B * gp.g.H * gp.g.W * gp.g.C / (gp.g.stride * gp.g.stride > 1 && gp.g.KH == 1 ? gp.g.stride * gp.g.stride : 1)
                                      : 2.0 * gp.M * gp.K;
     const double bytes = a_bytes + 2.0 * gp.N * gp.K + 2.0 * gp.M * gp.N * (1 + (gp.has_d2 ? 1 : 0) + (gp.residual ? 1 : 0));
     add(gp.im2col ? OPD_STEP_CONV : OPD_STEP_GEMM, cur_name, 2.0 * gp.M * gp.N * gp.K, bytes,
         [gp](cudaStream_t s) { return gemm_launch(gp, s); });
+    prev_reversed = rev;
   };
   auto conv = [&](const bf16* x, int H, int W, const ConvW& c, bf16* y, int epi, const bf16* res) -> int {
     if (dry) return OPD_OK;

@@ -17,6 +17,7 @@ std::atomic<int> g_option_gemm_cluster{0};
 std::atomic<int> g_option_gemm_outbufs{1};
 std::atomic<int> g_option_pdl{0};
 std::atomic<int> g_option_gemm_pair{1};
+std::atomic<int> g_option_gemm_reverse{1};
 std::atomic<int> g_option_dec0_const{1};
 std::atomic<int> g_option_bneck_pair{1};
 std::atomic<int> g_option_bneck_release{3};
@@ -70,6 +71,10 @@ int opd_set_option(const char* name, int32_t value) {
   }
   if (name && std::string(name) == "dec0_const") {   // 1 (default): decoder layer 0's frame-independent self-attention block runs once per plan; 0: in every step; new plans only
     opd::g_option_dec0_const.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "gemm_reverse") {   // engine: 1 = a GEMM layer walks its m-blocks in the direction opposite to the launch before it (L2 reuse); 0 = always ascending; new plans only
+    opd::g_option_gemm_reverse.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "gemm_pair") {   // cta_group::2 GEMM: 0 off, 1 (default) BLOCK_N = 256 layers with a tile pair per cluster, 3 whenever BLOCK_N = 256 (tests); new plans only

@@ -84,6 +84,7 @@ __device__ __forceinline__ long long gclk() { return kGemmCounters ? clock64() :
 
 struct GemmParams {
   CUtensorMap tmA, tmB, tmD, tmD2, tmR, tmA2;
+  int reverse;   // m-blocks in descending order (see tile_mn)
   int M, N, K;
   int num_m_blocks, num_n_blocks, num_k_blocks;
   int k_split;           // k-blocks >= k_split come from tmA2 (1x1 strided im2col of a second tensor; geometry in P, Q, stride)
@@ -224,6 +225,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       m_blk = tile / p.num_n_blocks;
       n_blk = tile - m_blk * p.num_n_blocks;
     }
+    // reverse: rows from the last m-block down.  A layer that reads what the previous launch has just written starts with the
+    // rows that launch wrote last - the part of a multi-GB activation tensor that is still in L2.
+    if (p.reverse) m_blk = p.num_m_blocks - 1 - m_blk;
   };
 
   if (warp == 8) {
@@ -886,6 +890,7 @@ int gemm_plan_linear_plus_shortcut(GemmPlan* plan, const __nv_bfloat16* A, int K
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   GemmParams p;
   p.tmA = plan.tmA; p.tmB = plan.tmB; p.tmD = plan.tmD; p.tmD2 = plan.tmD2; p.tmR = plan.tmR;
+  p.reverse = plan.reverse;
   p.M = plan.M; p.N = plan.N; p.K = plan.K;
   p.num_m_blocks = (plan.M + BLOCK_M - 1) / BLOCK_M;
   p.num_n_blocks = plan.N / plan.block_n;

@@ -28,6 +28,7 @@ struct ConvGeom {
 };
 
 struct GemmPlan {
+  int reverse = 0;   // walk the m-blocks from the last one down (set by the engine for layers that follow an ascending writer)
   CUtensorMap tmA, tmB, tmD, tmD2, tmR;   // tmR: residual, read by TMA in 64-column chunks
   CUtensorMap tmA2;    // second A source (k-blocks >= k_split): NHWC tensor through a 1x1 / stride-s im2col map
   int k_split;         // k-blocks served by tmA; == K / 64 without a second source

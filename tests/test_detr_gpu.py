@@ -304,3 +304,25 @@ def test_decoder_layer0_prologue_is_bit_identical(detector):
     assert per_step == per_step_all - 6
     for (l, bx), (rl, rb) in zip(got, ref + ref[:1]):
         assert torch.equal(l, rl) and torch.equal(bx, rb)
+
+
+def test_reversed_row_order_is_bit_identical(detector):
+    """GEMM / convolution layers walk their row blocks in the direction opposite to the launch before them (the rows that launch
+    wrote last are still in L2).  Tiles are independent: logits and boxes must not change by a bit."""
+    import torch
+
+    from office_person_detection_vit_b200 import _lib
+
+    eng = detector.model
+    x = torch.from_numpy(do.synthetic_frames(3, 480, 640, seed=51)).cuda()
+    try:
+        _lib.check(_lib.lib().opd_set_option(b"gemm_reverse", 0), "opd_set_option")
+        eng.set_debug(False)                                  # drops the plan: the next forward plans with the option
+        ref = tuple(t.clone() for t in eng.forward(x))
+        _lib.check(_lib.lib().opd_set_option(b"gemm_reverse", 1), "opd_set_option")
+        eng.set_debug(False)
+        got = tuple(t.clone() for t in eng.forward(x))
+    finally:
+        _lib.lib().opd_set_option(b"gemm_reverse", 1)
+        eng.set_debug(False)
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
