@@ -1,4 +1,5 @@
-"""Timeline of CTA 0 of tc_bneck_kernel<128> (globaltimer stamps at the pipeline hand-offs)."""
+"""Timeline of CTA 0 of tc_bneck_kernel<128> (globaltimer stamps at the pipeline hand-offs).
+Needs a measurement build: OPD_EXTRA_NVCC_FLAGS="-DOPD_BNECK_PROBE" python -m office_person_detection_vit_b200.build -f"""
 import ctypes as C, sys, collections
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))

@@ -1,4 +1,5 @@
-"""Cycles per tcgen05.mma (128 x N x 16) by shape, swizzle, accumulator rotation and A-operand view (csrc/mma_probe.cu)."""
+"""Cycles per tcgen05.mma (128 x N x 16) by shape, swizzle, accumulator rotation and A-operand view (csrc/probe/mma_probe.cu,
+built into libopd_probe.so - not part of the product library)."""
 import sys
 from pathlib import Path
 
@@ -6,7 +7,12 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch  # noqa: E402
 
 from office_person_detection_vit_b200 import _lib  # noqa: E402
-from office_person_detection_vit_b200.detection import ops  # noqa: E402,F401  (registers opd_debug_mma_probe)
+import ctypes as C  # noqa: E402
+
+_lib.lib()   # the probe library links against libopd_b200.so
+_probe = C.CDLL(str(_lib.LIB_PATH.with_name("libopd_probe.so")))
+_probe.opd_debug_mma_probe.restype = C.c_int
+_probe.opd_debug_mma_probe.argtypes = [C.c_int32] * 10 + [C.c_void_p, C.c_void_p]
 
 out = torch.zeros(296, dtype=torch.int64, device="cuda")
 iters, grid = 2048, 148
@@ -14,7 +20,7 @@ iters, grid = 2048, 148
 
 def run(N, sw32, n_acc, walk, sbo=0, step=0, ld_iters=0, both=False, commit_every=0):
     for _ in range(2):
-        _lib.check(_lib.lib().opd_debug_mma_probe(N, sw32, n_acc, iters, walk, grid, sbo, step, ld_iters, commit_every, out.data_ptr(), None), "probe")
+        _lib.check(_probe.opd_debug_mma_probe(N, sw32, n_acc, iters, walk, grid, sbo, step, ld_iters, commit_every, out.data_ptr(), None), "probe")
     torch.cuda.synchronize()
     mma = out[:grid].float().median().item() / iters
     if both:

@@ -266,15 +266,6 @@ int opd_tps_transform_f64(const opd_tps_table* t, const double* in_dev, int32_t 
 int opd_undistort_points_f64(double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2, double k3,
                              const double* in_dev, int32_t input_is_bbox, int64_t N, double* out_dev, void* stream);
 
-/* Measurement probe (benchmarks/mma_probe.py), not on the product path: `iters` tcgen05.mma 128 x N x 16 issued by one
- * thread per CTA, rotating over n_acc TMEM accumulators, operands with 32-byte (swizzle32 = 1) or 128-byte swizzled rows;
- * a_sbo / a_step != 0: A is a shifted view (8-row groups a_sbo bytes apart, consecutive MMAs a_step bytes apart);
- * commit_every > 0: two tcgen05.commit after every commit_every MMAs;  ld_iters > 0: four more warps run that many tcgen05.ld 32x32b.x32 (+ wait) against the MMAs, their ticks go to
- * cycles_dev[grid .. 2 grid);  cycles_dev[grid] receives clock64 ticks from the first issue to the completion of the last. */
-int opd_debug_mma_probe(int32_t N, int32_t swizzle32, int32_t n_acc, int32_t iters, int32_t walk, int32_t grid,
-                        int32_t a_sbo, int32_t a_step, int32_t ld_iters, int32_t commit_every, uint64_t* cycles_dev,
-                        void* stream);
-
 #ifdef __cplusplus
 }
 #endif

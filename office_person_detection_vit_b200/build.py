@@ -17,6 +17,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libopd_b200.so"
+PROBE_LIB = PKG / "libopd_probe.so"      # measurement probes (csrc/probe/): a separate library, never loaded by the product path
 OBJ_DIR = PKG / "build"
 
 # measurement builds: OPD_EXTRA_NVCC_FLAGS="-DOPD_GEMM_PROBE -DOPD_STEM_PROBE" python -m office_person_detection_vit_b200.build
@@ -24,7 +25,7 @@ NVCC_FLAGS = os.environ.get("OPD_EXTRA_NVCC_FLAGS", "").split() + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-    f"-I{ROOT / 'include'}", f"-I{CSRC}",
+    f"-I{ROOT / 'include'}", f"-I{CSRC}", f"-I{CSRC / 'probe'}",
 ]
 
 
@@ -39,7 +40,8 @@ def _digest(src: Path) -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
     h.update(src.read_bytes())
-    for hdr in sorted(list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list((ROOT / "include").glob("*.h"))):
+    for hdr in sorted(list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list((CSRC / "probe").glob("*.h")) +
+                      list((ROOT / "include").glob("*.h"))):
         h.update(hdr.read_bytes())
     return h.hexdigest()
 
@@ -69,16 +71,24 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         stamp.write_text(dig)
         return obj, True
 
-    with ThreadPoolExecutor(max_workers=min(8, len(sources))) as pool:
-        results = list(pool.map(compile_one, sources))
-    objs = [o for o, _ in results]
-    if force or any(changed for _, changed in results) or not LIB.exists():
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *map(str, objs),
-               "-lcudart", "-ldl"]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            sys.stderr.write(res.stdout + res.stderr)
-            raise RuntimeError("link failed")
+    probes = sorted((CSRC / "probe").glob("*.cu"))
+    with ThreadPoolExecutor(max_workers=min(8, len(sources) + len(probes))) as pool:
+        results = list(pool.map(compile_one, sources + probes))
+    n = len(sources)
+
+    def link(lib: Path, res: list, extra: list[str]) -> None:
+        if force or any(changed for _, changed in res) or not lib.exists():
+            cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(lib), *[str(o) for o, _ in res],
+                   *extra, "-lcudart", "-ldl"]
+            out = subprocess.run(cmd, capture_output=True, text=True)
+            if out.returncode != 0:
+                sys.stderr.write(out.stdout + out.stderr)
+                raise RuntimeError(f"link of {lib.name} failed")
+
+    link(LIB, results[:n], [])
+    # the probes use the product library's helpers (error string, tensor maps): linked against it, found next to it at run time
+    link(PROBE_LIB, results[n:],
+         [f"-L{PKG}", "-lopd_b200", "-Xlinker", "-rpath=$ORIGIN"])
     return LIB
 
 

@@ -339,12 +339,13 @@ int attn_launch(const AttnPlan& plan, cudaStream_t stream) {
   AttnParams p;
   p.tmQ = plan.tmQ; p.tmK = plan.tmK; p.tmV = plan.tmV;
   p.o = plan.o; p.ldo = plan.ldo; p.Lq = plan.Lq; p.Lk = plan.Lk;
-  static bool configured = false;
-  if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128>::kSmemBytes));
-    OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::kSmemBytes));
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  if (int rc = once_per_device(configured, []() -> int {
+        OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128>::kSmemBytes));
+        OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::kSmemBytes));
+        return OPD_OK;
+      }))
+    return rc;
   dim3 grid((plan.Lq + kQ - 1) / kQ, plan.heads, plan.B);
   if (plan.kv_tile == 128)
     attention_tc_kernel<128><<<grid, kThreads, AttnCfg<128>::kSmemBytes, stream>>>(p);

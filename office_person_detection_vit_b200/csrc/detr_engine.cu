@@ -822,7 +822,9 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   if (const0) {
     const size_t each = (act_bytes(Mq, kD) + 1023) & ~(size_t)1023;
     if (m->dec0_bytes < 5 * each) {
-      if (m->dec0_buf) cudaFree(m->dec0_buf);
+      // a larger batch: a NEW buffer; the old one stays alive until opd_detr_destroy (a CUDA graph captured from an earlier plan
+      // may still read it)
+      if (m->dec0_buf) m->allocs.push_back(m->dec0_buf);
       m->dec0_buf = nullptr;
       m->dec0_bytes = 0;
       OPD_CUDA_OK(cudaMalloc(&m->dec0_buf, 5 * each));
@@ -893,7 +895,8 @@ extern "C" {
 
 int opd_detr_create(const opd_tensor_f32* tensors, int32_t n_tensors, int32_t device, opd_detr** out) {
   OPD_REQUIRE(tensors && n_tensors > 0 && out, "opd_detr_create: NULL argument");
-  OPD_CUDA_OK(cudaSetDevice(device));
+  opd::DeviceGuard guard(device);
+  OPD_CUDA_OK(guard.err);
   opd_detr* m = new opd_detr();
   m->device = device;
   const int rc = opd::load_weights(m, tensors, n_tensors);
@@ -957,6 +960,8 @@ int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t 
   OPD_REQUIRE(m && frames_dev && workspace_dev && logits_dev && boxes_dev, "opd_detr_forward: NULL argument");
   OPD_REQUIRE(B > 0 && (long long)B * opd::kQueries < (1 << 24), "opd_detr_forward: bad batch %d", B);
   OPD_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) == 0, "opd_detr_forward: workspace must be 1024-byte aligned");
+  opd::DeviceGuard guard(m->device);   // the handle's device, whatever the caller's current device is
+  OPD_CUDA_OK(guard.err);
   opd::Plan& p = m->plan;
   if (p.B != B || p.H0 != H0 || p.W0 != W0 || p.ws != workspace_dev || p.steps.empty()) {
     p = opd::Plan{};
@@ -991,6 +996,8 @@ int opd_detr_profile(opd_detr* m, void* stream, int32_t max_steps, int32_t* n_st
   OPD_REQUIRE(m && n_steps, "opd_detr_profile: NULL argument");
   opd::Plan& p = m->plan;
   OPD_REQUIRE(!p.steps.empty() && m->cur_frames, "opd_detr_profile: run opd_detr_forward first");
+  opd::DeviceGuard guard(m->device);
+  OPD_CUDA_OK(guard.err);
   const int n = (int)p.steps.size();
   *n_steps = n;
   if (max_steps <= 0) return OPD_OK;

@@ -260,14 +260,20 @@ __global__ void __launch_bounds__(256) floor_exact_kernel(const FloorK p, int ce
         static_cast<T*>(p.floor_mm)[2 * i + 1] = (T)__dmul_rn(py, p.sy);
       }
       if (p.in_bounds) p.in_bounds[i] = (0.0 <= px && px < p.mw && 0.0 <= py && py < p.mh) ? 1 : 0;
-      if (p.zone_idx || p.zone_mask || p.hist) {
+      // a row whose slot lies outside [0, T) is an UNUSED row (the padding rows of the detector's [B, 100] tables carry
+      // slot -1): it is neither classified nor counted, its zone index is -1 and its mask 0
+      const int s = p.slot ? p.slot[i] : 0;
+      const bool used = p.slot == nullptr || (unsigned)s < (unsigned)p.T;
+      if (!used) {
+        if (p.zone_idx) p.zone_idx[i] = -1;
+        if (p.zone_mask) p.zone_mask[i] = 0;
+      } else if (p.zone_idx || p.zone_mask || p.hist) {
         int win;
         const uint64_t mask = classify_exact(p, t, px, py, &win);
         if (p.zone_idx) p.zone_idx[i] = win;
         if (p.zone_mask) p.zone_mask[i] = mask;
         if (p.hist) {
-          const int s = p.slot ? p.slot[i] : 0;
-          if ((unsigned)s < (unsigned)p.T) {
+          {
             const int row = s * (p.Z + 1);
             if (mask == 0) {
               key = row + p.Z;  // aggregator.py:71-73 "unclassified"
@@ -337,7 +343,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
   unsigned* s_queue = reinterpret_cast<unsigned*>(cur);  // [32 warps][kWarpQueue]
   cur += (kFastThreads / 32) * kWarpQueue * 4;
   unsigned* s_whist = reinterpret_cast<unsigned*>(cur);  // [32 warps][64]: private counters, ATOMS.POPC.INC per point
-  for (int i = threadIdx.x; i < (kFastThreads / 32) * 64; i += kFastThreads) s_whist[i] = 0;
+  unsigned* s_extra = s_whist + (kFastThreads / 32) * 64;  // [32 warps]: counts beyond the first of points in several zones
+  for (int i = threadIdx.x; i < (kFastThreads / 32) * 65; i += kFastThreads) s_whist[i] = 0;
   __syncthreads();   // class_winner is staged
   {
     // winner grid: byte = selected zone of a uniform cell (kNoZone: none), kBoundary stays kBoundary
@@ -352,7 +359,9 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const uint32_t code = (w[j] >> (8 * b)) & 255u;
-          const int win = code == (uint32_t)kBoundary ? kBoundary : t.class_winner[code];
+          // allow_overlap tables: a uniform cell inside SEVERAL zones counts once per zone (aggregator.py:66-69) - float64 path
+          const bool multi = p.allow_overlap && code != (uint32_t)kBoundary && (t.class_mask[code] & (t.class_mask[code] - 1)) != 0;
+          const int win = (code == (uint32_t)kBoundary || multi) ? kBoundary : t.class_winner[code];
           o |= (uint32_t)(win < 0 ? kNoZone : win) << (8 * b);
         }
         w[j] = o;
@@ -383,9 +392,19 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
         double px, py;
         int win = -1;
         project_exact(p, (double)xy.x, (double)xy.y, &px, &py);
-        classify_exact(pg, t, px, py, &win);
+        uint64_t m = classify_exact(pg, t, px, py, &win);
         if (p.zone_idx) p.zone_idx[i] = win;
-        if (do_hist && win >= 0) atomicAdd(&wh[win], 1u);
+        if (do_hist && win >= 0) {
+          if (!p.allow_overlap) {
+            atomicAdd(&wh[win], 1u);
+          } else {   // one count per containing zone
+            atomicAdd(&s_extra[warp], (unsigned)__popcll(m) - 1u);
+            while (m) {
+              atomicAdd(&wh[__ffsll((long long)m) - 1], 1u);
+              m &= m - 1;
+            }
+          }
+        }
       }
       __syncwarp();
     }
@@ -500,6 +519,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
         atomicAdd(p.hist + threadIdx.x, (int)c);
         atomicSub(p.hist + p.Z, (int)c);
       }
+    }
+    if (threadIdx.x == 64) {   // points inside k zones were subtracted k times above
+      unsigned e = 0;
+      for (int w = 0; w < kFastThreads / 32; ++w) e += s_extra[w];
+      if (e) atomicAdd(p.hist + p.Z, (int)e);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.hist + p.Z, (int)p.N);
   }
@@ -747,7 +771,8 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
   memcpy(&blob[o_po], poly_off.data(), 68 * 4);
   memcpy(&blob[o_rk], rank.data(), 64 * 4);
 
-  cudaError_t e = cudaSetDevice(device);
+  opd::DeviceGuard guard(device);
+  cudaError_t e = guard.err;
   if (e == cudaSuccess) e = cudaMalloc(&zt->d_blob, total);
   if (e == cudaSuccess) e = cudaMemcpy(zt->d_blob, blob.data(), total, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -822,12 +847,12 @@ int fill_params(FloorK& k, const opd_floor_params* p, const opd_zone_table* zt, 
 }
 
 int device_sm_count(int device, int* sms) {
-  static int cached_dev = -1, cached = 0;
-  if (cached_dev != device) {
-    OPD_CUDA_OK(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, device));
-    cached_dev = device;
-  }
-  *sms = cached;
+  static std::mutex mu;
+  static int cached[opd::kMaxDevices] = {0};
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= opd::kMaxDevices) return opd::fail(OPD_ERR_INVALID, "floor: device %d out of range", device);
+  if (cached[device] <= 0) OPD_CUDA_OK(cudaDeviceGetAttribute(&cached[device], cudaDevAttrMultiProcessorCount, device));
+  *sms = cached[device];
   return OPD_OK;
 }
 
@@ -898,7 +923,7 @@ extern "C" int opd_floor_project_classify_count_f32(const opd_floor_params* p, c
   if (int rc = device_sm_count(zt->device, &sms)) return rc;
   k.stage_grid = 1;
   const size_t smem = (size_t)zt->cells_rounded + (tables_smem_bytes(0, zt->cells_rounded, k.stage_verts, k.n_verts) + 15) / 16 * 16 +
-                      (kFastThreads / 32) * kWarpQueue * 4 + (kFastThreads / 32) * 64 * 4 + 16;
+                      (kFastThreads / 32) * kWarpQueue * 4 + (kFastThreads / 32) * 65 * 4 + 16;
   auto kern = floor_fast_kernel;
   OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long chunks = (N + kFastChunk - 1) / kFastChunk;

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 
 #include "opd_b200.h"
@@ -43,6 +44,59 @@ inline int fail(int code, const char* fmt, ...) {
 }
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// cudaFuncSetAttribute and the occupancy / SM-count queries are per DEVICE: one-time setup and cached limits are keyed by
+// the current device (handles of several devices may live in one process) and guarded by a mutex (handles are used from
+// several threads).
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  std::mutex mu;
+  uint64_t done = 0;
+};
+template <typename F>
+inline int once_per_device(PerDeviceOnce& o, F&& setup) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return setup();
+  std::lock_guard<std::mutex> lk(o.mu);
+  if ((o.done >> d) & 1ull) return 0;
+  const int rc = setup();
+  if (rc == 0) o.done |= 1ull << d;
+  return rc;
+}
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards (handles are bound to one
+// device; the caller's current device is not ours to change).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;   // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+struct PerDeviceInt {   // cached per-device integer, -1 = not yet computed
+  std::mutex mu;
+  int v[kMaxDevices];
+  PerDeviceInt() { for (int& x : v) x = -1; }
+};
+template <typename F>
+inline int cached_per_device(PerDeviceInt& c, int* out, F&& compute) {   // compute(int* value) -> status
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return compute(out);
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (c.v[d] < 0) {
+    int val = -1;
+    if (int rc = compute(&val)) return rc;
+    c.v[d] = val;
+  }
+  *out = c.v[d];
+  return 0;
+}
 
 }  // namespace opd
 

@@ -4,6 +4,7 @@
 // tile the previous one wrote), and whether consecutive MMAs read the same or different shared-memory operand tiles.
 // One CTA per SM, one issuing thread, operands are whatever the shared memory holds (values do not matter for timing).
 #include "opd_common.h"
+#include "opd_probe.h"
 #include "sm100_ptx.cuh"
 
 namespace opd {

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(256) pwa_transform_kernel(const PwaK p, int st
 extern "C" int opd_pwa_table_create(const double* bary /*[T,3,2]*/, const double* affine /*[T,2,3]*/, const double* centroids /*[T,2]*/,
                                     int32_t T, double eps, int32_t device, opd_pwa_table** out) {
   OPD_REQUIRE(bary && affine && centroids && out && T > 0, "opd_pwa_table_create: bad argument (T=%d)", T);
-  OPD_CUDA_OK(cudaSetDevice(device));
+  opd::DeviceGuard guard(device);
+  OPD_CUDA_OK(guard.err);
   std::vector<double> h((size_t)T * kTriDoubles);
   for (int t = 0; t < T; ++t) {
     double* q = h.data() + (size_t)t * kTriDoubles;
@@ -297,11 +298,12 @@ extern "C" int opd_pwa_transform_f64(const opd_pwa_table* t, const double* in_de
          floor_px_dev, floor_mm_dev, in_bounds_dev, tri_idx_dev, extrapolated_dev};
   const int stage = t->T <= kMaxSmemTris;
   const size_t smem = stage ? (size_t)t->T * kTriDoubles * sizeof(double) : 0;
-  static bool configured = false;
-  if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(pwa_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTris * kTriDoubles * 8));
-    configured = true;
-  }
+  static opd::PerDeviceOnce configured;
+  if (int rc = opd::once_per_device(configured, []() -> int {
+        OPD_CUDA_OK(cudaFuncSetAttribute(pwa_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTris * kTriDoubles * 8));
+        return OPD_OK;
+      }))
+    return rc;
   const long long blocks = std::min<long long>((N + 255) / 256, 148LL * 8);
   pwa_transform_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(k, stage);
   opd::count_launch();
@@ -381,7 +383,8 @@ extern "C" int opd_tps_table_create(const double* src_points /*[n,2]*/, const do
                                     opd_tps_table** out) {
   OPD_REQUIRE(src_points && weights_x && weights_y && affine_x && affine_y && out && n > 0 && n <= 4096,
               "opd_tps_table_create: bad argument (n=%d, at most 4096 control points)", n);
-  OPD_CUDA_OK(cudaSetDevice(device));
+  opd::DeviceGuard guard(device);
+  OPD_CUDA_OK(guard.err);
   std::vector<double> h((size_t)n * 4);
   for (int i = 0; i < n; ++i) {
     h[4 * i + 0] = src_points[2 * i];
@@ -419,11 +422,12 @@ extern "C" int opd_tps_transform_f64(const opd_tps_table* t, const double* in_de
   TpsK k{t->d_ctrl, t->n, t->ax[0], t->ax[1], t->ax[2], t->ay[0], t->ay[1], t->ay[2], in_dev, input_is_bbox, (long long)N,
          scale_x_mm, scale_y_mm, map_w_px, map_h_px, floor_px_dev, floor_mm_dev, in_bounds_dev};
   const size_t smem = (size_t)t->n * 4 * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(tps_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 4 * 8));
-    configured = true;
-  }
+  static opd::PerDeviceOnce configured;
+  if (int rc = opd::once_per_device(configured, []() -> int {
+        OPD_CUDA_OK(cudaFuncSetAttribute(tps_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 4 * 8));
+        return OPD_OK;
+      }))
+    return rc;
   const long long blocks = std::min<long long>((N + 255) / 256, 148LL * 8);
   tps_transform_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(k);
   opd::count_launch();

@@ -481,12 +481,13 @@ int stem_launch(const StemPlan& plan, cudaStream_t stream) {
   p.pooled = plan.pooled;
   p.H2 = plan.H2; p.W2 = plan.W2; p.P = plan.P; p.Q = plan.Q;
   p.probe = g_option_probe.load();
-  static bool configured = false;
-  if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBytes));
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  if (int rc = once_per_device(configured, []() -> int {
+        OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        OPD_CUDA_OK(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBytes));
+        return OPD_OK;
+      }))
+    return rc;
   if (pool)
     stem_kernel<true><<<plan.grid, kPoolThreads, kPoolSmemBytes, stream>>>(p);
   else

@@ -73,7 +73,7 @@ constexpr bool kBneckProbe = false;   // -DOPD_BNECK_PROBE: clock64 counters of 
 __device__ __forceinline__ long long pclk() { return kBneckProbe ? clock64() : 0; }
 
 __device__ __forceinline__ void trace_ev(unsigned long long* tr, int id) {
-  if (tr && blockIdx.x == 0) {
+  if (kBneckProbe && tr && blockIdx.x == 0) {   // timeline trace: measurement builds only (-DOPD_BNECK_PROBE)
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     const unsigned long long i = atomicAdd(tr, 1ull);
@@ -531,12 +531,13 @@ unsigned long long* g_bneck_trace = nullptr;
 
 template <int MID>
 int launch_t(const BneckParams& p, int grid, cudaStream_t s) {
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = tc_bneck_kernel<MID, false>;
-  if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MID>::kSmemBytes));
-    configured = true;
-  }
+  if (int rc = once_per_device(configured, [&]() -> int {
+        OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MID>::kSmemBytes));
+        return OPD_OK;
+      }))
+    return rc;
   kern<<<grid, kThreads, Cfg<MID>::kSmemBytes, s>>>(p);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
@@ -546,7 +547,8 @@ int launch_t(const BneckParams& p, int grid, cudaStream_t s) {
 // cta_group::2 variant: clusters of two CTAs, as many pairs as fit (GPCs with an odd SM count leave one SM without a partner)
 int launch_pair(const BneckParams& p, int grid, cudaStream_t s) {
   auto kern = tc_bneck_kernel<128, true>;
-  static int max_clusters = -1;
+  static PerDeviceInt cluster_limit;
+  int max_clusters = -1;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -558,13 +560,13 @@ int launch_pair(const BneckParams& p, int grid, cudaStream_t s) {
   cfg.stream = s;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (max_clusters < 0) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128, true>::kSmemBytes));
-    cfg.gridDim = dim3(sm_count() / 2 * 2);
-    int n = 0;
-    OPD_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-    max_clusters = n;
-  }
+  if (int rc = cached_per_device(cluster_limit, &max_clusters, [&](int* n) -> int {
+        OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128, true>::kSmemBytes));
+        cfg.gridDim = dim3(sm_count() / 2 * 2);
+        OPD_CUDA_OK(cudaOccupancyMaxActiveClusters(n, kern, &cfg));
+        return OPD_OK;
+      }))
+    return rc;
   OPD_REQUIRE(max_clusters > 0, "bottleneck tail: no 2-CTA cluster of the kernel fits on this device");
   cfg.gridDim = dim3(2 * std::min(grid / 2, max_clusters));
   OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
@@ -633,8 +635,11 @@ extern "C" int opd_bottleneck_tail_bf16(const void* x_dev, int32_t B, int32_t H,
   return opd::bneck_launch(plan, static_cast<cudaStream_t>(stream));
 }
 
-// debug: timeline trace of CTA 0 of the next tc_bneck_kernel launches (device buffer of >= 4001 uint64, [0] zeroed)
+#ifdef OPD_BNECK_PROBE
+// measurement builds only (benchmarks/bneck_trace.py): timeline trace of CTA 0 of the next tc_bneck_kernel launches
+// (device buffer of >= 4001 uint64, [0] zeroed)
 extern "C" int opd_debug_set_bneck_trace(unsigned long long* buf_dev) {
   opd::g_bneck_trace_set(buf_dev);
   return 0;
 }
+#endif

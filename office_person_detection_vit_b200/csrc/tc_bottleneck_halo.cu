@@ -557,13 +557,14 @@ int bneck_halo_launch(const BneckPlan& plan, cudaStream_t stream) {
   p.bias2 = plan.bias2;
   p.bias3 = plan.bias3;
   p.early_release = (g_option_bneck_release.load() & 2) != 0;
-  static bool configured = false;
-  if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::kSmemBytes));
-    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::kSmemBytes));
-    OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<128>::kSmemBytes));
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  if (int rc = once_per_device(configured, []() -> int {
+        OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::kSmemBytes));
+        OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<64>::kSmemBytes));
+        OPD_CUDA_OK(cudaFuncSetAttribute(tc_bneck_halo_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<128>::kSmemBytes));
+        return OPD_OK;
+      }))
+    return rc;
   if (plan.mid == 128)
     tc_bneck_halo_kernel<128, false><<<plan.grid, kThreads, HaloCfg<128>::kSmemBytes, stream>>>(p);
   else if (plan.fused_shortcut)

@@ -673,6 +673,21 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols,
   return OPD_OK;
 }
 
+// 4D tiled map over an NHWC bf16 tensor: box = [64 channels, box_w, box_h, 1 image], 128-byte swizzle, zero fill (halo patches
+// of the stem / stage-1 kernels; out-of-image pixels read as the convolution's zero padding)
+int make_tmap_nhwc_patch(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, int box_w, int box_h) {
+  if (int rc = load_driver_entry_points()) return rc;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OPD_ERR_CUDA, "cuTensorMapEncodeTiled (nhwc patch) failed (%d)", (int)r);
+  return OPD_OK;
+}
+
 int make_tmap_im2col(CUtensorMap* tm, const void* ptr, const ConvGeom& g) {
   if (int rc = load_driver_entry_points()) return rc;
   OPD_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && g.C % 64 == 0, "im2col map: C=%d must be a multiple of 64",
@@ -710,14 +725,15 @@ namespace {
 
 template <int BLOCK_N, bool kHasRes, bool kBRes = false, int kOutBufs = 1, int kMTiles = 1>
 int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, kBRes, 1, kOutBufs, kMTiles>;
   constexpr int smem = smem_bytes_for(BLOCK_N, kHasRes, kBRes, kOutBufs, kMTiles);
   static_assert(stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs, kMTiles) >= 2, "ring too shallow");
-  if (!configured) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  if (int rc = once_per_device(configured, [&]() -> int {
+        OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        return OPD_OK;
+      }))
+    return rc;
   if (g_option_pdl.load()) {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -741,7 +757,8 @@ int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
 template <int BLOCK_N, bool kHasRes, bool kPair = false>
 int launch_cluster2(const GemmParams& p, int grid, cudaStream_t s) {
   auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, false, 2, 1, 1, kPair>;
-  static int max_clusters = -1;
+  static PerDeviceInt cluster_limit;
+  int max_clusters = -1;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -753,13 +770,13 @@ int launch_cluster2(const GemmParams& p, int grid, cudaStream_t s) {
   cfg.stream = s;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (max_clusters < 0) {
-    OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes, false, 1, 1, kPair)));
-    cfg.gridDim = dim3(sm_count() / 2 * 2);
-    int n = 0;
-    OPD_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));   // GPCs with an odd SM count leave one SM without a partner
-    max_clusters = n;
-  }
+  if (int rc = cached_per_device(cluster_limit, &max_clusters, [&](int* n) -> int {
+        OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes, false, 1, 1, kPair)));
+        cfg.gridDim = dim3(sm_count() / 2 * 2);
+        OPD_CUDA_OK(cudaOccupancyMaxActiveClusters(n, kern, &cfg));   // GPCs with an odd SM count leave one SM without a partner
+        return OPD_OK;
+      }))
+    return rc;
   OPD_REQUIRE(max_clusters > 0, "gemm: no 2-CTA cluster of the tensor-core kernel fits on this device");
   cfg.gridDim = dim3(2 * std::min(grid / 2, max_clusters));
   OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
@@ -805,13 +822,15 @@ int finish_plan(GemmPlan* plan) {
 
 }  // namespace
 
-int sm_count() {
-  static int sms = 0;
-  if (!sms) {
+int sm_count() {   // of the current device
+  static PerDeviceInt cache;
+  int sms = 148;
+  cached_per_device(cache, &sms, [](int* n) -> int {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
+    if (cudaDeviceGetAttribute(n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || *n <= 0) *n = 148;
+    return OPD_OK;
+  });
   return sms;
 }
 

@@ -19,9 +19,6 @@ _lib.register("opd_attention_bf16", C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, 
 _lib.register("opd_bottleneck_tail_bf16", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P,
                                                    C.c_int32, _P, _P, _P])
 
-# measurement probe (benchmarks/mma_probe.py)
-_lib.register("opd_debug_mma_probe", C.c_int, [C.c_int32] * 10 + [_P, _P])
-
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_BIAS_RES_LN = 0, 1, 2, 3
 
 

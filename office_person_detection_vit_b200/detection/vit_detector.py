@@ -147,9 +147,10 @@ class DetrEngine:
             logits = torch.empty(B, N_QUERIES, N_LOGITS, dtype=torch.float32, device=frames.device)
         if boxes is None:
             boxes = torch.empty(B, N_QUERIES, 4, dtype=torch.float32, device=frames.device)
-        rc = _lib.lib().opd_detr_forward(self._h, frames.data_ptr(), B, H0, W0, int(bgr), base,
-                                         ws.numel() - (base - ws.data_ptr()), logits.data_ptr(), boxes.data_ptr(),
-                                         _lib.stream_ptr())
+        with torch.cuda.device(self.device_index):   # the stream of the ENGINE's device, whatever the caller's current device is
+            rc = _lib.lib().opd_detr_forward(self._h, frames.data_ptr(), B, H0, W0, int(bgr), base,
+                                             ws.numel() - (base - ws.data_ptr()), logits.data_ptr(), boxes.data_ptr(),
+                                             _lib.stream_ptr())
         _lib.check(rc, "opd_detr_forward")
         return logits, boxes
 
@@ -159,13 +160,14 @@ class DetrEngine:
         """One more forward with the last forward's arguments, a CUDA event between consecutive launches.
         -> [{name, kind, ms, flops, bytes}] per launch (algorithmic flops / bytes).  Synchronises."""
         n = C.c_int32()
-        _lib.check(_lib.lib().opd_detr_profile(self._h, _lib.stream_ptr(), 0, C.byref(n), None, None, None, None, None, 0),
-                   "opd_detr_profile")
-        k = n.value
-        kinds, flops, nbytes, ms = (C.c_int32 * k)(), (C.c_double * k)(), (C.c_double * k)(), (C.c_float * k)()
-        names = C.create_string_buffer(k * 48)
-        _lib.check(_lib.lib().opd_detr_profile(self._h, _lib.stream_ptr(), k, C.byref(n), kinds, flops, nbytes, ms, names, 48),
-                   "opd_detr_profile")
+        with self._torch.cuda.device(self.device_index):
+            _lib.check(_lib.lib().opd_detr_profile(self._h, _lib.stream_ptr(), 0, C.byref(n), None, None, None, None, None, 0),
+                       "opd_detr_profile")
+            k = n.value
+            kinds, flops, nbytes, ms = (C.c_int32 * k)(), (C.c_double * k)(), (C.c_double * k)(), (C.c_float * k)()
+            names = C.create_string_buffer(k * 48)
+            _lib.check(_lib.lib().opd_detr_profile(self._h, _lib.stream_ptr(), k, C.byref(n), kinds, flops, nbytes, ms, names, 48),
+                       "opd_detr_profile")
         raw = names.raw
         return [{"name": raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode(), "kind": self.STEP_KINDS[kinds[i]],
                  "ms": float(ms[i]), "flops": float(flops[i]), "bytes": float(nbytes[i])} for i in range(k)]
@@ -178,8 +180,9 @@ class DetrEngine:
                    "opd_detr_tap")
         dt = {0: torch.bfloat16, 1: torch.float32, 2: torch.uint8}[f32.value]
         out = torch.empty(rows.value, cols.value, dtype=dt, device=f"cuda:{self.device_index}")
-        _lib.check(_lib.lib().opd_detr_tap_copy(self._h, name.encode(), out.data_ptr(), out.numel() * out.element_size(),
-                                                _lib.stream_ptr()), "opd_detr_tap_copy")
+        with torch.cuda.device(self.device_index):
+            _lib.check(_lib.lib().opd_detr_tap_copy(self._h, name.encode(), out.data_ptr(), out.numel() * out.element_size(),
+                                                    _lib.stream_ptr()), "opd_detr_tap_copy")
         return out
 
     def roi_features(self, det_xywh, n_keep, h0: int, w0: int):
@@ -195,8 +198,9 @@ class DetrEngine:
         if not (det_xywh.is_cuda and det_xywh.dtype == torch.float64 and det_xywh.is_contiguous() and n_keep.dtype == torch.int32):
             raise ValueError("roi_features: det_xywh must be a contiguous float64 CUDA tensor, n_keep int32")
         out = torch.empty(B, Q, cols.value, dtype=torch.float32, device=det_xywh.device)
-        rc = _lib.lib().opd_roi_features_bf16(p.value, B, fh, fw, cols.value, det_xywh.data_ptr(), n_keep.data_ptr(), Q, h0, w0,
-                                              out.data_ptr(), _lib.stream_ptr())
+        with torch.cuda.device(self.device_index):
+            rc = _lib.lib().opd_roi_features_bf16(p.value, B, fh, fw, cols.value, det_xywh.data_ptr(), n_keep.data_ptr(), Q, h0, w0,
+                                                  out.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "opd_roi_features_bf16")
         return out
 
@@ -225,11 +229,12 @@ def postprocess_tensors(logits, boxes, h0: int, w0: int, threshold: float, perso
         "n_keep": torch.empty(B, dtype=torch.int32, device=dev),
         "det_slot": torch.empty(B, Q, dtype=torch.int32, device=dev),
     }
-    rc = _lib.lib().opd_detr_postprocess(
-        logits.data_ptr(), boxes.data_ptr(), B, Q, Cn, h0, w0, float(threshold), person_label,
-        out["scores"].data_ptr(), out["labels"].data_ptr(), out["xyxy"].data_ptr(), out["det_xywh"].data_ptr(),
-        out["det_score"].data_ptr(), out["det_foot"].data_ptr(), out["det_query"].data_ptr(), out["n_keep"].data_ptr(),
-        out["det_slot"].data_ptr(), int(slot_base), _lib.stream_ptr())
+    with torch.cuda.device(dev):
+        rc = _lib.lib().opd_detr_postprocess(
+            logits.data_ptr(), boxes.data_ptr(), B, Q, Cn, h0, w0, float(threshold), person_label,
+            out["scores"].data_ptr(), out["labels"].data_ptr(), out["xyxy"].data_ptr(), out["det_xywh"].data_ptr(),
+            out["det_score"].data_ptr(), out["det_foot"].data_ptr(), out["det_query"].data_ptr(), out["n_keep"].data_ptr(),
+            out["det_slot"].data_ptr(), int(slot_base), _lib.stream_ptr())
     _lib.check(rc, "opd_detr_postprocess")
     return out
 

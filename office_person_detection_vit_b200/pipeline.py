@@ -19,7 +19,8 @@ class DetectCountPipeline:
 
     def run_tensors(self, frames, hist=None, slot_base: int = 0, threshold: float | None = None, bgr: bool = True) -> dict:
         """frames [B,H,W,3] uint8 CUDA -> dict of device tensors: everything `ViTDetector.detect_tensors` returns plus
-        `zone_idx` [B,100] (-1 = unclassified / unused row) and `hist` [T, Z+1] int32, accumulated at rows
+        `zone_idx` [B,100] (-1 = unclassified, and -1 for the unused rows >= n_keep[b]: their slot is -1 and the floor kernel
+        neither classifies nor counts them) and `hist` [T, Z+1] int32, accumulated at rows
         slot_base .. slot_base+B-1 (allocated as [B, Z+1] when not given).  No host synchronisation."""
         torch = _lib.require_cuda()
         B = frames.shape[0]
@@ -69,7 +70,8 @@ class DetectCountPipeline:
         src/pipeline/orchestrator.py:155-202, src/pipeline/phases/detection.py:91-94): `batches` yields host batches - uint8
         [B,H,W,3] NumPy arrays or torch tensors of one size - and this generator yields `run_tensors` results, with batch i+1
         staged into pinned memory and copied to the device on a second stream while batch i runs (two pinned and two device
-        buffers).  Batch i's timestamp rows are slot_base + i * B ..; `hist` (if given) must hold every batch's rows."""
+        buffers).  Batch i's timestamp rows follow batch i - 1's (a running offset: batches may differ in size, e.g. a short
+        last one); `hist` (if given) must hold every batch's rows."""
         torch = _lib.require_cuda()
         dev = torch.device("cuda", torch.cuda.current_device())
         copy_stream = torch.cuda.Stream(device=dev)
@@ -102,6 +104,7 @@ class DetectCountPipeline:
         it = iter(batches)
         nxt = next(it, None)
         i = 0
+        slot = slot_base
         if nxt is not None:
             stage(0, nxt)
         while nxt is not None:
@@ -111,10 +114,11 @@ class DetectCountPipeline:
                 stage(i + 1, nxt)
             main.wait_event(ready[cur_k])
             B = device_bufs[cur_k].shape[0]
-            out = self.run_tensors(device_bufs[cur_k], hist=hist, slot_base=slot_base + i * B, threshold=threshold, bgr=bgr)
+            out = self.run_tensors(device_bufs[cur_k], hist=hist, slot_base=slot, threshold=threshold, bgr=bgr)
             consumed[cur_k].record(main)
             yield out
             i += 1
+            slot += B
 
     def all_reduce(self, hist):
         """Sum the per-timestamp histograms over all ranks (the path's only collective)."""

@@ -16,12 +16,27 @@ def _declared_symbols() -> set[str]:
     return set(re.findall(r"\b(opd_[a-z0-9_]+)\s*\(", text))
 
 
+def _exported_c_symbols(lib_path) -> set[str]:
+    out = subprocess.run(["nm", "-D", "--defined-only", str(lib_path)], capture_output=True, text=True, check=True).stdout
+    return {ln.split()[-1] for ln in out.splitlines() if len(ln.split()) >= 3 and ln.split()[-2] in "TW" and
+            ln.split()[-1].startswith("opd_")}
+
+
 def test_header_symbols_exported(built_lib):
     lib = ctypes.CDLL(str(built_lib))
     declared = _declared_symbols()
     assert declared, "no declarations parsed from include/opd_b200.h"
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"declared in the header but not exported: {missing}"
+    # ... and nothing else: the C ABI of the product library is exactly the header (measurement probes live in libopd_probe.so)
+    assert _exported_c_symbols(built_lib) == declared
+
+
+def test_probe_library_is_separate(built_lib):
+    probe = built_lib.with_name("libopd_probe.so")
+    assert probe.exists()
+    assert _exported_c_symbols(probe) == {"opd_debug_mma_probe", "opd_halo_conv3x3_test"}
+    assert not (_exported_c_symbols(built_lib) & _exported_c_symbols(probe))
 
 
 def test_python_binding_covers_header(built_lib):

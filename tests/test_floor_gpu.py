@@ -143,6 +143,47 @@ def test_fast_kernel_ragged_tail_and_idempotence(torch_cuda, built_lib):
         assert torch.equal(again, 2 * hist)
 
 
+def test_fast_kernel_overlapping_zones(torch_cuda, built_lib):
+    """allow_overlap=True (the class default) on zones that really overlap: the filtered kernel (N >= 65536, no slots) must count a
+    point once in EVERY containing zone (aggregator.py:66-69), like the exact kernel and the oracle - ADVICE r1."""
+    torch = torch_cuda
+    zones = fo.star_zones(16, seed=2)               # 3 deliberately overlapping pairs
+    zones += [{"id": "big", "polygon": [[300.0, 200.0], [1500.0, 250.0], [1400.0, 1100.0], [350.0, 1000.0]], "priority": 99}]
+    Z = len(zones)
+    for allow in (True, False):
+        tr, zc = _engines(fo.H_CONFIG, zones, allow)
+        for n in (1 << 17, (1 << 17) + 77):
+            pts = fo.camera_points(n, seed=21)
+            d = torch.from_numpy(pts).cuda()
+            hist, idx = zc.count(d, transformer=tr, return_index=True)                       # fast kernel
+            masks = zc.classify_masks(d, transformer=tr).cpu().numpy().astype(np.uint64)     # exact kernel
+            slot = torch.zeros(n, dtype=torch.int32, device="cuda")
+            hist_exact, idx_exact = zc.count(d, slot=slot, num_slots=1, transformer=tr, return_index=True)   # exact kernel
+            assert torch.equal(idx, idx_exact)
+            assert torch.equal(hist, hist_exact)
+            exp = np.array([int(((masks >> np.uint64(z)) & np.uint64(1)).sum()) for z in range(Z)] + [int((masks == 0).sum())])
+            assert (hist.cpu().numpy()[0] == exp).all()
+            if allow:
+                assert ((masks & (masks - np.uint64(1))) != 0).sum() > 1000      # the case under test really occurs
+                assert int(hist.sum()) > n
+            exp_idx, _ = fo.project_classify_count(fo.H_CONFIG, pts, zones)
+            assert (idx.cpu().numpy() != exp_idx).sum() <= 2
+            assert torch.equal(zc.count(d, transformer=tr), hist)                          # count-only launch
+
+
+def test_unused_rows_are_not_classified(torch_cuda, built_lib):
+    """Rows whose slot is outside [0, T) (the padding rows of the detector's [B, 100] tables: foot (0, 0), slot -1) get zone
+    index -1 / mask 0 and no count, wherever H maps them."""
+    torch = torch_cuda
+    zones = [{"id": "all", "polygon": [[-1e6, -1e6], [1e6, -1e6], [1e6, 1e6], [-1e6, 1e6]]}]
+    tr, zc = _engines(np.eye(3), zones, False)
+    pts = torch.zeros(8, 2, dtype=torch.float64, device="cuda")
+    slot = torch.tensor([0, -1, 1, -1, 5, 1, -1, 0], dtype=torch.int32, device="cuda")
+    hist, idx = zc.count(pts, slot=slot, num_slots=2, transformer=tr, return_index=True)
+    assert idx.cpu().tolist() == [0, -1, 0, -1, -1, 0, -1, 0]
+    assert hist.cpu().tolist() == [[2, 0], [2, 0]]
+
+
 def test_degenerate_points(torch_cuda, built_lib):
     """Points on the horizon (W = 0) and NaN/inf inputs are unclassified, as in the reference (every comparison
     with NaN is False); a huge finite point still projects to a finite ratio X/W and is classified like the oracle."""
