@@ -221,6 +221,13 @@ int opd_detr_postprocess(const float* logits_dev, const float* boxes_dev, int32_
                          double* det_foot_dev, int32_t* det_query_dev, int32_t* n_keep_dev, int32_t* det_slot_dev,
                          int32_t slot_base, void* stream);
 
+/* Synthetic frames generated on the device ("100 000 synthetic timelapse frames generated on device per
+ * rank from seed = 1000 + global_frame_idx // 64", no host I/O in the timed region): frames_dev [B,H,W,3] uint8, frame b is global
+ * frame global_frame0 + b, drawn from a counter-based hash of (seed_base + g / 64, g % 64, y, x, c) - large flat-colour blocks,
+ * finer blocks and pixel noise like detection/synthetic.py synthetic_frames (its device_frames_reference restates the kernel). */
+int opd_synthetic_frames_u8(uint64_t seed_base, int64_t global_frame0, int32_t B, int32_t H, int32_t W, uint8_t* frames_dev,
+                            void* stream);
+
 /* ROI features of the compacted detections (the removed ViTDetector.extract_features / _extract_features_from_outputs,
  * coverage.json method table; arithmetic of FeatureExtractor.extract_roi_features + normalize_features,
  * src/tracking/feature_extractor.py:39-88, :21-37): feat_dev [B, fh, fw, D] bf16 = the encoder output of the last

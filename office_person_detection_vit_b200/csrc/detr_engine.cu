@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <list>
 #include <map>
 #include <string>
 #include <vector>
@@ -109,10 +110,19 @@ struct opd_detr {
   int cur_bgr = 1;
   float* cur_logits = nullptr;
   float* cur_boxes = nullptr;
-  opd::Plan plan;
-  void* dec0_buf = nullptr;   // outputs of the frame-independent prologue (owned by the model, not the caller's workspace)
-  size_t dec0_bytes = 0;
+  // Launch plans, most recently used first, one per (B, H0, W0, workspace): a stream that alternates between batch shapes (a short
+  // last batch, frames of two sizes) re-encodes no tensor maps.  `plan` is the plan of the last forward (taps, profile).
+  std::list<opd::Plan> plans;
+  opd::Plan* plan = nullptr;
+  // outputs of the frame-independent prologue, per batch size (owned by the model, not the caller's workspace; never freed before
+  // opd_detr_destroy: a CUDA graph captured from an evicted plan may still read them)
+  std::map<int, void*> dec0_bufs;
+  void drop_plans() {
+    plans.clear();
+    plan = nullptr;
+  }
 };
+constexpr size_t kMaxPlans = 8;
 
 namespace opd {
 namespace {
@@ -821,16 +831,9 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   bf16 *c_y = dy, *c_yp = dyp, *c_y1 = dy1, *c_q = dq;   // layer-0 inputs / outputs of the prologue
   if (const0) {
     const size_t each = (act_bytes(Mq, kD) + 1023) & ~(size_t)1023;
-    if (m->dec0_bytes < 5 * each) {
-      // a larger batch: a NEW buffer; the old one stays alive until opd_detr_destroy (a CUDA graph captured from an earlier plan
-      // may still read it)
-      if (m->dec0_buf) m->allocs.push_back(m->dec0_buf);
-      m->dec0_buf = nullptr;
-      m->dec0_bytes = 0;
-      OPD_CUDA_OK(cudaMalloc(&m->dec0_buf, 5 * each));
-      m->dec0_bytes = 5 * each;
-    }
-    uint8_t* cb = static_cast<uint8_t*>(m->dec0_buf);
+    void*& buf = m->dec0_bufs[B];   // contents depend on the weights and B only: plans of the same batch size share it
+    if (!buf) OPD_CUDA_OK(cudaMalloc(&buf, 5 * each));
+    uint8_t* cb = static_cast<uint8_t*>(buf);
     c_y = reinterpret_cast<bf16*>(cb);               // zeros
     bf16* c_yp0 = reinterpret_cast<bf16*>(cb + each);   // query positions
     c_y1 = reinterpret_cast<bf16*>(cb + 2 * each);   // after self attention + LayerNorm
@@ -912,14 +915,15 @@ int opd_detr_create(const opd_tensor_f32* tensors, int32_t n_tensors, int32_t de
 void opd_detr_destroy(opd_detr* m) {
   if (!m) return;
   for (void* p : m->allocs) cudaFree(p);
-  if (m->dec0_buf) cudaFree(m->dec0_buf);
+  for (auto& kv : m->dec0_bufs)
+    if (kv.second) cudaFree(kv.second);
   delete m;
 }
 
 int opd_detr_set_debug(opd_detr* m, int32_t debug) {
   OPD_REQUIRE(m, "opd_detr_set_debug: NULL handle");
   m->debug = debug;
-  m->plan = opd::Plan{};
+  m->drop_plans();
   return OPD_OK;
 }
 
@@ -928,14 +932,14 @@ int opd_detr_set_fusion(opd_detr* m, int32_t fuse_bottleneck_tail) {
   m->fuse_tail = fuse_bottleneck_tail & 1;
   m->stem_halo = (fuse_bottleneck_tail & 2) ? 0 : 1;
   m->fuse_shortcut = (fuse_bottleneck_tail & 4) ? 0 : 1;   // bit 2 set: separate shortcut kernel   // bit 1 set: im2col stem over the 64-lane layout (A/B comparison)
-  m->plan = opd::Plan{};
+  m->drop_plans();
   return OPD_OK;
 }
 
 int opd_detr_set_resize(opd_detr* m, int32_t do_resize) {
   OPD_REQUIRE(m, "opd_detr_set_resize: NULL handle");
   m->do_resize = do_resize;
-  m->plan = opd::Plan{};
+  m->drop_plans();
   return OPD_OK;
 }
 
@@ -962,20 +966,28 @@ int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t 
   OPD_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) == 0, "opd_detr_forward: workspace must be 1024-byte aligned");
   opd::DeviceGuard guard(m->device);   // the handle's device, whatever the caller's current device is
   OPD_CUDA_OK(guard.err);
-  opd::Plan& p = m->plan;
-  if (p.B != B || p.H0 != H0 || p.W0 != W0 || p.ws != workspace_dev || p.steps.empty()) {
-    p = opd::Plan{};
+  auto hit = m->plans.begin();
+  for (; hit != m->plans.end(); ++hit)
+    if (hit->B == B && hit->H0 == H0 && hit->W0 == W0 && hit->ws == workspace_dev && !hit->steps.empty()) break;
+  if (hit != m->plans.end()) {
+    m->plans.splice(m->plans.begin(), m->plans, hit);   // most recently used first (list nodes do not move: m->plan stays valid)
+  } else {
+    m->plan = nullptr;
+    m->plans.emplace_front();
+    opd::Plan& fresh = m->plans.front();
     size_t need = 0;
-    if (int rc = opd::build_plan(m, B, H0, W0, workspace_dev, &p, &need)) {
-      p = opd::Plan{};
+    int rc = opd::build_plan(m, B, H0, W0, workspace_dev, &fresh, &need);
+    if (rc == OPD_OK && need > workspace_bytes)
+      rc = opd::fail(OPD_ERR_INVALID, "opd_detr_forward: workspace of %zu bytes, %zu needed", workspace_bytes, need);
+    if (rc != OPD_OK) {
+      m->plans.pop_front();
       return rc;
     }
-    if (need > workspace_bytes) {
-      p = opd::Plan{};
-      return opd::fail(OPD_ERR_INVALID, "opd_detr_forward: workspace of %zu bytes, %zu needed", workspace_bytes, need);
-    }
-    p.B = B; p.H0 = H0; p.W0 = W0; p.ws = workspace_dev; p.ws_bytes = need;
+    fresh.B = B; fresh.H0 = H0; fresh.W0 = W0; fresh.ws = workspace_dev; fresh.ws_bytes = need;
+    while (m->plans.size() > kMaxPlans) m->plans.pop_back();
   }
+  m->plan = &m->plans.front();
+  opd::Plan& p = *m->plan;
   m->cur_frames = frames_dev;
   m->cur_bgr = frames_are_bgr;
   m->cur_logits = logits_dev;
@@ -994,8 +1006,8 @@ int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t 
 int opd_detr_profile(opd_detr* m, void* stream, int32_t max_steps, int32_t* n_steps, int32_t* kinds, double* flops,
                      double* bytes, float* ms, char* names, int32_t name_stride) {
   OPD_REQUIRE(m && n_steps, "opd_detr_profile: NULL argument");
-  opd::Plan& p = m->plan;
-  OPD_REQUIRE(!p.steps.empty() && m->cur_frames, "opd_detr_profile: run opd_detr_forward first");
+  OPD_REQUIRE(m->plan && !m->plan->steps.empty() && m->cur_frames, "opd_detr_profile: run opd_detr_forward first");
+  opd::Plan& p = *m->plan;
   opd::DeviceGuard guard(m->device);
   OPD_CUDA_OK(guard.err);
   const int n = (int)p.steps.size();
@@ -1028,8 +1040,9 @@ int opd_detr_profile(opd_detr* m, void* stream, int32_t max_steps, int32_t* n_st
 
 int opd_detr_tap(const opd_detr* m, const char* name, const void** ptr_dev, int64_t* rows, int64_t* cols, int32_t* is_f32) {
   OPD_REQUIRE(m && name && ptr_dev && rows && cols && is_f32, "opd_detr_tap: NULL argument");
-  auto it = m->plan.taps.find(name);
-  OPD_REQUIRE(it != m->plan.taps.end(), "opd_detr_tap: no activation named '%s' (run a forward first)", name);
+  OPD_REQUIRE(m->plan, "opd_detr_tap: run a forward first");
+  auto it = m->plan->taps.find(name);
+  OPD_REQUIRE(it != m->plan->taps.end(), "opd_detr_tap: no activation named '%s' (run a forward first)", name);
   *ptr_dev = it->second.ptr;
   *rows = it->second.rows;
   *cols = it->second.cols;

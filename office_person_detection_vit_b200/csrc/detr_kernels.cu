@@ -2,6 +2,8 @@
 // positional embedding (K7), multi-head attention (K6), prediction heads and post-processing (K8).
 // Reference arithmetic: third-party `transformers` (file:line map in oracle/detr_oracle.py) and the reference's
 // src/detection/yolov8_detector.py:210-225, 229-241 (xyxy -> xywh, foot point).
+#include <algorithm>
+
 #include "detr_kernels.h"
 
 #include <cmath>
@@ -585,7 +587,84 @@ int grid_for(long long total, int threads) {
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+// Synthetic timelapse frames generated on the device (bench.py config 4, SURVEY.md §8d: "frames generated on device per rank
+// from seed = 1000 + global_frame_idx // 64", no host I/O in the timed region).  Same picture family as
+// detection/synthetic.py synthetic_frames (192-pixel flat-colour blocks + 32-pixel blocks + pixel noise around 128), from a
+// counter-based hash so that any frame can be regenerated anywhere: value(frame g, y, x, c) =
+//   clamp(128 + (h(0, y/192, x/192, c) % 221 - 110) + (h(1, y/32, x/32, c) % 81 - 40) + (h(2, y, x, c) % 25 - 12), 0, 255)
+// with h(level, yy, xx, c) = high 32 bits of mix64((seed_base + g / 64) * C1 + (g % 64) * C2 + key * C3), key =
+// ((level * 4096 + yy) * 4096 + xx) * 4 + c.  detection/synthetic.py device_frames_reference() restates it in NumPy.
+__device__ __forceinline__ uint32_t synth_hash(unsigned long long base, uint32_t level, uint32_t yy, uint32_t xx, uint32_t c) {
+  const unsigned long long key = ((((unsigned long long)level * 4096ull + yy) * 4096ull + xx) * 4ull + c);
+  unsigned long long z = base + key * 0x94D049BB133111EBull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+
+// one thread = 16 consecutive output bytes (one aligned 16-byte store); the pixel cursor (frame, y, x, channel) advances byte by
+// byte and the two block-level hashes are recomputed only when the cursor enters another 32-pixel block, row or frame
+__global__ void synthetic_frames_kernel(unsigned long long seed_base, long long frame0, int H, int W, uint8_t* __restrict__ out,
+                                        long long n_bytes) {
+  const long long n_chunks = (n_bytes + 15) / 16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += (long long)gridDim.x * blockDim.x) {
+    const long long byte0 = i * 16;
+    long long pix = byte0 / 3;
+    int c = (int)(byte0 - pix * 3);
+    long long row = pix / W;
+    int x = (int)(pix - row * W);
+    long long b = row / H;
+    int y = (int)(row - b * H);
+    unsigned long long base = 0;
+    int coarse[3] = {0, 0, 0};
+    bool stale = true;
+    union { uint8_t u8[16]; uint4 v; } buf;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (stale) {
+        const long long g = frame0 + b;
+        base = (seed_base + (unsigned long long)(g / 64)) * 0x9E3779B97F4A7C15ull + (unsigned long long)(g % 64) * 0xD1B54A32D192ED03ull;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          coarse[cc] = 128 + (int)(synth_hash(base, 0, y / 192, x / 192, cc) % 221u) - 110 + (int)(synth_hash(base, 1, y / 32, x / 32, cc) % 81u) - 40;
+        stale = false;
+      }
+      const int v = coarse[c] + (int)(synth_hash(base, 2, y, x, c) % 25u) - 12;
+      buf.u8[k] = (uint8_t)min(max(v, 0), 255);
+      if (++c == 3) {
+        c = 0;
+        if (++x == W) {
+          x = 0;
+          stale = true;
+          if (++y == H) {
+            y = 0;
+            ++b;
+          }
+        } else if ((x & 31) == 0) {
+          stale = true;
+        }
+      }
+    }
+    if (byte0 + 16 <= n_bytes) {
+      *reinterpret_cast<uint4*>(out + byte0) = buf.v;
+    } else {
+      for (int k = 0; byte0 + k < n_bytes; ++k) out[byte0 + k] = buf.u8[k];
+    }
+  }
+}
+
 }  // namespace
+
+int launch_synthetic_frames(unsigned long long seed_base, long long frame0, int B, int H, int W, uint8_t* out, cudaStream_t s) {
+  OPD_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "synthetic frames: the output must be 16-byte aligned");
+  const long long n = (long long)B * H * W * 3;
+  const unsigned blocks = (unsigned)std::min<long long>(((n + 15) / 16 + 255) / 256, 148LL * 16);
+  synthetic_frames_kernel<<<blocks, 256, 0, s>>>(seed_base, frame0, H, W, out, n);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
 
 int launch_preprocess(const uint8_t* src, int B, int Hs, int Ws, int src_is_bgr, __nv_bfloat16* x2, cudaStream_t s) {
   const int H2 = (Hs + 1) / 2, W2 = (Ws + 1) / 2;
@@ -693,6 +772,13 @@ extern "C" int opd_attention_bf16(const void* q_dev, int64_t ldq, const void* k_
   return opd::launch_attention(static_cast<const __nv_bfloat16*>(q_dev), ldq, static_cast<const __nv_bfloat16*>(k_dev),
                                ldk, static_cast<const __nv_bfloat16*>(v_dev), ldv, static_cast<__nv_bfloat16*>(o_dev),
                                ldo, B, heads, Lq, Lk, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int opd_synthetic_frames_u8(uint64_t seed_base, int64_t global_frame0, int32_t B, int32_t H, int32_t W, uint8_t* frames_dev,
+                                       void* stream) {
+  OPD_REQUIRE(frames_dev && B > 0 && H > 0 && W > 0 && H <= 4096 * 32 && W <= 4096 * 32 && global_frame0 >= 0,
+              "opd_synthetic_frames_u8: bad argument");
+  return opd::launch_synthetic_frames(seed_base, global_frame0, B, H, W, frames_dev, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int opd_roi_features_bf16(const void* feat_dev, int32_t B, int32_t fh, int32_t fw, int32_t D, const double* det_xywh_dev,

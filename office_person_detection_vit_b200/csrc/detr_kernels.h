@@ -19,6 +19,8 @@ int launch_preprocess_s2d(const uint8_t* src, int B, int Hs, int Ws, int src_is_
 int launch_resize_u8(const uint8_t* src, int B, int H0, int W0, int src_is_bgr, uint8_t* tmp, uint8_t* dst, int H1,
                      int W1, const int16_t* wx, const int32_t* x0, int kx, int px, const int16_t* wy, const int32_t* y0,
                      int ky, int py, cudaStream_t s);
+// synthetic uint8 frames [B,H,W,3] generated on the device (bench.py config 4), frame b = global frame frame0 + b
+int launch_synthetic_frames(unsigned long long seed_base, long long frame0, int B, int H, int W, uint8_t* out, cudaStream_t s);
 // K3: 3x3 / stride 2 / pad 1 max pooling, NHWC bf16
 int launch_maxpool(const __nv_bfloat16* x, int B, int H, int W, int C, __nv_bfloat16* y, int P, int Q, cudaStream_t s);
 // K7: sine positional embedding table [h*w, 256] fp32 (all-ones mask)

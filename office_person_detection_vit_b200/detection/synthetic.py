@@ -47,8 +47,12 @@ def conv_specs():
     return specs
 
 
-def random_init_state_dict(seed: int = 0) -> dict[str, torch.Tensor]:
+def random_init_state_dict(seed: int = 0, trained_like: bool = False) -> dict[str, torch.Tensor]:
     """Seeded random-init DETR-R50 state dict (transformers key names, float32).
+
+    `trained_like=True` is the variance-preserving set used by the parity study: every attention
+    projection at Xavier gain 1 (no sharpened softmax, no damped o_proj), LayerNorm weights at 1 +- 0.05, the other tensors as
+    below - per-layer gain ~ 1, so that a rounding difference is carried through the ~100 layers instead of being amplified.
 
     transformers' default init is degenerate for parity purposes (every query yields the same box, no score
     crosses 0.5 — SURVEY.md H2), so the variances are re-scaled: He-init convolutions with non-trivial frozen-BN
@@ -83,10 +87,12 @@ def random_init_state_dict(seed: int = 0) -> dict[str, torch.Tensor]:
         w[prefix + ".bias"] = randn(n_out, std=bias_std)
 
     def layer_norm(prefix):
-        w[prefix + ".weight"] = rand(D_MODEL, lo=0.8, hi=1.2)
+        w[prefix + ".weight"] = rand(D_MODEL, lo=0.95, hi=1.05) if trained_like else rand(D_MODEL, lo=0.8, hi=1.2)
         w[prefix + ".bias"] = randn(D_MODEL, std=0.05)
 
     def attn(prefix, qk_gain=1.0, o_gain=1.0):
+        if trained_like:
+            qk_gain = o_gain = 1.0
         # qk_gain > 1 sharpens the softmax so that different queries attend to different tokens; o_gain < 1 keeps
         # the residual stream token-specific (random post-norm attention stacks otherwise collapse to one token)
         for proj in ("q_proj", "k_proj", "v_proj", "o_proj"):
@@ -131,3 +137,28 @@ def synthetic_frames(batch: int, h: int, w: int, seed: int = 1) -> np.ndarray:
 
     img = 128 + blocks(192, 110) + blocks(32, 40) + rng.integers(-12, 13, (batch, h, w, 3), dtype=np.int16)
     return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def device_frames_reference(seed_base: int, global_frame0: int, batch: int, h: int, w: int) -> np.ndarray:
+    """NumPy restatement of opd_synthetic_frames_u8 (csrc/detr_kernels.cu synthetic_frames_kernel): the frames bench.py's
+    config 4 generates on the device, bit for bit."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+    def mix(z):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return ((z ^ (z >> np.uint64(31))) >> np.uint64(32)).astype(np.int64)
+
+    out = np.empty((batch, h, w, 3), np.uint8)
+    yy, xx, cc = np.meshgrid(np.arange(h, dtype=np.uint64), np.arange(w, dtype=np.uint64), np.arange(3, dtype=np.uint64), indexing="ij")
+    with np.errstate(over="ignore"):
+        for b in range(batch):
+            g = global_frame0 + b
+            base = (np.uint64((seed_base + g // 64) & int(M)) * np.uint64(0x9E3779B97F4A7C15) +
+                    np.uint64(g % 64) * np.uint64(0xD1B54A32D192ED03))
+            v = np.full((h, w, 3), 128, np.int64)
+            for level, div, mod, off in ((0, 192, 221, 110), (1, 32, 81, 40), (2, 1, 25, 12)):
+                key = ((np.uint64(level * 4096) + yy // np.uint64(div)) * np.uint64(4096) + xx // np.uint64(div)) * np.uint64(4) + cc
+                v += mix(base + key * np.uint64(0x94D049BB133111EB)) % mod - off
+            out[b] = np.clip(v, 0, 255).astype(np.uint8)
+    return out

@@ -54,6 +54,8 @@ _lib.register("opd_roi_features_bf16", C.c_int, [_P, C.c_int32, C.c_int32, C.c_i
 _lib.register("opd_detr_postprocess", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                                C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P])
 
+_lib.register("opd_synthetic_frames_u8", C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P])
+
 N_QUERIES = 100
 N_LOGITS = 92
 PERSON_LABEL = 1   # COCO id of "person" in facebook/detr-resnet-50 (reference tests use class_id=1)
@@ -212,6 +214,19 @@ class DetrEngine:
             pass
 
 
+def synthetic_frames_device(out, seed_base: int, global_frame0: int):
+    """Fill `out` ([B,H,W,3] uint8 CUDA tensor) with synthetic frames generated on the device: frame b is global frame
+    global_frame0 + b of the stream seeded by seed_base (opd_synthetic_frames_u8; bench.py config 4).  No host sync."""
+    torch = _lib.require_cuda()
+    if not (out.is_cuda and out.dtype == torch.uint8 and out.dim() == 4 and out.shape[-1] == 3 and out.is_contiguous()):
+        raise ValueError("out must be a contiguous [B,H,W,3] uint8 CUDA tensor")
+    B, H, W, _ = out.shape
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().opd_synthetic_frames_u8(int(seed_base), int(global_frame0), B, H, W, out.data_ptr(), _lib.stream_ptr()),
+                   "opd_synthetic_frames_u8")
+    return out
+
+
 def postprocess_tensors(logits, boxes, h0: int, w0: int, threshold: float, person_label: int = PERSON_LABEL,
                         slot_base: int = 0) -> dict:
     """K8b on device tensors: per-query scores / labels / xyxy and the compacted person detections per frame."""
@@ -250,6 +265,7 @@ class ViTDetector:
         self.batch_size = int(batch_size)
         self.model: DetrEngine | None = None
         self._state_dict = state_dict
+        self._pinned: dict[tuple[int, int], object] = {}
         logger.info(f"ViTDetector initialized with model: {model_name}")
         logger.info(f"Using device: {self.device}")
         logger.info(f"Confidence threshold: {confidence_threshold}")
@@ -324,13 +340,58 @@ class ViTDetector:
             logger.error(f"Detection failed: {e}")
             raise
 
-    def detect_batch(self, frames: Sequence[np.ndarray]) -> list[list[Detection]]:
+    def detect_batch(self, frames: Sequence[np.ndarray], strict: bool = False) -> list[list[Detection]]:
         """Batched detection.  Frames of equal size run as one device batch (chunks of `batch_size`); frames of
         different sizes are grouped by size (the reference pads to the batch maximum instead: different arithmetic at
-        the padded borders, so equal-size groups are the faithful choice here)."""
-        return self._detect_batch(frames, with_features=False)[0]
+        the padded borders, so equal-size groups are the faithful choice here).
 
-    def _detect_batch(self, frames: Sequence[np.ndarray], with_features: bool):
+        Failure isolation (the reference's DetectionPhase catches exceptions PER FRAME and records an empty list,
+        src/pipeline/phases/detection.py:124-127): a frame that is not a uint8 [H,W,3] array, or whose device batch fails and
+        which then fails again on its own, yields [] and an error log - its batch neighbours keep their detections.
+        `strict=True` raises instead."""
+        return self._detect_batch(frames, with_features=False, strict=strict)[0]
+
+    def _staging(self, n: int, h: int, w: int):
+        """Pinned host staging buffer [batch_size, h, w, 3] (one per frame size, reused across calls)."""
+        torch = _lib.require_cuda()
+        buf = self._pinned.get((h, w))
+        if buf is None or buf.shape[0] < n:
+            buf = torch.empty((max(n, min(self.batch_size, 64)), h, w, 3), dtype=torch.uint8).pin_memory()
+            self._pinned[(h, w)] = buf
+        return buf
+
+    def _detect_chunk(self, frames, chunk, h0, w0, with_features, dev):
+        """One device batch of equal-size frames -> ([list[Detection]] per frame, [features] per frame)."""
+        torch = _lib.require_cuda()
+        stage = self._staging(len(chunk), h0, w0)
+        view = stage[:len(chunk)]
+        host = view.numpy()
+        for j, i in enumerate(chunk):
+            host[j] = frames[i]                                  # one copy: frame -> pinned staging
+        out = self.detect_tensors(view.to(dev, non_blocking=True))
+        f_dev = self.model.roi_features(out["det_xywh"], out["n_keep"], h0, w0) if with_features else None
+        # one packed device -> host read of the result rows: [B, Q, 4 + 1 + 2 + 1] float64
+        packed = torch.cat([out["det_xywh"], out["det_score"].double().unsqueeze(-1), out["det_foot"],
+                            out["det_query"].double().unsqueeze(-1)], dim=-1)
+        n_keep = out["n_keep"].cpu().numpy()
+        rows = packed.cpu().numpy()
+        f_host = f_dev.cpu().numpy() if with_features else None
+        dets_all, feats_all = [], []
+        for j in range(len(chunk)):
+            n = int(n_keep[j])
+            r = rows[j, :n].tolist()
+            dets = [Detection(bbox=(x, y, w, h), confidence=float(np.float32(sc)), class_id=PERSON_LABEL, class_name="person",
+                              camera_coords=(fx, fy), query_index=int(q)) for x, y, w, h, sc, fx, fy, q in r]
+            feat = None
+            if with_features:
+                feat = f_host[j, :n].copy()
+                for k, d in enumerate(dets):      # like the YOLO twin (yolov8_detector.py:153-156)
+                    d.features = feat[k]
+            dets_all.append(dets)
+            feats_all.append(feat)
+        return dets_all, feats_all
+
+    def _detect_batch(self, frames: Sequence[np.ndarray], with_features: bool, strict: bool = False):
         if self.model is None:
             raise RuntimeError("Model not loaded. Call load_model() first.")
         torch = _lib.require_cuda()
@@ -338,35 +399,45 @@ class ViTDetector:
         feats: list[np.ndarray | None] = [None] * len(frames)
         groups: dict[tuple[int, int], list[int]] = {}
         for i, f in enumerate(frames):
-            f = np.asarray(f)
-            if f.ndim != 3 or f.shape[2] != 3 or f.dtype != np.uint8:
-                raise ValueError(f"frame {i}: expected a uint8 [H,W,3] BGR array, got {f.dtype} {f.shape}")
+            try:
+                f = np.asarray(f)
+                if f.ndim != 3 or f.shape[2] != 3 or f.dtype != np.uint8 or f.shape[0] < 1 or f.shape[1] < 1:
+                    raise ValueError(f"frame {i}: expected a uint8 [H,W,3] BGR array, got {f.dtype} {f.shape}")
+            except Exception as e:
+                if strict:
+                    raise
+                logger.error(f"Detection failed for frame {i}: {e}")
+                results[i] = []
+                continue
             groups.setdefault((f.shape[0], f.shape[1]), []).append(i)
         dev = torch.device("cuda", self._device_index())
         for (h0, w0), idxs in groups.items():
             for c0 in range(0, len(idxs), self.batch_size):
                 chunk = idxs[c0:c0 + self.batch_size]
-                host = torch.from_numpy(np.stack([np.ascontiguousarray(frames[i]) for i in chunk])).pin_memory()
-                out = self.detect_tensors(host.to(dev, non_blocking=True))
-                f_dev = self.model.roi_features(out["det_xywh"], out["n_keep"], h0, w0) if with_features else None
-                n_keep = out["n_keep"].cpu().numpy()
-                xywh = out["det_xywh"].cpu().numpy().astype(np.float64)
-                score = out["det_score"].cpu().numpy()
-                foot = out["det_foot"].cpu().numpy()
-                query = out["det_query"].cpu().numpy()
-                f_host = f_dev.cpu().numpy() if with_features else None
+                try:
+                    d, f = self._detect_chunk(frames, chunk, h0, w0, with_features, dev)
+                except _lib.OpdError as e:
+                    if strict or len(chunk) == 1:
+                        if strict:
+                            raise
+                        logger.error(f"Detection failed for frame {chunk[0]}: {e}")
+                        d, f = [[]], [None]
+                    else:
+                        # the batch failed as a whole (e.g. frames too small for the backbone): retry frame by frame so that one
+                        # bad frame costs only itself
+                        logger.error(f"Detection failed for a batch of {len(chunk)} frames ({e}); retrying frame by frame")
+                        d, f = [], []
+                        for i in chunk:
+                            try:
+                                di, fi = self._detect_chunk(frames, [i], h0, w0, with_features, dev)
+                            except _lib.OpdError as e1:
+                                logger.error(f"Detection failed for frame {i}: {e1}")
+                                di, fi = [[]], [None]
+                            d += di
+                            f += fi
                 for j, i in enumerate(chunk):
-                    dets = []
-                    for r in range(int(n_keep[j])):
-                        x, y, w, h = (float(v) for v in xywh[j, r])
-                        dets.append(Detection(bbox=(x, y, w, h), confidence=float(score[j, r]), class_id=PERSON_LABEL,
-                                              class_name="person", camera_coords=(float(foot[j, r, 0]), float(foot[j, r, 1])),
-                                              query_index=int(query[j, r])))
-                    results[i] = dets
-                    if with_features:
-                        feats[i] = f_host[j, :int(n_keep[j])].copy()
-                        for r, d in enumerate(dets):      # like the YOLO twin (yolov8_detector.py:153-156)
-                            d.features = feats[i][r]
+                    results[i] = d[j]
+                    feats[i] = f[j]
         return [r if r is not None else [] for r in results], feats
 
     def _get_foot_position(self, bbox: tuple[float, float, float, float]) -> tuple[float, float]:

@@ -42,11 +42,14 @@ class DetectCountPipeline:
         out["zone_idx"] = idx.view(B, -1)
         return out
 
-    def capture(self, frames, hist=None, slot_base: int = 0, threshold: float | None = None, bgr: bool = True, zero_hist: bool = False):
+    def capture(self, frames, hist=None, slot_base: int = 0, threshold: float | None = None, bgr: bool = True, zero_hist: bool = False,
+                all_reduce: bool = False):
         """Capture one `run_tensors(frames, ...)` step into a CUDA graph and return a callable that replays it and returns the
         (static) output tensors: for steady-state loops that refill the SAME `frames` buffer (and `hist`) between steps.  The
         143 launches of a step are enqueued by one graph launch instead of 143 API calls.  `zero_hist` clears `hist` inside the
-        graph before the step.  Everything the step reads (frames, weights, tables) must stay where it is while the graph lives."""
+        graph before the step; `all_reduce` captures the NCCL all-reduce of `hist` as the graph's last node (multi-GPU: the step's
+        only collective then costs no launch of its own).  Everything the step reads (frames, weights, tables) must stay where it is
+        while the graph lives."""
         torch = _lib.require_cuda()
         if hist is None:
             hist = torch.zeros(slot_base + frames.shape[0], self.zones.get_zone_count() + 1, dtype=torch.int32, device=frames.device)
@@ -57,6 +60,8 @@ class DetectCountPipeline:
             if zero_hist:
                 hist.zero_()
             out = self.run_tensors(frames, hist=hist, slot_base=slot_base, threshold=threshold, bgr=bgr)
+            if all_reduce:
+                self.all_reduce(hist)
 
         def replay():
             graph.replay()

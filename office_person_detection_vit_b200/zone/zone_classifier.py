@@ -124,7 +124,7 @@ class ZoneClassifier:
     def table(self) -> ZoneTable:
         return self._table
 
-    def _launch(self, pts, *, want_idx=False, want_mask=False, hist=None, slot=None, T=1, transformer=None):
+    def _launch(self, pts, *, want_idx=False, want_mask=False, hist=None, slot=None, T=1, transformer=None, idx_out=None):
         torch = _lib.require_cuda()
         if pts.dim() != 2 or pts.shape[1] != 2 or not pts.is_cuda:
             raise ValueError("points must be a CUDA tensor of shape [N,2]")
@@ -132,7 +132,12 @@ class ZoneClassifier:
             raise ValueError("points must be float32 or float64")
         pts = pts.contiguous()
         n = pts.shape[0]
-        idx = torch.empty((n,), dtype=torch.int32, device=pts.device) if want_idx else None
+        if idx_out is not None:
+            if tuple(idx_out.shape) != (n,) or idx_out.dtype != torch.int32 or not idx_out.is_contiguous() or idx_out.device != pts.device:
+                raise ValueError("index_out must be a contiguous int32 [N] tensor on the points' device")
+            idx = idx_out
+        else:
+            idx = torch.empty((n,), dtype=torch.int32, device=pts.device) if want_idx else None
         mask = torch.empty((n,), dtype=torch.int64, device=pts.device) if want_mask else None
         if transformer is None:
             params = _lib.FloorParams()
@@ -163,17 +168,20 @@ class ZoneClassifier:
         """[N,2] CUDA tensor -> int64 [N] bit mask of containing zones (bit z = zone z)."""
         return self._launch(points, want_mask=True, transformer=transformer)[1]
 
-    def count(self, points, slot=None, num_slots: int = 1, transformer=None, out=None, return_index: bool = False):
+    def count(self, points, slot=None, num_slots: int = 1, transformer=None, out=None, return_index: bool = False,
+              index_out=None):
         """Per-timestamp zone histogram: int32 [num_slots, Z+1]; column Z counts unclassified points
         (aggregator.py:64-75).  `slot[i]` is the timestamp row of point i (None: everything in row 0).
-        Accumulates into `out` when given (that is what the multi-GPU all-reduce sums)."""
+        Accumulates into `out` when given (that is what the multi-GPU all-reduce sums).  `index_out` (int32 [N]) receives the
+        zone index of every point (steady-state loops: no allocation per call); `return_index` allocates it."""
         torch = _lib.require_cuda()
         if out is None:
             out = torch.zeros((num_slots, self._table.Z + 1), dtype=torch.int32, device=points.device)
         elif tuple(out.shape) != (num_slots, self._table.Z + 1) or out.dtype != torch.int32 or not out.is_contiguous():
             raise ValueError("out must be a contiguous int32 [num_slots, Z+1] tensor")
-        idx, _ = self._launch(points, want_idx=return_index, hist=out, slot=slot, T=num_slots, transformer=transformer)
-        return (out, idx) if return_index else out
+        idx, _ = self._launch(points, want_idx=return_index, hist=out, slot=slot, T=num_slots, transformer=transformer,
+                              idx_out=index_out)
+        return (out, idx) if (return_index or index_out is not None) else out
 
     def counts_to_dicts(self, hist) -> list[dict[str, int]]:
         """Dense [T, Z+1] histogram -> the reference's sparse per-frame dicts (non-zero bins only)."""

@@ -30,6 +30,10 @@ Two arithmetic modes:
   "bf16"  float32 accumulation with the SAME bfloat16 rounding points as the CUDA path:
           BN folded into the conv weights in float32 and then rounded to bf16, every stored activation rounded
           to bf16, softmax / LayerNorm statistics / heads in float32.
+Study modes (oracle/parity_study.py: where does the bf16 error come from, what would a mixed-precision path buy):
+  "bf16+res32"  as "bf16", but the transformer's residual stream / LayerNorm inputs and outputs stay float32 (only the GEMM
+                and attention operands are rounded);
+  "bf16bb"      bf16 backbone + input projection, float32 transformer;   "bf16tr"  float32 backbone, bf16 transformer.
 """
 
 from __future__ import annotations
@@ -68,14 +72,22 @@ def _bf16(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-class _Mode:
-    def __init__(self, mode: str):
-        if mode not in ("fp32", "bf16"):
-            raise ValueError(mode)
-        self.bf16 = mode == "bf16"
+MODES = ("fp32", "bf16", "bf16+res32", "bf16bb", "bf16tr")
 
-    def act(self, x):      # a stored activation
+
+class _Mode:
+    def __init__(self, mode: str, part: str = "transformer"):
+        if mode not in MODES:
+            raise ValueError(mode)
+        self.bf16 = mode in ("bf16", "bf16+res32") or (mode == "bf16bb" and part == "backbone") or \
+            (mode == "bf16tr" and part == "transformer")
+        self.res32 = mode == "bf16+res32"
+
+    def act(self, x):      # a stored activation / a tensor-core activation operand
         return _bf16(x) if self.bf16 else x
+
+    def stream(self, x):   # the transformer's residual stream (LayerNorm output that the next residual add reads)
+        return x if self.res32 else self.act(x)
 
     def wt(self, x):       # a tensor-core weight operand
         return _bf16(x) if self.bf16 else x
@@ -187,7 +199,8 @@ def sine_position_embedding(h: int, w: int) -> torch.Tensor:
 
 
 def _linear(m: _Mode, w: dict, prefix: str, x: torch.Tensor) -> torch.Tensor:
-    return F.linear(x, m.wt(w[prefix + ".weight"]), w[prefix + ".bias"])
+    # the activation operand of a tensor-core GEMM is bf16 (a no-op in plain "bf16" mode, where every input already is)
+    return F.linear(m.act(x), m.wt(w[prefix + ".weight"]), w[prefix + ".bias"])
 
 
 def _mha(m: _Mode, w: dict, prefix: str, q_in, k_in, v_in) -> torch.Tensor:
@@ -220,7 +233,7 @@ def _ln(w: dict, prefix: str, x: torch.Tensor) -> torch.Tensor:
 @torch.no_grad()
 def backbone(w: dict, pixel_values: torch.Tensor, mode: str = "fp32", taps: dict | None = None) -> torch.Tensor:
     """ResNet-50 with frozen BN -> stage-4 feature map [B,2048,h,w]."""
-    m = _Mode(mode)
+    m = _Mode(mode, "backbone")
 
     def conv(prefix, x, stride, k, relu, residual=None, rounded=True):
         wt, shift = fold_bn(w, prefix)
@@ -257,13 +270,14 @@ def backbone(w: dict, pixel_values: torch.Tensor, mode: str = "fp32", taps: dict
 def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None, do_resize: bool = True):
     """frames [B,H0,W0,3] uint8 BGR -> (logits [B,100,92], boxes cxcywh in [0,1] [B,100,4]), float32."""
     m = _Mode(mode)
+    mb = _Mode(mode, "backbone")
     pv = preprocess(frames_bgr, do_resize)
     if taps is not None:
         taps["pixel_values"] = pv
     feat = backbone(w, pv, mode, taps)
     B, _, h, wd = feat.shape
-    proj = F.conv2d(feat, m.wt(w["model.input_projection.weight"]), w["model.input_projection.bias"])
-    x = m.act(proj.flatten(2).permute(0, 2, 1))                     # [B, S, 256]
+    proj = F.conv2d(feat, mb.wt(w["model.input_projection.weight"]), w["model.input_projection.bias"])
+    x = m.stream(mb.act(proj.flatten(2).permute(0, 2, 1)) if not m.res32 else proj.flatten(2).permute(0, 2, 1))   # [B, S, 256]
     pos = sine_position_embedding(h, wd)[None]                        # float32 table
     if taps is not None:
         taps["enc_in"] = x
@@ -273,10 +287,10 @@ def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None, d
         p = f"model.encoder.layers.{i}"
         qk = m.act(x + pos)
         a = _mha(m, w, p + ".self_attn", qk, qk, x)
-        x = m.act(_ln(w, p + ".self_attn_layer_norm", x + a))
+        x = m.stream(_ln(w, p + ".self_attn_layer_norm", x + a))
         f = m.act(F.relu(_linear(m, w, p + ".mlp.fc1", x)))
         f = _linear(m, w, p + ".mlp.fc2", f)
-        x = m.act(_ln(w, p + ".final_layer_norm", x + f))
+        x = m.stream(_ln(w, p + ".final_layer_norm", x + f))
         if taps is not None:
             taps[f"enc{i}"] = x
     memory = x
@@ -288,15 +302,15 @@ def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None, d
         p = f"model.decoder.layers.{i}"
         qk = m.act(y + qpos)
         a = _mha(m, w, p + ".self_attn", qk, qk, y)
-        y = m.act(_ln(w, p + ".self_attn_layer_norm", y + a))
+        y = m.stream(_ln(w, p + ".self_attn_layer_norm", y + a))
         a = _mha(m, w, p + ".encoder_attn", m.act(y + qpos), mem_k, memory)
-        y = m.act(_ln(w, p + ".encoder_attn_layer_norm", y + a))
+        y = m.stream(_ln(w, p + ".encoder_attn_layer_norm", y + a))
         f = m.act(F.relu(_linear(m, w, p + ".mlp.fc1", y)))
         f = _linear(m, w, p + ".mlp.fc2", f)
-        y = m.act(_ln(w, p + ".final_layer_norm", y + f))
+        y = m.stream(_ln(w, p + ".final_layer_norm", y + f))
         if taps is not None:
             taps[f"dec{i}"] = y
-    y = m.act(_ln(w, "model.decoder.layernorm", y))
+    y = m.stream(_ln(w, "model.decoder.layernorm", y))
     if taps is not None:
         taps["dec_out"] = y
 

@@ -326,3 +326,51 @@ def test_reversed_row_order_is_bit_identical(detector):
         _lib.lib().opd_set_option(b"gemm_reverse", 1)
         eng.set_debug(False)
     assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+
+
+def test_device_frame_generator_matches_numpy(built_lib):
+    """opd_synthetic_frames_u8 (bench.py config 4: frames generated on the device) against its NumPy restatement, bit for bit:
+    a batch that crosses a 64-frame seed boundary, sizes that are not multiples of the 32- / 192-pixel blocks, a byte count
+    that is not a multiple of 16 (ragged last chunk)."""
+    import torch
+
+    from office_person_detection_vit_b200.detection.synthetic import device_frames_reference
+    from office_person_detection_vit_b200.detection.vit_detector import synthetic_frames_device
+
+    torch.cuda.init()
+    for (b, h, w, g0) in [(3, 70, 45, 62), (2, 200, 333, 12480), (1, 33, 7, 0)]:
+        out = torch.zeros(b, h, w, 3, dtype=torch.uint8, device="cuda")
+        synthetic_frames_device(out, 1000, g0)
+        ref = device_frames_reference(1000, g0, b, h, w)
+        assert (out.cpu().numpy() == ref).all(), (b, h, w, g0)
+        assert ref.std() > 20          # pictures, not a constant
+
+
+def test_plan_cache_and_failure_isolation(detector):
+    """(1) A stream that alternates between batch shapes keeps one launch plan per shape (no re-planning) and every shape's
+    results stay bit-identical.  (2) detect_batch isolates failures per frame like the reference's DetectionPhase
+    (detection.py:124-127): a malformed frame or a frame too small for the backbone yields [] and its neighbours keep their
+    detections; strict=True raises."""
+    import torch
+
+    eng = detector.model
+    a = torch.from_numpy(do.synthetic_frames(3, 480, 640, seed=61)).cuda()
+    b = torch.from_numpy(do.synthetic_frames(2, 320, 512, seed=62)).cuda()
+    ra = tuple(t.clone() for t in eng.forward(a))
+    rb = tuple(t.clone() for t in eng.forward(b))
+    for _ in range(2):
+        ga = eng.forward(a)
+        assert torch.equal(ga[0], ra[0]) and torch.equal(ga[1], ra[1])
+        gb = eng.forward(b)
+        assert torch.equal(gb[0], rb[0]) and torch.equal(gb[1], rb[1])
+        g1 = eng.forward(a[:1].contiguous())                 # same frame size, another batch size: its own plan and prologue buffer
+        assert torch.equal(g1[0], ra[0][:1]) and torch.equal(g1[1], ra[1][:1])
+
+    good = do.synthetic_frames(2, 480, 640, seed=63)
+    frames = [good[0], np.zeros((480, 640), np.uint8), good[1], np.zeros((480, 640, 3), np.float32), np.zeros((8, 8, 3), np.uint8)]
+    res = detector.detect_batch(frames)
+    assert len(res) == 5 and res[1] == [] and res[3] == [] and res[4] == []
+    alone = detector.detect_batch([good[0], good[1]])
+    assert [d.bbox for d in res[0]] == [d.bbox for d in alone[0]] and [d.bbox for d in res[2]] == [d.bbox for d in alone[1]]
+    with pytest.raises(ValueError):
+        detector.detect_batch(frames[:2], strict=True)
