@@ -3,8 +3,32 @@ against the CPU oracle (oracle/detr_oracle.py, pinned to transformers' own DetrF
 tests/test_detr_oracle.py) on identical synthetic frames and identical seeded weights.
 
 Tolerances (DESIGN.md "numerics"): the CUDA path stores bf16 activations; the oracle's "bf16" mode rounds at the same
-points, so the remaining differences are fp32 accumulation order + bf16 rounding flips.  Measured bounds are asserted
-here with margin and written next to each check."""
+points, so the remaining differences are fp32 accumulation order + bf16 rounding flips, which every further rounding amplifies up
+to the bf16 noise floor.  Every bound below is 1.5 x the maximum MEASURED over seeds 0-3, two frame sizes and both
+oracle modes on a B200 (profiles/r02_parity_layers.json, written by tests/parity_table.py), against the oracle's bf16 mode AND
+against its fp32 mode (= the reference arithmetic, pinned to transformers' DetrForObjectDetection - at 96x128 by the golden
+vectors of tests/golden/detr_small.npz and at 800x1333 by tests/test_detr_oracle.py::test_oracle_matches_transformers_full_size;
+the oracle run at full size inside these tests is that same pinned code)."""
+
+# measured maxima x 1.5 (profiles/r02_parity_layers.json "summary"; random-init weights, the set every benchmark uses)
+TOL = {
+    "bf16": dict(box_max=19.2, box_median=2.0, score_max=0.040, score_median=0.0080, labels=0.99, logits_rel=1.51e-2, tap_rel=1.43e-2),
+    "fp32": dict(box_max=18.1, box_median=2.71, score_max=0.037, score_median=0.0063, labels=0.99, logits_rel=1.50e-2, tap_rel=1.40e-2),
+}
+TOL_STEM_BF16 = 4.1e-5      # stem / pool taps against the bf16 oracle: accumulation order only (measured 2.7e-5)
+
+
+def _final_errors(out, ref_logits, ref_boxes, h0, w0) -> dict:
+    sc, lb, xyxy = do.postprocess(ref_logits, ref_boxes, h0, w0)
+    e = (out["xyxy"].cpu() - xyxy).abs()
+    s = (out["scores"].cpu() - sc).abs()
+    return dict(box_max=float(e.max()), box_median=float(e.median()), score_max=float(s.max()), score_median=float(s.median()),
+                labels=float((out["labels"].cpu() == lb).float().mean()), logits_rel=_rel(out["logits"].cpu(), ref_logits))
+
+
+def _assert_within(err: dict, tol: dict, what: str) -> None:
+    bad = {k: (v, tol[k]) for k, v in err.items() if (v < tol[k] if k == "labels" else v > tol[k])}
+    assert not bad, f"{what}: {bad} (measured, bound)"
 
 from __future__ import annotations
 
@@ -65,11 +89,12 @@ def test_layer_taps_small_frame(detector, weights):
             assert got.shape == ref.shape, (name, got.shape, ref.shape)
             report[name] = _rel(got, ref)
         print({k: f"{v:.2e}" for k, v in report.items()})
-        assert report["pos"] < 1e-5
-        bad = {k: v for k, v in report.items() if v > 3e-2}
+        assert report["pos"] < 1e-6                              # measured 2.2e-8
+        assert report["stem"] < TOL_STEM_BF16 and report["pool"] < TOL_STEM_BF16
+        bad = {k: v for k, v in report.items() if v > TOL["bf16"]["tap_rel"]}
         assert not bad, bad
-        assert _rel(logits.cpu(), ref_logits) < 3e-2
-        assert float((boxes.cpu() - ref_boxes).abs().max()) < 2e-2
+        assert _rel(logits.cpu(), ref_logits) < TOL["bf16"]["logits_rel"]
+        assert float((boxes.cpu() - ref_boxes).abs().max()) < 1.4e-2      # cxcywh in [0, 1]: measured 9.1e-3 x 1.5
     finally:
         eng.set_debug(False)
         eng.set_resize(True)
@@ -84,25 +109,14 @@ def test_detections_800x1333(detector, weights):
     out = detector.detect_tensors(torch.from_numpy(frames).cuda(), threshold=0.0)
     torch.cuda.synchronize()
     sc, lb, xyxy = do.postprocess(ref_logits, ref_boxes, 800, 1333)
-    d_box = float((out["xyxy"].cpu() - xyxy).abs().max())
-    d_score = float((out["scores"].cpu() - sc).abs().max())
-    agree = float((out["labels"].cpu() == lb).float().mean())
-    m_box = float((out["xyxy"].cpu() - xyxy).abs().median())
-    m_score = float((out["scores"].cpu() - sc).abs().median())
-    print(f"max |box| err {d_box:.4f} px (median {m_box:.4f}), max |score| err {d_score:.5f} (median {m_score:.5f}), "
-          f"label agreement {agree:.4f}")
-    # bf16 activations through ~50 random-init layers: bounds are on the worst of 200 queries and on the median
-    assert d_box < 0.015 * 1333 and d_score < 5e-2 and agree > 0.97 and m_box < 2.5 and m_score < 1e-2
-    # for the record (DESIGN.md numerics): distance to the float32 reference arithmetic, and how far the bf16 rounding
-    # points alone move the reference (oracle bf16 mode vs oracle fp32 mode) - the CUDA path sits inside that envelope
+    err = _final_errors(out, ref_logits, ref_boxes, 800, 1333)
+    print("vs oracle bf16:", {k: round(v, 5) for k, v in err.items()})
+    _assert_within(err, TOL["bf16"], "800x1333 vs oracle bf16")
+    # distance to the float32 reference arithmetic: an ASSERTION, same kind of bound
     l32, b32 = do.forward(weights, frames, mode="fp32")
-    sc32, _, xyxy32 = do.postprocess(l32, b32, 800, 1333)
-    e_box = (out["xyxy"].cpu() - xyxy32).abs()
-    o_box = (xyxy - xyxy32).abs()
-    print(f"vs fp32 reference: CUDA box err median {float(e_box.median()):.3f} / max {float(e_box.max()):.3f} px, "
-          f"score max {float((out['scores'].cpu() - sc32).abs().max()):.4f}; oracle-bf16 box err median "
-          f"{float(o_box.median()):.3f} / max {float(o_box.max()):.3f} px")
-    assert float(e_box.max()) < 2.5 * max(float(o_box.max()), 4.0)
+    err32 = _final_errors(out, l32, b32, 800, 1333)
+    print("vs oracle fp32:", {k: round(v, 5) for k, v in err32.items()})
+    _assert_within(err32, TOL["fp32"], "800x1333 vs oracle fp32 (the reference arithmetic)")
 
     # device post-processing == oracle post-processing on the SAME logits / boxes (fp32, exact up to 1 ulp)
     from office_person_detection_vit_b200.detection import postprocess_tensors
@@ -147,16 +161,12 @@ def test_camera_frame_resize_path(detector, weights):
                                           align_corners=False).numpy().transpose(0, 2, 3, 1)
     assert (got == ref).all()
     ref_logits, ref_boxes = do.forward(weights, frames, mode="bf16")
-    sc, lb, xyxy = do.postprocess(ref_logits, ref_boxes, 720, 1280)
-    d_box = float((out["xyxy"].cpu() - xyxy).abs().max())
-    d_score = float((out["scores"].cpu() - sc).abs().max())
-    agree = float((out["labels"].cpu() == lb).float().mean())
-    m_box = float((out["xyxy"].cpu() - xyxy).abs().median())
-    m_score = float((out["scores"].cpu() - sc).abs().median())
-    print(f"720x1280: max |box| err {d_box:.4f} px (median {m_box:.4f}), max |score| err {d_score:.5f} (median {m_score:.5f}), "
-          f"label agreement {agree:.4f}")
+    err = _final_errors(out, ref_logits, ref_boxes, 720, 1280)
+    print("720x1280 vs oracle bf16:", {k: round(v, 5) for k, v in err.items()})
     assert out["logits"].shape == (2, 100, 92)
-    assert d_box < 0.015 * 1280 and d_score < 5e-2 and agree > 0.97 and m_box < 2.5 and m_score < 1e-2
+    _assert_within(err, TOL["bf16"], "720x1280 vs oracle bf16")
+    l32, b32 = do.forward(weights, frames, mode="fp32")
+    _assert_within(_final_errors(out, l32, b32, 720, 1280), TOL["fp32"], "720x1280 vs oracle fp32 (the reference arithmetic)")
 
 
 def test_roi_features_kernel_matches_reference_golden(built_lib):

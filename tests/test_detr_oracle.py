@@ -86,3 +86,26 @@ def test_roi_features_match_the_reference_feature_extractor():
     assert got.dtype == g["features"].dtype and got.shape == g["features"].shape
     np.testing.assert_array_equal(got, g["features"])
     assert do.roi_features(g["feat"], [], (720, 1280)).shape == (0, 64)
+
+
+@pytest.mark.parametrize("h0,w0", [(800, 1333), (720, 1280)])
+def test_oracle_matches_transformers_full_size(weights, h0, w0):
+    """The pin at BASELINE's frame sizes (the golden vectors are 96x128 only): oracle fp32 mode against transformers'
+    own DetrImageProcessor + DetrForObjectDetection, live, on one synthetic frame of the config-2 / config-1 size - preprocessing
+    (uint8 antialias resize for 720p), logits and boxes."""
+    import os
+
+    os.environ.setdefault("HF_HUB_OFFLINE", "1")
+    from transformers import DetrImageProcessor
+
+    frames = do.synthetic_frames(1, h0, w0, seed=17)
+    model = do.hf_model(weights)
+    inp = DetrImageProcessor()(images=[np.ascontiguousarray(frames[0][:, :, ::-1])], return_tensors="pt")
+    with torch.no_grad():
+        out = model(**inp)
+    pv = do.preprocess(frames)
+    assert tuple(pv.shape) == tuple(inp["pixel_values"].shape)
+    np.testing.assert_allclose(pv.numpy(), inp["pixel_values"].numpy(), rtol=0, atol=1e-6)
+    logits, boxes = do.forward(weights, frames, mode="fp32")
+    np.testing.assert_allclose(logits.numpy(), out.logits.numpy(), rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(boxes.numpy(), out.pred_boxes.numpy(), rtol=1e-4, atol=5e-5)
