@@ -195,7 +195,7 @@ def main_reference(args) -> None:
                 "warmup": 1, "ms_per_step": 1e9 / r["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config5_workload(args.gpus, CONFIG5_POINTS),
                 "cpu_baseline": r, "e2e": {"value": r["value"], "unit": UNIT5, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
     if args.config == 1:
         r = cpu_detect_run(max(1, args.steps), warm, 1, 720, 1280, 4)
@@ -211,7 +211,7 @@ def main_reference(args) -> None:
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "legs": r["legs"],
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n_gpus: int) -> dict:
@@ -302,8 +302,15 @@ class Ctx:
         return self.max_over_ranks(e0.elapsed_time(e1))
 
     def close(self):
+        """End of the run.  Multi-GPU: the captured CUDA graphs hold NCCL kernels and the ranks finish at different times (rank 0
+        still profiles and runs the CPU legs after the others are done); tearing the communicator down rank by rank under those
+        conditions hung on the 2-GPU box (r02), so every rank flushes, synchronises its device and leaves without the collective
+        teardown - the driver reclaims the context."""
+        self.torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
         if self.world > 1:
-            self.dist.destroy_process_group()
+            os._exit(0)
 
 
 def build_pipeline(ctx: Ctx, n_zones: int, batch: int):
@@ -619,7 +626,7 @@ def main_headline(args) -> None:
             line["parity"] = parity_block(out, host)
         except Exception as e:
             line["parity"] = {"error": f"{type(e).__name__}: {e}"}
-    print(json.dumps(line))
+    emit(line)
     ctx.close()
 
 
@@ -900,11 +907,30 @@ def main_single_config(args) -> None:
         res.setdefault("steps", args.steps)
         res |= {"warmup": 3, "higher_is_better": True, "vs_baseline": None, "data": "synthetic"}
         res.setdefault("dtype", "bf16")
-        print(json.dumps(res))
+        emit(res)
     ctx.close()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line, on the process's original stdout."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
+
+
 def main() -> None:
+    # Libraries write banners to file descriptor 1 (NCCL prints its version there when NCCL_DEBUG is set on the box): keep the real
+    # stdout for the one JSON line and point fd 1 at stderr for everything else.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
