@@ -112,6 +112,14 @@ int opd_floor_project_classify_count_f64(const opd_floor_params* p, const opd_zo
                                          int32_t* zone_idx_dev, uint64_t* zone_mask_dev, int32_t* hist_dev,
                                          void* stream);
 
+/* More than OPD_MAX_ZONES zones (the reference sets no limit, zone_classifier.py:44-112): the caller splits the zones into groups of
+ * <= OPD_MAX_ZONES in declaration order, builds one table per group and classifies against each; this keeps, per point, the best
+ * group winner by the GLOBAL rank (rank_dev [Z]: position in the order sorted by (priority or +inf, declaration order)):
+ * idx_groups_dev [G, N] group-local winner or -1 -> out_idx_dev [N] global zone index (g * OPD_MAX_ZONES + z) or -1;
+ * out_count_dev [N] (optional): number of groups that contain the point. */
+int opd_zone_combine_groups(const int32_t* idx_groups_dev, const int32_t* rank_dev, int32_t G, int64_t N,
+                            int32_t* out_idx_dev, int32_t* out_count_dev, void* stream);
+
 /* Histogram only: Aggregator.get_zone_counts on already classified points (aggregator.py:52-75).
  * Exactly one of zone_idx_dev / zone_mask_dev is non-NULL. */
 int opd_zone_histogram(const int32_t* zone_idx_dev, const uint64_t* zone_mask_dev, const int32_t* slot_dev,

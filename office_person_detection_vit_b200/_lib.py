@@ -47,6 +47,7 @@ _SIGNATURES = {
     "opd_floor_project_classify_count_f64": (C.c_int, [C.POINTER(FloorParams), _P, _P, _P, C.c_int64, C.c_int32,
                                                        _P, _P, _P, _P, _P, _P, _P]),
     "opd_zone_histogram": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    "opd_zone_combine_groups": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, _P, _P]),
 }
 
 

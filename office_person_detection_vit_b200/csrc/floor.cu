@@ -646,6 +646,32 @@ __global__ void zone_histogram_kernel(const int32_t* zone_idx, const uint64_t* z
   }
 }
 
+// More than 64 zones (zone_classifier.py:44-112 sets no limit): the zones are split into groups of <= 64, one table per group; every
+// group answers with its own winner, this kernel keeps the best of them by the global rank (priority or +inf, declaration order):
+// idx_groups [G, N] group-local zone index or -1, rank [Z] -> out_idx [N] global zone index or -1, out_count [N] (optional) number of
+// GROUPS with a hit (0 = unclassified).
+__global__ void zone_combine_kernel(const int32_t* __restrict__ idx_groups, const int32_t* __restrict__ rank, int G, long long N,
+                                    int32_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    int best = -1, best_rank = 0x7fffffff, hits = 0;
+    for (int g = 0; g < G; ++g) {
+      const int z = idx_groups[(long long)g * N + i];
+      if (z >= 0) {
+        ++hits;
+        const int gz = g * OPD_MAX_ZONES + z;
+        const int r = rank[gz];
+        if (r < best_rank) {
+          best_rank = r;
+          best = gz;
+        }
+      }
+    }
+    out_idx[i] = best;
+    if (out_count) out_count[i] = hits;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Host: zone table construction (float64).
 // ---------------------------------------------------------------------------------------------------------
@@ -1141,6 +1167,18 @@ extern "C" int opd_zone_histogram(const int32_t* zone_idx_dev, const uint64_t* z
   const unsigned blocks = (unsigned)std::min<long long>((N + threads - 1) / threads, 148 * 8);
   zone_histogram_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(zone_idx_dev, zone_mask_dev, slot_dev,
                                                                                   N, Z, T, hist_dev);
+  opd::count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+extern "C" int opd_zone_combine_groups(const int32_t* idx_groups_dev, const int32_t* rank_dev, int32_t G, int64_t N,
+                                       int32_t* out_idx_dev, int32_t* out_count_dev, void* stream) {
+  OPD_REQUIRE(idx_groups_dev && rank_dev && out_idx_dev && G >= 1 && N >= 0, "opd_zone_combine_groups: bad argument");
+  if (N == 0) return OPD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)std::min<long long>((N + threads - 1) / threads, 148 * 8);
+  zone_combine_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(idx_groups_dev, rank_dev, G, N, out_idx_dev, out_count_dev);
   opd::count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

@@ -28,7 +28,8 @@ class ZoneTable:
 
     def __init__(self, zones: list[dict], allow_overlap: bool):
         if len(zones) > _lib.OPD_MAX_ZONES:
-            raise NotImplementedError(f"at most {_lib.OPD_MAX_ZONES} zones are supported, got {len(zones)}")
+            raise ValueError(f"one device table holds at most {_lib.OPD_MAX_ZONES} zones, got {len(zones)} (ZoneClassifier splits "
+                             "larger zone lists into groups)")
         self.allow_overlap = bool(allow_overlap)
         self.Z = len(zones)
         offs = [0]
@@ -77,7 +78,17 @@ class ZoneClassifier:
     def __init__(self, zones: list[dict], allow_overlap: bool = True):
         self.allow_overlap = allow_overlap
         self.zones = self._validate_zones(zones)
-        self._table = ZoneTable(self.zones, allow_overlap)
+        # The reference sets no limit on the number of zones (zone_classifier.py:44-112).  One device table holds 64 (its masks are
+        # 64-bit words): longer lists are split into groups of 64 in declaration order, every group answers with its own table and
+        # opd_zone_combine_groups keeps the best group winner by the global (priority or +inf, declaration order) rank.
+        M = _lib.OPD_MAX_ZONES
+        self._tables = [ZoneTable(self.zones[g:g + M], allow_overlap) for g in range(0, max(len(self.zones), 1), M)]
+        self._table = self._tables[0]
+        order = sorted(range(len(self.zones)),
+                       key=lambda i: (math.inf if self.zones[i]["priority"] is None else self.zones[i]["priority"], i))
+        self._rank = np.empty(len(self.zones), dtype=np.int32)
+        self._rank[order] = np.arange(len(self.zones), dtype=np.int32)
+        self._rank_dev: dict = {}
         self._ids = [z["id"] for z in self.zones]
         logger.info("ZoneClassifierを初期化しました。ゾーン数: %d, allow_overlap=%s", len(self.zones), self.allow_overlap)
 
@@ -122,10 +133,64 @@ class ZoneClassifier:
     # -- tensor entries ---------------------------------------------------------------------------------
     @property
     def table(self) -> ZoneTable:
+        """The device table (the first group's when there are more than 64 zones)."""
         return self._table
 
-    def _launch(self, pts, *, want_idx=False, want_mask=False, hist=None, slot=None, T=1, transformer=None, idx_out=None):
+    @property
+    def grouped(self) -> bool:
+        return len(self._tables) > 1
+
+    def _rank_on(self, device):
         torch = _lib.require_cuda()
+        r = self._rank_dev.get(device)
+        if r is None:
+            r = self._rank_dev[device] = torch.from_numpy(self._rank).to(device)
+        return r
+
+    def _launch_grouped(self, pts, *, want_idx=False, want_mask=False, hist=None, slot=None, T=1, transformer=None, idx_out=None):
+        """More than 64 zones: one launch per group of 64, then the combine kernel (and the histogram kernel for counts)."""
+        torch = _lib.require_cuda()
+        n, G, Z = pts.shape[0], len(self._tables), len(self.zones)
+        idx_g = torch.empty((G, n), dtype=torch.int32, device=pts.device)
+        masks = torch.empty((n, G), dtype=torch.int64, device=pts.device) if (want_mask or (hist is not None and self.allow_overlap)) else None
+        for g, table in enumerate(self._tables):
+            _, m = self._launch(pts, table=table, want_mask=masks is not None, transformer=transformer, idx_out=idx_g[g])
+            if masks is not None:
+                masks[:, g] = m
+        idx = idx_out if idx_out is not None else torch.empty((n,), dtype=torch.int32, device=pts.device)
+        if slot is not None:
+            slot = slot.to(device=pts.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(pts.device):
+            _lib.check(_lib.lib().opd_zone_combine_groups(_lib.ptr(idx_g), _lib.ptr(self._rank_on(pts.device)), G, n, _lib.ptr(idx), None,
+                                                          _lib.stream_ptr()), "opd_zone_combine_groups")
+            if slot is not None:     # rows outside [0, T) are unused rows: not classified, not counted
+                idx.masked_fill_((slot < 0) | (slot >= T), -1)
+            if hist is not None:
+                if not self.allow_overlap:
+                    _lib.check(_lib.lib().opd_zone_histogram(_lib.ptr(idx), None, _lib.ptr(slot), n, Z, T, _lib.ptr(hist), _lib.stream_ptr()),
+                               "opd_zone_histogram")
+                else:
+                    # one count per containing zone (aggregator.py:66-69): per-group mask histograms into the group's columns, the
+                    # "unclassified" column from the combined index
+                    M = _lib.OPD_MAX_ZONES
+                    tmp = torch.zeros((T, Z + 1), dtype=torch.int32, device=pts.device)
+                    _lib.check(_lib.lib().opd_zone_histogram(_lib.ptr(idx), None, _lib.ptr(slot), n, Z, T, _lib.ptr(tmp), _lib.stream_ptr()),
+                               "opd_zone_histogram")
+                    hist[:, Z] += tmp[:, Z]
+                    for g, table in enumerate(self._tables):
+                        hg = torch.zeros((T, table.Z + 1), dtype=torch.int32, device=pts.device)
+                        mg = masks[:, g].contiguous()
+                        _lib.check(_lib.lib().opd_zone_histogram(None, _lib.ptr(mg), _lib.ptr(slot), n, table.Z, T, _lib.ptr(hg),
+                                                                 _lib.stream_ptr()), "opd_zone_histogram")
+                        hist[:, g * M:g * M + table.Z] += hg[:, :table.Z]
+        return (idx if (want_idx or idx_out is not None) else None), masks
+
+    def _launch(self, pts, *, want_idx=False, want_mask=False, hist=None, slot=None, T=1, transformer=None, idx_out=None, table=None):
+        torch = _lib.require_cuda()
+        if table is None and self.grouped:
+            return self._launch_grouped(pts.contiguous(), want_idx=want_idx, want_mask=want_mask, hist=hist, slot=slot, T=T,
+                                        transformer=transformer, idx_out=idx_out)
+        table = table or self._table
         if pts.dim() != 2 or pts.shape[1] != 2 or not pts.is_cuda:
             raise ValueError("points must be a CUDA tensor of shape [N,2]")
         if pts.dtype not in (torch.float32, torch.float64):
@@ -151,7 +216,7 @@ class ZoneClassifier:
         fn = (_lib.lib().opd_floor_project_classify_count_f64 if pts.dtype == torch.float64
               else _lib.lib().opd_floor_project_classify_count_f32)
         with torch.cuda.device(pts.device):
-            zt = self._table.handle(pts.device.index)
+            zt = table.handle(pts.device.index)
             _lib.check(fn(params, zt, _lib.ptr(pts), _lib.ptr(slot), n, T, None, None, None, _lib.ptr(idx),
                           _lib.ptr(mask), _lib.ptr(hist), _lib.stream_ptr()), "classify")
         return idx, mask
@@ -165,7 +230,8 @@ class ZoneClassifier:
         return self._launch(points, want_idx=True, transformer=transformer)[0]
 
     def classify_masks(self, points, transformer=None):
-        """[N,2] CUDA tensor -> int64 [N] bit mask of containing zones (bit z = zone z)."""
+        """[N,2] CUDA tensor -> int64 [N] bit mask of containing zones (bit z = zone z); with more than 64 zones int64 [N, G], word g
+        holding zones 64 g .. 64 g + 63."""
         return self._launch(points, want_mask=True, transformer=transformer)[1]
 
     def count(self, points, slot=None, num_slots: int = 1, transformer=None, out=None, return_index: bool = False,
@@ -175,9 +241,10 @@ class ZoneClassifier:
         Accumulates into `out` when given (that is what the multi-GPU all-reduce sums).  `index_out` (int32 [N]) receives the
         zone index of every point (steady-state loops: no allocation per call); `return_index` allocates it."""
         torch = _lib.require_cuda()
+        Z = len(self.zones)
         if out is None:
-            out = torch.zeros((num_slots, self._table.Z + 1), dtype=torch.int32, device=points.device)
-        elif tuple(out.shape) != (num_slots, self._table.Z + 1) or out.dtype != torch.int32 or not out.is_contiguous():
+            out = torch.zeros((num_slots, Z + 1), dtype=torch.int32, device=points.device)
+        elif tuple(out.shape) != (num_slots, Z + 1) or out.dtype != torch.int32 or not out.is_contiguous():
             raise ValueError("out must be a contiguous int32 [num_slots, Z+1] tensor")
         idx, _ = self._launch(points, want_idx=return_index, hist=out, slot=slot, T=num_slots, transformer=transformer,
                               idx_out=index_out)
@@ -201,7 +268,16 @@ class ZoneClassifier:
         arr = np.array([(float(p[0]), float(p[1])) for p in floor_points], dtype=np.float64).reshape(-1, 2)
         pts = torch.from_numpy(arr).to(torch.device("cuda", torch.cuda.current_device()))
         _, mask = self._launch(pts, want_mask=True)
-        return [self._ids_from_mask(int(m) & 0xFFFFFFFFFFFFFFFF) for m in mask.cpu().numpy().astype(np.uint64)]
+        words = mask.cpu().numpy().astype(np.uint64).reshape(len(arr), -1)      # [N, G] (G = 1 up to 64 zones)
+        M = _lib.OPD_MAX_ZONES
+        if self.allow_overlap:
+            return [self._ids_from_mask(sum(int(w) << (M * g) for g, w in enumerate(row))) for row in words]
+        # single label: every group's table already picked its own winner; keep the best of them by the global rank
+        out = []
+        for row in words:
+            hits = [M * g + int(w).bit_length() - 1 for g, w in enumerate(row) if w]
+            out.append([self._ids[min(hits, key=lambda z: self._rank[z])]] if hits else [])
+        return out
 
     def classify(self, floor_point: tuple[float, float]) -> list[str]:
         """Zone ids containing the point; [] when outside every zone (zone_classifier.py:114-149)."""

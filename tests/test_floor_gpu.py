@@ -225,5 +225,48 @@ def test_zone_table_info_and_limits(torch_cuda, built_lib):
     info = zc.table.info()
     assert info["grid_w"] * info["grid_h"] <= 160 * 1024 and info["boundary_cells"] > 0
     assert info["boundary_cells"] < 0.12 * info["grid_w"] * info["grid_h"]
-    with pytest.raises(NotImplementedError):
-        ZoneClassifier(fo.grid_zones(65))
+
+
+@pytest.mark.parametrize("allow_overlap", [False, True])
+def test_more_than_64_zones(allow_overlap, torch_cuda, built_lib):
+    """The reference sets no limit on the number of zones (zone_classifier.py:44-112): 100 zones = two device tables + the combine
+    kernel.  Checked against the line-by-line Python restatement of classify (the C oracle's masks are 64-bit): zone ids per point
+    through the object surface, the tensor index, and the [T, Z + 1] histogram with per-timestamp slots."""
+    import math
+
+    torch = torch_cuda
+    from office_person_detection_vit_b200.zone import ZoneClassifier
+
+    zones = fo.star_zones(100, seed=6)
+    zones[70]["priority"] = 0.5          # a late zone that beats every earlier one where they overlap
+    zones += [{"id": "wide", "polygon": [[200.0, 150.0], [1700.0, 180.0], [1650.0, 1200.0], [250.0, 1150.0]], "priority": 1e6}]
+    Z = len(zones)
+    zc = ZoneClassifier(zones, allow_overlap=allow_overlap)
+    assert zc.grouped and zc.get_zone_count() == Z
+    rng = np.random.default_rng(5)
+    n = 3000
+    pts = np.stack([rng.uniform(-50, 1950, n), rng.uniform(-50, 1420, n)], axis=1)
+    slot = rng.integers(0, 3, n).astype(np.int32)
+    ids = [z["id"] for z in zones]
+    exp_ids, exp_idx = [], []
+    for x, y in pts:
+        hit = [i for i, z in enumerate(zones) if fo.point_in_polygon_py(float(x), float(y), z["polygon"])]
+        win = min(hit, key=lambda i: (math.inf if zones[i]["priority"] is None else zones[i]["priority"], i)) if hit else -1
+        exp_idx.append(win)
+        exp_ids.append([ids[i] for i in hit] if allow_overlap else ([ids[win]] if hit else []))
+    got = zc.classify_batch([tuple(p) for p in pts])
+    assert got == exp_ids
+    assert sum(len(e) > 1 for e in exp_ids) > 50 or not allow_overlap
+    d = torch.from_numpy(pts).cuda()
+    idx = zc.classify_points(d).cpu().numpy()
+    assert (idx == np.array(exp_idx)).all()
+    assert (idx >= 64).sum() > 100                                   # zones of the second table are really used
+    hist = zc.count(d, slot=torch.from_numpy(slot).cuda(), num_slots=3).cpu().numpy()
+    exp_hist = np.zeros((3, Z + 1), np.int64)
+    for s_, e in zip(slot, exp_ids):
+        for zid in e:
+            exp_hist[s_, ids.index(zid)] += 1
+        if not e:
+            exp_hist[s_, Z] += 1
+    assert (hist == exp_hist).all()
+    assert zc.counts_to_dicts(torch.from_numpy(hist))[0] == {([*ids, "unclassified"])[j]: int(c) for j, c in enumerate(exp_hist[0]) if c}
