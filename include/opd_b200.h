@@ -201,6 +201,19 @@ int opd_detr_workspace_bytes(const opd_detr* m, int32_t B, int32_t H0, int32_t W
 int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t H0, int32_t W0,
                      int32_t frames_are_bgr, void* workspace_dev, size_t workspace_bytes, float* logits_dev,
                      float* boxes_dev, void* stream);
+/* Batches that mix frame sizes (the removed ViTDetector._preprocess_batch, coverage.json lines 562-578: DetrImageProcessor pads to
+ * the batch maximum and returns pixel_mask; models/detr/image_processing_detr.py:638-667 pad, modeling_detr.py:281-283 mask
+ * downsampling, :322-349 mask-aware sine embedding, :386-411 key-padding mask): the batch is given group after group, n frames of one
+ * size per group; every frame is resized on its own (800 / 1333 rule), placed in the top-left corner of a canvas of the largest model
+ * input size, padded with zeros AFTER normalisation, and the transformer masks the padded feature cells.  Outputs in group order. */
+typedef struct opd_frame_group {
+  const uint8_t* frames_dev; /* [n, H0, W0, 3] uint8 */
+  int32_t n, H0, W0;
+  int32_t frames_are_bgr;
+} opd_frame_group;
+int opd_detr_workspace_bytes_mixed(const opd_detr* m, const opd_frame_group* groups, int32_t n_groups, size_t* bytes);
+int opd_detr_forward_mixed(opd_detr* m, const opd_frame_group* groups, int32_t n_groups, void* workspace_dev,
+                           size_t workspace_bytes, float* logits_dev, float* boxes_dev, void* stream);
 /* Per-kernel timing of one more forward with the arguments of the last opd_detr_forward: a CUDA event is recorded
  * on `stream` between consecutive launches (the kernels still run back to back on that stream).  Synchronises.
  * Call with max_steps = 0 to get *n_steps.  kinds[i] is an opd_step_kind, flops[i] / bytes[i] are the ALGORITHMIC

@@ -1,7 +1,7 @@
 // K6: fused multi-head attention on the 5th-generation tensor cores (head_dim 32, bf16 in, fp32 softmax):
 //     o = softmax(q k^T / sqrt(32)) v          per (batch, head)
 // replaces transformers models/detr/modeling_detr.py:386-411 (eager_attention_forward) inside DetrSelfAttention /
-// DetrCrossAttention (:414-557); no key-padding mask (all frames of a batch have one size).
+// DetrCrossAttention (:414-557), including the key-padding mask of padded batches (masked keys get probability 0).
 //
 // One CTA = 128 query rows of one (batch, head); key/value tiles of 128 stream through a 2-stage TMA ring.
 //   warp 0   TMA producer: Q tile once, then K_j / V_j tiles ([128 x 32] bf16, 64-byte rows, 64-byte swizzle)
@@ -41,6 +41,8 @@ struct AttnParams {
   __nv_bfloat16* o;
   long long ldo;
   int Lq, Lk;
+  const uint32_t* key_mask;   // [B, key_mask_stride] 32-key words, or nullptr (see AttnPlan)
+  int key_mask_stride;
 };
 
 // shared-memory descriptors: 64-byte swizzle (rows of 32 bf16), 8-row groups 512 B apart; 128-byte swizzle for P
@@ -196,20 +198,29 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after_sync();
       const int valid = p.Lk - j * kKV;           // keys of this tile that exist (>= kKV: all)
-      // pass 1: row maximum (3-input max; only the last tile of a row of tiles needs the key mask)
+      // keys of each 32-key chunk that take part: those that exist (the last tile of a row of tiles is ragged) and, in a padded
+      // batch, are not padding; all-ones for almost every chunk -> the fast loops
+      uint32_t kbits[kKV / 32];
+#pragma unroll
+      for (int c = 0; c < kKV / 32; ++c) {
+        const int left = valid - c * 32;
+        kbits[c] = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : (1u << left) - 1u);
+        if (p.key_mask) kbits[c] &= p.key_mask[(long long)b * p.key_mask_stride + (j * kKV) / 32 + c];
+      }
+      // pass 1: row maximum (3-input max)
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < kKV / 32; ++c) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
         ptx::tmem_ld_wait();
-        if (valid >= (c + 1) * 32) {
+        if (kbits[c] == 0xFFFFFFFFu) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if ((kbits[c] >> i) & 1u) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
       }
       const float m_new = fmaxf(m, mx * sl2);
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
         ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
         ptx::tmem_ld_wait();
         uint32_t packed[16];
-        if (valid >= (c + 1) * 32) {
+        if (kbits[c] == 0xFFFFFFFFu) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float x0, x1;
@@ -243,8 +254,8 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
           for (int i = 0; i < 16; ++i) {
             float a = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, -m_new));
             float bb = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_new));
-            if (c * 32 + 2 * i >= valid) a = 0.f;
-            if (c * 32 + 2 * i + 1 >= valid) bb = 0.f;
+            if (!((kbits[c] >> (2 * i)) & 1u)) a = 0.f;
+            if (!((kbits[c] >> (2 * i + 1)) & 1u)) bb = 0.f;
             lsum += a + bb;
             packed[i] = ptx::pack_bf16(a, bb);
           }
@@ -339,6 +350,7 @@ int attn_launch(const AttnPlan& plan, cudaStream_t stream) {
   AttnParams p;
   p.tmQ = plan.tmQ; p.tmK = plan.tmK; p.tmV = plan.tmV;
   p.o = plan.o; p.ldo = plan.ldo; p.Lq = plan.Lq; p.Lk = plan.Lk;
+  p.key_mask = plan.key_mask; p.key_mask_stride = plan.key_mask_stride;
   static PerDeviceOnce configured;
   if (int rc = once_per_device(configured, []() -> int {
         OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128>::kSmemBytes));

@@ -74,8 +74,14 @@ struct Step {
   std::string name;
 };
 
+struct FrameGroup {   // n frames of one size (a batch may mix sizes: opd_detr_forward_mixed)
+  int n, H0, W0;
+  bool operator==(const FrameGroup& o) const { return n == o.n && H0 == o.H0 && W0 == o.W0; }
+};
+
 struct Plan {
   int B = 0, H0 = 0, W0 = 0;
+  std::vector<FrameGroup> groups;
   void* ws = nullptr;
   size_t ws_bytes = 0;
   std::vector<Step> steps;
@@ -108,6 +114,8 @@ struct opd_detr {
   // per-call arguments read by the plan's steps
   const uint8_t* cur_frames = nullptr;
   int cur_bgr = 1;
+  std::vector<const uint8_t*> cur_group_frames;   // mixed-size batches: one frame block per group
+  std::vector<int> cur_group_bgr;
   float* cur_logits = nullptr;
   float* cur_boxes = nullptr;
   // Launch plans, most recently used first, one per (B, H0, W0, workspace): a stream that alternates between batch shapes (a short
@@ -505,10 +513,34 @@ struct Arena {
   }
 };
 
+// torch.nn.functional.interpolate(mask, size=(out,)) in its default "nearest" mode: source index of output index i
+// (modeling_detr.py:281-283 downsamples pixel_mask to the feature map this way)
+inline int nearest_src(int i, int in_size, int out_size) {
+  const float scale = (float)in_size / (float)out_size;
+  const int src = (int)floorf((float)i * scale);
+  return src < in_size - 1 ? src : in_size - 1;
+}
+
 // Builds the launch plan.  With ws == nullptr only the workspace size is computed (no tensor maps are encoded).
-int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t* bytes_out) {
+// `groups`: the batch, group after group; more than one frame size -> every frame is resized on its own (800 / 1333 rule), placed
+// in the top-left corner of a canvas of the largest model input size and the rest of the path runs with DetrImageProcessor's
+// pixel_mask semantics (zero padding after normalisation, mask-aware sine embedding, key-padding mask in the attentions).
+int build_plan(opd_detr* m, const std::vector<FrameGroup>& groups, void* ws, Plan* plan, size_t* bytes_out) {
   const bool dry = ws == nullptr;
-  const Shapes sh = shapes_for(H0, W0, m->do_resize != 0);
+  int B = 0;
+  for (const FrameGroup& g : groups) B += g.n;
+  // model input size of every group and of the batch canvas
+  std::vector<std::pair<int, int>> gin(groups.size());
+  int Hc = 0, Wc = 0;
+  for (size_t i = 0; i < groups.size(); ++i) {
+    gin[i] = {groups[i].H0, groups[i].W0};
+    if (m->do_resize) resized_size(groups[i].H0, groups[i].W0, &gin[i].first, &gin[i].second);
+    Hc = std::max(Hc, gin[i].first);
+    Wc = std::max(Wc, gin[i].second);
+  }
+  const bool mixed = groups.size() > 1;
+  const int H0 = mixed ? Hc : groups[0].H0, W0 = mixed ? Wc : groups[0].W0;
+  const Shapes sh = shapes_for(H0, W0, !mixed && m->do_resize != 0);
   OPD_REQUIRE(sh.Hs >= 4 && sh.h[3] >= 1 && sh.w[3] >= 1, "detr: frames of %dx%d are too small", H0, W0);
   OPD_REQUIRE(sh.Hs == (sh.Hin + 1) / 2 && sh.Ws == (sh.Win + 1) / 2, "detr: unexpected stem geometry");
   Arena A{static_cast<uint8_t*>(ws)};
@@ -576,6 +608,55 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
     }
   }
 
+  // ---- mixed-size batch: every group is resized (or copied) into the top-left corner of its frames of one uint8 canvas ----
+  int32_t* valid_hw = nullptr;   // [B, 2] picture size of every frame inside the canvas (device)
+  if (mixed) {
+    OPD_REQUIRE(m->stem_halo != 0, "detr: mixed-size batches need the space-to-depth stem path");
+    const long long frame_stride = (long long)Hc * Wc * 3, row_pitch = (long long)Wc * 3;
+    resized = static_cast<uint8_t*>(A.take((size_t)B * frame_stride));
+    valid_hw = static_cast<int32_t*>(A.take((size_t)B * 2 * sizeof(int32_t)));
+    std::vector<int32_t> hv;
+    int b0 = 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      const FrameGroup g = groups[gi];
+      const int H1 = gin[gi].first, W1 = gin[gi].second;
+      for (int i = 0; i < g.n; ++i) {
+        hv.push_back(H1);
+        hv.push_back(W1);
+      }
+      uint8_t* dst = resized + (size_t)b0 * frame_stride;
+      if (H1 != g.H0 || W1 != g.W0) {
+        const ResizeTable tx = resize_table(g.W0, W1), ty = resize_table(g.H0, H1);
+        uint8_t* tmp = static_cast<uint8_t*>(A.take((size_t)g.n * g.H0 * W1 * 3));
+        int16_t* wx = static_cast<int16_t*>(A.take(tx.w.size() * sizeof(int16_t)));
+        int32_t* x0 = static_cast<int32_t*>(A.take(tx.x0.size() * sizeof(int32_t)));
+        int16_t* wy = static_cast<int16_t*>(A.take(ty.w.size() * sizeof(int16_t)));
+        int32_t* y0 = static_cast<int32_t*>(A.take(ty.x0.size() * sizeof(int32_t)));
+        if (!dry) {
+          OPD_CUDA_OK(cudaMemcpy(wx, tx.w.data(), tx.w.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+          OPD_CUDA_OK(cudaMemcpy(x0, tx.x0.data(), tx.x0.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+          OPD_CUDA_OK(cudaMemcpy(wy, ty.w.data(), ty.w.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+          OPD_CUDA_OK(cudaMemcpy(y0, ty.x0.data(), ty.x0.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+          const int kx = tx.ksize, px = tx.precision, ky = ty.ksize, py = ty.precision;
+          add(OPD_STEP_ELEMENTWISE, "resize", 0.0, 3.0 * g.n * ((double)g.H0 * g.W0 + 2.0 * g.H0 * W1 + (double)H1 * W1),
+              [=](cudaStream_t st) {
+                return launch_resize_u8(m->cur_group_frames[gi], g.n, g.H0, g.W0, m->cur_group_bgr[gi], tmp, dst, H1, W1, wx, x0, kx, px,
+                                        wy, y0, ky, py, st, frame_stride, row_pitch);
+              });
+        }
+      } else if (!dry) {
+        add(OPD_STEP_ELEMENTWISE, "copy_to_canvas", 0.0, 6.0 * g.n * g.H0 * g.W0, [=](cudaStream_t st) {
+          return launch_copy_into_canvas(m->cur_group_frames[gi], g.n, g.H0, g.W0, m->cur_group_bgr[gi], dst, frame_stride, row_pitch, st);
+        });
+      }
+      b0 += g.n;
+    }
+    if (!dry) {
+      OPD_CUDA_OK(cudaMemcpy(valid_hw, hv.data(), hv.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      taps["resized_u8"] = {resized, (long long)B * Hc * Wc, 3, 2};
+    }
+  }
+
   // ---- K1 preprocess: -> S [B, Hs, Ws, 16] (stem_conv.cu) or, on the im2col fallback path, X2 [B, Hs, Ws, 64] ----
   const bool stem_halo = m->stem_halo != 0;
   bf16* x2 = static_cast<bf16*>(big_slot(0, act_bytes(Ms, stem_halo ? 16 : 64)));
@@ -583,8 +664,8 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
     const uint8_t* fixed_src = resized;
     if (stem_halo) {
       add(OPD_STEP_ELEMENTWISE, "preprocess", 0.0, (double)B * sh.Hin * sh.Win * 3 + (double)act_bytes(Ms, 16),
-          [m, B, sh, x2, fixed_src](cudaStream_t s) {
-            return fixed_src ? launch_preprocess_s2d(fixed_src, B, sh.Hin, sh.Win, 0, x2, s)
+          [m, B, sh, x2, fixed_src, valid_hw](cudaStream_t s) {
+            return fixed_src ? launch_preprocess_s2d(fixed_src, B, sh.Hin, sh.Win, 0, x2, s, valid_hw)
                              : launch_preprocess_s2d(m->cur_frames, B, sh.Hin, sh.Win, m->cur_bgr, x2, s);
           });
     } else {
@@ -735,7 +816,12 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
   // ---- transformer ----
   const int S = hh * ww;
   const int M = B * S, Mq = B * kQueries;
-  float* pos = static_cast<float*>(A.take((size_t)S * kD * sizeof(float)));
+  // sine position table: [S, 256] shared by the batch, or [B, S, 256] (one per frame: it depends on the frame's mask) when padded
+  const int pos_rows = mixed ? B * S : S;
+  float* pos = static_cast<float*>(A.take((size_t)pos_rows * kD * sizeof(float)));
+  const int mask_words = (S + 31) / 32 + 4;   // 32-key words per frame (+ slack for the tiles' whole-word reads past S)
+  uint32_t* key_mask = mixed ? static_cast<uint32_t*>(A.take((size_t)B * mask_words * sizeof(uint32_t))) : nullptr;
+  int32_t* fvalid = mixed ? static_cast<int32_t*>(A.take((size_t)B * 2 * sizeof(int32_t))) : nullptr;
   bf16* ex = static_cast<bf16*>(A.take(act_bytes(M, kD)));     // encoder stream
   bf16* ex1 = static_cast<bf16*>(A.take(act_bytes(M, kD)));    // after attention + LN
   bf16* exp_ = static_cast<bf16*>(A.take(act_bytes(M, kD)));   // stream + pos (q / k input)
@@ -775,11 +861,40 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
     return OPD_OK;
   };
   int attn_rc = OPD_OK;
+  if (mixed) {
+    OPD_REQUIRE(g_option_attention_tc.load(), "detr: mixed-size batches need the tcgen05 attention kernel (key-padding mask)");
+    // pixel_mask -> feature mask by nearest interpolation (modeling_detr.py:281-283): frame b keeps the feature cells whose source
+    // pixel lies inside its picture - a top-left rectangle (fh, fw); keys outside it are masked in every attention over the map
+    std::vector<int32_t> fv;
+    std::vector<uint32_t> words((size_t)B * mask_words, 0u);
+    int b = 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      int fh = 0, fw = 0;
+      for (int y = 0; y < hh; ++y) fh += nearest_src(y, Hc, hh) < gin[gi].first;
+      for (int x = 0; x < ww; ++x) fw += nearest_src(x, Wc, ww) < gin[gi].second;
+      OPD_REQUIRE(fh >= 1 && fw >= 1, "detr: a frame of the mixed batch has no valid feature cell");
+      for (int i = 0; i < groups[gi].n; ++i, ++b) {
+        fv.push_back(fh);
+        fv.push_back(fw);
+        for (int y = 0; y < fh; ++y)
+          for (int x = 0; x < fw; ++x) {
+            const int k = y * ww + x;
+            words[(size_t)b * mask_words + k / 32] |= 1u << (k % 32);
+          }
+      }
+    }
+    OPD_CUDA_OK(cudaMemcpy(fvalid, fv.data(), fv.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    OPD_CUDA_OK(cudaMemcpy(key_mask, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
   auto attn = [&](const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int Lq, int Lk) {
     const double flops = 4.0 * B * kHeads * (double)Lq * Lk * 32, bytes = 2.0 * B * kD * (2.0 * Lq + 2.0 * Lk);
     if (g_option_attention_tc.load()) {
       AttnPlan ap;
       attn_rc = attn_plan(&ap, q, ldq, k, ldk, v, ldv, o, kD, B, kHeads, Lq, Lk);
+      if (mixed && Lk == S) {   // attention over the feature map (encoder self-attention, decoder cross-attention)
+        ap.key_mask = key_mask;
+        ap.key_mask_stride = mask_words;
+      }
       add(OPD_STEP_ATTENTION, cur_name, flops, bytes, [ap](cudaStream_t s) { return attn_launch(ap, s); });
     } else {
       add(OPD_STEP_ATTENTION, cur_name, flops, bytes,
@@ -787,11 +902,15 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
     }
   };
 
-  add(OPD_STEP_ELEMENTWISE, "pos_embed", 0.0, 4.0 * S * kD, [pos, hh, ww](cudaStream_t s) { return launch_pos_embed(pos, hh, ww, s); });
+  if (mixed)
+    add(OPD_STEP_ELEMENTWISE, "pos_embed", 0.0, 4.0 * B * S * kD,
+        [pos, B, hh, ww, fvalid](cudaStream_t s) { return launch_pos_embed_masked(pos, B, hh, ww, fvalid, s); });
+  else
+    add(OPD_STEP_ELEMENTWISE, "pos_embed", 0.0, 4.0 * S * kD, [pos, hh, ww](cudaStream_t s) { return launch_pos_embed(pos, hh, ww, s); });
   cur_name = "input_proj";
-  taps["pos"] = {pos, S, kD, 1};
+  taps["pos"] = {pos, pos_rows, kD, 1};
   // input_projection (+ pos for the first layer's q / k input)
-  if (int rc = linear(x, M, m->input_proj, ex, EPI_BIAS, nullptr, nullptr, exp_, pos, S)) return rc;
+  if (int rc = linear(x, M, m->input_proj, ex, EPI_BIAS, nullptr, nullptr, exp_, pos, pos_rows)) return rc;
   taps["enc_in"] = {ex, M, kD, 0};
 
   bf16* xin = ex;
@@ -813,7 +932,7 @@ int build_plan(opd_detr* m, int B, int H0, int W0, void* ws, Plan* plan, size_t*
     if (int rc = linear(ex1, M, e.fc1, ef, EPI_BIAS_RELU, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
     // layer output overwrites the layer input stream (its last reader, the o_proj residual, has completed)
     cur_name = ln + ".fc2+ln";
-    if (int rc = linear(ef, M, e.fc2, xout, EPI_BIAS_RES_LN, ex1, &e.ln2, exp_, pos, S)) return rc;
+    if (int rc = linear(ef, M, e.fc2, xout, EPI_BIAS_RES_LN, ex1, &e.ln2, exp_, pos, pos_rows)) return rc;
     taps["enc" + std::to_string(i)] = {xout, M, kD, 0};
     xin = xout;
   }
@@ -956,7 +1075,93 @@ int opd_detr_input_shape(int32_t H0, int32_t W0, int32_t* H_in, int32_t* W_in, i
 int opd_detr_workspace_bytes(const opd_detr* m, int32_t B, int32_t H0, int32_t W0, size_t* bytes) {
   OPD_REQUIRE(m && bytes && B > 0 && H0 > 0 && W0 > 0, "opd_detr_workspace_bytes: bad argument");
   opd::Plan scratch;
-  return opd::build_plan(const_cast<opd_detr*>(m), B, H0, W0, nullptr, &scratch, bytes);
+  return opd::build_plan(const_cast<opd_detr*>(m), {opd::FrameGroup{B, H0, W0}}, nullptr, &scratch, bytes);
+}
+
+namespace {
+int groups_from_abi(const opd_frame_group* groups, int32_t n_groups, std::vector<opd::FrameGroup>* out, bool need_frames) {
+  OPD_REQUIRE(groups && n_groups >= 1 && n_groups <= 64, "detr: 1 .. 64 frame groups (got %d)", n_groups);
+  long long B = 0;
+  for (int i = 0; i < n_groups; ++i) {
+    OPD_REQUIRE(groups[i].n > 0 && groups[i].H0 > 0 && groups[i].W0 > 0 && (!need_frames || groups[i].frames_dev),
+                "detr: frame group %d is empty or has no frames", i);
+    out->push_back(opd::FrameGroup{groups[i].n, groups[i].H0, groups[i].W0});
+    B += groups[i].n;
+  }
+  OPD_REQUIRE(B * opd::kQueries < (1 << 24), "detr: bad batch %lld", B);
+  return OPD_OK;
+}
+
+// finds or builds the plan of this batch description (most recently used first) and makes it current
+int select_plan(opd_detr* m, const std::vector<opd::FrameGroup>& groups, void* workspace_dev, size_t workspace_bytes) {
+  auto hit = m->plans.begin();
+  for (; hit != m->plans.end(); ++hit)
+    if (hit->groups == groups && hit->ws == workspace_dev && !hit->steps.empty()) break;
+  if (hit != m->plans.end()) {
+    m->plans.splice(m->plans.begin(), m->plans, hit);   // list nodes do not move: m->plan stays valid
+  } else {
+    m->plan = nullptr;
+    m->plans.emplace_front();
+    opd::Plan& fresh = m->plans.front();
+    size_t need = 0;
+    int rc = opd::build_plan(m, groups, workspace_dev, &fresh, &need);
+    if (rc == OPD_OK && need > workspace_bytes)
+      rc = opd::fail(OPD_ERR_INVALID, "opd_detr_forward: workspace of %zu bytes, %zu needed", workspace_bytes, need);
+    if (rc != OPD_OK) {
+      m->plans.pop_front();
+      return rc;
+    }
+    fresh.groups = groups;
+    fresh.B = 0;
+    for (const auto& g : groups) fresh.B += g.n;
+    fresh.H0 = groups[0].H0; fresh.W0 = groups[0].W0; fresh.ws = workspace_dev; fresh.ws_bytes = need;
+    while (m->plans.size() > kMaxPlans) m->plans.pop_back();
+  }
+  m->plan = &m->plans.front();
+  return OPD_OK;
+}
+
+int run_plan(opd_detr* m, cudaStream_t s) {
+  opd::Plan& p = *m->plan;
+  if (!p.once_done) {   // frame-independent prologue: on the same stream, ahead of the first step of this plan
+    for (auto& step : p.once)
+      if (int rc = step.run(s)) return rc;
+    p.once_done = true;
+  }
+  for (auto& step : p.steps)
+    if (int rc = step.run(s)) return rc;
+  return OPD_OK;
+}
+}  // namespace
+
+int opd_detr_workspace_bytes_mixed(const opd_detr* m, const opd_frame_group* groups, int32_t n_groups, size_t* bytes) {
+  OPD_REQUIRE(m && bytes, "opd_detr_workspace_bytes_mixed: NULL argument");
+  std::vector<opd::FrameGroup> g;
+  if (int rc = groups_from_abi(groups, n_groups, &g, false)) return rc;
+  opd::Plan scratch;
+  return opd::build_plan(const_cast<opd_detr*>(m), g, nullptr, &scratch, bytes);
+}
+
+int opd_detr_forward_mixed(opd_detr* m, const opd_frame_group* groups, int32_t n_groups, void* workspace_dev, size_t workspace_bytes,
+                           float* logits_dev, float* boxes_dev, void* stream) {
+  OPD_REQUIRE(m && workspace_dev && logits_dev && boxes_dev, "opd_detr_forward_mixed: NULL argument");
+  OPD_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) == 0, "opd_detr_forward_mixed: workspace must be 1024-byte aligned");
+  std::vector<opd::FrameGroup> g;
+  if (int rc = groups_from_abi(groups, n_groups, &g, true)) return rc;
+  opd::DeviceGuard guard(m->device);
+  OPD_CUDA_OK(guard.err);
+  if (int rc = select_plan(m, g, workspace_dev, workspace_bytes)) return rc;
+  m->cur_group_frames.clear();
+  m->cur_group_bgr.clear();
+  for (int i = 0; i < n_groups; ++i) {
+    m->cur_group_frames.push_back(groups[i].frames_dev);
+    m->cur_group_bgr.push_back(groups[i].frames_are_bgr);
+  }
+  m->cur_frames = groups[0].frames_dev;   // a one-group batch runs the plain path
+  m->cur_bgr = groups[0].frames_are_bgr;
+  m->cur_logits = logits_dev;
+  m->cur_boxes = boxes_dev;
+  return run_plan(m, static_cast<cudaStream_t>(stream));
 }
 
 int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t H0, int32_t W0, int32_t frames_are_bgr,
@@ -966,41 +1171,12 @@ int opd_detr_forward(opd_detr* m, const uint8_t* frames_dev, int32_t B, int32_t 
   OPD_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) == 0, "opd_detr_forward: workspace must be 1024-byte aligned");
   opd::DeviceGuard guard(m->device);   // the handle's device, whatever the caller's current device is
   OPD_CUDA_OK(guard.err);
-  auto hit = m->plans.begin();
-  for (; hit != m->plans.end(); ++hit)
-    if (hit->B == B && hit->H0 == H0 && hit->W0 == W0 && hit->ws == workspace_dev && !hit->steps.empty()) break;
-  if (hit != m->plans.end()) {
-    m->plans.splice(m->plans.begin(), m->plans, hit);   // most recently used first (list nodes do not move: m->plan stays valid)
-  } else {
-    m->plan = nullptr;
-    m->plans.emplace_front();
-    opd::Plan& fresh = m->plans.front();
-    size_t need = 0;
-    int rc = opd::build_plan(m, B, H0, W0, workspace_dev, &fresh, &need);
-    if (rc == OPD_OK && need > workspace_bytes)
-      rc = opd::fail(OPD_ERR_INVALID, "opd_detr_forward: workspace of %zu bytes, %zu needed", workspace_bytes, need);
-    if (rc != OPD_OK) {
-      m->plans.pop_front();
-      return rc;
-    }
-    fresh.B = B; fresh.H0 = H0; fresh.W0 = W0; fresh.ws = workspace_dev; fresh.ws_bytes = need;
-    while (m->plans.size() > kMaxPlans) m->plans.pop_back();
-  }
-  m->plan = &m->plans.front();
-  opd::Plan& p = *m->plan;
+  if (int rc = select_plan(m, {opd::FrameGroup{B, H0, W0}}, workspace_dev, workspace_bytes)) return rc;
   m->cur_frames = frames_dev;
   m->cur_bgr = frames_are_bgr;
   m->cur_logits = logits_dev;
   m->cur_boxes = boxes_dev;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!p.once_done) {   // frame-independent prologue: on the same stream, ahead of the first step of this plan
-    for (auto& step : p.once)
-      if (int rc = step.run(s)) return rc;
-    p.once_done = true;
-  }
-  for (auto& step : p.steps)
-    if (int rc = step.run(s)) return rc;
-  return OPD_OK;
+  return run_plan(m, static_cast<cudaStream_t>(stream));
 }
 
 int opd_detr_profile(opd_detr* m, void* stream, int32_t max_steps, int32_t* n_steps, int32_t* kinds, double* flops,

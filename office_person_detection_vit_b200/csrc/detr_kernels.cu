@@ -95,7 +95,8 @@ __global__ void resize_h_kernel(const uint8_t* __restrict__ src, int B, int H0, 
 }
 
 __global__ void resize_v_kernel(const uint8_t* __restrict__ tmp, int B, int H0, int W1, uint8_t* __restrict__ dst,
-                                int H1, const int16_t* __restrict__ wy, const int32_t* __restrict__ y0, int ky, int py) {
+                                int H1, const int16_t* __restrict__ wy, const int32_t* __restrict__ y0, int ky, int py,
+                                long long dst_frame_stride, long long dst_row_pitch) {
   const long long total = (long long)B * H1 * W1 * 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -109,7 +110,24 @@ __global__ void resize_v_kernel(const uint8_t* __restrict__ tmp, int B, int H0, 
       const int w = wy[oy * ky + j];
       if (w != 0) acc += (int)s[(long long)j * W1 * 3] * w;
     }
-    dst[i] = (uint8_t)min(max(acc >> py, 0), 255);
+    dst[b * dst_frame_stride + oy * dst_row_pitch + xc] = (uint8_t)min(max(acc >> py, 0), 255);
+  }
+}
+
+// frames that need no resize, into the top-left corner of their canvas (BGR -> RGB on the way)
+__global__ void copy_into_canvas_kernel(const uint8_t* __restrict__ src, int B, int H, int W, int bgr, uint8_t* __restrict__ dst,
+                                        long long dst_frame_stride, long long dst_row_pitch) {
+  const long long total = (long long)B * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const long long r = i / W;
+    const int y = (int)(r % H);
+    const long long b = r / H;
+    const uint8_t* s = src + i * 3;
+    uint8_t* d = dst + b * dst_frame_stride + y * dst_row_pitch + x * 3;
+    d[0] = s[bgr ? 2 : 0];
+    d[1] = s[1];
+    d[2] = s[bgr ? 0 : 2];
   }
 }
 
@@ -168,6 +186,33 @@ __global__ void pos_embed_kernel(float* __restrict__ pos, int h, int w) {
   const float scale = 6.283185307179586f;   // 2*pi rounded to float32, like torch's python-float * tensor
   const float embed = from_y ? ((float)(y + 1) / ((float)h + 1e-6f)) * scale : ((float)(x + 1) / ((float)w + 1e-6f)) * scale;
   // dim_t = 10000 ** (2 * (k // 2) / 128)   (float32 pow of a float32 exponent)
+  const float dim_t = powf(10000.0f, (float)(2 * (k / 2)) / 128.0f);
+  const float v = embed / dim_t;
+  pos[i] = (k & 1) ? cosf(v) : sinf(v);
+}
+
+// Padded batches (modeling_detr.py:322-349 with a real mask): frame b's valid feature cells are the top-left fvalid[b] = (fh, fw)
+// rectangle of the h x w map.  y_embed = cumsum of the mask along y = min(y + 1, fh) in a valid column, 0 elsewhere, normalised by
+// its last row (fh, or 0 -> 0 / eps = 0); x_embed likewise.  pos [B, h * w, 256].
+__global__ void pos_embed_masked_kernel(float* __restrict__ pos, int B, int h, int w, const int32_t* __restrict__ fvalid) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * h * w * kD) return;
+  const int c = (int)(i % kD);
+  const long long t = i / kD;
+  const int x = (int)(t % w), y = (int)((t / w) % h), b = (int)(t / ((long long)w * h));
+  const int fh = fvalid[2 * b], fw = fvalid[2 * b + 1];
+  const bool from_y = c < 128;
+  const int k = from_y ? c : c - 128;
+  const float scale = 6.283185307179586f;
+  float num, den;
+  if (from_y) {
+    num = x < fw ? (float)min(y + 1, fh) : 0.f;
+    den = x < fw ? (float)fh : 0.f;
+  } else {
+    num = y < fh ? (float)min(x + 1, fw) : 0.f;
+    den = y < fh ? (float)fw : 0.f;
+  }
+  const float embed = (num / (den + 1e-6f)) * scale;
   const float dim_t = powf(10000.0f, (float)(2 * (k / 2)) / 128.0f);
   const float v = embed / dim_t;
   pos[i] = (k & 1) ? cosf(v) : sinf(v);
@@ -675,13 +720,24 @@ int launch_preprocess(const uint8_t* src, int B, int Hs, int Ws, int src_is_bgr,
   return OPD_OK;
 }
 
+int launch_copy_into_canvas(const uint8_t* src, int B, int H, int W, int src_is_bgr, uint8_t* dst, long long dst_frame_stride,
+                            long long dst_row_pitch, cudaStream_t s) {
+  copy_into_canvas_kernel<<<grid_for((long long)B * H * W, 256), 256, 0, s>>>(src, B, H, W, src_is_bgr, dst, dst_frame_stride, dst_row_pitch);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
 int launch_resize_u8(const uint8_t* src, int B, int H0, int W0, int src_is_bgr, uint8_t* tmp, uint8_t* dst, int H1,
                      int W1, const int16_t* wx, const int32_t* x0, int kx, int px, const int16_t* wy, const int32_t* y0,
-                     int ky, int py, cudaStream_t s) {
+                     int ky, int py, cudaStream_t s, long long dst_frame_stride, long long dst_row_pitch) {
+  if (dst_frame_stride == 0) dst_frame_stride = (long long)H1 * W1 * 3;
+  if (dst_row_pitch == 0) dst_row_pitch = (long long)W1 * 3;
   resize_h_kernel<<<grid_for((long long)B * H0 * W1, 256), 256, 0, s>>>(src, B, H0, W0, src_is_bgr, tmp, W1, wx, x0, kx, px);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
-  resize_v_kernel<<<grid_for((long long)B * H1 * W1 * 3, 256), 256, 0, s>>>(tmp, B, H0, W1, dst, H1, wy, y0, ky, py);
+  resize_v_kernel<<<grid_for((long long)B * H1 * W1 * 3, 256), 256, 0, s>>>(tmp, B, H0, W1, dst, H1, wy, y0, ky, py, dst_frame_stride,
+                                                                           dst_row_pitch);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;
@@ -699,6 +755,14 @@ int launch_maxpool(const __nv_bfloat16* x, int B, int H, int W, int C, __nv_bflo
 int launch_pos_embed(float* pos, int h, int w, cudaStream_t s) {
   const int total = h * w * kD;
   pos_embed_kernel<<<(total + 255) / 256, 256, 0, s>>>(pos, h, w);
+  count_launch();
+  OPD_CUDA_OK(cudaGetLastError());
+  return OPD_OK;
+}
+
+int launch_pos_embed_masked(float* pos, int B, int h, int w, const int32_t* fvalid, cudaStream_t s) {
+  const long long total = (long long)B * h * w * kD;
+  pos_embed_masked_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pos, B, h, w, fvalid);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

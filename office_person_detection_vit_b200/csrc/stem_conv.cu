@@ -54,8 +54,11 @@ struct StemParams {
 // The input is uint8: (u - 255 * mean[c]) / (255 * std[c]) rounded to bf16 takes 3 x 256 values.  Every CTA tabulates them
 // with exactly that expression (one division per table entry instead of one per pixel channel) and the pixel loop is byte load ->
 // table -> pack: the same bits as computing each value in place, a third of the instructions.
+// valid_hw (optional, [B, 2] int32): frame b holds a picture of valid_hw[b] = (h, w) pixels in the top-left corner of its
+// Hs x Ws canvas; the rest is the batch padding and becomes 0 AFTER normalisation, like DetrImageProcessor.pad (pixel_mask = 0).
 __global__ void __launch_bounds__(256) s2d_preprocess_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, int bgr,
-                                                             __nv_bfloat16* __restrict__ S, int H2, int W2) {
+                                                             __nv_bfloat16* __restrict__ S, int H2, int W2,
+                                                             const int32_t* __restrict__ valid_hw) {
   __shared__ uint16_t lut[3][256];   // [colour of the OUTPUT (RGB)][byte value] -> bf16 bits
   {
     const float mean[3] = {0.485f * 255.0f, 0.456f * 255.0f, 0.406f * 255.0f};
@@ -78,7 +81,8 @@ __global__ void __launch_bounds__(256) s2d_preprocess_kernel(const uint8_t* __re
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
         const int iy = 2 * y + dy, ix = 2 * x + dx;
-        const bool ok = iy < Hs && ix < Ws;
+        const int vh = valid_hw ? valid_hw[2 * b] : Hs, vw = valid_hw ? valid_hw[2 * b + 1] : Ws;
+        const bool ok = iy < vh && ix < vw;
         const uint8_t* px = src + (((long long)b * Hs + (ok ? iy : 0)) * Ws + (ok ? ix : 0)) * 3;
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[(dy * 2 + dx) * 3 + c] = ok ? (uint32_t)lut[c][px[bgr ? 2 - c : c]] : 0u;
@@ -497,11 +501,12 @@ int stem_launch(const StemPlan& plan, cudaStream_t stream) {
   return OPD_OK;
 }
 
-int launch_preprocess_s2d(const uint8_t* src, int B, int Hs, int Ws, int src_is_bgr, __nv_bfloat16* s2d, cudaStream_t s) {
+int launch_preprocess_s2d(const uint8_t* src, int B, int Hs, int Ws, int src_is_bgr, __nv_bfloat16* s2d, cudaStream_t s,
+                          const int32_t* valid_hw) {
   const int H2 = (Hs + 1) / 2, W2 = (Ws + 1) / 2;
   const long long total = (long long)B * H2 * W2;
   const long long blocks = (total + 255) / 256;
-  s2d_preprocess_kernel<<<(int)std::min<long long>(blocks, 148LL * 16), 256, 0, s>>>(src, B, Hs, Ws, src_is_bgr, s2d, H2, W2);
+  s2d_preprocess_kernel<<<(int)std::min<long long>(blocks, 148LL * 16), 256, 0, s>>>(src, B, Hs, Ws, src_is_bgr, s2d, H2, W2, valid_hw);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

@@ -87,6 +87,10 @@ struct AttnPlan {
   int64_t ldo;
   int B, heads, Lq, Lk;
   int kv_tile;   // keys per tile: 64 (4 CTAs per SM) or 128 (2 CTAs per SM)
+  // key-padding mask of padded batches (modeling_detr.py:386-411 attention_mask): bit k % 32 of word [b, k / 32] set <=> key k of
+  // frame b takes part; nullptr: every key does.  key_mask_stride = words per frame.
+  const uint32_t* key_mask = nullptr;
+  int key_mask_stride = 0;
 };
 int attn_plan(AttnPlan* plan, const __nv_bfloat16* q, int64_t ldq, const __nv_bfloat16* k, int64_t ldk, const __nv_bfloat16* v,
               int64_t ldv, __nv_bfloat16* o, int64_t ldo, int B, int heads, int Lq, int Lk);

@@ -54,6 +54,12 @@ _lib.register("opd_roi_features_bf16", C.c_int, [_P, C.c_int32, C.c_int32, C.c_i
 _lib.register("opd_detr_postprocess", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                                C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P])
 
+class _FrameGroup(C.Structure):
+    _fields_ = [("frames_dev", C.c_void_p), ("n", C.c_int32), ("H0", C.c_int32), ("W0", C.c_int32), ("frames_are_bgr", C.c_int32)]
+
+
+_lib.register("opd_detr_workspace_bytes_mixed", C.c_int, [_P, C.POINTER(_FrameGroup), C.c_int32, C.POINTER(C.c_size_t)])
+_lib.register("opd_detr_forward_mixed", C.c_int, [_P, C.POINTER(_FrameGroup), C.c_int32, _P, C.c_size_t, _P, _P, _P])
 _lib.register("opd_synthetic_frames_u8", C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P])
 
 N_QUERIES = 100
@@ -154,6 +160,34 @@ class DetrEngine:
                                              ws.numel() - (base - ws.data_ptr()), logits.data_ptr(), boxes.data_ptr(),
                                              _lib.stream_ptr())
         _lib.check(rc, "opd_detr_forward")
+        return logits, boxes
+
+    def forward_mixed(self, groups, bgr: bool = True):
+        """A batch that mixes frame sizes, like DetrImageProcessor + DetrForObjectDetection on a list of images: `groups` is a list
+        of contiguous [n, H, W, 3] uint8 CUDA tensors (one frame size per tensor).  Every frame is resized on its own, padded to the
+        batch maximum with pixel_mask semantics (opd_detr_forward_mixed) -> (logits [B,100,92], boxes [B,100,4]) in group order."""
+        torch = self._torch
+        for g in groups:
+            if not (g.is_cuda and g.dtype == torch.uint8 and g.dim() == 4 and g.shape[-1] == 3 and g.is_contiguous() and g.shape[0] > 0):
+                raise ValueError("every group must be a non-empty contiguous [n,H,W,3] uint8 CUDA tensor")
+        arr = (_FrameGroup * len(groups))()
+        for i, g in enumerate(groups):
+            arr[i].frames_dev, arr[i].n, arr[i].H0, arr[i].W0, arr[i].frames_are_bgr = g.data_ptr(), g.shape[0], g.shape[1], g.shape[2], int(bgr)
+        key = ("mixed", tuple((g.shape[0], g.shape[1], g.shape[2]) for g in groups))
+        ws = self._ws.get(key)
+        if ws is None:
+            n = C.c_size_t()
+            _lib.check(_lib.lib().opd_detr_workspace_bytes_mixed(self._h, arr, len(groups), C.byref(n)), "opd_detr_workspace_bytes_mixed")
+            ws = self._ws[key] = torch.empty(n.value + 1024, dtype=torch.uint8, device=f"cuda:{self.device_index}")
+        base = (ws.data_ptr() + 1023) & ~1023
+        B = sum(g.shape[0] for g in groups)
+        dev = groups[0].device
+        logits = torch.empty(B, N_QUERIES, N_LOGITS, dtype=torch.float32, device=dev)
+        boxes = torch.empty(B, N_QUERIES, 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(self.device_index):
+            rc = _lib.lib().opd_detr_forward_mixed(self._h, arr, len(groups), base, ws.numel() - (base - ws.data_ptr()),
+                                                   logits.data_ptr(), boxes.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "opd_detr_forward_mixed")
         return logits, boxes
 
     STEP_KINDS = ("elementwise", "gemm", "conv", "attention", "heads")
@@ -258,11 +292,15 @@ class ViTDetector:
     """Person detector with the reference's ViTDetector / YOLOv8Detector surface, backed by libopd_b200.so."""
 
     def __init__(self, model_name: str = "facebook/detr-resnet-50", confidence_threshold: float = 0.5,
-                 device: str | None = None, state_dict: dict | None = None, batch_size: int = 64):
+                 device: str | None = None, state_dict: dict | None = None, batch_size: int = 64, mixed_sizes: str = "pad"):
         self.model_name = model_name
         self.confidence_threshold = confidence_threshold
         self.device = self._setup_device(device)
         self.batch_size = int(batch_size)
+        if mixed_sizes not in ("pad", "group"):
+            raise ValueError("mixed_sizes must be 'pad' (one padded device batch, the reference's DetrImageProcessor behaviour) or "
+                             "'group' (one device batch per frame size)")
+        self.mixed_sizes = mixed_sizes
         self.model: DetrEngine | None = None
         self._state_dict = state_dict
         self._pinned: dict[tuple[int, int], object] = {}
@@ -341,9 +379,10 @@ class ViTDetector:
             raise
 
     def detect_batch(self, frames: Sequence[np.ndarray], strict: bool = False) -> list[list[Detection]]:
-        """Batched detection.  Frames of equal size run as one device batch (chunks of `batch_size`); frames of
-        different sizes are grouped by size (the reference pads to the batch maximum instead: different arithmetic at
-        the padded borders, so equal-size groups are the faithful choice here).
+        """Batched detection.  Frames of equal size run as one device batch (chunks of `batch_size`).  A call that mixes frame
+        sizes runs, like the reference's _preprocess_batch (DetrImageProcessor pads to the batch maximum and returns pixel_mask), as
+        padded device batches with the mask carried through the transformer (`mixed_sizes="pad"`, the default), or as one device
+        batch per frame size (`mixed_sizes="group"`: no padding arithmetic at all; also what detect_batch_with_features uses).
 
         Failure isolation (the reference's DetectionPhase catches exceptions PER FRAME and records an empty list,
         src/pipeline/phases/detection.py:124-127): a frame that is not a uint8 [H,W,3] array, or whose device batch fails and
@@ -370,6 +409,13 @@ class ViTDetector:
             host[j] = frames[i]                                  # one copy: frame -> pinned staging
         out = self.detect_tensors(view.to(dev, non_blocking=True))
         f_dev = self.model.roi_features(out["det_xywh"], out["n_keep"], h0, w0) if with_features else None
+        return self._to_detections(out, f_dev, len(chunk))
+
+    @staticmethod
+    def _to_detections(out: dict, f_dev, n_frames: int):
+        """Compacted device rows -> ([list[Detection]] per frame, [features] per frame)."""
+        torch = _lib.require_cuda()
+        with_features = f_dev is not None
         # one packed device -> host read of the result rows: [B, Q, 4 + 1 + 2 + 1] float64
         packed = torch.cat([out["det_xywh"], out["det_score"].double().unsqueeze(-1), out["det_foot"],
                             out["det_query"].double().unsqueeze(-1)], dim=-1)
@@ -377,7 +423,7 @@ class ViTDetector:
         rows = packed.cpu().numpy()
         f_host = f_dev.cpu().numpy() if with_features else None
         dets_all, feats_all = [], []
-        for j in range(len(chunk)):
+        for j in range(n_frames):
             n = int(n_keep[j])
             r = rows[j, :n].tolist()
             dets = [Detection(bbox=(x, y, w, h), confidence=float(np.float32(sc)), class_id=PERSON_LABEL, class_name="person",
@@ -411,6 +457,9 @@ class ViTDetector:
                 continue
             groups.setdefault((f.shape[0], f.shape[1]), []).append(i)
         dev = torch.device("cuda", self._device_index())
+        if len(groups) > 1 and self.mixed_sizes == "pad" and not with_features:
+            self._detect_padded(frames, groups, results, dev, strict)
+            groups = {}
         for (h0, w0), idxs in groups.items():
             for c0 in range(0, len(idxs), self.batch_size):
                 chunk = idxs[c0:c0 + self.batch_size]
@@ -439,6 +488,40 @@ class ViTDetector:
                     results[i] = d[j]
                     feats[i] = f[j]
         return [r if r is not None else [] for r in results], feats
+
+    def _detect_padded(self, frames, groups: dict, results: list, dev, strict: bool) -> None:
+        """Mixed frame sizes as padded device batches (chunks of `batch_size` frames in call order)."""
+        torch = _lib.require_cuda()
+        order = sorted(i for idxs in groups.values() for i in idxs)
+        for c0 in range(0, len(order), self.batch_size):
+            chunk = order[c0:c0 + self.batch_size]
+            by_size: dict[tuple[int, int], list[int]] = {}
+            for i in chunk:
+                by_size.setdefault((frames[i].shape[0], frames[i].shape[1]), []).append(i)
+            try:
+                tensors = []
+                for (h0, w0), idxs in by_size.items():
+                    stage = self._staging(len(idxs), h0, w0)[:len(idxs)]
+                    host = stage.numpy()
+                    for j, i in enumerate(idxs):
+                        host[j] = frames[i]
+                    tensors.append(stage.to(dev, non_blocking=True))
+                logits, boxes = self.model.forward_mixed(tensors) if len(tensors) > 1 else self.model.forward(tensors[0])
+                b0 = 0
+                for (h0, w0), idxs in by_size.items():
+                    n = len(idxs)
+                    out = postprocess_tensors(logits[b0:b0 + n].contiguous(), boxes[b0:b0 + n].contiguous(), h0, w0,
+                                              self.confidence_threshold)
+                    dets, _ = self._to_detections(out, None, n)
+                    for j, i in enumerate(idxs):
+                        results[i] = dets[j]
+                    b0 += n
+            except _lib.OpdError as e:
+                if strict:
+                    raise
+                logger.error(f"Detection failed for a padded batch of {len(chunk)} frames: {e}")
+                for i in chunk:
+                    results[i] = []
 
     def _get_foot_position(self, bbox: tuple[float, float, float, float]) -> tuple[float, float]:
         x, y, w, h = bbox

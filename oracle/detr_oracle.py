@@ -198,13 +198,31 @@ def sine_position_embedding(h: int, w: int) -> torch.Tensor:
     return torch.cat((pos_y, pos_x), dim=2).reshape(h * w, D_MODEL)
 
 
+def sine_position_embedding_masked(mask: torch.Tensor) -> torch.Tensor:
+    """modeling_detr.py:322-349 with a real pixel mask [B, h, w] (bool, True = picture) -> [B, h*w, 256]."""
+    npf = D_MODEL // 2
+    y_embed = mask.cumsum(1, dtype=torch.float32)
+    x_embed = mask.cumsum(2, dtype=torch.float32)
+    eps, scale = 1e-6, 2 * math.pi
+    y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
+    x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
+    dim_t = torch.arange(npf, dtype=torch.int64).to(torch.float32)
+    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / npf)
+    pos_x = x_embed[:, :, :, None] / dim_t
+    pos_y = y_embed[:, :, :, None] / dim_t
+    pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).flatten(1, 2)
+
+
 def _linear(m: _Mode, w: dict, prefix: str, x: torch.Tensor) -> torch.Tensor:
     # the activation operand of a tensor-core GEMM is bf16 (a no-op in plain "bf16" mode, where every input already is)
     return F.linear(m.act(x), m.wt(w[prefix + ".weight"]), w[prefix + ".bias"])
 
 
-def _mha(m: _Mode, w: dict, prefix: str, q_in, k_in, v_in) -> torch.Tensor:
-    """modeling_detr.py:386-411, 441-477, 508-557: softmax(QK^T / sqrt(d)) V per head, no mask (nothing is padded)."""
+def _mha(m: _Mode, w: dict, prefix: str, q_in, k_in, v_in, key_mask=None) -> torch.Tensor:
+    """modeling_detr.py:386-411, 441-477, 508-557: softmax(QK^T / sqrt(d)) V per head; key_mask [B, Lk] (bool, True = takes part):
+    the key-padding mask of a padded batch - masked keys get probability 0."""
     B, Lq, _ = q_in.shape
     Lk = k_in.shape[1]
     dh = D_MODEL // N_HEADS
@@ -212,6 +230,8 @@ def _mha(m: _Mode, w: dict, prefix: str, q_in, k_in, v_in) -> torch.Tensor:
     k = m.act(_linear(m, w, prefix + ".k_proj", k_in)).view(B, Lk, N_HEADS, dh).transpose(1, 2)
     v = m.act(_linear(m, w, prefix + ".v_proj", v_in)).view(B, Lk, N_HEADS, dh).transpose(1, 2)
     s = torch.matmul(q, k.transpose(2, 3)) * dh ** -0.5
+    if key_mask is not None:
+        s = s.masked_fill(~key_mask[:, None, None, :], float("-inf"))
     if m.bf16:
         # CUDA path: P is rounded to bf16 for the PV product, the row sum stays float32 (flash-attention style)
         s = s - s.amax(dim=-1, keepdim=True)
@@ -266,27 +286,21 @@ def backbone(w: dict, pixel_values: torch.Tensor, mode: str = "fp32", taps: dict
     return x
 
 
-@torch.no_grad()
-def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None, do_resize: bool = True):
-    """frames [B,H0,W0,3] uint8 BGR -> (logits [B,100,92], boxes cxcywh in [0,1] [B,100,4]), float32."""
+def _transformer(w: dict, mode: str, feat: torch.Tensor, pos: torch.Tensor, key_mask, taps: dict | None):
+    """input projection, 6 encoder + 6 decoder layers, heads.  feat [B,2048,h,w]; pos [1 or B, h*w, 256]; key_mask [B, h*w] or None."""
     m = _Mode(mode)
     mb = _Mode(mode, "backbone")
-    pv = preprocess(frames_bgr, do_resize)
-    if taps is not None:
-        taps["pixel_values"] = pv
-    feat = backbone(w, pv, mode, taps)
-    B, _, h, wd = feat.shape
+    B = feat.shape[0]
     proj = F.conv2d(feat, mb.wt(w["model.input_projection.weight"]), w["model.input_projection.bias"])
     x = m.stream(mb.act(proj.flatten(2).permute(0, 2, 1)) if not m.res32 else proj.flatten(2).permute(0, 2, 1))   # [B, S, 256]
-    pos = sine_position_embedding(h, wd)[None]                        # float32 table
     if taps is not None:
         taps["enc_in"] = x
-        taps["pos"] = pos[0]
+        taps["pos"] = pos.reshape(-1, D_MODEL)
 
     for i in range(N_ENC):
         p = f"model.encoder.layers.{i}"
         qk = m.act(x + pos)
-        a = _mha(m, w, p + ".self_attn", qk, qk, x)
+        a = _mha(m, w, p + ".self_attn", qk, qk, x, key_mask)
         x = m.stream(_ln(w, p + ".self_attn_layer_norm", x + a))
         f = m.act(F.relu(_linear(m, w, p + ".mlp.fc1", x)))
         f = _linear(m, w, p + ".mlp.fc2", f)
@@ -303,7 +317,7 @@ def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None, d
         qk = m.act(y + qpos)
         a = _mha(m, w, p + ".self_attn", qk, qk, y)
         y = m.stream(_ln(w, p + ".self_attn_layer_norm", y + a))
-        a = _mha(m, w, p + ".encoder_attn", m.act(y + qpos), mem_k, memory)
+        a = _mha(m, w, p + ".encoder_attn", m.act(y + qpos), mem_k, memory, key_mask)
         y = m.stream(_ln(w, p + ".encoder_attn_layer_norm", y + a))
         f = m.act(F.relu(_linear(m, w, p + ".mlp.fc1", y)))
         f = _linear(m, w, p + ".mlp.fc2", f)
@@ -320,6 +334,39 @@ def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None, d
     b = F.relu(F.linear(b, w["bbox_predictor.layers.1.weight"], w["bbox_predictor.layers.1.bias"]))
     boxes = F.linear(b, w["bbox_predictor.layers.2.weight"], w["bbox_predictor.layers.2.bias"]).sigmoid()
     return logits, boxes
+
+
+@torch.no_grad()
+def forward(w: dict, frames_bgr, mode: str = "fp32", taps: dict | None = None, do_resize: bool = True):
+    """frames [B,H0,W0,3] uint8 BGR -> (logits [B,100,92], boxes cxcywh in [0,1] [B,100,4]), float32."""
+    pv = preprocess(frames_bgr, do_resize)
+    if taps is not None:
+        taps["pixel_values"] = pv
+    feat = backbone(w, pv, mode, taps)
+    pos = sine_position_embedding(feat.shape[2], feat.shape[3])[None]                        # float32 table
+    return _transformer(w, mode, feat, pos, None, taps)
+
+
+@torch.no_grad()
+def forward_mixed(w: dict, frames_list, mode: str = "fp32", taps: dict | None = None, do_resize: bool = True):
+    """A batch that mixes frame sizes: `frames_list` = list of [H0,W0,3] uint8 BGR frames.  Every frame is preprocessed on its own,
+    zero-padded (after normalisation) at the bottom / right to the batch maximum with pixel_mask = 0 there
+    (image_processing_detr.py:638-667), the mask is downsampled to the feature map by nearest interpolation
+    (modeling_detr.py:281-283), drives the sine embedding (:322-349) and masks the keys of the encoder self-attention and the
+    decoder cross-attention (:386-411)."""
+    pvs = [preprocess(np.asarray(f)[None], do_resize) for f in frames_list]
+    Hc, Wc = max(p.shape[2] for p in pvs), max(p.shape[3] for p in pvs)
+    pv = torch.zeros(len(pvs), 3, Hc, Wc)
+    mask = torch.zeros(len(pvs), Hc, Wc, dtype=torch.bool)
+    for i, p_ in enumerate(pvs):
+        pv[i, :, :p_.shape[2], :p_.shape[3]] = p_[0]
+        mask[i, :p_.shape[2], :p_.shape[3]] = True
+    if taps is not None:
+        taps["pixel_values"] = pv
+    feat = backbone(w, pv, mode, taps)
+    fmask = F.interpolate(mask[None].float(), size=feat.shape[-2:]).to(torch.bool)[0]      # [B, h, w]
+    pos = sine_position_embedding_masked(fmask)
+    return _transformer(w, mode, feat, pos, fmask.flatten(1), taps)
 
 
 @torch.no_grad()

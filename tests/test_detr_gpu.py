@@ -386,3 +386,75 @@ def test_plan_cache_and_failure_isolation(detector):
     assert [d.bbox for d in res[0]] == [d.bbox for d in alone[0]] and [d.bbox for d in res[2]] == [d.bbox for d in alone[1]]
     with pytest.raises(ValueError):
         detector.detect_batch(frames[:2], strict=True)
+
+
+def test_mixed_size_batch_small(detector, weights):
+    """A batch that mixes three frame sizes (un-resized small frames): zero padding after normalisation, mask-aware sine embedding
+    and the key-padding mask in the encoder / cross attentions, tap by tap against the oracle's forward_mixed (bf16 mode; the
+    oracle is pinned to transformers' padded-batch arithmetic in tests/test_detr_oracle.py)."""
+    import torch
+
+    eng = detector.model
+    eng.set_debug(True)
+    eng.set_resize(False)
+    try:
+        sizes = [(224, 320), (192, 352), (160, 160)]
+        counts = [2, 1, 2]
+        groups = [do.synthetic_frames(n, h, w, seed=70 + i) for i, ((h, w), n) in enumerate(zip(sizes, counts))]
+        flat = [f for g in groups for f in g]
+        taps: dict = {}
+        ref_logits, ref_boxes = do.forward_mixed(weights, flat, mode="bf16", taps=taps, do_resize=False)
+        logits, boxes = eng.forward_mixed([torch.from_numpy(g).cuda() for g in groups])
+        torch.cuda.synchronize()
+        assert float((eng.tap("pos").cpu() - taps["pos"]).abs().max()) < 2e-6          # per-frame tables, masked cumsum
+        report = {}
+        for name, ref in taps.items():
+            if name in ("pixel_values", "pos"):
+                continue
+            got = eng.tap(name).float().cpu()
+            ref = ref.permute(0, 2, 3, 1).reshape(-1, ref.shape[1]) if ref.dim() == 4 else ref.reshape(-1, ref.shape[-1])
+            assert got.shape == ref.shape, (name, got.shape, ref.shape)
+            report[name] = _rel(got, ref)
+        print({k: f"{v:.2e}" for k, v in report.items()})
+        assert report["stem"] < TOL_STEM_BF16
+        bad = {k: v for k, v in report.items() if v > TOL["bf16"]["tap_rel"]}
+        assert not bad, bad
+        assert _rel(logits.cpu(), ref_logits) < TOL["bf16"]["logits_rel"]
+        assert float((boxes.cpu() - ref_boxes).abs().max()) < 1.4e-2
+        # the mask matters: the same frames WITHOUT it (each size on its own) give other numbers for the padded frames
+        alone, _ = eng.forward(torch.from_numpy(groups[2]).cuda())
+        assert _rel(logits[3:].cpu(), alone.cpu()) > 1e-3
+    finally:
+        eng.set_debug(False)
+        eng.set_resize(True)
+
+
+def test_mixed_size_batch_camera_and_model_size(detector, weights):
+    """720x1280 camera frames (-> 750x1333) batched with 800x1333 frames: per-frame resize, padding to 800x1333, one feature row
+    masked for the camera frames.  Final detections against the oracle (bf16 and fp32 modes), and through detect_batch."""
+    import torch
+
+    cam = do.synthetic_frames(2, 720, 1280, seed=81)
+    big = do.synthetic_frames(1, 800, 1333, seed=82)
+    flat = [cam[0], cam[1], big[0]]
+    logits, boxes = detector.model.forward_mixed([torch.from_numpy(cam).cuda(), torch.from_numpy(big).cuda()])
+    torch.cuda.synchronize()
+    for mode in ("bf16", "fp32"):
+        rl, rb = do.forward_mixed(weights, flat, mode=mode)
+        for sl, (h0, w0) in ((slice(0, 2), (720, 1280)), (slice(2, 3), (800, 1333))):
+            from office_person_detection_vit_b200.detection import postprocess_tensors
+
+            out = postprocess_tensors(logits[sl].contiguous(), boxes[sl].contiguous(), h0, w0, 0.0)
+            out["logits"] = logits[sl]
+            _assert_within(_final_errors(out, rl[sl], rb[sl], h0, w0), TOL[mode], f"mixed batch {h0}x{w0} vs oracle {mode}")
+    # reference-shaped surface: one call with both sizes, results in call order; "group" mode = each size on its own
+    from office_person_detection_vit_b200.detection import ViTDetector
+
+    padded = detector.detect_batch([big[0], cam[0], cam[1]])
+    assert len(padded) == 3 and all(len(d) > 0 for d in padded)
+    grouped = ViTDetector(confidence_threshold=0.5, state_dict=weights, mixed_sizes="group")
+    grouped.model = detector.model
+    per_size = grouped.detect_batch([big[0], cam[0], cam[1]])
+    assert [d.bbox for d in per_size[0]] == [d.bbox for d in detector.detect(big[0])]
+    for a, b in zip(padded, per_size):          # same scene, padded vs not: the same people within the bf16 envelope
+        assert abs(len(a) - len(b)) <= max(3, 0.1 * len(b))

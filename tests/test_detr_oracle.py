@@ -109,3 +109,26 @@ def test_oracle_matches_transformers_full_size(weights, h0, w0):
     logits, boxes = do.forward(weights, frames, mode="fp32")
     np.testing.assert_allclose(logits.numpy(), out.logits.numpy(), rtol=1e-4, atol=5e-4)
     np.testing.assert_allclose(boxes.numpy(), out.pred_boxes.numpy(), rtol=1e-4, atol=5e-5)
+
+
+@pytest.mark.parametrize("sizes,do_resize", [([(96, 128), (80, 144), (64, 64)], False), ([(720, 1280), (800, 1333)], True)])
+def test_oracle_mixed_batch_matches_transformers(weights, sizes, do_resize):
+    """Batches that mix frame sizes: DetrImageProcessor pads to the batch maximum and returns pixel_mask, DetrForObjectDetection
+    carries the mask through the sine embedding and the attentions.  oracle.forward_mixed (fp32) against transformers, live: small
+    un-resized frames of three sizes, and a 720p + 800x1333 pair through the 800 / 1333 resize rule."""
+    import os
+
+    os.environ.setdefault("HF_HUB_OFFLINE", "1")
+    from transformers import DetrImageProcessor
+
+    frames = [do.synthetic_frames(1, h, w, seed=30 + i)[0] for i, (h, w) in enumerate(sizes)]
+    model = do.hf_model(weights)
+    inp = DetrImageProcessor(do_resize=do_resize)(images=[np.ascontiguousarray(f[:, :, ::-1]) for f in frames], return_tensors="pt")
+    assert "pixel_mask" in inp and not bool(inp["pixel_mask"].all())        # the batch really is padded
+    with torch.no_grad():
+        out = model(**inp)
+    taps: dict = {}
+    logits, boxes = do.forward_mixed(weights, frames, mode="fp32", taps=taps, do_resize=do_resize)
+    np.testing.assert_allclose(taps["pixel_values"].numpy(), inp["pixel_values"].numpy(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(logits.numpy(), out.logits.numpy(), rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(boxes.numpy(), out.pred_boxes.numpy(), rtol=1e-4, atol=5e-5)
