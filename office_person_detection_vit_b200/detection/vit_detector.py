@@ -304,6 +304,7 @@ class ViTDetector:
         self.model: DetrEngine | None = None
         self._state_dict = state_dict
         self._pinned: dict[tuple[int, int], object] = {}
+        self._copy_pool = None
         logger.info(f"ViTDetector initialized with model: {model_name}")
         logger.info(f"Using device: {self.device}")
         logger.info(f"Confidence threshold: {confidence_threshold}")
@@ -399,14 +400,30 @@ class ViTDetector:
             self._pinned[(h, w)] = buf
         return buf
 
-    def _detect_chunk(self, frames, chunk, h0, w0, with_features, dev):
-        """One device batch of equal-size frames -> ([list[Detection]] per frame, [features] per frame)."""
-        torch = _lib.require_cuda()
+    def _stage(self, frames, chunk, h0, w0):
+        """frames[chunk] -> the pinned staging buffer of their size (one copy per frame; large copies release the GIL, so a few
+        threads share the 3 MB memcpys: 24 -> 6 ms for 64 frames of 800x1333)."""
         stage = self._staging(len(chunk), h0, w0)
         view = stage[:len(chunk)]
         host = view.numpy()
-        for j, i in enumerate(chunk):
-            host[j] = frames[i]                                  # one copy: frame -> pinned staging
+
+        def put(j):
+            host[j] = frames[chunk[j]]
+
+        if len(chunk) >= 8:
+            if self._copy_pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self._copy_pool = ThreadPoolExecutor(max_workers=8, thread_name_prefix="opd-stage")
+            list(self._copy_pool.map(put, range(len(chunk))))
+        else:
+            for j in range(len(chunk)):
+                put(j)
+        return view
+
+    def _detect_chunk(self, frames, chunk, h0, w0, with_features, dev):
+        """One device batch of equal-size frames -> ([list[Detection]] per frame, [features] per frame)."""
+        view = self._stage(frames, chunk, h0, w0)
         out = self.detect_tensors(view.to(dev, non_blocking=True))
         f_dev = self.model.roi_features(out["det_xywh"], out["n_keep"], h0, w0) if with_features else None
         return self._to_detections(out, f_dev, len(chunk))
@@ -501,11 +518,7 @@ class ViTDetector:
             try:
                 tensors = []
                 for (h0, w0), idxs in by_size.items():
-                    stage = self._staging(len(idxs), h0, w0)[:len(idxs)]
-                    host = stage.numpy()
-                    for j, i in enumerate(idxs):
-                        host[j] = frames[i]
-                    tensors.append(stage.to(dev, non_blocking=True))
+                    tensors.append(self._stage(frames, idxs, h0, w0).to(dev, non_blocking=True))
                 logits, boxes = self.model.forward_mixed(tensors) if len(tensors) > 1 else self.model.forward(tensors[0])
                 b0 = 0
                 for (h0, w0), idxs in by_size.items():
