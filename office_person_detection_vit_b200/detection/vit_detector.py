@@ -391,19 +391,20 @@ class ViTDetector:
         `strict=True` raises instead."""
         return self._detect_batch(frames, with_features=False, strict=strict)[0]
 
-    def _staging(self, n: int, h: int, w: int):
-        """Pinned host staging buffer [batch_size, h, w, 3] (one per frame size, reused across calls)."""
+    def _staging(self, n: int, h: int, w: int, slot: int = 0):
+        """Pinned host staging buffer [batch_size, h, w, 3] (two per frame size - device batches are pipelined -, reused across
+        calls)."""
         torch = _lib.require_cuda()
-        buf = self._pinned.get((h, w))
+        buf = self._pinned.get((h, w, slot))
         if buf is None or buf.shape[0] < n:
             buf = torch.empty((max(n, min(self.batch_size, 64)), h, w, 3), dtype=torch.uint8).pin_memory()
-            self._pinned[(h, w)] = buf
+            self._pinned[(h, w, slot)] = buf
         return buf
 
-    def _stage(self, frames, chunk, h0, w0):
+    def _stage(self, frames, chunk, h0, w0, slot: int = 0):
         """frames[chunk] -> the pinned staging buffer of their size (one copy per frame; large copies release the GIL, so a few
         threads share the 3 MB memcpys: 24 -> 6 ms for 64 frames of 800x1333)."""
-        stage = self._staging(len(chunk), h0, w0)
+        stage = self._staging(len(chunk), h0, w0, slot)
         view = stage[:len(chunk)]
         host = view.numpy()
 
@@ -423,22 +424,45 @@ class ViTDetector:
 
     def _detect_chunk(self, frames, chunk, h0, w0, with_features, dev):
         """One device batch of equal-size frames -> ([list[Detection]] per frame, [features] per frame)."""
-        view = self._stage(frames, chunk, h0, w0)
+        return self._finish_chunk(self._launch_chunk(frames, chunk, h0, w0, with_features, dev, 0))
+
+    def _launch_chunk(self, frames, chunk, h0, w0, with_features, dev, slot: int):
+        """Stage the frames, enqueue the copy, the forward and the post-processing, and the device -> host copy of the packed result
+        rows into pinned memory; returns without waiting (the caller stages the next device batch meanwhile)."""
+        torch = _lib.require_cuda()
+        view = self._stage(frames, chunk, h0, w0, slot)
         out = self.detect_tensors(view.to(dev, non_blocking=True))
         f_dev = self.model.roi_features(out["det_xywh"], out["n_keep"], h0, w0) if with_features else None
-        return self._to_detections(out, f_dev, len(chunk))
+        # one packed read of the result rows: [B, Q, 4 + 1 + 2 + 1] float64
+        packed = torch.cat([out["det_xywh"], out["det_score"].double().unsqueeze(-1), out["det_foot"],
+                            out["det_query"].double().unsqueeze(-1)], dim=-1)
+        host = {"rows": torch.empty(packed.shape, dtype=packed.dtype).pin_memory().copy_(packed, non_blocking=True),
+                "n_keep": torch.empty(out["n_keep"].shape, dtype=out["n_keep"].dtype).pin_memory().copy_(out["n_keep"], non_blocking=True)}
+        if with_features:
+            host["feats"] = torch.empty(f_dev.shape, dtype=f_dev.dtype).pin_memory().copy_(f_dev, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return host, done, len(chunk)
+
+    @staticmethod
+    def _finish_chunk(pending):
+        host, done, n_frames = pending
+        done.synchronize()
+        return ViTDetector._rows_to_detections(host["rows"].numpy(), host["n_keep"].numpy(),
+                                               host["feats"].numpy() if "feats" in host else None, n_frames)
 
     @staticmethod
     def _to_detections(out: dict, f_dev, n_frames: int):
         """Compacted device rows -> ([list[Detection]] per frame, [features] per frame)."""
         torch = _lib.require_cuda()
-        with_features = f_dev is not None
-        # one packed device -> host read of the result rows: [B, Q, 4 + 1 + 2 + 1] float64
         packed = torch.cat([out["det_xywh"], out["det_score"].double().unsqueeze(-1), out["det_foot"],
                             out["det_query"].double().unsqueeze(-1)], dim=-1)
-        n_keep = out["n_keep"].cpu().numpy()
-        rows = packed.cpu().numpy()
-        f_host = f_dev.cpu().numpy() if with_features else None
+        return ViTDetector._rows_to_detections(packed.cpu().numpy(), out["n_keep"].cpu().numpy(),
+                                               f_dev.cpu().numpy() if f_dev is not None else None, n_frames)
+
+    @staticmethod
+    def _rows_to_detections(rows, n_keep, f_host, n_frames: int):
+        with_features = f_host is not None
         dets_all, feats_all = [], []
         for j in range(n_frames):
             n = int(n_keep[j])
@@ -477,33 +501,53 @@ class ViTDetector:
         if len(groups) > 1 and self.mixed_sizes == "pad" and not with_features:
             self._detect_padded(frames, groups, results, dev, strict)
             groups = {}
-        for (h0, w0), idxs in groups.items():
-            for c0 in range(0, len(idxs), self.batch_size):
-                chunk = idxs[c0:c0 + self.batch_size]
+        # Device batches are pipelined: while batch k runs on the GPU the host stages batch k + 1 into the other pinned buffer and
+        # then builds the Detection objects of batch k - 1.  A call that fits one device batch is split in two halves for that.
+        per = self.batch_size
+        total = sum(len(v) for v in groups.values())
+        if total > 16 and all(len(v) <= per for v in groups.values()):
+            per = max(8, (max(len(v) for v in groups.values()) + 1) // 2)
+        chunks = [(h0, w0, idxs[c0:c0 + per]) for (h0, w0), idxs in groups.items() for c0 in range(0, len(idxs), per)]
+
+        def store(chunk, d, f):
+            for j, i in enumerate(chunk):
+                results[i] = d[j]
+                feats[i] = f[j]
+
+        def careful(h0, w0, chunk):
+            """A device batch that failed as a whole (e.g. frames too small for the backbone) is retried frame by frame, so that
+            one bad frame costs only itself."""
+            d, f = [], []
+            for i in chunk:
                 try:
-                    d, f = self._detect_chunk(frames, chunk, h0, w0, with_features, dev)
-                except _lib.OpdError as e:
-                    if strict or len(chunk) == 1:
-                        if strict:
-                            raise
-                        logger.error(f"Detection failed for frame {chunk[0]}: {e}")
-                        d, f = [[]], [None]
-                    else:
-                        # the batch failed as a whole (e.g. frames too small for the backbone): retry frame by frame so that one
-                        # bad frame costs only itself
-                        logger.error(f"Detection failed for a batch of {len(chunk)} frames ({e}); retrying frame by frame")
-                        d, f = [], []
-                        for i in chunk:
-                            try:
-                                di, fi = self._detect_chunk(frames, [i], h0, w0, with_features, dev)
-                            except _lib.OpdError as e1:
-                                logger.error(f"Detection failed for frame {i}: {e1}")
-                                di, fi = [[]], [None]
-                            d += di
-                            f += fi
-                for j, i in enumerate(chunk):
-                    results[i] = d[j]
-                    feats[i] = f[j]
+                    di, fi = self._detect_chunk(frames, [i], h0, w0, with_features, dev)
+                except _lib.OpdError as e1:
+                    if strict:
+                        raise
+                    logger.error(f"Detection failed for frame {i}: {e1}")
+                    di, fi = [[]], [None]
+                d += di
+                f += fi
+            store(chunk, d, f)
+
+        pending = None
+        for k, (h0, w0, chunk) in enumerate(chunks):
+            try:
+                launched = self._launch_chunk(frames, chunk, h0, w0, with_features, dev, k % 2)
+            except _lib.OpdError as e:
+                if strict:
+                    raise
+                logger.error(f"Detection failed for a batch of {len(chunk)} frames ({e}); retrying frame by frame")
+                launched = None
+            if pending is not None:
+                store(pending[0], *self._finish_chunk(pending[1]))
+                pending = None
+            if launched is None:
+                careful(h0, w0, chunk)
+            else:
+                pending = (chunk, launched)
+        if pending is not None:
+            store(pending[0], *self._finish_chunk(pending[1]))
         return [r if r is not None else [] for r in results], feats
 
     def _detect_padded(self, frames, groups: dict, results: list, dev, strict: bool) -> None:
