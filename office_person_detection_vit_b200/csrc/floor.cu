@@ -35,7 +35,10 @@ constexpr int kGridCellBudget = 128 * 1024;
 // pick), kByteNone = outside every zone, kByteSlow = the float64 path decides, Z + t (t < 254 - Z) = the cell is crossed by exactly
 // one line, type t of the line table (see opd_zone_table_create).  Per-point codes in the kernel: zone, kCodeNone or kCodeSlow.
 constexpr int kByteNone = 255, kByteSlow = 254;
-constexpr int kMaxLineRecords = 258;    // record 0 + up to 254 line types + the two records of kByteSlow / kByteNone
+constexpr int kMaxLineRecords = 256;    // one table for the whole grid: up to 254 - Z line types
+constexpr int kTypeTile = 32;           // tiled type tables (more triples than a byte can name): tiles of 32 x 32 cells
+constexpr int kMaxTiledRecords = 2048;  // 32 KB of shared memory
+constexpr int kMaxTiles = 1024;
 constexpr int kCodeNone = -1, kCodeSlow = -2;
 constexpr int kMaxSmemVerts = 1024;     // polygons vertices staged in shared memory (16 KB)
 constexpr int kFastThreads = 512;
@@ -111,6 +114,8 @@ struct FloorK {
   const uint8_t* wgrid;          // [gw*gh] winner grid of the float32 path (see kByteNone)
   const float4* line_types;      // [n_line_types]
   int n_line_types;
+  const uint16_t* tile_base;     // tiled type tables: [n_tiles] first record of every 32 x 32-cell tile
+  int tiles_x, n_tiles;
   float line_band;               // a point closer than this to its cell's line goes to the float64 path
   int l2_ahead;                  // floor_fast_kernel: units (per warp) pulled into L2 ahead of the register loads
   // io
@@ -388,6 +393,8 @@ constexpr int kUnitPoints = 256;
 //
 // Drain, when a lane's queue is half full and at the end: the lane queues are compacted row by row (ballot) into the warp's dense
 // float64 queue, which is processed 32 points at a time through the reference's exact arithmetic.
+// kTiled: the line-type byte is relative to the cell's 32 x 32-cell tile (record = tile_base[tile] + t), see opd_zone_table_create.
+template <bool kTiled>
 __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const FloorK p, int cells_rounded) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int kWarps = kFastThreads / 32;
@@ -396,8 +403,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
   const SmemTables t = stage_tables(pg, smem + cells_rounded, cells_rounded);
   uint8_t* s_wgrid = smem;                                                              // [cells_rounded] winner grid
   unsigned char* cur = smem + cells_rounded + (tables_smem_bytes(0, cells_rounded, p.stage_verts, p.n_verts) + 15) / 16 * 16;
-  float4* s_types = reinterpret_cast<float4*>(cur);      // [kMaxLineRecords]
-  cur += kMaxLineRecords * 16;
+  float4* s_types = reinterpret_cast<float4*>(cur);      // [kMaxLineRecords] or, tiled, [kMaxTiledRecords] + tile_base [kMaxTiles] u16
+  cur += (kTiled ? kMaxTiledRecords : kMaxLineRecords) * 16;
+  uint16_t* s_tile_base = reinterpret_cast<uint16_t*>(cur);
+  if (kTiled) cur += kMaxTiles * 2;
   unsigned* s_lq = reinterpret_cast<unsigned*>(cur);     // [warps][kLaneSlots][32]: lane queues
   cur += kWarps * kLaneSlots * 32 * 4;
   unsigned* s_xq = reinterpret_cast<unsigned*>(cur);     // [warps][kExactQueue]: dense float64 queues
@@ -410,6 +419,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
     uint4* dst = reinterpret_cast<uint4*>(s_wgrid);
     for (int i = threadIdx.x; i < cells_rounded / 16; i += kFastThreads) dst[i] = src[i];
     for (int i = threadIdx.x; i < p.n_line_types; i += kFastThreads) s_types[i] = p.line_types[i];
+    if (kTiled)
+      for (int i = threadIdx.x; i < p.n_tiles; i += kFastThreads) s_tile_base[i] = p.tile_base[i];
   }
   __syncthreads();
 
@@ -432,7 +443,10 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
   const uint32_t hist_base = pin_reg((uint32_t)__cvta_generic_to_shared(wh + 2));   // bin of code c: hist_base + 4 c
   const uint32_t type_base = pin_reg((uint32_t)__cvta_generic_to_shared(s_types));
   const float band = pin_reg(p.line_band);
-  const unsigned zu = pin_reg((uint32_t)p.Z), n_types = pin_reg((uint32_t)p.n_line_types);
+  // a type byte names a line when it is below n_types: the table's size, or (tiled) every byte short of kByteSlow / kByteNone
+  const unsigned zu = pin_reg((uint32_t)p.Z), n_types = pin_reg(kTiled ? (uint32_t)(kByteSlow - p.Z) : (uint32_t)p.n_line_types);
+  const uint32_t tile_addr = pin_reg((uint32_t)__cvta_generic_to_shared(s_tile_base));
+  const unsigned tiles_x = pin_reg((uint32_t)p.tiles_x);
   float la = 0.f, lb = 0.f, lc = 1.f;   // the last line record read by this lane
   uint32_t lcodes = 0;
   const uint32_t lq_base = pin_reg((uint32_t)__cvta_generic_to_shared(s_lq + warp * kLaneSlots * 32 + lane));
@@ -485,8 +499,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) floor_fast_kernel(const Floor
     if (in_grid & (qq <= T1)) u = lds_u8(grid_base + (unsigned)iy * gw + (unsigned)ix);
     // single-line cells only (a few percent of the lanes) read their 16-byte record {a, b, c, codes}: a predicated load, so the
     // other lanes cost the shared-memory pipe nothing; their registers keep the previous record (finite, unused)
-    const unsigned t = (unsigned)u - zu;
+    unsigned t = (unsigned)u - zu;
     const bool is_line = t < n_types;
+    if (kTiled) {   // + the first record of the cell's tile (the same few lanes; ix, iy are in the grid whenever is_line)
+      unsigned tb = 0;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u16 %0, [%1];\n\t}"
+                   : "+r"(tb)
+                   : "r"(tile_addr + 2u * (((unsigned)iy / kTypeTile) * tiles_x + (unsigned)ix / kTypeTile)), "r"((unsigned)is_line));
+      t += tb;
+    }
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
                  : "+f"(la), "+f"(lb), "+f"(lc), "+r"(lcodes)
                  : "r"(type_base + 16u * t), "r"((unsigned)is_line));
@@ -720,6 +741,8 @@ struct opd_zone_table {
   uint8_t* d_wgrid = nullptr;     // winner grid (see kByteNone)
   float4* d_line_types = nullptr; // [n_line_types] {a, b, c, codes}: a x + b y + c > 0 -> code A (low byte) else code B (second byte)
   int n_line_types = 0, n_line_cells = 0;
+  int tiles_x = 0, n_tiles = 0;   // tiles_x > 0: tiled type tables
+  uint16_t* d_tile_base = nullptr;
 };
 
 extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly_offsets, const double* priority,
@@ -770,6 +793,7 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
   std::vector<uint64_t> entry_inside, entry_cand;
   std::vector<uint8_t> wgrid;
   std::vector<float4> line_types;
+  std::vector<uint16_t> tile_base;   // tiled type tables: first record of every tile (empty: one table for the whole grid)
 
   if (Z == 0) {
     zt->gw = zt->gh = 1;
@@ -939,15 +963,43 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
     for (auto& kv : type_cells) order.push_back({kv.second.size(), kv.first});
     std::sort(order.begin(), order.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
     const bool lines_ok = zt->delta >= 0.01;   // the band argument needs delta well above the float32 error of the line function
-    for (size_t t = 0; lines_ok && t < order.size() && t < (size_t)(254 - Z); ++t) {
-      const TypeKey& k = order[t].second;
+    auto record_of = [&](const TypeKey& k) {
       const Line& L = lines[k.line];
       const uint32_t codes = ((uint32_t)k.a & 255u) | (((uint32_t)k.b & 255u) << 8);
       float cf;
       memcpy(&cf, &codes, 4);
-      line_types.push_back(make_float4((float)L.a, (float)L.b, (float)L.c, cf));
-      for (size_t c : type_cells[k]) wgrid[c] = (uint8_t)(Z + (int)t);
-      zt->n_line_cells += (int)type_cells[k].size();
+      return make_float4((float)L.a, (float)L.b, (float)L.c, cf);
+    };
+    const size_t cap = (size_t)(254 - Z);
+    if (lines_ok && order.size() <= cap) {
+      // one table for the whole grid: byte Z + t = type t
+      for (size_t t = 0; t < order.size(); ++t) {
+        const TypeKey& k = order[t].second;
+        line_types.push_back(record_of(k));
+        for (size_t c : type_cells[k]) wgrid[c] = (uint8_t)(Z + (int)t);
+        zt->n_line_cells += (int)type_cells[k].size();
+      }
+    } else if (lines_ok) {
+      // more (line, code A, code B) triples than a byte can name (e.g. 64 many-sided polygons): one table per TILE of
+      // kTypeTile x kTypeTile cells; byte Z + t = type t of the cell's tile, record tile_base[tile] + t.  The most frequent triples
+      // of every tile first; a tile keeps at most 254 - Z types and the grid at most kMaxTiledRecords records (the rest: slow cells).
+      zt->tiles_x = (gw + kTypeTile - 1) / kTypeTile;
+      const int tiles_y = (gh + kTypeTile - 1) / kTypeTile;
+      std::vector<std::map<TypeKey, std::vector<size_t>>> per_tile((size_t)zt->tiles_x * tiles_y);
+      for (auto& kv : type_cells)
+        for (size_t c : kv.second) per_tile[(c / gw / kTypeTile) * zt->tiles_x + (c % gw) / kTypeTile][kv.first].push_back(c);
+      tile_base.assign(per_tile.size() + 1, 0);
+      for (size_t ti = 0; ti < per_tile.size(); ++ti) {
+        tile_base[ti] = (uint16_t)line_types.size();
+        std::vector<std::pair<size_t, TypeKey>> ord;
+        for (auto& kv : per_tile[ti]) ord.push_back({kv.second.size(), kv.first});
+        std::sort(ord.begin(), ord.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+        for (size_t t = 0; t < ord.size() && t < cap && line_types.size() < (size_t)kMaxTiledRecords; ++t) {
+          line_types.push_back(record_of(ord[t].second));
+          for (size_t c : per_tile[ti][ord[t].second]) wgrid[c] = (uint8_t)(Z + (int)t);
+          zt->n_line_cells += (int)per_tile[ti][ord[t].second].size();
+        }
+      }
     }
     zt->n_line_types = (int)line_types.size();
   }
@@ -971,7 +1023,8 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
   const size_t o_rk = o_po + up16(68 * 4);
   const size_t o_wg = o_rk + up16(64 * 4);
   const size_t o_lt = o_wg + up16(wgrid.size());
-  const size_t total = o_lt + (size_t)kMaxLineRecords * 16 + 16;
+  const size_t o_tb = o_lt + up16(std::max<size_t>(kMaxLineRecords, line_types.size()) * 16);
+  const size_t total = o_tb + up16((tile_base.size() + 8) * 2) + 16;
   std::vector<unsigned char> blob(total, 0);
   memcpy(&blob[o_grid], grid.data(), grid.size());
   memcpy(&blob[o_cm], class_mask.data(), 256 * 8);
@@ -984,6 +1037,7 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
   memcpy(&blob[o_rk], rank.data(), 64 * 4);
   memcpy(&blob[o_wg], wgrid.data(), wgrid.size());
   if (!line_types.empty()) memcpy(&blob[o_lt], line_types.data(), line_types.size() * 16);
+  if (!tile_base.empty()) memcpy(&blob[o_tb], tile_base.data(), tile_base.size() * 2);
 
   opd::DeviceGuard guard(device);
   cudaError_t e = guard.err;
@@ -1005,6 +1059,12 @@ extern "C" int opd_zone_table_create(const double* verts_xy, const int32_t* poly
   zt->d_zone_rank = reinterpret_cast<int32_t*>(zt->d_blob + o_rk);
   zt->d_wgrid = zt->d_blob + o_wg;
   zt->d_line_types = reinterpret_cast<float4*>(zt->d_blob + o_lt);
+  zt->d_tile_base = reinterpret_cast<uint16_t*>(zt->d_blob + o_tb);
+  if (zt->tiles_x > 0 && (int)tile_base.size() > kMaxTiles) {   // absurdly large grids: no line types at all
+    zt->tiles_x = 0;
+    zt->n_line_types = 0;
+  }
+  zt->n_tiles = zt->tiles_x > 0 ? (int)tile_base.size() : 0;
   *out = zt;
   return OPD_OK;
 }
@@ -1056,6 +1116,7 @@ int fill_params(FloorK& k, const opd_floor_params* p, const opd_zone_table* zt, 
   k.cell_entry = zt->d_cell_entry; k.entry_inside = zt->d_entry_inside; k.entry_cand = zt->d_entry_cand;
   k.verts = zt->d_verts; k.poly_off = zt->d_poly_off; k.zone_rank = zt->d_zone_rank;
   k.wgrid = zt->d_wgrid; k.line_types = zt->d_line_types; k.n_line_types = zt->n_line_types;
+  k.tile_base = zt->d_tile_base; k.tiles_x = zt->tiles_x; k.n_tiles = zt->n_tiles;
   // |p̂ - p| <= Δ/2 per coordinate (q <= T1) -> <= Δ/sqrt(2) along the unit normal; + float32 rounding of a, b, c and of the two
   // multiply-adds (<= 1e-3 px for |p| <= 4000) + the 1e-6 px tolerance under which coincident edges were merged into one line
   k.line_band = (float)(0.75 * zt->delta + 1.5e-3);
@@ -1145,9 +1206,11 @@ extern "C" int opd_floor_project_classify_count_f32(const opd_floor_params* p, c
   if (int rc = device_sm_count(zt->device, &sms)) return rc;
   k.stage_grid = 1;
   const size_t smem = (size_t)zt->cells_rounded + (tables_smem_bytes(0, zt->cells_rounded, k.stage_verts, k.n_verts) + 15) / 16 * 16 +
-                      kMaxLineRecords * 16 + (kFastThreads / 32) * (kLaneSlots * 32 + kExactQueue) * 4 +
+                      (zt->tiles_x > 0 ? kMaxTiledRecords * 16 + kMaxTiles * 2 : kMaxLineRecords * 16) +
+                      (kFastThreads / 32) * (kLaneSlots * 32 + kExactQueue) * 4 +
                       (kFastThreads / 32) * (kHistBins + 1) * 4 + 16;
-  auto kern = floor_fast_kernel;
+  if (smem > 227 * 1024) return launch_exact<float>(k, zt, s);   // cannot happen with the budgets above; never launch past the limit
+  auto kern = zt->tiles_x > 0 ? floor_fast_kernel<true> : floor_fast_kernel<false>;
   OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long chunks = (N + kFastChunk - 1) / kFastChunk;
   const unsigned blocks = (unsigned)std::min<long long>(chunks, sms);
