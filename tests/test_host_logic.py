@@ -76,3 +76,51 @@ def test_csv_layout(tmp_path):
     out = tmp_path / "zone_counts.csv"
     agg.export_csv(str(out), zone_ids=["zone_a", "zone_b"])
     assert out.read_text().splitlines() == ["timestamp,zone_a,zone_b,unclassified", "12:00,0,3,0", "12:05,1,0,2"]
+
+
+# ---- phases.py host logic (no GPU): config handling, the reference's error messages, the JSON writer ----------------------
+def test_phase_config_errors_match_the_reference():
+    import logging
+
+    from office_person_detection_vit_b200.phases import DetectionPhase, TransformPhase, _cfg
+
+    log = logging.getLogger("test_host_logic")
+    assert _cfg({"a": {"b": 3}}, "a.b") == 3 and _cfg({"a": {"b": 3}}, "a.c", 7) == 7 and _cfg(None, "x", 1) == 1
+    with pytest.raises(RuntimeError, match="initialize"):                      # detection.py:70-71
+        DetectionPhase({}, log).execute([])
+    with pytest.raises(ValueError, match="homography.matrix が設定されていません"):    # transform.py:144-145
+        TransformPhase({"zones": []}, log).initialize()
+    with pytest.raises(ValueError, match="3x3"):                               # transform.py:148-149
+        TransformPhase({"homography": {"matrix": [[1, 0], [0, 1]]}}, log).initialize()
+    with pytest.raises(RuntimeError, match="Not initialized"):                 # transform.py:266-267
+        TransformPhase({}, log).execute([])
+
+
+@pytest.mark.parametrize("name", ["grid16", "star16"])
+def test_export_results_reproduces_the_reference_json(name, tmp_path):
+    """TransformPhase.export_results on the records the REFERENCE's phases produced (tests/golden/phase_golden/<name>/
+    frame_results.json, full precision) writes the reference's coordinate_transformations.json byte for byte
+    (transform.py:398-531: key names, rounding, indent)."""
+    import json
+    import logging
+
+    from office_person_detection_vit_b200.models import Detection, FrameResult
+    from office_person_detection_vit_b200.phases import TransformPhase
+
+    from .conftest import GOLDEN
+
+    gold = GOLDEN / "phase_golden" / name
+    c = json.loads((gold / "config.json").read_text())
+    cfg = {"homography": {"matrix": c["homography"]}, "floormap": c["floormap"], "zones": c["zones"],
+           "output": {"json_optimization": c["json_optimization"]}}
+    p3 = TransformPhase(cfg, logging.getLogger("test_host_logic"))
+    p3.initialize()                                                            # host only: validation, no device table yet
+    frs = [FrameResult(frame_number=r["frame_number"], timestamp=r["timestamp"], zone_counts=r["zone_counts"],
+                       detections=[Detection(bbox=tuple(d["bbox"]), confidence=d["confidence"], class_id=1, class_name="person",
+                                             camera_coords=tuple(d["camera_coords"]), floor_coords=tuple(d["floor_coords"]),
+                                             floor_coords_mm=tuple(d["floor_coords_mm"]), zone_ids=d["zone_ids"])
+                                   for d in r["detections"]])
+           for r in json.loads((gold / "frame_results.json").read_text())]
+    p3.export_results(frs, tmp_path)
+    assert (tmp_path / "coordinate_transformations.json").read_text(encoding="utf-8") == \
+        (gold / "coordinate_transformations.json").read_text(encoding="utf-8")
