@@ -1129,7 +1129,10 @@ int run_plan(opd_detr* m, cudaStream_t s) {
     p.once_done = true;
   }
   for (auto& step : p.steps)
-    if (int rc = step.run(s)) return rc;
+    if (int rc = step.run(s)) {   // name the layer: a launch error otherwise only carries the kernel's source line
+      const std::string why = opd::last_error_ref();
+      return opd::fail(rc, "step '%s': %s", step.name.c_str(), why.c_str());
+    }
   return OPD_OK;
 }
 }  // namespace

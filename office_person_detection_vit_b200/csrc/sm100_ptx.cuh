@@ -46,10 +46,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+#ifdef OPD_TRAP_INFO
+// Debug builds (-DOPD_TRAP_INFO): a thread that has waited for half of the spin budget records what it waits for in a mapped host
+// buffer (set per translation unit by the launching code): [0] = count, then (barrier smem address | parity << 31) | block << 32 |
+// thread << 48.  The host prints the list when the launch fails, i.e. the wait graph of a protocol deadlock.
+static __device__ unsigned long long* g_trap_info = nullptr;
+static __device__ __noinline__ void trap_record(uint64_t* bar, uint32_t parity) {
+  if (!g_trap_info) return;
+  const unsigned long long i = atomicAdd(g_trap_info, 1ull);
+  if (i < 1023)
+    g_trap_info[1 + i] = (unsigned long long)(smem_u32(bar) | (parity << 31)) | ((unsigned long long)blockIdx.x << 32) |
+                         ((unsigned long long)threadIdx.x << 48);
+  __threadfence_system();
+}
+constexpr uint32_t kSpinLimit = 1u << 22;
+#else
+constexpr uint32_t kSpinLimit = 1u << 26;
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    ++spins;
+#ifdef OPD_TRAP_INFO
+    if (spins == kSpinLimit / 2) trap_record(bar, parity);
+#endif
+    if (spins > kSpinLimit) __trap();
   }
 }
 

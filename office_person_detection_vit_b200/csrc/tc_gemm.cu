@@ -44,8 +44,12 @@ constexpr int kNumThreads = 384;
 constexpr int kSmemBudget = 232448;           // 227 KB
 
 // residual tiles travel global -> smem by TMA in 64-column chunks (same swizzled layout as the output staging)
-__host__ __device__ constexpr int res_stages_for(int block_n, bool has_res) {
-  return !has_res ? 0 : (block_n >= 256 ? 2 : 4);
+// (cta_group::2 tiles hold half a weight tile per ring slot: a third residual slot fits without costing an operand slot)
+__host__ __device__ constexpr int res_stages_for(int block_n, bool has_res, bool pair = false) {
+#ifndef OPD_PAIR_RES_SLOTS
+#define OPD_PAIR_RES_SLOTS 3
+#endif
+  return !has_res ? 0 : (block_n >= 256 ? (pair ? OPD_PAIR_RES_SLOTS : 2) : 4);
 }
 // bias of the WHOLE layer [kMaxN floats, loaded once per CTA] + barriers (+ LayerNorm partial sums [2][128][2] floats for the
 // residual / LayerNorm epilogues, double-buffered by tile parity: no
@@ -58,7 +62,7 @@ __host__ __device__ constexpr int tail_bytes_for(bool has_res) { return kMaxN * 
 constexpr int kBResKBlocks = 4;
 __host__ __device__ constexpr int stages_for(int block_n, bool has_res, bool b_res = false, int out_bufs = 1, int m_tiles = 1,
                                              bool pair = false) {
-  const int fixed = (2 * out_bufs + res_stages_for(block_n, has_res)) * STAGING_BYTES + tail_bytes_for(has_res);
+  const int fixed = (2 * out_bufs + res_stages_for(block_n, has_res, pair)) * STAGING_BYTES + tail_bytes_for(has_res);
   if (b_res) {
     const int n = (kSmemBudget - fixed - kBResKBlocks * block_n * BLOCK_K * 2) / A_STAGE_BYTES;
     return n > 8 ? 8 : n;
@@ -71,7 +75,7 @@ __host__ __device__ constexpr int smem_bytes_for(int block_n, bool has_res, bool
                                                  bool pair = false) {
   return stages_for(block_n, has_res, b_res, out_bufs, m_tiles, pair) *
              (m_tiles * A_STAGE_BYTES + (b_res ? 0 : block_n * BLOCK_K * 2 / (pair ? 2 : 1))) +
-         (b_res ? kBResKBlocks * block_n * BLOCK_K * 2 : 0) + (2 * out_bufs + res_stages_for(block_n, has_res)) * STAGING_BYTES +
+         (b_res ? kBResKBlocks * block_n * BLOCK_K * 2 : 0) + (2 * out_bufs + res_stages_for(block_n, has_res, pair)) * STAGING_BYTES +
          tail_bytes_for(has_res);
 }
 
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   constexpr int A_SLOT_BYTES = kMTiles * A_STAGE_BYTES;
   static_assert(kCluster == 1 || (kCluster == 2 && !kBRes), "clusters of two, not combined with the weight-stationary variant");
   constexpr int kStages = stages_for(BLOCK_N, kHasRes, kBRes, kOutBufs, kMTiles, kPair);
-  constexpr int kResStages = res_stages_for(BLOCK_N, kHasRes);
+  constexpr int kResStages = res_stages_for(BLOCK_N, kHasRes, kPair);
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2 / (kPair ? 2 : 1);   // kPair: this CTA's half of the weight tile
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kPair ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
@@ -405,7 +409,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
       for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rowp + (((h * 4 + j) ^ (row & 7)) << 4));
     };
     auto res_slot = [&]() { return (int)(rq % kResStages); };
-    auto res_wait = [&]() { ptx::mbar_wait(&res_full[rq % kResStages], (rq / kResStages) & 1); };
+    // An odd ring (three slots, cta_group::2 tiles) hands every slot to the two warpgroups in turn, so a warpgroup sees only every
+    // second phase of a slot's barrier and a parity wait alone cannot tell "my chunk has not landed" from "the other warpgroup's
+    // chunk before it has not landed" (both look like a completed phase of my parity: the wait would fall through and read stale
+    // bytes, then release the slot out of turn).  Waiting first for the other warpgroup's RELEASE of the previous occupant - which
+    // the producer needs anyway before it can load my chunk - pins the phase: that release follows the previous load's completion,
+    // and the next one needs my own release.  (My own release two phases back is complete: the staging barrier of that chunk
+    // follows it.)  Even rings give each warpgroup its own slots and need none of this.
+    auto res_wait = [&]() {
+      if constexpr (kHasRes && kResStages % 2 == 1 && kChunks > 1) {
+        if (rq >= (uint32_t)kResStages) ptx::mbar_wait(&res_empty[rq % kResStages], (rq / kResStages - 1) & 1);
+      }
+      ptx::mbar_wait(&res_full[rq % kResStages], (rq / kResStages) & 1);
+    };
     auto res_release = [&]() {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&res_empty[rq % kResStages]);
@@ -754,6 +770,29 @@ int launch_t(const GemmParams& p, int grid, cudaStream_t s) {
   return OPD_OK;
 }
 
+#ifdef OPD_TRAP_INFO
+unsigned long long* g_trap_host = nullptr;
+void trap_info_arm() {
+  if (!g_trap_host) {
+    cudaHostAlloc(&g_trap_host, 1024 * 8, cudaHostAllocMapped);
+    unsigned long long* dev = nullptr;
+    cudaHostGetDevicePointer(&dev, g_trap_host, 0);
+    cudaMemcpyToSymbol(ptx::g_trap_info, &dev, sizeof(dev));
+  }
+  g_trap_host[0] = 0;
+}
+void trap_info_print(const GemmParams& p, int grid) {
+  const unsigned long long n = g_trap_host ? g_trap_host[0] : 0;
+  fprintf(stderr, "trap info: M=%d N=%d K=%d grid=%d m_blocks=%d n_blocks=%d: %llu waiting threads\n", p.M, p.N, p.K, grid, p.num_m_blocks,
+          p.num_n_blocks, n);
+  for (unsigned long long i = 0; i < n && i < 1023; ++i) {
+    const unsigned long long v = g_trap_host[1 + i];
+    fprintf(stderr, "  block %llu thread %llu (warp %llu): barrier 0x%llx parity %llu\n", (v >> 32) & 0xffff, v >> 48, (v >> 48) / 32,
+            v & 0x7fffffffull, (v >> 31) & 1);
+  }
+}
+#endif
+
 template <int BLOCK_N, bool kHasRes, bool kPair = false>
 int launch_cluster2(const GemmParams& p, int grid, cudaStream_t s) {
   auto kern = tc_gemm_kernel<BLOCK_N, kHasRes, false, 2, 1, 1, kPair>;
@@ -779,6 +818,15 @@ int launch_cluster2(const GemmParams& p, int grid, cudaStream_t s) {
     return rc;
   OPD_REQUIRE(max_clusters > 0, "gemm: no 2-CTA cluster of the tensor-core kernel fits on this device");
   cfg.gridDim = dim3(2 * std::min(grid / 2, max_clusters));
+#ifdef OPD_TRAP_INFO
+  trap_info_arm();
+  if (cudaLaunchKernelEx(&cfg, kern, p) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+    trap_info_print(p, (int)cfg.gridDim.x);
+    return fail(OPD_ERR_CUDA, "cluster GEMM failed (trap info on stderr)");
+  }
+  count_launch();
+  return OPD_OK;
+#endif
   OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
@@ -792,8 +840,13 @@ int finish_plan(GemmPlan* plan) {
   OPD_REQUIRE(N <= kMaxN, "gemm: N=%d exceeds the %d columns whose bias fits the kernel's shared-memory table", N, kMaxN);
   int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
   if (plan->epi == EPI_BIAS_RES_LN) OPD_REQUIRE(N == 256, "gemm: the LayerNorm epilogue needs N == 256 (got %d)", N);
-  // bottleneck outputs (bias + residual + ReLU) are HBM-bound: narrower tiles leave room for a deeper residual ring
-  if (plan->epi == EPI_BIAS_RES_RELU && bn == 256) bn = 128;
+  // bottleneck outputs (bias + residual + ReLU) are HBM-bound.  K >= 256: 256-column cta_group::2 tiles (four operand slots of
+  // 512 MMA cycles each + three residual slots; the 128-column kernel with double staging boxes is left with TWO operand slots:
+  // M = 67200, N = 2048, K = 512 ran in 265 us against 140 us, benchmarks/gemm_shapes.py).  K < 256: 128-column tiles with the
+  // four-slot residual ring.
+  const int rw = g_option_gemm_res_wide.load();
+  const bool res_wide = rw == 2 || (rw == 1 && plan->K / BLOCK_K >= 4);
+  if (plan->epi == EPI_BIAS_RES_RELU && bn == 256 && !res_wide) bn = 128;
   // small problems: prefer more, narrower tiles so that every SM gets work
   const long long m_blocks = (plan->M + BLOCK_M - 1) / BLOCK_M;
   while (bn > 64 && plan->epi != EPI_BIAS_RES_LN && m_blocks * (N / bn) < sm_count() && N % (bn / 2) == 0) bn /= 2;

@@ -65,6 +65,7 @@ def test_gemm_weight_stationary_variant_is_bit_identical(T, M, N, K):
     a, w = _rand(torch, M, K, seed=11), _rand(torch, N, K, seed=12, scale=K ** -0.5)
     bias, res = torch.randn(N, device="cuda"), _rand(torch, M, N, seed=13)
     try:
+        _lib.check(_lib.lib().opd_set_option(b"gemm_res_wide", 0), "opd_set_option")   # the variant belongs to the 128-column tiles
         _lib.check(_lib.lib().opd_set_option(b"gemm_bres", 0), "opd_set_option")
         ref = ops.gemm(a, w, bias, epilogue=2, residual=res)
         _lib.check(_lib.lib().opd_set_option(b"gemm_bres", 2), "opd_set_option")
@@ -72,8 +73,60 @@ def test_gemm_weight_stationary_variant_is_bit_identical(T, M, N, K):
         torch.cuda.synchronize()
     finally:
         _lib.lib().opd_set_option(b"gemm_bres", 1)
+        _lib.lib().opd_set_option(b"gemm_res_wide", 1)
     assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
     _close(torch, got, (a.float() @ w.float().T + bias + res.float()).relu(), f"weight-stationary gemm {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(128 * 301 + 77, 2048, 512), (128 * 160, 1024, 256), (128 * 9 + 1, 512, 256), (128 * 75, 256, 128), (90, 1024, 512)])
+def test_gemm_residual_wide_tiles_are_bit_identical(T, M, N, K):
+    """Bias + residual + ReLU layers with K >= 256 run on 256-column cta_group::2 tiles with a three-slot residual ring (default);
+    the 128-column kernel they replaced accumulates in the same order: bit-identical outputs for even / odd / ragged m-block
+    counts, for shapes with too few tile pairs for clusters (single-CTA 256-column kernel) and when forced on a K = 128 layer."""
+    from office_person_detection_vit_b200 import _lib
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    a, w = _rand(torch, M, K, seed=41), _rand(torch, N, K, seed=42, scale=K ** -0.5)
+    bias, res = torch.randn(N, device="cuda"), _rand(torch, M, N, seed=43)
+    try:
+        _lib.check(_lib.lib().opd_set_option(b"gemm_res_wide", 0), "opd_set_option")
+        ref = ops.gemm(a, w, bias, epilogue=2, residual=res)
+        _lib.check(_lib.lib().opd_set_option(b"gemm_res_wide", 2), "opd_set_option")
+        got = ops.gemm(a, w, bias, epilogue=2, residual=res)
+        _lib.check(_lib.lib().opd_set_option(b"gemm_res_wide", 1), "opd_set_option")
+        dflt = ops.gemm(a, w, bias, epilogue=2, residual=res)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().opd_set_option(b"gemm_res_wide", 1)
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    assert torch.equal(dflt.view(torch.int16), ref.view(torch.int16))
+    _close(torch, got, (a.float() @ w.float().T + bias + res.float()).relu(), f"wide residual gemm {M}x{N}x{K}")
+
+
+def test_gemm_residual_ring_with_l2_warm_residual(T):
+    """Regression: the three-slot residual ring of the cta_group::2 kernel hands each slot to the two epilogue warpgroups in turn;
+    with a parity wait alone a warpgroup could take the OTHER warpgroup's not-yet-landed chunk for its own completed phase (seen
+    as flaky launch failures at batch 5, where the residual written by the previous layer is partly L2-resident and TMA latencies
+    vary between chunks).  Residual rewritten right before every launch, many launches, every output bit-identical."""
+    from office_person_detection_vit_b200 import _lib
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    M, N, K = 21000, 1024, 256
+    a, w = _rand(torch, M, K, seed=51), _rand(torch, N, K, seed=52, scale=K ** -0.5)
+    bias, src = torch.randn(N, device="cuda"), _rand(torch, M, N, seed=53)
+    res = torch.empty_like(src)
+    try:
+        _lib.check(_lib.lib().opd_set_option(b"gemm_res_wide", 0), "opd_set_option")
+        ref = ops.gemm(a, w, bias, epilogue=2, residual=src)
+    finally:
+        _lib.lib().opd_set_option(b"gemm_res_wide", 1)
+    for it in range(40):
+        res.copy_(src)
+        got = ops.gemm(a, w, bias, epilogue=2, residual=res)
+        assert torch.equal(got.view(torch.int16), ref.view(torch.int16)), f"launch {it}"
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize("M,N,K,epi", [(128 * 7 + 9, 256, 256, 0), (128 * 40, 512, 1024, 1), (128 * 301 + 77, 2048, 256, 1),
