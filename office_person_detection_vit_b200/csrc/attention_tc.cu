@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
   ptx::tc_fence_before_sync();
   __syncthreads();
+  // programmatic dependent launch (opd_set_option("pdl", 1)): everything above overlaps the previous kernel's tail
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + kKV;
@@ -358,11 +361,22 @@ int attn_launch(const AttnPlan& plan, cudaStream_t stream) {
         return OPD_OK;
       }))
     return rc;
-  dim3 grid((plan.Lq + kQ - 1) / kQ, plan.heads, plan.B);
-  if (plan.kv_tile == 128)
-    attention_tc_kernel<128><<<grid, kThreads, AttnCfg<128>::kSmemBytes, stream>>>(p);
-  else
-    attention_tc_kernel<64><<<grid, kThreads, AttnCfg<64>::kSmemBytes, stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = dim3((plan.Lq + kQ - 1) / kQ, plan.heads, plan.B);
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_option_pdl.load() ? 1 : 0;
+  if (plan.kv_tile == 128) {
+    cfg.dynamicSmemBytes = AttnCfg<128>::kSmemBytes;
+    OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_tc_kernel<128>, p));
+  } else {
+    cfg.dynamicSmemBytes = AttnCfg<64>::kSmemBytes;
+    OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_tc_kernel<64>, p));
+  }
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

@@ -22,7 +22,7 @@ extern std::atomic<int> g_option_attention_tc;  // 1 (default): tcgen05 attentio
 extern std::atomic<int> g_option_probe;        // measurement probes, 0 in production: bit 0 stem without patch reloads, bit 1 stem without stores
 extern std::atomic<int> g_option_gemm_cluster; // 0 (default) / 1: BLOCK_N = 256 layers as 2-CTA clusters with multicast weight tiles (measured: no gain)
 extern std::atomic<int> g_option_gemm_outbufs; // 1 (default): short-K GEMMs double-buffer the epilogue's staging boxes
-extern std::atomic<int> g_option_pdl;          // 1: GEMM launches allow programmatic dependent launch (default 0: launch gaps are not what the step waits on)
+extern std::atomic<int> g_option_pdl;          // 1 (default): GEMM / attention launches allow programmatic dependent launch (see opd_set_option)
 extern std::atomic<int> g_option_gemm_mpairs;  // 0 (default) / 1: long-K BLOCK_N = 256 layers on pairs of m-blocks sharing every weight tile (measured: slower)
 extern std::atomic<int> g_option_bneck_release;   // see opd_set_option
 extern std::atomic<int> g_option_bneck_pair;   // cta_group::2 fused bottleneck tail (see opd_set_option)

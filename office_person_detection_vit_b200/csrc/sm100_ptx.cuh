@@ -181,6 +181,9 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
 // ---- programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
 // the previous kernel of the stream drains; everything it reads or writes in global memory must come after this wait ----
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the next kernel of the stream (launched with programmatic stream serialization) start its prologue on free SM resources;
+// its griddepcontrol.wait still blocks until THIS grid has completed and its writes are visible
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // ---- cta_group::2: the two CTAs of a cluster pair act as one 256-row MMA; only the leader (rank 0) issues it ----
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: "the leader's copy of this barrier"
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* leader_bar, void* dst, int c0, int c1) {

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_gemm_kernel(const __grid_co
   if (kCluster > 1) ptx::cluster_sync();   // the peer's barriers are initialised before anything is multicast to them
   // PDL: barriers, TMEM and tensor-map prefetches above overlap the previous kernel's last wave; its results are visible below
   ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   const int cta_rank = kCluster > 1 ? (int)ptx::cluster_ctarank() : 0;
@@ -799,16 +800,18 @@ int launch_cluster2(const GemmParams& p, int grid, cudaStream_t s) {
   static PerDeviceInt cluster_limit;
   int max_clusters = -1;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = smem_bytes_for(BLOCK_N, kHasRes, false, 1, 1, kPair);
   cfg.stream = s;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_option_pdl.load() ? 2 : 1;
   if (int rc = cached_per_device(cluster_limit, &max_clusters, [&](int* n) -> int {
         OPD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(BLOCK_N, kHasRes, false, 1, 1, kPair)));
         cfg.gridDim = dim3(sm_count() / 2 * 2);
