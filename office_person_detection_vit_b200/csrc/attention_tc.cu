@@ -85,8 +85,17 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int kKV>
+// kRegS (64-key tiles): the softmax warps copy the whole S tile into registers (64 per thread) as soon as it is complete and hand
+// the TMEM columns straight back, so S_{j+1} is computed WHILE tile j's maximum / exponentials run instead of after them: the
+// MMA round trip (softmax done -> barrier -> issue -> commit -> barrier -> tcgen05.ld, ~600 cycles per tile) leaves the per-CTA
+// chain.  Price: 3 CTAs per SM instead of 4 (registers).  MEASURED (benchmarks/attention_microbench.py, batch 64): 267 us against
+// 263 us for the default - the shorter chain and the lost CTA cancel - so it stays an option (opd_set_option("attention_kv", 65)).
+// Also measured on the default kernel: nanosleep back-off in the two single-thread roles' barrier spins (a third of all issued
+// instructions, on two of the four schedulers): no change.  ncu (profiles/r02_ncu_attention_raw.csv): MUFU pipe 60 % busy, issue
+// 52 %, the softmax warps' samples are 33 % fixed-latency dependency stalls, 14 % MIO queue, 12 % waiting for MUFU results.
+template <int kKV, bool kRegS = false>
 __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+  static_assert(!kRegS || kKV == 64, "S in registers: 64-key tiles only");
   using C = AttnCfg<kKV>;
   constexpr int TILE_BYTES = C::kTileBytes;
   constexpr int kTmemCols = C::kTmemCols;
@@ -107,7 +116,8 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
   uint64_t* s_full = bars + 9;
   uint64_t* p_ready = bars + 10;
   uint64_t* pv_done = bars + 11;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_free = bars + 12;    // kRegS: every softmax thread holds its S row in registers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kQ, head = blockIdx.y, b = blockIdx.z;
@@ -128,6 +138,7 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
     ptx::mbar_init(s_full, 1);
     ptx::mbar_init(p_ready, 128);
     ptx::mbar_init(pv_done, 1);
+    ptx::mbar_init(s_free, 128);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<kTmemCols>(tmem_ptr);
@@ -175,9 +186,14 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
       issue_s(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
+        if (kRegS && j + 1 < n_tiles) {          // S_j sits in the softmax warps' registers: the next scores go out now
+          ptx::mbar_wait(s_free, j & 1);
+          ptx::tc_fence_after_sync();
+          issue_s(j + 1);
+        }
         ptx::mbar_wait(p_ready, j & 1);          // softmax_j: S consumed, P written, O rescaled
         ptx::tc_fence_after_sync();
-        if (j + 1 < n_tiles) issue_s(j + 1);     // next scores first: their softmax overlaps P V_j
+        if (!kRegS && j + 1 < n_tiles) issue_s(j + 1);     // next scores first: their softmax overlaps P V_j
         ptx::mbar_wait(&v_full[st], (j >> 1) & 1);
         ptx::tc_fence_after_sync();
         const uint32_t v_addr = ptx::smem_u32(s_v + st * TILE_BYTES);
@@ -197,9 +213,23 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
     const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
     float m = -INFINITY, l = 0.f;
     uint8_t* prow = s_p + row * 128;
+    // A warp whose 32 query rows all lie past Lq (the ragged last tile: 1050 = 8 x 128 + 26 leaves three of its four warps
+    // without a row, 8 % of all softmax work) only keeps the barrier protocol going.  Its rows of P stay whatever shared memory
+    // held: every row of P V depends on its own row of P alone, and these rows are never stored.
+    const bool idle_warp = q0 + quarter * 32 >= p.Lq;
     for (int j = 0; j < n_tiles; ++j) {
       ptx::mbar_wait(s_full, j & 1);
       ptx::tc_fence_after_sync();
+      if (idle_warp) {
+        if constexpr (kRegS) {
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(s_free);
+        }
+        if (j > 0) ptx::mbar_wait(pv_done, (j - 1) & 1);
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(p_ready);
+        continue;
+      }
       const int valid = p.Lk - j * kKV;           // keys of this tile that exist (>= kKV: all)
       // keys of each 32-key chunk that take part: those that exist (the last tile of a row of tiles is ragged) and, in a padded
       // batch, are not padding; all-ones for almost every chunk -> the fast loops
@@ -210,13 +240,24 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
         kbits[c] = left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : (1u << left) - 1u);
         if (p.key_mask) kbits[c] &= p.key_mask[(long long)b * p.key_mask_stride + (j * kKV) / 32 + c];
       }
+      uint32_t sv[kRegS ? kKV / 32 : 1][32];
+      if constexpr (kRegS) {
+#pragma unroll
+        for (int c = 0; c < kKV / 32; ++c) ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv[c]);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(s_free);
+      }
       // pass 1: row maximum (3-input max)
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < kKV / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
-        ptx::tmem_ld_wait();
+        uint32_t vv[32];
+        uint32_t(&v)[32] = kRegS ? sv[kRegS ? c : 0] : vv;
+        if constexpr (!kRegS) {
+          ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
+          ptx::tmem_ld_wait();
+        }
         if (kbits[c] == 0xFFFFFFFFu) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
@@ -239,9 +280,12 @@ __global__ void __launch_bounds__(kThreads, AttnCfg<kKV>::kCtasPerSm) attention_
       uint64_t sum2 = pack2f(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < kKV / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
-        ptx::tmem_ld_wait();
+        uint32_t vv[32];
+        uint32_t(&v)[32] = kRegS ? sv[kRegS ? c : 0] : vv;
+        if constexpr (!kRegS) {
+          ptx::tmem_ld_32x32(tmem_s + lane_addr + c * 32, v);
+          ptx::tmem_ld_wait();
+        }
         uint32_t packed[16];
         if (kbits[c] == 0xFFFFFFFFu) {
 #pragma unroll
@@ -341,10 +385,11 @@ int attn_plan(AttnPlan* plan, const __nv_bfloat16* q, int64_t ldq, const __nv_bf
   OPD_REQUIRE(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "attention: bad shape");
   OPD_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention: output not 16-byte aligned");
   const uint64_t cols = (uint64_t)heads * kD;
-  plan->kv_tile = g_option_attention_kv.load() == 128 ? 128 : 64;
+  const int kv_opt = g_option_attention_kv.load();   // 64 (default) / 128 keys per tile; 65 = 64 keys with S held in registers
+  plan->kv_tile = kv_opt == 128 ? 128 : (kv_opt == 65 ? 65 : 64);
   if (int rc = make_tmap_head(&plan->tmQ, q, (uint64_t)B * Lq, cols, ldq, 128)) return rc;
-  if (int rc = make_tmap_head(&plan->tmK, k, (uint64_t)B * Lk, cols, ldk, plan->kv_tile)) return rc;
-  if (int rc = make_tmap_head(&plan->tmV, v, (uint64_t)B * Lk, cols, ldv, plan->kv_tile)) return rc;
+  if (int rc = make_tmap_head(&plan->tmK, k, (uint64_t)B * Lk, cols, ldk, plan->kv_tile & ~1)) return rc;
+  if (int rc = make_tmap_head(&plan->tmV, v, (uint64_t)B * Lk, cols, ldv, plan->kv_tile & ~1)) return rc;
   plan->o = o; plan->ldo = ldo; plan->B = B; plan->heads = heads; plan->Lq = Lq; plan->Lk = Lk;
   return OPD_OK;
 }
@@ -358,6 +403,7 @@ int attn_launch(const AttnPlan& plan, cudaStream_t stream) {
   if (int rc = once_per_device(configured, []() -> int {
         OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128>::kSmemBytes));
         OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::kSmemBytes));
+        OPD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::kSmemBytes));
         return OPD_OK;
       }))
     return rc;
@@ -373,6 +419,9 @@ int attn_launch(const AttnPlan& plan, cudaStream_t stream) {
   if (plan.kv_tile == 128) {
     cfg.dynamicSmemBytes = AttnCfg<128>::kSmemBytes;
     OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_tc_kernel<128>, p));
+  } else if (plan.kv_tile == 65) {
+    cfg.dynamicSmemBytes = AttnCfg<64>::kSmemBytes;
+    OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_tc_kernel<64, true>, p));
   } else {
     cfg.dynamicSmemBytes = AttnCfg<64>::kSmemBytes;
     OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_tc_kernel<64>, p));

@@ -18,6 +18,9 @@ int opd_debug_mma_probe(int32_t N, int32_t swizzle32, int32_t n_acc, int32_t ite
  * memory through shifted UMMA descriptors (mode 0) or nine im2col copies (mode 1). */
 int opd_halo_conv3x3_test(const void* x_dev, int32_t B, int32_t H, int32_t W, const void* w_dev, const float* bias_dev,
                           void* y_dev, int32_t mode, void* stream);
+/* benchmarks/pipe_probe.py: instruction-pipe throughput (mode 0 MUFU.EX2, 1 cvt.rn.bf16x2.f32, 2 fma.rn.f32x2, 3 the softmax mix);
+ * cycles_dev[grid] receives each CTA's clock64 ticks for `iters` iterations of 8 (modes 0-2) or 4 pairs (mode 3) per thread. */
+int opd_debug_pipe_probe(int32_t mode, int32_t iters, int32_t grid, int32_t threads, float* out_dev, uint64_t* cycles_dev, void* stream);
 #ifdef __cplusplus
 }
 #endif

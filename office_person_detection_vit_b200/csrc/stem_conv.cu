@@ -69,30 +69,33 @@ __global__ void __launch_bounds__(256) s2d_preprocess_kernel(const uint8_t* __re
         lut[c][u] = __bfloat16_as_ushort(__float2bfloat16_rn(((float)u - mean[c]) / stdv[c]));
     __syncthreads();
   }
-  const long long total = (long long)B * H2 * W2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W2);
-    long long r = i / W2;
-    const int y = (int)(r % H2);
-    const int b = (int)(r / H2);
-    uint32_t v[12];
+  // Work unit = one row of S (frame b, row y): blocks stride over the B * H2 rows, threads over the row's pixels.  (A flat index
+  // cost two 64-bit divisions per pixel: ~300 of the thread's ~400 instructions.)
+  const int rows = B * H2;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / H2, y = r - b * H2;
+    const int vh = valid_hw ? valid_hw[2 * b] : Hs, vw = valid_hw ? valid_hw[2 * b + 1] : Ws;
+    const uint8_t* row0 = src + ((long long)b * Hs + 2 * y) * Ws * 3;
+    const bool ok0 = 2 * y < vh, ok1 = 2 * y + 1 < vh;
+    uint4* dst_row = reinterpret_cast<uint4*>(S + (long long)r * W2 * 16);
+    for (int x = threadIdx.x; x < W2; x += blockDim.x) {
+      uint32_t v[12];
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
+      for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int iy = 2 * y + dy, ix = 2 * x + dx;
-        const int vh = valid_hw ? valid_hw[2 * b] : Hs, vw = valid_hw ? valid_hw[2 * b + 1] : Ws;
-        const bool ok = iy < vh && ix < vw;
-        const uint8_t* px = src + (((long long)b * Hs + (ok ? iy : 0)) * Ws + (ok ? ix : 0)) * 3;
+        for (int dx = 0; dx < 2; ++dx) {
+          const int ix = 2 * x + dx;
+          const bool ok = (dy ? ok1 : ok0) && ix < vw;
+          const uint8_t* px = row0 + (ok ? (long long)dy * Ws * 3 + ix * 3 : 0);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[(dy * 2 + dx) * 3 + c] = ok ? (uint32_t)lut[c][px[bgr ? 2 - c : c]] : 0u;
-      }
-    uint4 o0, o1;
-    o0.x = v[0] | (v[1] << 16); o0.y = v[2] | (v[3] << 16); o0.z = v[4] | (v[5] << 16); o0.w = v[6] | (v[7] << 16);
-    o1.x = v[8] | (v[9] << 16); o1.y = v[10] | (v[11] << 16); o1.z = 0u; o1.w = 0u;
-    uint4* dst = reinterpret_cast<uint4*>(S + i * 16);
-    dst[0] = o0;
-    dst[1] = o1;
+          for (int c = 0; c < 3; ++c) v[(dy * 2 + dx) * 3 + c] = ok ? (uint32_t)lut[c][px[bgr ? 2 - c : c]] : 0u;
+        }
+      uint4 o0, o1;
+      o0.x = v[0] | (v[1] << 16); o0.y = v[2] | (v[3] << 16); o0.z = v[4] | (v[5] << 16); o0.w = v[6] | (v[7] << 16);
+      o1.x = v[8] | (v[9] << 16); o1.y = v[10] | (v[11] << 16); o1.z = 0u; o1.w = 0u;
+      dst_row[2 * x] = o0;
+      dst_row[2 * x + 1] = o1;
+    }
   }
 }
 
@@ -504,9 +507,7 @@ int stem_launch(const StemPlan& plan, cudaStream_t stream) {
 int launch_preprocess_s2d(const uint8_t* src, int B, int Hs, int Ws, int src_is_bgr, __nv_bfloat16* s2d, cudaStream_t s,
                           const int32_t* valid_hw) {
   const int H2 = (Hs + 1) / 2, W2 = (Ws + 1) / 2;
-  const long long total = (long long)B * H2 * W2;
-  const long long blocks = (total + 255) / 256;
-  s2d_preprocess_kernel<<<(int)std::min<long long>(blocks, 148LL * 16), 256, 0, s>>>(src, B, Hs, Ws, src_is_bgr, s2d, H2, W2, valid_hw);
+  s2d_preprocess_kernel<<<std::min(B * H2, sm_count() * 8), 224, 0, s>>>(src, B, Hs, Ws, src_is_bgr, s2d, H2, W2, valid_hw);
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;
