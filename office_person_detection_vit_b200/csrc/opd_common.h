@@ -17,7 +17,7 @@ namespace opd {
 
 std::string& last_error_ref();
 extern std::atomic<int64_t> g_launches;
-extern std::atomic<int> g_option_attention_kv;  // keys per attention tile: 64 (default) or 128
+extern std::atomic<int> g_option_attention_kv;  // keys per attention tile: 96 (default), 64 or 128; 65 = 64 with S in registers
 extern std::atomic<int> g_option_attention_tc;  // 1 (default): tcgen05 attention kernel; 0: the mma.sync kernel
 extern std::atomic<int> g_option_probe;        // measurement probes, 0 in production: bit 0 stem without patch reloads, bit 1 stem without stores
 extern std::atomic<int> g_option_gemm_cluster; // 0 (default) / 1: BLOCK_N = 256 layers as 2-CTA clusters with multicast weight tiles (measured: no gain)

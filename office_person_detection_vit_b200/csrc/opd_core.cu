@@ -9,7 +9,7 @@ std::string& last_error_ref() {
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_option_bneck_halo{1};
 std::atomic<int> g_option_attention_tc{1};
-std::atomic<int> g_option_attention_kv{64};
+std::atomic<int> g_option_attention_kv{96};
 std::atomic<int> g_option_probe{0};
 std::atomic<int> g_option_stem_pool{1};
 std::atomic<int> g_option_gemm_bres{1};

@@ -233,10 +233,10 @@ def test_conv_nhwc(T, B, H, W, C, N, k, stride, epi):
 
 
 @pytest.mark.parametrize("B,Lq,Lk", [(2, 100, 100), (2, 100, 1050), (1, 1050, 1050), (3, 1008, 1008), (1, 7, 65), (2, 128, 256)])
-@pytest.mark.parametrize("tc", [1, 2, 3, 0])
+@pytest.mark.parametrize("tc", [4, 1, 2, 3, 0])
 def test_attention(T, B, Lq, Lk, tc):
-    """tc = 1 / 2: the tcgen05 / TMEM kernel (attention_tc.cu) with 64 / 128 keys per tile; tc = 3: 64 keys with the S tile held in
-    registers (early S issue); tc = 0: the mma.sync kernel."""
+    """tc = 4 / 1 / 2: the tcgen05 / TMEM kernel (attention_tc.cu) with 96 (default) / 64 / 128 keys per tile; tc = 3: 64 keys with
+    the S tile held in registers (early S issue); tc = 0: the mma.sync kernel."""
     from office_person_detection_vit_b200 import _lib
     from office_person_detection_vit_b200.detection import ops
 
@@ -244,12 +244,12 @@ def test_attention(T, B, Lq, Lk, tc):
     D, heads = 256, 8
     q, k, v = _rand(torch, B, Lq, D, seed=10), _rand(torch, B, Lk, D, seed=11), _rand(torch, B, Lk, D, seed=12)
     _lib.check(_lib.lib().opd_set_option(b"attention_tc", int(tc > 0)))
-    _lib.check(_lib.lib().opd_set_option(b"attention_kv", {2: 128, 3: 65}.get(tc, 64)))
+    _lib.check(_lib.lib().opd_set_option(b"attention_kv", {1: 64, 2: 128, 3: 65}.get(tc, 96)))
     try:
         o = ops.attention(q, k, v, heads)
     finally:
         _lib.lib().opd_set_option(b"attention_tc", 1)
-        _lib.lib().opd_set_option(b"attention_kv", 64)
+        _lib.lib().opd_set_option(b"attention_kv", 96)
     qh, kh, vh = (t.float().view(B, -1, heads, 32).transpose(1, 2) for t in (q, k, v))
     ref = torch.softmax(qh @ kh.transpose(2, 3) * 32 ** -0.5, -1) @ vh
     ref = ref.transpose(1, 2).reshape(B, Lq, D)
