@@ -22,7 +22,8 @@ SHAPES = (("stage3.conv1x1b", 67200, 2048, 512, 2), ("stage2.conv1x1b", 268800, 
           ("dec.cross_kv", 67200, 1536, 256, 0), ("enc.fc1", 67200, 2048, 256, 1), ("enc.fc2+ln", 67200, 256, 2048, 3),
           ("input_proj", 67200, 256, 2048, 0), ("enc.qk", 67200, 512, 256, 0), ("enc.o+ln", 67200, 256, 256, 3),
           ("stage3.conv1x1a", 67200, 512, 2048, 1), ("stage2.conv1x1a", 268800, 256, 1024, 1),
-          ("stage2.conv1x1b@B8", 33600, 1024, 256, 2), ("stage3.conv1x1b@B8", 8400, 2048, 512, 2))
+          ("stage2.conv1x1b@B8", 33600, 1024, 256, 2), ("stage3.conv1x1b@B8", 8400, 2048, 512, 2),
+          ("dec.fc2+ln", 6400, 256, 2048, 3), ("dec.fc1", 6400, 2048, 256, 1), ("stage4.conv1x1a", 16800, 512, 2048, 1))
 
 
 def main():
