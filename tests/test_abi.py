@@ -35,7 +35,10 @@ def test_header_symbols_exported(built_lib):
 def test_probe_library_is_separate(built_lib):
     probe = built_lib.with_name("libopd_probe.so")
     assert probe.exists()
-    assert _exported_c_symbols(probe) == {"opd_debug_mma_probe", "opd_halo_conv3x3_test"}
+    header = (built_lib.parent / "csrc" / "probe" / "opd_probe.h").read_text()
+    declared = set(re.findall(r"\b(opd_\w+)\s*\(", header))
+    assert declared == {"opd_debug_mma_probe", "opd_halo_conv3x3_test", "opd_debug_pipe_probe"}
+    assert _exported_c_symbols(probe) == declared
     assert not (_exported_c_symbols(built_lib) & _exported_c_symbols(probe))
 
 
