@@ -51,24 +51,24 @@ struct StemParams {
   int probe;   // measurement probes (opd_set_option("probe")): bit 0 no patch reloads, bit 1 no output stores
 };
 
-// The input is uint8: (u - 255 * mean[c]) / (255 * std[c]) rounded to bf16 takes 3 x 256 values.  Every CTA tabulates them
-// with exactly that expression (one division per table entry instead of one per pixel channel) and the pixel loop is byte load ->
-// table -> pack: the same bits as computing each value in place, a third of the instructions.
+// The input is uint8: (u - 255 * mean[c]) / (255 * std[c]) rounded to bf16 takes 3 x 256 values, each reproduced bit for bit by
+// one FMA (see `norm` below).
 // valid_hw (optional, [B, 2] int32): frame b holds a picture of valid_hw[b] = (h, w) pixels in the top-left corner of its
 // Hs x Ws canvas; the rest is the batch padding and becomes 0 AFTER normalisation, like DetrImageProcessor.pad (pixel_mask = 0).
 __global__ void __launch_bounds__(256) s2d_preprocess_kernel(const uint8_t* __restrict__ src, int B, int Hs, int Ws, int bgr,
                                                              __nv_bfloat16* __restrict__ S, int H2, int W2,
                                                              const int32_t* __restrict__ valid_hw) {
-  __shared__ uint16_t lut[3][256];   // [colour of the OUTPUT (RGB)][byte value] -> bf16 bits
-  {
-    const float mean[3] = {0.485f * 255.0f, 0.456f * 255.0f, 0.406f * 255.0f};
-    const float stdv[3] = {0.229f * 255.0f, 0.224f * 255.0f, 0.225f * 255.0f};
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      for (int u = threadIdx.x; u < 256; u += blockDim.x)
-        lut[c][u] = __bfloat16_as_ushort(__float2bfloat16_rn(((float)u - mean[c]) / stdv[c]));
-    __syncthreads();
-  }
+  // (u - 255 mean[c]) / (255 std[c]) -> bf16, as fma(u, 1 / s, -m / s): for every one of the 3 x 256 possible inputs the bf16 result
+  // has the bits of the reference's subtract-then-divide (enumerated offline and in tests/test_detr_gpu.py; the two float32
+  // values differ by at most one ulp, never across a bf16 rounding boundary).  A 3 x 256-entry shared-memory table of those
+  // values (round 1) cost ~3.5 bank-conflicted wavefronts per look-up: 80 us of the kernel's 180.
+  constexpr float kMean[3] = {0.485f * 255.0f, 0.456f * 255.0f, 0.406f * 255.0f};
+  constexpr float kStd[3] = {0.229f * 255.0f, 0.224f * 255.0f, 0.225f * 255.0f};
+  constexpr float kInv[3] = {1.0f / kStd[0], 1.0f / kStd[1], 1.0f / kStd[2]};
+  constexpr float kOff[3] = {-kMean[0] / kStd[0], -kMean[1] / kStd[1], -kMean[2] / kStd[2]};
+  auto norm = [&](int c, uint32_t u) {   // float(u) through the 2^23 trick (LOP3 + FADD instead of an I2F on the XU pipe)
+    return fmaf(__uint_as_float(0x4B000000u | u) - 8388608.0f, kInv[c], kOff[c]);
+  };
   // Work unit = one row of S (frame b, row y): blocks stride over the B * H2 rows, threads over the row's pixels.  (A flat index
   // cost two 64-bit divisions per pixel: ~300 of the thread's ~400 instructions.)
   const int rows = B * H2;
@@ -78,23 +78,44 @@ __global__ void __launch_bounds__(256) s2d_preprocess_kernel(const uint8_t* __re
     const uint8_t* row0 = src + ((long long)b * Hs + 2 * y) * Ws * 3;
     const bool ok0 = 2 * y < vh, ok1 = 2 * y + 1 < vh;
     uint4* dst_row = reinterpret_cast<uint4*>(S + (long long)r * W2 * 16);
-    for (int x = threadIdx.x; x < W2; x += blockDim.x) {
-      uint32_t v[12];
+    // kPx pixels per thread and trip, every byte load issued before the first table look-up: the kernel is paced by the bytes a
+    // thread keeps in flight (12 per pixel), not by instructions
+    constexpr int kPx = 3;
+    for (int x0 = threadIdx.x; x0 < W2; x0 += kPx * blockDim.x) {
+      uint8_t raw[kPx][12];
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
+      for (int u = 0; u < kPx; ++u) {
+        const int x = x0 + u * blockDim.x;
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int ix = 2 * x + dx;
-          const bool ok = (dy ? ok1 : ok0) && ix < vw;
-          const uint8_t* px = row0 + (ok ? (long long)dy * Ws * 3 + ix * 3 : 0);
+        for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) v[(dy * 2 + dx) * 3 + c] = ok ? (uint32_t)lut[c][px[bgr ? 2 - c : c]] : 0u;
-        }
-      uint4 o0, o1;
-      o0.x = v[0] | (v[1] << 16); o0.y = v[2] | (v[3] << 16); o0.z = v[4] | (v[5] << 16); o0.w = v[6] | (v[7] << 16);
-      o1.x = v[8] | (v[9] << 16); o1.y = v[10] | (v[11] << 16); o1.z = 0u; o1.w = 0u;
-      dst_row[2 * x] = o0;
-      dst_row[2 * x + 1] = o1;
+          for (int dx = 0; dx < 2; ++dx) {
+            const int ix = 2 * x + dx;
+            const bool ok = x < W2 && (dy ? ok1 : ok0) && ix < vw;
+            const uint8_t* px = row0 + (ok ? (long long)dy * Ws * 3 + ix * 3 : 0);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) raw[u][(dy * 2 + dx) * 3 + c] = px[bgr ? 2 - c : c];
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < kPx; ++u) {
+        const int x = x0 + u * blockDim.x;
+        if (x >= W2) break;
+        float v[12];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const bool ok = (dy ? ok1 : ok0) && 2 * x + dx < vw;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[(dy * 2 + dx) * 3 + c] = ok ? norm(c, raw[u][(dy * 2 + dx) * 3 + c]) : 0.f;
+          }
+        uint4 o0, o1;
+        o0.x = ptx::pack_bf16(v[0], v[1]); o0.y = ptx::pack_bf16(v[2], v[3]); o0.z = ptx::pack_bf16(v[4], v[5]); o0.w = ptx::pack_bf16(v[6], v[7]);
+        o1.x = ptx::pack_bf16(v[8], v[9]); o1.y = ptx::pack_bf16(v[10], v[11]); o1.z = 0u; o1.w = 0u;
+        dst_row[2 * x] = o0;
+        dst_row[2 * x + 1] = o1;
+      }
     }
   }
 }

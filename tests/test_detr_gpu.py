@@ -103,6 +103,35 @@ def test_layer_taps_small_frame(detector, weights):
         eng.set_resize(True)
 
 
+def test_preprocess_bits_all_byte_values(detector):
+    """The space-to-depth preprocess computes fma(u, 1 / s, -m / s) instead of the reference's (u - m) / s: the bf16 result must
+    have the same bits for every byte value of every colour (a frame that holds all 3 x 256 of them), at every lane of the
+    16-lane pixel (BGR -> RGB, 2 x 2 space-to-depth, 4 zero lanes)."""
+    import torch
+
+    eng = detector.model
+    eng.set_debug(True)
+    eng.set_resize(False)
+    try:
+        h, w = 224, 320
+        ramp = (np.arange(h * w * 3, dtype=np.int64) * 7 % 256).astype(np.uint8).reshape(h, w, 3)
+        frames = np.stack([ramp, 255 - ramp])                       # BGR, every value in every colour and sub-pixel position
+        assert all(len(np.unique(frames[..., c])) == 256 for c in range(3))
+        eng.forward(torch.from_numpy(frames).cuda())
+        torch.cuda.synchronize()
+        got = eng.tap("x2").cpu().view(torch.int16).reshape(2, h // 2, w // 2, 16)
+        mean = torch.tensor([0.485, 0.456, 0.406], dtype=torch.float32) * 255.0
+        std = torch.tensor([0.229, 0.224, 0.225], dtype=torch.float32) * 255.0
+        rgb = torch.from_numpy(frames[..., ::-1].copy()).float()
+        ref = ((rgb - mean) / std).to(torch.bfloat16)                # the reference's expression, float32, then rounded
+        ref = ref.reshape(2, h // 2, 2, w // 2, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(2, h // 2, w // 2, 12)
+        assert torch.equal(got[..., :12], ref.view(torch.int16))
+        assert int(got[..., 12:].abs().max()) == 0
+    finally:
+        eng.set_debug(False)
+        eng.set_resize(True)
+
+
 def test_detections_800x1333(detector, weights):
     """Config-2 shape (no resize needed): all 100 queries pre-threshold + the thresholded person set."""
     import torch
