@@ -22,8 +22,10 @@ allL = list(L.values())
 # the step is periodic in the launch list: P library launches + torch's fill kernels (hist.zero_, output buffers).  The period
 # is the smallest shift >= P under which the captured names repeat; any window of that length is one whole step (rotated).
 names = [x["name"] for x in allL]
-Pn = next(k for k in range(P, len(names)) if all(names[i] == names[i + k] for i in range(len(names) - k)))
-step = allL[:Pn]
+# (a plan's first call launches its frame-independent prologue once: the periodic part may start a few launches in)
+s0, Pn = next((s, k) for s in range(0, 64) for k in range(P, len(names) - s)
+              if all(names[i] == names[i + k] for i in range(s, len(names) - k)))
+step = allL[s0:s0 + Pn]
 
 def short(n):
     n = re.sub(r"\(.*", "", n)
