@@ -43,7 +43,10 @@ const char* opd_last_error(void);
 int64_t opd_launch_count(void);
 /* Kernel-selection knobs for A/B measurements (plans built afterwards see the new value):
  *   "attention_tc" 1 (default): fused attention on tcgen05 / TMEM; 0: the mma.sync flash kernel
- *   "attention_kv" 64 (default) or 128: keys per tile of the tcgen05 attention kernel (4 or 2 CTAs per SM)
+ *   "attention_kv" 96 (default), 64 or 128: keys per tile of the tcgen05 attention kernel (4, 4 or 2 CTAs per SM); 65: 64 keys with
+ *                  the score tile held in registers
+ *   "gemm_res_wide" 1 (default): bias + residual + ReLU GEMMs with K >= 256 use 256-column cta_group::2 tiles; 0: 128-column tiles
+ *   "pdl"         1 (default): GEMM / attention launches allow programmatic dependent launch; 0: plain stream order
  *   "bneck_halo"  1 (default): 64-channel stride-1 bottleneck tails load one halo patch per tile; 0: im2col TMA.
  *   "bneck_pair"  1 (default): 128-channel bottleneck tails run as cta_group::2 pairs; 0: one CTA per tile; 3: tests
  *   "bneck_release" 3 (default): the fused tails hand a residual slot back early in the next epilogue step (bit 0 im2col, bit 1 halo kernel)
