@@ -47,6 +47,7 @@ int64_t opd_launch_count(void);
  *                  the score tile held in registers
  *   "gemm_res_wide" 1 (default): bias + residual + ReLU GEMMs with K >= 256 use 256-column cta_group::2 tiles; 0: 128-column tiles
  *   "pdl"         1 (default): GEMM / attention launches allow programmatic dependent launch; 0: plain stream order
+ *   "mlp_fused"   1 (default): the feed-forward blocks run as one kernel (opd_mlp_ln_bf16); 0: two GEMM launches
  *   "bneck_halo"  1 (default): 64-channel stride-1 bottleneck tails load one halo patch per tile; 0: im2col TMA.
  *   "bneck_pair"  1 (default): 128-channel bottleneck tails run as cta_group::2 pairs; 0: one CTA per tile; 3: tests
  *   "bneck_release" 3 (default): the fused tails hand a residual slot back early in the next epilogue step (bit 0 im2col, bit 1 halo kernel)
@@ -155,6 +156,14 @@ int opd_conv2d_nhwc_bf16(const void* x_dev, int32_t B, int32_t H, int32_t W, int
 int opd_bottleneck_tail_bf16(const void* x_dev, int32_t B, int32_t H, int32_t W, int32_t mid, const void* w2_dev,
                              const float* bias2_dev, int32_t stride, const void* w3_dev, const float* bias3_dev,
                              int32_t width, const void* residual_dev, void* y_dev, void* stream);
+/* Fused feed-forward block of a DETR encoder / decoder layer (modeling_detr.py:560-640, 643-760: mlp.fc1 -> ReLU -> mlp.fc2 ->
+ * residual -> final_layer_norm) in one kernel; the [M, 2048] hidden activations never reach memory:
+ *   d  = LayerNorm(relu(x w1^T + b1) w2^T + b2 + x) * gamma + beta,   d2 (optional) = bf16(d + pos[row % pos_rows])
+ * x, d, d2 [M, 256] bf16 contiguous; w1 [2048, 256], w2 [256, 2048] bf16; b1 [2048], b2 / gamma / beta [256], pos [pos_rows, 256] f32.
+ * Bit-identical to opd_gemm_bf16(epilogue 1) followed by opd_gemm_bf16(epilogue 3). */
+int opd_mlp_ln_bf16(const void* x_dev, const void* w1_dev, const float* b1_dev, const void* w2_dev, const float* b2_dev,
+                    const float* gamma_dev, const float* beta_dev, void* d_dev, void* d2_dev, const float* pos_dev,
+                    int32_t pos_rows, int32_t M, void* stream);
 /* o = softmax(q k^T / sqrt(32)) v per (batch, head); head h = columns [32h, 32h+32); row strides in elements */
 int opd_attention_bf16(const void* q_dev, int64_t ldq, const void* k_dev, int64_t ldk, const void* v_dev,
                        int64_t ldv, void* o_dev, int64_t ldo, int32_t B, int32_t heads, int32_t Lq, int32_t Lk,

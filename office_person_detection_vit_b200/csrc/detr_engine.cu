@@ -860,6 +860,21 @@ int build_plan(opd_detr* m, const std::vector<FrameGroup>& groups, void* ws, Pla
     add_gemm(gp);
     return OPD_OK;
   };
+  // fc1 + ReLU + fc2 + residual + LayerNorm (+ pos) of one layer as ONE kernel (tc_mlp.cu): the [rows, 2048] hidden tensor stays on chip
+  // (one CTA streams the 2 MB of weights per 128-row tile through an 80 KB ring: faster than the two launches while every tile has its
+  // own SM - 45 against 55 us at 6 400 rows - slower at 67 200 rows, 172 against 164 us; option value 2 forces it everywhere)
+  const int mlp_opt = g_option_mlp_fused.load();
+  auto use_mlp = [&](int rows) { return mlp_opt == 2 || (mlp_opt == 1 && (rows + 127) / 128 <= sm_count()); };
+  auto mlp = [&](const bf16* xa, int rows, const LinW& fc1, const LinW& fc2, const LnW& ln, bf16* d, bf16* d2, const float* posv,
+                 int pos_rows_) -> int {
+    OPD_REQUIRE(fc1.n == kFFN && fc1.k == kD && fc2.n == kD && fc2.k == kFFN, "detr: unexpected feed-forward shape");
+    MlpPlan mp;
+    if (int rc = mlp_plan(&mp, xa, fc1.w, fc1.b, fc2.w, fc2.b, ln.g, ln.b, d, d2, posv, pos_rows_, rows)) return rc;
+    add(OPD_STEP_GEMM, cur_name, 4.0 * rows * kD * kFFN, 2.0 * rows * kD * (d2 ? 3 : 2) + 4.0 * kD * kFFN,
+        [mp](cudaStream_t s) { return mlp_launch(mp, s); });
+    prev_reversed = false;   // ascending row blocks
+    return OPD_OK;
+  };
   int attn_rc = OPD_OK;
   if (mixed) {
     OPD_REQUIRE(g_option_attention_tc.load(), "detr: mixed-size batches need the tcgen05 attention kernel (key-padding mask)");
@@ -928,11 +943,16 @@ int build_plan(opd_detr* m, const std::vector<FrameGroup>& groups, void* ws, Pla
     if (int rc = linear(eo, M, e.o, ex1, EPI_BIAS_RES_LN, xin, &e.ln1, nullptr, nullptr, 0)) return rc;
     // (Measured and dropped: running the FFN in L2-sized row chunks, so that fc2 reads the hidden tensor from L2, costs more in
     // ramp-up / drain of the eight small launches than it gains: 0.19 -> 0.22 ms per layer.)
-    cur_name = ln + ".fc1";
-    if (int rc = linear(ex1, M, e.fc1, ef, EPI_BIAS_RELU, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
     // layer output overwrites the layer input stream (its last reader, the o_proj residual, has completed)
-    cur_name = ln + ".fc2+ln";
-    if (int rc = linear(ef, M, e.fc2, xout, EPI_BIAS_RES_LN, ex1, &e.ln2, exp_, pos, pos_rows)) return rc;
+    if (use_mlp(M)) {
+      cur_name = ln + ".mlp+ln";
+      if (int rc = mlp(ex1, M, e.fc1, e.fc2, e.ln2, xout, exp_, pos, pos_rows)) return rc;
+    } else {
+      cur_name = ln + ".fc1";
+      if (int rc = linear(ex1, M, e.fc1, ef, EPI_BIAS_RELU, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+      cur_name = ln + ".fc2+ln";
+      if (int rc = linear(ef, M, e.fc2, xout, EPI_BIAS_RES_LN, ex1, &e.ln2, exp_, pos, pos_rows)) return rc;
+    }
     taps["enc" + std::to_string(i)] = {xout, M, kD, 0};
     xin = xout;
   }
@@ -993,8 +1013,12 @@ int build_plan(opd_detr* m, const std::vector<FrameGroup>& groups, void* ws, Pla
     attn(q, kD, memk + i * kD, kDec * kD, memv + i * kD, kDec * kD, dob, kQueries, S);
     if (int rc = linear(dob, Mq, d.co, dy2, EPI_BIAS_RES_LN, y1, &d.ln2, nullptr, nullptr, 0)) return rc;
     // FFN
-    if (int rc = linear(dy2, Mq, d.fc1, df, EPI_BIAS_RELU, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
-    if (int rc = linear(df, Mq, d.fc2, yout, EPI_BIAS_RES_LN, dy2, &d.ln3, dyp, m->qpos, kQueries)) return rc;
+    if (use_mlp(Mq)) {
+      if (int rc = mlp(dy2, Mq, d.fc1, d.fc2, d.ln3, yout, dyp, m->qpos, kQueries)) return rc;
+    } else {
+      if (int rc = linear(dy2, Mq, d.fc1, df, EPI_BIAS_RELU, nullptr, nullptr, nullptr, nullptr, 0)) return rc;
+      if (int rc = linear(df, Mq, d.fc2, yout, EPI_BIAS_RES_LN, dy2, &d.ln3, dyp, m->qpos, kQueries)) return rc;
+    }
     taps["dec" + std::to_string(i)] = {yout, Mq, kD, 0};
     yin = yout;
   }

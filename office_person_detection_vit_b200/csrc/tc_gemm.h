@@ -96,6 +96,25 @@ int attn_plan(AttnPlan* plan, const __nv_bfloat16* q, int64_t ldq, const __nv_bf
               int64_t ldv, __nv_bfloat16* o, int64_t ldo, int B, int heads, int Lq, int Lk);
 int attn_launch(const AttnPlan& plan, cudaStream_t stream);
 
+// Fused feed-forward block (tc_mlp.cu): y = LayerNorm(relu(x W1^T + b1) W2^T + b2 + x) * gamma + beta, y2 = bf16(y + pos[row % pos_rows]);
+// x, y, y2 [M, 256] bf16 (contiguous rows), W1 [2048, 256], W2 [256, 2048].  Bit-identical to the two GEMM launches it replaces.
+struct MlpPlan {
+  CUtensorMap tmX, tmW1, tmW2, tmD, tmD2;
+  int M;
+  const float* b1;
+  const float* b2;
+  const float* gamma;
+  const float* beta;
+  const float* pos;
+  int pos_rows;
+  int pos_row0 = 0;
+  int has_d2;
+  int grid;
+};
+int mlp_plan(MlpPlan* plan, const __nv_bfloat16* x, const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2, const float* b2,
+             const float* gamma, const float* beta, __nv_bfloat16* d, __nv_bfloat16* d2, const float* pos, int pos_rows, int M);
+int mlp_launch(const MlpPlan& plan, cudaStream_t stream);
+
 // Stem (stem_conv.cu): 4x4-tap convolution over the space-to-depth tensor S[B,H2,W2,16] -> y[B,H2,W2,64], bias + ReLU.
 struct StemPlan {
   CUtensorMap tmS, tmW, tmD;

@@ -19,7 +19,22 @@ _lib.register("opd_attention_bf16", C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, 
 _lib.register("opd_bottleneck_tail_bf16", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P,
                                                    C.c_int32, _P, _P, _P])
 
+_lib.register("opd_mlp_ln_bf16", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P])
+
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RES_RELU, EPI_BIAS_RES_LN = 0, 1, 2, 3
+
+
+def mlp_ln(x, w1, b1, w2, b2, gamma, beta, pos=None):
+    """LayerNorm(relu(x w1^T + b1) w2^T + b2 + x) * gamma + beta in one kernel (and D2 = D + pos[row % len(pos)] if pos is given)."""
+    torch = _lib.require_cuda()
+    M = x.shape[0]
+    d = torch.empty_like(x)
+    d2 = torch.empty_like(x) if pos is not None else None
+    rc = _lib.lib().opd_mlp_ln_bf16(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(gamma), _lib.ptr(beta),
+                                    _lib.ptr(d), _lib.ptr(d2), _lib.ptr(pos), pos.shape[0] if pos is not None else 0, M,
+                                    _lib.stream_ptr())
+    _lib.check(rc, "opd_mlp_ln_bf16")
+    return (d, d2) if pos is not None else d
 
 
 def gemm(a, w, bias=None, epilogue=EPI_BIAS, residual=None, gamma=None, beta=None, pos=None):

@@ -232,6 +232,32 @@ def test_conv_nhwc(T, B, H, W, C, N, k, stride, epi):
     _close(torch, y, ref, f"conv {B}x{H}x{W}x{C}->{N} k{k} s{stride}")
 
 
+@pytest.mark.parametrize("M,with_pos", [(100, True), (128 * 5, False), (1050 * 3 + 17, True), (128 * 149 + 1, True)])
+def test_fused_mlp_is_bit_identical_to_two_gemms(T, M, with_pos):
+    """tc_mlp.cu (fc1 + ReLU + fc2 + residual + LayerNorm (+ pos) in one kernel, the hidden activations stay on chip) against the
+    two GEMM launches it replaces: same accumulation order, same epilogue operations -> the same bits; one tile, ragged last tile,
+    more tiles than SMs (CTAs with two tiles)."""
+    from office_person_detection_vit_b200.detection import ops
+
+    torch = T
+    x = _rand(torch, M, 256, seed=61)
+    w1, w2 = _rand(torch, 2048, 256, seed=62, scale=256 ** -0.5), _rand(torch, 256, 2048, seed=63, scale=2048 ** -0.5)
+    b1, b2 = torch.randn(2048, device="cuda") * 0.1, torch.randn(256, device="cuda") * 0.1
+    gamma, beta = torch.rand(256, device="cuda") + 0.5, torch.randn(256, device="cuda") * 0.1
+    pos = torch.randn(50, 256, device="cuda") if with_pos else None
+    h = ops.gemm(x, w1, b1, epilogue=1)
+    ref = ops.gemm(h, w2, b2, epilogue=3, residual=x, gamma=gamma, beta=beta, pos=pos)
+    got = ops.mlp_ln(x, w1, b1, w2, b2, gamma, beta, pos=pos)
+    torch.cuda.synchronize()
+    ref, got = (ref, got) if with_pos else ((ref,), (got,))
+    for r, g in zip(ref, got):
+        assert torch.equal(g.view(torch.int16), r.view(torch.int16)), float((g.float() - r.float()).abs().max())
+    # and against plain float32 arithmetic
+    hf = (x.float() @ w1.float().T + b1).relu().to(torch.bfloat16).float()
+    yf = torch.nn.functional.layer_norm(hf @ w2.float().T + b2 + x.float(), (256,), gamma, beta, 1e-5)
+    _close(torch, got[0], yf, f"fused mlp M={M}")
+
+
 @pytest.mark.parametrize("B,Lq,Lk", [(2, 100, 100), (2, 100, 1050), (1, 1050, 1050), (3, 1008, 1008), (1, 7, 65), (2, 128, 256)])
 @pytest.mark.parametrize("tc", [4, 1, 2, 3, 0])
 def test_attention(T, B, Lq, Lk, tc):
