@@ -10,6 +10,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch  # noqa: E402
 
+from office_person_detection_vit_b200 import _lib  # noqa: E402
 from office_person_detection_vit_b200.detection import ops  # noqa: E402
 
 
@@ -42,11 +43,15 @@ def main():
             return ops.gemm(h, w2, b2, epilogue=3, residual=x, gamma=gamma, beta=beta, pos=pos)
 
         t2 = timed(two, args.iters)
-        t1 = timed(lambda: ops.mlp_ln(x, w1, b1, w2, b2, gamma, beta, pos=pos), args.iters)
-        a, b = two(), ops.mlp_ln(x, w1, b1, w2, b2, gamma, beta, pos=pos)
-        print(json.dumps({"shape": name, "M": M, "two_gemms_us": round(t2, 1), "fused_us": round(t1, 1),
-                          "fused_tflops": round(4 * M * 256 * 2048 / t1 / 1e6, 1),
-                          "bit_identical": bool(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]))}), flush=True)
+        a = two()
+        for pair in (1, 0):
+            _lib.check(_lib.lib().opd_set_option(b"mlp_pair", pair), "mlp_pair")
+            t1 = timed(lambda: ops.mlp_ln(x, w1, b1, w2, b2, gamma, beta, pos=pos), args.iters)
+            b = ops.mlp_ln(x, w1, b1, w2, b2, gamma, beta, pos=pos)
+            print(json.dumps({"shape": name, "M": M, "two_gemms_us": round(t2, 1), "fused_us": round(t1, 1), "pair": pair,
+                              "fused_tflops": round(4 * M * 256 * 2048 / t1 / 1e6, 1),
+                              "bit_identical": bool(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]))}), flush=True)
+        _lib.lib().opd_set_option(b"mlp_pair", 1)
 
 
 if __name__ == "__main__":

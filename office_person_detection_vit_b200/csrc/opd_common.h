@@ -31,6 +31,7 @@ extern std::atomic<int> g_option_gemm_reverse;   // see opd_set_option
 extern std::atomic<int> g_option_gemm_pair;    // cta_group::2 GEMM variant (see opd_set_option)
 extern std::atomic<int> g_option_gemm_res_wide;   // see opd_set_option
 extern std::atomic<int> g_option_mlp_fused;   // see opd_set_option
+extern std::atomic<int> g_option_mlp_pair;    // see opd_set_option
 extern std::atomic<int> g_option_gemm_bres;    // 1 (default): short-K bottleneck outputs use the weight-stationary GEMM variant
 extern std::atomic<int> g_option_stem_pool;    // 1 (default): max pooling fused into the stem kernel's epilogue
 extern std::atomic<int> g_option_bneck_halo;   // 1 (default): stride-1 / 64-channel bottleneck tails use the halo-patch kernel

@@ -24,6 +24,7 @@ std::atomic<int> g_option_bneck_release{3};
 std::atomic<int> g_option_gemm_mpairs{0};
 std::atomic<int> g_option_gemm_res_wide{1};
 std::atomic<int> g_option_mlp_fused{1};
+std::atomic<int> g_option_mlp_pair{1};
 }  // namespace opd
 
 extern "C" {
@@ -87,8 +88,12 @@ int opd_set_option(const char* name, int32_t value) {
     opd::g_option_gemm_res_wide.store(value);
     return OPD_OK;
   }
-  if (name && std::string(name) == "mlp_fused") {   // 1 (default): fc1 + ReLU + fc2 + residual + LayerNorm of a layer in one kernel (tc_mlp.cu) when every 128-row tile gets its own SM; 2: always; 0: two GEMM launches; new plans only
+  if (name && std::string(name) == "mlp_fused") {   // 1 (default): fc1 + ReLU + fc2 + residual + LayerNorm of every encoder / decoder layer in one kernel (tc_mlp.cu); 0: two GEMM launches; new plans only
     opd::g_option_mlp_fused.store(value);
+    return OPD_OK;
+  }
+  if (name && std::string(name) == "mlp_pair") {   // 1 (default): the fused feed-forward kernel runs as cta_group::2 pairs; 0: one CTA per row tile; new plans only
+    opd::g_option_mlp_pair.store(value);
     return OPD_OK;
   }
   if (name && std::string(name) == "stem_pool") {   // 0: stem and max pooling as two kernels; 1: fused (default); 2: fused in debug plans too

@@ -109,6 +109,7 @@ struct MlpPlan {
   int pos_rows;
   int pos_row0 = 0;
   int has_d2;
+  int pair;            // 1: cta_group::2 variant (two row tiles = one 256-row MMA, half of every weight tile per SM)
   int grid;
 };
 int mlp_plan(MlpPlan* plan, const __nv_bfloat16* x, const __nv_bfloat16* w1, const float* b1, const __nv_bfloat16* w2, const float* b2,

@@ -6,18 +6,23 @@
 // (275 MB per encoder layer at batch 64) are neither written nor read back.  As two GEMM launches, fc1 ran at the WRITE roofline of
 // HBM (3.9 TB/s) and fc2 re-read what it had written: 79 + 98 us per encoder layer, 19 + 36 us per decoder layer.
 //
-// Per 128-row tile (persistent CTAs, static schedule), for the eight 256-wide chunks c of the hidden layer:
-//   G1(c): acc1[128 x 256] = X[128 x 256] * W1[c]^T           X resident in shared memory (also the LayerNorm residual)
-//   E1(c): H = bf16(relu(acc1 + b1[c]))  -> shared memory      four K-chunks [128 x 64]; G2 starts on a chunk as soon as it is written
-//   G2(c): acc2[128 x 256] += H * W2[:, c]^T
-//   E2   : LayerNorm(acc2 + b2 + X) -> y (staged over H), y + pos -> y2 (staged over X), TMA stores
+// Per 128-row tile (persistent CTAs, static schedule), for the sixteen 128-wide chunks c of the hidden layer:
+//   G1(c): acc1[c & 1][128 x 128] = X[128 x 256] * W1[c]^T    X resident in shared memory (also the LayerNorm residual)
+//   E1(c): H[c & 1] = bf16(relu(acc1 + b1[c])) -> shared memory   two K-chunks [128 x 64], one per epilogue warpgroup
+//   G2(c): acc2[128 x 256] += H[c & 1] * W2[:, c]^T
+//   E2   : LayerNorm(acc2 + b2 + X) -> y, y + pos -> y2 (both staged over H), TMA stores; X is released after the residual pass, so
+//          the next tile's X load and first GEMMs overlap the rest of E2
+// acc1 and H are double-buffered and the MMA thread issues G1(c + 2) right after G2(c): the tensor pipe works on G2(c) / G1(c + 2)
+// while the epilogue warps convert chunk c + 1 (with 256-wide chunks and single buffers the pipe idled through every E1: 86 k
+// cycles per tile against 33 k of MMA work).
 // Weight tiles [128 rows x 64 k] stream through one ring in the order the MMA thread consumes them (W1[0]; W2[0], W1[1]; ...).
 // Every output element is accumulated in the order of the two-launch path (k ascending, fp32 in TMEM) and both epilogues apply
 // the same operations in the same order, so the results are bit-identical to gemm(EPI_BIAS_RELU) + gemm(EPI_BIAS_RES_LN)
 // (tests/test_tc_ops_gpu.py).
-// Warps: 0-7 epilogue (two warpgroups: warpgroup g owns the K-chunks / column chunks g and g + 2 of every step), 8 TMA producer,
-// 9 MMA issuer + TMEM owner.  TMEM: acc1 = columns [0, 256), acc2 = [256, 512).
+// Warps: 0-7 epilogue (two warpgroups: warpgroup g owns K-chunk g of H and the column chunks g and g + 2 of the output), 8 TMA
+// producer, 9 MMA issuer + TMEM owner.  TMEM: acc1 buffers = columns [0, 128) and [128, 256), acc2 = [256, 512).
 #include <algorithm>
+#include <cstdio>
 
 #include "opd_common.h"
 #include "sm100_ptx.cuh"
@@ -26,16 +31,23 @@
 namespace opd {
 namespace {
 
-constexpr int BLOCK_M = 128, kDm = 256, kHidden = 2048, kChunk = 256, kNC = kHidden / kChunk;
+constexpr int BLOCK_M = 128, kDm = 256, kHidden = 2048, kChunk = 128, kNC = kHidden / kChunk;
 constexpr int BLOCK_K = 64, UMMA_K = 16;
 constexpr int CHUNK_BYTES = BLOCK_M * 64 * 2;        // [128 x 64] bf16, 128-byte swizzle
-constexpr int B_STAGE_BYTES = 128 * 64 * 2;          // half a weight tile: 128 output rows x 64 k
+constexpr int B_STAGE_BYTES = 128 * 64 * 2;          // ring slot: up to 128 weight rows x 64 k
 constexpr int kStages = 5;
 constexpr int kThreads = 320;
 constexpr int kSmemBytes = 8 * CHUNK_BYTES + kStages * B_STAGE_BYTES + (kHidden + 3 * kDm) * 4 + 4096 + 256;
 
+#ifdef OPD_MLP_PROBE
+constexpr bool kMlpProbe = true;    // clock64 counters of the MMA thread's waits, printed by CTA 0
+#else
+constexpr bool kMlpProbe = false;
+#endif
+__device__ __forceinline__ long long mclk() { return kMlpProbe ? clock64() : 0; }
+
 struct MlpParams {
-  CUtensorMap tmX, tmW1, tmW2, tmD, tmD2;
+  CUtensorMap tmX, tmW1, tmW2, tmD, tmD2;   // tmW1: box of 128 rows (kPair: 64 = this CTA's half of a 128-unit hidden chunk)
   int M, num_tiles;
   const float* b1;
   const float* b2;
@@ -45,11 +57,20 @@ struct MlpParams {
   int pos_rows, pos_row0, has_d2;
 };
 
+// kPair (cta_group::2, clusters of two CTAs): the two CTAs work on two consecutive row tiles as ONE 256-row MMA.  Each CTA keeps
+// its own X / H tiles and loads HALF of every weight tile, so a ring slot feeds twice the MMA cycles and the L2 -> SM weight
+// traffic halves.  The leader's MMA thread issues both GEMMs for both CTAs; its commits are multicast to both CTAs' barriers; both
+// CTAs' TMA loads signal the leader's full barriers and both CTAs' epilogue warps arrive on the leader's accumulator / H barriers
+// (same protocol as tc_gemm.cu / tc_bottleneck.cu).
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const __grid_constant__ MlpParams p) {
-  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(BLOCK_M, 128);
+  constexpr uint32_t kIdesc1 = kPair ? ptx::umma_idesc_bf16(2 * BLOCK_M, kChunk) : ptx::umma_idesc_bf16(BLOCK_M, kChunk);
+  constexpr uint32_t kIdesc2 = kPair ? ptx::umma_idesc_bf16(2 * BLOCK_M, 256) : ptx::umma_idesc_bf16(BLOCK_M, 128);
+  constexpr int kEpiWarps = kPair ? 16 : 8;      // arrivals on the MMA thread's barriers: one per epilogue warp (of both CTAs)
+  constexpr uint32_t kW1Bytes = (kPair ? 64 : 128) * BLOCK_K * 2;   // one k-block of a hidden chunk's W1 rows (this CTA's share)
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* smem_a1 = smem;                              // X tile: 4 K-chunks; E2: residual, then y2 staging
-  uint8_t* smem_a2 = smem_a1 + 4 * CHUNK_BYTES;         // H chunk: 4 K-chunks; E2: y staging
+  uint8_t* smem_a1 = smem;                              // X tile: 4 K-chunks; E2: the LayerNorm residual
+  uint8_t* smem_a2 = smem_a1 + 4 * CHUNK_BYTES;         // H: 2 buffers x 2 K-chunks; E2: y / y2 staging (4 boxes)
   uint8_t* smem_b = smem_a2 + 4 * CHUNK_BYTES;          // weight ring
   float* s_b1 = reinterpret_cast<float*>(smem_b + kStages * B_STAGE_BYTES);   // [2048]
   float* s_b2 = s_b1 + kHidden;                                               // [256]
@@ -60,14 +81,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const __grid_consta
   uint64_t* full_bar = bars;            // [kStages]
   uint64_t* empty_bar = bars + 5;       // [kStages]
   uint64_t* a1_full = bars + 10;
-  uint64_t* a1_free = bars + 11;        // both warpgroups' stores out of the X / H buffers have been read
-  uint64_t* acc1_full = bars + 12;
-  uint64_t* acc1_empty = bars + 13;     // 8 warps
-  uint64_t* a2_ready = bars + 14;       // [4] K-chunk of H written (4 warps each)
-  uint64_t* a2_free = bars + 18;        // G2 has read H
-  uint64_t* acc2_full = bars + 19;
-  uint64_t* acc2_empty = bars + 20;     // 8 warps
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* a1_free = bars + 11;        // the epilogue warps have read the residual out of X
+  uint64_t* acc1_full = bars + 12;      // [2]
+  uint64_t* acc1_empty = bars + 14;     // [2] all epilogue warps have read the buffer
+  uint64_t* a2_ready = bars + 16;       // [2 buffers][2 K-chunks] written (one warpgroup each)
+  uint64_t* a2_free = bars + 20;        // [2] G2 has read the H buffer
+  uint64_t* acc2_full = bars + 22;
+  uint64_t* acc2_empty = bars + 23;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -81,109 +102,190 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const __grid_consta
       ptx::mbar_init(&empty_bar[i], 1);
     }
     ptx::mbar_init(a1_full, 1);
-    ptx::mbar_init(a1_free, 2);
-    ptx::mbar_init(acc1_full, 1);
-    ptx::mbar_init(acc1_empty, 8);
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(&a2_ready[i], 4);
-    ptx::mbar_init(a2_free, 1);
+    ptx::mbar_init(a1_free, 8);     // this CTA's eight epilogue warps, after the residual pass
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc1_full[i], 1);
+      ptx::mbar_init(&acc1_empty[i], kEpiWarps);
+      ptx::mbar_init(&a2_free[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&a2_ready[i], kEpiWarps / 2);
     ptx::mbar_init(acc2_full, 1);
-    ptx::mbar_init(acc2_empty, 8);
+    ptx::mbar_init(acc2_empty, kEpiWarps);
     ptx::fence_barrier_init();
   }
-  if (warp == 9) ptx::tmem_alloc<512>(tmem_ptr);
+  if (warp == 9) {
+    if (kPair) ptx::tmem_alloc_2sm<512>(tmem_ptr);
+    else ptx::tmem_alloc<512>(tmem_ptr);
+  }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (kPair) ptx::cluster_sync();   // the peer's barriers are initialised before anything signals them
   ptx::grid_dependency_wait();      // programmatic dependent launch: everything above overlaps the previous kernel's tail
   ptx::grid_launch_dependents();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + 256;
-  const int n_my = (int)blockIdx.x < p.num_tiles ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t tmem_acc2 = tmem_base + 256;   // acc1 buffers: columns [0, 128) and [128, 256)
+  // work units: row tiles, or (kPair) pairs of consecutive row tiles, dealt round-robin to the CTAs / clusters
+  const int cta_rank = kPair ? (int)ptx::cluster_ctarank() : 0;
+  const int n_units = kPair ? (p.num_tiles + 1) / 2 : p.num_tiles;
+  const int my_id = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x, n_ids = kPair ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int n_my = my_id < n_units ? (n_units - my_id + n_ids - 1) / n_ids : 0;
+  // odd tail: rank 1 repeats the last tile (identical stores)
+  auto tile_m0 = [&](int it) { return (kPair ? min(2 * (my_id + it * n_ids) + cta_rank, p.num_tiles - 1) : my_id + it * n_ids) * BLOCK_M; };
 
   if (warp == 8) {
     // ===================================== TMA producer =====================================
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      auto ring_load = [&](const CUtensorMap* tm, int c0, int c1) {
+      // kPair: both CTAs' bytes are counted by the LEADER's barrier; each CTA waits for its own copy of the empty barrier
+      auto ring_load = [&](const CUtensorMap* tm, uint32_t bytes, int c0, int c1) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&full_bar[stage], B_STAGE_BYTES);
-        ptx::tma_load_2d(tm, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, c0, c1);
+        if (!kPair) ptx::mbar_expect_tx(&full_bar[stage], bytes);
+        else if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * bytes);
+        if (kPair) ptx::tma_load_2d_2sm(tm, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, c0, c1);
+        else ptx::tma_load_2d(tm, &full_bar[stage], smem_b + stage * B_STAGE_BYTES, c0, c1);
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       };
-      auto load_w1 = [&](int c) {   // rows = hidden units [256 c, 256 c + 256), k = model columns
-        for (int kb = 0; kb < 4; ++kb)
-          for (int nh = 0; nh < 2; ++nh) ring_load(&p.tmW1, kb * BLOCK_K, c * kChunk + nh * 128);
+      auto load_w1 = [&](int c) {   // rows = hidden units [128 c, 128 c + 128), k = model columns
+        if constexpr (kPair) {      // this CTA's 64 rows: two k-blocks (8 KB each) share a ring slot, so that every slot feeds 512 MMA cycles
+          for (int kp = 0; kp < 2; ++kp) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 4 * kW1Bytes);
+            for (int hk = 0; hk < 2; ++hk)
+              ptx::tma_load_2d_2sm(&p.tmW1, &full_bar[stage], smem_b + stage * B_STAGE_BYTES + hk * kW1Bytes, (2 * kp + hk) * BLOCK_K,
+                                   c * kChunk + cta_rank * 64);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else {
+          for (int kb = 0; kb < 4; ++kb) ring_load(&p.tmW1, kW1Bytes, kb * BLOCK_K, c * kChunk);
+        }
       };
-      auto load_w2 = [&](int c) {   // rows = the 256 outputs, k = hidden units [256 c, 256 c + 256)
-        for (int kb = 0; kb < 4; ++kb)
-          for (int nh = 0; nh < 2; ++nh) ring_load(&p.tmW2, c * kChunk + kb * BLOCK_K, nh * 128);
+      auto load_w2 = [&](int c) {   // rows = the 256 outputs (two halves; kPair: this CTA's), k = hidden units [128 c, 128 c + 128)
+        for (int kb = 0; kb < 2; ++kb)
+          for (int nh = (kPair ? cta_rank : 0); nh < (kPair ? cta_rank + 1 : 2); ++nh)
+            ring_load(&p.tmW2, B_STAGE_BYTES, c * kChunk + kb * BLOCK_K, nh * 128);
       };
       for (int it = 0; it < n_my; ++it) {
-        const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BLOCK_M;
+        const int m0 = tile_m0(it);
         ptx::mbar_wait(a1_free, (it & 1) ^ 1);
-        ptx::mbar_expect_tx(a1_full, 4 * CHUNK_BYTES);
-        for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(&p.tmX, a1_full, smem_a1 + kb * CHUNK_BYTES, kb * BLOCK_K, m0);
-        load_w1(0);
+        if (!kPair) ptx::mbar_expect_tx(a1_full, 4 * CHUNK_BYTES);
+        else if (cta_rank == 0) ptx::mbar_expect_tx(a1_full, 8 * CHUNK_BYTES);
+        for (int kb = 0; kb < 4; ++kb) {
+          if (kPair) ptx::tma_load_2d_2sm(&p.tmX, a1_full, smem_a1 + kb * CHUNK_BYTES, kb * BLOCK_K, m0);
+          else ptx::tma_load_2d(&p.tmX, a1_full, smem_a1 + kb * CHUNK_BYTES, kb * BLOCK_K, m0);
+        }
+        load_w1(0);   // the order in which the MMA thread consumes them: G1(0) G1(1) | G2(c) G1(c + 2) ...
+        load_w1(1);
         for (int c = 0; c < kNC; ++c) {
           load_w2(c);
-          if (c + 1 < kNC) load_w1(c + 1);
+          if (c + 2 < kNC) load_w1(c + 2);
         }
       }
     }
   } else if (warp == 9) {
     // ===================================== MMA issuer =====================================
-    if (ptx::elect_one()) {
+    if ((!kPair || cta_rank == 0) && ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      // one k-block of a [128 x 256] x [256 x 64]^T product: two ring stages (output halves), four MMAs each
-      auto kblock = [&](uint32_t acc, const uint8_t* a_chunk, bool first) {
-        const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(a_chunk));
-        for (int nh = 0; nh < 2; ++nh) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after_sync();
-          const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
+      long long w_ring = 0, w_a2 = 0, w_acc1 = 0, w_a1 = 0, w_acc2 = 0, t_begin = mclk();
+      auto commit = [&](uint64_t* bar) {   // kPair: to both CTAs' copies of the barrier
+        if (kPair) ptx::umma_commit_2sm(bar, (uint16_t)0x3);
+        else ptx::umma_commit(bar);
+      };
+      // four MMAs (k = 0 .. 3) of one ring slot
+      auto slot_mmas = [&](uint32_t acc, uint64_t da, uint32_t idesc, bool first) {
+        const long long t0 = mclk();
+        ptx::mbar_wait(&full_bar[stage], phase);
+        w_ring += mclk() - t0;
+        ptx::tc_fence_after_sync();
+        const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            ptx::umma_bf16_ss(acc + nh * 128, da + 2 * k, db + 2 * k, kIdesc, !(first && k == 0));
-          ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          if (kPair) ptx::umma_bf16_ss_2sm(acc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+          else ptx::umma_bf16_ss(acc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+        }
+        commit(&empty_bar[stage]);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       };
-      uint32_t q = 0;   // hidden chunks issued by this CTA (G1 count)
-      auto issue_g1 = [&]() {
-        ptx::mbar_wait(acc1_empty, (q & 1) ^ 1);
+      uint32_t q1 = 0, q2 = 0;   // hidden chunks issued: first / second GEMM
+      auto issue_g1 = [&]() {    // acc1[q1 & 1] = X * W1[chunk]^T
+        const uint32_t b = q1 & 1;
+        const long long t0 = mclk();
+        ptx::mbar_wait(&acc1_empty[b], ((q1 >> 1) & 1) ^ 1);
+        w_acc1 += mclk() - t0;
         ptx::tc_fence_after_sync();
-        for (int kb = 0; kb < 4; ++kb) kblock(tmem_acc1, smem_a1 + kb * CHUNK_BYTES, kb == 0);
-        ptx::umma_commit(acc1_full);
-        ++q;
+        if constexpr (kPair) {   // two k-blocks per ring slot
+          for (int kp = 0; kp < 2; ++kp) {
+            const long long t4 = mclk();
+            ptx::mbar_wait(&full_bar[stage], phase);
+            w_ring += mclk() - t4;
+            ptx::tc_fence_after_sync();
+#pragma unroll
+            for (int hk = 0; hk < 2; ++hk) {
+              const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a1 + (2 * kp + hk) * CHUNK_BYTES));
+              const uint64_t db = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES + hk * kW1Bytes));
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                ptx::umma_bf16_ss_2sm(tmem_base + b * kChunk, da + 2 * k, db + 2 * k, kIdesc1, (kp | hk | k) != 0);
+            }
+            commit(&empty_bar[stage]);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else {
+          for (int kb = 0; kb < 4; ++kb)
+            slot_mmas(tmem_base + b * kChunk, ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a1 + kb * CHUNK_BYTES)), kIdesc1, kb == 0);
+        }
+        commit(&acc1_full[b]);
+        ++q1;
+      };
+      auto issue_g2 = [&](int c, int it) {   // acc2 += H[q2 & 1] * W2[:, chunk]^T
+        const uint32_t b = q2 & 1;
+        if (c == 0) {
+          const long long t2 = mclk();
+          ptx::mbar_wait(acc2_empty, (it & 1) ^ 1);
+          w_acc2 += mclk() - t2;
+          ptx::tc_fence_after_sync();
+        }
+        for (int kb = 0; kb < 2; ++kb) {
+          const long long t3 = mclk();
+          ptx::mbar_wait(&a2_ready[b * 2 + kb], (q2 >> 1) & 1);
+          w_a2 += mclk() - t3;
+          ptx::tc_fence_after_sync();
+          const uint64_t da = ptx::umma_desc_kmajor_sw128(ptx::smem_u32(smem_a2 + (b * 2 + kb) * CHUNK_BYTES));
+          for (int nh = 0; nh < (kPair ? 1 : 2); ++nh) slot_mmas(tmem_acc2 + nh * 128, da, kIdesc2, c == 0 && kb == 0);
+        }
+        commit(&a2_free[b]);
+        if (c + 1 == kNC) commit(acc2_full);
+        ++q2;
       };
       for (int it = 0; it < n_my; ++it) {
+        const long long t1 = mclk();
         ptx::mbar_wait(a1_full, it & 1);
+        w_a1 += mclk() - t1;
         ptx::tc_fence_after_sync();
         issue_g1();
+        issue_g1();
         for (int c = 0; c < kNC; ++c) {
-          const uint32_t qc = (uint32_t)it * kNC + c;
-          if (c == 0) {
-            ptx::mbar_wait(acc2_empty, (it & 1) ^ 1);
-            ptx::tc_fence_after_sync();
-          }
-          for (int kb = 0; kb < 4; ++kb) {
-            ptx::mbar_wait(&a2_ready[kb], qc & 1);
-            ptx::tc_fence_after_sync();
-            kblock(tmem_acc2, smem_a2 + kb * CHUNK_BYTES, c == 0 && kb == 0);
-          }
-          ptx::umma_commit(a2_free);
-          if (c + 1 == kNC) ptx::umma_commit(acc2_full);
-          else issue_g1();
+          issue_g2(c, it);
+          if (c + 2 < kNC) issue_g1();
         }
       }
+      if (kMlpProbe && blockIdx.x == 0)
+        printf("mlp CTA 0 MMA thread: %d tile(s), %lld cycles: waiting for X %lld, weight ring %lld, H chunks %lld, acc1 free %lld, acc2 free %lld\n",
+               n_my, mclk() - t_begin, w_a1, w_ring, w_a2, w_acc1, w_acc2);
     }
   } else if (warp < 8) {
     // ===================================== epilogue warps =====================================
@@ -200,46 +302,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const __grid_consta
       s_beta[i] = p.beta[i];
     }
     ptx::named_bar_sync(3, 256);
-    auto warp_arrive = [&](uint64_t* bar) {
+    auto warp_arrive = [&](uint64_t* bar) {   // the MMA thread's barriers live in the leader CTA
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar);
+      if (lane == 0) {
+        if (kPair) ptx::mbar_arrive_cluster(bar, 0);
+        else ptx::mbar_arrive(bar);
+      }
     };
     for (int it = 0; it < n_my; ++it) {
-      const int m0 = ((int)blockIdx.x + it * (int)gridDim.x) * BLOCK_M;
+      const int m0 = tile_m0(it);
       const long long m = (long long)m0 + row;
       const bool row_ok = m < p.M;
-      // ---------------- E1: eight hidden chunks ----------------
+      // ---------------- E1: sixteen hidden chunks of 128; warpgroup g converts hidden units [64 g, 64 g + 64) = K-chunk g of H ----------------
       for (int c = 0; c < kNC; ++c) {
-        const uint32_t qc = (uint32_t)it * kNC + c;
-        ptx::mbar_wait(acc1_full, qc & 1);
-        ptx::mbar_wait(a2_free, (qc & 1) ^ 1);     // G2 of the previous chunk has read H (E2's stores out of H: waited for below)
+        const uint32_t qc = (uint32_t)it * kNC + c, b = qc & 1;
+        ptx::mbar_wait(&acc1_full[b], (qc >> 1) & 1);
+        ptx::mbar_wait(&a2_free[b], ((qc >> 1) & 1) ^ 1);     // G2 of the chunk two back has read this H buffer
         ptx::tc_fence_after_sync();
-        for (int i = wg; i < 4; i += 2) {          // K-chunk i of H = hidden units [64 i, 64 i + 64) of this chunk
-          uint32_t packed[32];
+        uint32_t packed[32];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32(tmem_acc1 + lane_addr + i * 64 + h * 32, v);
-            ptx::tmem_ld_wait();
-            const float4* bias4 = reinterpret_cast<const float4*>(s_b1 + c * kChunk + i * 64 + h * 32);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + lane_addr + b * kChunk + wg * 64 + h * 32, v);
+          ptx::tmem_ld_wait();
+          const float4* bias4 = reinterpret_cast<const float4*>(s_b1 + c * kChunk + wg * 64 + h * 32);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bq = bias4[j4];
-              const uint64_t s0 = ptx::add_f32x2(ptx::f32x2(v[4 * j4], v[4 * j4 + 1]), ptx::f32x2(__float_as_uint(bq.x), __float_as_uint(bq.y)));
-              const uint64_t s1 = ptx::add_f32x2(ptx::f32x2(v[4 * j4 + 2], v[4 * j4 + 3]), ptx::f32x2(__float_as_uint(bq.z), __float_as_uint(bq.w)));
-              packed[h * 16 + 2 * j4] = ptx::relu_bf16x2(ptx::cvt_bf16x2(s0));
-              packed[h * 16 + 2 * j4 + 1] = ptx::relu_bf16x2(ptx::cvt_bf16x2(s1));
-            }
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 bq = bias4[j4];
+            const uint64_t s0 = ptx::add_f32x2(ptx::f32x2(v[4 * j4], v[4 * j4 + 1]), ptx::f32x2(__float_as_uint(bq.x), __float_as_uint(bq.y)));
+            const uint64_t s1 = ptx::add_f32x2(ptx::f32x2(v[4 * j4 + 2], v[4 * j4 + 3]), ptx::f32x2(__float_as_uint(bq.z), __float_as_uint(bq.w)));
+            packed[h * 16 + 2 * j4] = ptx::relu_bf16x2(ptx::cvt_bf16x2(s0));
+            packed[h * 16 + 2 * j4 + 1] = ptx::relu_bf16x2(ptx::cvt_bf16x2(s1));
           }
-          uint8_t* rowp = smem_a2 + i * CHUNK_BYTES + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          ptx::fence_proxy_async_smem();
-          warp_arrive(&a2_ready[i]);
         }
         ptx::tc_fence_before_sync();
-        warp_arrive(acc1_empty);
+        warp_arrive(&acc1_empty[b]);              // this warp's TMEM reads are complete: the accumulator buffer is free first
+        uint8_t* rowp = smem_a2 + (b * 2 + wg) * CHUNK_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        ptx::fence_proxy_async_smem();
+        warp_arrive(&a2_ready[b * 2 + wg]);
       }
       // ---------------- E2: bias + residual + LayerNorm (+ pos) ----------------
       ptx::mbar_wait(acc2_full, it & 1);
@@ -271,6 +374,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const __grid_consta
         }
       }
       ptx::tmem_st_wait();
+      // X has been read for the last time (the MMAs of this tile completed before acc2_full): the next tile's X may land and its
+      // first GEMMs run while the second pass and the stores below are still going on
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a1_free);
       float* st = s_stat + (it & 1) * 512;
       st[(wg * 128 + row) * 2 + 0] = sum;
       st[(wg * 128 + row) * 2 + 1] = sq;
@@ -314,9 +421,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const __grid_consta
               packed[2 * j + 1] = ptx::pack_bf16(ptx::bf16_lo(packed[2 * j + 1]) + q4.z, ptx::bf16_hi(packed[2 * j + 1]) + q4.w);
             }
           }
-          // y is staged over H chunk c (G2 of the last hidden chunk has read it: acc2_full), y2 over X chunk c (this warpgroup read
-          // its residual columns in the first pass; the barrier below orders the other rows' reads before the box is overwritten)
-          uint8_t* box = (o == 0 ? smem_a2 : smem_a1) + c * CHUNK_BYTES;
+          // both outputs are staged over this warpgroup's two H boxes (G2 of the last hidden chunk has read them: acc2_full):
+          // y in box wg, y2 in box wg + 2; the second column chunk waits until the first one's stores have read them
+          uint8_t* box = smem_a2 + (wg + 2 * o) * CHUNK_BYTES;
+          if (c >= 2 && o == 0 && et == 0) ptx::tma_store_wait_read<0>();
           ptx::named_bar_sync(bar_id, 128);
           uint8_t* rowp = box + row * 128;
 #pragma unroll
@@ -332,18 +440,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_kernel(const __grid_consta
       }
       ptx::tc_fence_before_sync();
       warp_arrive(acc2_empty);
-      // this warpgroup's stores out of the X / H buffers have been read: the next X tile may land, E1 may write H again
-      if (et == 0) {
-        ptx::tma_store_wait_read<0>();
-        ptx::mbar_arrive(a1_free);
-      }
+      // this warpgroup's stores out of its H boxes have been read: E1 of the next tile may write them again
+      if (et == 0) ptx::tma_store_wait_read<0>();
       ptx::named_bar_sync(bar_id, 128);
     }
     if (et == 0) ptx::tma_store_wait_all<0>();
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc<512>(tmem_base);
+  if (kPair) ptx::cluster_sync();   // no CTA leaves while its peer may still signal its barriers or read its shared memory
+  if (warp == 9) {
+    if (kPair) ptx::tmem_dealloc_2sm<512>(tmem_base);
+    else ptx::tmem_dealloc<512>(tmem_base);
+  }
 }
 
 }  // namespace
@@ -356,8 +465,11 @@ int mlp_plan(MlpPlan* plan, const __nv_bfloat16* x, const __nv_bfloat16* w1, con
   plan->M = M;
   plan->b1 = b1; plan->b2 = b2; plan->gamma = gamma; plan->beta = beta; plan->pos = pos; plan->pos_rows = pos_rows;
   plan->has_d2 = d2 != nullptr;
+  const int tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  plan->grid = std::min(tiles, sm_count());
+  plan->pair = g_option_mlp_pair.load() != 0 && tiles >= 2;   // cta_group::2 pairs (default) unless there is a single tile
   if (int rc = make_tmap_2d(&plan->tmX, x, M, kDm, kDm, BLOCK_M)) return rc;
-  if (int rc = make_tmap_2d(&plan->tmW1, w1, kHidden, kDm, kDm, 128)) return rc;
+  if (int rc = make_tmap_2d(&plan->tmW1, w1, kHidden, kDm, kDm, plan->pair ? 64 : 128)) return rc;
   if (int rc = make_tmap_2d(&plan->tmW2, w2, kDm, kHidden, kHidden, 128)) return rc;
   if (int rc = make_tmap_2d(&plan->tmD, d, M, kDm, kDm, BLOCK_M)) return rc;
   if (d2) {
@@ -365,7 +477,6 @@ int mlp_plan(MlpPlan* plan, const __nv_bfloat16* x, const __nv_bfloat16* w1, con
   } else {
     plan->tmD2 = plan->tmD;
   }
-  plan->grid = std::min((M + BLOCK_M - 1) / BLOCK_M, sm_count());
   return OPD_OK;
 }
 
@@ -376,23 +487,49 @@ int mlp_launch(const MlpPlan& plan, cudaStream_t stream) {
   p.num_tiles = (plan.M + BLOCK_M - 1) / BLOCK_M;
   p.b1 = plan.b1; p.b2 = plan.b2; p.gamma = plan.gamma; p.beta = plan.beta; p.pos = plan.pos;
   p.pos_rows = plan.pos_rows > 0 ? plan.pos_rows : 1; p.pos_row0 = plan.pos_row0; p.has_d2 = plan.has_d2;
-  static PerDeviceOnce configured;
-  if (int rc = once_per_device(configured, []() -> int {
-        OPD_CUDA_OK(cudaFuncSetAttribute(tc_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        return OPD_OK;
-      }))
-    return rc;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.gridDim = dim3(plan.grid);
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (plan.pair) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  if (g_option_pdl.load()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
   cfg.attrs = attr;
-  cfg.numAttrs = g_option_pdl.load() ? 1 : 0;
-  OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_mlp_kernel, p));
+  cfg.numAttrs = n_attr;
+  if (plan.pair) {
+    static PerDeviceInt cluster_limit;
+    int max_clusters = -1;
+    if (int rc = cached_per_device(cluster_limit, &max_clusters, [&](int* n) -> int {
+          OPD_CUDA_OK(cudaFuncSetAttribute(tc_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+          cfg.gridDim = dim3(sm_count() / 2 * 2);
+          OPD_CUDA_OK(cudaOccupancyMaxActiveClusters(n, tc_mlp_kernel<true>, &cfg));
+          return OPD_OK;
+        }))
+      return rc;
+    OPD_REQUIRE(max_clusters > 0, "mlp: no 2-CTA cluster of the kernel fits on this device");
+    cfg.gridDim = dim3(2 * std::min((p.num_tiles + 1) / 2, max_clusters));
+    OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_mlp_kernel<true>, p));
+  } else {
+    static PerDeviceOnce configured;
+    if (int rc = once_per_device(configured, []() -> int {
+          OPD_CUDA_OK(cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+          return OPD_OK;
+        }))
+      return rc;
+    cfg.gridDim = dim3(plan.grid);
+    OPD_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_mlp_kernel<false>, p));
+  }
   count_launch();
   OPD_CUDA_OK(cudaGetLastError());
   return OPD_OK;

@@ -232,11 +232,13 @@ def test_conv_nhwc(T, B, H, W, C, N, k, stride, epi):
     _close(torch, y, ref, f"conv {B}x{H}x{W}x{C}->{N} k{k} s{stride}")
 
 
-@pytest.mark.parametrize("M,with_pos", [(100, True), (128 * 5, False), (1050 * 3 + 17, True), (128 * 149 + 1, True)])
-def test_fused_mlp_is_bit_identical_to_two_gemms(T, M, with_pos):
+@pytest.mark.parametrize("pair", [1, 0])
+@pytest.mark.parametrize("M,with_pos", [(100, True), (128 * 5, False), (1050 * 3 + 17, True), (128 * 149 + 1, True), (128 * 300, True)])
+def test_fused_mlp_is_bit_identical_to_two_gemms(T, M, with_pos, pair):
     """tc_mlp.cu (fc1 + ReLU + fc2 + residual + LayerNorm (+ pos) in one kernel, the hidden activations stay on chip) against the
     two GEMM launches it replaces: same accumulation order, same epilogue operations -> the same bits; one tile, ragged last tile,
-    more tiles than SMs (CTAs with two tiles)."""
+    more tiles than SMs (CTAs with two tiles); as cta_group::2 pairs (odd tile counts: the last pair repeats a tile) and as single CTAs."""
+    from office_person_detection_vit_b200 import _lib
     from office_person_detection_vit_b200.detection import ops
 
     torch = T
@@ -247,8 +249,12 @@ def test_fused_mlp_is_bit_identical_to_two_gemms(T, M, with_pos):
     pos = torch.randn(50, 256, device="cuda") if with_pos else None
     h = ops.gemm(x, w1, b1, epilogue=1)
     ref = ops.gemm(h, w2, b2, epilogue=3, residual=x, gamma=gamma, beta=beta, pos=pos)
-    got = ops.mlp_ln(x, w1, b1, w2, b2, gamma, beta, pos=pos)
-    torch.cuda.synchronize()
+    try:
+        _lib.check(_lib.lib().opd_set_option(b"mlp_pair", pair), "opd_set_option")
+        got = ops.mlp_ln(x, w1, b1, w2, b2, gamma, beta, pos=pos)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().opd_set_option(b"mlp_pair", 1)
     ref, got = (ref, got) if with_pos else ((ref,), (got,))
     for r, g in zip(ref, got):
         assert torch.equal(g.view(torch.int16), r.view(torch.int16)), float((g.float() - r.float()).abs().max())
