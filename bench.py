@@ -586,7 +586,7 @@ def main_headline(args) -> None:
             traffic_src = f"profiles/{tname}: constant from the committed ncu capture (one step at batch 64), not measured in this run"
             break
     peak = pk["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": "tcgen05 GEMM / convolution kernels: tc_gemm_kernel, tc_bneck_kernel, tc_bneck_halo_kernel, stem_kernel",
+    roofline = {"bound": "tensor", "kernel": "tcgen05 GEMM / convolution kernels: tc_gemm_kernel, tc_mlp_kernel, tc_bneck_kernel, tc_bneck_halo_kernel, stem_kernel",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per step over the family's launches (algorithmic: "
                                                     f"{tc['bytes']:.3e})",

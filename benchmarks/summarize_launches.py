@@ -23,7 +23,7 @@ allL = list(L.values())
 # is the smallest shift >= P under which the captured names repeat; any window of that length is one whole step (rotated).
 names = [x["name"] for x in allL]
 # (a plan's first call launches its frame-independent prologue once: the periodic part may start a few launches in)
-s0, Pn = next((s, k) for s in range(0, 64) for k in range(P, len(names) - s)
+s0, Pn = next((s, k) for s in range(0, 64) for k in range(P, (len(names) - s) // 2 + 1)
               if all(names[i] == names[i + k] for i in range(s, len(names) - k)))
 step = allL[s0:s0 + Pn]
 
@@ -50,7 +50,7 @@ tot = sum(a[1] for a in agg.values())
 out = [f"{'kernel':64s}   n      us  share  dramR GB dramW GB  grid"]
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{k[:64]:64s} {a[0]:3d} {a[1]:8.1f} {100 * a[1] / tot:5.1f}% {a[2] / 1e9:7.2f} {a[3] / 1e9:7.2f}  {a[4]}")
-fam = [a for k, a in agg.items() if any(s in k for s in ("tc_gemm_kernel", "tc_bneck", "stem_kernel"))]
+fam = [a for k, a in agg.items() if any(s in k for s in ("tc_gemm_kernel", "tc_mlp_kernel", "tc_bneck", "stem_kernel"))]
 out.append(f"tensor-core family: {sum(a[0] for a in fam)} launches, {sum(a[1] for a in fam):.0f} us = {100 * sum(a[1] for a in fam) / tot:.1f}% "
            f"of the step under ncu, DRAM {sum(a[2] + a[3] for a in fam) / 1e9:.2f} GB")
 out.append(f"whole step: {Pn} launches ({P} of this library + {Pn - P} torch fills), {tot:.0f} us under ncu (serialised, cold caches), DRAM {sum(a[2] + a[3] for a in agg.values()) / 1e9:.2f} GB; "

@@ -863,7 +863,9 @@ int build_plan(opd_detr* m, const std::vector<FrameGroup>& groups, void* ws, Pla
   // fc1 + ReLU + fc2 + residual + LayerNorm (+ pos) of one layer as ONE kernel (tc_mlp.cu): the [rows, 2048] hidden tensor stays on chip
   // (benchmarks/mlp_microbench.py, cta_group::2 pairs: 138 against 163 us at 67 200 rows, 39 against 56 us at 6 400; option 0 = two launches)
   const int mlp_opt = g_option_mlp_fused.load();
-  auto use_mlp = [&](int) { return mlp_opt != 0; };
+  // below 16 row tiles the two launches win: they spread fc1's 2048 columns over many SMs, the fused kernel has one CTA per row tile
+  // (batch 1: 1.63 -> 1.75 ms per frame with it)
+  auto use_mlp = [&](int rows) { return mlp_opt == 2 || (mlp_opt == 1 && (rows + 127) / 128 >= 16); };
   auto mlp = [&](const bf16* xa, int rows, const LinW& fc1, const LinW& fc2, const LnW& ln, bf16* d, bf16* d2, const float* posv,
                  int pos_rows_) -> int {
     OPD_REQUIRE(fc1.n == kFFN && fc1.k == kD && fc2.n == kD && fc2.k == kFFN, "detr: unexpected feed-forward shape");

@@ -88,7 +88,7 @@ int opd_set_option(const char* name, int32_t value) {
     opd::g_option_gemm_res_wide.store(value);
     return OPD_OK;
   }
-  if (name && std::string(name) == "mlp_fused") {   // 1 (default): fc1 + ReLU + fc2 + residual + LayerNorm of every encoder / decoder layer in one kernel (tc_mlp.cu); 0: two GEMM launches; new plans only
+  if (name && std::string(name) == "mlp_fused") {   // 1 (default): fc1 + ReLU + fc2 + residual + LayerNorm of a layer in one kernel (tc_mlp.cu) when it has at least 16 row tiles; 2: always; 0: two GEMM launches; new plans only
     opd::g_option_mlp_fused.store(value);
     return OPD_OK;
   }
