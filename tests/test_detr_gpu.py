@@ -297,6 +297,32 @@ def test_fused_stem_maxpool_is_bit_identical(detector, size):
         eng.set_resize(True)
 
 
+@pytest.mark.parametrize("batch,h,w", [(1, 800, 1333), (3, 800, 1333), (5, 720, 1280), (9, 480, 640)])
+def test_fused_feed_forward_keeps_every_bit_of_the_forward(weights, built_lib, batch, h, w):
+    """The fused feed-forward kernel (tc_mlp.cu) against the two GEMM launches per layer, through the whole engine: raw logits and
+    boxes must be bit-identical with the kernel forced on for every layer (option 2: also where the engine would not pick it -
+    single tiles, odd tile counts) and switched off."""
+    import torch
+
+    from office_person_detection_vit_b200 import _lib
+    from office_person_detection_vit_b200.detection import ViTDetector
+
+    frames = torch.from_numpy(do.synthetic_frames(batch, h, w, seed=40 + batch)).cuda()
+    outs = []
+    try:
+        for opt in (0, 2):
+            _lib.check(_lib.lib().opd_set_option(b"mlp_fused", opt), "opd_set_option")
+            det = ViTDetector(confidence_threshold=0.5, state_dict=weights)
+            det.load_model()
+            l, b = det.model.forward(frames)
+            torch.cuda.synchronize()
+            outs.append((l.clone(), b.clone()))
+            del det
+    finally:
+        _lib.lib().opd_set_option(b"mlp_fused", 1)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_full_size_batch_invariance_and_determinism(detector):
     """Size-independent properties at BASELINE's frame size (800x1333, where no oracle run fits a test): a frame's raw
     outputs do not depend on its batch neighbours or its position in the batch (frames are independent through the whole
